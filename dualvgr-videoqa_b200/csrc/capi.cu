@@ -1,0 +1,151 @@
+// extern "C" entry points of libdualvgr_b200.so (declared in include/dualvgr_b200.h).
+#include <atomic>
+#include <limits.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "capi_internal.h"
+
+namespace dvgr {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+int set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return 1;
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+static void fill_lstm_params(GemmParams& p, const dvgr_lstm_args& a) {
+  p.gates = reinterpret_cast<__nv_bfloat16*>(a.gates);
+  p.gates_ld = (long long)a.ndir * 4 * a.H;
+  p.gates_dir = 4LL * a.H;
+  p.c_hist = a.c_hist;
+  p.h_hist = reinterpret_cast<__nv_bfloat16*>(a.h_hist);
+  p.h_last = reinterpret_cast<__nv_bfloat16*>(a.h_last);
+  p.h_last_ld = a.h_last_ld;
+  p.dc = a.dc;
+  p.seq_len = a.seq_len;
+  p.seq_out = reinterpret_cast<__nv_bfloat16*>(a.seq_out);
+  p.seq_out_ld = a.seq_out_ld;
+  p.T = a.T;
+  p.s = a.s;
+  p.batch = a.ndir;
+  p.k_inner = INT_MAX;
+}
+
+static int check_lstm(const dvgr_lstm_args& a) {
+  if (a.S <= 0 || a.T <= 0) return set_error("lstm: S and T must be positive");
+  if (a.H <= 0 || a.H % 64 != 0) return set_error("lstm: H=%d must be a multiple of 64", a.H);
+  if (a.ndir < 1 || a.ndir > kMaxBatch) return set_error("lstm: ndir=%d out of range", a.ndir);
+  if (a.s < 0 || a.s >= a.T) return set_error("lstm: step %d out of range [0,%d)", a.s, a.T);
+  if (!a.gates || !a.whh || !a.h_hist || !a.c_hist) return set_error("lstm: null buffer");
+  return 0;
+}
+
+}  // namespace dvgr
+
+using namespace dvgr;
+
+extern "C" {
+
+const char* dvgr_last_error(void) { return g_err; }
+int dvgr_abi_version(void) { return DVGR_ABI_VERSION; }
+long long dvgr_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int dvgr_gemm(const dvgr_gemm_args* a, void* stream) {
+  if (!a) return set_error("dvgr_gemm: null args");
+  if (!a->A.ptr || !a->B.ptr || !a->C) return set_error("dvgr_gemm: null operand");
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = a->M; p.N = a->N; p.K = a->K; p.batch = a->batch > 0 ? a->batch : 1;
+  if (p.batch > kMaxBatch) return set_error("dvgr_gemm: batch %d > %d", p.batch, kMaxBatch);
+  for (int i = 0; i < kMaxBatch; ++i) {
+    p.a_c0[i] = a->a_c0[i]; p.a_c2[i] = a->a_c2[i]; p.a_c3[i] = a->a_c3[i];
+    p.b_c0[i] = a->b_c0[i]; p.b_c2[i] = a->b_c2[i]; p.b_c3[i] = a->b_c3[i];
+    p.a_c2_step[i] = a->a_c2_step[i]; p.b_c2_step[i] = a->b_c2_step[i];
+  }
+  p.k_inner = a->k_inner > 0 ? a->k_inner : INT_MAX;
+  p.mode = EPI_LINEAR;
+  p.C = a->C; p.ldc = a->ldc; p.c_batch = a->c_batch;
+  p.out_f32 = a->out_f32; p.act = a->act; p.beta = a->beta;
+  p.bias = a->bias; p.bias_batch = a->bias_batch; p.row_map = a->row_map;
+  int rc = gemm_dispatch(a->A, a->B, p, a->bn, a->max_ctas, reinterpret_cast<cudaStream_t>(stream));
+  if (rc == 0) count_launch();
+  return rc;
+}
+
+int dvgr_gemm_reference(const void* A, long long a_rs, long long a_ks, const void* B, long long b_rs, long long b_ks,
+                        float* C, long long ldc, int M, int N, int K, void* stream) {
+  int rc = gemm_ref(A, a_rs, a_ks, B, b_rs, b_ks, C, ldc, M, N, K, reinterpret_cast<cudaStream_t>(stream));
+  if (rc == 0) count_launch();
+  return rc;
+}
+
+int dvgr_lstm_step_fwd(const dvgr_lstm_args* a, void* stream) {
+  if (!a) return set_error("dvgr_lstm_step_fwd: null args");
+  if (int rc = check_lstm(*a)) return rc;
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  fill_lstm_params(p, *a);
+  p.mode = EPI_LSTM_FWD;
+  p.M = a->S; p.N = 4 * a->H; p.K = a->H;
+  dvgr_operand A, B;
+  memset(&A, 0, sizeof(A)); memset(&B, 0, sizeof(B));
+  // A = h_hist[d][s] : dims {H, S, T+1, D}
+  A.ptr = a->h_hist; A.major = 0; A.ndim = 4;
+  A.dims[0] = a->H; A.dims[1] = a->S; A.dims[2] = a->T + 1; A.dims[3] = a->ndir;
+  A.strides[0] = 1; A.strides[1] = a->H; A.strides[2] = (long long)a->S * a->H; A.strides[3] = (long long)(a->T + 1) * a->S * a->H;
+  // B = whh[d] : dims {H, 4H, D}
+  B.ptr = a->whh; B.major = 0; B.ndim = 3;
+  B.dims[0] = a->H; B.dims[1] = 4LL * a->H; B.dims[2] = a->ndir;
+  B.strides[0] = 1; B.strides[1] = a->H; B.strides[2] = 4LL * a->H * a->H;
+  for (int d = 0; d < a->ndir; ++d) { p.a_c2[d] = a->s; p.a_c3[d] = d; p.b_c2[d] = d; }
+  int rc = gemm_dispatch(A, B, p, 128, 0, reinterpret_cast<cudaStream_t>(stream));
+  if (rc == 0) count_launch();
+  return rc;
+}
+
+int dvgr_lstm_step_bwd(const dvgr_lstm_args* a, void* stream) {
+  if (!a) return set_error("dvgr_lstm_step_bwd: null args");
+  if (int rc = check_lstm(*a)) return rc;
+  if (!a->dc) return set_error("dvgr_lstm_step_bwd: dc is null");
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  fill_lstm_params(p, *a);
+  p.mode = EPI_LSTM_BWD;
+  p.dh_ext = reinterpret_cast<const __nv_bfloat16*>(a->dh_seq);
+  p.M = a->S; p.N = a->H; p.K = 4 * a->H;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (a->s == a->T - 1) {
+    int rc = lstm_bwd_first(p, a->dh_last, a->dh_last_ld, st);
+    if (rc == 0) count_launch();
+    return rc;
+  }
+  // dh_s = dgates[s+1] * W_hh  : A = gates rows of the step processed after s, K = 4H inside the direction's column block
+  dvgr_operand A, B;
+  memset(&A, 0, sizeof(A)); memset(&B, 0, sizeof(B));
+  A.ptr = a->gates; A.major = 0; A.ndim = 3;
+  A.dims[0] = (long long)a->ndir * 4 * a->H; A.dims[1] = a->S; A.dims[2] = a->T;
+  A.strides[0] = 1; A.strides[1] = A.dims[0]; A.strides[2] = A.dims[0] * a->S;
+  // B = whh[d] as [K = 4H][N = H], N contiguous -> MN-major
+  B.ptr = a->whh; B.major = 1; B.ndim = 3;
+  B.dims[0] = a->H; B.dims[1] = 4LL * a->H; B.dims[2] = a->ndir;
+  B.strides[0] = 1; B.strides[1] = a->H; B.strides[2] = 4LL * a->H * a->H;
+  for (int d = 0; d < a->ndir; ++d) {
+    const int s1 = a->s + 1;
+    p.a_c0[d] = d * 4 * a->H;
+    p.a_c2[d] = (d == 0) ? s1 : a->T - 1 - s1;
+    p.b_c2[d] = d;
+  }
+  int rc = gemm_dispatch(A, B, p, 128, 0, st);
+  if (rc == 0) count_launch();
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,26 @@
+// Internal glue shared by the .cu translation units of libdualvgr_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "../../include/dualvgr_b200.h"
+#include "gemm.cuh"
+
+namespace dvgr {
+
+// printf-style thread-local error message; returns a non-zero status for `return set_error(...)`.
+int set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+int gemm_dispatch(const dvgr_operand& A, const dvgr_operand& B, GemmParams p, int bn, int max_ctas, cudaStream_t stream);
+int lstm_bwd_first(const GemmParams& p, const void* dh_last, long long dh_ld, cudaStream_t stream);
+int gemm_ref(const void* A, long long a_rs, long long a_ks, const void* B, long long b_rs, long long b_ks, float* C,
+             long long ldc, int M, int N, int K, cudaStream_t stream);
+
+#define DVGR_CHECK_LAUNCH(name)                                                            \
+  do {                                                                                     \
+    cudaError_t e__ = cudaGetLastError();                                                  \
+    if (e__ != cudaSuccess) return ::dvgr::set_error("%s launch failed: %s", name, cudaGetErrorString(e__)); \
+    ::dvgr::count_launch();                                                                \
+  } while (0)
+
+}  // namespace dvgr

@@ -1,0 +1,604 @@
+// tcgen05 / TMEM / TMA GEMM family for the DualVGR hot path (sm_100a only).
+//
+//   D[b][m][n] = epilogue( sum_k A[b][m][k] * B[b][n][k] )          bf16 operands, fp32 accumulation in TMEM
+//
+// One persistent CTA per SM, warp-specialised:
+//   warp 0   : TMA producer  (cp.async.bulk.tensor, SWIZZLE_128B, 4-D tensor maps)
+//   warp 1   : MMA issuer    (one thread, tcgen05.mma.cta_group::1.kind::f16, 128 x BN x 16)
+//   warp 2   : TMEM allocator
+//   warps 4-7: epilogue      (tcgen05.ld 32x32b -> registers -> fused epilogue -> global)
+// Two TMEM accumulator stages so the epilogue of tile i overlaps the main loop of tile i+1.
+//
+// Operands may be K-major (rows x K, K contiguous: activations / nn.Linear weights in the forward GEMM) or
+// MN-major (K x rows, rows contiguous: the same tensors seen by dgrad / wgrad), so no transposed copies exist.
+//
+// Epilogues (gemm.cuh: EpiMode):
+//   EPI_LINEAR    bias + {none, ELU, tanh} (+ accumulate), bf16 / fp32 output, optional output-row permutation
+//                 -> replaces every nn.Linear on the path (reference model/models.py:46, GraphNN.py:96,
+//                    Attention.py:14-18, fusions.py:420-449, AnswerDecoder.py:173-200, model/utils.py:68)
+//   EPI_LSTM_FWD  LSTM cell on the recurrent product (reference nn.LSTM, model/Preprocessing.py:227)
+//   EPI_LSTM_BWD  LSTM cell backward on dh = dgates * W_hh
+#include "gemm.cuh"
+#include "ptx.cuh"
+
+#include <limits.h>
+#include <map>
+#include <mutex>
+#include <string.h>
+#include <tuple>
+#include <vector>
+
+#include "capi_internal.h"
+
+namespace dvgr {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int kGemmThreads = 256;
+
+template <int BN> struct TileCfg {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+      "r"(c3)
+      : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------ epilogues
+__device__ __forceinline__ void epi_linear(const GemmParams& p, int b, int row, int col0, const uint32_t (&r)[32]) {
+  if (row >= p.M || col0 >= p.N) return;
+  const long long orow = p.row_map ? p.row_map[row] : row;
+  const float* bias = p.bias ? p.bias + (long long)b * p.bias_batch : nullptr;
+  float v[32];
+  const int nvalid = min(32, p.N - col0);
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    float x = __uint_as_float(r[j]);
+    if (bias != nullptr && j < nvalid) x += __ldg(bias + col0 + j);
+    if (p.act == ACT_ELU) x = eluf_(x);
+    else if (p.act == ACT_TANH) x = tanhf_(x);
+    v[j] = x;
+  }
+  if (p.out_f32) {
+    float* c = reinterpret_cast<float*>(p.C) + (long long)b * p.c_batch + orow * p.ldc + col0;
+    const bool vec = (nvalid == 32) && ((reinterpret_cast<uintptr_t>(c) & 15) == 0);
+    if (vec) {
+      float4* c4 = reinterpret_cast<float4*>(c);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        if (p.beta) {
+          float4 old = c4[j];
+          o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+        }
+        c4[j] = o;
+      }
+    } else {
+      for (int j = 0; j < nvalid; ++j) c[j] = p.beta ? c[j] + v[j] : v[j];
+    }
+  } else {
+    __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(p.C) + (long long)b * p.c_batch + orow * p.ldc + col0;
+    const bool vec = (nvalid == 32) && ((reinterpret_cast<uintptr_t>(c) & 15) == 0);
+    if (vec) {
+      uint4* c4 = reinterpret_cast<uint4*>(c);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float* s = v + 8 * j;
+        if (p.beta) {
+          uint4 old = c4[j];
+          float2 a0 = unpack_bf16x2(old.x), a1 = unpack_bf16x2(old.y), a2 = unpack_bf16x2(old.z), a3 = unpack_bf16x2(old.w);
+          s[0] += a0.x; s[1] += a0.y; s[2] += a1.x; s[3] += a1.y; s[4] += a2.x; s[5] += a2.y; s[6] += a3.x; s[7] += a3.y;
+        }
+        uint4 o;
+        o.x = pack_bf16x2(s[0], s[1]); o.y = pack_bf16x2(s[2], s[3]);
+        o.z = pack_bf16x2(s[4], s[5]); o.w = pack_bf16x2(s[6], s[7]);
+        c4[j] = o;
+      }
+    } else {
+      for (int j = 0; j < nvalid; ++j) {
+        float x = v[j];
+        if (p.beta) x += __bfloat162float(c[j]);
+        c[j] = __float2bfloat16_rn(x);
+      }
+    }
+  }
+}
+
+// LSTM cell forward on one row (sequence) and 8 hidden units (32 interleaved gate columns 4*j + {i,f,g,o}).
+__device__ __forceinline__ void epi_lstm_fwd(const GemmParams& p, int dir, int seq, int col0, const uint32_t (&r)[32]) {
+  if (seq >= p.M || col0 >= p.N) return;
+  const int H = p.N >> 2;
+  const int S = p.M;
+  const int t = dir == 0 ? p.s : p.T - 1 - p.s;
+  const int j0 = col0 >> 2;
+  __nv_bfloat16* g = p.gates + ((long long)t * p.M + seq) * p.gates_ld + (long long)dir * p.gates_dir + col0;
+  const long long st = ((long long)dir * (p.T + 1) + p.s) * S * H + (long long)seq * H + j0;   // slot s
+  const long long st1 = st + (long long)S * H;                                                // slot s+1
+  const bool live = (p.seq_len == nullptr) || (t < p.seq_len[seq]);
+
+  uint4 gin[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) gin[q] = reinterpret_cast<const uint4*>(g)[q];
+  float4 cp0 = *reinterpret_cast<const float4*>(p.c_hist + st);
+  float4 cp1 = *reinterpret_cast<const float4*>(p.c_hist + st + 4);
+  float cprev[8] = {cp0.x, cp0.y, cp0.z, cp0.w, cp1.x, cp1.y, cp1.z, cp1.w};
+  float cnew[8], hnew[8];
+  uint4 gout[4];
+  const uint32_t* gw = reinterpret_cast<const uint32_t*>(gin);
+  uint32_t* go = reinterpret_cast<uint32_t*>(gout);
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    float2 a01 = unpack_bf16x2(gw[2 * u]);
+    float2 a23 = unpack_bf16x2(gw[2 * u + 1]);
+    float ig = sigmoidf_(__uint_as_float(r[4 * u + 0]) + a01.x);
+    float fg = sigmoidf_(__uint_as_float(r[4 * u + 1]) + a01.y);
+    float gg = tanhf_(__uint_as_float(r[4 * u + 2]) + a23.x);
+    float og = sigmoidf_(__uint_as_float(r[4 * u + 3]) + a23.y);
+    float c = fg * cprev[u] + ig * gg;
+    cnew[u] = c;
+    hnew[u] = og * tanhf_(c);
+    go[2 * u] = pack_bf16x2(ig, fg);
+    go[2 * u + 1] = pack_bf16x2(gg, og);
+  }
+  if (!live) {
+    // padded step: state is carried unchanged, gates are zeroed so the backward pass sees no contribution
+    uint4 hp = *reinterpret_cast<const uint4*>(p.h_hist + st);
+    const uint32_t* hw = reinterpret_cast<const uint32_t*>(&hp);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float2 h2 = unpack_bf16x2(hw[u]);
+      hnew[2 * u] = h2.x; hnew[2 * u + 1] = h2.y;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) cnew[u] = cprev[u];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) gout[q] = make_uint4(0, 0, 0, 0);
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) reinterpret_cast<uint4*>(g)[q] = gout[q];
+  *reinterpret_cast<float4*>(p.c_hist + st1) = make_float4(cnew[0], cnew[1], cnew[2], cnew[3]);
+  *reinterpret_cast<float4*>(p.c_hist + st1 + 4) = make_float4(cnew[4], cnew[5], cnew[6], cnew[7]);
+  uint4 hv;
+  hv.x = pack_bf16x2(hnew[0], hnew[1]); hv.y = pack_bf16x2(hnew[2], hnew[3]);
+  hv.z = pack_bf16x2(hnew[4], hnew[5]); hv.w = pack_bf16x2(hnew[6], hnew[7]);
+  *reinterpret_cast<uint4*>(p.h_hist + st1) = hv;
+  if (p.h_last != nullptr && p.s == p.T - 1)
+    *reinterpret_cast<uint4*>(p.h_last + (long long)seq * p.h_last_ld + (long long)dir * H + j0) = hv;
+  if (p.seq_out != nullptr) {
+    uint4 ov = live ? hv : make_uint4(0, 0, 0, 0);
+    *reinterpret_cast<uint4*>(p.seq_out + ((long long)seq * p.T + t) * p.seq_out_ld + (long long)dir * H + j0) = ov;
+  }
+}
+
+// LSTM cell backward for 8 hidden units of one sequence at processed step p.s.
+//   dh[8]      : gradient w.r.t. h after step s (everything already summed)
+//   reads  gates (activated i,f,g,o), c_hist[s], c_hist[s+1], dc (running)
+//   writes dgates (pre-activation) in place, dc <- dc_total * f
+__device__ __forceinline__ void lstm_cell_bwd8(const GemmParams& p, int dir, int seq, int j0, const float (&dh)[8]) {
+  const int H = p.N;   // bwd GEMM has N = H
+  const int S = p.M;
+  const int t = dir == 0 ? p.s : p.T - 1 - p.s;
+  __nv_bfloat16* g = p.gates + ((long long)t * p.M + seq) * p.gates_ld + (long long)dir * p.gates_dir + 4 * j0;
+  const long long st = ((long long)dir * (p.T + 1) + p.s) * S * H + (long long)seq * H + j0;
+  const long long st1 = st + (long long)S * H;
+  float* dcp = p.dc + ((long long)dir * S + seq) * H + j0;
+  const bool live = (p.seq_len == nullptr) || (t < p.seq_len[seq]);
+  if (!live) {   // padded step: dgates = 0 (already zero from forward), dc and dh pass through (dh handled by caller)
+    return;
+  }
+  uint4 gin[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) gin[q] = reinterpret_cast<const uint4*>(g)[q];
+  float4 a0 = *reinterpret_cast<const float4*>(p.c_hist + st), a1 = *reinterpret_cast<const float4*>(p.c_hist + st + 4);
+  float4 b0 = *reinterpret_cast<const float4*>(p.c_hist + st1), b1 = *reinterpret_cast<const float4*>(p.c_hist + st1 + 4);
+  float4 d0 = *reinterpret_cast<const float4*>(dcp), d1 = *reinterpret_cast<const float4*>(dcp + 4);
+  float cprev[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+  float cc[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+  float dc[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+  uint4 gout[4];
+  const uint32_t* gw = reinterpret_cast<const uint32_t*>(gin);
+  uint32_t* go = reinterpret_cast<uint32_t*>(gout);
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    float2 i_f = unpack_bf16x2(gw[2 * u]);
+    float2 g_o = unpack_bf16x2(gw[2 * u + 1]);
+    float ig = i_f.x, fg = i_f.y, gg = g_o.x, og = g_o.y;
+    float tc = tanhf_(cc[u]);
+    float dct = dc[u] + dh[u] * og * (1.f - tc * tc);
+    float d_o = dh[u] * tc * og * (1.f - og);
+    float d_i = dct * gg * ig * (1.f - ig);
+    float d_f = dct * cprev[u] * fg * (1.f - fg);
+    float d_g = dct * ig * (1.f - gg * gg);
+    dc[u] = dct * fg;
+    go[2 * u] = pack_bf16x2(d_i, d_f);
+    go[2 * u + 1] = pack_bf16x2(d_g, d_o);
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) reinterpret_cast<uint4*>(g)[q] = gout[q];
+  *reinterpret_cast<float4*>(dcp) = make_float4(dc[0], dc[1], dc[2], dc[3]);
+  *reinterpret_cast<float4*>(dcp + 4) = make_float4(dc[4], dc[5], dc[6], dc[7]);
+}
+
+__device__ __forceinline__ void epi_lstm_bwd(const GemmParams& p, int dir, int seq, int col0, const uint32_t (&r)[32]) {
+  if (seq >= p.M || col0 >= p.N) return;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float dh[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) dh[u] = __uint_as_float(r[8 * q + u]);
+    if (p.dh_ext != nullptr) {
+      // external gradient on the per-step hidden output (question encoder): [S, T, ld] at column dir*H
+      const int t = dir == 0 ? p.s : p.T - 1 - p.s;
+      const __nv_bfloat16* e = p.dh_ext + ((long long)seq * p.T + t) * p.seq_out_ld + (long long)dir * p.N + col0 + 8 * q;
+      uint4 ev = *reinterpret_cast<const uint4*>(e);
+      const uint32_t* ew = reinterpret_cast<const uint32_t*>(&ev);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float2 e2 = unpack_bf16x2(ew[u]);
+        dh[2 * u] += e2.x; dh[2 * u + 1] += e2.y;
+      }
+    }
+    lstm_cell_bwd8(p, dir, seq, col0 + 8 * q, dh);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ kernel
+template <bool A_MN, bool B_MN, int BN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const GemmParams p) {
+  using Cfg = TileCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;   // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;       // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int m_blocks = (p.M + BM - 1) / BM;
+  const int n_blocks = (p.N + BN - 1) / BN;
+  const int k_blocks = (p.K + BK - 1) / BK;
+  const int tiles_per_batch = m_blocks * n_blocks;
+  const int num_tiles = tiles_per_batch * p.batch;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ===================================================== TMA producer
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int b = tile / tiles_per_batch;
+      const int rem = tile - b * tiles_per_batch;
+      const int m_blk = rem / n_blocks;
+      const int n_blk = rem - m_blk * n_blocks;
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
+        uint8_t* sB = sA + Cfg::A_BYTES;
+        mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+        const int seg = kb / p.k_inner;
+        const int kin = (kb - seg * p.k_inner) * BK;
+        if (!A_MN) {
+          tma_load_4d(sA, &tmA, &full_bar[stage], p.a_c0[b] + kb * BK, m_blk * BM, p.a_c2[b], p.a_c3[b]);
+        } else {
+#pragma unroll
+          for (int c = 0; c < BM / 64; ++c)
+            tma_load_4d(sA + c * (64 * BK * 2), &tmA, &full_bar[stage], p.a_c0[b] + m_blk * BM + c * 64, kin,
+                        p.a_c2[b] + seg * p.a_c2_step[b], p.a_c3[b]);
+        }
+        if (!B_MN) {
+          tma_load_4d(sB, &tmB, &full_bar[stage], p.b_c0[b] + kb * BK, n_blk * BN, p.b_c2[b], p.b_c3[b]);
+        } else {
+#pragma unroll
+          for (int c = 0; c < BN / 64; ++c)
+            tma_load_4d(sB + c * (64 * BK * 2), &tmB, &full_bar[stage], p.b_c0[b] + n_blk * BN + c * 64, kin,
+                        p.b_c2[b] + seg * p.b_c2_step[b], p.b_c3[b]);
+        }
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================================================== MMA issuer (single thread)
+    constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
+    int stage = 0;
+    uint32_t phase = 0;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty_bar[as], aphase ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sA = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+        const uint32_t sB = sA + Cfg::A_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          const uint64_t da = A_MN ? umma_smem_desc(sA + k * 2048, 64 * BK * 2, 1024) : umma_smem_desc(sA + k * 32, 16, 1024);
+          const uint64_t db = B_MN ? umma_smem_desc(sB + k * 2048, 64 * BK * 2, 1024) : umma_smem_desc(sB + k * 32, 16, 1024);
+          umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+      umma_commit(&tfull_bar[as]);
+      if (++as == 2) { as = 0; aphase ^= 1u; }
+    }
+  } else if (warp >= 4) {
+    // ===================================================== epilogue (4 warps <-> 4 TMEM lane quarters)
+    const int q = warp & 3;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int b = tile / tiles_per_batch;
+      const int rem = tile - b * tiles_per_batch;
+      const int m_blk = rem / n_blocks;
+      const int n_blk = rem - m_blk * n_blocks;
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const int row = m_blk * BM + q * 32 + lane;
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(t_addr + c * 32, r);
+        tmem_ld_wait();
+        if (c == BN / 32 - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        }
+        const int col0 = n_blk * BN + c * 32;
+        if (p.mode == EPI_LINEAR) epi_linear(p, b, row, col0, r);
+        else if (p.mode == EPI_LSTM_FWD) epi_lstm_fwd(p, b, row, col0, r);
+        else epi_lstm_bwd(p, b, row, col0, r);
+      }
+      if (++as == 2) { as = 0; aphase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+// First (s == T-1) backward step of the LSTM: no recurrent product yet, dh comes from the encoder output gradient.
+__global__ void lstm_bwd_first_kernel(const GemmParams p, const __nv_bfloat16* __restrict__ dh_last, long long dh_ld) {
+  const int H = p.N, S = p.M;
+  const int groups = H / 8;
+  const long long total = (long long)p.batch * S * groups;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int jg = (int)(i % groups);
+    const long long rest = i / groups;
+    const int seq = (int)(rest % S);
+    const int dir = (int)(rest / S);
+    float dh[8];
+    if (dh_last != nullptr) {
+      uint4 v = *reinterpret_cast<const uint4*>(dh_last + (long long)seq * dh_ld + (long long)dir * H + jg * 8);
+      const uint32_t* w = reinterpret_cast<const uint32_t*>(&v);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float2 f = unpack_bf16x2(w[u]);
+        dh[2 * u] = f.x; dh[2 * u + 1] = f.y;
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) dh[u] = 0.f;
+    }
+    if (p.dh_ext != nullptr) {
+      const int t = dir == 0 ? p.s : p.T - 1 - p.s;
+      uint4 ev = *reinterpret_cast<const uint4*>(p.dh_ext + ((long long)seq * p.T + t) * p.seq_out_ld + (long long)dir * H + jg * 8);
+      const uint32_t* ew = reinterpret_cast<const uint32_t*>(&ev);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float2 e2 = unpack_bf16x2(ew[u]);
+        dh[2 * u] += e2.x; dh[2 * u + 1] += e2.y;
+      }
+    }
+    lstm_cell_bwd8(p, dir, seq, jg * 8, dh);
+  }
+}
+
+// Plain SIMT reference GEMM (fp32 accumulate) used ONLY by the test-suite to check the tcgen05 path on the device
+// at sizes the CPU oracle cannot reach. Arbitrary element strides.
+__global__ void gemm_ref_kernel(const __nv_bfloat16* A, long long a_rs, long long a_ks, const __nv_bfloat16* B,
+                                long long b_rs, long long b_ks, float* C, long long ldc, int M, int N, int K) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int m = blockIdx.y * blockDim.y + threadIdx.y;
+  if (m >= M || n >= N) return;
+  float acc = 0.f;
+  for (int k = 0; k < K; ++k)
+    acc += __bfloat162float(A[m * a_rs + k * a_ks]) * __bfloat162float(B[n * b_rs + k * b_ks]);
+  C[m * ldc + n] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+    if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+  });
+  return fn;
+}
+
+struct TmKey {
+  const void* ptr;
+  long long dims[4];
+  long long strides[4];
+  int box0, box1;
+  bool operator<(const TmKey& o) const { return memcmp(this, &o, sizeof(TmKey)) < 0; }
+};
+
+static int make_tensor_map(CUtensorMap* out, const dvgr_operand& op, int box0, int box1) {
+  static std::map<TmKey, CUtensorMap> cache;
+  static std::mutex mu;
+  TmKey key;
+  memset(&key, 0, sizeof(key));
+  key.ptr = op.ptr;
+  for (int i = 0; i < 4; ++i) {
+    key.dims[i] = i < op.ndim ? op.dims[i] : 1;
+    key.strides[i] = i < op.ndim ? op.strides[i] : 0;
+  }
+  key.box0 = box0;
+  key.box1 = box1;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = it->second; return 0; }
+  }
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return set_error("cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t gdim[4];
+  cuuint64_t gstride[3];
+  cuuint32_t box[4] = {(cuuint32_t)box0, (cuuint32_t)box1, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  for (int i = 0; i < 4; ++i) gdim[i] = (cuuint64_t)key.dims[i];
+  long long str[4];
+  str[0] = 1;
+  for (int i = 1; i < 4; ++i) {
+    long long s;
+    if (i < op.ndim) {
+      s = op.strides[i];
+    } else {   // padded unit dimension: any valid 16-byte-multiple stride (its coordinate is always 0)
+      s = str[i - 1] * key.dims[i - 1];
+      if (s < 8) s = 8;
+      s = (s + 7) / 8 * 8;
+    }
+    if (s <= 0 || (s * 2) % 16 != 0)
+      return set_error("tensor-map stride (dim %d = %lld elements) is not a positive multiple of 16 bytes", i, s);
+    str[i] = s;
+    gstride[i - 1] = (cuuint64_t)s * 2;
+  }
+  if ((reinterpret_cast<uintptr_t>(op.ptr) & 15) != 0) return set_error("tensor-map base pointer not 16-byte aligned");
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(op.ptr), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    if (cache.size() > 4096) cache.clear();
+    cache[key] = *out;
+  }
+  return 0;
+}
+
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
+template <bool A_MN, bool B_MN, int BN>
+static int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int max_ctas,
+                          cudaStream_t stream) {
+  using Cfg = TileCfg<BN>;
+  static bool attr_set = false;
+  auto kern = gemm_tcgen05_kernel<A_MN, B_MN, BN>;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return set_error("cudaFuncSetAttribute(smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int m_blocks = (p.M + BM - 1) / BM, n_blocks = (p.N + BN - 1) / BN;
+  const long long tiles = (long long)m_blocks * n_blocks * p.batch;
+  int grid = (int)std::min<long long>(tiles, max_ctas > 0 ? max_ctas : num_sms());
+  if (grid <= 0) return 0;
+  kern<<<grid, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error("gemm launch failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+int gemm_dispatch(const dvgr_operand& A, const dvgr_operand& B, GemmParams p, int bn, int max_ctas, cudaStream_t stream) {
+  if (p.M <= 0 || p.N <= 0 || p.batch <= 0) return 0;
+  if (p.K <= 0) return set_error("gemm: K must be positive");
+  if (p.batch > kMaxBatch) return set_error("gemm: batch %d exceeds %d", p.batch, kMaxBatch);
+  if (bn != 128 && bn != 256) bn = (p.N > 128) ? 256 : 128;
+  if (p.mode != EPI_LINEAR) bn = 128;
+  if (p.k_inner <= 0) p.k_inner = INT_MAX;
+  const bool a_mn = A.major != 0, b_mn = B.major != 0;
+  CUtensorMap ta, tb;
+  int rc = make_tensor_map(&ta, A, 64, a_mn ? 64 : BM);
+  if (rc) return rc;
+  rc = make_tensor_map(&tb, B, 64, b_mn ? 64 : bn);
+  if (rc) return rc;
+#define DVGR_LAUNCH(AM, BMJ, BNV) return launch_variant<AM, BMJ, BNV>(ta, tb, p, max_ctas, stream)
+  if (!a_mn && !b_mn) { if (bn == 256) DVGR_LAUNCH(false, false, 256); else DVGR_LAUNCH(false, false, 128); }
+  if (!a_mn && b_mn) { if (bn == 256) DVGR_LAUNCH(false, true, 256); else DVGR_LAUNCH(false, true, 128); }
+  if (a_mn && b_mn) { if (bn == 256) DVGR_LAUNCH(true, true, 256); else DVGR_LAUNCH(true, true, 128); }
+#undef DVGR_LAUNCH
+  return set_error("gemm: operand layout combination (A MN-major, B K-major) is not instantiated");
+}
+
+int lstm_bwd_first(const GemmParams& p, const void* dh_last, long long dh_ld, cudaStream_t stream) {
+  const long long total = (long long)p.batch * p.M * (p.N / 8);
+  if (total <= 0) return 0;
+  int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 8);
+  lstm_bwd_first_kernel<<<blocks, 256, 0, stream>>>(p, reinterpret_cast<const __nv_bfloat16*>(dh_last), dh_ld);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error("lstm_bwd_first launch failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+int gemm_ref(const void* A, long long a_rs, long long a_ks, const void* B, long long b_rs, long long b_ks, float* C,
+             long long ldc, int M, int N, int K, cudaStream_t stream) {
+  dim3 blk(32, 8), grd((N + 31) / 32, (M + 7) / 8);
+  gemm_ref_kernel<<<grd, blk, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(A), a_rs, a_ks,
+                                            reinterpret_cast<const __nv_bfloat16*>(B), b_rs, b_ks, C, ldc, M, N, K);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error("gemm_ref launch failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+}  // namespace dvgr

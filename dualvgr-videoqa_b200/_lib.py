@@ -77,3 +77,57 @@ gemm_reference = _sig("dvgr_gemm_reference",
                       [c_void_p, c_ll, c_ll, c_void_p, c_ll, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_void_p])
 lstm_step_fwd = _sig("dvgr_lstm_step_fwd", [ctypes.POINTER(LstmArgs), c_void_p])
 lstm_step_bwd = _sig("dvgr_lstm_step_bwd", [ctypes.POINTER(LstmArgs), c_void_p])
+
+
+class GatGraph(ctypes.Structure):
+    _fields_ = [("wh", c_void_p), ("gate", c_void_p), ("avec", c_void_p), ("out", c_void_p), ("out_f32", c_void_p),
+                ("dout", c_void_p), ("dout_f32", c_void_p), ("dwh", c_void_p), ("dgate", c_void_p),
+                ("davec", c_void_p), ("drop_stream", ctypes.c_uint)]
+
+
+class GatArgs(ctypes.Structure):
+    _fields_ = [("graphs", GatGraph * 4), ("n_graphs", c_int), ("B", c_int), ("N", c_int), ("D", c_int),
+                ("heads", c_int), ("ld_wh", c_ll), ("ld_out", c_ll), ("adj", c_void_p), ("slope", c_float),
+                ("p_att", c_float), ("p_out", c_float), ("seed", ctypes.c_ulonglong)]
+
+
+P = c_void_p
+c_ull, c_uint = ctypes.c_ulonglong, ctypes.c_uint
+gat_attn_fwd = _sig("dvgr_gat_attn_fwd", [ctypes.POINTER(GatArgs), P])
+gat_attn_bwd = _sig("dvgr_gat_attn_bwd", [ctypes.POINTER(GatArgs), P])
+qattn_fwd = _sig("dvgr_qattn_fwd", [P, P, P, P, P, c_ll, c_int, c_int, c_int, c_int, P, P, P, P, P, c_ll, P])
+qattn_bwd = _sig("dvgr_qattn_bwd", [P, c_ll, P, P, P, P, c_ll, c_int, c_int, c_int, c_int, P, P, P, P, P, P, c_int, P, P, P])
+gate_fwd = _sig("dvgr_gate_fwd", [P, P, P, c_ll, c_int, c_int, c_int, P, P, P])
+gate_bwd = _sig("dvgr_gate_bwd", [P, P, P, c_ll, c_int, c_int, c_int, P, P, P, P, P, P, P, P, P, P])
+view_attn_fwd = _sig("dvgr_view_attn_fwd", [P, P, P, P, c_ll, c_int, P, P, P, P])
+view_attn_bwd_blocks = _sig("dvgr_view_attn_bwd_blocks", [c_ll])
+view_attn_bwd = _sig("dvgr_view_attn_bwd", [P, P, P, P, P, P, c_ll, c_int, P, P, P, P])
+mfb_fwd = _sig("dvgr_mfb_fwd", [P, P, P, c_ll, c_int, P])
+mfb_bwd = _sig("dvgr_mfb_bwd", [P, P, P, P, P, c_ll, c_int, P])
+readout_fwd = _sig("dvgr_readout_fwd", [P, P, P, P, c_int, c_int, c_int, P, P, c_ll, P])
+readout_bwd = _sig("dvgr_readout_bwd", [P, c_ll, P, P, P, P, c_int, c_int, c_int, P, P, P, P, P])
+bn_fwd = _sig("dvgr_bn_fwd", [P, c_int, c_int, P, P, P, P, c_int, c_float, c_float, P, P, P, P])
+bn_bwd = _sig("dvgr_bn_bwd", [P, P, c_int, c_int, P, P, P, c_int, P, P, P, P])
+cross_entropy = _sig("dvgr_cross_entropy", [P, P, c_int, c_int, c_float, P, P, c_ll, P, P])
+pair_loss = _sig("dvgr_pair_loss", [P, P, c_int, c_int, c_int, c_int, c_float, P, P, P, c_int, c_int, P])
+prep_features = _sig("dvgr_prep_features", [P, P, c_ll, c_int, c_int, c_int, c_int, c_float, c_ull, c_uint, P])
+cast_rows = _sig("dvgr_cast_rows", [P, c_ll, P, c_ll, c_int, c_int, c_int, c_int, P])
+dropout = _sig("dvgr_dropout", [P, P, c_ll, c_float, c_ull, c_uint, P])
+act_bwd = _sig("dvgr_act_bwd", [P, P, P, c_ll, c_int, c_int, c_float, c_ull, c_uint, P])
+add = _sig("dvgr_add", [P, P, c_ll, P])
+lib.dvgr_colsum_workspace.argtypes = [c_ll, c_int]
+lib.dvgr_colsum_workspace.restype = c_ll
+colsum = _sig("dvgr_colsum", [P, c_int, c_ll, c_ll, c_int, P, P, c_int, c_float, P])
+sumsq_blocks = _sig("dvgr_sumsq_blocks", [])
+sumsq = _sig("dvgr_sumsq", [P, c_ll, P, P, P])
+adam_step = _sig("dvgr_adam_step", [P, P, P, P, c_ll, c_float, c_float, c_float, c_float, c_int, c_float, P, c_float, P])
+
+EXPORTED = [
+    "dvgr_last_error", "dvgr_abi_version", "dvgr_launch_count", "dvgr_gemm", "dvgr_gemm_reference",
+    "dvgr_lstm_step_fwd", "dvgr_lstm_step_bwd", "dvgr_gat_attn_fwd", "dvgr_gat_attn_bwd", "dvgr_qattn_fwd",
+    "dvgr_qattn_bwd", "dvgr_gate_fwd", "dvgr_gate_bwd", "dvgr_view_attn_fwd", "dvgr_view_attn_bwd_blocks",
+    "dvgr_view_attn_bwd", "dvgr_mfb_fwd", "dvgr_mfb_bwd", "dvgr_readout_fwd", "dvgr_readout_bwd", "dvgr_bn_fwd",
+    "dvgr_bn_bwd", "dvgr_cross_entropy", "dvgr_pair_loss", "dvgr_prep_features", "dvgr_cast_rows", "dvgr_dropout",
+    "dvgr_act_bwd", "dvgr_add", "dvgr_colsum_workspace", "dvgr_colsum", "dvgr_sumsq_blocks", "dvgr_sumsq",
+    "dvgr_adam_step",
+]

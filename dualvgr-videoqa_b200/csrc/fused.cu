@@ -1,0 +1,681 @@
+// Memory-bound fused kernels of the DualVGR unit tail: two-view attention + residual, MFB pair-sum, attention
+// read-out, BatchNorm1d, cross-entropy, plus the streaming helpers (feature prologue, weight casts, dropout, ELU
+// backward, column sums). Each is a single pass over its operands with 128-bit accesses and warp-shuffle reductions.
+#include <cuda_bf16.h>
+
+#include "capi_internal.h"
+#include "ptx.cuh"
+#include "rng.cuh"
+
+namespace dvgr {
+
+typedef __nv_bfloat16 bf16;
+
+__device__ __forceinline__ void load8(const bf16* p, float (&f)[8]) {
+  uint4 v = *reinterpret_cast<const uint4*>(p);
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(&v);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float2 t = unpack_bf16x2(w[q]);
+    f[2 * q] = t.x;
+    f[2 * q + 1] = t.y;
+  }
+}
+__device__ __forceinline__ void store8(bf16* p, const float (&f)[8]) {
+  uint4 o;
+  o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
+  o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+  *reinterpret_cast<uint4*>(p) = o;
+}
+
+// =============================================================================================== view attention
+// reference model/Attention.py:20-23 on the stack of model/models.py:163-166, + the residual of :168-169.
+//   hidden [2][M][D] = tanh(W1 z + b1) (GEMM epilogue), z [2][M][D], X [M][D]
+//   w_v = w2 . hidden_v ; beta = softmax_v(w) ; embed = sum_v beta_v z_v ; Xnew = X + embed
+// one warp per node row.
+__global__ void __launch_bounds__(256)
+view_attn_fwd_kernel(const bf16* __restrict__ hidden, const bf16* __restrict__ z, const bf16* __restrict__ X,
+                     const float* __restrict__ w2, long long M, int D, bf16* __restrict__ Xnew,
+                     bf16* __restrict__ embed, float* __restrict__ beta) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (long long r = (long long)blockIdx.x * 8 + warp; r < M; r += (long long)gridDim.x * 8) {
+    float w0 = 0.f, w1 = 0.f;
+    for (int c = lane * 8; c < D; c += 256) {
+      float h0[8], h1[8];
+      load8(hidden + r * D + c, h0);
+      load8(hidden + (M + r) * D + c, h1);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float w = w2[c + q];
+        w0 += w * h0[q];
+        w1 += w * h1[q];
+      }
+    }
+    w0 = warp_sum(w0);
+    w1 = warp_sum(w1);
+    const float m = fmaxf(w0, w1);
+    const float e0 = __expf(w0 - m), e1 = __expf(w1 - m);
+    const float b0 = e0 / (e0 + e1), b1 = e1 / (e0 + e1);
+    if (lane == 0) {
+      beta[r * 2] = b0;
+      beta[r * 2 + 1] = b1;
+    }
+    for (int c = lane * 8; c < D; c += 256) {
+      float z0[8], z1[8], x[8], e[8];
+      load8(z + r * D + c, z0);
+      load8(z + (M + r) * D + c, z1);
+      load8(X + r * D + c, x);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        e[q] = b0 * z0[q] + b1 * z1[q];
+        x[q] += e[q];
+      }
+      store8(Xnew + r * D + c, x);
+      if (embed != nullptr) store8(embed + r * D + c, e);
+    }
+  }
+}
+
+// dXnew [M][D] (+ optional dembed_ext) -> dz [2][M][D], dhid_pre [2][M][D] (tanh' applied), dw2 partial [gridDim][D]
+__global__ void __launch_bounds__(256)
+view_attn_bwd_kernel(const bf16* __restrict__ dXnew, const bf16* __restrict__ dembed_ext, const bf16* __restrict__ hidden,
+                     const bf16* __restrict__ z, const float* __restrict__ w2, const float* __restrict__ beta,
+                     long long M, int D, bf16* __restrict__ dz, bf16* __restrict__ dhid, float* __restrict__ dw2_part) {
+  extern __shared__ float dw2_s[];   // [D]
+  for (int c = threadIdx.x; c < D; c += blockDim.x) dw2_s[c] = 0.f;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (long long r = (long long)blockIdx.x * 8 + warp; r < M; r += (long long)gridDim.x * 8) {
+    const float b0 = beta[r * 2], b1 = beta[r * 2 + 1];
+    float db0 = 0.f, db1 = 0.f;
+    for (int c = lane * 8; c < D; c += 256) {
+      float de[8], z0[8], z1[8], o0[8], o1[8];
+      load8(dXnew + r * D + c, de);
+      if (dembed_ext != nullptr) {
+        float ex[8];
+        load8(dembed_ext + r * D + c, ex);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) de[q] += ex[q];
+      }
+      load8(z + r * D + c, z0);
+      load8(z + (M + r) * D + c, z1);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        db0 += de[q] * z0[q];
+        db1 += de[q] * z1[q];
+        o0[q] = b0 * de[q];
+        o1[q] = b1 * de[q];
+      }
+      store8(dz + r * D + c, o0);
+      store8(dz + (M + r) * D + c, o1);
+    }
+    db0 = warp_sum(db0);
+    db1 = warp_sum(db1);
+    const float t = b0 * db0 + b1 * db1;
+    const float dw0 = b0 * (db0 - t), dw1 = b1 * (db1 - t);
+    for (int c = lane * 8; c < D; c += 256) {
+      float h0[8], h1[8], o0[8], o1[8];
+      load8(hidden + r * D + c, h0);
+      load8(hidden + (M + r) * D + c, h1);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float w = w2[c + q];
+        o0[q] = dw0 * w * (1.f - h0[q] * h0[q]);
+        o1[q] = dw1 * w * (1.f - h1[q] * h1[q]);
+        atomicAdd(&dw2_s[c + q], dw0 * h0[q] + dw1 * h1[q]);
+      }
+      store8(dhid + r * D + c, o0);
+      store8(dhid + (M + r) * D + c, o1);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < D; c += blockDim.x) dw2_part[(long long)blockIdx.x * D + c] = dw2_s[c];
+}
+
+// =============================================================================================== MFB pair-sum
+// reference model/fusions/fusions.py:433-441: z = (x0 * x1).view(..., 256, 2).sum(-1)   (x0, x1 already ELU'd by the GEMM)
+__global__ void mfb_fwd_kernel(const bf16* __restrict__ x0, const bf16* __restrict__ x1, bf16* __restrict__ z,
+                               long long n_out4) {   // n_out4 = M*mm/4 ; each thread: 8 inputs -> 4 outputs
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_out4; i += (long long)gridDim.x * blockDim.x) {
+    float a[8], b[8];
+    load8(x0 + i * 8, a);
+    load8(x1 + i * 8, b);
+    uint2 o;
+    o.x = pack_bf16x2(a[0] * b[0] + a[1] * b[1], a[2] * b[2] + a[3] * b[3]);
+    o.y = pack_bf16x2(a[4] * b[4] + a[5] * b[5], a[6] * b[6] + a[7] * b[7]);
+    *reinterpret_cast<uint2*>(z + i * 4) = o;
+  }
+}
+// dz -> dpre0 = dz_pair * x1 * ELU'(x0), dpre1 = dz_pair * x0 * ELU'(x1)
+__global__ void mfb_bwd_kernel(const bf16* __restrict__ dz, const bf16* __restrict__ x0, const bf16* __restrict__ x1,
+                               bf16* __restrict__ d0, bf16* __restrict__ d1, long long n_out4) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_out4; i += (long long)gridDim.x * blockDim.x) {
+    float a[8], b[8], oa[8], ob[8];
+    load8(x0 + i * 8, a);
+    load8(x1 + i * 8, b);
+    uint2 dv = *reinterpret_cast<const uint2*>(dz + i * 4);
+    float2 d01 = unpack_bf16x2(dv.x), d23 = unpack_bf16x2(dv.y);
+    const float d[4] = {d01.x, d01.y, d23.x, d23.y};
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      oa[q] = d[q >> 1] * b[q] * elu_grad_from_out(a[q]);
+      ob[q] = d[q >> 1] * a[q] * elu_grad_from_out(b[q]);
+    }
+    store8(d0 + i * 8, oa);
+    store8(d1 + i * 8, ob);
+  }
+}
+
+// =============================================================================================== read-out
+// reference model/AnswerDecoder.py:176-180: alpha = softmax_n(w . u_n + c), pooled = sum_n alpha_n v_n
+//   u = ELU(v W_v^T) comes from the GEMM; v is the (already dropped-out) feature block.
+__global__ void __launch_bounds__(256)
+readout_fwd_kernel(const bf16* __restrict__ v, const bf16* __restrict__ u, const float* __restrict__ w,
+                   const float* __restrict__ c, int N, int D, float* __restrict__ alpha, bf16* __restrict__ pooled,
+                   long long ld_p) {
+  __shared__ float sc[64];
+  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int n = warp; n < N; n += 8) {
+    float acc = 0.f;
+    const bf16* row = u + ((long long)b * N + n) * D;
+    for (int k = lane * 8; k < D; k += 256) {
+      float f[8];
+      load8(row + k, f);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc += f[q] * w[k + q];
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) sc[n] = acc + c[0];
+  }
+  __syncthreads();
+  if (warp == 0) {
+    float m = -INFINITY;
+    for (int n = lane; n < N; n += 32) m = fmaxf(m, sc[n]);
+    m = warp_max(m);
+    float s = 0.f;
+    for (int n = lane; n < N; n += 32) s += __expf(sc[n] - m);
+    s = warp_sum(s);
+    for (int n = lane; n < N; n += 32) {
+      const float a = __expf(sc[n] - m) / s;
+      sc[n] = a;
+      alpha[(long long)b * N + n] = a;
+    }
+  }
+  __syncthreads();
+  for (int k = threadIdx.x * 2; k < D; k += 512) {
+    float ax = 0.f, ay = 0.f;
+    for (int n = 0; n < N; ++n) {
+      const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(v + ((long long)b * N + n) * D + k));
+      ax += sc[n] * x.x;
+      ay += sc[n] * x.y;
+    }
+    *reinterpret_cast<__nv_bfloat162*>(pooled + (long long)b * ld_p + k) = __floats2bfloat162_rn(ax, ay);
+  }
+}
+
+// dpooled [B][ld_p] -> dv [B][N][D] = alpha_n dpooled ; du_pre = dscore_n * w * ELU'(u) ; dw partial [B][D], dc partial [B]
+__global__ void __launch_bounds__(256)
+readout_bwd_kernel(const bf16* __restrict__ dpooled, long long ld_p, const bf16* __restrict__ v,
+                   const bf16* __restrict__ u, const float* __restrict__ w, const float* __restrict__ alpha, int N,
+                   int D, bf16* __restrict__ dv, bf16* __restrict__ du, float* __restrict__ dw_part,
+                   float* __restrict__ dc_part) {
+  __shared__ float da[64];
+  __shared__ float al[64];
+  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bf16* dp = dpooled + (long long)b * ld_p;
+  for (int n = warp; n < N; n += 8) {
+    float acc = 0.f;
+    const bf16* row = v + ((long long)b * N + n) * D;
+    for (int k = lane * 8; k < D; k += 256) {
+      float f[8], g[8];
+      load8(row + k, f);
+      load8(dp + k, g);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc += f[q] * g[q];
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      da[n] = acc;
+      al[n] = alpha[(long long)b * N + n];
+    }
+  }
+  __syncthreads();
+  if (warp == 0) {
+    float t = 0.f;
+    for (int n = lane; n < N; n += 32) t += al[n] * da[n];
+    t = warp_sum(t);
+    float dcs = 0.f;
+    for (int n = lane; n < N; n += 32) {
+      const float ds = al[n] * (da[n] - t);
+      da[n] = ds;
+      dcs += ds;
+    }
+    dcs = warp_sum(dcs);
+    if (lane == 0) dc_part[b] = dcs;
+  }
+  __syncthreads();
+  for (int k = threadIdx.x * 2; k < D; k += 512) {
+    const float2 g = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dp + k));
+    const float w0 = w[k], w1 = w[k + 1];
+    float dwx = 0.f, dwy = 0.f;
+    for (int n = 0; n < N; ++n) {
+      const long long off = ((long long)b * N + n) * D + k;
+      *reinterpret_cast<__nv_bfloat162*>(dv + off) = __floats2bfloat162_rn(al[n] * g.x, al[n] * g.y);
+      const float2 uu = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(u + off));
+      dwx += da[n] * uu.x;
+      dwy += da[n] * uu.y;
+      *reinterpret_cast<__nv_bfloat162*>(du + off) =
+          __floats2bfloat162_rn(da[n] * w0 * elu_grad_from_out(uu.x), da[n] * w1 * elu_grad_from_out(uu.y));
+    }
+    dw_part[(long long)b * D + k] = dwx;
+    dw_part[(long long)b * D + k + 1] = dwy;
+  }
+}
+
+// =============================================================================================== BatchNorm1d
+// reference model/AnswerDecoder.py:193 (nn.BatchNorm1d(module_dim)): batch statistics (biased variance) in training,
+// running statistics in eval; running stats updated with momentum 0.1 and the UNBIASED variance, as torch does.
+__global__ void bn_fwd_kernel(const bf16* __restrict__ x, int B, int D, const float* __restrict__ gamma,
+                              const float* __restrict__ betap, float* __restrict__ run_mean, float* __restrict__ run_var,
+                              int training, float momentum, float eps, bf16* __restrict__ y, float* __restrict__ mean_out,
+                              float* __restrict__ rstd_out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= D) return;
+  float mean, var;
+  if (training) {
+    float s = 0.f;
+    for (int r = 0; r < B; ++r) s += __bfloat162float(x[(long long)r * D + c]);
+    mean = s / B;
+    float v = 0.f;
+    for (int r = 0; r < B; ++r) {
+      const float d = __bfloat162float(x[(long long)r * D + c]) - mean;
+      v += d * d;
+    }
+    var = v / B;
+    if (run_mean != nullptr) {
+      run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * mean;
+      run_var[c] = (1.f - momentum) * run_var[c] + momentum * (B > 1 ? v / (B - 1) : var);
+    }
+  } else {
+    mean = run_mean[c];
+    var = run_var[c];
+  }
+  const float rstd = rsqrtf(var + eps);
+  if (mean_out != nullptr) {
+    mean_out[c] = mean;
+    rstd_out[c] = rstd;
+  }
+  const float g = gamma[c], bt = betap[c];
+  for (int r = 0; r < B; ++r)
+    y[(long long)r * D + c] = __float2bfloat16_rn((__bfloat162float(x[(long long)r * D + c]) - mean) * rstd * g + bt);
+}
+
+__global__ void bn_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, int B, int D,
+                              const float* __restrict__ gamma, const float* __restrict__ mean,
+                              const float* __restrict__ rstd, int training, bf16* __restrict__ dx,
+                              float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= D) return;
+  const float m = mean[c], rs = rstd[c], g = gamma[c];
+  float sdy = 0.f, sdyx = 0.f;
+  for (int r = 0; r < B; ++r) {
+    const float d = __bfloat162float(dy[(long long)r * D + c]);
+    const float xh = (__bfloat162float(x[(long long)r * D + c]) - m) * rs;
+    sdy += d;
+    sdyx += d * xh;
+  }
+  dgamma[c] = sdyx;
+  dbeta[c] = sdy;
+  for (int r = 0; r < B; ++r) {
+    const float d = __bfloat162float(dy[(long long)r * D + c]);
+    const float xh = (__bfloat162float(x[(long long)r * D + c]) - m) * rs;
+    const float o = training ? g * rs * (d - sdy / B - xh * sdyx / B) : g * rs * d;
+    dx[(long long)r * D + c] = __float2bfloat16_rn(o);
+  }
+}
+
+// =============================================================================================== cross-entropy
+// nn.CrossEntropyLoss (mean) at train.py:121,146: loss_part[b] = -log softmax(logits_b)[ans_b] / B,
+// dlogits = (softmax - onehot) * scale / B  (bf16, row stride ld_d, padding columns zeroed)
+__global__ void ce_kernel(const float* __restrict__ logits, const long long* __restrict__ ans, int B, int A,
+                          float scale, float* __restrict__ loss_part, bf16* __restrict__ dlogits, long long ld_d,
+                          int* __restrict__ correct) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (b >= B) return;
+  const float* row = logits + (long long)b * A;
+  float m = -INFINITY;
+  int am = 0;
+  for (int a = lane; a < A; a += 32) {
+    if (row[a] > m) { m = row[a]; am = a; }
+  }
+  // warp arg-max (first index wins on ties, like torch.argmax / batch_accuracy at train.py:352-356)
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, m, o);
+    const int oa = __shfl_xor_sync(0xffffffffu, am, o);
+    if (om > m || (om == m && oa < am)) { m = om; am = oa; }
+  }
+  float s = 0.f;
+  for (int a = lane; a < A; a += 32) s += __expf(row[a] - m);
+  s = warp_sum(s);
+  const long long t = ans[b];
+  const float lse = m + __logf(s);
+  if (lane == 0) {
+    loss_part[b] = (lse - row[t]) / B;
+    if (correct != nullptr) correct[b] = (am == (int)t) ? 1 : 0;
+  }
+  if (dlogits != nullptr) {
+    for (int a = lane; a < ld_d; a += 32) {
+      float g = 0.f;
+      if (a < A) g = (__expf(row[a] - lse) - (a == t ? 1.f : 0.f)) * scale / B;
+      dlogits[(long long)b * ld_d + a] = __float2bfloat16_rn(g);
+    }
+  }
+}
+
+// =============================================================================================== streaming helpers
+// Appearance prologue, reference model/Preprocessing.py:220-223: tanh(dropout(x)) and the [B,N,F,C] -> [F, B*N, C]
+// re-layout (two full transposed copies in the reference) fused with the fp32 -> bf16 cast in ONE pass.
+__global__ void prep_features_kernel(const float* __restrict__ in, bf16* __restrict__ out, long long S, int T, int C,
+                                     int do_tanh, int time_major, DropoutCfg dc) {
+  const long long n8 = S * T * (long long)C / 8;
+  const int c8 = C / 8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    const float4 a = reinterpret_cast<const float4*>(in)[2 * i];
+    const float4 b = reinterpret_cast<const float4*>(in)[2 * i + 1];
+    float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    if (dc.p > 0.f) {
+      float s0[4], s1[4];
+      dropout_scale4(dc, 2 * i, s0);
+      dropout_scale4(dc, 2 * i + 1, s1);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        f[q] *= s0[q];
+        f[4 + q] *= s1[q];
+      }
+    }
+    if (do_tanh) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) f[q] = tanhf_(f[q]);
+    }
+    long long o = i;
+    if (time_major) {
+      const long long row = i / c8;     // = s * T + t
+      const int cc = (int)(i - row * c8);
+      const long long s = row / T;
+      const int t = (int)(row - s * T);
+      o = ((long long)t * S + s) * c8 + cc;
+    }
+    store8(out + o * 8, f);
+  }
+}
+
+// fp32 [rows][cols] (ld_in) -> bf16 [rows][out_cols] (ld_out), zero padded columns; optional LSTM gate interleave:
+// output row 4*j + g <- input row g*H + j  (nn.LSTM stores i|f|g|o blocks; the fused cell wants them per unit).
+__global__ void cast_rows_kernel(const float* __restrict__ in, long long ld_in, bf16* __restrict__ out, long long ld_out,
+                                 int rows, int cols, int out_cols, int lstm_H) {
+  const long long total = (long long)rows * out_cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / out_cols), c = (int)(i - (long long)r * out_cols);
+    int src = r;
+    if (lstm_H > 0) src = (r & 3) * lstm_H + (r >> 2);
+    out[(long long)r * ld_out + c] = __float2bfloat16_rn(c < cols ? in[(long long)src * ld_in + c] : 0.f);
+  }
+}
+
+// out = in * dropout mask (the same kernel is its own backward)
+__global__ void dropout_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, long long n8, DropoutCfg dc) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    float f[8], s0[4], s1[4];
+    load8(in + i * 8, f);
+    dropout_scale4(dc, 2 * i, s0);
+    dropout_scale4(dc, 2 * i + 1, s1);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      f[q] *= s0[q];
+      f[4 + q] *= s1[q];
+    }
+    store8(out + i * 8, f);
+  }
+}
+
+// out = dy * dropout mask * act'(y)   (y is the activation OUTPUT; act: 0 none, 1 ELU, 2 tanh); optional accumulate
+__global__ void act_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ y, bf16* __restrict__ out,
+                               long long n8, int act, int accumulate, DropoutCfg dc) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    float d[8], yy[8];
+    load8(dy + i * 8, d);
+    if (dc.p > 0.f) {
+      float s0[4], s1[4];
+      dropout_scale4(dc, 2 * i, s0);
+      dropout_scale4(dc, 2 * i + 1, s1);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        d[q] *= s0[q];
+        d[4 + q] *= s1[q];
+      }
+    }
+    if (act != 0) {
+      load8(y + i * 8, yy);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) d[q] *= (act == 1) ? elu_grad_from_out(yy[q]) : (1.f - yy[q] * yy[q]);
+    }
+    if (accumulate) {
+      float o[8];
+      load8(out + i * 8, o);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) d[q] += o[q];
+    }
+    store8(out + i * 8, d);
+  }
+}
+
+// a (+)= b elementwise (bf16), used to merge gradient branches
+__global__ void add_kernel(bf16* __restrict__ a, const bf16* __restrict__ b, long long n8) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    float x[8], y[8];
+    load8(a + i * 8, x);
+    load8(b + i * 8, y);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) x[q] += y[q];
+    store8(a + i * 8, x);
+  }
+}
+
+// Column sums, two deterministic passes: partial[chunk][C] then out[C] (+)= sum_chunk. Input bf16 or fp32.
+template <typename T>
+__global__ void colsum_partial_kernel(const T* __restrict__ in, long long ld, long long R, int C, int rows_per_chunk,
+                                      float* __restrict__ partial) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const long long r0 = (long long)blockIdx.y * rows_per_chunk;
+  const long long r1 = min(R, r0 + rows_per_chunk);
+  float acc = 0.f;
+  for (long long r = r0; r < r1; ++r) acc += ldf<T>(in + r * ld + c);
+  partial[(long long)blockIdx.y * C + c] = acc;
+}
+__global__ void colsum_final_kernel(const float* __restrict__ partial, int chunks, int C, float* __restrict__ out,
+                                    int accumulate, float scale) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float acc = 0.f;
+  for (int k = 0; k < chunks; ++k) acc += partial[(long long)k * C + c];
+  acc *= scale;
+  out[c] = accumulate ? out[c] + acc : acc;
+}
+
+static inline int grid_for(long long n, int threads = 256, int max_blocks = 148 * 16) {
+  long long b = (n + threads - 1) / threads;
+  if (b < 1) b = 1;
+  return (int)std::min<long long>(b, max_blocks);
+}
+
+}  // namespace dvgr
+
+using namespace dvgr;
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+#define BF(p) reinterpret_cast<bf16*>(p)
+#define CBF(p) reinterpret_cast<const bf16*>(p)
+
+extern "C" int dvgr_view_attn_fwd(const void* hidden, const void* z, const void* x, const float* w2, long long M, int D,
+                                  void* xnew, void* embed, float* beta, void* stream) {
+  if (M <= 0) return 0;
+  if (D % 8 != 0) return set_error("view_attn: D=%d must be a multiple of 8", D);
+  view_attn_fwd_kernel<<<grid_for(M, 8, 148 * 8), 256, 0, ST(stream)>>>(CBF(hidden), CBF(z), CBF(x), w2, M, D, BF(xnew),
+                                                                       BF(embed), beta);
+  DVGR_CHECK_LAUNCH("view_attn_fwd");
+  return 0;
+}
+
+extern "C" int dvgr_view_attn_bwd_blocks(long long M) { return grid_for(M, 8, 148 * 2); }
+
+extern "C" int dvgr_view_attn_bwd(const void* dxnew, const void* dembed_ext, const void* hidden, const void* z,
+                                  const float* w2, const float* beta, long long M, int D, void* dz, void* dhid,
+                                  float* dw2_part, void* stream) {
+  if (M <= 0) return 0;
+  if (D % 8 != 0) return set_error("view_attn: D=%d must be a multiple of 8", D);
+  const int blocks = dvgr_view_attn_bwd_blocks(M);
+  view_attn_bwd_kernel<<<blocks, 256, D * sizeof(float), ST(stream)>>>(CBF(dxnew), CBF(dembed_ext), CBF(hidden), CBF(z),
+                                                                      w2, beta, M, D, BF(dz), BF(dhid), dw2_part);
+  DVGR_CHECK_LAUNCH("view_attn_bwd");
+  return 0;
+}
+
+extern "C" int dvgr_mfb_fwd(const void* x0, const void* x1, void* z, long long M, int mm2, void* stream) {
+  if (mm2 % 8 != 0) return set_error("mfb: 2*mm_dim=%d must be a multiple of 8", mm2);
+  const long long n = M * mm2 / 8;
+  if (n <= 0) return 0;
+  mfb_fwd_kernel<<<grid_for(n), 256, 0, ST(stream)>>>(CBF(x0), CBF(x1), BF(z), n);
+  DVGR_CHECK_LAUNCH("mfb_fwd");
+  return 0;
+}
+extern "C" int dvgr_mfb_bwd(const void* dz, const void* x0, const void* x1, void* d0, void* d1, long long M, int mm2,
+                            void* stream) {
+  if (mm2 % 8 != 0) return set_error("mfb: 2*mm_dim=%d must be a multiple of 8", mm2);
+  const long long n = M * mm2 / 8;
+  if (n <= 0) return 0;
+  mfb_bwd_kernel<<<grid_for(n), 256, 0, ST(stream)>>>(CBF(dz), CBF(x0), CBF(x1), BF(d0), BF(d1), n);
+  DVGR_CHECK_LAUNCH("mfb_bwd");
+  return 0;
+}
+
+extern "C" int dvgr_readout_fwd(const void* v, const void* u, const float* w, const float* c, int B, int N, int D,
+                                float* alpha, void* pooled, long long ld_p, void* stream) {
+  if (B <= 0) return 0;
+  if (N > 64) return set_error("readout: N=%d > 64", N);
+  if (D % 8 != 0) return set_error("readout: D=%d must be a multiple of 8", D);
+  readout_fwd_kernel<<<B, 256, 0, ST(stream)>>>(CBF(v), CBF(u), w, c, N, D, alpha, BF(pooled), ld_p);
+  DVGR_CHECK_LAUNCH("readout_fwd");
+  return 0;
+}
+extern "C" int dvgr_readout_bwd(const void* dpooled, long long ld_p, const void* v, const void* u, const float* w,
+                                const float* alpha, int B, int N, int D, void* dv, void* du, float* dw_part,
+                                float* dc_part, void* stream) {
+  if (B <= 0) return 0;
+  if (N > 64) return set_error("readout: N=%d > 64", N);
+  if (D % 8 != 0) return set_error("readout: D=%d must be a multiple of 8", D);
+  readout_bwd_kernel<<<B, 256, 0, ST(stream)>>>(CBF(dpooled), ld_p, CBF(v), CBF(u), w, alpha, N, D, BF(dv), BF(du),
+                                                dw_part, dc_part);
+  DVGR_CHECK_LAUNCH("readout_bwd");
+  return 0;
+}
+
+extern "C" int dvgr_bn_fwd(const void* x, int B, int D, const float* gamma, const float* beta, float* run_mean,
+                           float* run_var, int training, float momentum, float eps, void* y, float* mean_out,
+                           float* rstd_out, void* stream) {
+  if (B <= 0 || D <= 0) return 0;
+  bn_fwd_kernel<<<(D + 127) / 128, 128, 0, ST(stream)>>>(CBF(x), B, D, gamma, beta, run_mean, run_var, training,
+                                                        momentum, eps, BF(y), mean_out, rstd_out);
+  DVGR_CHECK_LAUNCH("bn_fwd");
+  return 0;
+}
+extern "C" int dvgr_bn_bwd(const void* dy, const void* x, int B, int D, const float* gamma, const float* mean,
+                           const float* rstd, int training, void* dx, float* dgamma, float* dbeta, void* stream) {
+  if (B <= 0 || D <= 0) return 0;
+  bn_bwd_kernel<<<(D + 127) / 128, 128, 0, ST(stream)>>>(CBF(dy), CBF(x), B, D, gamma, mean, rstd, training, BF(dx),
+                                                        dgamma, dbeta);
+  DVGR_CHECK_LAUNCH("bn_bwd");
+  return 0;
+}
+
+extern "C" int dvgr_cross_entropy(const float* logits, const long long* answers, int B, int A, float scale,
+                                  float* loss_part, void* dlogits, long long ld_d, int* correct, void* stream) {
+  if (B <= 0) return 0;
+  ce_kernel<<<(B + 7) / 8, 256, 0, ST(stream)>>>(logits, answers, B, A, scale, loss_part, BF(dlogits), ld_d, correct);
+  DVGR_CHECK_LAUNCH("cross_entropy");
+  return 0;
+}
+
+extern "C" int dvgr_prep_features(const float* in, void* out, long long S, int T, int C, int do_tanh, int time_major,
+                                  float p, unsigned long long seed, unsigned int drop_stream, void* stream) {
+  if (C % 8 != 0) return set_error("prep_features: C=%d must be a multiple of 8", C);
+  const long long n = S * T * (long long)C / 8;
+  if (n <= 0) return 0;
+  DropoutCfg dc{seed, drop_stream, p};
+  prep_features_kernel<<<grid_for(n, 256, 148 * 32), 256, 0, ST(stream)>>>(in, BF(out), S, T, C, do_tanh, time_major, dc);
+  DVGR_CHECK_LAUNCH("prep_features");
+  return 0;
+}
+
+extern "C" int dvgr_cast_rows(const float* in, long long ld_in, void* out, long long ld_out, int rows, int cols,
+                              int out_cols, int lstm_H, void* stream) {
+  const long long n = (long long)rows * out_cols;
+  if (n <= 0) return 0;
+  if (lstm_H > 0 && rows != 4 * lstm_H) return set_error("cast_rows: rows=%d != 4*H=%d", rows, 4 * lstm_H);
+  cast_rows_kernel<<<grid_for(n), 256, 0, ST(stream)>>>(in, ld_in, BF(out), ld_out, rows, cols, out_cols, lstm_H);
+  DVGR_CHECK_LAUNCH("cast_rows");
+  return 0;
+}
+
+extern "C" int dvgr_dropout(const void* in, void* out, long long n, float p, unsigned long long seed,
+                            unsigned int drop_stream, void* stream) {
+  if (n % 8 != 0) return set_error("dropout: n=%lld must be a multiple of 8", n);
+  if (n <= 0) return 0;
+  DropoutCfg dc{seed, drop_stream, p};
+  dropout_kernel<<<grid_for(n / 8), 256, 0, ST(stream)>>>(CBF(in), BF(out), n / 8, dc);
+  DVGR_CHECK_LAUNCH("dropout");
+  return 0;
+}
+
+extern "C" int dvgr_act_bwd(const void* dy, const void* y, void* out, long long n, int act, int accumulate, float p,
+                            unsigned long long seed, unsigned int drop_stream, void* stream) {
+  if (n % 8 != 0) return set_error("act_bwd: n=%lld must be a multiple of 8", n);
+  if (n <= 0) return 0;
+  DropoutCfg dc{seed, drop_stream, p};
+  act_bwd_kernel<<<grid_for(n / 8), 256, 0, ST(stream)>>>(CBF(dy), CBF(y), BF(out), n / 8, act, accumulate, dc);
+  DVGR_CHECK_LAUNCH("act_bwd");
+  return 0;
+}
+
+extern "C" int dvgr_add(void* a, const void* b, long long n, void* stream) {
+  if (n % 8 != 0) return set_error("add: n=%lld must be a multiple of 8", n);
+  if (n <= 0) return 0;
+  add_kernel<<<grid_for(n / 8), 256, 0, ST(stream)>>>(BF(a), CBF(b), n / 8);
+  DVGR_CHECK_LAUNCH("add");
+  return 0;
+}
+
+extern "C" long long dvgr_colsum_workspace(long long R, int C) {
+  long long chunks = (R + 255) / 256;
+  if (chunks > 128) chunks = 128;
+  if (chunks < 1) chunks = 1;
+  return chunks * C;
+}
+
+extern "C" int dvgr_colsum(const void* in, int in_is_f32, long long ld, long long R, int C, float* workspace, float* out,
+                           int accumulate, float scale, void* stream) {
+  if (C <= 0) return 0;
+  long long chunks = (R + 255) / 256;
+  if (chunks > 128) chunks = 128;
+  if (chunks < 1) chunks = 1;
+  const int rpc = (int)((R + chunks - 1) / chunks);
+  dim3 grid((C + 127) / 128, (unsigned)chunks);
+  if (in_is_f32)
+    colsum_partial_kernel<float><<<grid, 128, 0, ST(stream)>>>(reinterpret_cast<const float*>(in), ld, R, C, rpc, workspace);
+  else
+    colsum_partial_kernel<bf16><<<grid, 128, 0, ST(stream)>>>(CBF(in), ld, R, C, rpc, workspace);
+  DVGR_CHECK_LAUNCH("colsum_partial");
+  colsum_final_kernel<<<(C + 127) / 128, 128, 0, ST(stream)>>>(workspace, (int)chunks, C, out, accumulate, scale);
+  DVGR_CHECK_LAUNCH("colsum_final");
+  return 0;
+}

@@ -1,0 +1,88 @@
+// Flat-buffer optimizer step of the DualVGR train loop: global-norm clipping + Adam in two launches over ONE fp32
+// buffer (the reference walks ~250 parameter tensors: nn.utils.clip_grad_norm_(max_norm=12) + optim.Adam(lr=1e-4),
+// train.py:85,158-159). Matches torch.optim.Adam (no weight decay, no amsgrad) and clip_grad_norm_ (eps 1e-6).
+#include "capi_internal.h"
+#include "ptx.cuh"
+
+namespace dvgr {
+
+__global__ void sumsq_partial_kernel(const float* __restrict__ g, long long n, float* __restrict__ partial) {
+  float acc = 0.f;
+  const long long n4 = n / 4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(g)[i];
+    acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (long long i = n4 * 4; i < n; ++i) acc += g[i] * g[i];
+  acc = warp_sum(acc);
+  __shared__ float red[32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) red[warp] = acc;
+  __syncthreads();
+  if (warp == 0) {
+    float v = lane < (blockDim.x >> 5) ? red[lane] : 0.f;
+    v = warp_sum(v);
+    if (lane == 0) partial[blockIdx.x] = v;
+  }
+}
+__global__ void sumsq_final_kernel(const float* __restrict__ partial, int n, float* __restrict__ out) {
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < n; i += 32) acc += partial[i];
+  acc = warp_sum(acc);
+  if (threadIdx.x == 0) out[0] = acc;
+}
+
+// norm_sq: device scalar = sum of squares of the (already averaged) gradient. grad_scale multiplies g before use.
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, long long n, float lr, float b1, float b2, float eps, float bc1,
+                            float bc2_sqrt, float max_norm, const float* __restrict__ norm_sq, float grad_scale) {
+  float clip = 1.f;
+  if (max_norm > 0.f && norm_sq != nullptr) {
+    const float total = sqrtf(norm_sq[0]) * grad_scale;
+    clip = fminf(1.f, max_norm / (total + 1e-6f));
+  }
+  const float gs = grad_scale * clip;
+  const float step = lr / bc1;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i] * gs;
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] -= step * mi / (sqrtf(vi) / bc2_sqrt + eps);
+  }
+}
+
+}  // namespace dvgr
+
+using namespace dvgr;
+
+extern "C" int dvgr_sumsq_blocks(void) { return 1024; }
+
+extern "C" int dvgr_sumsq(const float* g, long long n, float* partial_ws, float* out, void* stream) {
+  if (n <= 0) return 0;
+  if ((reinterpret_cast<uintptr_t>(g) & 15) != 0) return set_error("sumsq: buffer must be 16-byte aligned");
+  const int blocks = dvgr_sumsq_blocks();
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  sumsq_partial_kernel<<<blocks, 256, 0, st>>>(g, n, partial_ws);
+  DVGR_CHECK_LAUNCH("sumsq_partial");
+  sumsq_final_kernel<<<1, 32, 0, st>>>(partial_ws, blocks, out);
+  DVGR_CHECK_LAUNCH("sumsq_final");
+  return 0;
+}
+
+extern "C" int dvgr_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n,
+                              float lr, float beta1, float beta2, float eps, int step, float max_norm,
+                              const float* norm_sq, float grad_scale, void* stream) {
+  if (n <= 0) return 0;
+  if (step < 1) return set_error("adam: step must be >= 1");
+  const float bc1 = 1.f - powf(beta1, (float)step);
+  const float bc2 = 1.f - powf(beta2, (float)step);
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  adam_kernel<<<(int)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, bc1, sqrtf(bc2), max_norm, norm_sq, grad_scale);
+  DVGR_CHECK_LAUNCH("adam_step");
+  return 0;
+}

@@ -1,0 +1,52 @@
+// Counter-based dropout masks (Philox-4x32-10). A mask element is a pure function of (seed, stream id, element index):
+// the backward kernels regenerate it instead of reading a stored mask.
+#pragma once
+#include <stdint.h>
+
+namespace dvgr {
+
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0;
+    key.y += W1;
+  }
+  return ctr;
+}
+
+struct DropoutCfg {
+  unsigned long long seed;   // per-step seed
+  unsigned int stream;       // distinguishes the dropout sites of one step
+  float p;                   // drop probability; 0 disables
+};
+
+// Keep-scale (0 or 1/(1-p)) for 4 consecutive elements starting at index 4*quad.
+__device__ __forceinline__ void dropout_scale4(const DropoutCfg& c, unsigned long long quad, float (&s)[4]) {
+  if (c.p <= 0.f) {
+    s[0] = s[1] = s[2] = s[3] = 1.f;
+    return;
+  }
+  uint4 r = philox4x32_10(make_uint4((uint32_t)quad, (uint32_t)(quad >> 32), c.stream, 0x2545F491u),
+                          make_uint2((uint32_t)c.seed, (uint32_t)(c.seed >> 32)));
+  const float inv = 1.f / (1.f - c.p);
+  const uint32_t thr = (uint32_t)(c.p * 4294967296.0f);
+  s[0] = r.x >= thr ? inv : 0.f;
+  s[1] = r.y >= thr ? inv : 0.f;
+  s[2] = r.z >= thr ? inv : 0.f;
+  s[3] = r.w >= thr ? inv : 0.f;
+}
+
+// Keep-scale for a single element index (costs a full Philox call; use dropout_scale4 in streaming kernels).
+__device__ __forceinline__ float dropout_scale1(const DropoutCfg& c, unsigned long long idx) {
+  if (c.p <= 0.f) return 1.f;
+  float s[4];
+  dropout_scale4(c, idx >> 2, s);
+  const int k = (int)(idx & 3);
+  return k == 0 ? s[0] : k == 1 ? s[1] : k == 2 ? s[2] : s[3];
+}
+
+}  // namespace dvgr

@@ -170,3 +170,282 @@ def lstm_bwd(gates, whh, h_hist, c_hist, dh_last, seq_len=None, dh_seq=None):
         a.s = s
         _lib.check(_lib.lstm_step_bwd(ctypes.byref(a), st), "dvgr_lstm_step_bwd")
     return gates
+
+
+# ======================================================================================================================
+# raw wrappers of the fused kernels (used directly by the per-kernel parity tests, and by the autograd layer below)
+# ======================================================================================================================
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+def _empty(shape, dtype, like):
+    return torch.empty(shape, dtype=dtype, device=like.device)
+
+
+def colsum(x, out=None, accumulate=False, scale=1.0):
+    """out[C] (+)= scale * sum over rows of x[R, C] (bf16 or fp32, last dim contiguous)."""
+    assert x.dim() == 2 and x.stride(1) == 1
+    R, C = x.shape
+    ws = _empty((int(_lib.lib.dvgr_colsum_workspace(R, C)),), F32, x)
+    if out is None:
+        out = _empty((C,), F32, x)
+    _lib.check(_lib.colsum(_ptr(x), 1 if x.dtype == F32 else 0, x.stride(0), R, C, _ptr(ws), _ptr(out),
+                           1 if accumulate else 0, float(scale), _stream()), "dvgr_colsum")
+    return out
+
+
+def cast_rows(w, out=None, out_cols=None, lstm_H=0):
+    """fp32 [R, C] -> bf16 [R, out_cols] (zero padded); lstm_H>0 interleaves LSTM gate rows (4j+g <- g*H+j)."""
+    assert w.dtype == F32 and w.dim() == 2 and w.stride(1) == 1
+    R, C = w.shape
+    oc = out_cols or C
+    if out is None:
+        out = _empty((R, oc), BF16, w)
+    assert out.stride(1) == 1
+    _lib.check(_lib.cast_rows(_ptr(w), w.stride(0), _ptr(out), out.stride(0), R, C, oc, lstm_H, _stream()), "dvgr_cast_rows")
+    return out
+
+
+def prep_features(x, T, do_tanh, time_major, p=0.0, seed=0, stream_id=0):
+    """x fp32 [S*T, C] (S sequences of T steps) -> bf16 [T*S, C] (time_major) / [S*T, C]: tanh(dropout(x)) in one pass."""
+    assert x.dtype == F32 and x.is_contiguous()
+    C = x.shape[-1]
+    rows = x.numel() // C
+    S = rows // T
+    out = _empty((rows, C), BF16, x)
+    _lib.check(_lib.prep_features(_ptr(x), _ptr(out), S, T, C, 1 if do_tanh else 0, 1 if time_major else 0, float(p),
+                                  int(seed), int(stream_id), _stream()), "dvgr_prep_features")
+    return out
+
+
+def dropout_raw(x, p, seed, stream_id, out=None):
+    assert x.dtype == BF16 and x.is_contiguous()
+    if out is None:
+        out = torch.empty_like(x)
+    _lib.check(_lib.dropout(_ptr(x), _ptr(out), x.numel(), float(p), int(seed), int(stream_id), _stream()), "dvgr_dropout")
+    return out
+
+
+def act_bwd(dy, y, act, out=None, accumulate=False, p=0.0, seed=0, stream_id=0):
+    """out (+)= dy * dropout_mask * act'(y) with y the activation output."""
+    assert dy.dtype == BF16 and dy.is_contiguous()
+    if out is None:
+        out = torch.empty_like(dy)
+    a = _ACT[act] if not isinstance(act, int) else act
+    _lib.check(_lib.act_bwd(_ptr(dy), _ptr(y) if y is not None else _ptr(dy), _ptr(out), dy.numel(), a,
+                            1 if accumulate else 0, float(p), int(seed), int(stream_id), _stream()), "dvgr_act_bwd")
+    return out
+
+
+def add_(a, b):
+    assert a.dtype == BF16 and b.dtype == BF16 and a.is_contiguous() and b.is_contiguous() and a.numel() == b.numel()
+    _lib.check(_lib.add(_ptr(a), _ptr(b), a.numel(), _stream()), "dvgr_add")
+    return a
+
+
+def qattn_fwd(y, wf, cf, qlen, words, W, ld_qc):
+    B, L, D = y.shape
+    alpha, nrm, prob = (_empty((B, L), F32, y) for _ in range(3))
+    ssum = _empty((B,), F32, y)
+    qc = _empty((B, ld_qc), BF16, y)
+    _lib.check(_lib.qattn_fwd(_ptr(y), _ptr(wf), _ptr(cf), _ptr(qlen), _ptr(words), words.stride(1), B, L, D, W,
+                              _ptr(alpha), _ptr(nrm), _ptr(prob), _ptr(ssum), _ptr(qc), ld_qc, _stream()), "dvgr_qattn_fwd")
+    return qc, alpha, nrm, prob, ssum
+
+
+def qattn_bwd(dqc, y, wf, qlen, words, W, alpha, nrm, prob, ssum, dwords=None):
+    B, L, D = y.shape
+    dy = torch.empty_like(y)
+    acc = dwords is not None
+    if dwords is None:
+        dwords = torch.zeros_like(words)
+    dwf_part = _empty((B, D), F32, y)
+    dcf_part = _empty((B, 1), F32, y)
+    _lib.check(_lib.qattn_bwd(_ptr(dqc), dqc.stride(0), _ptr(y), _ptr(wf), _ptr(qlen), _ptr(words), words.stride(1), B, L,
+                              D, W, _ptr(alpha), _ptr(nrm), _ptr(prob), _ptr(ssum), _ptr(dy), _ptr(dwords),
+                              1 if acc else 0, _ptr(dwf_part), _ptr(dcf_part), _stream()), "dvgr_qattn_bwd")
+    return dy, dwords, colsum(dwf_part), colsum(dcf_part)
+
+
+def gate_fwd(xa, xm, query):
+    B, N, D = xa.shape
+    ga, gm = _empty((B, N), F32, xa), _empty((B, N), F32, xa)
+    _lib.check(_lib.gate_fwd(_ptr(xa), _ptr(xm), _ptr(query), query.stride(0), B, N, D, _ptr(ga), _ptr(gm), _stream()),
+               "dvgr_gate_fwd")
+    return ga, gm
+
+
+def gate_bwd(xa, xm, query, ga, gm, dga, dga2, dgm, dgm2, dxa, dxm):
+    """dxa / dxm are accumulated into; returns dquery [B, ld_q]."""
+    B, N, D = xa.shape
+    dquery = torch.empty_like(query)
+    _lib.check(_lib.gate_bwd(_ptr(xa), _ptr(xm), _ptr(query), query.stride(0), B, N, D, _ptr(ga), _ptr(gm), _ptr(dga),
+                             _ptr(dga2), _ptr(dgm), _ptr(dgm2), _ptr(dxa), _ptr(dxm), _ptr(dquery), _stream()),
+               "dvgr_gate_bwd")
+    return dquery
+
+
+def _gat_args(whs, gates, avecs, outs, adj, B, N, D, heads, slope, p_att, p_out, seed, streams):
+    a = _lib.GatArgs()
+    a.n_graphs = len(whs)
+    a.B, a.N, a.D, a.heads = B, N, D, heads
+    a.ld_wh, a.ld_out = whs[0].stride(-2), outs[0].stride(-2)
+    a.adj = adj.data_ptr()
+    a.slope, a.p_att, a.p_out, a.seed = slope, p_att, p_out, seed
+    for i in range(len(whs)):
+        g = a.graphs[i]
+        g.wh, g.gate, g.avec, g.out = whs[i].data_ptr(), gates[i].data_ptr(), avecs[i].data_ptr(), outs[i].data_ptr()
+        g.drop_stream = streams[i]
+    return a
+
+
+def gat_attn_fwd(whs, gates, avecs, adj, B, N, heads=4, slope=0.01, p_att=0.0, p_out=0.0, seed=0, streams=None,
+                 outs=None, want_f32=False):
+    """whs: list of [B*N, D] bf16 (row stride free), gates: list of [B, N] f32, avecs: list of [heads, 2*Dh+1] f32."""
+    D = whs[0].shape[-1]
+    G = len(whs)
+    streams = streams or [2 * i for i in range(G)]
+    if outs is None:
+        outs = [_empty((B * N, D), BF16, whs[0]) for _ in range(G)]
+    a = _gat_args(whs, gates, avecs, outs, adj, B, N, D, heads, slope, p_att, p_out, seed, streams)
+    outs32 = None
+    if want_f32:
+        outs32 = [_empty((B, N, D), F32, whs[0]) for _ in range(G)]
+        for i in range(G):
+            a.graphs[i].out_f32 = outs32[i].data_ptr()
+    _lib.check(_lib.gat_attn_fwd(ctypes.byref(a), _stream()), "dvgr_gat_attn_fwd")
+    return outs, outs32
+
+
+def gat_attn_bwd(whs, gates, avecs, outs, douts, adj, B, N, heads=4, slope=0.01, p_att=0.0, p_out=0.0, seed=0,
+                 streams=None, douts32=None):
+    D = whs[0].shape[-1]
+    G = len(whs)
+    Dh = D // heads
+    streams = streams or [2 * i for i in range(G)]
+    a = _gat_args(whs, gates, avecs, outs, adj, B, N, D, heads, slope, p_att, p_out, seed, streams)
+    dwhs = [torch.empty_like(w) for w in whs]
+    dgates = [_empty((B, N), F32, whs[0]) for _ in range(G)]
+    dav_part = [_empty((B, heads * (2 * Dh + 1)), F32, whs[0]) for _ in range(G)]
+    for i in range(G):
+        g = a.graphs[i]
+        assert dwhs[i].stride(-2) == whs[i].stride(-2) and douts[i].stride(-2) == outs[i].stride(-2)
+        g.dout, g.dwh, g.dgate, g.davec = douts[i].data_ptr(), dwhs[i].data_ptr(), dgates[i].data_ptr(), dav_part[i].data_ptr()
+        if douts32 is not None and douts32[i] is not None:
+            g.dout_f32 = douts32[i].data_ptr()
+    _lib.check(_lib.gat_attn_bwd(ctypes.byref(a), _stream()), "dvgr_gat_attn_bwd")
+    davecs = [colsum(p).view(heads, 2 * Dh + 1) for p in dav_part]
+    return dwhs, dgates, davecs
+
+
+def view_attn_fwd(hidden, z, x, w2, want_embed=True):
+    """hidden, z: [2, M, D] bf16; x [M, D] bf16; w2 [D] f32."""
+    _, M, D = z.shape
+    xnew = torch.empty_like(x)
+    embed = torch.empty_like(x) if want_embed else None
+    beta = _empty((M, 2), F32, x)
+    _lib.check(_lib.view_attn_fwd(_ptr(hidden), _ptr(z), _ptr(x), _ptr(w2), M, D, _ptr(xnew), _ptr(embed), _ptr(beta),
+                                  _stream()), "dvgr_view_attn_fwd")
+    return xnew, embed, beta
+
+
+def view_attn_bwd(dxnew, dembed, hidden, z, w2, beta):
+    _, M, D = z.shape
+    dz, dhid = torch.empty_like(z), torch.empty_like(hidden)
+    blocks = int(_lib.lib.dvgr_view_attn_bwd_blocks(M))
+    part = _empty((blocks, D), F32, z)
+    _lib.check(_lib.view_attn_bwd(_ptr(dxnew), _ptr(dembed), _ptr(hidden), _ptr(z), _ptr(w2), _ptr(beta), M, D, _ptr(dz),
+                                  _ptr(dhid), _ptr(part), _stream()), "dvgr_view_attn_bwd")
+    return dz, dhid, colsum(part)
+
+
+def mfb_fwd(x0, x1):
+    M, mm2 = x0.shape
+    z = _empty((M, mm2 // 2), BF16, x0)
+    _lib.check(_lib.mfb_fwd(_ptr(x0), _ptr(x1), _ptr(z), M, mm2, _stream()), "dvgr_mfb_fwd")
+    return z
+
+
+def mfb_bwd(dz, x0, x1):
+    M, mm2 = x0.shape
+    d0, d1 = torch.empty_like(x0), torch.empty_like(x1)
+    _lib.check(_lib.mfb_bwd(_ptr(dz), _ptr(x0), _ptr(x1), _ptr(d0), _ptr(d1), M, mm2, _stream()), "dvgr_mfb_bwd")
+    return d0, d1
+
+
+def readout_fwd(v, u, w, c, pooled=None):
+    B, N, D = v.shape
+    alpha = _empty((B, N), F32, v)
+    if pooled is None:
+        pooled = _empty((B, D), BF16, v)
+    _lib.check(_lib.readout_fwd(_ptr(v), _ptr(u), _ptr(w), _ptr(c), B, N, D, _ptr(alpha), _ptr(pooled), pooled.stride(0),
+                                _stream()), "dvgr_readout_fwd")
+    return pooled, alpha
+
+
+def readout_bwd(dpooled, v, u, w, alpha):
+    B, N, D = v.shape
+    dv, du = torch.empty_like(v), torch.empty_like(u)
+    dw_part, dc_part = _empty((B, D), F32, v), _empty((B, 1), F32, v)
+    _lib.check(_lib.readout_bwd(_ptr(dpooled), dpooled.stride(0), _ptr(v), _ptr(u), _ptr(w), _ptr(alpha), B, N, D, _ptr(dv),
+                                _ptr(du), _ptr(dw_part), _ptr(dc_part), _stream()), "dvgr_readout_bwd")
+    return dv, du, colsum(dw_part), colsum(dc_part)
+
+
+def bn_fwd(x, gamma, beta, run_mean, run_var, training, momentum=0.1, eps=1e-5):
+    B, D = x.shape
+    y = torch.empty_like(x)
+    mean, rstd = _empty((D,), F32, x), _empty((D,), F32, x)
+    _lib.check(_lib.bn_fwd(_ptr(x), B, D, _ptr(gamma), _ptr(beta), _ptr(run_mean), _ptr(run_var), 1 if training else 0,
+                           momentum, eps, _ptr(y), _ptr(mean), _ptr(rstd), _stream()), "dvgr_bn_fwd")
+    return y, mean, rstd
+
+
+def bn_bwd(dy, x, gamma, mean, rstd, training):
+    B, D = x.shape
+    dx = torch.empty_like(x)
+    dgamma, dbeta = _empty((D,), F32, x), _empty((D,), F32, x)
+    _lib.check(_lib.bn_bwd(_ptr(dy), _ptr(x), B, D, _ptr(gamma), _ptr(mean), _ptr(rstd), 1 if training else 0, _ptr(dx),
+                           _ptr(dgamma), _ptr(dbeta), _stream()), "dvgr_bn_bwd")
+    return dx, dgamma, dbeta
+
+
+def cross_entropy(logits, answers, scale=1.0, want_grad=True):
+    """Mean CE over the batch. Returns (loss scalar tensor, dlogits [B, A8] bf16 (A padded to 8), correct [B] int32)."""
+    B, A = logits.shape
+    assert logits.dtype == F32 and logits.is_contiguous() and answers.dtype == torch.int64
+    A8 = (A + 7) // 8 * 8
+    part = _empty((B, 1), F32, logits)
+    dlog = _empty((B, A8), BF16, logits) if want_grad else None
+    correct = torch.empty((B,), dtype=torch.int32, device=logits.device)
+    _lib.check(_lib.cross_entropy(_ptr(logits), _ptr(answers), B, A, float(scale), _ptr(part), _ptr(dlog), A8,
+                                  _ptr(correct), _stream()), "dvgr_cross_entropy")
+    return colsum(part)[0], dlog, correct
+
+
+def pair_loss(x, y, mode, coef, dx=None, dy=None, want_grad=True):
+    """mode 0: coef * sum (G_x - G_y)^2 ; mode 1: coef * HSIC. x, y fp32 [B, N, D]. dx / dy given => accumulated into.
+    Returns (loss scalar tensor, dx, dy)."""
+    B, N, D = x.shape
+    assert x.dtype == F32 and y.dtype == F32 and x.is_contiguous() and y.is_contiguous()
+    part = _empty((B, 1), F32, x)
+    accx, accy = dx is not None, dy is not None
+    if want_grad:
+        dx = dx if accx else torch.empty_like(x)
+        dy = dy if accy else torch.empty_like(y)
+    _lib.check(_lib.pair_loss(_ptr(x), _ptr(y), B, N, D, mode, float(coef), _ptr(part), _ptr(dx) if want_grad else None,
+                              _ptr(dy) if want_grad else None, 1 if accx else 0, 1 if accy else 0, _stream()),
+               "dvgr_pair_loss")
+    return colsum(part)[0], dx, dy
+
+
+def sumsq(g):
+    ws = _empty((int(_lib.lib.dvgr_sumsq_blocks()),), F32, g)
+    out = _empty((1,), F32, g)
+    _lib.check(_lib.sumsq(_ptr(g), g.numel(), _ptr(ws), _ptr(out), _stream()), "dvgr_sumsq")
+    return out
+
+
+def adam_step(p, g, m, v, lr, step, beta1=0.9, beta2=0.999, eps=1e-8, max_norm=0.0, norm_sq=None, grad_scale=1.0):
+    _lib.check(_lib.adam_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), lr, beta1, beta2, eps, step, max_norm,
+                              _ptr(norm_sq), grad_scale, _stream()), "dvgr_adam_step")

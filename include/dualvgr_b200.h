@@ -108,6 +108,139 @@ int dvgr_lstm_step_fwd(const dvgr_lstm_args* args, void* stream);
 /* Backward of step s; must be called for s = T-1, T-2, ..., 0. */
 int dvgr_lstm_step_bwd(const dvgr_lstm_args* args, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Video-based multi-view graph attention (punishGAT): model/GraphNN.py:95-113 for all heads of a graph, plus the head
+ * concat and the attention / output dropouts of :107,:175-177. Up to 4 graphs per launch (acGCN, appearance_GCN, mcGCN,
+ * motion_GCN of one DualVGR unit, model/models.py:151-158); one CTA per (video, graph), node block staged in shared memory.
+ *   wh    [B*N][ld_wh] bf16 : W_k x + b_k of the graph's heads, concatenated along columns (from dvgr_gemm)
+ *   gate  [B][N] f32        : QueryPunish gate of the stream (applied to the values only, after the logits)
+ *   avec  [heads][2*Dh+1] f32 : a_k[:Dh] | a_k[Dh:] | c_k   (attention_k.a.weight, attention_k.a.bias)
+ *   adj   [N][N] f32        : edge iff adj > 0 (a fully masked row yields uniform attention, as in the reference)
+ *   out   [B*N][ld_out] bf16
+ * Backward additionally needs out (forward result), dout, and writes dwh, dgate [B][N], davec partials [B][heads][2*Dh+1]
+ * (sum over B with dvgr_colsum).
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct dvgr_gat_graph {
+  const void* wh;
+  const float* gate;
+  const float* avec;
+  void* out;
+  float* out_f32;           /* optional dense [B*N][D] f32 copy of out (what the auxiliary losses read) */
+  const void* dout;
+  const float* dout_f32;    /* optional extra gradient on the f32 copy */
+  void* dwh;
+  float* dgate;
+  float* davec;
+  unsigned int drop_stream;
+} dvgr_gat_graph;
+
+typedef struct dvgr_gat_args {
+  dvgr_gat_graph graphs[4];
+  int n_graphs;
+  int B, N, D, heads;
+  long long ld_wh, ld_out;
+  const float* adj;
+  float slope;              /* LeakyReLU slope, 0.01 in the reference (model/models.py:95) */
+  float p_att, p_out;       /* dropout probabilities; 0 = eval / parity mode */
+  unsigned long long seed;
+} dvgr_gat_args;
+
+int dvgr_gat_attn_fwd(const dvgr_gat_args* args, void* stream);
+int dvgr_gat_attn_bwd(const dvgr_gat_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Query Punishment Module (model/utils.py:60-105).
+ * dvgr_qattn_fwd: QueryAttn.forward tail (model/utils.py:68-84) given y = feat_enhance(dynamic_q) [B][L][D] bf16 from
+ *   dvgr_gemm: L2-normalise, fc score, softmax over ALL L positions, question_len mask (no per-sample host loop),
+ *   renormalise (eps 1e-5), q_c = alpha . words.   Saves alpha, nrm, prob [B][L] and ssum [B] for backward.
+ *   words [B][L][ld_w] bf16; qc [B][ld_qc] bf16 (columns W..ld_qc-1 zeroed: it is the K-padded A operand of the
+ *   QueryPunish.query_weight GEMM, model/utils.py:100).
+ * dvgr_gate_fwd: QueryPunish.forward tail (model/utils.py:101-103): gate[b][n] = sigmoid(X[b][n] . query[b]) for the
+ *   appearance (x0 / columns 0..D-1 of query) and motion (x1 / columns D..2D-1) streams in one launch.
+ * ------------------------------------------------------------------------------------------------------------------ */
+int dvgr_qattn_fwd(const void* y, const float* wf, const float* cf, const int* qlen, const void* words, long long ld_w,
+                   int B, int L, int D, int W, float* alpha, float* nrm, float* prob, float* ssum, void* qc,
+                   long long ld_qc, void* stream);
+/* dy [B][L][D] bf16, dwords [B][L][ld_w] bf16 (+= when accumulate_dwords), dwf_part [B][D], dcf_part [B] (sum over B). */
+int dvgr_qattn_bwd(const void* dqc, long long ld_qc, const void* y, const float* wf, const int* qlen, const void* words,
+                   long long ld_w, int B, int L, int D, int W, const float* alpha, const float* nrm, const float* prob,
+                   const float* ssum, void* dy, void* dwords, int accumulate_dwords, float* dwf_part, float* dcf_part,
+                   void* stream);
+int dvgr_gate_fwd(const void* x0, const void* x1, const void* query, long long ld_q, int B, int N, int D, float* gate0,
+                  float* gate1, void* stream);
+/* dgate of stream s = dg{s}a (+ dg{s}b: the two graphs sharing the gate, model/models.py:151-158).
+ * dx{s} [B][N][D] bf16 is ACCUMULATED into; dquery [B][ld_q] bf16 is written. */
+int dvgr_gate_bwd(const void* x0, const void* x1, const void* query, long long ld_q, int B, int N, int D,
+                  const float* gate0, const float* gate1, const float* dg0a, const float* dg0b, const float* dg1a,
+                  const float* dg1b, void* dx0, void* dx1, void* dquery, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Two-view attention + residual: AttentionSFGCN.forward (model/Attention.py:20-23) on the [common, specific] stack of
+ * model/models.py:163-166 and the residual add of :168-169.
+ *   hidden [2][M][D] bf16 = tanh(project.0(z)) from dvgr_gemm (tanh epilogue); z [2][M][D] bf16; x [M][D] bf16
+ *   xnew = x + sum_v beta_v z_v ; embed (optional) = sum_v beta_v z_v ; beta [M][2] f32
+ * Backward: dxnew is also the gradient of x (residual) — the caller keeps accumulating into that buffer.
+ *   dz [2][M][D], dhid [2][M][D] (tanh' applied: feeds the project.0 dgrad/wgrad), dw2_part [dvgr_view_attn_bwd_blocks(M)][D]
+ * ------------------------------------------------------------------------------------------------------------------ */
+int dvgr_view_attn_fwd(const void* hidden, const void* z, const void* x, const float* w2, long long M, int D, void* xnew,
+                       void* embed, float* beta, void* stream);
+int dvgr_view_attn_bwd_blocks(long long M);
+int dvgr_view_attn_bwd(const void* dxnew, const void* dembed_ext, const void* hidden, const void* z, const float* w2,
+                       const float* beta, long long M, int D, void* dz, void* dhid, float* dw2_part, void* stream);
+
+/* MFB pair-sum (model/fusions/fusions.py:433-441): z[M][mm2/2] = pairsum(x0 * x1), x0/x1 [M][mm2] already ELU'd. */
+int dvgr_mfb_fwd(const void* x0, const void* x1, void* z, long long M, int mm2, void* stream);
+int dvgr_mfb_bwd(const void* dz, const void* x0, const void* x1, void* d0, void* d1, long long M, int mm2, void* stream);
+
+/* Attention read-out (model/AnswerDecoder.py:176-180): alpha = softmax_n(w . u_n + c), pooled[b] = sum_n alpha_n v_n,
+ * u = ELU(v_proj(v)) from dvgr_gemm; pooled is written with row stride ld_p (left half of the classifier input). */
+int dvgr_readout_fwd(const void* v, const void* u, const float* w, const float* c, int B, int N, int D, float* alpha,
+                     void* pooled, long long ld_p, void* stream);
+int dvgr_readout_bwd(const void* dpooled, long long ld_p, const void* v, const void* u, const float* w,
+                     const float* alpha, int B, int N, int D, void* dv, void* du, float* dw_part, float* dc_part,
+                     void* stream);
+
+/* BatchNorm1d of the classifier (model/AnswerDecoder.py:193), x/y [B][D] bf16. */
+int dvgr_bn_fwd(const void* x, int B, int D, const float* gamma, const float* beta, float* run_mean, float* run_var,
+                int training, float momentum, float eps, void* y, float* mean_out, float* rstd_out, void* stream);
+int dvgr_bn_bwd(const void* dy, const void* x, int B, int D, const float* gamma, const float* mean, const float* rstd,
+                int training, void* dx, float* dgamma, float* dbeta, void* stream);
+
+/* nn.CrossEntropyLoss (train.py:121,146) value + gradient: loss_part[b] (sum = mean CE), dlogits [B][ld_d] bf16 =
+ * (softmax - onehot) * scale / B with zeroed padding columns, correct[b] = argmax == answer (train.py:352-356). */
+int dvgr_cross_entropy(const float* logits, const long long* answers, int B, int A, float scale, float* loss_part,
+                       void* dlogits, long long ld_d, int* correct, void* stream);
+
+/* Auxiliary losses (utils.py:10-31), value and gradient fused per video. x, y, dx, dy are [B][N][D] f32.
+ * mode 0: common_loss term  coef * sum_ij (G_x - G_y)^2 ; mode 1: HSIC  coef * tr(R K_x R K_y). */
+int dvgr_pair_loss(const float* x, const float* y, int B, int N, int D, int mode, float coef, float* loss_part,
+                   float* dx, float* dy, int accumulate_x, int accumulate_y, void* stream);
+
+/* Streaming helpers.
+ * dvgr_prep_features: model/Preprocessing.py:220-223 — tanh(dropout(x)), fp32 -> bf16, [S][T][C] -> [T][S][C] in one pass.
+ * dvgr_cast_rows: fp32 parameter -> bf16 GEMM operand (zero-padded columns; lstm_H > 0 interleaves LSTM gate rows).
+ * dvgr_dropout: out = in * mask/(1-p) (its own backward). dvgr_act_bwd: out (+)= dy * mask * act'(y).
+ * dvgr_colsum: out[C] (+)= scale * sum_r in[r][c] (bias gradients, per-video partial reductions); deterministic. */
+int dvgr_prep_features(const float* in, void* out, long long S, int T, int C, int do_tanh, int time_major, float p,
+                       unsigned long long seed, unsigned int drop_stream, void* stream);
+int dvgr_cast_rows(const float* in, long long ld_in, void* out, long long ld_out, int rows, int cols, int out_cols,
+                   int lstm_H, void* stream);
+int dvgr_dropout(const void* in, void* out, long long n, float p, unsigned long long seed, unsigned int drop_stream,
+                 void* stream);
+int dvgr_act_bwd(const void* dy, const void* y, void* out, long long n, int act, int accumulate, float p,
+                 unsigned long long seed, unsigned int drop_stream, void* stream);
+int dvgr_add(void* a, const void* b, long long n, void* stream);
+long long dvgr_colsum_workspace(long long R, int C);
+int dvgr_colsum(const void* in, int in_is_f32, long long ld, long long R, int C, float* workspace, float* out,
+                int accumulate, float scale, void* stream);
+
+/* Flat-buffer optimizer (train.py:85,158-159): sum of squares for clip_grad_norm_(12), then Adam with the clip folded in. */
+int dvgr_sumsq_blocks(void);
+int dvgr_sumsq(const float* g, long long n, float* partial_ws, float* out, void* stream);
+int dvgr_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr,
+                   float beta1, float beta2, float eps, int step, float max_norm, const float* norm_sq,
+                   float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,447 @@
+"""torch.autograd.Function wrappers: each pairs a forward and a backward entry point of the C ABI so that the nn.Module
+mirror in ``model/`` trains through ``loss.backward()`` exactly like the reference. PyTorch only routes tensors here
+(allocation, views, concatenation of tiny parameter vectors); all arithmetic of the hot path is in the library."""
+import torch
+from torch.autograd import Function
+
+from . import ops
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+# ---------------------------------------------------------------------------------------------------------------------
+# dropout bookkeeping: one seed per forward pass, one stream id per dropout site (regenerated, never stored)
+# ---------------------------------------------------------------------------------------------------------------------
+_rng = {"seed": 0x5EED, "site": 0, "epoch": 0}
+
+
+def begin_forward():
+    """Called by DualVGR.forward: new seed for this pass, site counter reset."""
+    _rng["seed"] = (int(torch.initial_seed()) * 1000003 + _rng["epoch"] * 7919 + 12345) & 0x7FFFFFFFFFFFFFFF
+    _rng["epoch"] += 1
+    _rng["site"] = 0
+
+
+def _site(n=1):
+    s = _rng["site"]
+    _rng["site"] += n
+    return _rng["seed"], s
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# bf16 operand cache for fp32 parameters (re-cast only when the parameter changed)
+# ---------------------------------------------------------------------------------------------------------------------
+_wcache = {}
+_wepoch = [0]
+
+
+def invalidate_weight_cache():
+    """The flat-buffer optimizer updates parameters behind autograd's version counters: it calls this after a step."""
+    _wepoch[0] += 1
+
+
+def _versions(params):
+    return tuple((p.data_ptr(), p._version) for p in params) + (_wepoch[0],)
+
+
+def bf16_rows(params, out_cols=None, lstm_H=0, tag=""):
+    """bf16 operand made of the row-wise concatenation of fp32 matrices `params` (all [r_i, C])."""
+    key = (tag, tuple((p.data_ptr(), tuple(p.shape)) for p in params), out_cols, lstm_H)
+    ver = _versions(params)
+    ent = _wcache.get(key)
+    if ent is not None and ent[0] == ver:
+        return ent[1]
+    C = params[0].shape[1]
+    oc = out_cols or C
+    rows = sum(p.shape[0] for p in params)
+    buf = ent[1] if ent is not None else torch.empty((rows, oc), dtype=BF16, device=params[0].device)
+    r = 0
+    with torch.no_grad():
+        for p in params:
+            ops.cast_rows(p.detach(), out=buf[r:r + p.shape[0]], out_cols=oc, lstm_H=lstm_H)
+            r += p.shape[0]
+    _wcache[key] = (ver, buf)
+    return buf
+
+
+def _c(t):
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+class LinearFn(Function):
+    """y = act(x W^T + b) on the tcgen05 GEMM; backward = activation', dgrad (W read MN-major), wgrad, bias column-sum.
+    x: [..., K'] bf16 with K' >= K (zero padded to a multiple of 8); W fp32 [N, K]; output bf16 (or fp32: the logits)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, act, out_f32, act_grad_folded=False):
+        Kp = x.shape[-1]
+        x2 = _c(x.reshape(-1, Kp))
+        w = bf16_rows([weight], out_cols=Kp)
+        y = ops.linear_fwd(x2, w, bias=bias, act=act, out_dtype=F32 if out_f32 else BF16)
+        ctx.save_for_backward(x2, w, y if (act not in (None, "none") and not act_grad_folded) else None)
+        ctx.act, ctx.out_f32, ctx.lead, ctx.K, ctx.has_bias = act, out_f32, x.shape[:-1], weight.shape[1], bias is not None
+        return y.view(*x.shape[:-1], weight.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w, y = ctx.saved_tensors
+        N = w.shape[0]
+        M = x2.shape[0]
+        if ctx.out_f32:
+            N8 = (N + 7) // 8 * 8
+            d = torch.zeros((M, N8), dtype=BF16, device=dy.device)
+            d[:, :N] = dy.reshape(M, N)
+        else:
+            d = _c(dy.reshape(M, N))
+            if d.dtype != BF16:
+                d = d.to(BF16)
+        if y is not None:
+            d = ops.act_bwd(d, y, ctx.act)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = ops.linear_dgrad(d, w).view(*ctx.lead, w.shape[1])
+        if ctx.needs_input_grad[1]:
+            dw = ops.linear_wgrad(d, x2)[:N, :ctx.K]
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = ops.colsum(d)[:N]
+        return dx, dw, db, None, None, None
+
+
+def linear(x, weight, bias=None, act=None, out_f32=False, act_grad_folded=False):
+    """act_grad_folded: the consumer's backward kernel already returns d(pre-activation) (view attention, MFB pair-sum,
+    read-out fold act' into their own pass), so this backward must not apply act' again."""
+    return LinearFn.apply(x, weight, bias, act, out_f32, act_grad_folded)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+class DropoutFn(Function):
+    @staticmethod
+    def forward(ctx, x, p):
+        ctx.p = p
+        ctx.seed, ctx.sid = _site()
+        return ops.dropout_raw(_c(x), p, ctx.seed, ctx.sid).view_as(x)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return ops.dropout_raw(_c(dy), ctx.p, ctx.seed, ctx.sid).view_as(dy), None
+
+
+def dropout(x, p, training):
+    return DropoutFn.apply(x, p) if (training and p > 0) else x
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def _lstm_unmap(H, ndir, device):
+    """row_map for gate-interleaved rows -> nn.LSTM row order: interleaved row d*4H + 4j + g -> d*4H + g*H + j."""
+    r = torch.arange(ndir * 4 * H, device=device)
+    d, rr = r // (4 * H), r % (4 * H)
+    return (d * 4 * H + (rr % 4) * H + rr // 4).to(torch.int32)
+
+
+class AppearanceEncoderFn(Function):
+    """VisualAppearanceEncoder.forward (reference model/Preprocessing.py:209-234): prologue pass, ONE tcgen05 GEMM for the
+    input-to-hidden product of both directions (N = 8H), T fused recurrent steps, final dropout."""
+
+    @staticmethod
+    def forward(ctx, app, w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r, p_in, p_out, training):
+        B, N, T, Dv = app.shape
+        S, H = B * N, w_hh.shape[1]
+        seed, sid = _site(2)
+        xa = ops.prep_features(_c(app).view(S * T, Dv), T, True, True, p_in if training else 0.0, seed, sid)
+        wih = _lstm_weight([w_ih, w_ih_r], H, "ih")
+        whh = _lstm_weight([w_hh, w_hh_r], H, "hh").view(2, 4 * H, H)
+        bias = torch.cat([(b_ih + b_hh).view(4, H).t().reshape(-1), (b_ih_r + b_hh_r).view(4, H).t().reshape(-1)]).detach()
+        gates = ops.linear_fwd(xa, wih, bias=bias, bn=256).view(T, S, 8 * H)
+        h_hist, c_hist, h_last, _ = ops.lstm_fwd(gates, whh)
+        out = h_last
+        p_o = p_out if training else 0.0
+        if p_o > 0:
+            out = ops.dropout_raw(h_last, p_o, seed, sid + 1)
+        ctx.save_for_backward(xa, whh, gates, h_hist, c_hist)
+        ctx.cfg = (B, N, T, Dv, S, H, p_o, seed, sid)
+        return out.view(B, N, 2 * H)
+
+    @staticmethod
+    def backward(ctx, dout):
+        xa, whh, gates, h_hist, c_hist = ctx.saved_tensors
+        B, N, T, Dv, S, H, p_o, seed, sid = ctx.cfg
+        dh = _c(dout.reshape(S, 2 * H))
+        if p_o > 0:
+            dh = ops.dropout_raw(dh, p_o, seed, sid + 1)
+        ops.lstm_bwd(gates, whh, h_hist, c_hist, dh)            # gates now holds d(pre-activation gates)
+        dg = gates.view(T * S, 8 * H)
+        unmap = _lstm_unmap(H, 2, dg.device)
+        dwih = ops.linear_wgrad(dg, xa, row_map=unmap, bn=256)  # [8H, Dv] fp32 in nn.LSTM row order
+        db = torch.empty(8 * H, dtype=F32, device=dg.device)
+        db[unmap.long()] = ops.colsum(dg)
+        # dW_hh[d] = sum_s dgates[t_d(s)]^T h_hist[d][s]   (segmented MN-major reduction, both directions in one launch)
+        kin = (S + 63) // 64
+        dwhh = torch.empty((2, 4 * H, H), dtype=F32, device=dg.device)
+        ops.gemm(gates, 1, h_hist, 1, 4 * H, H, T * kin * 64, dwhh, ldc=H, batch=2, c_batch=4 * H * H,
+                 row_map=_lstm_unmap(H, 1, dg.device), a_c0=[0, 4 * H], a_c2=[0, T - 1], a_c2_step=[1, -1],
+                 b_c2=[0, 0], b_c2_step=[1, 1], b_c3=[0, 1], k_inner=kin)
+        return (None, dwih[:4 * H], dwhh[0], db[:4 * H], db[:4 * H], dwih[4 * H:], dwhh[1], db[4 * H:], db[4 * H:],
+                None, None, None)
+
+
+def _lstm_weight(params, H, tag):
+    return bf16_rows(params, lstm_H=H, tag="lstm_" + tag)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+class QAttnFn(Function):
+    """QueryAttn.forward after feat_enhance (reference model/utils.py:68-84). y [B,L,D] bf16, words [B,L,Wp] bf16
+    (zero padded to Wp), qlen int32. Returns q_c [B, Wp] bf16 (zero padded) and alpha [B, L] fp32 (not differentiated)."""
+
+    @staticmethod
+    def forward(ctx, y, words, qlen, fc_w, fc_b, W):
+        y, words = _c(y), _c(words)
+        wf = _c(fc_w.detach().view(-1))
+        qc, alpha, nrm, prob, ssum = ops.qattn_fwd(y, wf, fc_b.detach(), qlen, words, W, words.shape[-1])
+        ctx.save_for_backward(y, words, qlen, wf, alpha, nrm, prob, ssum)
+        ctx.W = W
+        ctx.mark_non_differentiable(alpha)
+        return qc, alpha
+
+    @staticmethod
+    def backward(ctx, dqc, _dalpha):
+        y, words, qlen, wf, alpha, nrm, prob, ssum = ctx.saved_tensors
+        dy, dwords, dwf, dcf = ops.qattn_bwd(_c(dqc), y, wf, qlen, words, ctx.W, alpha, nrm, prob, ssum)
+        return dy, dwords, None, dwf.view(1, -1), dcf.view(1), None
+
+
+class GateFn(Function):
+    """QueryPunish gates of both streams (reference model/utils.py:101-103): g = sigmoid(X . query)."""
+
+    @staticmethod
+    def forward(ctx, xa, xm, query):
+        xa, xm, query = _c(xa), _c(xm), _c(query)
+        ga, gm = ops.gate_fwd(xa, xm, query)
+        ctx.save_for_backward(xa, xm, query, ga, gm)
+        return ga, gm
+
+    @staticmethod
+    def backward(ctx, dga, dgm):
+        xa, xm, query, ga, gm = ctx.saved_tensors
+        dxa, dxm = torch.zeros_like(xa), torch.zeros_like(xm)
+        dq = ops.gate_bwd(xa, xm, query, ga, gm, _c(dga), None, _c(dgm), None, dxa, dxm)
+        return dxa, dxm, dq
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+class GatLayerFn(Function):
+    """Several punishGATs in one shot (reference model/GraphNN.py:95-113,174-178): per input stream ONE batched projection
+    GEMM for all graphs reading that stream, then ONE fused attention launch for all graphs (<= 4).
+    A DualVGR unit calls it with 2 streams and graph_stream = (0, 0, 1, 1): acGCN, appearance_GCN, mcGCN, motion_GCN
+    (reference model/models.py:151-158).
+    tensors = xs (n_streams x [B,N,D] bf16) + gates (n_streams x [B,N] f32)
+              + per graph, per head: W.weight, W.bias, a.weight, a.bias
+    returns: per stream a stack [n_graphs_of_stream, B*N, D] bf16, then per graph a dense fp32 copy [B,N,D]."""
+
+    @staticmethod
+    def forward(ctx, graph_stream, adj, p, training, heads, *tensors):
+        ns, G = max(graph_stream) + 1, len(graph_stream)
+        xs, gates_in, params = tensors[:ns], tensors[ns:2 * ns], tensors[2 * ns:]
+        B, N, D = xs[0].shape
+        M, Dh = B * N, D // heads
+        pdrop = p if training else 0.0
+        seed, sid = _site(3 * G)          # graph g: input dropout sid+g, attention sid+G+2g, output sid+G+2g+1
+        gp = [params[g * heads * 4:(g + 1) * heads * 4] for g in range(G)]
+        avecs = [torch.cat([torch.cat([gp[g][4 * k + 2].detach().reshape(-1), gp[g][4 * k + 3].detach().reshape(-1)])
+                            for k in range(heads)]).view(heads, 2 * Dh + 1).contiguous() for g in range(G)]
+        of_stream = [[g for g in range(G) if graph_stream[g] == s] for s in range(ns)]
+        whs, xts, wbufs, outs_s = [], [], [], []
+        wh_list, out_list = [None] * G, [None] * G
+        for s in range(ns):
+            gs = of_stream[s]
+            cnt = len(gs)
+            x = _c(xs[s]).view(M, D)
+            wb = bf16_rows([gp[g][4 * k] for g in gs for k in range(heads)], tag="gat").view(cnt, D, D)
+            bias = torch.stack([torch.cat([gp[g][4 * k + 1].detach() for k in range(heads)]) for g in gs])
+            wh = torch.empty((cnt, M, D), dtype=BF16, device=x.device)
+            if pdrop > 0:
+                xt = torch.stack([ops.dropout_raw(x, pdrop, seed, sid + g) for g in gs])
+                a_c2 = list(range(cnt))
+            else:
+                xt, a_c2 = x, [0] * cnt
+            ops.gemm(xt, 0, wb, 0, M, D, D, wh, ldc=D, bias=bias, batch=cnt, c_batch=M * D, bias_batch=D,
+                     a_c2=a_c2, b_c2=list(range(cnt)))
+            out = torch.empty((cnt, M, D), dtype=BF16, device=x.device)
+            for i, g in enumerate(gs):
+                wh_list[g], out_list[g] = wh[i], out[i]
+            whs.append(wh); xts.append(xt); wbufs.append(wb); outs_s.append(out)
+        streams = [sid + G + 2 * g for g in range(G)]
+        gate_list = [_c(gates_in[graph_stream[g]]) for g in range(G)]
+        _, f32s = ops.gat_attn_fwd(wh_list, gate_list, avecs, adj, B, N, heads=heads, p_att=pdrop, p_out=pdrop, seed=seed,
+                                   streams=streams, outs=out_list, want_f32=True)
+        ctx.save_for_backward(adj, *xts, *wbufs, *whs, *outs_s, *gate_list, *avecs)
+        ctx.cfg = (B, N, D, M, heads, pdrop, seed, sid, streams, graph_stream, of_stream)
+        return tuple(outs_s) + tuple(f32s)
+
+    @staticmethod
+    def backward(ctx, *grads_out):
+        B, N, D, M, heads, pdrop, seed, sid, streams, graph_stream, of_stream = ctx.cfg
+        ns, G = len(of_stream), len(graph_stream)
+        sv = ctx.saved_tensors
+        adj = sv[0]
+        xts, wbufs, whs, outs_s = sv[1:1 + ns], sv[1 + ns:1 + 2 * ns], sv[1 + 2 * ns:1 + 3 * ns], sv[1 + 3 * ns:1 + 4 * ns]
+        gate_list = list(sv[1 + 4 * ns:1 + 4 * ns + G])
+        avecs = list(sv[1 + 4 * ns + G:])
+        Dh = D // heads
+        dev = adj.device
+        douts_s = [(_c(grads_out[s]) if grads_out[s] is not None else torch.zeros_like(outs_s[s])) for s in range(ns)]
+        d32 = [None if t is None else _c(t) for t in grads_out[ns:ns + G]]
+        wh_list, out_list, dout_list, dwh_list = [None] * G, [None] * G, [None] * G, [None] * G
+        dwh_s = [torch.empty_like(w) for w in whs]
+        for s in range(ns):
+            for i, g in enumerate(of_stream[s]):
+                wh_list[g], out_list[g], dout_list[g], dwh_list[g] = whs[s][i], outs_s[s][i], douts_s[s][i], dwh_s[s][i]
+        _, dgates, davecs = ops.gat_attn_bwd(wh_list, gate_list, avecs, out_list, dout_list, adj, B, N, heads=heads,
+                                             p_att=pdrop, p_out=pdrop, seed=seed, streams=streams, douts32=d32,
+                                             dwhs=dwh_list)
+        dxs, dgs = [], []
+        dW, db = [None] * G, [None] * G
+        for s in range(ns):
+            gs = of_stream[s]
+            cnt = len(gs)
+            dwh, wb, xt = dwh_s[s], wbufs[s], xts[s]
+            dWs = torch.empty((cnt, D, D), dtype=F32, device=dev)
+            if pdrop > 0:
+                dxt = torch.empty((cnt, M, D), dtype=BF16, device=dev)
+                ops.gemm(dwh, 0, wb, 1, M, D, D, dxt, ldc=D, batch=cnt, c_batch=M * D, a_c2=list(range(cnt)),
+                         b_c2=list(range(cnt)))
+                dx = ops.dropout_raw(dxt[0], pdrop, seed, sid + gs[0])
+                for i in range(1, cnt):
+                    ops.act_bwd(dxt[i], None, "none", out=dx, accumulate=True, p=pdrop, seed=seed, stream_id=sid + gs[i])
+                ops.gemm(dwh, 1, xt, 1, D, D, M, dWs, ldc=D, batch=cnt, c_batch=D * D, a_c2=list(range(cnt)),
+                         b_c2=list(range(cnt)))
+            else:
+                dx = ops.linear_dgrad(dwh[0], wb[0])
+                for i in range(1, cnt):
+                    ops.linear_dgrad(dwh[i], wb[i], out=dx, beta=True)
+                ops.gemm(dwh, 1, xt, 1, D, D, M, dWs, ldc=D, batch=cnt, c_batch=D * D, a_c2=list(range(cnt)),
+                         b_c2=[0] * cnt)
+            dxs.append(dx.view(B, N, D))
+            dg = dgates[gs[0]]
+            for g in gs[1:]:
+                dg = dg + dgates[g]
+            dgs.append(dg)
+            for i, g in enumerate(gs):
+                dW[g], db[g] = dWs[i], ops.colsum(dwh[i])
+        grads = []
+        for g in range(G):
+            for k in range(heads):
+                grads += [dW[g][k * Dh:(k + 1) * Dh], db[g][k * Dh:(k + 1) * Dh],
+                          davecs[g][k, :2 * Dh].reshape(1, 2 * Dh), davecs[g][k, 2 * Dh:].reshape(1)]
+        return (None, None, None, None, None) + tuple(dxs) + tuple(dgs) + tuple(grads)
+
+
+class ViewAttnFn(Function):
+    """AttentionSFGCN tail + residual (reference model/Attention.py:21-23, model/models.py:168-169)."""
+
+    @staticmethod
+    def forward(ctx, hidden, z, x, w2):
+        hidden, z, x = _c(hidden), _c(z), _c(x)
+        w2v = _c(w2.detach().view(-1))
+        x2 = x.view(-1, x.shape[-1])
+        xnew, embed, beta = ops.view_attn_fwd(hidden, z, x2, w2v)
+        ctx.save_for_backward(hidden, z, w2v, beta)
+        return xnew.view_as(x), embed.view_as(x)
+
+    @staticmethod
+    def backward(ctx, dxnew, dembed):
+        hidden, z, w2v, beta = ctx.saved_tensors
+        D = z.shape[-1]
+        if dxnew is None:
+            dxnew = torch.zeros(z.shape[1:], dtype=BF16, device=z.device)
+        dxn = _c(dxnew).view(-1, D)
+        de = _c(dembed).view(-1, D) if dembed is not None else None
+        dz, dhid, dw2 = ops.view_attn_bwd(dxn, de, hidden, z, w2v, beta)
+        return dhid, dz, dxnew, dw2.view(1, -1)
+
+
+class MfbPairFn(Function):
+    """MFB product + pair-sum (reference model/fusions/fusions.py:433-441). Inputs are ELU outputs; the backward returns
+    gradients w.r.t. the PRE-activations of linear0 / linear1 (ELU' folded in)."""
+
+    @staticmethod
+    def forward(ctx, x0, x1):
+        x0, x1 = _c(x0), _c(x1)
+        lead = x0.shape[:-1]
+        a, b = x0.view(-1, x0.shape[-1]), x1.view(-1, x1.shape[-1])
+        z = ops.mfb_fwd(a, b)
+        ctx.save_for_backward(a, b)
+        ctx.lead = lead
+        return z.view(*lead, z.shape[-1])
+
+    @staticmethod
+    def backward(ctx, dz):
+        a, b = ctx.saved_tensors
+        d0, d1 = ops.mfb_bwd(_c(dz).view(-1, dz.shape[-1]), a, b)
+        return d0.view(*ctx.lead, -1), d1.view(*ctx.lead, -1)
+
+
+class ReadoutFn(Function):
+    """ContextSelfAttn tail (reference model/AnswerDecoder.py:176-180). Backward returns d(pre-activation of v_proj) for u."""
+
+    @staticmethod
+    def forward(ctx, v, u, w, c):
+        v, u = _c(v), _c(u)
+        wv = _c(w.detach().view(-1))
+        pooled, alpha = ops.readout_fwd(v, u, wv, c.detach())
+        ctx.save_for_backward(v, u, wv, alpha)
+        return pooled
+
+    @staticmethod
+    def backward(ctx, dp):
+        v, u, wv, alpha = ctx.saved_tensors
+        dv, du, dw, dc = ops.readout_bwd(_c(dp), v, u, wv, alpha)
+        return dv, du, dw.view(1, -1), dc.view(1)
+
+
+class BatchNormFn(Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, run_mean, run_var, training, momentum, eps):
+        x = _c(x)
+        y, mean, rstd = ops.bn_fwd(x, gamma.detach(), beta.detach(), run_mean, run_var, training, momentum, eps)
+        ctx.save_for_backward(x, gamma.detach(), mean, rstd)
+        ctx.training = training
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, mean, rstd = ctx.saved_tensors
+        dx, dg, db = ops.bn_bwd(_c(dy), x, gamma, mean, rstd, ctx.training)
+        return dx, dg, db, None, None, None, None, None
+
+
+class CrossEntropyFn(Function):
+    """Mean cross-entropy with the gradient produced in the same launch."""
+
+    @staticmethod
+    def forward(ctx, logits, answers):
+        loss, dlog, correct = ops.cross_entropy(_c(logits), answers)
+        ctx.save_for_backward(dlog)
+        ctx.A = logits.shape[1]
+        ctx.mark_non_differentiable(correct)
+        return loss, correct
+
+    @staticmethod
+    def backward(ctx, g, _):
+        (dlog,) = ctx.saved_tensors
+        return dlog[:, :ctx.A].float() * g, None
+
+
+class PairLossFn(Function):
+    """common_loss / loss_dependence (reference utils.py:10-31): value and gradients from one fused launch."""
+
+    @staticmethod
+    def forward(ctx, x, y, mode, coef):
+        loss, dx, dy = ops.pair_loss(_c(x.float()), _c(y.float()), mode, coef)
+        ctx.save_for_backward(dx, dy)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        dx, dy = ctx.saved_tensors
+        return dx * g, dy * g, None, None

@@ -1,0 +1,81 @@
+"""Mirror of the live part of reference model/Preprocessing.py: DynamicRNN (:7-45), InputUnitLinguisticDynamic (:89-127)
+and VisualAppearanceEncoder (:191-234).
+
+The appearance encoder (70-76 % of the model's FLOPs) runs entirely in the library: one prologue pass, one
+tcgen05 GEMM for the W_ih product of both directions and 16 fused recurrent steps. The question encoder (3 % of FLOPs, not
+in the north-star kernel list) stays on PyTorch/cuDNN, as SURVEY.md §2 row 7 allows."""
+import torch
+import torch.nn as nn
+from torch.nn import functional as F
+
+from dualvgr_videoqa_b200 import autograd as ag
+
+
+class DynamicRNN(nn.Module):
+    """Length-aware RNN: packs by length, runs the cuDNN RNN, re-pads to max_num_frames; returns (outputs, final state)."""
+
+    def __init__(self, input_size, hidden_size, num_layers=1, bias=True, batch_first=False, dropout=0,
+                 bidirectional=False, rnn_encoder='GRU'):
+        super().__init__()
+        self.batch_first = batch_first
+        self.rnn = getattr(nn, rnn_encoder)(input_size, hidden_size, num_layers=num_layers, bias=bias,
+                                            batch_first=batch_first, dropout=dropout if num_layers > 1 else 0,
+                                            bidirectional=bidirectional)
+        self.bidirectional = bidirectional
+
+    def forward(self, x, seq_len, max_num_frames):
+        lengths = seq_len.detach().to("cpu", torch.int64)
+        packed = nn.utils.rnn.pack_padded_sequence(x, lengths, batch_first=self.batch_first, enforce_sorted=False)
+        out, state = self.rnn(packed)
+        if isinstance(state, tuple):
+            state = state[0]
+        out, _ = nn.utils.rnn.pad_packed_sequence(out, batch_first=self.batch_first, total_length=max_num_frames)
+        if self.bidirectional:
+            state = torch.cat([state[0], state[1]], -1)
+        return out, state
+
+
+class InputUnitLinguisticDynamic(nn.Module):
+    def __init__(self, vocab_size, wordvec_dim=300, rnn_dim=512, bidirectional=True, textual_encoder='LSTM'):
+        super().__init__()
+        self.bidirectional = bidirectional
+        if bidirectional:
+            rnn_dim = rnn_dim // 2
+        self.encoder_embed = nn.Embedding(vocab_size, wordvec_dim)
+        self.tanh = nn.Tanh()
+        self.concatRNN = DynamicRNN(wordvec_dim, rnn_dim, num_layers=1, bias=True, batch_first=True, dropout=0.15,
+                                    bidirectional=bidirectional, rnn_encoder=textual_encoder)
+        self.encoder = getattr(nn, textual_encoder)(wordvec_dim, rnn_dim, batch_first=True, bidirectional=bidirectional)
+        self.embedding_dropout = nn.Dropout(p=0.15)
+        self.final_dropout = nn.Dropout(0.18)
+
+    def forward(self, questions, question_len):
+        """-> (question_embedding [B,D], words [B,L,W], per-token states [B,L,D] with zero rows at padded positions)."""
+        max_len = questions.size(1)
+        words = self.tanh(self.embedding_dropout(self.encoder_embed(questions)))
+        output_embedding, _ = self.concatRNN(words, question_len, max_len)
+        lengths = question_len.detach().to("cpu", torch.int64)
+        packed = nn.utils.rnn.pack_padded_sequence(words, lengths, batch_first=True, enforce_sorted=False)
+        _, (h, _) = self.encoder(packed)
+        q = torch.cat([h[0], h[1]], -1) if self.bidirectional else h[0]
+        return self.final_dropout(q), words, output_embedding
+
+
+class VisualAppearanceEncoder(nn.Module):
+    def __init__(self, appearance_dim=2048, module_dim=512, bidirectional=True):
+        super().__init__()
+        if not bidirectional:
+            raise NotImplementedError("the sm_100a appearance encoder is the bidirectional one DualVGR builds")
+        self.input_dim, self.bidirectional, self.module_dim = appearance_dim, bidirectional, module_dim
+        self.tanh = nn.Tanh()
+        self.encoder = nn.LSTM(appearance_dim, module_dim // 2, batch_first=False, bidirectional=True)
+        self.embedding_dropout = nn.Dropout(p=0.15)
+        self.finalvisual_dropout = nn.Dropout(p=0.18)
+
+    def forward(self, appearance_clips):
+        """[B, N, F, Dv] fp32 -> [B, N, module_dim] bf16 (final forward / backward hidden states, concatenated)."""
+        e = self.encoder
+        return ag.AppearanceEncoderFn.apply(
+            appearance_clips.float(), e.weight_ih_l0, e.weight_hh_l0, e.bias_ih_l0, e.bias_hh_l0,
+            e.weight_ih_l0_reverse, e.weight_hh_l0_reverse, e.bias_ih_l0_reverse, e.bias_hh_l0_reverse,
+            self.embedding_dropout.p, self.finalvisual_dropout.p, self.training)

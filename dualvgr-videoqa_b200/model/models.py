@@ -1,0 +1,140 @@
+"""Mirror of reference model/models.py: DualVGR (:35-83) and DualVGRUnit_multiple (:86-173).
+
+Same constructor arguments, forward signature, returned 7-tuple and state_dict keys/shapes as the reference, so
+train.py / validate.py drive it unchanged. Differences that are fixes of environment bugs, not of arithmetic:
+  * the adjacency lives on the module's own device (the reference pins it to the literal 'cuda:1', models.py:118-119);
+    it is a non-persistent buffer, so it is NOT in the state_dict (as in the reference, where it is a plain attribute);
+  * the per-layer GAT outputs are returned as CUDA tensors (the reference moves them to the CPU at :153-160 and
+    train.py:152-153 moves them straight back with .cuda(), which is a no-op here).
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from dualvgr_videoqa_b200 import autograd as ag
+
+from .AnswerDecoder import ContextSelfAttn, SimpleOutputUnitOpenEnded
+from .Attention import AttentionSFGCN
+from .GraphNN import fused_gat_layer, punishGAT
+from .Preprocessing import InputUnitLinguisticDynamic, VisualAppearanceEncoder
+from .fusions.fusions import MFB
+from .utils import QueryAttn, QueryPunish, init_modules, pad_last
+
+BF16 = torch.bfloat16
+
+
+def normalize(mx):
+    """Row-normalise a dense non-negative matrix (reference :26-33, there on a scipy sparse matrix)."""
+    rowsum = mx.sum(1)
+    r_inv = np.where(rowsum > 0, 1.0 / np.maximum(rowsum, 1e-300), 0.0)
+    return mx * r_inv[:, None]
+
+
+def build_adjacency(num_of_nodes):
+    """Fully connected clip graph of reference :114-116: ones -> symmetrise -> + I -> row-normalise (dense)."""
+    adj = np.ones((num_of_nodes, num_of_nodes), dtype=np.float64)
+    adj = np.maximum(adj, adj.T)
+    return torch.from_numpy(normalize(adj + np.eye(num_of_nodes)).astype(np.float32))
+
+
+class DualVGR(nn.Module):
+    def __init__(self, vision_dim=2048, module_dim=768, word_dim=300, vocab=None, num_of_nodes=8, graph_module='GCN',
+                 graph_layers=1, unit_layers=2):
+        super().__init__()
+        self.feature_aggregation = ContextSelfAttn(module_dim)
+        encoder_vocab_size = len(vocab['question_token_to_idx'])
+        self.num_classes = len(vocab['answer_token_to_idx'])
+        self.linguistic_input_unit = InputUnitLinguisticDynamic(vocab_size=encoder_vocab_size, wordvec_dim=word_dim,
+                                                                rnn_dim=module_dim, textual_encoder='LSTM')
+        self.visual_appearance_input_unit = VisualAppearanceEncoder(appearance_dim=vision_dim, module_dim=module_dim,
+                                                                    bidirectional=True)
+        self.visual_motion_input_unit = nn.Linear(vision_dim, module_dim)
+        self.visual_input_unit = DualVGRUnit_multiple(word_dim=word_dim, module_dim=module_dim,
+                                                      num_of_nodes=num_of_nodes, appearance_graph_layers=graph_layers,
+                                                      motion_graph_layers=graph_layers, graph_module=graph_module,
+                                                      unit_layers=unit_layers)
+        self.output_unit = SimpleOutputUnitOpenEnded(module_dim=module_dim, num_answers=self.num_classes)
+        init_modules(self.modules(), w_init="xavier_uniform")
+        nn.init.uniform_(self.linguistic_input_unit.encoder_embed.weight, -1.0, 1.0)
+
+    def forward(self, video_appearance_feat, video_motion_feat, question, question_len):
+        """
+        video_appearance_feat [B, N, F, vision_dim] fp32, video_motion_feat [B, N, vision_dim] fp32,
+        question [B, L] int64, question_len [B] int64
+        -> (logits [B, A] fp32, aq_embed, mq_embed [B,N,D], com_app[U], com_motion[U], aq_fusion[U], mq_fusion[U])
+        """
+        if not video_appearance_feat.is_cuda:
+            raise RuntimeError("dualvgr_b200: DualVGR runs on sm_100a CUDA devices only; there is no CPU path")
+        ag.begin_forward()
+        question_embedding, word_embedding, dynamic_q = self.linguistic_input_unit(question, question_len)
+        app = self.visual_appearance_input_unit(video_appearance_feat)
+        B, N = video_motion_feat.shape[:2]
+        mot_in = ag.ops.prep_features(video_motion_feat.float().contiguous().view(B * N, -1), 1, False, False)
+        mot = ag.linear(mot_in, self.visual_motion_input_unit.weight, self.visual_motion_input_unit.bias).view(B, N, -1)
+        visual, aq_embed, mq_embed, com_app, com_motion, aq_fusion, mq_fusion = self.visual_input_unit(
+            app, mot, dynamic_q, word_embedding, question_len)
+        pooled = self.feature_aggregation(visual)
+        out = self.output_unit(question_embedding, pooled)
+        return out, aq_embed, mq_embed, com_app, com_motion, aq_fusion, mq_fusion
+
+
+class DualVGRUnit_multiple(nn.Module):
+    def __init__(self, word_dim=300, module_dim=512, num_of_nodes=8, appearance_graph_layers=1, motion_graph_layers=1,
+                 graph_module='GAT', unit_layers=3):
+        super().__init__()
+        if appearance_graph_layers != 1 or motion_graph_layers != 1:
+            raise NotImplementedError("graph_layers must be 1 (every shipped config; for >1 the reference aliases layers "
+                                      "through its [i+j] indexing, model/models.py:151-158)")
+        self.layers = unit_layers
+        self.word_dim = word_dim
+        self.queryAttn = nn.ModuleList([QueryAttn(module_dim=module_dim) for _ in range(unit_layers)])
+        self.queryPunish_appear = nn.ModuleList([QueryPunish(word_dim=word_dim, module_dim=module_dim) for _ in range(unit_layers)])
+        self.queryPunish_motion = nn.ModuleList([QueryPunish(word_dim=word_dim, module_dim=module_dim) for _ in range(unit_layers)])
+        if graph_module == 'GAT':
+            mk = lambda: nn.ModuleList([punishGAT(module_dim, module_dim // 4, dropout=0.15, alpha=0.01, n_heads=4)
+                                        for _ in range(unit_layers)])
+            self.appearance_GCN = mk()
+            self.motion_GCN = mk()
+            self.acGCN = mk()
+            self.mcGCN = mk()
+        elif unit_layers > 0:
+            raise NotImplementedError("only graph_module='GAT' builds graph layers (reference model/models.py:94)")
+        self.attention_appearance = nn.ModuleList([AttentionSFGCN(module_dim, module_dim) for _ in range(unit_layers)])
+        self.attention_motion = nn.ModuleList([AttentionSFGCN(module_dim, module_dim) for _ in range(unit_layers)])
+        self.num_of_appearance_graph_layers = appearance_graph_layers
+        self.num_of_motion_graph_layers = motion_graph_layers
+        self.visualfusion = MFB([module_dim, module_dim], module_dim)
+        self.module_dim = module_dim
+        self.activation = nn.ELU()
+        adj = build_adjacency(num_of_nodes)
+        self.register_buffer("appearance_adj", adj.clone(), persistent=False)
+        self.register_buffer("motion_adj", adj.clone(), persistent=False)
+
+    def forward(self, appearance_video_feat, motion_video_feat, dynamic_question_embedding, word_embedding, question_len):
+        """app / motion [B,N,D], dynamic_q [B,L,D], words [B,L,W], question_len [B] ->
+        (visual [B,N,D], aq_embed, mq_embed, com_app[U], com_motion[U], aq_fusion[U], mq_fusion[U])"""
+        B, N, D = appearance_video_feat.shape
+        app = appearance_video_feat.to(BF16)
+        mot = motion_video_feat.to(BF16)
+        dq = dynamic_question_embedding.to(BF16)
+        words = pad_last(word_embedding).to(BF16)
+        qlen = question_len.to(torch.int32)
+        adj = self.appearance_adj
+        aq_fusion_list, mq_fusion_list, com_app_list, com_motion_list = [], [], [], []
+        aq_embed = mq_embed = None
+        for i in range(self.layers):
+            # Query Punishment Module: word attention -> cycle query -> per-clip gates of both streams
+            q_c, _ = self.queryAttn[i](words, dq, qlen, word_dim=self.word_dim)
+            query = torch.cat([self.queryPunish_appear[i].query(q_c), self.queryPunish_motion[i].query(q_c)], dim=1)
+            g_app, g_mot = ag.GateFn.apply(app, mot, query)
+            # multi-view GAT: common + specific graph of each stream, one fused launch for the four graphs
+            (z_app, z_mot), (com_app, aq_fusion, com_mot, mq_fusion) = fused_gat_layer(
+                [self.acGCN[i], self.appearance_GCN[i], self.mcGCN[i], self.motion_GCN[i]], [0, 0, 1, 1],
+                [app, mot], [g_app, g_mot], adj, self.training)
+            aq_fusion_list.append(aq_fusion); com_app_list.append(com_app)
+            mq_fusion_list.append(mq_fusion); com_motion_list.append(com_mot)
+            # common-vs-specific view attention + residual
+            app, aq_embed = self.attention_appearance[i].fused(z_app, app)
+            mot, mq_embed = self.attention_motion[i].fused(z_mot, mot)
+        visual = self.visualfusion([app, mot])
+        return visual, aq_embed, mq_embed, com_app_list, com_motion_list, aq_fusion_list, mq_fusion_list

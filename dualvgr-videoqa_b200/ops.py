@@ -318,13 +318,14 @@ def gat_attn_fwd(whs, gates, avecs, adj, B, N, heads=4, slope=0.01, p_att=0.0, p
 
 
 def gat_attn_bwd(whs, gates, avecs, outs, douts, adj, B, N, heads=4, slope=0.01, p_att=0.0, p_out=0.0, seed=0,
-                 streams=None, douts32=None):
+                 streams=None, douts32=None, dwhs=None):
     D = whs[0].shape[-1]
     G = len(whs)
     Dh = D // heads
     streams = streams or [2 * i for i in range(G)]
     a = _gat_args(whs, gates, avecs, outs, adj, B, N, D, heads, slope, p_att, p_out, seed, streams)
-    dwhs = [torch.empty_like(w) for w in whs]
+    if dwhs is None:
+        dwhs = [torch.empty_like(w) for w in whs]
     dgates = [_empty((B, N), F32, whs[0]) for _ in range(G)]
     dav_part = [_empty((B, heads * (2 * Dh + 1)), F32, whs[0]) for _ in range(G)]
     for i in range(G):

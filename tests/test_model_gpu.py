@@ -1,0 +1,158 @@
+"""Whole-path parity on the GPU: the CUDA DualVGR (through the nn.Module mirror and the C ABI) against
+ (a) the committed golden fixtures produced by the UNMODIFIED reference (tests/golden, float64 run), and
+ (b) the CPU oracle run live on the same seeded inputs / weights (full gradient tensors).
+Tolerances (north_star, bf16 mode): logits and gradients within 2e-2 relative (global L2), identical argmax wherever
+the reference's own top-2 margin exceeds the tolerance. Dropout off (p = 0), train-mode BatchNorm, randomised biases —
+the protocol of SURVEY.md §8c."""
+import numpy as np
+import pytest
+import torch
+
+import dualvgr_oracle as orc
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-2
+
+
+def _probe(name, shape, seed=4242):
+    h = 0
+    for ch in name:
+        h = (h * 131 + ord(ch)) % 1000003
+    g = torch.Generator().manual_seed(seed + (h % 100000))
+    return torch.randn(shape, generator=g, dtype=torch.float64)
+
+
+def rel(a, b):
+    a = torch.as_tensor(np.asarray(a), dtype=torch.float64) if not torch.is_tensor(a) else a.detach().double().cpu()
+    b = torch.as_tensor(np.asarray(b), dtype=torch.float64) if not torch.is_tensor(b) else b.detach().double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def no_dropout(model):
+    for m in model.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+        if hasattr(m, "dropout") and isinstance(getattr(m, "dropout"), float):
+            m.dropout = 0.0
+
+
+def build(cfg, training=True):
+    import dualvgr_videoqa_b200.model.models as M
+    B, N, L, A, V, U = cfg
+    model = M.DualVGR(vocab=orc.make_vocab(V, A), num_of_nodes=N, graph_module="GAT", graph_layers=1, unit_layers=U)
+    model.load_state_dict(orc.make_state_dict(U, A, V), strict=True)
+    no_dropout(model)
+    model = model.cuda().train(training)
+    app, mot, q, qlen, ans = orc.make_inputs(B, N, L, A, V)
+    return model, [t.cuda() for t in (app, mot, q, qlen)], ans.cuda()
+
+
+def total_loss(out, ans, N):
+    import dualvgr_videoqa_b200.utils as U
+    logits, _, _, ca, cm, aq, mq = out
+    ce = torch.nn.functional.cross_entropy(logits, ans)
+    dep = sum(U.loss_dependence(aq[i], ca[i], N) + U.loss_dependence(mq[i], cm[i], N) for i in range(len(aq)))
+    com = sum(U.common_loss(ca[i], cm[i]) for i in range(len(aq)))
+    n = len(aq)
+    return ce + 1.0 * com / n + 1e-8 * dep / n, ce, com, dep
+
+
+@pytest.mark.parametrize("name", ["g1_B4_N8_U2", "g2_B3_N20_U3", "g3_B5_N16_U1"])
+def test_against_reference_golden(golden, name):
+    g = golden(name)
+    cfg = [int(x) for x in g["cfg"]]
+    N = cfg[1]
+    # ---- eval mode
+    model, inputs, ans = build(cfg, training=False)
+    with torch.no_grad():
+        logits_eval = model(*inputs)[0]
+    assert rel(logits_eval, g["f64_logits_eval"]) < TOL
+    # ---- train mode
+    model, inputs, ans = build(cfg, training=True)
+    out = model(*inputs)
+    logits = out[0]
+    ref_logits = g["f64_logits_train"]
+    assert logits.dtype == torch.float32 and tuple(logits.shape) == ref_logits.shape
+    assert rel(logits, ref_logits) < TOL
+    srt = np.sort(ref_logits, axis=1)
+    confident = (srt[:, -1] - srt[:, -2]) > 2 * TOL * np.abs(ref_logits).max()
+    assert np.array_equal(logits.argmax(1).cpu().numpy()[confident], ref_logits.argmax(1)[confident])
+    assert rel(out[1], g["f64_aq_embed"]) < TOL and rel(out[2], g["f64_mq_embed"]) < TOL
+    if "f64_com_app_0" in g.files:
+        for i in range(len(out[3])):
+            for key, lst in (("com_app", out[3]), ("com_mot", out[4]), ("aq_fusion", out[5]), ("mq_fusion", out[6])):
+                assert rel(lst[i], g[f"f64_{key}_{i}"]) < TOL, (key, i)
+    total, ce, com, dep = total_loss(out, ans, N)
+    ref_total, ref_ce, ref_com, ref_dep = g["f64_losses"]
+    f32_total, f32_ce, f32_com, f32_dep = g["f32_losses"]
+    assert abs(float(ce) - ref_ce) < TOL * abs(ref_ce)
+    # aux losses: judged against the reference's own fp32-vs-fp64 gap (ill-conditioned), floor 5 %
+    assert abs(float(com) - ref_com) < max(4 * abs(f32_com - ref_com), 0.05 * abs(ref_com))
+    assert abs(float(dep) - ref_dep) < max(4 * abs(f32_dep - ref_dep), 0.05 * abs(ref_dep))
+    # ---- CE-only gradients vs the reference (per-parameter norm + probe projection, global relative error)
+    names = [str(n) for n in g["grad_names"]]
+    params = dict(model.named_parameters())
+    grads = torch.autograd.grad(ce, [params[n] for n in names], retain_graph=False, allow_unused=True)
+    got_norm = np.array([0.0 if gr is None else float(gr.double().norm()) for gr in grads])
+    got_proj = np.array([0.0 if gr is None else float((gr.double().cpu() * _probe(n, gr.shape)).sum())
+                         for n, gr in zip(names, grads)])
+    ref = g["f64_grad_ce"]
+    assert np.linalg.norm(got_norm - ref[:, 0]) / np.linalg.norm(ref[:, 0]) < TOL
+    assert np.linalg.norm(got_proj - ref[:, 1]) / np.linalg.norm(ref[:, 1]) < 2 * TOL
+    for n, gr in zip(names, grads):
+        assert gr is None or bool(torch.isfinite(gr).all()), n
+
+
+def test_against_live_oracle_full_gradients():
+    """Full gradient tensors (CE-only) of every parameter against the oracle's autograd in float64."""
+    cfg = (6, 20, 8, 32, 60, 3)
+    B, N, L, A, V, U = cfg
+    model, inputs, ans = build(cfg, training=True)
+    out = model(*inputs)
+    ce = torch.nn.functional.cross_entropy(out[0], ans)
+    names = [n for n, _ in model.named_parameters()]
+    grads = torch.autograd.grad(ce, [p for _, p in model.named_parameters()], allow_unused=True)
+
+    sd = orc.cast_state_dict(orc.make_state_dict(U, A, V), torch.float64)
+    for v in sd.values():
+        if v.is_floating_point():
+            v.requires_grad_(True)
+    app, mot, q, qlen, ans_c = orc.make_inputs(B, N, L, A, V)
+    ref_out = orc.dualvgr_forward(sd, U, app.double(), mot.double(), q, qlen, training=True)
+    ref_ce = torch.nn.functional.cross_entropy(ref_out[0], ans_c)
+    ref_grads = torch.autograd.grad(ref_ce, [sd[n] for n in names], allow_unused=True)
+    assert rel(out[0], ref_out[0]) < TOL
+    num = den = 0.0
+    worst = []
+    gmax = max(float(r.norm()) for r in ref_grads if r is not None)
+    for n, gr, rg in zip(names, grads, ref_grads):
+        if rg is None:
+            continue
+        gr = torch.zeros_like(rg) if gr is None else gr.double().cpu()
+        num += float((gr - rg).pow(2).sum()); den += float(rg.pow(2).sum())
+        if float(rg.norm()) > 1e-3 * gmax:                     # skip mathematically-zero gradients (softmax biases)
+            worst.append((float((gr - rg).norm() / rg.norm()), n))
+    assert (num / den) ** 0.5 < TOL, sorted(worst)[-5:]
+    assert max(w for w, _ in worst) < 0.15, sorted(worst)[-5:]   # per-tensor bound in bf16 (global bound is the gate)
+
+
+def test_full_loss_backward_and_train_mode_dropout_runs():
+    """Train mode with the reference's dropout rates: finite loss/grads, masks differ between passes, eval is deterministic."""
+    import dualvgr_videoqa_b200.model.models as M
+    cfg = (8, 20, 8, 32, 60, 2)
+    B, N, L, A, V, U = cfg
+    model = M.DualVGR(vocab=orc.make_vocab(V, A), num_of_nodes=N, graph_module="GAT", graph_layers=1, unit_layers=U)
+    model.load_state_dict(orc.make_state_dict(U, A, V), strict=True)
+    model = model.cuda().train()
+    app, mot, q, qlen, ans = [t.cuda() for t in orc.make_inputs(B, N, L, A, V)]
+    out = model(app, mot, q, qlen)
+    total, ce, com, dep = total_loss(out, ans, N)
+    total.backward()
+    for n, p in model.named_parameters():
+        assert p.grad is not None and bool(torch.isfinite(p.grad).all()), n
+    out2 = model(app, mot, q, qlen)
+    assert not torch.equal(out[0], out2[0])
+    model.eval()
+    with torch.no_grad():
+        e1, e2 = model(app, mot, q, qlen)[0], model(app, mot, q, qlen)[0]
+    assert torch.equal(e1, e2)

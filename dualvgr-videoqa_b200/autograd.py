@@ -1,6 +1,8 @@
 """torch.autograd.Function wrappers: each pairs a forward and a backward entry point of the C ABI so that the nn.Module
 mirror in ``model/`` trains through ``loss.backward()`` exactly like the reference. PyTorch only routes tensors here
 (allocation, views, concatenation of tiny parameter vectors); all arithmetic of the hot path is in the library."""
+import weakref
+
 import torch
 from torch.autograd import Function
 
@@ -44,22 +46,26 @@ def _versions(params):
 
 
 def bf16_rows(params, out_cols=None, lstm_H=0, tag=""):
-    """bf16 operand made of the row-wise concatenation of fp32 matrices `params` (all [r_i, C])."""
-    key = (tag, tuple((p.data_ptr(), tuple(p.shape)) for p in params), out_cols, lstm_H)
+    """bf16 operand made of the row-wise concatenation of fp32 matrices `params` (all [r_i, C]).
+    Cached per parameter OBJECT (weak references: a freed model whose storage address is recycled by the caching
+    allocator must not alias a live one) and re-cast whenever a version counter, data pointer or the optimizer epoch moves."""
+    key = (tag, tuple(id(p) for p in params), out_cols, lstm_H)
     ver = _versions(params)
     ent = _wcache.get(key)
-    if ent is not None and ent[0] == ver:
+    if ent is not None and ent[0] == ver and all(r() is p for r, p in zip(ent[2], params)):
         return ent[1]
     C = params[0].shape[1]
     oc = out_cols or C
     rows = sum(p.shape[0] for p in params)
-    buf = ent[1] if ent is not None else torch.empty((rows, oc), dtype=BF16, device=params[0].device)
+    buf = torch.empty((rows, oc), dtype=BF16, device=params[0].device)
     r = 0
     with torch.no_grad():
         for p in params:
             ops.cast_rows(p.detach(), out=buf[r:r + p.shape[0]], out_cols=oc, lstm_H=lstm_H)
             r += p.shape[0]
-    _wcache[key] = (ver, buf)
+    if len(_wcache) > 4096:
+        _wcache.clear()
+    _wcache[key] = (ver, buf, tuple(weakref.ref(p) for p in params))
     return buf
 
 

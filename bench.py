@@ -1,0 +1,310 @@
+#!/usr/bin/env python
+"""bench.py — DualVGR train-step throughput on N B200s of one node (contract: see the task statement / DESIGN.md).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (sm_100a kernels through the nn.Module mirror)
+  python bench.py --impl reference [...]                          the reference's CPU algorithm (oracle port) on host cores
+
+Workload (BASELINE.json configs[1]): SVQA shapes, N=20 clips x 16 frames x 2048-d appearance + 2048-d motion, GloVe-300
+question of L=20 tokens, unit_layers=3, batch 256 per GPU, bf16 activations, full train step
+(forward, CE + common + HSIC losses, backward, gradient all-reduce, clip 12, Adam). Synthetic data, seeded weights.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG = dict(B=256, N=20, L=20, A=32, V=200, U=3, F=16, Dv=2048)
+METRIC, UNIT = "dualvgr_train_samples_per_sec", "samples/s"
+
+
+def workload_name(n_gpus):
+    return (f"SVQA config (svqa_DualVGR_20.yml shapes): N={CFG['N']} clips x {CFG['F']} frames x {CFG['Dv']}-d, L={CFG['L']}, "
+            f"A={CFG['A']}, unit_layers={CFG['U']}, batch {CFG['B']}/GPU x {n_gpus} GPU, full train step")
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=p["hbm_gbs"], tf_burst=p["bf16_tflops"], tf=p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                    src="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf=1400.0, src="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle sampling DURING the timed region (recipe line of B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax = float(f[2])
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------- reference arm
+def cpu_reference_step_rate(sample_B, steps, warmup, threads):
+    """The reference's algorithm for the path (oracle port, fp32) on the host cores: full train step on a bounded sample."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import dualvgr_oracle as orc
+    torch.set_num_threads(threads)
+    c = CFG
+    sd = orc.make_state_dict(c["U"], c["A"], c["V"])
+    params = []
+    for k, v in sd.items():
+        if v.is_floating_point() and "running_" not in k:
+            v.requires_grad_(True)
+            params.append(v)
+    opt = torch.optim.Adam(params, lr=1e-4)
+    app, mot, q, qlen, ans = orc.make_inputs(sample_B, c["N"], c["L"], c["A"], c["V"])
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad(set_to_none=True)
+        out = orc.dualvgr_forward(sd, c["U"], app, mot, q, qlen, training=True)
+        total, ce, com, dep = orc.train_loss(out, ans, c["N"])
+        total.backward()
+        torch.nn.utils.clip_grad_norm_(params, 12)
+        opt.step()
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    return sample_B / statistics.median(times), statistics.median(times)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample_B = 16
+    rate, sec = cpu_reference_step_rate(sample_B, max(1, args.steps), max(0, min(args.warmup, 2)), threads)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.gpus), "note": "CPU arm: each step is a bounded sample of the workload"},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"oracle port (oracle/dualvgr_oracle.py, fp32, torch CPU) full train step on {sample_B} of the "
+                                   f"{CFG['B']} samples of the workload batch; the Python reference cannot travel to the GPU box"},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import dualvgr_oracle as orc                      # ONLY make_state_dict / make_inputs / cpu_baseline (checker side)
+    import dualvgr_videoqa_b200._lib as L
+    import dualvgr_videoqa_b200.model.models as M
+    from dualvgr_videoqa_b200.engine import TrainEngine
+    from dualvgr_videoqa_b200 import autograd as ag
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    c = CFG
+    torch.manual_seed(666)
+    model = M.DualVGR(vocab=orc.make_vocab(c["V"], c["A"]), num_of_nodes=c["N"], graph_module="GAT", graph_layers=1,
+                      unit_layers=c["U"])
+    model.load_state_dict(orc.make_state_dict(c["U"], c["A"], c["V"]), strict=True)
+    model = model.to(dev).train()
+    eng = TrainEngine(model, lr=1e-4, max_norm=12.0, alpha=1.0, beta=1e-8)
+
+    # synthetic shard of this rank, generated on the host, pinned; a device-resident copy for the kernel-side number
+    g = torch.Generator().manual_seed(1000 + rank)
+    host = {
+        "app": torch.randn((c["B"], c["N"], c["F"], c["Dv"]), generator=g).abs_().pin_memory(),
+        "mot": torch.randn((c["B"], c["N"], c["Dv"]), generator=g).abs_().pin_memory(),
+    }
+    qlen = torch.randint(5, c["L"] + 1, (c["B"],), generator=g); qlen[0] = c["L"]
+    q = torch.randint(2, c["V"], (c["B"], c["L"]), generator=g) * (torch.arange(c["L"])[None] < qlen[:, None])
+    host["q"], host["qlen"] = q.long().pin_memory(), qlen.long().pin_memory()
+    host["ans"] = torch.randint(0, c["A"], (c["B"],), generator=g).pin_memory()
+    res = {k: v.to(dev) for k, v in host.items()}
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
+
+    def step_resident():
+        return eng.train_step(res["app"], res["mot"], res["q"], res["qlen"], res["ans"])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # instrument the dominant kernel (the W_ih tcgen05 GEMM of the appearance encoder) with CUDA events on its stream
+    ag.PROFILE["wih_gemm"] = []
+    for _ in range(max(3, args.warmup)):
+        step_resident()
+    barrier()
+    ag.PROFILE["wih_gemm"].clear()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    n0 = L.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        loss = step_resident()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = L.launch_count() - n0
+    clocks = sampler.stop() if rank == 0 else None
+    gemm_ms = [a.elapsed_time(b) for a, b in ag.PROFILE["wih_gemm"]]
+    ag.PROFILE.pop("wih_gemm", None)
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = c["B"] * world * args.steps / (ms_max / 1e3)
+
+    # ---- e2e: same step through the public API with HOST buffers; H2D of every step's inputs inside the timed region
+    #      (double-buffered on a copy stream, as an input pipeline would), D2H read of the loss every step
+    copy_stream = torch.cuda.Stream(device=dev)
+    bufs = [{k: torch.empty_like(v, device=dev) for k, v in host.items()} for _ in range(2)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+    loss_host = torch.zeros(args.steps + 8, dtype=torch.float32).pin_memory()
+
+    def prefetch(i):
+        b = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[b])
+            for k, v in host.items():
+                bufs[b][k].copy_(v, non_blocking=True)
+            ready[b].record(copy_stream)
+
+    def run_e2e(n):
+        cur = torch.cuda.current_stream()
+        for b in range(2):
+            consumed[b].record(cur)
+        prefetch(0)
+        for i in range(n):
+            if i + 1 < n:
+                prefetch(i + 1)
+            b = i % 2
+            cur.wait_event(ready[b])
+            lo = eng.train_step(bufs[b]["app"], bufs[b]["mot"], bufs[b]["q"], bufs[b]["qlen"], bufs[b]["ans"])
+            consumed[b].record(cur)
+            loss_host[i].copy_(lo, non_blocking=True)
+
+    run_e2e(2)
+    barrier()
+    e0.record()
+    run_e2e(args.steps)
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = c["B"] * world * args.steps / (float(t.item()) / 1e3)
+
+    if rank == 0:
+        pk = peaks()
+        flops = 2.0 * (c["B"] * c["N"] * c["F"]) * c["Dv"] * (8 * 384)        # W_ih product, both directions
+        gemm_avg = statistics.mean(gemm_ms) if gemm_ms else float("nan")
+        achieved = flops / (gemm_avg * 1e-3) / 1e12 if gemm_ms else None
+        traffic = None
+        prof = os.path.join(ROOT, "profiles", "dominant_kernel.json")
+        if os.path.exists(prof):
+            traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": workload_name(world), "parallelism": f"dp{world}" if world > 1 else "single",
+                       "l2": "no explicit flush: each step streams 713 MB of fp32 features + ~1.5 GB of intermediates, far above the 126 MB L2",
+                       "optimizer": "clip 12 + Adam lr 1e-4 (flat fused)", "dropout": "on (train mode, reference rates)",
+                       "final_loss": float(loss)},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
+            "gpu_launches": int(launches),
+            "roofline": {"kernel": "gemm_tcgen05_kernel<K-major,K-major,BN=256> (appearance W_ih product, forward)",
+                         "bound": "tensor", "achieved": achieved, "peak": pk["tf"], "unit": "TFLOP/s",
+                         "frac": (achieved / pk["tf"]) if achieved else None, "traffic": traffic,
+                         "peak_source": pk["src"] + ", sustained bf16 figure (kernel timed inside a long step)",
+                         "launch_ms": gemm_avg},
+        }
+        if world == 1:
+            threads = os.cpu_count() or 1
+            rate, sec = cpu_reference_step_rate(8, 3, 1, threads)
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": "oracle port, fp32, full train step on 8 of the 256 samples of the batch, "
+                                              "median of 3 steps after 1 warm-up"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -34,6 +34,8 @@ def _site(n=1):
 # ---------------------------------------------------------------------------------------------------------------------
 _wcache = {}
 _wepoch = [0]
+# optional CUDA-event instrumentation of the dominant kernel (bench.py sets PROFILE["wih_gemm"] = [] to collect)
+PROFILE = {}
 
 
 def invalidate_weight_cache():
@@ -157,7 +159,14 @@ class AppearanceEncoderFn(Function):
         wih = _lstm_weight([w_ih, w_ih_r], H, "ih")
         whh = _lstm_weight([w_hh, w_hh_r], H, "hh").view(2, 4 * H, H)
         bias = torch.cat([(b_ih + b_hh).view(4, H).t().reshape(-1), (b_ih_r + b_hh_r).view(4, H).t().reshape(-1)]).detach()
+        rec = PROFILE.get("wih_gemm")
+        if rec is not None:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
         gates = ops.linear_fwd(xa, wih, bias=bias, bn=256).view(T, S, 8 * H)
+        if rec is not None:
+            ev1.record()
+            rec.append((ev0, ev1))
         h_hist, c_hist, h_last, _ = ops.lstm_fwd(gates, whh)
         out = h_last
         p_o = p_out if training else 0.0

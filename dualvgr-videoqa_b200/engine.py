@@ -1,0 +1,86 @@
+"""Data-parallel train step for DualVGR on B200: the loop body of the reference's train.py:131-160 with the device
+work restated B200-first.
+
+  * one process per GPU; parameters live in ONE flat fp32 buffer, gradients in another (views handed to autograd), so the
+    gradient exchange is a single NCCL all-reduce over NVLink and the optimizer is two kernel launches
+  * loss = CE + alpha * mean_l common_loss + beta * mean_l (HSIC_app + HSIC_mot)  (train.py:146-154) from the fused
+    cross-entropy / pair-loss kernels (value and gradient in the same launch)
+  * clip_grad_norm_(12) + Adam(lr)  (train.py:85,158-159) = dvgr_sumsq + dvgr_adam_step on the flat buffers
+
+Videos are independent, so ranks shard the batch and never exchange activations. Two cross-sample couplings remain and
+are handled as standard DDP does: BatchNorm uses per-rank batch statistics; CE / common_loss are means
+(gradient averaging reproduces the global-batch gradient), HSIC is a SUM over the batch, so its coefficient is multiplied
+by world_size before averaging."""
+import torch
+import torch.distributed as dist
+
+from . import autograd as ag
+from . import ops
+
+
+class TrainEngine:
+    def __init__(self, model, lr=1e-4, max_norm=12.0, alpha=1.0, beta=1e-8, betas=(0.9, 0.999), eps=1e-8,
+                 process_group=None):
+        self.model = model
+        self.lr, self.max_norm, self.alpha, self.beta, self.betas, self.eps = lr, max_norm, alpha, beta, betas, eps
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        dev = self.params[0].device
+        sizes = [(p.numel() + 3) // 4 * 4 for p in self.params]           # 16-byte aligned slices
+        total = sum(sizes)
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.gflat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.m = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.v = torch.zeros(total, dtype=torch.float32, device=dev)
+        off = 0
+        with torch.no_grad():
+            for p, n in zip(self.params, sizes):
+                sl = self.flat[off:off + p.numel()].view_as(p)
+                sl.copy_(p.data)
+                p.data = sl
+                p.grad = self.gflat[off:off + p.numel()].view_as(p)
+                off += n
+        self.step_count = 0
+        self.numel = total
+        if self.world > 1:      # replicas must start identical (the reference seeds every process the same, train.py:425-428)
+            dist.broadcast(self.flat, src=0, group=self.pg)
+        ag.invalidate_weight_cache()
+
+    # ------------------------------------------------------------------------------------------------------------
+    def loss(self, outputs, answers):
+        """(total, ce, loss_com_sum, loss_dep_sum, n_correct) — train.py:146-154 and batch_accuracy (train.py:352-356)."""
+        logits, _, _, com_app, com_mot, aq, mq = outputs
+        n = len(aq)
+        B, N = aq[0].shape[0], aq[0].shape[1]
+        ce, correct = ag.CrossEntropyFn.apply(logits, answers)
+        com = dep = None
+        for i in range(n):
+            c = ag.PairLossFn.apply(com_app[i], com_mot[i], 0, 1.0 / (B * N * N))
+            d = ag.PairLossFn.apply(aq[i], com_app[i], 1, 1.0) + ag.PairLossFn.apply(mq[i], com_mot[i], 1, 1.0)
+            com = c if com is None else com + c
+            dep = d if dep is None else dep + d
+        total = ce
+        if n > 0:
+            total = ce + (self.alpha / n) * com + (self.beta * self.world / n) * dep
+        return total, ce, com, dep, correct
+
+    def train_step(self, app, mot, question, question_len, answers):
+        """One optimizer step on this rank's shard. Returns the (device) total loss of the shard."""
+        self.model.train()
+        self.gflat.zero_()
+        outputs = self.model(app, mot, question, question_len)
+        total, ce, com, dep, correct = self.loss(outputs, answers)
+        total.backward()
+        self.optimizer_step()
+        return total.detach()
+
+    def optimizer_step(self):
+        if self.world > 1:
+            dist.all_reduce(self.gflat, op=dist.ReduceOp.SUM, group=self.pg)
+        self.step_count += 1
+        scale = 1.0 / self.world
+        nsq = ops.sumsq(self.gflat)
+        ops.adam_step(self.flat, self.gflat, self.m, self.v, self.lr, self.step_count, self.betas[0], self.betas[1],
+                      self.eps, max_norm=self.max_norm, norm_sq=nsq, grad_scale=scale)
+        ag.invalidate_weight_cache()

@@ -244,16 +244,18 @@ def run_ours(args):
             consumed[b].record(cur)
             loss_host[i].copy_(lo, non_blocking=True)
 
-    run_e2e(2)
-    barrier()
-    e0.record()
-    run_e2e(args.steps)
-    e1.record()
-    barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = c["B"] * world * args.steps / (float(t.item()) / 1e3)
+    e2e_value = None
+    if not args.no_e2e:
+        run_e2e(2)
+        barrier()
+        e0.record()
+        run_e2e(args.steps)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_value = c["B"] * world * args.steps / (float(t.item()) / 1e3)
 
     if rank == 0:
         pk = peaks()
@@ -281,7 +283,7 @@ def run_ours(args):
                          "peak_source": pk["src"] + ", sustained bf16 figure (kernel timed inside a long step)",
                          "launch_ms": gemm_avg},
         }
-        if world == 1:
+        if world == 1 and not args.no_cpu:
             threads = os.cpu_count() or 1
             rate, sec = cpu_reference_step_rate(8, 3, 1, threads)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
@@ -299,6 +301,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-e2e", action="store_true", help="profiling aid: skip the host-buffer e2e leg")
+    ap.add_argument("--no-cpu", action="store_true", help="profiling aid: skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

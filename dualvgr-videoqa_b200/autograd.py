@@ -204,6 +204,67 @@ def _lstm_weight(params, H, tag):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+class QuestionEncoderFn(Function):
+    """Both question BiLSTMs of InputUnitLinguisticDynamic (reference model/Preprocessing.py:97-101,112-123) as ONE
+    4-direction fused recurrence: directions 0/1 = concatRNN (per-token states, zero at padded positions like
+    pad_packed_sequence), directions 2/3 = encoder (final states of the packed run). No packing, no host sync on
+    question_len: padded steps are masked inside the cell epilogue.
+    words fp32 [B, L, W] (= tanh(dropout(embedding))), qlen int32 [B]; params = the 8 tensors of concatRNN.rnn then the 8 of
+    encoder, each in nn.LSTM order (w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r).
+    Returns (dynamic_q [B, L, 2H] bf16, question_embedding [B, 2H] bf16)."""
+
+    @staticmethod
+    def forward(ctx, words, qlen, *params):
+        B, L, W = words.shape
+        H = params[1].shape[1]
+        Wp = (W + 7) // 8 * 8
+        x = torch.zeros((L, B, Wp), dtype=BF16, device=words.device)
+        x[:, :, :W] = words.transpose(0, 1)
+        w_ih = [params[0], params[4], params[8], params[12]]
+        w_hh = [params[1], params[5], params[9], params[13]]
+        wih = bf16_rows(w_ih, out_cols=Wp, lstm_H=H, tag="lstm_ih")
+        whh = bf16_rows(w_hh, lstm_H=H, tag="lstm_hh").view(4, 4 * H, H)
+        bias = torch.cat([(params[4 * d + 2] + params[4 * d + 3]).view(4, H).t().reshape(-1) for d in range(4)]).detach()
+        gates = ops.linear_fwd(x.view(L * B, Wp), wih, bias=bias).view(L, B, 16 * H)
+        h_hist, c_hist, h_last, seq_out = ops.lstm_fwd(gates, whh, seq_len=qlen, want_seq=True)
+        ctx.save_for_backward(x, wih, whh, gates, h_hist, c_hist, qlen)
+        ctx.cfg = (B, L, W, Wp, H)
+        return seq_out[:, :, :2 * H].contiguous(), h_last[:, 2 * H:].contiguous()
+
+    @staticmethod
+    def backward(ctx, d_dq, d_q):
+        x, wih, whh, gates, h_hist, c_hist, qlen = ctx.saved_tensors
+        B, L, W, Wp, H = ctx.cfg
+        dev = x.device
+        dh_seq = torch.zeros((B, L, 4 * H), dtype=BF16, device=dev)
+        dh_last = torch.zeros((B, 4 * H), dtype=BF16, device=dev)
+        if d_dq is not None:
+            dh_seq[:, :, :2 * H] = d_dq
+        if d_q is not None:
+            dh_last[:, 2 * H:] = d_q
+        ops.lstm_bwd(gates, whh, h_hist, c_hist, dh_last, seq_len=qlen, dh_seq=dh_seq)
+        dg = gates.view(L * B, 16 * H)
+        x2 = x.view(L * B, Wp)
+        dwords = None
+        if ctx.needs_input_grad[0]:
+            dwords = ops.linear_dgrad(dg, wih).view(L, B, Wp)[:, :, :W].transpose(0, 1).float()
+        unmap = _lstm_unmap(H, 4, dev)
+        dwih = ops.linear_wgrad(dg, x2, row_map=unmap)[:, :W]
+        db = torch.empty(16 * H, dtype=F32, device=dev)
+        db[unmap.long()] = ops.colsum(dg)
+        kin = (B + 63) // 64
+        dwhh = torch.empty((4, 4 * H, H), dtype=F32, device=dev)
+        ops.gemm(gates, 1, h_hist, 1, 4 * H, H, L * kin * 64, dwhh, ldc=H, batch=4, c_batch=4 * H * H,
+                 row_map=_lstm_unmap(H, 1, dev), a_c0=[4 * H * d for d in range(4)], a_c2=[0, L - 1, 0, L - 1],
+                 a_c2_step=[1, -1, 1, -1], b_c2=[0, 0, 0, 0], b_c2_step=[1, 1, 1, 1], b_c3=[0, 1, 2, 3], k_inner=kin)
+        grads = []
+        for d in range(4):
+            sl = slice(4 * H * d, 4 * H * (d + 1))
+            grads += [dwih[sl], dwhh[d], db[sl], db[sl]]
+        return (dwords, None) + tuple(grads)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
 class QAttnFn(Function):
     """QueryAttn.forward after feat_enhance (reference model/utils.py:68-84). y [B,L,D] bf16, words [B,L,Wp] bf16
     (zero padded to Wp), qlen int32. Returns q_c [B, Wp] bf16 (zero padded) and alpha [B, L] fp32 (not differentiated)."""

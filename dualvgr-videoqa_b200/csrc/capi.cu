@@ -30,6 +30,7 @@ static void fill_lstm_params(GemmParams& p, const dvgr_lstm_args& a) {
   p.h_last = reinterpret_cast<__nv_bfloat16*>(a.h_last);
   p.h_last_ld = a.h_last_ld;
   p.dc = a.dc;
+  p.dh_carry = a.dh_carry;
   p.seq_len = a.seq_len;
   p.seq_out = reinterpret_cast<__nv_bfloat16*>(a.seq_out);
   p.seq_out_ld = a.seq_out_ld;
@@ -115,6 +116,7 @@ int dvgr_lstm_step_bwd(const dvgr_lstm_args* a, void* stream) {
   if (!a) return set_error("dvgr_lstm_step_bwd: null args");
   if (int rc = check_lstm(*a)) return rc;
   if (!a->dc) return set_error("dvgr_lstm_step_bwd: dc is null");
+  if (a->seq_len && !a->dh_carry) return set_error("dvgr_lstm_step_bwd: dh_carry is required with seq_len");
   GemmParams p;
   memset(&p, 0, sizeof(p));
   fill_lstm_params(p, *a);
@@ -140,7 +142,7 @@ int dvgr_lstm_step_bwd(const dvgr_lstm_args* a, void* stream) {
   for (int d = 0; d < a->ndir; ++d) {
     const int s1 = a->s + 1;
     p.a_c0[d] = d * 4 * a->H;
-    p.a_c2[d] = (d == 0) ? s1 : a->T - 1 - s1;
+    p.a_c2[d] = ((d & 1) == 0) ? s1 : a->T - 1 - s1;
     p.b_c2[d] = d;
   }
   int rc = gemm_dispatch(A, B, p, 128, 0, st);

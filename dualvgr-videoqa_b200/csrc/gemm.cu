@@ -119,7 +119,7 @@ __device__ __forceinline__ void epi_lstm_fwd(const GemmParams& p, int dir, int s
   if (seq >= p.M || col0 >= p.N) return;
   const int H = p.N >> 2;
   const int S = p.M;
-  const int t = dir == 0 ? p.s : p.T - 1 - p.s;
+  const int t = (dir & 1) == 0 ? p.s : p.T - 1 - p.s;
   const int j0 = col0 >> 2;
   __nv_bfloat16* g = p.gates + ((long long)t * p.M + seq) * p.gates_ld + (long long)dir * p.gates_dir + col0;
   const long long st = ((long long)dir * (p.T + 1) + p.s) * S * H + (long long)seq * H + j0;   // slot s
@@ -184,18 +184,40 @@ __device__ __forceinline__ void epi_lstm_fwd(const GemmParams& p, int dir, int s
 //   dh[8]      : gradient w.r.t. h after step s (everything already summed)
 //   reads  gates (activated i,f,g,o), c_hist[s], c_hist[s+1], dc (running)
 //   writes dgates (pre-activation) in place, dc <- dc_total * f
-__device__ __forceinline__ void lstm_cell_bwd8(const GemmParams& p, int dir, int seq, int j0, const float (&dh)[8]) {
+__device__ __forceinline__ void lstm_cell_bwd8(const GemmParams& p, int dir, int seq, int j0, float (&dh)[8]) {
   const int H = p.N;   // bwd GEMM has N = H
   const int S = p.M;
-  const int t = dir == 0 ? p.s : p.T - 1 - p.s;
+  const int t = (dir & 1) == 0 ? p.s : p.T - 1 - p.s;
   __nv_bfloat16* g = p.gates + ((long long)t * p.M + seq) * p.gates_ld + (long long)dir * p.gates_dir + 4 * j0;
   const long long st = ((long long)dir * (p.T + 1) + p.s) * S * H + (long long)seq * H + j0;
   const long long st1 = st + (long long)S * H;
   float* dcp = p.dc + ((long long)dir * S + seq) * H + j0;
   const bool live = (p.seq_len == nullptr) || (t < p.seq_len[seq]);
-  if (!live) {   // padded step: dgates = 0 (already zero from forward), dc and dh pass through (dh handled by caller)
-    return;
+  if (live && p.dh_ext != nullptr) {
+    // gradient arriving on the per-step hidden output [S][T][ld] (column dir*H); padded steps emit constant zeros
+    uint4 ev = *reinterpret_cast<const uint4*>(p.dh_ext + ((long long)seq * p.T + t) * p.seq_out_ld + (long long)dir * H + j0);
+    const uint32_t* ew = reinterpret_cast<const uint32_t*>(&ev);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float2 e2 = unpack_bf16x2(ew[u]);
+      dh[2 * u] += e2.x; dh[2 * u + 1] += e2.y;
+    }
   }
+  if (p.dh_carry != nullptr) {
+    // padded steps carry the state forward, so their incoming dh must reach the last live step unchanged
+    float* cp = p.dh_carry + ((long long)dir * S + seq) * H + j0;
+    float4 c0 = *reinterpret_cast<float4*>(cp), c1 = *reinterpret_cast<float4*>(cp + 4);
+    dh[0] += c0.x; dh[1] += c0.y; dh[2] += c0.z; dh[3] += c0.w;
+    dh[4] += c1.x; dh[5] += c1.y; dh[6] += c1.z; dh[7] += c1.w;
+    if (live) {
+      *reinterpret_cast<float4*>(cp) = make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(cp + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+      *reinterpret_cast<float4*>(cp) = make_float4(dh[0], dh[1], dh[2], dh[3]);
+      *reinterpret_cast<float4*>(cp + 4) = make_float4(dh[4], dh[5], dh[6], dh[7]);
+    }
+  }
+  if (!live) return;   // dgates stay zero (written by the forward pass); dc passes through untouched
   uint4 gin[4];
 #pragma unroll
   for (int q = 0; q < 4; ++q) gin[q] = reinterpret_cast<const uint4*>(g)[q];
@@ -236,18 +258,6 @@ __device__ __forceinline__ void epi_lstm_bwd(const GemmParams& p, int dir, int s
     float dh[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) dh[u] = __uint_as_float(r[8 * q + u]);
-    if (p.dh_ext != nullptr) {
-      // external gradient on the per-step hidden output (question encoder): [S, T, ld] at column dir*H
-      const int t = dir == 0 ? p.s : p.T - 1 - p.s;
-      const __nv_bfloat16* e = p.dh_ext + ((long long)seq * p.T + t) * p.seq_out_ld + (long long)dir * p.N + col0 + 8 * q;
-      uint4 ev = *reinterpret_cast<const uint4*>(e);
-      const uint32_t* ew = reinterpret_cast<const uint32_t*>(&ev);
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        float2 e2 = unpack_bf16x2(ew[u]);
-        dh[2 * u] += e2.x; dh[2 * u + 1] += e2.y;
-      }
-    }
     lstm_cell_bwd8(p, dir, seq, col0 + 8 * q, dh);
   }
 }
@@ -423,16 +433,6 @@ __global__ void lstm_bwd_first_kernel(const GemmParams p, const __nv_bfloat16* _
     } else {
 #pragma unroll
       for (int u = 0; u < 8; ++u) dh[u] = 0.f;
-    }
-    if (p.dh_ext != nullptr) {
-      const int t = dir == 0 ? p.s : p.T - 1 - p.s;
-      uint4 ev = *reinterpret_cast<const uint4*>(p.dh_ext + ((long long)seq * p.T + t) * p.seq_out_ld + (long long)dir * H + jg * 8);
-      const uint32_t* ew = reinterpret_cast<const uint32_t*>(&ev);
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        float2 e2 = unpack_bf16x2(ew[u]);
-        dh[2 * u] += e2.x; dh[2 * u + 1] += e2.y;
-      }
     }
     lstm_cell_bwd8(p, dir, seq, jg * 8, dh);
   }

@@ -47,6 +47,7 @@ struct GemmParams {
   __nv_bfloat16* h_last;    // optional [S, h_last_ld]: final hidden, written at column dir*H when s == T-1
   long long h_last_ld;
   float* dc;                // [dir][S][H] running cell gradient (bwd)
+  float* dh_carry;          // optional [dir][S][H]: dh passed through padded steps (bwd, with seq_len)
   const __nv_bfloat16* dh_ext;  // optional extra dh for this step (unused for the appearance encoder)
   const int* seq_len;       // optional [S]: steps at t >= len keep the state (question encoder)
   __nv_bfloat16* seq_out;   // optional [S][T][seq_out_ld] per-step hidden output (zero at padded steps)

@@ -2,8 +2,9 @@
 and VisualAppearanceEncoder (:191-234).
 
 The appearance encoder (70-76 % of the model's FLOPs) runs entirely in the library: one prologue pass, one
-tcgen05 GEMM for the W_ih product of both directions and 16 fused recurrent steps. The question encoder (3 % of FLOPs, not
-in the north-star kernel list) stays on PyTorch/cuDNN, as SURVEY.md §2 row 7 allows."""
+tcgen05 GEMM for the W_ih product of both directions and 16 fused recurrent steps. The question encoder's two BiLSTMs run
+on the same fused recurrence (4 directions per step, length-masked in the cell epilogue), which removes cuDNN, the
+pack/unpack round trip and the host sync on question_len from the step."""
 import torch
 import torch.nn as nn
 from torch.nn import functional as F
@@ -50,15 +51,19 @@ class InputUnitLinguisticDynamic(nn.Module):
         self.final_dropout = nn.Dropout(0.18)
 
     def forward(self, questions, question_len):
-        """-> (question_embedding [B,D], words [B,L,W], per-token states [B,L,D] with zero rows at padded positions)."""
-        max_len = questions.size(1)
+        """-> (question_embedding [B,D] bf16, words [B,L,W] fp32, per-token states [B,L,D] bf16, zero rows at padded
+        positions). The embedding lookup / dropout / tanh are three tiny PyTorch ops; both BiLSTMs run as one fused
+        4-direction recurrence in the library (no pack_padded_sequence, no host sync on question_len)."""
         words = self.tanh(self.embedding_dropout(self.encoder_embed(questions)))
-        output_embedding, _ = self.concatRNN(words, question_len, max_len)
-        lengths = question_len.detach().to("cpu", torch.int64)
-        packed = nn.utils.rnn.pack_padded_sequence(words, lengths, batch_first=True, enforce_sorted=False)
-        _, (h, _) = self.encoder(packed)
-        q = torch.cat([h[0], h[1]], -1) if self.bidirectional else h[0]
-        return self.final_dropout(q), words, output_embedding
+        if not (self.bidirectional and isinstance(self.encoder, nn.LSTM)):
+            raise NotImplementedError("the sm_100a question encoder is the bidirectional LSTM pair DualVGR builds")
+        r, e = self.concatRNN.rnn, self.encoder
+        params = []
+        for m in (r, e):
+            params += [m.weight_ih_l0, m.weight_hh_l0, m.bias_ih_l0, m.bias_hh_l0,
+                       m.weight_ih_l0_reverse, m.weight_hh_l0_reverse, m.bias_ih_l0_reverse, m.bias_hh_l0_reverse]
+        dq, q = ag.QuestionEncoderFn.apply(words.float(), question_len.to(torch.int32), *params)
+        return ag.dropout(q, self.final_dropout.p, self.training), words, dq
 
 
 class VisualAppearanceEncoder(nn.Module):

@@ -163,6 +163,8 @@ def lstm_bwd(gates, whh, h_hist, c_hist, dh_last, seq_len=None, dh_seq=None):
         a.dh_last, a.dh_last_ld = dh_last.data_ptr(), dh_last.stride(0)
     if seq_len is not None:
         a.seq_len = seq_len.data_ptr()
+        carry = torch.zeros((D, S, H), dtype=torch.float32, device=gates.device)
+        a.dh_carry = carry.data_ptr()
     if dh_seq is not None:
         a.dh_seq, a.seq_out_ld = dh_seq.data_ptr(), D * H
     st = _stream()

@@ -84,7 +84,7 @@ int dvgr_gemm_reference(const void* A, long long a_rs, long long a_ks, const voi
  *                              after dvgr_lstm_step_bwd it holds the pre-activation gate gradients
  *   h_hist [D][T+1][S][H] bf16, c_hist [D][T+1][S][H] f32 : slot 0 = initial state (zeros), slot s+1 = state after step s
  *   whh    [D][4H][H] bf16 (rows interleaved like the gate columns)
- *   direction d processes time t = s (d = 0) or T-1-s (d = 1) at step s
+ *   direction d processes time t = s (d even) or T-1-s (d odd) at step s; up to 4 directions per call (two BiLSTMs)
  * ------------------------------------------------------------------------------------------------------------------ */
 typedef struct dvgr_lstm_args {
   int S, H, T, ndir, s;
@@ -102,6 +102,7 @@ typedef struct dvgr_lstm_args {
   const void* dh_last;      /* [S][dh_last_ld] bf16 gradient of h_last (used at s = T-1) */
   long long dh_last_ld;
   const void* dh_seq;       /* optional [S][T][seq_out_ld] bf16 gradient of seq_out */
+  float* dh_carry;          /* [D][S][H] f32, zero before the first backward step; required with seq_len */
 } dvgr_lstm_args;
 
 int dvgr_lstm_step_fwd(const dvgr_lstm_args* args, void* stream);

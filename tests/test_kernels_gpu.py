@@ -348,3 +348,42 @@ def test_prep_cast_adam(ops):
         assert abs(float(nsq) - float(g.double().pow(2).sum())) < 1e-4 * float(g.double().pow(2).sum())
         ops.adam_step(p, gc, m, v, 1e-4, step, max_norm=12.0, norm_sq=nsq)
     assert rel(p, pr.detach()) < 1e-6
+
+
+def test_masked_four_direction_lstm_matches_oracle(ops):
+    """Question-encoder recurrence: 4 directions, per-sequence lengths, per-step outputs, padded-step gradient carry.
+    Checked against the oracle's step-by-step LSTM (which restates pack_padded_sequence semantics)."""
+    import dualvgr_videoqa_b200.autograd as ag
+    torch.manual_seed(11)
+    B, L, W, H = 70, 7, 300, 384
+    words = torch.randn(B, L, W).tanh()
+    qlen = torch.randint(1, L + 1, (B,)); qlen[0] = L; qlen[1] = 1
+    params = []
+    for _ in range(2):
+        for _d in range(2):
+            params += [torch.randn(4 * H, W) * 0.05, torch.randn(4 * H, H) * 0.05, torch.randn(4 * H) * 0.1, torch.randn(4 * H) * 0.1]
+    pb = [p.to(BF16).float() for p in params]                      # weights as the kernel sees them (bf16-rounded)
+    for i in (2, 3, 6, 7, 10, 11, 14, 15):
+        pb[i] = params[i]                                           # biases stay fp32
+    wb = words.to(BF16).float()
+    cp = [p.clone().cuda().requires_grad_(True) for p in pb]
+    wc = wb.clone().cuda().requires_grad_(True)
+    dq, q = ag.QuestionEncoderFn.apply(wc, qlen.int().cuda(), *cp)
+    rp = [p.double().requires_grad_(True) for p in pb]
+    wr = wb.double().requires_grad_(True)
+    outs = []
+    for base in (0, 8):
+        of, hf = orc.lstm_direction(wr, rp[base], rp[base + 1], rp[base + 2], rp[base + 3], False, qlen)
+        ob, hb = orc.lstm_direction(wr, rp[base + 4], rp[base + 5], rp[base + 6], rp[base + 7], True, qlen)
+        outs.append((torch.cat([of, ob], -1), torch.cat([hf, hb], -1)))
+    dq_ref, q_ref = outs[0][0], outs[1][1]
+    assert rel(dq, dq_ref) < 1e-2 and rel(q, q_ref) < 1e-2
+    pad = torch.arange(L)[None, :] >= qlen[:, None]
+    assert float(dq.float().cpu()[pad].abs().max()) == 0.0
+    g1, g1r = bf(torch.randn(B, L, 2 * H))
+    g2, g2r = bf(torch.randn(B, 2 * H))
+    ((dq_ref * g1r.detach()).sum() + (q_ref * g2r.detach()).sum()).backward()
+    ((dq.float() * g1.float()).sum() + (q.float() * g2.float()).sum()).backward()
+    assert rel(wc.grad, wr.grad) < 2e-2
+    for i, (a, b) in enumerate(zip(cp, rp)):
+        assert rel(a.grad, b.grad) < 2e-2, i

@@ -54,6 +54,8 @@ class LstmArgs(ctypes.Structure):
 lib.dvgr_last_error.restype = ctypes.c_char_p
 lib.dvgr_abi_version.restype = c_int
 lib.dvgr_launch_count.restype = c_ll
+lib.dvgr_set_seed_offset.argtypes = [c_void_p]
+lib.dvgr_set_seed_offset.restype = None
 
 
 def check(rc, what=""):
@@ -120,10 +122,10 @@ lib.dvgr_colsum_workspace.restype = c_ll
 colsum = _sig("dvgr_colsum", [P, c_int, c_ll, c_ll, c_int, P, P, c_int, c_float, P])
 sumsq_blocks = _sig("dvgr_sumsq_blocks", [])
 sumsq = _sig("dvgr_sumsq", [P, c_ll, P, P, P])
-adam_step = _sig("dvgr_adam_step", [P, P, P, P, c_ll, c_float, c_float, c_float, c_float, c_int, c_float, P, c_float, P])
+adam_step = _sig("dvgr_adam_step", [P, P, P, P, c_ll, c_float, c_float, c_float, c_float, c_int, c_float, P, c_float, P, P])
 
 EXPORTED = [
-    "dvgr_last_error", "dvgr_abi_version", "dvgr_launch_count", "dvgr_gemm", "dvgr_gemm_reference",
+    "dvgr_last_error", "dvgr_abi_version", "dvgr_launch_count", "dvgr_set_seed_offset", "dvgr_gemm", "dvgr_gemm_reference",
     "dvgr_lstm_step_fwd", "dvgr_lstm_step_bwd", "dvgr_gat_attn_fwd", "dvgr_gat_attn_bwd", "dvgr_qattn_fwd",
     "dvgr_qattn_bwd", "dvgr_gate_fwd", "dvgr_gate_bwd", "dvgr_view_attn_fwd", "dvgr_view_attn_bwd_blocks",
     "dvgr_view_attn_bwd", "dvgr_mfb_fwd", "dvgr_mfb_bwd", "dvgr_readout_fwd", "dvgr_readout_bwd", "dvgr_bn_fwd",

@@ -20,6 +20,9 @@ int set_error(const char* fmt, ...) {
   return 1;
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+static const unsigned long long* g_seed_off = nullptr;
+const unsigned long long* seed_offset_ptr() { return g_seed_off; }
+void g_seed_off_set(const unsigned long long* p) { g_seed_off = p; }
 
 static void fill_lstm_params(GemmParams& p, const dvgr_lstm_args& a) {
   p.gates = reinterpret_cast<__nv_bfloat16*>(a.gates);
@@ -58,6 +61,7 @@ extern "C" {
 const char* dvgr_last_error(void) { return g_err; }
 int dvgr_abi_version(void) { return DVGR_ABI_VERSION; }
 long long dvgr_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+void dvgr_set_seed_offset(const unsigned long long* dev_ptr) { dvgr::g_seed_off_set(dev_ptr); }
 
 int dvgr_gemm(const dvgr_gemm_args* a, void* stream) {
   if (!a) return set_error("dvgr_gemm: null args");

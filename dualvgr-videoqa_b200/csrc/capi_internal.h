@@ -10,6 +10,8 @@ namespace dvgr {
 // printf-style thread-local error message; returns a non-zero status for `return set_error(...)`.
 int set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+const unsigned long long* seed_offset_ptr();
+void g_seed_off_set(const unsigned long long* p);
 
 int gemm_dispatch(const dvgr_operand& A, const dvgr_operand& B, GemmParams p, int bn, int max_ctas, cudaStream_t stream);
 int lstm_bwd_first(const GemmParams& p, const void* dh_last, long long dh_ld, cudaStream_t stream);

@@ -611,7 +611,7 @@ extern "C" int dvgr_prep_features(const float* in, void* out, long long S, int T
   if (C % 8 != 0) return set_error("prep_features: C=%d must be a multiple of 8", C);
   const long long n = S * T * (long long)C / 8;
   if (n <= 0) return 0;
-  DropoutCfg dc{seed, drop_stream, p};
+  DropoutCfg dc{seed, drop_stream, p, seed_offset_ptr()};
   prep_features_kernel<<<grid_for(n, 256, 148 * 32), 256, 0, ST(stream)>>>(in, BF(out), S, T, C, do_tanh, time_major, dc);
   DVGR_CHECK_LAUNCH("prep_features");
   return 0;
@@ -631,7 +631,7 @@ extern "C" int dvgr_dropout(const void* in, void* out, long long n, float p, uns
                             unsigned int drop_stream, void* stream) {
   if (n % 8 != 0) return set_error("dropout: n=%lld must be a multiple of 8", n);
   if (n <= 0) return 0;
-  DropoutCfg dc{seed, drop_stream, p};
+  DropoutCfg dc{seed, drop_stream, p, seed_offset_ptr()};
   dropout_kernel<<<grid_for(n / 8), 256, 0, ST(stream)>>>(CBF(in), BF(out), n / 8, dc);
   DVGR_CHECK_LAUNCH("dropout");
   return 0;
@@ -641,7 +641,7 @@ extern "C" int dvgr_act_bwd(const void* dy, const void* y, void* out, long long 
                             unsigned long long seed, unsigned int drop_stream, void* stream) {
   if (n % 8 != 0) return set_error("act_bwd: n=%lld must be a multiple of 8", n);
   if (n <= 0) return 0;
-  DropoutCfg dc{seed, drop_stream, p};
+  DropoutCfg dc{seed, drop_stream, p, seed_offset_ptr()};
   act_bwd_kernel<<<grid_for(n / 8), 256, 0, ST(stream)>>>(CBF(dy), CBF(y), BF(out), n / 8, act, accumulate, dc);
   DVGR_CHECK_LAUNCH("act_bwd");
   return 0;

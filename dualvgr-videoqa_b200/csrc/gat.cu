@@ -41,6 +41,7 @@ struct GatParams {
   float slope;                // LeakyReLU negative slope (0.01)
   float p_att, p_out;         // dropout probabilities (0 in eval)
   unsigned long long seed;
+  const unsigned long long* seed_off;
 };
 
 struct GatSmem {
@@ -173,7 +174,7 @@ __global__ void __launch_bounds__(kGatThreads) gat_attn_fwd_kernel(const GatPara
   gat_stage(p, gr, b, sm);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
-  const DropoutCfg datt{p.seed, gr.drop_stream, p.p_att};
+  const DropoutCfg datt{p.seed, gr.drop_stream, p.p_att, p.seed_off};
   for (int pr = warp; pr < N * K; pr += nwarps) {
     const int k = pr / N, i = pr - k * N;
     gat_softmax_row(p, sm, k, i, lane);
@@ -188,7 +189,7 @@ __global__ void __launch_bounds__(kGatThreads) gat_attn_fwd_kernel(const GatPara
   __syncthreads();
 
   // aggregation: out[i][c] = dropout(ELU(sum_j P[k(c)][i][j] * Wh[j][c]))
-  const DropoutCfg dout{p.seed, gr.drop_stream + 1u, p.p_out};
+  const DropoutCfg dout{p.seed, gr.drop_stream + 1u, p.p_out, p.seed_off};
   __nv_bfloat16* outp = gr.out + (long long)b * N * p.ld_out;
   const __nv_bfloat162* wh2 = reinterpret_cast<const __nv_bfloat162*>(sm.wh);
   for (int pair = tid; pair < D / 2; pair += blockDim.x) {
@@ -261,8 +262,8 @@ __global__ void __launch_bounds__(kGatThreads) gat_attn_bwd_kernel(const GatPara
 
   gat_stage(p, gr, b, sm);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
-  const DropoutCfg datt{p.seed, gr.drop_stream, p.p_att};
-  const DropoutCfg dout{p.seed, gr.drop_stream + 1u, p.p_out};
+  const DropoutCfg datt{p.seed, gr.drop_stream, p.p_att, p.seed_off};
+  const DropoutCfg dout{p.seed, gr.drop_stream + 1u, p.p_out, p.seed_off};
 
   // 1. probabilities (pre-dropout, ungated) and dz = dout * mask * ELU'(z)
   for (int pr = warp; pr < N * K; pr += nwarps) gat_softmax_row(p, sm, pr / N, pr % N, lane);
@@ -434,6 +435,7 @@ static int fill_gat(GatParams& p, const dvgr_gat_args* a, bool bwd) {
   p.B = a->B; p.N = a->N; p.D = a->D; p.heads = a->heads;
   p.ld_wh = a->ld_wh; p.ld_out = a->ld_out;
   p.adj = a->adj; p.slope = a->slope; p.p_att = a->p_att; p.p_out = a->p_out; p.seed = a->seed;
+  p.seed_off = seed_offset_ptr();
   for (int i = 0; i < a->n_graphs; ++i) {
     const dvgr_gat_graph& s = a->graphs[i];
     GatGraph& d = p.g[i];

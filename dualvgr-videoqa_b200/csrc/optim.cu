@@ -36,7 +36,13 @@ __global__ void sumsq_final_kernel(const float* __restrict__ partial, int n, flo
 // norm_sq: device scalar = sum of squares of the (already averaged) gradient. grad_scale multiplies g before use.
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, long long n, float lr, float b1, float b2, float eps, float bc1,
-                            float bc2_sqrt, float max_norm, const float* __restrict__ norm_sq, float grad_scale) {
+                            float bc2_sqrt, float max_norm, const float* __restrict__ norm_sq, float grad_scale,
+                            const int* __restrict__ step_dev) {
+  if (step_dev != nullptr) {      // device-resident step counter (CUDA-graph replay): bias corrections computed here
+    const float t = (float)step_dev[0];
+    bc1 = 1.f - powf(b1, t);
+    bc2_sqrt = sqrtf(1.f - powf(b2, t));
+  }
   float clip = 1.f;
   if (max_norm > 0.f && norm_sq != nullptr) {
     const float total = sqrtf(norm_sq[0]) * grad_scale;
@@ -74,15 +80,16 @@ extern "C" int dvgr_sumsq(const float* g, long long n, float* partial_ws, float*
 
 extern "C" int dvgr_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n,
                               float lr, float beta1, float beta2, float eps, int step, float max_norm,
-                              const float* norm_sq, float grad_scale, void* stream) {
+                              const float* norm_sq, float grad_scale, const int* step_dev, void* stream) {
   if (n <= 0) return 0;
-  if (step < 1) return set_error("adam: step must be >= 1");
+  if (step < 1 && step_dev == nullptr) return set_error("adam: step must be >= 1");
+  if (step < 1) step = 1;
   const float bc1 = 1.f - powf(beta1, (float)step);
   const float bc2 = 1.f - powf(beta2, (float)step);
   long long blocks = (n + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   adam_kernel<<<(int)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, bc1, sqrtf(bc2), max_norm, norm_sq, grad_scale);
+      params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, bc1, sqrtf(bc2), max_norm, norm_sq, grad_scale, step_dev);
   DVGR_CHECK_LAUNCH("adam_step");
   return 0;
 }

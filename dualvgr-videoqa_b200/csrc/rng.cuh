@@ -19,9 +19,11 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
 }
 
 struct DropoutCfg {
-  unsigned long long seed;   // per-step seed
+  unsigned long long seed;   // per-forward seed (host side)
   unsigned int stream;       // distinguishes the dropout sites of one step
   float p;                   // drop probability; 0 disables
+  const unsigned long long* seed_off;   // optional device counter added to the seed: lets a captured CUDA graph draw
+                                        // fresh masks on every replay (dvgr_set_seed_offset)
 };
 
 // Keep-scale (0 or 1/(1-p)) for 4 consecutive elements starting at index 4*quad.
@@ -30,8 +32,9 @@ __device__ __forceinline__ void dropout_scale4(const DropoutCfg& c, unsigned lon
     s[0] = s[1] = s[2] = s[3] = 1.f;
     return;
   }
+  const unsigned long long seed = c.seed + (c.seed_off != nullptr ? *c.seed_off : 0ull);
   uint4 r = philox4x32_10(make_uint4((uint32_t)quad, (uint32_t)(quad >> 32), c.stream, 0x2545F491u),
-                          make_uint2((uint32_t)c.seed, (uint32_t)(c.seed >> 32)));
+                          make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
   const float inv = 1.f / (1.f - c.p);
   const uint32_t thr = (uint32_t)(c.p * 4294967296.0f);
   s[0] = r.x >= thr ? inv : 0.f;

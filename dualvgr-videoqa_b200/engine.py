@@ -42,6 +42,9 @@ class TrainEngine:
                 p.grad = self.gflat[off:off + p.numel()].view_as(p)
                 off += n
         self.step_count = 0
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)     # device-side step counter (graph replay)
+        self.seed_dev = torch.zeros(1, dtype=torch.int64, device=dev)     # device-side dropout seed offset
+        self.graph = None
         self.numel = total
         if self.world > 1:      # replicas must start identical (the reference seeds every process the same, train.py:425-428)
             dist.broadcast(self.flat, src=0, group=self.pg)
@@ -79,8 +82,49 @@ class TrainEngine:
         if self.world > 1:
             dist.all_reduce(self.gflat, op=dist.ReduceOp.SUM, group=self.pg)
         self.step_count += 1
+        self.step_dev += 1
         scale = 1.0 / self.world
         nsq = ops.sumsq(self.gflat)
         ops.adam_step(self.flat, self.gflat, self.m, self.v, self.lr, self.step_count, self.betas[0], self.betas[1],
-                      self.eps, max_norm=self.max_norm, norm_sq=nsq, grad_scale=scale)
+                      self.eps, max_norm=self.max_norm, norm_sq=nsq, grad_scale=scale, step_dev=self.step_dev)
         ag.invalidate_weight_cache()
+
+    # ------------------------------------------------------------------------------------------------------------
+    # whole-step CUDA graph: forward, losses, backward, all-reduce, clip + Adam, weight re-casts = ONE graph launch.
+    # Everything that changes between steps lives on the device (inputs in static buffers, dropout seed offset, Adam step).
+    def capture(self, app, mot, question, question_len, answers, warmup=3):
+        from . import _lib
+        self.static = {k: torch.empty_like(v) for k, v in
+                       dict(app=app, mot=mot, q=question, qlen=question_len, ans=answers).items()}
+        for k, v in dict(app=app, mot=mot, q=question, qlen=question_len, ans=answers).items():
+            self.static[k].copy_(v)
+        _lib.lib.dvgr_set_seed_offset(self.seed_dev.data_ptr())
+
+        def body():
+            self.seed_dev += 1
+            st = self.static
+            return self.train_step(st["app"], st["mot"], st["q"], st["qlen"], st["ans"])
+
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                body()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.static_loss = body()
+        ag.invalidate_weight_cache()
+        return self.graph
+
+    def load_batch(self, app, mot, question, question_len, answers, non_blocking=True):
+        st = self.static
+        for k, v in dict(app=app, mot=mot, q=question, qlen=question_len, ans=answers).items():
+            st[k].copy_(v, non_blocking=non_blocking)
+
+    def replay(self):
+        """One captured train step on the batch currently in the static buffers; returns the (device) loss tensor."""
+        self.graph.replay()
+        self.step_count += 1
+        return self.static_loss

@@ -449,6 +449,7 @@ def sumsq(g):
     return out
 
 
-def adam_step(p, g, m, v, lr, step, beta1=0.9, beta2=0.999, eps=1e-8, max_norm=0.0, norm_sq=None, grad_scale=1.0):
+def adam_step(p, g, m, v, lr, step, beta1=0.9, beta2=0.999, eps=1e-8, max_norm=0.0, norm_sq=None, grad_scale=1.0,
+              step_dev=None):
     _lib.check(_lib.adam_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), lr, beta1, beta2, eps, step, max_norm,
-                              _ptr(norm_sq), grad_scale, _stream()), "dvgr_adam_step")
+                              _ptr(norm_sq), grad_scale, _ptr(step_dev), _stream()), "dvgr_adam_step")

@@ -29,6 +29,9 @@ const char* dvgr_last_error(void);
 int dvgr_abi_version(void);
 /* Number of kernels launched by this library in the calling process so far (bench.py reports the delta). */
 long long dvgr_launch_count(void);
+/* Optional device-resident counter added to every dropout seed (NULL disables). A train step captured in a CUDA graph
+ * increments it on the device, so each replay draws fresh Philox masks although the kernel arguments are frozen. */
+void dvgr_set_seed_offset(const unsigned long long* dev_ptr);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * GEMM family (tcgen05 + TMEM + TMA).  D[b][m][n] = epi( sum_k A[b][m][k] * B[b][n][k] ), bf16 operands, fp32 accumulate.
@@ -240,7 +243,8 @@ int dvgr_sumsq_blocks(void);
 int dvgr_sumsq(const float* g, long long n, float* partial_ws, float* out, void* stream);
 int dvgr_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr,
                    float beta1, float beta2, float eps, int step, float max_norm, const float* norm_sq,
-                   float grad_scale, void* stream);
+                   float grad_scale, const int* step_dev /* optional device step counter, overrides `step` */,
+                   void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,87 @@
+"""Train-step engine on the GPU: flat-buffer clip+Adam against torch.optim.Adam + clip_grad_norm_ on the same gradients,
+and whole-step CUDA-graph replay against eager steps."""
+import copy
+
+import pytest
+import torch
+
+import dualvgr_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def no_dropout(model):
+    for m in model.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+        if hasattr(m, "dropout") and isinstance(getattr(m, "dropout"), float):
+            m.dropout = 0.0
+
+
+def make(cfg):
+    import dualvgr_videoqa_b200.model.models as M
+    B, N, L, A, V, U = cfg
+    model = M.DualVGR(vocab=orc.make_vocab(V, A), num_of_nodes=N, graph_module="GAT", graph_layers=1, unit_layers=U)
+    model.load_state_dict(orc.make_state_dict(U, A, V), strict=True)
+    no_dropout(model)
+    return model.cuda().train(), [t.cuda() for t in orc.make_inputs(B, N, L, A, V)]
+
+
+def test_flat_optimizer_matches_torch_adam_with_clipping():
+    from dualvgr_videoqa_b200.engine import TrainEngine
+    import dualvgr_videoqa_b200.utils as U
+    cfg = (4, 8, 6, 10, 30, 1)
+    model, batch = make(cfg)
+    ref_model = copy.deepcopy(model)
+    eng = TrainEngine(model, lr=1e-3, max_norm=0.05)          # tiny max_norm so the clip is active
+    opt = torch.optim.Adam(ref_model.parameters(), lr=1e-3)
+    N = cfg[1]
+    for step in range(3):
+        eng.train_step(*batch)
+        opt.zero_grad()
+        out = ref_model(*batch[:4])
+        logits, _, _, ca, cm, aq, mq = out
+        loss = torch.nn.functional.cross_entropy(logits, batch[4])
+        n = len(aq)
+        loss = loss + sum(U.common_loss(ca[i], cm[i]) for i in range(n)) / n \
+            + 1e-8 * sum(U.loss_dependence(aq[i], ca[i], N) + U.loss_dependence(mq[i], cm[i], N) for i in range(n)) / n
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(ref_model.parameters(), max_norm=0.05)
+        opt.step()
+    num = den = 0.0
+    for (n1, p1), (n2, p2) in zip(model.named_parameters(), ref_model.named_parameters()):
+        num += float((p1 - p2).double().pow(2).sum()); den += float(p2.double().pow(2).sum())
+    assert (num / den) ** 0.5 < 1e-4      # same kernels produce the gradients; only the optimizer differs
+
+
+def test_graph_replay_matches_eager_steps():
+    from dualvgr_videoqa_b200.engine import TrainEngine
+    cfg = (6, 20, 8, 32, 60, 2)
+    m1, batch = make(cfg)
+    m2 = copy.deepcopy(m1)
+    e1, e2 = TrainEngine(m1, lr=1e-3), TrainEngine(m2, lr=1e-3)
+    e1.capture(*batch, warmup=3)
+    l1 = [float(e1.replay()) for _ in range(2)]
+    l2 = [float(e2.train_step(*batch)) for _ in range(5)][3:]
+    assert all(abs(a - b) < 2e-3 * abs(b) for a, b in zip(l1, l2)), (l1, l2)
+    d = float((e1.flat - e2.flat).norm() / e2.flat.norm())
+    assert d < 1e-3, d
+    # a replay on a different batch really uses the new inputs
+    app2 = batch[0] * 0.5
+    e1.load_batch(app2, *batch[1:])
+    l_new = float(e1.replay())
+    assert abs(l_new - l1[-1]) > 1e-6
+
+
+def test_graph_replay_draws_fresh_dropout_masks():
+    import dualvgr_videoqa_b200.model.models as M
+    from dualvgr_videoqa_b200.engine import TrainEngine
+    B, N, L, A, V, U = 6, 20, 8, 32, 60, 1
+    model = M.DualVGR(vocab=orc.make_vocab(V, A), num_of_nodes=N, graph_module="GAT", graph_layers=1, unit_layers=U)
+    model.load_state_dict(orc.make_state_dict(U, A, V), strict=True)
+    model = model.cuda().train()
+    batch = [t.cuda() for t in orc.make_inputs(B, N, L, A, V)]
+    eng = TrainEngine(model, lr=0.0)                   # lr 0: parameters frozen, only the dropout masks can change the loss
+    eng.capture(*batch, warmup=3)
+    losses = [float(eng.replay()) for _ in range(4)]
+    assert len(set(round(x, 6) for x in losses)) > 1, losses

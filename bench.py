@@ -208,6 +208,8 @@ def run_ours(args):
     barrier()
     ms = e0.elapsed_time(e1)
     launches = L.launch_count() - n0
+    if use_graph:
+        launches = eng.launches_per_replay * args.steps      # kernels of libdualvgr_b200.so inside each replayed graph
     clocks = sampler.stop() if rank == 0 else None
     # the dominant kernel (W_ih tcgen05 GEMM of the appearance encoder, forward) timed live with CUDA events on its
     # launching stream at the workload's exact shape; operands (335 MB + 503 MB) exceed the 126 MB L2

@@ -113,8 +113,10 @@ class TrainEngine:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
+        n0 = _lib.launch_count()
         with torch.cuda.graph(self.graph):
             self.static_loss = body()
+        self.launches_per_replay = _lib.launch_count() - n0    # library kernels recorded into the graph
         ag.invalidate_weight_cache()
         return self.graph
 

@@ -33,8 +33,11 @@ def test_flat_optimizer_matches_torch_adam_with_clipping():
     cfg = (4, 8, 6, 10, 30, 1)
     model, batch = make(cfg)
     ref_model = copy.deepcopy(model)
-    eng = TrainEngine(model, lr=1e-3, max_norm=0.05)          # tiny max_norm so the clip is active
-    opt = torch.optim.Adam(ref_model.parameters(), lr=1e-3)
+    p0 = [p.detach().clone() for p in ref_model.parameters()]
+    # small lr: Adam's first steps move EVERY weight by ~lr regardless of gradient size, so a large lr makes the
+    # trajectory chaotic under bf16 rounding and the comparison meaningless. max_norm tiny so the clip is active.
+    eng = TrainEngine(model, lr=1e-5, max_norm=0.05)
+    opt = torch.optim.Adam(ref_model.parameters(), lr=1e-5)
     N = cfg[1]
     for step in range(3):
         eng.train_step(*batch)
@@ -49,9 +52,9 @@ def test_flat_optimizer_matches_torch_adam_with_clipping():
         torch.nn.utils.clip_grad_norm_(ref_model.parameters(), max_norm=0.05)
         opt.step()
     num = den = 0.0
-    for (n1, p1), (n2, p2) in zip(model.named_parameters(), ref_model.named_parameters()):
-        num += float((p1 - p2).double().pow(2).sum()); den += float(p2.double().pow(2).sum())
-    assert (num / den) ** 0.5 < 1e-4      # same kernels produce the gradients; only the optimizer differs
+    for p1, p2, q in zip(model.parameters(), ref_model.parameters(), p0):
+        num += float((p1 - p2).double().pow(2).sum()); den += float((p2 - q).double().pow(2).sum())
+    assert (num / den) ** 0.5 < 2e-2      # relative error of the accumulated UPDATE (same gradient kernels, other optimizer)
 
 
 def test_graph_replay_matches_eager_steps():
@@ -59,13 +62,16 @@ def test_graph_replay_matches_eager_steps():
     cfg = (6, 20, 8, 32, 60, 2)
     m1, batch = make(cfg)
     m2 = copy.deepcopy(m1)
-    e1, e2 = TrainEngine(m1, lr=1e-3), TrainEngine(m2, lr=1e-3)
+    start = torch.cat([p.detach().reshape(-1) for p in m1.parameters()]).clone()
+    e1, e2 = TrainEngine(m1, lr=1e-5), TrainEngine(m2, lr=1e-5)
     e1.capture(*batch, warmup=3)
     l1 = [float(e1.replay()) for _ in range(2)]
     l2 = [float(e2.train_step(*batch)) for _ in range(5)][3:]
     assert all(abs(a - b) < 2e-3 * abs(b) for a, b in zip(l1, l2)), (l1, l2)
-    d = float((e1.flat - e2.flat).norm() / e2.flat.norm())
-    assert d < 1e-3, d
+    c1 = torch.cat([p.detach().reshape(-1) for p in m1.parameters()])
+    c2 = torch.cat([p.detach().reshape(-1) for p in m2.parameters()])
+    d = float((c1 - c2).norm() / (c2 - start).norm())
+    assert d < 2e-2, d                     # relative error of the accumulated update after 5 steps
     # a replay on a different batch really uses the new inputs
     app2 = batch[0] * 0.5
     e1.load_batch(app2, *batch[1:])

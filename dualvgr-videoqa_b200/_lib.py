@@ -37,7 +37,7 @@ class GemmArgs(ctypes.Structure):
         ("C", c_void_p), ("ldc", c_ll), ("c_batch", c_ll),
         ("out_f32", c_int), ("act", c_int), ("beta", c_int),
         ("bias", c_void_p), ("bias_batch", c_ll), ("row_map", c_void_p),
-        ("bn", c_int), ("max_ctas", c_int),
+        ("bn", c_int), ("max_ctas", c_int), ("ksplit", c_int),
     ]
 
 
@@ -111,7 +111,17 @@ readout_bwd = _sig("dvgr_readout_bwd", [P, c_ll, P, P, P, P, c_int, c_int, c_int
 bn_fwd = _sig("dvgr_bn_fwd", [P, c_int, c_int, P, P, P, P, c_int, c_float, c_float, P, P, P, P])
 bn_bwd = _sig("dvgr_bn_bwd", [P, P, c_int, c_int, P, P, P, c_int, P, P, P, P])
 cross_entropy = _sig("dvgr_cross_entropy", [P, P, c_int, c_int, c_float, P, P, c_ll, P, P])
-pair_loss = _sig("dvgr_pair_loss", [P, P, c_int, c_int, c_int, c_int, c_float, P, P, P, c_int, c_int, P])
+
+
+class PairJob(ctypes.Structure):
+    _fields_ = [("x", c_void_p), ("y", c_void_p), ("dx", c_void_p), ("dy", c_void_p), ("loss_part", c_void_p),
+                ("loss_col", c_int), ("loss_ld", c_int), ("mode", c_int), ("accumulate_x", c_int),
+                ("accumulate_y", c_int), ("coef", c_float)]
+
+
+lib.dvgr_pair_loss_workspace.argtypes = [c_int, c_int, c_int, c_int]
+lib.dvgr_pair_loss_workspace.restype = c_ll
+pair_loss_multi = _sig("dvgr_pair_loss_multi", [ctypes.POINTER(PairJob), c_int, c_int, c_int, c_int, P, P])
 prep_features = _sig("dvgr_prep_features", [P, P, c_ll, c_int, c_int, c_int, c_int, c_float, c_ull, c_uint, P])
 cast_rows = _sig("dvgr_cast_rows", [P, c_ll, P, c_ll, c_int, c_int, c_int, c_int, P])
 dropout = _sig("dvgr_dropout", [P, P, c_ll, c_float, c_ull, c_uint, P])
@@ -129,7 +139,7 @@ EXPORTED = [
     "dvgr_lstm_step_fwd", "dvgr_lstm_step_bwd", "dvgr_gat_attn_fwd", "dvgr_gat_attn_bwd", "dvgr_qattn_fwd",
     "dvgr_qattn_bwd", "dvgr_gate_fwd", "dvgr_gate_bwd", "dvgr_view_attn_fwd", "dvgr_view_attn_bwd_blocks",
     "dvgr_view_attn_bwd", "dvgr_mfb_fwd", "dvgr_mfb_bwd", "dvgr_readout_fwd", "dvgr_readout_bwd", "dvgr_bn_fwd",
-    "dvgr_bn_bwd", "dvgr_cross_entropy", "dvgr_pair_loss", "dvgr_prep_features", "dvgr_cast_rows", "dvgr_dropout",
+    "dvgr_bn_bwd", "dvgr_cross_entropy", "dvgr_pair_loss_workspace", "dvgr_pair_loss_multi", "dvgr_prep_features", "dvgr_cast_rows", "dvgr_dropout",
     "dvgr_act_bwd", "dvgr_add", "dvgr_colsum_workspace", "dvgr_colsum", "dvgr_sumsq_blocks", "dvgr_sumsq",
     "dvgr_adam_step",
 ]

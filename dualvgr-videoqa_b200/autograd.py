@@ -76,6 +76,56 @@ def _c(t):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+# direct gradient accumulation (engine mode): when the parameters' .grad are pre-bound views of the engine's flat fp32
+# gradient buffer, weight-gradient GEMMs add into them directly (split-K, fp32 atomics) and bias column-sums accumulate in
+# place; the Function then returns None for that gradient, so autograd launches no separate accumulation kernel.
+# ---------------------------------------------------------------------------------------------------------------------
+DIRECT_GRAD = [False]
+DIRECT_STATS = {"hits": 0, "misses": 0}
+
+
+def grad_target(params):
+    """[sum rows, cols] fp32 view over the .grad of `params` if they are bound, fp32, and contiguous in this order."""
+    if not DIRECT_GRAD[0]:
+        return None
+    g0 = getattr(params[0], "grad", None)
+    if g0 is None:
+        DIRECT_STATS["misses"] += 1
+        return None
+    ptr, rows, cols = g0.data_ptr(), 0, params[0].shape[-1]
+    for p in params:
+        g = getattr(p, "grad", None)
+        if g is None or g.dtype != F32 or not g.is_contiguous() or g.data_ptr() != ptr or p.shape[-1] != cols:
+            DIRECT_STATS["misses"] += 1
+            return None
+        ptr += g.numel() * 4
+        rows += g.numel() // cols
+    DIRECT_STATS["hits"] += 1
+    return torch.as_strided(g0, (rows, cols), (cols, 1))
+
+
+def grad_groups(model):
+    """Parameter groups that the fused kernels treat as ONE row-concatenated matrix; the engine lays each group out
+    contiguously in its flat buffers so that grad_target() can hand the whole block to a single weight-gradient GEMM."""
+    groups = []
+    app = getattr(model, "visual_appearance_input_unit", None)
+    if app is not None:
+        e = app.encoder
+        groups += [[e.weight_ih_l0, e.weight_ih_l0_reverse], [e.weight_hh_l0, e.weight_hh_l0_reverse]]
+    lin = getattr(model, "linguistic_input_unit", None)
+    if lin is not None:
+        r, e = lin.concatRNN.rnn, lin.encoder
+        groups += [[r.weight_ih_l0, r.weight_ih_l0_reverse, e.weight_ih_l0, e.weight_ih_l0_reverse],
+                   [r.weight_hh_l0, r.weight_hh_l0_reverse, e.weight_hh_l0, e.weight_hh_l0_reverse]]
+    unit = getattr(model, "visual_input_unit", None)
+    if unit is not None and hasattr(unit, "acGCN"):
+        for i in range(unit.layers):
+            for pair in ((unit.acGCN[i], unit.appearance_GCN[i]), (unit.mcGCN[i], unit.motion_GCN[i])):
+                groups.append([att.W.weight for g in pair for att in g.attentions])
+    return groups
+
+
+# ---------------------------------------------------------------------------------------------------------------------
 class LinearFn(Function):
     """y = act(x W^T + b) on the tcgen05 GEMM; backward = activation', dgrad (W read MN-major), wgrad, bias column-sum.
     x: [..., K'] bf16 with K' >= K (zero padded to a multiple of 8); W fp32 [N, K]; output bf16 (or fp32: the logits)."""
@@ -88,6 +138,7 @@ class LinearFn(Function):
         y = ops.linear_fwd(x2, w, bias=bias, act=act, out_dtype=F32 if out_f32 else BF16)
         ctx.save_for_backward(x2, w, y if (act not in (None, "none") and not act_grad_folded) else None)
         ctx.act, ctx.out_f32, ctx.lead, ctx.K, ctx.has_bias = act, out_f32, x.shape[:-1], weight.shape[1], bias is not None
+        ctx.wparam, ctx.bparam = weight, bias
         return y.view(*x.shape[:-1], weight.shape[0])
 
     @staticmethod
@@ -109,10 +160,27 @@ class LinearFn(Function):
         if ctx.needs_input_grad[0]:
             dx = ops.linear_dgrad(d, w).view(*ctx.lead, w.shape[1])
         if ctx.needs_input_grad[1]:
-            dw = ops.linear_wgrad(d, x2)[:N, :ctx.K]
+            tgt = grad_target([ctx.wparam])
+            if tgt is not None:
+                ops.linear_wgrad(d, x2, out=tgt, atomic=True, rows=N, cols=ctx.K)
+            else:
+                dw = ops.linear_wgrad(d, x2)[:N, :ctx.K]
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = ops.colsum(d)[:N]
+            tgt = _bias_target(ctx.bparam)
+            if tgt is not None:
+                ops.colsum(d[:, :N], out=tgt, accumulate=True)
+            else:
+                db = ops.colsum(d)[:N]
         return dx, dw, db, None, None, None
+
+
+def _bias_target(b):
+    if not DIRECT_GRAD[0]:
+        return None
+    g = getattr(b, "grad", None)
+    if g is None or g.dtype != F32 or not g.is_contiguous():
+        return None
+    return g
 
 
 def linear(x, weight, bias=None, act=None, out_f32=False, act_grad_folded=False):
@@ -174,6 +242,7 @@ class AppearanceEncoderFn(Function):
             out = ops.dropout_raw(h_last, p_o, seed, sid + 1)
         ctx.save_for_backward(xa, whh, gates, h_hist, c_hist)
         ctx.cfg = (B, N, T, Dv, S, H, p_o, seed, sid)
+        ctx.wih_params, ctx.whh_params = [w_ih, w_ih_r], [w_hh, w_hh_r]
         return out.view(B, N, 2 * H)
 
     @staticmethod
@@ -186,16 +255,23 @@ class AppearanceEncoderFn(Function):
         ops.lstm_bwd(gates, whh, h_hist, c_hist, dh)            # gates now holds d(pre-activation gates)
         dg = gates.view(T * S, 8 * H)
         unmap = _lstm_unmap(H, 2, dg.device)
-        dwih = ops.linear_wgrad(dg, xa, row_map=unmap, bn=256)  # [8H, Dv] fp32 in nn.LSTM row order
+        t_ih, t_hh = grad_target(ctx.wih_params), grad_target(ctx.whh_params)
+        if t_ih is not None:
+            ops.linear_wgrad(dg, xa, out=t_ih, row_map=unmap, atomic=True)
+            dwih = None
+        else:
+            dwih = ops.linear_wgrad(dg, xa, row_map=unmap, bn=256)  # [8H, Dv] fp32 in nn.LSTM row order
         db = torch.empty(8 * H, dtype=F32, device=dg.device)
         db[unmap.long()] = ops.colsum(dg)
         # dW_hh[d] = sum_s dgates[t_d(s)]^T h_hist[d][s]   (segmented MN-major reduction, both directions in one launch)
         kin = (S + 63) // 64
-        dwhh = torch.empty((2, 4 * H, H), dtype=F32, device=dg.device)
+        dwhh = t_hh.view(2, 4 * H, H) if t_hh is not None else torch.empty((2, 4 * H, H), dtype=F32, device=dg.device)
         ops.gemm(gates, 1, h_hist, 1, 4 * H, H, T * kin * 64, dwhh, ldc=H, batch=2, c_batch=4 * H * H,
                  row_map=_lstm_unmap(H, 1, dg.device), a_c0=[0, 4 * H], a_c2=[0, T - 1], a_c2_step=[1, -1],
-                 b_c2=[0, 0], b_c2_step=[1, 1], b_c3=[0, 1], k_inner=kin)
-        return (None, dwih[:4 * H], dwhh[0], db[:4 * H], db[:4 * H], dwih[4 * H:], dwhh[1], db[4 * H:], db[4 * H:],
+                 b_c2=[0, 0], b_c2_step=[1, 1], b_c3=[0, 1], k_inner=kin, beta=2 if t_hh is not None else 0)
+        g_ih = (None, None) if dwih is None else (dwih[:4 * H], dwih[4 * H:])
+        g_hh = (None, None) if t_hh is not None else (dwhh[0], dwhh[1])
+        return (None, g_ih[0], g_hh[0], db[:4 * H], db[:4 * H], g_ih[1], g_hh[1], db[4 * H:], db[4 * H:],
                 None, None, None)
 
 
@@ -229,6 +305,7 @@ class QuestionEncoderFn(Function):
         h_hist, c_hist, h_last, seq_out = ops.lstm_fwd(gates, whh, seq_len=qlen, want_seq=True)
         ctx.save_for_backward(x, wih, whh, gates, h_hist, c_hist, qlen)
         ctx.cfg = (B, L, W, Wp, H)
+        ctx.wih_params, ctx.whh_params = w_ih, w_hh
         return seq_out[:, :, :2 * H].contiguous(), h_last[:, 2 * H:].contiguous()
 
     @staticmethod
@@ -249,18 +326,24 @@ class QuestionEncoderFn(Function):
         if ctx.needs_input_grad[0]:
             dwords = ops.linear_dgrad(dg, wih).view(L, B, Wp)[:, :, :W].transpose(0, 1).float()
         unmap = _lstm_unmap(H, 4, dev)
-        dwih = ops.linear_wgrad(dg, x2, row_map=unmap)[:, :W]
+        t_ih, t_hh = grad_target(ctx.wih_params), grad_target(ctx.whh_params)
+        if t_ih is not None:
+            ops.linear_wgrad(dg, x2, out=t_ih, row_map=unmap, atomic=True, cols=W)
+            dwih = None
+        else:
+            dwih = ops.linear_wgrad(dg, x2, row_map=unmap)[:, :W]
         db = torch.empty(16 * H, dtype=F32, device=dev)
         db[unmap.long()] = ops.colsum(dg)
         kin = (B + 63) // 64
-        dwhh = torch.empty((4, 4 * H, H), dtype=F32, device=dev)
+        dwhh = t_hh.view(4, 4 * H, H) if t_hh is not None else torch.empty((4, 4 * H, H), dtype=F32, device=dev)
         ops.gemm(gates, 1, h_hist, 1, 4 * H, H, L * kin * 64, dwhh, ldc=H, batch=4, c_batch=4 * H * H,
                  row_map=_lstm_unmap(H, 1, dev), a_c0=[4 * H * d for d in range(4)], a_c2=[0, L - 1, 0, L - 1],
-                 a_c2_step=[1, -1, 1, -1], b_c2=[0, 0, 0, 0], b_c2_step=[1, 1, 1, 1], b_c3=[0, 1, 2, 3], k_inner=kin)
+                 a_c2_step=[1, -1, 1, -1], b_c2=[0, 0, 0, 0], b_c2_step=[1, 1, 1, 1], b_c3=[0, 1, 2, 3], k_inner=kin,
+                 beta=2 if t_hh is not None else 0)
         grads = []
         for d in range(4):
             sl = slice(4 * H * d, 4 * H * (d + 1))
-            grads += [dwih[sl], dwhh[d], db[sl], db[sl]]
+            grads += [None if dwih is None else dwih[sl], None if t_hh is not None else dwhh[d], db[sl], db[sl]]
         return (dwords, None) + tuple(grads)
 
 
@@ -352,6 +435,7 @@ class GatLayerFn(Function):
                                    streams=streams, outs=out_list, want_f32=True)
         ctx.save_for_backward(adj, *xts, *wbufs, *whs, *outs_s, *gate_list, *avecs)
         ctx.cfg = (B, N, D, M, heads, pdrop, seed, sid, streams, graph_stream, of_stream)
+        ctx.wparams = [[gp[g][4 * k] for g in of_stream[s] for k in range(heads)] for s in range(ns)]
         return tuple(outs_s) + tuple(f32s)
 
     @staticmethod
@@ -381,7 +465,11 @@ class GatLayerFn(Function):
             gs = of_stream[s]
             cnt = len(gs)
             dwh, wb, xt = dwh_s[s], wbufs[s], xts[s]
-            dWs = torch.empty((cnt, D, D), dtype=F32, device=dev)
+            tgt = grad_target(ctx.wparams[s])
+            direct = tgt is not None
+            dWs = tgt.view(cnt, D, D) if direct else torch.empty((cnt, D, D), dtype=F32, device=dev)
+            wbn, wks = ops.wgrad_split(D, D, M, batch=cnt) if direct else (0, 0)
+            wkw = dict(beta=2, bn=wbn, ksplit=wks) if direct else {}
             if pdrop > 0:
                 dxt = torch.empty((cnt, M, D), dtype=BF16, device=dev)
                 ops.gemm(dwh, 0, wb, 1, M, D, D, dxt, ldc=D, batch=cnt, c_batch=M * D, a_c2=list(range(cnt)),
@@ -390,24 +478,24 @@ class GatLayerFn(Function):
                 for i in range(1, cnt):
                     ops.act_bwd(dxt[i], None, "none", out=dx, accumulate=True, p=pdrop, seed=seed, stream_id=sid + gs[i])
                 ops.gemm(dwh, 1, xt, 1, D, D, M, dWs, ldc=D, batch=cnt, c_batch=D * D, a_c2=list(range(cnt)),
-                         b_c2=list(range(cnt)))
+                         b_c2=list(range(cnt)), **wkw)
             else:
                 dx = ops.linear_dgrad(dwh[0], wb[0])
                 for i in range(1, cnt):
                     ops.linear_dgrad(dwh[i], wb[i], out=dx, beta=True)
                 ops.gemm(dwh, 1, xt, 1, D, D, M, dWs, ldc=D, batch=cnt, c_batch=D * D, a_c2=list(range(cnt)),
-                         b_c2=[0] * cnt)
+                         b_c2=[0] * cnt, **wkw)
             dxs.append(dx.view(B, N, D))
             dg = dgates[gs[0]]
             for g in gs[1:]:
                 dg = dg + dgates[g]
             dgs.append(dg)
             for i, g in enumerate(gs):
-                dW[g], db[g] = dWs[i], ops.colsum(dwh[i])
+                dW[g], db[g] = (None if direct else dWs[i]), ops.colsum(dwh[i])
         grads = []
         for g in range(G):
             for k in range(heads):
-                grads += [dW[g][k * Dh:(k + 1) * Dh], db[g][k * Dh:(k + 1) * Dh],
+                grads += [None if dW[g] is None else dW[g][k * Dh:(k + 1) * Dh], db[g][k * Dh:(k + 1) * Dh],
                           davecs[g][k, :2 * Dh].reshape(1, 2 * Dh), davecs[g][k, 2 * Dh:].reshape(1)]
         return (None, None, None, None, None) + tuple(dxs) + tuple(dgs) + tuple(grads)
 
@@ -506,6 +594,31 @@ class CrossEntropyFn(Function):
     def backward(ctx, g, _):
         (dlog,) = ctx.saved_tensors
         return dlog[:, :ctx.A].float() * g, None
+
+
+class AuxLossFn(Function):
+    """The three auxiliary-loss pairs of one DualVGR unit (reference train.py:148-154, utils.py:10-31) in ONE fused call:
+    coef_com * sum (G_ca - G_cm)^2 + coef_dep * (HSIC(aq, ca) + HSIC(mq, cm)), value and all four gradients together.
+    Returns (combined scalar, [3] tensor of the coef-scaled terms (not differentiated))."""
+
+    @staticmethod
+    def forward(ctx, ca, cm, aq, mq, coef_com, coef_dep):
+        ca, cm, aq, mq = (_c(t.float()) for t in (ca, cm, aq, mq))
+        B, N, D = ca.shape
+        d_ca, d_cm = torch.zeros_like(ca), torch.zeros_like(cm)       # two addends each -> atomic adds are deterministic
+        d_aq, d_mq = torch.empty_like(aq), torch.empty_like(mq)
+        jobs = [dict(x=ca, y=cm, mode=0, coef=coef_com, dx=d_ca, dy=d_cm, acc_x=2, acc_y=2),
+                dict(x=aq, y=ca, mode=1, coef=coef_dep, dx=d_aq, dy=d_ca, acc_x=0, acc_y=2),
+                dict(x=mq, y=cm, mode=1, coef=coef_dep, dx=d_mq, dy=d_cm, acc_x=0, acc_y=2)]
+        vals = ops.pair_loss_multi(jobs, B, N, D, ca)
+        ctx.save_for_backward(d_ca, d_cm, d_aq, d_mq)
+        ctx.mark_non_differentiable(vals)
+        return vals.sum(), vals
+
+    @staticmethod
+    def backward(ctx, g, _):
+        d_ca, d_cm, d_aq, d_mq = ctx.saved_tensors
+        return d_ca * g, d_cm * g, d_aq * g, d_mq * g, None, None
 
 
 class PairLossFn(Function):

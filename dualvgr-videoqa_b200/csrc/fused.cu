@@ -385,18 +385,14 @@ __global__ void prep_features_kernel(const float* __restrict__ in, bf16* __restr
     const float4 b = reinterpret_cast<const float4*>(in)[2 * i + 1];
     float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
     if (dc.p > 0.f) {
-      float s0[4], s1[4];
-      dropout_scale4(dc, 2 * i, s0);
-      dropout_scale4(dc, 2 * i + 1, s1);
+      float sc[8];
+      dropout_scale8(dc, i, sc);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        f[q] *= s0[q];
-        f[4 + q] *= s1[q];
-      }
+      for (int q = 0; q < 8; ++q) f[q] *= sc[q];
     }
     if (do_tanh) {
 #pragma unroll
-      for (int q = 0; q < 8; ++q) f[q] = tanhf_(f[q]);
+      for (int q = 0; q < 8; ++q) f[q] = tanh_fast(f[q]);   // output is bf16: the 2^-11 approximation is below its ulp
     }
     long long o = i;
     if (time_major) {
@@ -426,15 +422,11 @@ __global__ void cast_rows_kernel(const float* __restrict__ in, long long ld_in, 
 // out = in * dropout mask (the same kernel is its own backward)
 __global__ void dropout_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, long long n8, DropoutCfg dc) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
-    float f[8], s0[4], s1[4];
+    float f[8], sc[8];
     load8(in + i * 8, f);
-    dropout_scale4(dc, 2 * i, s0);
-    dropout_scale4(dc, 2 * i + 1, s1);
+    dropout_scale8(dc, i, sc);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      f[q] *= s0[q];
-      f[4 + q] *= s1[q];
-    }
+    for (int q = 0; q < 8; ++q) f[q] *= sc[q];
     store8(out + i * 8, f);
   }
 }
@@ -446,14 +438,10 @@ __global__ void act_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restri
     float d[8], yy[8];
     load8(dy + i * 8, d);
     if (dc.p > 0.f) {
-      float s0[4], s1[4];
-      dropout_scale4(dc, 2 * i, s0);
-      dropout_scale4(dc, 2 * i + 1, s1);
+      float sc[8];
+      dropout_scale8(dc, i, sc);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        d[q] *= s0[q];
-        d[4 + q] *= s1[q];
-      }
+      for (int q = 0; q < 8; ++q) d[q] *= sc[q];
     }
     if (act != 0) {
       load8(y + i * 8, yy);

@@ -160,8 +160,24 @@ __device__ __forceinline__ void gat_softmax_row(const GatParams& p, const GatSme
   }
 }
 
-__device__ __forceinline__ unsigned long long att_index(const GatParams& p, int b, int k, int i, int j) {
-  return (((unsigned long long)b * p.heads + k) * p.N + i) * p.N + j;
+// Dropout stream layout (any bijection works as long as forward and backward agree; these make ONE Philox call serve
+// eight mask elements where the kernels consume them):
+//   attention mask (b, k, i, j)  : call ((b*K + k)*N + i) * ceil(N/8) + j/8 , element j%8
+//   output mask    (b, i, c)     : call ((b*(D/2) + c/2) * ceil(N/4) + i/4 , element (i%4)*2 + (c&1)
+__device__ __forceinline__ float att_keep(const GatParams& p, const DropoutCfg& cfg, int b, int k, int i, int j) {
+  if (cfg.p <= 0.f) return 1.f;
+  float sc[8];
+  const unsigned long long call = (((unsigned long long)b * p.heads + k) * p.N + i) * ((p.N + 7) >> 3) + (j >> 3);
+  dropout_scale8(cfg, call, sc);
+  float v = sc[0];
+#pragma unroll
+  for (int q = 1; q < 8; ++q) v = ((j & 7) == q) ? sc[q] : v;
+  return v;
+}
+__device__ __forceinline__ void out_keep8(const GatParams& p, const DropoutCfg& cfg, int b, int pair, int rowquad,
+                                          float (&sc)[8]) {
+  const unsigned long long call = ((unsigned long long)b * (p.D >> 1) + pair) * ((p.N + 3) >> 2) + rowquad;
+  dropout_scale8(cfg, call, sc);
 }
 
 // ------------------------------------------------------------------------------------------------------ forward
@@ -180,15 +196,12 @@ __global__ void __launch_bounds__(kGatThreads) gat_attn_fwd_kernel(const GatPara
     gat_softmax_row(p, sm, k, i, lane);
     __syncwarp();
     float* Prow = sm.P + ((size_t)k * N + i) * NP;
-    for (int j = lane; j < N; j += 32) {
-      float v = Prow[j] * sm.gate[j];                       // gate multiplies the values: fold it into P
-      if (p.p_att > 0.f) v *= dropout_scale1(datt, att_index(p, b, k, i, j));
-      Prow[j] = v;
-    }
+    for (int j = lane; j < N; j += 32)
+      Prow[j] = Prow[j] * sm.gate[j] * att_keep(p, datt, b, k, i, j);   // gate multiplies the values: fold it into P
   }
   __syncthreads();
 
-  // aggregation: out[i][c] = dropout(ELU(sum_j P[k(c)][i][j] * Wh[j][c]))
+  // aggregation: out[i][c] = dropout(ELU(sum_j P[k(c)][i][j] * Wh[j][c])) ; 2 columns x 8 rows per thread and pass
   const DropoutCfg dout{p.seed, gr.drop_stream + 1u, p.p_out, p.seed_off};
   __nv_bfloat16* outp = gr.out + (long long)b * N * p.ld_out;
   const __nv_bfloat162* wh2 = reinterpret_cast<const __nv_bfloat162*>(sm.wh);
@@ -214,18 +227,19 @@ __global__ void __launch_bounds__(kGatThreads) gat_attn_fwd_kernel(const GatPara
           }
         }
       }
+      float keep[2][8];
+      if (p.p_out > 0.f) {
+        out_keep8(p, dout, b, pair, i0 >> 2, keep[0]);
+        out_keep8(p, dout, b, pair, (i0 >> 2) + 1, keep[1]);
+      }
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
         const int i = i0 + r;
         if (i < N) {
           float o0 = eluf_(acc[r][0]), o1 = eluf_(acc[r][1]);
           if (p.p_out > 0.f) {
-            const unsigned long long idx = ((unsigned long long)b * N + i) * D + c;
-            float sc[4];
-            dropout_scale4(dout, idx >> 2, sc);
-            const int h = (int)(idx & 3);   // c is even -> h in {0, 2}
-            o0 *= sc[h];
-            o1 *= sc[h + 1];
+            o0 *= keep[r >> 2][(r & 3) * 2];
+            o1 *= keep[r >> 2][(r & 3) * 2 + 1];
           }
           *reinterpret_cast<__nv_bfloat162*>(outp + (long long)i * p.ld_out + c) = __floats2bfloat162_rn(o0, o1);
           if (gr.out_f32 != nullptr)
@@ -237,7 +251,7 @@ __global__ void __launch_bounds__(kGatThreads) gat_attn_fwd_kernel(const GatPara
 }
 
 // ------------------------------------------------------------------------------------------------------ backward
-// extra shared memory: dz [N][D] bf16, dP [heads][N][NP] f32, ds/dt [heads][N] f32, dg [N] f32
+// extra shared memory: dz [N][D] bf16, dP [heads][N][NP] f32 (dP~ -> du -> transposed P~), ds/dt [heads][N], dg [N]
 __host__ __device__ inline size_t gat_smem_bwd_extra(int N, int D, int heads) {
   const int NP = round4(N);
   return (size_t)N * D * 2 + (size_t)heads * N * NP * 4 + (size_t)heads * N * 4 * 2 + (size_t)round4(N) * 4 + 16;
@@ -252,78 +266,86 @@ __global__ void __launch_bounds__(kGatThreads) gat_attn_bwd_kernel(const GatPara
   unsigned char* ext = smem_raw + gat_smem_common(N, D, K);
   __nv_bfloat16* dz = reinterpret_cast<__nv_bfloat16*>(ext);
   ext += (size_t)N * D * 2;
-  float* dP = reinterpret_cast<float*>(ext);       // dP~ then du
+  float* dP = reinterpret_cast<float*>(ext);
   ext += (size_t)K * N * NP * 4;
   float* ds = reinterpret_cast<float*>(ext);
   ext += (size_t)K * N * 4;
   float* dt = reinterpret_cast<float*>(ext);
   ext += (size_t)K * N * 4;
   float* dg = reinterpret_cast<float*>(ext);
+  __shared__ float dc_s[kMaxHeads];
 
   gat_stage(p, gr, b, sm);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
   const DropoutCfg datt{p.seed, gr.drop_stream, p.p_att, p.seed_off};
   const DropoutCfg dout{p.seed, gr.drop_stream + 1u, p.p_out, p.seed_off};
 
-  // 1. probabilities (pre-dropout, ungated) and dz = dout * mask * ELU'(z)
+  // 1. probabilities (pre-dropout, ungated); dz = (dout [+ dout_f32]) * mask * ELU'(z), 4 rows x 2 columns per unit
   for (int pr = warp; pr < N * K; pr += nwarps) gat_softmax_row(p, sm, pr / N, pr % N, lane);
   for (int i = tid; i < N; i += blockDim.x) dg[i] = 0.f;
   {
     const __nv_bfloat16* hp = gr.out + (long long)b * N * p.ld_out;
     const __nv_bfloat16* dop = gr.dout + (long long)b * N * p.ld_out;
-    const float keep = 1.f - p.p_out;
-    for (int pair = tid; pair < N * (D / 2); pair += blockDim.x) {
-      const int i = pair / (D / 2), c = (pair - i * (D / 2)) * 2;
-      float2 h = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(hp + (long long)i * p.ld_out + c));
-      float2 d = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dop + (long long)i * p.ld_out + c));
-      if (gr.dout_f32 != nullptr) {
-        const float2 e = *reinterpret_cast<const float2*>(gr.dout_f32 + ((long long)b * N + i) * D + c);
-        d.x += e.x;
-        d.y += e.y;
+    const float keepf = 1.f - p.p_out;
+    const int quads = (N + 3) >> 2;
+    for (int u = tid; u < quads * (D / 2); u += blockDim.x) {
+      const int rq = u / (D / 2), pair = u - rq * (D / 2), c = pair * 2;
+      float keep[8];
+      if (p.p_out > 0.f) out_keep8(p, dout, b, pair, rq, keep);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int i = rq * 4 + r;
+        if (i >= N) break;
+        float2 h = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(hp + (long long)i * p.ld_out + c));
+        float2 d = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dop + (long long)i * p.ld_out + c));
+        if (gr.dout_f32 != nullptr) {
+          const float2 e = *reinterpret_cast<const float2*>(gr.dout_f32 + ((long long)b * N + i) * D + c);
+          d.x += e.x;
+          d.y += e.y;
+        }
+        if (p.p_out > 0.f) {
+          d.x *= keep[2 * r];
+          d.y *= keep[2 * r + 1];
+          h.x *= keepf;   // recover ELU(z) of the kept elements (dropped ones have zero gradient anyway)
+          h.y *= keepf;
+        }
+        d.x *= elu_grad_from_out(h.x);
+        d.y *= elu_grad_from_out(h.y);
+        *reinterpret_cast<__nv_bfloat162*>(dz + (size_t)i * D + c) = __floats2bfloat162_rn(d.x, d.y);
       }
-      if (p.p_out > 0.f) {
-        const unsigned long long idx = ((unsigned long long)b * N + i) * D + c;
-        float sc[4];
-        dropout_scale4(dout, idx >> 2, sc);
-        const int q = (int)(idx & 3);
-        d.x *= sc[q];
-        d.y *= sc[q + 1];
-        h.x *= keep;   // recover ELU(z) of the kept elements (dropped ones have zero gradient anyway)
-        h.y *= keep;
-      }
-      d.x *= elu_grad_from_out(h.x);
-      d.y *= elu_grad_from_out(h.y);
-      *reinterpret_cast<__nv_bfloat162*>(dz + (size_t)i * D + c) = __floats2bfloat162_rn(d.x, d.y);
     }
   }
   __syncthreads();
 
-  // 2. dP~[k][i][j] = g_j * sum_{c in head k} dz[i][c] * Wh[j][c]   (one warp per (k, i), lanes over c)
+  // 2. dP[k][i][j] = mask_ij * g_j * sum_{c in head k} dz[i][c] * Wh[j][c]   (one warp per (k, i), lanes over c)
   for (int pr = warp; pr < N * K; pr += nwarps) {
     const int k = pr / N, i = pr - k * N;
     float zreg[8];
-    const int cnt = (Dh + 31) / 32;   // <= 8 for Dh <= 256
-    for (int q = 0; q < cnt; ++q) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
       const int c = lane + 32 * q;
       zreg[q] = c < Dh ? __bfloat162float(dz[(size_t)i * D + k * Dh + c]) : 0.f;
     }
+    float mine[2] = {0.f, 0.f};
     for (int j = 0; j < N; ++j) {
       float acc = 0.f;
-      for (int q = 0; q < cnt; ++q) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
         const int c = lane + 32 * q;
         if (c < Dh) acc += zreg[q] * __bfloat162float(sm.wh[(size_t)j * D + k * Dh + c]);
       }
       acc = warp_sum(acc);
-      if (lane == 0) {
-        float v = acc * sm.gate[j];
-        if (p.p_att > 0.f) v *= dropout_scale1(datt, att_index(p, b, k, i, j));
-        dP[((size_t)k * N + i) * NP + j] = v;    // = dP (gradient w.r.t. the pre-dropout probability)
-      }
+      if ((j & 31) == lane) mine[j >> 5] = acc;
+    }
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int j = lane + 32 * q;
+      if (j < N) dP[((size_t)k * N + i) * NP + j] = mine[q] * sm.gate[j] * att_keep(p, datt, b, k, i, j);
     }
   }
   __syncthreads();
 
-  // 3. softmax / LeakyReLU backward -> du (in place in dP), ds_i = sum_j du_ij
+  // 3. softmax / LeakyReLU backward -> du (in place), ds_i = sum_j du_ij
   for (int pr = warp; pr < N * K; pr += nwarps) {
     const int k = pr / N, i = pr - k * N;
     const float* Prow = sm.P + ((size_t)k * N + i) * NP;
@@ -345,67 +367,76 @@ __global__ void __launch_bounds__(kGatThreads) gat_attn_bwd_kernel(const GatPara
     if (lane == 0) ds[k * N + i] = srow;
   }
   __syncthreads();
-  // dt_j = sum_i du_ij ; dc
-  for (int pr = tid; pr < N * K; pr += blockDim.x) {
+  for (int pr = tid; pr < N * K; pr += blockDim.x) {      // dt_j = sum_i du_ij
     const int k = pr / N, j = pr - k * N;
     float a = 0.f;
     for (int i = 0; i < N; ++i) a += dP[((size_t)k * N + i) * NP + j];
     dt[k * N + j] = a;
   }
-  float* dav = gr.davec + ((long long)b * K) * (2 * Dh + 1);
-  __shared__ float dc_s[kMaxHeads];
-  for (int k = warp; k < K; k += nwarps) {     // dc_k = sum_ij du_ij = sum_i ds_i
+  for (int k = warp; k < K; k += nwarps) {                // dc_k = sum_i ds_i
     float a = 0.f;
     for (int i = lane; i < N; i += 32) a += ds[k * N + i];
     a = warp_sum(a);
     if (lane == 0) dc_s[k] = a;
   }
   __syncthreads();
-  // du is consumed: reuse its buffer for P~ = P * attention-dropout mask (what the forward aggregation used, ungated)
-  for (int e = tid; e < K * N * N; e += blockDim.x) {
-    const int k = e / (N * N), r = e - k * N * N, i = r / N, j = r - i * N;
-    float pt = sm.P[((size_t)k * N + i) * NP + j];
-    if (p.p_att > 0.f) pt *= dropout_scale1(datt, att_index(p, b, k, i, j));
-    dP[((size_t)k * N + i) * NP + j] = pt;
+  // du is consumed: reuse its buffer for the TRANSPOSED P~[k][j][i] = P_ij * mask_ij (ungated), zero padded along i
+  for (int e = tid; e < K * N * NP; e += blockDim.x) {
+    const int k = e / (N * NP), r = e - k * N * NP, j = r / NP, i = r - j * NP;
+    dP[e] = (i < N) ? sm.P[((size_t)k * N + i) * NP + j] * att_keep(p, datt, b, k, i, j) : 0.f;
   }
   __syncthreads();
 
-  // 4. dV_j[c] = sum_i P~[k][i][j] * dz[i][c] ; dWh = g*dV + ds*a1 + dt*a2 ; dgate ; da1, da2
+  // 4. dV_j[c] = sum_i P~_ij dz_i[c] ; dWh_j = g_j dV_j + ds_j a1 + dt_j a2 ; dgate_j ; da1, da2   (8 j x 2 columns / pass)
   const __nv_bfloat162* wh2 = reinterpret_cast<const __nv_bfloat162*>(sm.wh);
   const __nv_bfloat162* dz2 = reinterpret_cast<const __nv_bfloat162*>(dz);
   __nv_bfloat16* dwhp = gr.dwh + (long long)b * N * p.ld_wh;
+  float* dav = gr.davec + ((long long)b * K) * (2 * Dh + 1);
   for (int pair0 = 0; pair0 < D / 2; pair0 += blockDim.x) {
     const int pair = pair0 + tid;
     const bool active = pair < D / 2;
     const int c = active ? pair * 2 : 0;
-    const int k = c / Dh;
-    const int cl = c - k * Dh;
+    const int k = c / Dh, cl = c - k * Dh;
     const float* a1 = sm.avec + k * (2 * Dh + 1);
     const float* a2 = a1 + Dh;
+    const float* Ptk = dP + (size_t)k * N * NP;
     float da1x = 0.f, da1y = 0.f, da2x = 0.f, da2y = 0.f;
-    for (int j = 0; j < N; ++j) {
-      float dvx = 0.f, dvy = 0.f;
+    for (int j0 = 0; j0 < N; j0 += 8) {
+      float acc[8][2];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) acc[r][0] = acc[r][1] = 0.f;
       if (active) {
-        for (int i = 0; i < N; ++i) {
-          const float pt = dP[((size_t)k * N + i) * NP + j];
-          const float2 z = __bfloat1622float2(dz2[(size_t)i * (D / 2) + pair]);
-          dvx += pt * z.x;
-          dvy += pt * z.y;
+        for (int i0 = 0; i0 < N; i0 += 4) {
+          float2 z[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            z[q] = (i0 + q < N) ? __bfloat1622float2(dz2[(size_t)(i0 + q) * (D / 2) + pair]) : make_float2(0.f, 0.f);
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            if (j0 + r < N) {
+              const float4 pv = *reinterpret_cast<const float4*>(Ptk + (size_t)(j0 + r) * NP + i0);
+              acc[r][0] += pv.x * z[0].x + pv.y * z[1].x + pv.z * z[2].x + pv.w * z[3].x;
+              acc[r][1] += pv.x * z[0].y + pv.y * z[1].y + pv.z * z[2].y + pv.w * z[3].y;
+            }
+          }
         }
       }
-      const float2 w = active ? __bfloat1622float2(wh2[(size_t)j * (D / 2) + pair]) : make_float2(0.f, 0.f);
-      // gate gradient: dg_j += sum_c dV_j[c] * Wh[j][c]
-      float part = dvx * w.x + dvy * w.y;
-      part = warp_sum(part);
-      if (lane == 0) atomicAdd(&dg[j], part);
-      if (active) {
-        const float gj = sm.gate[j];
-        const float dsj = ds[k * N + j], dtj = dt[k * N + j];
-        const float ox = gj * dvx + dsj * a1[cl] + dtj * a2[cl];
-        const float oy = gj * dvy + dsj * a1[cl + 1] + dtj * a2[cl + 1];
-        *reinterpret_cast<__nv_bfloat162*>(dwhp + (long long)j * p.ld_wh + c) = __floats2bfloat162_rn(ox, oy);
-        da1x += dsj * w.x; da1y += dsj * w.y;
-        da2x += dtj * w.x; da2y += dtj * w.y;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const int j = j0 + r;
+        if (j >= N) break;                                  // uniform across the block
+        const float2 w = active ? __bfloat1622float2(wh2[(size_t)j * (D / 2) + pair]) : make_float2(0.f, 0.f);
+        float part = acc[r][0] * w.x + acc[r][1] * w.y;     // gate gradient: dg_j += sum_c dV_j[c] Wh_j[c]
+        part = warp_sum(part);
+        if (lane == 0) atomicAdd(&dg[j], part);
+        if (active) {
+          const float gj = sm.gate[j], dsj = ds[k * N + j], dtj = dt[k * N + j];
+          const float ox = gj * acc[r][0] + dsj * a1[cl] + dtj * a2[cl];
+          const float oy = gj * acc[r][1] + dsj * a1[cl + 1] + dtj * a2[cl + 1];
+          *reinterpret_cast<__nv_bfloat162*>(dwhp + (long long)j * p.ld_wh + c) = __floats2bfloat162_rn(ox, oy);
+          da1x += dsj * w.x; da1y += dsj * w.y;
+          da2x += dtj * w.x; da2y += dtj * w.y;
+        }
       }
     }
     if (active) {

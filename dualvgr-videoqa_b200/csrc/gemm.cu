@@ -34,7 +34,8 @@ namespace dvgr {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kGemmThreads = 256;
+constexpr int kGemmThreads = 384;   // warps 0-3: TMA / MMA / TMEM alloc / spare ; warps 4-11: epilogue (2 per TMEM lane quarter)
+constexpr int kEpiWarps = 8;
 
 template <int BN> struct TileCfg {
   static constexpr int A_BYTES = BM * BK * 2;
@@ -55,10 +56,10 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
 }
 
 // ------------------------------------------------------------------------------------------------ epilogues
-__device__ __forceinline__ void epi_linear(const GemmParams& p, int b, int row, int col0, const uint32_t (&r)[32]) {
+__device__ __forceinline__ void epi_linear(const GemmParams& p, int b, int row, int col0, const uint32_t (&r)[32], int ks) {
   if (row >= p.M || col0 >= p.N) return;
   const long long orow = p.row_map ? p.row_map[row] : row;
-  const float* bias = p.bias ? p.bias + (long long)b * p.bias_batch : nullptr;
+  const float* bias = (p.bias && ks == 0) ? p.bias + (long long)b * p.bias_batch : nullptr;
   float v[32];
   const int nvalid = min(32, p.N - col0);
 #pragma unroll
@@ -72,7 +73,17 @@ __device__ __forceinline__ void epi_linear(const GemmParams& p, int b, int row, 
   if (p.out_f32) {
     float* c = reinterpret_cast<float*>(p.C) + (long long)b * p.c_batch + orow * p.ldc + col0;
     const bool vec = (nvalid == 32) && ((reinterpret_cast<uintptr_t>(c) & 15) == 0);
-    if (vec) {
+    if (p.beta == 2) {
+      if (vec) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(c + 4 * j), "f"(v[4 * j]), "f"(v[4 * j + 1]),
+                       "f"(v[4 * j + 2]), "f"(v[4 * j + 3])
+                       : "memory");
+      } else {
+        for (int j = 0; j < nvalid; ++j) atomicAdd(c + j, v[j]);
+      }
+    } else if (vec) {
       float4* c4 = reinterpret_cast<float4*>(c);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -140,13 +151,14 @@ __device__ __forceinline__ void epi_lstm_fwd(const GemmParams& p, int dir, int s
   for (int u = 0; u < 8; ++u) {
     float2 a01 = unpack_bf16x2(gw[2 * u]);
     float2 a23 = unpack_bf16x2(gw[2 * u + 1]);
-    float ig = sigmoidf_(__uint_as_float(r[4 * u + 0]) + a01.x);
-    float fg = sigmoidf_(__uint_as_float(r[4 * u + 1]) + a01.y);
-    float gg = tanhf_(__uint_as_float(r[4 * u + 2]) + a23.x);
-    float og = sigmoidf_(__uint_as_float(r[4 * u + 3]) + a23.y);
+    // single-MUFU tanh / sigmoid: the gates and h are stored as bf16, whose ulp (2^-8) dwarfs the 2^-11 approximation
+    float ig = sigmoid_fast(__uint_as_float(r[4 * u + 0]) + a01.x);
+    float fg = sigmoid_fast(__uint_as_float(r[4 * u + 1]) + a01.y);
+    float gg = tanh_fast(__uint_as_float(r[4 * u + 2]) + a23.x);
+    float og = sigmoid_fast(__uint_as_float(r[4 * u + 3]) + a23.y);
     float c = fg * cprev[u] + ig * gg;
     cnew[u] = c;
-    hnew[u] = og * tanhf_(c);
+    hnew[u] = og * tanh_fast(c);
     go[2 * u] = pack_bf16x2(ig, fg);
     go[2 * u + 1] = pack_bf16x2(gg, og);
   }
@@ -235,7 +247,7 @@ __device__ __forceinline__ void lstm_cell_bwd8(const GemmParams& p, int dir, int
     float2 i_f = unpack_bf16x2(gw[2 * u]);
     float2 g_o = unpack_bf16x2(gw[2 * u + 1]);
     float ig = i_f.x, fg = i_f.y, gg = g_o.x, og = g_o.y;
-    float tc = tanhf_(cc[u]);
+    float tc = tanh_fast(cc[u]);
     float dct = dc[u] + dh[u] * og * (1.f - tc * tc);
     float d_o = dh[u] * tc * og * (1.f - og);
     float d_i = dct * gg * ig * (1.f - ig);
@@ -283,8 +295,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int m_blocks = (p.M + BM - 1) / BM;
   const int n_blocks = (p.N + BN - 1) / BN;
   const int k_blocks = (p.K + BK - 1) / BK;
+  const int ksplit = p.ksplit > 1 ? p.ksplit : 1;
+  const int kb_per = (k_blocks + ksplit - 1) / ksplit;
   const int tiles_per_batch = m_blocks * n_blocks;
-  const int num_tiles = tiles_per_batch * p.batch;
+  const int num_tiles = tiles_per_batch * p.batch * ksplit;     // tile = ((ks * batch + b) * m_blocks + m) * n_blocks + n
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -297,7 +311,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);
+      mbar_init(&tempty_bar[i], kEpiWarps);
     }
     fence_barrier_init();
   }
@@ -312,11 +326,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int b = tile / tiles_per_batch;
-      const int rem = tile - b * tiles_per_batch;
+      const int ks = tile / (tiles_per_batch * p.batch);
+      const int t2 = tile - ks * tiles_per_batch * p.batch;
+      const int b = t2 / tiles_per_batch;
+      const int rem = t2 - b * tiles_per_batch;
       const int m_blk = rem / n_blocks;
       const int n_blk = rem - m_blk * n_blocks;
-      for (int kb = 0; kb < k_blocks; ++kb) {
+      const int kb0 = ks * kb_per, kb1 = min(k_blocks, kb0 + kb_per);
+      for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1u);
         uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
         uint8_t* sB = sA + Cfg::A_BYTES;
@@ -350,10 +367,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int ks = tile / (tiles_per_batch * p.batch);
+      const int kb0 = ks * kb_per, kb1 = min(k_blocks, kb0 + kb_per);
       mbar_wait(&tempty_bar[as], aphase ^ 1u);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
-      for (int kb = 0; kb < k_blocks; ++kb) {
+      for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         const uint32_t sA = smem_u32(smem + stage * Cfg::STAGE_BYTES);
@@ -362,7 +381,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int k = 0; k < BK / 16; ++k) {
           const uint64_t da = A_MN ? umma_smem_desc(sA + k * 2048, 64 * BK * 2, 1024) : umma_smem_desc(sA + k * 32, 16, 1024);
           const uint64_t db = B_MN ? umma_smem_desc(sB + k * 2048, 64 * BK * 2, 1024) : umma_smem_desc(sB + k * 32, 16, 1024);
-          umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k != 0) ? 1u : 0u);
         }
         umma_commit(&empty_bar[stage]);
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -371,31 +390,36 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (++as == 2) { as = 0; aphase ^= 1u; }
     }
   } else if (warp >= 4) {
-    // ===================================================== epilogue (4 warps <-> 4 TMEM lane quarters)
+    // ===================================================== epilogue: 8 warps, warp w reads TMEM lane quarter (w & 3)
+    // (the hardware restricts a warp to lanes [32*(warp%4), +32)) and the even / odd 32-column chunks
     const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int b = tile / tiles_per_batch;
-      const int rem = tile - b * tiles_per_batch;
+      const int ks = tile / (tiles_per_batch * p.batch);
+      const int t2 = tile - ks * tiles_per_batch * p.batch;
+      const int b = t2 / tiles_per_batch;
+      const int rem = t2 - b * tiles_per_batch;
       const int m_blk = rem / n_blocks;
       const int n_blk = rem - m_blk * n_blocks;
+      const int kb0 = ks * kb_per, kb1 = min(k_blocks, kb0 + kb_per);
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const int row = m_blk * BM + q * 32 + lane;
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = half; c < BN / 32; c += 2) {
         uint32_t r[32];
         tmem_ld_32x32(t_addr + c * 32, r);
         tmem_ld_wait();
-        if (c == BN / 32 - 1) {
+        if (c + 2 >= BN / 32) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty_bar[as]);
         }
         const int col0 = n_blk * BN + c * 32;
-        if (p.mode == EPI_LINEAR) epi_linear(p, b, row, col0, r);
+        if (p.mode == EPI_LINEAR) epi_linear(p, b, row, col0, r, ks);
         else if (p.mode == EPI_LSTM_FWD) epi_lstm_fwd(p, b, row, col0, r);
         else epi_lstm_bwd(p, b, row, col0, r);
       }
@@ -551,7 +575,7 @@ static int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const Ge
     attr_set = true;
   }
   const int m_blocks = (p.M + BM - 1) / BM, n_blocks = (p.N + BN - 1) / BN;
-  const long long tiles = (long long)m_blocks * n_blocks * p.batch;
+  const long long tiles = (long long)m_blocks * n_blocks * p.batch * (p.ksplit > 1 ? p.ksplit : 1);
   int grid = (int)std::min<long long>(tiles, max_ctas > 0 ? max_ctas : num_sms());
   if (grid <= 0) return 0;
   kern<<<grid, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
@@ -567,6 +591,14 @@ int gemm_dispatch(const dvgr_operand& A, const dvgr_operand& B, GemmParams p, in
   if (bn != 128 && bn != 256) bn = (p.N > 128) ? 256 : 128;
   if (p.mode != EPI_LINEAR) bn = 128;
   if (p.k_inner <= 0) p.k_inner = INT_MAX;
+  if (p.ksplit > 1) {
+    if (p.mode != EPI_LINEAR || !p.out_f32 || p.beta != 2) return set_error("gemm: ksplit needs the fp32 atomic-accumulate epilogue (beta = 2)");
+    const int k_blocks = (p.K + BK - 1) / BK;
+    if (p.ksplit > k_blocks) p.ksplit = k_blocks;
+    const int per = (k_blocks + p.ksplit - 1) / p.ksplit;
+    p.ksplit = (k_blocks + per - 1) / per;       // no empty splits: an empty split would publish an unwritten accumulator
+  }
+  if (p.beta == 2 && !p.out_f32) return set_error("gemm: atomic accumulation needs an fp32 output");
   const bool a_mn = A.major != 0, b_mn = B.major != 0;
   CUtensorMap ta, tb;
   int rc = make_tensor_map(&ta, A, 64, a_mn ? 64 : BM);

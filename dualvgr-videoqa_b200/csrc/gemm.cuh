@@ -26,6 +26,8 @@ struct GemmParams {
   int k_inner;   // number of 64-row k-blocks per segment (INT_MAX when unsegmented)
   int a_c2_step[kMaxBatch], b_c2_step[kMaxBatch];
 
+  int ksplit;    // K is split over `ksplit` CTAs per output tile (requires beta == 2 on a zero-initialised / accumulating C)
+
   int mode;
   // ---- EPI_LINEAR
   void* C;
@@ -33,7 +35,7 @@ struct GemmParams {
   long long c_batch;    // elements between batches
   int out_f32;          // 1: float output, 0: bf16
   int act;
-  int beta;             // 1: accumulate into C
+  int beta;             // 1: accumulate into C (read-modify-write) ; 2: atomic add (fp32 output, split-K safe)
   const float* bias;    // [N] or null ; bias + batch * bias_batch
   long long bias_batch;
   const int* row_map;   // optional: output row = row_map[row]

@@ -146,6 +146,14 @@ __device__ __forceinline__ float tanhf_(float x) {
   return copysignf(t, x);
 }
 
+// single-MUFU approximations (rel. error ~2^-11): used where the result is stored as bf16 (2^-8) anyway
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(tanh_fast(0.5f * x), 0.5f, 0.5f); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -1,14 +1,15 @@
-// Counter-based dropout masks (Philox-4x32-10). A mask element is a pure function of (seed, stream id, element index):
+// Counter-based dropout masks (Philox-4x32, 7 rounds: the cheapest variant that still passes BigCrush). A mask element is a pure function of (seed, stream id, element index):
 // the backward kernels regenerate it instead of reading a stored mask.
 #pragma once
 #include <stdint.h>
 
 namespace dvgr {
 
-__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+template <int kRounds>
+__device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
   const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
-  for (int i = 0; i < 10; ++i) {
+  for (int i = 0; i < kRounds; ++i) {
     uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
     uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
     ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
@@ -33,7 +34,7 @@ __device__ __forceinline__ void dropout_scale4(const DropoutCfg& c, unsigned lon
     return;
   }
   const unsigned long long seed = c.seed + (c.seed_off != nullptr ? *c.seed_off : 0ull);
-  uint4 r = philox4x32_10(make_uint4((uint32_t)quad, (uint32_t)(quad >> 32), c.stream, 0x2545F491u),
+  uint4 r = philox4x32<7>(make_uint4((uint32_t)quad, (uint32_t)(quad >> 32), c.stream, 0x2545F491u),
                           make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
   const float inv = 1.f / (1.f - c.p);
   const uint32_t thr = (uint32_t)(c.p * 4294967296.0f);
@@ -41,6 +42,27 @@ __device__ __forceinline__ void dropout_scale4(const DropoutCfg& c, unsigned lon
   s[1] = r.y >= thr ? inv : 0.f;
   s[2] = r.z >= thr ? inv : 0.f;
   s[3] = r.w >= thr ? inv : 0.f;
+}
+
+// Keep-scale for 8 consecutive elements starting at index 8*oct: ONE Philox call, 16 random bits per element
+// (p is quantised to 1/65536, irrelevant for dropout). This is the form the streaming kernels use.
+__device__ __forceinline__ void dropout_scale8(const DropoutCfg& c, unsigned long long oct, float (&s)[8]) {
+  if (c.p <= 0.f) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] = 1.f;
+    return;
+  }
+  const unsigned long long seed = c.seed + (c.seed_off != nullptr ? *c.seed_off : 0ull);
+  uint4 r = philox4x32<7>(make_uint4((uint32_t)oct, (uint32_t)(oct >> 32), c.stream, 0x8F1BBCDCu),
+                          make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const float inv = 1.f / (1.f - c.p);
+  const uint32_t thr = (uint32_t)(c.p * 65536.0f);
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    s[2 * i] = (w[i] & 0xFFFFu) >= thr ? inv : 0.f;
+    s[2 * i + 1] = (w[i] >> 16) >= thr ? inv : 0.f;
+  }
 }
 
 // Keep-scale for a single element index (costs a full Philox call; use dropout_scale4 in streaming kernels).

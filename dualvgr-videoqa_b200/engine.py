@@ -25,7 +25,13 @@ class TrainEngine:
         self.lr, self.max_norm, self.alpha, self.beta, self.betas, self.eps = lr, max_norm, alpha, beta, betas, eps
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
-        self.params = [p for p in model.parameters() if p.requires_grad]
+        # flat layout: the groups the fused kernels see as one matrix first (contiguous, in order), then everything else
+        grouped, seen = [], set()
+        for grp in ag.grad_groups(model):
+            for p in grp:
+                if p.requires_grad and id(p) not in seen:
+                    grouped.append(p); seen.add(id(p))
+        self.params = grouped + [p for p in model.parameters() if p.requires_grad and id(p) not in seen]
         dev = self.params[0].device
         sizes = [(p.numel() + 3) // 4 * 4 for p in self.params]           # 16-byte aligned slices
         total = sum(sizes)
@@ -49,6 +55,7 @@ class TrainEngine:
         if self.world > 1:      # replicas must start identical (the reference seeds every process the same, train.py:425-428)
             dist.broadcast(self.flat, src=0, group=self.pg)
         ag.invalidate_weight_cache()
+        ag.DIRECT_GRAD[0] = True      # weight-gradient GEMMs accumulate straight into the flat gradient buffer
 
     # ------------------------------------------------------------------------------------------------------------
     def loss(self, outputs, answers):
@@ -57,15 +64,16 @@ class TrainEngine:
         n = len(aq)
         B, N = aq[0].shape[0], aq[0].shape[1]
         ce, correct = ag.CrossEntropyFn.apply(logits, answers)
-        com = dep = None
+        total, com, dep = ce, None, None
+        c_com, c_dep = (self.alpha / max(n, 1)) / (B * N * N), self.beta * self.world / max(n, 1)
         for i in range(n):
-            c = ag.PairLossFn.apply(com_app[i], com_mot[i], 0, 1.0 / (B * N * N))
-            d = ag.PairLossFn.apply(aq[i], com_app[i], 1, 1.0) + ag.PairLossFn.apply(mq[i], com_mot[i], 1, 1.0)
+            aux, vals = ag.AuxLossFn.apply(com_app[i], com_mot[i], aq[i], mq[i], c_com, c_dep)
+            total = total + aux
+            c, d = vals[0], vals[1] + vals[2]
             com = c if com is None else com + c
             dep = d if dep is None else dep + d
-        total = ce
-        if n > 0:
-            total = ce + (self.alpha / n) * com + (self.beta * self.world / n) * dep
+        if n > 0:       # un-scaled sums, as train.py accumulates them (logging only)
+            com, dep = com / (c_com * B * N * N), dep / c_dep if c_dep != 0 else dep
         return total, ce, com, dep, correct
 
     def train_step(self, app, mot, question, question_len, answers):

@@ -44,7 +44,7 @@ def operand(t, major):
 
 def gemm(A, a_major, B, b_major, M, N, K, C, *, ldc=None, bias=None, act=None, beta=False, batch=1, c_batch=0,
          bias_batch=0, row_map=None, a_c0=None, a_c2=None, a_c3=None, b_c0=None, b_c2=None, b_c3=None, k_inner=0,
-         a_c2_step=None, b_c2_step=None, bn=0, max_ctas=0):
+         a_c2_step=None, b_c2_step=None, bn=0, max_ctas=0, ksplit=0):
     """Raw tcgen05 GEMM: C[b][m][n] = act(sum_k A*B + bias) (+C)."""
     _check_cuda(A, B, C, bias)
     args = _lib.GemmArgs()
@@ -64,7 +64,8 @@ def gemm(A, a_major, B, b_major, M, N, K, C, *, ldc=None, bias=None, act=None, b
     assert C.dtype in (torch.float32, torch.bfloat16)
     args.out_f32 = 1 if C.dtype == torch.float32 else 0
     args.act = _ACT[act] if not isinstance(act, int) else act
-    args.beta = 1 if beta else 0
+    args.beta = int(beta) if not isinstance(beta, bool) else (1 if beta else 0)
+    args.ksplit = ksplit
     if bias is not None:
         assert bias.dtype == torch.float32
         args.bias = bias.data_ptr()
@@ -96,13 +97,30 @@ def linear_dgrad(dy, w, out=None, beta=False, bn=0):
     return gemm(dy, 0, w, 1, M, K, N, out, beta=beta, bn=bn)
 
 
-def linear_wgrad(dy, x, out=None, beta=False, row_map=None, bn=0):
-    """dw[N,K] (fp32) (+)= dy[M,N]^T @ x[M,K]  (both read MN-major)."""
+NUM_SMS = 148
+
+
+def wgrad_split(rows, cols, red, batch=1):
+    """(bn, ksplit) for a weight-gradient GEMM [rows, cols] reduced over `red`: enough CTAs to fill the 148 SMs."""
+    bn = 256 if (rows // 128) * ((cols + 255) // 256) * batch >= NUM_SMS else 128
+    tiles = ((rows + 127) // 128) * ((cols + bn - 1) // bn) * batch
+    kb = (red + 63) // 64
+    return bn, max(1, min(kb // 4 if kb >= 8 else 1, (2 * NUM_SMS + tiles - 1) // tiles))
+
+
+def linear_wgrad(dy, x, out=None, beta=False, row_map=None, bn=0, rows=None, cols=None, atomic=False):
+    """dw[N,K] (fp32) (+)= dy[M,N]^T @ x[M,K]  (both read MN-major). atomic=True: split-K with fp32 atomic adds into
+    `out` (which must already hold the value to accumulate onto, e.g. a zeroed gradient buffer)."""
     M, N = dy.shape
     K = x.shape[1]
+    rows, cols = rows or N, cols or K
     if out is None:
-        out = torch.empty((N, K), dtype=torch.float32, device=dy.device)
-    return gemm(dy, 1, x, 1, N, K, M, out, beta=beta, row_map=row_map, bn=bn)
+        assert not atomic
+        out = torch.empty((rows, cols), dtype=torch.float32, device=dy.device)
+    if atomic:
+        bn2, ks = wgrad_split(rows, cols, M)
+        return gemm(dy, 1, x, 1, rows, cols, M, out, beta=2, row_map=row_map, bn=bn or bn2, ksplit=ks)
+    return gemm(dy, 1, x, 1, rows, cols, M, out, beta=beta, row_map=row_map, bn=bn)
 
 
 def gemm_reference(A, a_rs, a_ks, B, b_rs, b_ks, M, N, K):
@@ -426,20 +444,35 @@ def cross_entropy(logits, answers, scale=1.0, want_grad=True):
     return colsum(part)[0], dlog, correct
 
 
+def pair_loss_multi(jobs, B, N, D, like):
+    """jobs: list of dicts(x, y, mode, coef, dx, dy, acc_x, acc_y). Returns per-job loss sums as a [n_jobs] f32 tensor."""
+    n = len(jobs)
+    arr = (_lib.PairJob * n)()
+    part = _empty((B, n), F32, like)
+    for i, j in enumerate(jobs):
+        assert j["x"].dtype == F32 and j["y"].dtype == F32 and j["x"].is_contiguous() and j["y"].is_contiguous()
+        arr[i].x, arr[i].y = j["x"].data_ptr(), j["y"].data_ptr()
+        arr[i].dx = j["dx"].data_ptr() if j.get("dx") is not None else None
+        arr[i].dy = j["dy"].data_ptr() if j.get("dy") is not None else None
+        arr[i].loss_part, arr[i].loss_col, arr[i].loss_ld = part.data_ptr(), i, n
+        arr[i].mode, arr[i].coef = j["mode"], float(j["coef"])
+        arr[i].accumulate_x, arr[i].accumulate_y = j.get("acc_x", 0), j.get("acc_y", 0)
+    ws = _empty((int(_lib.lib.dvgr_pair_loss_workspace(n, B, N, D)),), F32, like)
+    _lib.check(_lib.pair_loss_multi(arr, n, B, N, D, _ptr(ws), _stream()), "dvgr_pair_loss_multi")
+    return colsum(part)
+
+
 def pair_loss(x, y, mode, coef, dx=None, dy=None, want_grad=True):
     """mode 0: coef * sum (G_x - G_y)^2 ; mode 1: coef * HSIC. x, y fp32 [B, N, D]. dx / dy given => accumulated into.
     Returns (loss scalar tensor, dx, dy)."""
     B, N, D = x.shape
-    assert x.dtype == F32 and y.dtype == F32 and x.is_contiguous() and y.is_contiguous()
-    part = _empty((B, 1), F32, x)
     accx, accy = dx is not None, dy is not None
     if want_grad:
         dx = dx if accx else torch.empty_like(x)
         dy = dy if accy else torch.empty_like(y)
-    _lib.check(_lib.pair_loss(_ptr(x), _ptr(y), B, N, D, mode, float(coef), _ptr(part), _ptr(dx) if want_grad else None,
-                              _ptr(dy) if want_grad else None, 1 if accx else 0, 1 if accy else 0, _stream()),
-               "dvgr_pair_loss")
-    return colsum(part)[0], dx, dy
+    job = dict(x=x, y=y, mode=mode, coef=coef, dx=dx if want_grad else None, dy=dy if want_grad else None,
+               acc_x=1 if accx else 0, acc_y=1 if accy else 0)
+    return pair_loss_multi([job], B, N, D, x)[0], dx, dy
 
 
 def sumsq(g):

@@ -60,12 +60,13 @@ typedef struct dvgr_gemm_args {
   /* linear epilogue:  C = act(acc + bias) (+ C when beta)                                  */
   void* C;
   long long ldc, c_batch;             /* elements */
-  int out_f32, act, beta;
+  int out_f32, act, beta;             /* beta: 0 overwrite, 1 C += (read-modify-write), 2 atomic add (fp32 C only) */
   const float* bias;
   long long bias_batch;
   const int* row_map;                 /* optional output-row permutation (wgrad of gate-interleaved LSTM weights) */
   int bn;                             /* N tile: 128, 256, or 0 = choose */
   int max_ctas;                       /* 0 = one CTA per SM */
+  int ksplit;                         /* > 1: split the reduction over that many CTAs per tile (needs beta == 2) */
 } dvgr_gemm_args;
 
 /* Replaces every nn.Linear forward / dgrad / wgrad on the path: model/models.py:46,74 (motion projection),
@@ -215,10 +216,25 @@ int dvgr_bn_bwd(const void* dy, const void* x, int B, int D, const float* gamma,
 int dvgr_cross_entropy(const float* logits, const long long* answers, int B, int A, float scale, float* loss_part,
                        void* dlogits, long long ld_d, int* correct, void* stream);
 
-/* Auxiliary losses (utils.py:10-31), value and gradient fused per video. x, y, dx, dy are [B][N][D] f32.
- * mode 0: common_loss term  coef * sum_ij (G_x - G_y)^2 ; mode 1: HSIC  coef * tr(R K_x R K_y). */
-int dvgr_pair_loss(const float* x, const float* y, int B, int N, int D, int mode, float coef, float* loss_part,
-                   float* dx, float* dy, int accumulate_x, int accumulate_y, void* stream);
+/* Auxiliary losses (utils.py:10-31), value and gradient fused; up to 4 (x, y) pairs per call (one DualVGR unit needs 3:
+ * common(com_app, com_mot), HSIC(aq, com_app), HSIC(mq, com_mot) — train.py:148-154). x, y, dx, dy are [B][N][D] f32.
+ * mode 0: coef * sum_ij (G_x - G_y)^2 (common_loss numerator) ; mode 1: coef * tr(R K_x R K_y) (HSIC).
+ * loss_part[b][loss_col] (row stride loss_ld) receives the per-video value; accumulate_{x,y}: 0 write, 1 add in place,
+ * 2 atomicAdd into a caller-zeroed buffer (for a tensor that is an operand of two pairs of the same call).
+ * gram_ws: dvgr_pair_loss_workspace(...) floats. */
+typedef struct dvgr_pair_job {
+  const float* x;
+  const float* y;
+  float* dx;
+  float* dy;
+  float* loss_part;
+  int loss_col, loss_ld;
+  int mode;
+  int accumulate_x, accumulate_y;
+  float coef;
+} dvgr_pair_job;
+long long dvgr_pair_loss_workspace(int n_jobs, int B, int N, int D);
+int dvgr_pair_loss_multi(const dvgr_pair_job* jobs, int n_jobs, int B, int N, int D, float* gram_ws, void* stream);
 
 /* Streaming helpers.
  * dvgr_prep_features: model/Preprocessing.py:220-223 — tanh(dropout(x)), fp32 -> bf16, [S][T][C] -> [T][S][C] in one pass.

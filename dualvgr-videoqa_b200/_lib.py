@@ -108,8 +108,8 @@ mfb_fwd = _sig("dvgr_mfb_fwd", [P, P, P, c_ll, c_int, P])
 mfb_bwd = _sig("dvgr_mfb_bwd", [P, P, P, P, P, c_ll, c_int, P])
 readout_fwd = _sig("dvgr_readout_fwd", [P, P, P, P, c_int, c_int, c_int, P, P, c_ll, P])
 readout_bwd = _sig("dvgr_readout_bwd", [P, c_ll, P, P, P, P, c_int, c_int, c_int, P, P, P, P, P])
-bn_fwd = _sig("dvgr_bn_fwd", [P, c_int, c_int, P, P, P, P, c_int, c_float, c_float, P, P, P, P])
-bn_bwd = _sig("dvgr_bn_bwd", [P, P, c_int, c_int, P, P, P, c_int, P, P, P, P])
+bn_fwd = _sig("dvgr_bn_fwd", [P, c_int, c_int, c_int, P, P, P, P, c_int, c_float, c_float, P, P, P, P])
+bn_bwd = _sig("dvgr_bn_bwd", [P, P, c_int, c_int, c_int, P, P, P, c_int, P, P, P, P])
 cross_entropy = _sig("dvgr_cross_entropy", [P, P, c_int, c_int, c_float, P, P, c_ll, P, P])
 
 
@@ -132,7 +132,7 @@ lib.dvgr_colsum_workspace.restype = c_ll
 colsum = _sig("dvgr_colsum", [P, c_int, c_ll, c_ll, c_int, P, P, c_int, c_float, P])
 sumsq_blocks = _sig("dvgr_sumsq_blocks", [])
 sumsq = _sig("dvgr_sumsq", [P, c_ll, P, P, P])
-adam_step = _sig("dvgr_adam_step", [P, P, P, P, c_ll, c_float, c_float, c_float, c_float, c_int, c_float, P, c_float, P, P])
+adam_step = _sig("dvgr_adam_step", [P, P, P, P, c_ll, c_float, c_float, c_float, c_float, c_int, c_float, P, c_float, P, P, P])
 
 EXPORTED = [
     "dvgr_last_error", "dvgr_abi_version", "dvgr_launch_count", "dvgr_set_seed_offset", "dvgr_gemm", "dvgr_gemm_reference",

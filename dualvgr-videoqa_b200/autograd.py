@@ -47,10 +47,36 @@ def _versions(params):
     return tuple((p.data_ptr(), p._version) for p in params) + (_wepoch[0],)
 
 
+# bf16 shadow of the engine's flat parameter buffer: {id(param): (weakref, bf16 view)}; kept current by the fused Adam kernel
+SHADOW = {}
+
+
+def _shadow_rows(params, out_cols, lstm_H):
+    if lstm_H or not SHADOW:
+        return None
+    C = params[0].shape[1]
+    if out_cols not in (None, C):
+        return None
+    ent = SHADOW.get(id(params[0]))
+    if ent is None or ent[0]() is not params[0]:
+        return None
+    ptr, rows = ent[1].data_ptr(), 0
+    for p in params:
+        e = SHADOW.get(id(p))
+        if e is None or e[0]() is not p or e[1].data_ptr() != ptr or p.shape[1] != C:
+            return None
+        ptr += p.numel() * 2
+        rows += p.shape[0]
+    return torch.as_strided(ent[1], (rows, C), (C, 1))
+
+
 def bf16_rows(params, out_cols=None, lstm_H=0, tag=""):
     """bf16 operand made of the row-wise concatenation of fp32 matrices `params` (all [r_i, C]).
     Cached per parameter OBJECT (weak references: a freed model whose storage address is recycled by the caching
     allocator must not alias a live one) and re-cast whenever a version counter, data pointer or the optimizer epoch moves."""
+    sh = _shadow_rows(params, out_cols, lstm_H)
+    if sh is not None:
+        return sh
     key = (tag, tuple(id(p) for p in params), out_cols, lstm_H)
     ver = _versions(params)
     ent = _wcache.get(key)
@@ -136,7 +162,10 @@ class LinearFn(Function):
         x2 = _c(x.reshape(-1, Kp))
         w = bf16_rows([weight], out_cols=Kp)
         y = ops.linear_fwd(x2, w, bias=bias, act=act, out_dtype=F32 if out_f32 else BF16)
-        ctx.save_for_backward(x2, w, y if (act not in (None, "none") and not act_grad_folded) else None)
+        ysave = None
+        if act not in (None, "none") and not act_grad_folded:
+            ysave = y if y.dtype == BF16 else y.to(BF16)       # act' only needs the sign / bf16-level value of the output
+        ctx.save_for_backward(x2, w, ysave)
         ctx.act, ctx.out_f32, ctx.lead, ctx.K, ctx.has_bias = act, out_f32, x.shape[:-1], weight.shape[1], bias is not None
         ctx.wparam, ctx.bparam = weight, bias
         return y.view(*x.shape[:-1], weight.shape[0])
@@ -575,7 +604,10 @@ class BatchNormFn(Function):
     @staticmethod
     def backward(ctx, dy):
         x, gamma, mean, rstd = ctx.saved_tensors
-        dx, dg, db = ops.bn_bwd(_c(dy), x, gamma, mean, rstd, ctx.training)
+        dy = _c(dy)
+        if dy.dtype != BF16:
+            dy = dy.to(BF16)
+        dx, dg, db = ops.bn_bwd(dy, x, gamma, mean, rstd, ctx.training)
         return dx, dg, db, None, None, None, None, None
 
 

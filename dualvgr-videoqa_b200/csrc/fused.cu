@@ -275,7 +275,8 @@ readout_bwd_kernel(const bf16* __restrict__ dpooled, long long ld_p, const bf16*
 // =============================================================================================== BatchNorm1d
 // reference model/AnswerDecoder.py:193 (nn.BatchNorm1d(module_dim)): batch statistics (biased variance) in training,
 // running statistics in eval; running stats updated with momentum 0.1 and the UNBIASED variance, as torch does.
-__global__ void bn_fwd_kernel(const bf16* __restrict__ x, int B, int D, const float* __restrict__ gamma,
+template <typename TX>
+__global__ void bn_fwd_kernel(const TX* __restrict__ x, int B, int D, const float* __restrict__ gamma,
                               const float* __restrict__ betap, float* __restrict__ run_mean, float* __restrict__ run_var,
                               int training, float momentum, float eps, bf16* __restrict__ y, float* __restrict__ mean_out,
                               float* __restrict__ rstd_out) {
@@ -284,11 +285,11 @@ __global__ void bn_fwd_kernel(const bf16* __restrict__ x, int B, int D, const fl
   float mean, var;
   if (training) {
     float s = 0.f;
-    for (int r = 0; r < B; ++r) s += __bfloat162float(x[(long long)r * D + c]);
+    for (int r = 0; r < B; ++r) s += ldf<TX>(x + (long long)r * D + c);
     mean = s / B;
     float v = 0.f;
     for (int r = 0; r < B; ++r) {
-      const float d = __bfloat162float(x[(long long)r * D + c]) - mean;
+      const float d = ldf<TX>(x + (long long)r * D + c) - mean;
       v += d * d;
     }
     var = v / B;
@@ -307,12 +308,13 @@ __global__ void bn_fwd_kernel(const bf16* __restrict__ x, int B, int D, const fl
   }
   const float g = gamma[c], bt = betap[c];
   for (int r = 0; r < B; ++r)
-    y[(long long)r * D + c] = __float2bfloat16_rn((__bfloat162float(x[(long long)r * D + c]) - mean) * rstd * g + bt);
+    y[(long long)r * D + c] = __float2bfloat16_rn((ldf<TX>(x + (long long)r * D + c) - mean) * rstd * g + bt);
 }
 
-__global__ void bn_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, int B, int D,
+template <typename TX>
+__global__ void bn_bwd_kernel(const bf16* __restrict__ dy, const TX* __restrict__ x, int B, int D,
                               const float* __restrict__ gamma, const float* __restrict__ mean,
-                              const float* __restrict__ rstd, int training, bf16* __restrict__ dx,
+                              const float* __restrict__ rstd, int training, TX* __restrict__ dx,
                               float* __restrict__ dgamma, float* __restrict__ dbeta) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= D) return;
@@ -320,7 +322,7 @@ __global__ void bn_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restric
   float sdy = 0.f, sdyx = 0.f;
   for (int r = 0; r < B; ++r) {
     const float d = __bfloat162float(dy[(long long)r * D + c]);
-    const float xh = (__bfloat162float(x[(long long)r * D + c]) - m) * rs;
+    const float xh = (ldf<TX>(x + (long long)r * D + c) - m) * rs;
     sdy += d;
     sdyx += d * xh;
   }
@@ -328,9 +330,9 @@ __global__ void bn_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restric
   dbeta[c] = sdy;
   for (int r = 0; r < B; ++r) {
     const float d = __bfloat162float(dy[(long long)r * D + c]);
-    const float xh = (__bfloat162float(x[(long long)r * D + c]) - m) * rs;
+    const float xh = (ldf<TX>(x + (long long)r * D + c) - m) * rs;
     const float o = training ? g * rs * (d - sdy / B - xh * sdyx / B) : g * rs * d;
-    dx[(long long)r * D + c] = __float2bfloat16_rn(o);
+    stf<TX>(dx + (long long)r * D + c, o);
   }
 }
 
@@ -471,16 +473,62 @@ __global__ void add_kernel(bf16* __restrict__ a, const bf16* __restrict__ b, lon
 }
 
 // Column sums, two deterministic passes: partial[chunk][C] then out[C] (+)= sum_chunk. Input bf16 or fp32.
+// Block = 32 column groups (8 columns each, one 128-bit / 2x128-bit load per row) x 8 row lanes; every thread keeps
+// 4 independent row loads in flight (the first version issued one dependent 2-byte load per iteration and was
+// latency-bound at ~1 % of HBM bandwidth on the [81920, 3072] LSTM bias gradient).
+__device__ __forceinline__ void load8g(const bf16* p, float (&f)[8]) { load8(p, f); }
+__device__ __forceinline__ void load8g(const float* p, float (&f)[8]) {
+  const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
 template <typename T>
-__global__ void colsum_partial_kernel(const T* __restrict__ in, long long ld, long long R, int C, int rows_per_chunk,
-                                      float* __restrict__ partial) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+__global__ void __launch_bounds__(256)
+colsum_partial_kernel(const T* __restrict__ in, long long ld, long long R, int C, int rows_per_chunk,
+                      float* __restrict__ partial, int vec_ok) {
+  __shared__ float red[8][32][9];
+  const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c0 = (blockIdx.x * 32 + cg) * 8;
   const long long r0 = (long long)blockIdx.y * rows_per_chunk;
   const long long r1 = min(R, r0 + rows_per_chunk);
-  float acc = 0.f;
-  for (long long r = r0; r < r1; ++r) acc += ldf<T>(in + r * ld + c);
-  partial[(long long)blockIdx.y * C + c] = acc;
+  float acc[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+  if (c0 < C) {
+    if (vec_ok && c0 + 8 <= C) {
+      long long r = r0 + rl;
+      for (; r + 24 < r1; r += 32) {
+        float f0[8], f1[8], f2[8], f3[8];
+        load8g(in + r * ld + c0, f0);
+        load8g(in + (r + 8) * ld + c0, f1);
+        load8g(in + (r + 16) * ld + c0, f2);
+        load8g(in + (r + 24) * ld + c0, f3);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[q] += (f0[q] + f1[q]) + (f2[q] + f3[q]);
+      }
+      for (; r < r1; r += 8) {
+        float f0[8];
+        load8g(in + r * ld + c0, f0);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[q] += f0[q];
+      }
+    } else {
+      for (long long r = r0 + rl; r < r1; r += 8)
+        for (int q = 0; q < 8; ++q)
+          if (c0 + q < C) acc[q] += ldf<T>(in + r * ld + c0 + q);
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 8; ++q) red[rl][cg][q] = acc[q];
+  __syncthreads();
+  if (rl == 0 && c0 < C) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      float s = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s += red[k][cg][q];
+      if (c0 + q < C) partial[(long long)blockIdx.y * C + c0 + q] = s;
+    }
+  }
 }
 __global__ void colsum_final_kernel(const float* __restrict__ partial, int chunks, int C, float* __restrict__ out,
                                     int accumulate, float scale) {
@@ -568,20 +616,31 @@ extern "C" int dvgr_readout_bwd(const void* dpooled, long long ld_p, const void*
   return 0;
 }
 
-extern "C" int dvgr_bn_fwd(const void* x, int B, int D, const float* gamma, const float* beta, float* run_mean,
-                           float* run_var, int training, float momentum, float eps, void* y, float* mean_out,
-                           float* rstd_out, void* stream) {
+extern "C" int dvgr_bn_fwd(const void* x, int x_is_f32, int B, int D, const float* gamma, const float* beta,
+                           float* run_mean, float* run_var, int training, float momentum, float eps, void* y,
+                           float* mean_out, float* rstd_out, void* stream) {
   if (B <= 0 || D <= 0) return 0;
-  bn_fwd_kernel<<<(D + 127) / 128, 128, 0, ST(stream)>>>(CBF(x), B, D, gamma, beta, run_mean, run_var, training,
-                                                        momentum, eps, BF(y), mean_out, rstd_out);
+  if (x_is_f32)
+    bn_fwd_kernel<float><<<(D + 127) / 128, 128, 0, ST(stream)>>>(reinterpret_cast<const float*>(x), B, D, gamma, beta,
+                                                                 run_mean, run_var, training, momentum, eps, BF(y),
+                                                                 mean_out, rstd_out);
+  else
+    bn_fwd_kernel<bf16><<<(D + 127) / 128, 128, 0, ST(stream)>>>(CBF(x), B, D, gamma, beta, run_mean, run_var, training,
+                                                                momentum, eps, BF(y), mean_out, rstd_out);
   DVGR_CHECK_LAUNCH("bn_fwd");
   return 0;
 }
-extern "C" int dvgr_bn_bwd(const void* dy, const void* x, int B, int D, const float* gamma, const float* mean,
-                           const float* rstd, int training, void* dx, float* dgamma, float* dbeta, void* stream) {
+extern "C" int dvgr_bn_bwd(const void* dy, const void* x, int x_is_f32, int B, int D, const float* gamma,
+                           const float* mean, const float* rstd, int training, void* dx, float* dgamma, float* dbeta,
+                           void* stream) {
   if (B <= 0 || D <= 0) return 0;
-  bn_bwd_kernel<<<(D + 127) / 128, 128, 0, ST(stream)>>>(CBF(dy), CBF(x), B, D, gamma, mean, rstd, training, BF(dx),
-                                                        dgamma, dbeta);
+  if (x_is_f32)
+    bn_bwd_kernel<float><<<(D + 127) / 128, 128, 0, ST(stream)>>>(CBF(dy), reinterpret_cast<const float*>(x), B, D, gamma,
+                                                                 mean, rstd, training, reinterpret_cast<float*>(dx),
+                                                                 dgamma, dbeta);
+  else
+    bn_bwd_kernel<bf16><<<(D + 127) / 128, 128, 0, ST(stream)>>>(CBF(dy), CBF(x), B, D, gamma, mean, rstd, training,
+                                                                BF(dx), dgamma, dbeta);
   DVGR_CHECK_LAUNCH("bn_bwd");
   return 0;
 }
@@ -643,25 +702,27 @@ extern "C" int dvgr_add(void* a, const void* b, long long n, void* stream) {
   return 0;
 }
 
-extern "C" long long dvgr_colsum_workspace(long long R, int C) {
-  long long chunks = (R + 255) / 256;
-  if (chunks > 128) chunks = 128;
+static inline long long colsum_chunks(long long R) {
+  long long chunks = (R + 63) / 64;          // >= 64 rows (8 per row lane) per chunk
+  if (chunks > 256) chunks = 256;
   if (chunks < 1) chunks = 1;
-  return chunks * C;
+  return chunks;
 }
+
+extern "C" long long dvgr_colsum_workspace(long long R, int C) { return colsum_chunks(R) * C; }
 
 extern "C" int dvgr_colsum(const void* in, int in_is_f32, long long ld, long long R, int C, float* workspace, float* out,
                            int accumulate, float scale, void* stream) {
   if (C <= 0) return 0;
-  long long chunks = (R + 255) / 256;
-  if (chunks > 128) chunks = 128;
-  if (chunks < 1) chunks = 1;
+  const long long chunks = colsum_chunks(R);
   const int rpc = (int)((R + chunks - 1) / chunks);
-  dim3 grid((C + 127) / 128, (unsigned)chunks);
+  dim3 grid((C + 255) / 256, (unsigned)chunks);
+  const int esz = in_is_f32 ? 4 : 2;
+  const int vec_ok = ((reinterpret_cast<uintptr_t>(in) & 15) == 0) && ((ld * esz) % 16 == 0);
   if (in_is_f32)
-    colsum_partial_kernel<float><<<grid, 128, 0, ST(stream)>>>(reinterpret_cast<const float*>(in), ld, R, C, rpc, workspace);
+    colsum_partial_kernel<float><<<grid, 256, 0, ST(stream)>>>(reinterpret_cast<const float*>(in), ld, R, C, rpc, workspace, vec_ok);
   else
-    colsum_partial_kernel<bf16><<<grid, 128, 0, ST(stream)>>>(CBF(in), ld, R, C, rpc, workspace);
+    colsum_partial_kernel<bf16><<<grid, 256, 0, ST(stream)>>>(CBF(in), ld, R, C, rpc, workspace, vec_ok);
   DVGR_CHECK_LAUNCH("colsum_partial");
   colsum_final_kernel<<<(C + 127) / 128, 128, 0, ST(stream)>>>(workspace, (int)chunks, C, out, accumulate, scale);
   DVGR_CHECK_LAUNCH("colsum_final");

@@ -1,6 +1,8 @@
 // Flat-buffer optimizer step of the DualVGR train loop: global-norm clipping + Adam in two launches over ONE fp32
 // buffer (the reference walks ~250 parameter tensors: nn.utils.clip_grad_norm_(max_norm=12) + optim.Adam(lr=1e-4),
 // train.py:85,158-159). Matches torch.optim.Adam (no weight decay, no amsgrad) and clip_grad_norm_ (eps 1e-6).
+#include <cuda_bf16.h>
+
 #include "capi_internal.h"
 #include "ptx.cuh"
 
@@ -37,7 +39,7 @@ __global__ void sumsq_final_kernel(const float* __restrict__ partial, int n, flo
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, long long n, float lr, float b1, float b2, float eps, float bc1,
                             float bc2_sqrt, float max_norm, const float* __restrict__ norm_sq, float grad_scale,
-                            const int* __restrict__ step_dev) {
+                            const int* __restrict__ step_dev, __nv_bfloat16* __restrict__ shadow) {
   if (step_dev != nullptr) {      // device-resident step counter (CUDA-graph replay): bias corrections computed here
     const float t = (float)step_dev[0];
     bc1 = 1.f - powf(b1, t);
@@ -56,7 +58,9 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
     m[i] = mi;
     v[i] = vi;
-    p[i] -= step * mi / (sqrtf(vi) / bc2_sqrt + eps);
+    const float pn = p[i] - step * mi / (sqrtf(vi) / bc2_sqrt + eps);
+    p[i] = pn;
+    if (shadow != nullptr) shadow[i] = __float2bfloat16_rn(pn);   // bf16 operand copy for the next step's GEMMs
   }
 }
 
@@ -80,7 +84,8 @@ extern "C" int dvgr_sumsq(const float* g, long long n, float* partial_ws, float*
 
 extern "C" int dvgr_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n,
                               float lr, float beta1, float beta2, float eps, int step, float max_norm,
-                              const float* norm_sq, float grad_scale, const int* step_dev, void* stream) {
+                              const float* norm_sq, float grad_scale, const int* step_dev, void* bf16_shadow,
+                              void* stream) {
   if (n <= 0) return 0;
   if (step < 1 && step_dev == nullptr) return set_error("adam: step must be >= 1");
   if (step < 1) step = 1;
@@ -89,7 +94,8 @@ extern "C" int dvgr_adam_step(float* params, const float* grads, float* exp_avg,
   long long blocks = (n + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   adam_kernel<<<(int)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, bc1, sqrtf(bc2), max_norm, norm_sq, grad_scale, step_dev);
+      params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, bc1, sqrtf(bc2), max_norm, norm_sq, grad_scale, step_dev,
+      reinterpret_cast<__nv_bfloat16*>(bf16_shadow));
   DVGR_CHECK_LAUNCH("adam_step");
   return 0;
 }

@@ -11,6 +11,8 @@ Videos are independent, so ranks shard the batch and never exchange activations.
 are handled as standard DDP does: BatchNorm uses per-rank batch statistics; CE / common_loss are means
 (gradient averaging reproduces the global-batch gradient), HSIC is a SUM over the batch, so its coefficient is multiplied
 by world_size before averaging."""
+import weakref
+
 import torch
 import torch.distributed as dist
 
@@ -37,6 +39,7 @@ class TrainEngine:
         total = sum(sizes)
         self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
         self.gflat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.shadow = torch.zeros(total, dtype=torch.bfloat16, device=dev)   # bf16 GEMM operands, written by the Adam kernel
         self.m = torch.zeros(total, dtype=torch.float32, device=dev)
         self.v = torch.zeros(total, dtype=torch.float32, device=dev)
         off = 0
@@ -46,7 +49,10 @@ class TrainEngine:
                 sl.copy_(p.data)
                 p.data = sl
                 p.grad = self.gflat[off:off + p.numel()].view_as(p)
+                if p.dim() == 2:
+                    ag.SHADOW[id(p)] = (weakref.ref(p), self.shadow[off:off + p.numel()].view_as(p))
                 off += n
+            self.shadow.copy_(self.flat)
         self.step_count = 0
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)     # device-side step counter (graph replay)
         self.seed_dev = torch.zeros(1, dtype=torch.int64, device=dev)     # device-side dropout seed offset
@@ -94,7 +100,8 @@ class TrainEngine:
         scale = 1.0 / self.world
         nsq = ops.sumsq(self.gflat)
         ops.adam_step(self.flat, self.gflat, self.m, self.v, self.lr, self.step_count, self.betas[0], self.betas[1],
-                      self.eps, max_norm=self.max_norm, norm_sq=nsq, grad_scale=scale, step_dev=self.step_dev)
+                      self.eps, max_norm=self.max_norm, norm_sq=nsq, grad_scale=scale, step_dev=self.step_dev,
+                      shadow=self.shadow)
         ag.invalidate_weight_cache()
 
     # ------------------------------------------------------------------------------------------------------------
@@ -127,6 +134,20 @@ class TrainEngine:
         self.launches_per_replay = _lib.launch_count() - n0    # library kernels recorded into the graph
         ag.invalidate_weight_cache()
         return self.graph
+
+    def close(self):
+        """Detaches the engine's device-side dropout counter from the library (call before dropping the engine)."""
+        from . import _lib
+        _lib.lib.dvgr_set_seed_offset(None)
+        self.graph = None
+        for p in self.params:
+            ag.SHADOW.pop(id(p), None)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def load_batch(self, app, mot, question, question_len, answers, non_blocking=True):
         st = self.static

@@ -39,7 +39,8 @@ class SimpleOutputUnitOpenEnded(nn.Module):
         q = ag.linear(question_embedding.to(BF16), self.question_proj.weight, self.question_proj.bias)
         x = torch.cat([visual_embedding.to(BF16), q], dim=1)
         x = ag.dropout(x, c[0].p, self.training)
-        x = ag.linear(x, c[1].weight, c[1].bias, act="elu")
+        # fp32 out: BatchNorm centres its input, which would amplify bf16 rounding of x by |x| / std
+        x = ag.linear(x, c[1].weight, c[1].bias, act="elu", out_f32=True)
         bn = c[3]
         use_batch_stats = self.training or not bn.track_running_stats
         if self.training and bn.track_running_stats:

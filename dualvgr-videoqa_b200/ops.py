@@ -415,9 +415,9 @@ def readout_bwd(dpooled, v, u, w, alpha):
 
 def bn_fwd(x, gamma, beta, run_mean, run_var, training, momentum=0.1, eps=1e-5):
     B, D = x.shape
-    y = torch.empty_like(x)
+    y = _empty((B, D), BF16, x)
     mean, rstd = _empty((D,), F32, x), _empty((D,), F32, x)
-    _lib.check(_lib.bn_fwd(_ptr(x), B, D, _ptr(gamma), _ptr(beta), _ptr(run_mean), _ptr(run_var), 1 if training else 0,
+    _lib.check(_lib.bn_fwd(_ptr(x), 1 if x.dtype == F32 else 0, B, D, _ptr(gamma), _ptr(beta), _ptr(run_mean), _ptr(run_var), 1 if training else 0,
                            momentum, eps, _ptr(y), _ptr(mean), _ptr(rstd), _stream()), "dvgr_bn_fwd")
     return y, mean, rstd
 
@@ -426,7 +426,7 @@ def bn_bwd(dy, x, gamma, mean, rstd, training):
     B, D = x.shape
     dx = torch.empty_like(x)
     dgamma, dbeta = _empty((D,), F32, x), _empty((D,), F32, x)
-    _lib.check(_lib.bn_bwd(_ptr(dy), _ptr(x), B, D, _ptr(gamma), _ptr(mean), _ptr(rstd), 1 if training else 0, _ptr(dx),
+    _lib.check(_lib.bn_bwd(_ptr(dy), _ptr(x), 1 if x.dtype == F32 else 0, B, D, _ptr(gamma), _ptr(mean), _ptr(rstd), 1 if training else 0, _ptr(dx),
                            _ptr(dgamma), _ptr(dbeta), _stream()), "dvgr_bn_bwd")
     return dx, dgamma, dbeta
 
@@ -483,6 +483,6 @@ def sumsq(g):
 
 
 def adam_step(p, g, m, v, lr, step, beta1=0.9, beta2=0.999, eps=1e-8, max_norm=0.0, norm_sq=None, grad_scale=1.0,
-              step_dev=None):
+              step_dev=None, shadow=None):
     _lib.check(_lib.adam_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), lr, beta1, beta2, eps, step, max_norm,
-                              _ptr(norm_sq), grad_scale, _ptr(step_dev), _stream()), "dvgr_adam_step")
+                              _ptr(norm_sq), grad_scale, _ptr(step_dev), _ptr(shadow), _stream()), "dvgr_adam_step")

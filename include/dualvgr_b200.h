@@ -205,11 +205,13 @@ int dvgr_readout_bwd(const void* dpooled, long long ld_p, const void* v, const v
                      const float* alpha, int B, int N, int D, void* dv, void* du, float* dw_part, float* dc_part,
                      void* stream);
 
-/* BatchNorm1d of the classifier (model/AnswerDecoder.py:193), x/y [B][D] bf16. */
-int dvgr_bn_fwd(const void* x, int B, int D, const float* gamma, const float* beta, float* run_mean, float* run_var,
-                int training, float momentum, float eps, void* y, float* mean_out, float* rstd_out, void* stream);
-int dvgr_bn_bwd(const void* dy, const void* x, int B, int D, const float* gamma, const float* mean, const float* rstd,
-                int training, void* dx, float* dgamma, float* dbeta, void* stream);
+/* BatchNorm1d of the classifier (model/AnswerDecoder.py:193). x [B][D] is f32 (x_is_f32, the precise path: centring
+ * a bf16-rounded input amplifies its rounding error by |x|/std) or bf16; y and dy are bf16; dx has x's type. */
+int dvgr_bn_fwd(const void* x, int x_is_f32, int B, int D, const float* gamma, const float* beta, float* run_mean,
+                float* run_var, int training, float momentum, float eps, void* y, float* mean_out, float* rstd_out,
+                void* stream);
+int dvgr_bn_bwd(const void* dy, const void* x, int x_is_f32, int B, int D, const float* gamma, const float* mean,
+                const float* rstd, int training, void* dx, float* dgamma, float* dbeta, void* stream);
 
 /* nn.CrossEntropyLoss (train.py:121,146) value + gradient: loss_part[b] (sum = mean CE), dlogits [B][ld_d] bf16 =
  * (softmax - onehot) * scale / B with zeroed padding columns, correct[b] = argmax == answer (train.py:352-356). */
@@ -260,6 +262,7 @@ int dvgr_sumsq(const float* g, long long n, float* partial_ws, float* out, void*
 int dvgr_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr,
                    float beta1, float beta2, float eps, int step, float max_norm, const float* norm_sq,
                    float grad_scale, const int* step_dev /* optional device step counter, overrides `step` */,
+                   void* bf16_shadow /* optional [n] bf16 copy of the updated parameters (next step's GEMM operands) */,
                    void* stream);
 
 #ifdef __cplusplus

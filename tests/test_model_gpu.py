@@ -125,15 +125,19 @@ def test_against_live_oracle_full_gradients():
     ref_grads = torch.autograd.grad(ref_ce, [sd[n] for n in names], allow_unused=True)
     assert rel(out[0], ref_out[0]) < TOL
     num = den = 0.0
-    worst = []
+    worst, contrib = [], []
     gmax = max(float(r.norm()) for r in ref_grads if r is not None)
     for n, gr, rg in zip(names, grads, ref_grads):
         if rg is None:
             continue
         gr = torch.zeros_like(rg) if gr is None else gr.double().cpu()
         num += float((gr - rg).pow(2).sum()); den += float(rg.pow(2).sum())
+        contrib.append((float((gr - rg).pow(2).sum()), float(rg.pow(2).sum()), n))
         if float(rg.norm()) > 1e-3 * gmax:                     # skip mathematically-zero gradients (softmax biases)
             worst.append((float((gr - rg).norm() / rg.norm()), n))
+    top = sorted(contrib)[-6:]
+    print("largest error-energy contributors (err^2 share, own rel err):",
+          [(round(e / num, 3), round((e / max(r, 1e-300)) ** 0.5, 4), n) for e, r, n in top])
     print(f"global CE-gradient rel-L2 vs oracle fp64: {(num / den) ** 0.5:.3e}; logits {rel(out[0], ref_out[0]):.3e}; "
           f"worst tensors {sorted(worst)[-3:]}")
     assert (num / den) ** 0.5 < TOL, sorted(worst)[-5:]

@@ -14,6 +14,10 @@ for r in rd:
     us = v / 1e3 if unit in ("ns", "nsecond") else v if unit in ("us", "usecond") else v * 1e3 if unit in ("ms", "msecond") else v
     rows.append((int(r["ID"]), r["Kernel Name"], us))
 rows = rows[skip:]
+if len(sys.argv) > 3 and sys.argv[3] == "laststep":
+    idx = [i for i, r in enumerate(rows) if "adam_kernel" in r[1]]
+    if len(idx) >= 2:
+        rows = rows[idx[-2] + 1: idx[-1] + 1]
 agg = collections.OrderedDict()
 for _, name, us in rows:
     name = re.sub(r"\(.*", "", name)

@@ -35,7 +35,7 @@ class TrainEngine:
                     grouped.append(p); seen.add(id(p))
         self.params = grouped + [p for p in model.parameters() if p.requires_grad and id(p) not in seen]
         dev = self.params[0].device
-        sizes = [(p.numel() + 3) // 4 * 4 for p in self.params]           # 16-byte aligned slices
+        sizes = [(p.numel() + 7) // 8 * 8 for p in self.params]           # 16-byte aligned slices (also in the bf16 shadow)
         total = sum(sizes)
         self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
         self.gflat = torch.zeros(total, dtype=torch.float32, device=dev)

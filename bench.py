@@ -318,11 +318,20 @@ def run_ours(args):
                                               "median of 3 steps after 1 warm-up"}
         print(json.dumps(line), flush=True)
     if world > 1:
+        # the captured graph holds NCCL work objects; tearing the communicator down under it can block forever, so
+        # synchronise, drop the graph, and leave without the (optional) destroy_process_group handshake
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        eng.close()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
+    if os.environ.get("DVGR_HANG_DUMP"):          # debugging aid: dump all Python stacks if the run stalls
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["DVGR_HANG_DUMP"]), exit=True)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

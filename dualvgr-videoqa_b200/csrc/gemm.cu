@@ -22,6 +22,7 @@
 #include "ptx.cuh"
 
 #include <limits.h>
+#include <stdlib.h>
 #include <map>
 #include <mutex>
 #include <string.h>
@@ -37,11 +38,14 @@ constexpr int BK = 64;
 constexpr int kGemmThreads = 384;   // warps 0-3: TMA / MMA / TMEM alloc / spare ; warps 4-11: epilogue (2 per TMEM lane quarter)
 constexpr int kEpiWarps = 8;
 
-template <int BN> struct TileCfg {
+// kOcc = CTAs per SM the variant is built for: 1 (deep pipeline, GEMM-bound shapes) or 2 (3 stages, 96 KB: the LSTM
+// recurrence steps, whose epilogue (scattered state loads/stores + cell math) is the bottleneck, get twice the
+// epilogue warps and memory-level parallelism per SM; 2 x 256 TMEM columns still fit the 512 available).
+template <int BN, int kOcc = 1> struct TileCfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int STAGES = (kOcc == 2) ? 3 : (BN == 256) ? 4 : 6;
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
@@ -53,6 +57,32 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
       "r"(c3)
       : "memory");
+}
+
+// multicast variant: the box lands at the same shared-memory offset of every CTA in `mask` and completes bytes on the
+// barrier at the same offset in each of them
+__device__ __forceinline__ void tma_load_4d_mc(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
+                                               int c3, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+      "r"(c3), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 // ------------------------------------------------------------------------------------------------ epilogues
@@ -275,11 +305,15 @@ __device__ __forceinline__ void epi_lstm_bwd(const GemmParams& p, int dir, int s
 }
 
 // ------------------------------------------------------------------------------------------------ kernel
-template <bool A_MN, bool B_MN, int BN>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+// kCluster == 2: CTA pairs (a thread-block cluster of 2 along M) share every B tile — each CTA fetches HALF of it and
+// TMA-multicasts it into both shared memories, which cuts the L2 -> SMEM operand traffic per MMA by a third (the
+// single-CTA kernel measured 36 % tensor-pipe activity at the ~6.3 KB/clk L2 throughput cap).
+template <bool A_MN, bool B_MN, int BN, int kOcc, int kCluster>
+__global__ void __launch_bounds__(kGemmThreads, kOcc)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const GemmParams p) {
-  using Cfg = TileCfg<BN>;
+  using Cfg = TileCfg<BN, kOcc>;
+  const uint32_t crank = (kCluster > 1) ? cluster_ctarank() : 0u;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -292,10 +326,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int m_blocks = (p.M + BM - 1) / BM;
+  const int m_blocks = ((p.M + BM - 1) / BM + kCluster - 1) / kCluster;   // per-cluster M blocks (pairs when kCluster == 2)
   const int n_blocks = (p.N + BN - 1) / BN;
   const int k_blocks = (p.K + BK - 1) / BK;
   const int ksplit = p.ksplit > 1 ? p.ksplit : 1;
+  const int tile0 = blockIdx.x / kCluster, tile_step = gridDim.x / kCluster;
   const int kb_per = (k_blocks + ksplit - 1) / ksplit;
   const int tiles_per_batch = m_blocks * n_blocks;
   const int num_tiles = tiles_per_batch * p.batch * ksplit;     // tile = ((ks * batch + b) * m_blocks + m) * n_blocks + n
@@ -307,7 +342,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], kCluster);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
@@ -318,6 +353,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
+  if (kCluster > 1) cluster_sync_all();     // the peer's barriers must be initialised before any multicast touches them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -325,13 +361,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ===================================================== TMA producer
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = tile0; tile < num_tiles; tile += tile_step) {
       const int ks = tile / (tiles_per_batch * p.batch);
       const int t2 = tile - ks * tiles_per_batch * p.batch;
       const int b = t2 / tiles_per_batch;
       const int rem = t2 - b * tiles_per_batch;
-      const int m_blk = rem / n_blocks;
-      const int n_blk = rem - m_blk * n_blocks;
+      const int m_blk = (rem / n_blocks) * kCluster + (int)crank;
+      const int n_blk = rem - (rem / n_blocks) * n_blocks;
       const int kb0 = ks * kb_per, kb1 = min(k_blocks, kb0 + kb_per);
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1u);
@@ -348,13 +384,29 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tma_load_4d(sA + c * (64 * BK * 2), &tmA, &full_bar[stage], p.a_c0[b] + m_blk * BM + c * 64, kin,
                         p.a_c2[b] + seg * p.a_c2_step[b], p.a_c3[b]);
         }
-        if (!B_MN) {
-          tma_load_4d(sB, &tmB, &full_bar[stage], p.b_c0[b] + kb * BK, n_blk * BN, p.b_c2[b], p.b_c3[b]);
-        } else {
+        if (kCluster == 1) {
+          if (!B_MN) {
+            tma_load_4d(sB, &tmB, &full_bar[stage], p.b_c0[b] + kb * BK, n_blk * BN, p.b_c2[b], p.b_c3[b]);
+          } else {
 #pragma unroll
-          for (int c = 0; c < BN / 64; ++c)
-            tma_load_4d(sB + c * (64 * BK * 2), &tmB, &full_bar[stage], p.b_c0[b] + n_blk * BN + c * 64, kin,
-                        p.b_c2[b] + seg * p.b_c2_step[b], p.b_c3[b]);
+            for (int c = 0; c < BN / 64; ++c)
+              tma_load_4d(sB + c * (64 * BK * 2), &tmB, &full_bar[stage], p.b_c0[b] + n_blk * BN + c * 64, kin,
+                          p.b_c2[b] + seg * p.b_c2_step[b], p.b_c3[b]);
+          }
+        } else {   // this CTA fetches its half of the B tile and multicasts it to the pair
+          constexpr uint16_t kMask = (1u << kCluster) - 1u;
+          if (!B_MN) {
+            const int half_rows = BN / kCluster;
+            tma_load_4d_mc(sB + crank * (half_rows * BK * 2), &tmB, &full_bar[stage], p.b_c0[b] + kb * BK,
+                           n_blk * BN + (int)crank * half_rows, p.b_c2[b], p.b_c3[b], kMask);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BN / 64 / kCluster; ++c) {
+              const int cc = (int)crank * (BN / 64 / kCluster) + c;
+              tma_load_4d_mc(sB + cc * (64 * BK * 2), &tmB, &full_bar[stage], p.b_c0[b] + n_blk * BN + cc * 64, kin,
+                             p.b_c2[b] + seg * p.b_c2_step[b], p.b_c3[b], kMask);
+            }
+          }
         }
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
@@ -366,7 +418,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint32_t phase = 0;
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = tile0; tile < num_tiles; tile += tile_step) {
       const int ks = tile / (tiles_per_batch * p.batch);
       const int kb0 = ks * kb_per, kb1 = min(k_blocks, kb0 + kb_per);
       mbar_wait(&tempty_bar[as], aphase ^ 1u);
@@ -383,7 +435,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const uint64_t db = B_MN ? umma_smem_desc(sB + k * 2048, 64 * BK * 2, 1024) : umma_smem_desc(sB + k * 32, 16, 1024);
           umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k != 0) ? 1u : 0u);
         }
-        umma_commit(&empty_bar[stage]);
+        if (kCluster == 1) umma_commit(&empty_bar[stage]);
+        else umma_commit_mc(&empty_bar[stage], (1u << kCluster) - 1u);   // the slot is reusable once BOTH CTAs drained it
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
       umma_commit(&tfull_bar[as]);
@@ -396,13 +449,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int half = (warp - 4) >> 2;
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = tile0; tile < num_tiles; tile += tile_step) {
       const int ks = tile / (tiles_per_batch * p.batch);
       const int t2 = tile - ks * tiles_per_batch * p.batch;
       const int b = t2 / tiles_per_batch;
       const int rem = t2 - b * tiles_per_batch;
-      const int m_blk = rem / n_blocks;
-      const int n_blk = rem - m_blk * n_blocks;
+      const int m_blk = (rem / n_blocks) * kCluster + (int)crank;
+      const int n_blk = rem - (rem / n_blocks) * n_blocks;
       const int kb0 = ks * kb_per, kb1 = min(k_blocks, kb0 + kb_per);
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
@@ -429,6 +482,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   tc_fence_before();
   __syncthreads();
+  if (kCluster > 1) cluster_sync_all();     // no CTA may retire while its peer can still multicast into its shared memory
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
@@ -563,22 +617,40 @@ static int num_sms() {
   return n;
 }
 
-template <bool A_MN, bool B_MN, int BN>
+template <bool A_MN, bool B_MN, int BN, int kOcc = 1, int kCluster = 1>
 static int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int max_ctas,
                           cudaStream_t stream) {
-  using Cfg = TileCfg<BN>;
+  using Cfg = TileCfg<BN, kOcc>;
   static bool attr_set = false;
-  auto kern = gemm_tcgen05_kernel<A_MN, B_MN, BN>;
+  auto kern = gemm_tcgen05_kernel<A_MN, B_MN, BN, kOcc, kCluster>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return set_error("cudaFuncSetAttribute(smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
     attr_set = true;
   }
-  const int m_blocks = (p.M + BM - 1) / BM, n_blocks = (p.N + BN - 1) / BN;
+  const int m_blocks = ((p.M + BM - 1) / BM + kCluster - 1) / kCluster, n_blocks = (p.N + BN - 1) / BN;
   const long long tiles = (long long)m_blocks * n_blocks * p.batch * (p.ksplit > 1 ? p.ksplit : 1);
-  int grid = (int)std::min<long long>(tiles, max_ctas > 0 ? max_ctas : num_sms());
+  long long grid = std::min<long long>(tiles * kCluster, max_ctas > 0 ? max_ctas : num_sms() * kOcc);
+  grid = grid / kCluster * kCluster;
   if (grid <= 0) return 0;
-  kern<<<grid, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
+  if (kCluster == 1) {
+    kern<<<(int)grid, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kCluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, p);
+    if (e != cudaSuccess) return set_error("gemm cluster launch failed: %s", cudaGetErrorString(e));
+  }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("gemm launch failed: %s", cudaGetErrorString(e));
   return 0;
@@ -603,9 +675,20 @@ int gemm_dispatch(const dvgr_operand& A, const dvgr_operand& B, GemmParams p, in
   CUtensorMap ta, tb;
   int rc = make_tensor_map(&ta, A, 64, a_mn ? 64 : BM);
   if (rc) return rc;
-  rc = make_tensor_map(&tb, B, 64, b_mn ? 64 : bn);
+  static const int use_cluster = getenv("DVGR_GEMM_CLUSTER") ? atoi(getenv("DVGR_GEMM_CLUSTER")) : 0;   // measured r1: multicast at cluster size 2 does not raise throughput (L2 broadcast ~ unicast below cluster size 8); kept as an opt-in
+  static const int lstm_occ = getenv("DVGR_LSTM_OCC") ? atoi(getenv("DVGR_LSTM_OCC")) : 0;   // tuning knob (bit0: fwd, bit1: bwd use 2 CTAs/SM)
+  const bool lstm2 = (p.mode == EPI_LSTM_FWD && !a_mn && !b_mn && (lstm_occ & 1)) ||
+                     (p.mode == EPI_LSTM_BWD && !a_mn && b_mn && (lstm_occ & 2));
+  const bool cluster = use_cluster && !lstm2 && ((p.M + BM - 1) / BM >= 2);
+  rc = make_tensor_map(&tb, B, 64, b_mn ? 64 : (cluster ? bn / 2 : bn));
   if (rc) return rc;
-#define DVGR_LAUNCH(AM, BMJ, BNV) return launch_variant<AM, BMJ, BNV>(ta, tb, p, max_ctas, stream)
+  if (p.mode == EPI_LSTM_FWD && !a_mn && !b_mn && (lstm_occ & 1)) return launch_variant<false, false, 128, 2, 1>(ta, tb, p, max_ctas, stream);
+  if (p.mode == EPI_LSTM_BWD && !a_mn && b_mn && (lstm_occ & 2)) return launch_variant<false, true, 128, 2, 1>(ta, tb, p, max_ctas, stream);
+#define DVGR_LAUNCH(AM, BMJ, BNV)                                                         \
+  do {                                                                                    \
+    if (cluster) return launch_variant<AM, BMJ, BNV, 1, 2>(ta, tb, p, max_ctas, stream);  \
+    return launch_variant<AM, BMJ, BNV, 1, 1>(ta, tb, p, max_ctas, stream);               \
+  } while (0)
   if (!a_mn && !b_mn) { if (bn == 256) DVGR_LAUNCH(false, false, 256); else DVGR_LAUNCH(false, false, 128); }
   if (!a_mn && b_mn) { if (bn == 256) DVGR_LAUNCH(false, true, 256); else DVGR_LAUNCH(false, true, 128); }
   if (a_mn && b_mn) { if (bn == 256) DVGR_LAUNCH(true, true, 256); else DVGR_LAUNCH(true, true, 128); }

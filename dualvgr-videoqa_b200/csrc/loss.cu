@@ -35,47 +35,58 @@ struct PairParams {
   float* gram_ws;     // [jobs][B][chunks][2][N][N]
 };
 
-// Loads a column chunk of both tensors, centred over the nodes (columns beyond D are zero).
+constexpr int kTS = kChunk + 4;     // padded tile row stride (floats): conflict-free TF32 fragment loads
+
+__host__ __device__ inline int round16(int n) { return (n + 15) & ~15; }
+
+// Loads a column chunk of both tensors, centred over the nodes, into tile[2][NP16][kTS]
+// (columns beyond D and rows beyond N are zero).
 __device__ __forceinline__ void load_centered_chunk(const float* __restrict__ x, const float* __restrict__ y, int N, int D,
                                                     int c0, float* tile) {
+  const int NP = round16(N);
   for (int cc = threadIdx.x; cc < kChunk; cc += blockDim.x) {
     const int c = c0 + cc;
 #pragma unroll
     for (int which = 0; which < 2; ++which) {
       const float* src = which ? y : x;
-      float* t = tile + (size_t)which * N * kChunk;
+      float* t = tile + (size_t)which * NP * kTS;
       float s = 0.f;
       if (c < D)
         for (int n = 0; n < N; ++n) s += src[(long long)n * D + c];
       const float mean = s / N;
-      for (int n = 0; n < N; ++n) t[n * kChunk + cc] = (c < D) ? src[(long long)n * D + c] - mean : 0.f;
+      for (int n = 0; n < N; ++n) t[n * kTS + cc] = (c < D) ? src[(long long)n * D + c] - mean : 0.f;
+      for (int n = N; n < NP; ++n) t[n * kTS + cc] = 0.f;
     }
   }
 }
 
-// pass 1: partial centred Gram matrices of one (video, job, column chunk)
+// pass 1: partial centred Gram matrices of one (video, job, column chunk): T T^T on the tensor cores (TF32 m16n8k8)
 __global__ void __launch_bounds__(kLossThreads) pair_gram_kernel(const PairParams p) {
   extern __shared__ __align__(16) float sm[];
-  float* tile = sm;   // [2][N][kChunk]
-  const int b = blockIdx.x, jb = blockIdx.y, ch = blockIdx.z, N = p.N, D = p.D;
+  float* tile = sm;   // [2][NP16][kTS]
+  const int b = blockIdx.x, jb = blockIdx.y, ch = blockIdx.z, N = p.N, D = p.D, NP = round16(N);
   const PairJob& J = p.job[jb];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = kLossThreads / 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = kLossThreads / 32, g = lane >> 2, t = lane & 3;
   load_centered_chunk(J.x + (long long)b * N * D, J.y + (long long)b * N * D, N, D, ch * kChunk, tile);
   __syncthreads();
   float* out = p.gram_ws + ((((long long)jb * p.B + b) * p.chunks + ch) * 2) * N * N;
-  for (int pr = warp; pr < 2 * N * N; pr += nwarps) {
-    const int which = pr / (N * N), r = pr - which * N * N, i = r / N, j = r - i * N;
-    if (j < i) continue;
-    const float* ti = tile + ((size_t)which * N + i) * kChunk;
-    const float* tj = tile + ((size_t)which * N + j) * kChunk;
-    float acc = 0.f;
-#pragma unroll
-    for (int q = 0; q < kChunk / 32; ++q) acc += ti[lane + 32 * q] * tj[lane + 32 * q];
-    acc = warp_sum(acc);
-    if (lane == 0) {
-      out[which * N * N + i * N + j] = acc;
-      out[which * N * N + j * N + i] = acc;
-    }
+  const int MT = NP / 16, NT = NP / 8;
+  for (int ot = warp; ot < 2 * MT * NT; ot += nwarps) {
+    const int which = ot / (MT * NT), r = ot - which * MT * NT, mt = r / NT, nt = r - mt * NT;
+    const float* T = tile + (size_t)which * NP * kTS;
+    const float* ar = T + (size_t)(mt * 16 + g) * kTS + t;
+    const float* br = T + (size_t)(nt * 8 + g) * kTS + t;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+    for (int k0 = 0; k0 < kChunk; k0 += 8)
+      mma_tf32(acc, to_tf32(ar[k0]), to_tf32(ar[8 * kTS + k0]), to_tf32(ar[k0 + 4]), to_tf32(ar[8 * kTS + k0 + 4]),
+               to_tf32(br[k0]), to_tf32(br[k0 + 4]));
+    const int row = mt * 16 + g, col = nt * 8 + 2 * t;
+    float* o = out + which * N * N;
+    if (row < N && col < N) o[row * N + col] = acc[0];
+    if (row < N && col + 1 < N) o[row * N + col + 1] = acc[1];
+    if (row + 8 < N && col < N) o[(row + 8) * N + col] = acc[2];
+    if (row + 8 < N && col + 1 < N) o[(row + 8) * N + col + 1] = acc[3];
   }
 }
 
@@ -86,47 +97,59 @@ __device__ __forceinline__ void emit(float* dst, long long o, float v, int acc) 
 }
 
 // pass 2: N x N algebra (redundantly per chunk CTA: it is tiny), loss value (chunk 0), gradient of this column chunk
+// as (N x N) . (N x 256) products on the tensor cores.
+__host__ __device__ inline size_t pair_grad_smem(int N) {
+  const int NP = round16(N), CS = NP + 4;
+  return (size_t)(2 * NP * kTS + 3 * NP * CS + 4 * NP) * sizeof(float);
+}
+
 __global__ void __launch_bounds__(kLossThreads) pair_grad_kernel(const PairParams p) {
   extern __shared__ __align__(16) float sm[];
-  const int b = blockIdx.x, jb = blockIdx.y, ch = blockIdx.z, N = p.N, D = p.D;
+  const int b = blockIdx.x, jb = blockIdx.y, ch = blockIdx.z, N = p.N, D = p.D, NP = round16(N), CS = NP + 4;
   const PairJob& J = p.job[jb];
-  float* tile = sm;                               // [2][N][kChunk]
-  float* C = tile + 2 * N * kChunk;               // [2][N][N]
-  float* Delta = C + 2 * N * N;                   // [N][N]
-  float* nrm = Delta + N * N;                     // [2][N]
-  float* rdot = nrm + 2 * N;                      // [2][N]
+  float* tile = sm;                               // [2][NP][kTS]
+  float* C = tile + 2 * NP * kTS;                 // [2][NP][CS]  (zero padded)
+  float* Delta = C + 2 * NP * CS;                 // [NP][CS]
+  float* nrm = Delta + NP * CS;                   // [2][NP]
+  float* rdot = nrm + 2 * NP;                     // [2][NP]
   __shared__ float red[kLossThreads / 32];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = kLossThreads / 32;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = kLossThreads / 32, g = lane >> 2, t = lane & 3;
   const float* x = J.x + (long long)b * N * D;
   const float* y = J.y + (long long)b * N * D;
   const float coef = J.coef;
   const float* gw = p.gram_ws + (((long long)jb * p.B + b) * p.chunks * 2) * N * N;
-  for (int e = tid; e < 2 * N * N; e += kLossThreads) {
+  for (int e = tid; e < 2 * NP * CS; e += kLossThreads) {
+    const int which = e / (NP * CS), r = e - which * NP * CS, i = r / CS, j = r - i * CS;
     float s = 0.f;
-    for (int k = 0; k < p.chunks; ++k) s += gw[(long long)k * 2 * N * N + e];
+    if (i < N && j < N)
+      for (int k = 0; k < p.chunks; ++k) s += gw[(long long)k * 2 * N * N + which * N * N + i * N + j];
     C[e] = s;
   }
+  for (int e = tid; e < NP * CS; e += kLossThreads) Delta[e] = 0.f;
   load_centered_chunk(x, y, N, D, ch * kChunk, tile);
   __syncthreads();
   float part = 0.f;
   if (J.mode == 0) {
     for (int i = tid; i < 2 * N; i += kLossThreads) {
       const int which = i / N, n = i - which * N;
-      nrm[i] = fmaxf(sqrtf(fmaxf(C[which * N * N + n * N + n], 0.f)), 1e-12f);
+      nrm[which * NP + n] = fmaxf(sqrtf(fmaxf(C[which * NP * CS + n * CS + n], 0.f)), 1e-12f);
     }
     __syncthreads();
     for (int e = tid; e < N * N; e += kLossThreads) {
       const int i = e / N, j = e - i * N;
-      const float g1 = C[e] / (nrm[i] * nrm[j]);
-      const float g2 = C[N * N + e] / (nrm[N + i] * nrm[N + j]);
+      const float g1 = C[i * CS + j] / (nrm[i] * nrm[j]);
+      const float g2 = C[NP * CS + i * CS + j] / (nrm[NP + i] * nrm[NP + j]);
       const float d = g1 - g2;
       part += d * d;
-      Delta[e] = 2.f * coef * d;      // dL/dG1 ; dL/dG2 = -Delta
-      C[e] = g1;                      // keep the normalised Grams for r_i
-      C[N * N + e] = g2;
+      Delta[i * CS + j] = 2.f * coef * d;     // dL/dG1 ; dL/dG2 = -Delta
+      C[i * CS + j] = g1;                      // keep the normalised Grams for r_i
+      C[NP * CS + i * CS + j] = g2;
     }
   } else {
-    for (int e = tid; e < N * N; e += kLossThreads) part += C[e] * C[N * N + e];
+    for (int e = tid; e < N * N; e += kLossThreads) {
+      const int i = e / N, j = e - i * N;
+      part += C[i * CS + j] * C[NP * CS + i * CS + j];
+    }
   }
   part = warp_sum(part);
   if (lane == 0) red[warp] = part;
@@ -140,50 +163,82 @@ __global__ void __launch_bounds__(kLossThreads) pair_grad_kernel(const PairParam
     for (int i = tid; i < 2 * N; i += kLossThreads) {     // r_i = E^_i . dE^_i = 2 sum_j (+-Delta_ij) G_ij
       const int which = i / N, n = i - which * N;
       float s = 0.f;
-      for (int j = 0; j < N; ++j) s += Delta[n * N + j] * C[which * N * N + n * N + j];
-      rdot[i] = (which ? -2.f : 2.f) * s;
+      for (int j = 0; j < N; ++j) s += Delta[n * CS + j] * C[which * NP * CS + n * CS + j];
+      rdot[which * NP + n] = (which ? -2.f : 2.f) * s;
     }
+    // E^ = E' / n (in place; each thread owns whole columns of both tiles)
+    for (int cc = tid; cc < kChunk; cc += kLossThreads)
+      for (int which = 0; which < 2; ++which)
+        for (int j = 0; j < N; ++j) tile[((size_t)which * NP + j) * kTS + cc] /= nrm[which * NP + j];
   }
   __syncthreads();
   if (J.dx == nullptr && J.dy == nullptr) return;
-  float* dx = J.dx ? J.dx + (long long)b * N * D : nullptr;
-  float* dy = J.dy ? J.dy + (long long)b * N * D : nullptr;
-  for (int cc = tid; cc < kChunk; cc += kLossThreads) {
-    const int c = ch * kChunk + cc;
-    if (c >= D) continue;
+
+  const int MT = NP / 16;
+  for (int which = 0; which < 2; ++which) {
+    float* dst = which ? (J.dy ? J.dy + (long long)b * N * D : nullptr) : (J.dx ? J.dx + (long long)b * N * D : nullptr);
+    if (dst == nullptr) continue;
+    const int acc_flag = which ? J.acc_y : J.acc_x;
+    const float* A = (J.mode == 0) ? Delta : C + (size_t)(1 - which) * NP * CS;     // [NP][CS]
+    const float* Bt = tile + (size_t)which * NP * kTS;                                // [NP][kTS]
+    const float scale = (J.mode == 0) ? (which ? -2.f : 2.f) : 2.f * coef;
+    for (int nt = warp; nt < kChunk / 8; nt += nwarps) {
+      float acc[4][4];
 #pragma unroll
-    for (int which = 0; which < 2; ++which) {
-      float* dst = which ? dy : dx;
-      if (dst == nullptr) continue;
-      const int acc_flag = which ? J.acc_y : J.acc_x;
-      float* col = tile + (size_t)which * N * kChunk;          // centred values of this tensor, column cc
-      if (J.mode == 1) {
-        // d/dE_which = 2 coef * C_other (R E_which)   (its column mean is already zero: rows of C sum to zero)
-        const float* Co = C + (1 - which) * N * N;
-        for (int i = 0; i < N; ++i) {
-          float s = 0.f;
-          for (int j = 0; j < N; ++j) s += Co[i * N + j] * col[j * kChunk + cc];
-          emit(dst, (long long)i * D + c, 2.f * coef * s, acc_flag);
+      for (int m = 0; m < 4; ++m) acc[m][0] = acc[m][1] = acc[m][2] = acc[m][3] = 0.f;
+      for (int k0 = 0; k0 < NP; k0 += 8) {
+        const uint32_t b0 = to_tf32(Bt[(size_t)(k0 + t) * kTS + nt * 8 + g]);
+        const uint32_t b1 = to_tf32(Bt[(size_t)(k0 + t + 4) * kTS + nt * 8 + g]);
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          if (m < MT) {
+            const float* ar = A + (size_t)(m * 16 + g) * CS + k0 + t;
+            mma_tf32(acc[m], to_tf32(ar[0]), to_tf32(ar[8 * CS]), to_tf32(ar[4]), to_tf32(ar[8 * CS + 4]), b0, b1);
+          }
         }
-      } else {
-        // E^_j[c] (the thread owns column cc of both tiles: in-place scaling is race-free)
-        const float sign = which ? -1.f : 1.f;
-        const float* nr = nrm + which * N;
-        const float* rd = rdot + which * N;
-        for (int j = 0; j < N; ++j) col[j * kChunk + cc] /= nr[j];
-        // dE'_i = (dE^_i - E^_i r_i) / n_i with dE^_i = 2 sign sum_j Delta_ij E^_j ; dE = dE' - column mean(dE')
-        float colsum = 0.f;
-        for (int i = 0; i < N; ++i) {
-          float sacc = 0.f;
-          for (int j = 0; j < N; ++j) sacc += Delta[i * N + j] * col[j * kChunk + cc];
-          colsum += (2.f * sign * sacc - col[i * kChunk + cc] * rd[i]) / nr[i];
+      }
+      const int cc = nt * 8 + 2 * t, c = ch * kChunk + cc;
+      float v[4][4];
+      float cs0 = 0.f, cs1 = 0.f;
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {      // h = 0: row g, h = 1: row g + 8
+          const int i = m * 16 + g + 8 * h;
+          float v0 = scale * acc[m][2 * h], v1 = scale * acc[m][2 * h + 1];
+          if (J.mode == 0) {
+            if (m < MT && i < N) {
+              const float nr = nrm[which * NP + i], rd = rdot[which * NP + i];
+              v0 = (v0 - Bt[(size_t)i * kTS + cc] * rd) / nr;
+              v1 = (v1 - Bt[(size_t)i * kTS + cc + 1] * rd) / nr;
+            } else {
+              v0 = v1 = 0.f;
+            }
+            cs0 += v0;
+            cs1 += v1;
+          }
+          v[m][2 * h] = v0;
+          v[m][2 * h + 1] = v1;
         }
-        const float mean = colsum / N;
-        for (int i = 0; i < N; ++i) {
-          float sacc = 0.f;
-          for (int j = 0; j < N; ++j) sacc += Delta[i * N + j] * col[j * kChunk + cc];
-          const float v = (2.f * sign * sacc - col[i * kChunk + cc] * rd[i]) / nr[i] - mean;
-          emit(dst, (long long)i * D + c, v, acc_flag);
+      }
+      if (J.mode == 0) {      // dE = dE' - column mean(dE') ; rows live in the 8 lanes sharing t
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+          cs0 += __shfl_xor_sync(0xffffffffu, cs0, o);
+          cs1 += __shfl_xor_sync(0xffffffffu, cs1, o);
+        }
+        cs0 /= N;
+        cs1 /= N;
+      }
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int i = m * 16 + g + 8 * h;
+          if (m < MT && i < N) {
+            if (c < D) emit(dst, (long long)i * D + c, v[m][2 * h] - (J.mode == 0 ? cs0 : 0.f), acc_flag);
+            if (c + 1 < D) emit(dst, (long long)i * D + c + 1, v[m][2 * h + 1] - (J.mode == 0 ? cs1 : 0.f), acc_flag);
+          }
         }
       }
     }
@@ -216,8 +271,8 @@ extern "C" int dvgr_pair_loss_multi(const dvgr_pair_job* jobs, int n_jobs, int B
     d.x = s.x; d.y = s.y; d.dx = s.dx; d.dy = s.dy; d.loss_part = s.loss_part; d.loss_col = s.loss_col;
     d.loss_ld = s.loss_ld; d.mode = s.mode; d.acc_x = s.accumulate_x; d.acc_y = s.accumulate_y; d.coef = s.coef;
   }
-  const size_t smem1 = (size_t)2 * N * kChunk * sizeof(float);
-  const size_t smem2 = (size_t)(2 * N * kChunk + 3 * N * N + 4 * N) * sizeof(float);
+  const size_t smem1 = (size_t)2 * round16(N) * kTS * sizeof(float);
+  const size_t smem2 = pair_grad_smem(N);
   static size_t conf1 = 0, conf2 = 0;
   if (smem1 > 48 * 1024 && smem1 > conf1) {
     cudaError_t e = cudaFuncSetAttribute(pair_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);

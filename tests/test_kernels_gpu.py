@@ -313,7 +313,9 @@ def test_pair_losses(ops, N):
         com = orc.common_loss(xr, yr)
         gx, gy = torch.autograd.grad(com, (xr, yr))
         loss, dx, dy = ops.pair_loss(x.cuda(), y.cuda(), 0, 1.0 / (B * N * N))
-        tol = 1e-4 if spread == 1.0 else 5e-2      # fp32 noise floor of the centred/normalised form
+        # N x N Grams and gradient products run on TF32 tensor cores (10-bit mantissa): 1e-3; the ill-conditioned regime
+        # (nearly identical nodes) sits at the fp32 noise floor of the centred/normalised form
+        tol = 1e-3 if spread == 1.0 else 5e-2
         assert abs(float(loss) - float(com)) <= tol * abs(float(com))
         assert rel(dx, gx) < max(tol, 1e-3) and rel(dy, gy) < max(tol, 1e-3)
         hs = orc.loss_dependence(xr, yr, N)

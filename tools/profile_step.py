@@ -1,0 +1,42 @@
+"""In-situ kernel timing of the captured train step with torch.profiler (CUPTI): warm caches, real overlap."""
+import os, sys, collections, re
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import torch
+import dualvgr_oracle as orc
+import dualvgr_videoqa_b200.model.models as M
+from dualvgr_videoqa_b200.engine import TrainEngine
+import bench
+
+c = bench.CFG
+dev = torch.device("cuda", 0)
+model = M.DualVGR(vocab=orc.make_vocab(c["V"], c["A"]), num_of_nodes=c["N"], graph_module="GAT", graph_layers=1, unit_layers=c["U"])
+model.load_state_dict(orc.make_state_dict(c["U"], c["A"], c["V"]), strict=True)
+model = model.to(dev).train()
+eng = TrainEngine(model)
+g = torch.Generator().manual_seed(1)
+app = torch.randn((c["B"], c["N"], c["F"], c["Dv"]), generator=g).abs_().to(dev)
+mot = torch.randn((c["B"], c["N"], c["Dv"]), generator=g).abs_().to(dev)
+qlen = torch.randint(5, c["L"] + 1, (c["B"],), generator=g); qlen[0] = c["L"]
+q = (torch.randint(2, c["V"], (c["B"], c["L"]), generator=g) * (torch.arange(c["L"])[None] < qlen[:, None])).to(dev)
+ans = torch.randint(0, c["A"], (c["B"],), generator=g).to(dev)
+eng.capture(app, mot, q, qlen.to(dev), ans)
+for _ in range(3):
+    eng.replay()
+torch.cuda.synchronize()
+from torch.profiler import profile, ProfilerActivity
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    for _ in range(3):
+        eng.replay()
+    torch.cuda.synchronize()
+agg = collections.OrderedDict()
+tot = 0.0
+for ev in prof.events():
+    if ev.device_type == torch.autograd.DeviceType.CUDA:
+        name = re.sub(r"\(.*", "", ev.name)[:100]
+        a = agg.setdefault(name, [0, 0.0]); a[0] += 1; a[1] += ev.device_time_total if hasattr(ev, "device_time_total") else ev.cuda_time_total
+        tot += a[1] * 0
+tot = sum(v[1] for v in agg.values())
+print(f"kernel time per step: {tot/3/1e3:.3f} ms over {sum(v[0] for v in agg.values())//3} launches")
+for name, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:40]:
+    print(f"{us/3/1e3:8.3f} ms {100*us/tot:5.1f}%  x{n//3:<4d} {name}")

@@ -162,17 +162,10 @@ __device__ __forceinline__ void gat_softmax_row(const GatParams& p, const GatSme
 
 // Dropout stream layout (any bijection works as long as forward and backward agree; these make ONE Philox call serve
 // eight mask elements where the kernels consume them):
-//   attention mask (b, k, i, j)  : call ((b*K + k)*N + i) * ceil(N/8) + j/8 , element j%8
+//   attention mask (b, k, i, j)  : murmur-hashed element index ((b*K + k)*N + i)*N + j (rng.cuh: dropout_scale1_hash)
 //   output mask    (b, i, c)     : call ((b*(D/2) + c/2) * ceil(N/4) + i/4 , element (i%4)*2 + (c&1)
 __device__ __forceinline__ float att_keep(const GatParams& p, const DropoutCfg& cfg, int b, int k, int i, int j) {
-  if (cfg.p <= 0.f) return 1.f;
-  float sc[8];
-  const unsigned long long call = (((unsigned long long)b * p.heads + k) * p.N + i) * ((p.N + 7) >> 3) + (j >> 3);
-  dropout_scale8(cfg, call, sc);
-  float v = sc[0];
-#pragma unroll
-  for (int q = 1; q < 8; ++q) v = ((j & 7) == q) ? sc[q] : v;
-  return v;
+  return dropout_scale1_hash(cfg, (((unsigned long long)b * p.heads + k) * p.N + i) * p.N + j);
 }
 __device__ __forceinline__ void out_keep8(const GatParams& p, const DropoutCfg& cfg, int b, int pair, int rowquad,
                                           float (&sc)[8]) {

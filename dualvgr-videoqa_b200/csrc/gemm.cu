@@ -47,7 +47,9 @@ template <int BN, int kOcc = 1> struct TileCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (kOcc == 2) ? 3 : (BN == 256) ? 4 : 6;
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int STAGING_BYTES = 8 * 32 * 33 * 4;      // per-epilogue-warp transpose tiles (epi_linear)
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + STAGING_BYTES;
+  static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory a CTA can opt into");
 };
 
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
@@ -70,6 +72,11 @@ __device__ __forceinline__ void tma_load_4d_mc(void* smem_dst, const CUtensorMap
       "r"(c3), "h"(mask)
       : "memory");
 }
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* m, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
 __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(smem_u32(bar)), "h"(mask)
@@ -86,73 +93,93 @@ __device__ __forceinline__ void cluster_sync_all() {
 }
 
 // ------------------------------------------------------------------------------------------------ epilogues
-__device__ __forceinline__ void epi_linear(const GemmParams& p, int b, int row, int col0, const uint32_t (&r)[32], int ks) {
-  if (row >= p.M || col0 >= p.N) return;
-  const long long orow = p.row_map ? p.row_map[row] : row;
+constexpr int kStagePitch = 33;                                  // floats per staged row: conflict-free both ways
+constexpr int kStageFloats = 32 * kStagePitch;                   // one 32 x 32 fp32 chunk per epilogue warp
+
+// Linear epilogue of one 32-row x 32-column accumulator chunk (this warp's TMEM lane quarter).
+// The accumulators arrive one ROW per lane (tcgen05.ld 32x32b); storing them like that issues 16-byte writes to 32
+// different rows per instruction (measured: ~12 us per 128x256 tile, the whole GEMM was epilogue-bound). They are
+// transposed through a per-warp shared-memory tile instead, so every store instruction writes whole 64 / 128-byte row
+// segments; bias, activation, accumulation and the bf16 conversion happen on the transposed side.
+__device__ __forceinline__ void epi_linear(const GemmParams& p, int b, int row0, int col0, const uint32_t (&r)[32], int ks,
+                                           float* stage, int lane) {
+  if (row0 >= p.M || col0 >= p.N) return;      // warp-uniform
+#pragma unroll
+  for (int j = 0; j < 32; ++j) stage[lane * kStagePitch + j] = __uint_as_float(r[j]);
+  __syncwarp();
   const float* bias = (p.bias && ks == 0) ? p.bias + (long long)b * p.bias_batch : nullptr;
-  float v[32];
   const int nvalid = min(32, p.N - col0);
+  // NOTE on code size: this body runs once per 32x32 chunk by every epilogue warp; the first version unrolled the
+  // activation switch per element (~40 KB of SASS) and ran at instruction-fetch speed. Loops stay rolled on purpose.
+  const int per = p.out_f32 ? 4 : 8;                    // elements per lane: one 16-byte store either way
+  const int lanes_per_row = 32 / per;                    // 8 (fp32: 128-byte row segment) or 4 (bf16: 64-byte segment)
+  const int q = lane % lanes_per_row, cq = per * q;
+  const int rows_per_it = 32 / lanes_per_row;
+  float bv[8];
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    float x = __uint_as_float(r[j]);
-    if (bias != nullptr && j < nvalid) x += __ldg(bias + col0 + j);
-    if (p.act == ACT_ELU) x = eluf_(x);
-    else if (p.act == ACT_TANH) x = tanhf_(x);
-    v[j] = x;
-  }
-  if (p.out_f32) {
-    float* c = reinterpret_cast<float*>(p.C) + (long long)b * p.c_batch + orow * p.ldc + col0;
-    const bool vec = (nvalid == 32) && ((reinterpret_cast<uintptr_t>(c) & 15) == 0);
-    if (p.beta == 2) {
-      if (vec) {
+  for (int e = 0; e < 8; ++e) bv[e] = (bias != nullptr && e < per && cq + e < nvalid) ? __ldg(bias + col0 + cq + e) : 0.f;
+  const int act = p.act;
+#pragma unroll 1
+  for (int it = 0; it < lanes_per_row; ++it) {
+    const int rr = it * rows_per_it + lane / lanes_per_row, row = row0 + rr;
+    if (row >= p.M) continue;
+    const long long orow = p.row_map ? p.row_map[row] : row;
+    float v[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(c + 4 * j), "f"(v[4 * j]), "f"(v[4 * j + 1]),
-                       "f"(v[4 * j + 2]), "f"(v[4 * j + 3])
+    for (int e = 0; e < 8; ++e) v[e] = (e < per) ? stage[rr * kStagePitch + cq + e] + bv[e] : 0.f;
+    if (act == ACT_ELU) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = eluf_(v[e]);
+    } else if (act == ACT_TANH) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = tanhf_(v[e]);
+    }
+    if (p.out_f32) {
+      float* c = reinterpret_cast<float*>(p.C) + (long long)b * p.c_batch + orow * p.ldc + col0 + cq;
+      if (cq + 4 <= nvalid && (reinterpret_cast<uintptr_t>(c) & 15) == 0) {
+        if (p.beta == 2) {
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(c), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3])
                        : "memory");
-      } else {
-        for (int j = 0; j < nvalid; ++j) atomicAdd(c + j, v[j]);
-      }
-    } else if (vec) {
-      float4* c4 = reinterpret_cast<float4*>(c);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        if (p.beta) {
-          float4 old = c4[j];
-          o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+        } else {
+          float4 o = make_float4(v[0], v[1], v[2], v[3]);
+          if (p.beta) {
+            const float4 old = *reinterpret_cast<const float4*>(c);
+            o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+          }
+          *reinterpret_cast<float4*>(c) = o;
         }
-        c4[j] = o;
+      } else {
+#pragma unroll 1
+        for (int e = 0; e < 4; ++e) {
+          if (cq + e >= nvalid) break;
+          if (p.beta == 2) atomicAdd(c + e, v[e]);
+          else c[e] = p.beta ? c[e] + v[e] : v[e];
+        }
       }
     } else {
-      for (int j = 0; j < nvalid; ++j) c[j] = p.beta ? c[j] + v[j] : v[j];
-    }
-  } else {
-    __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(p.C) + (long long)b * p.c_batch + orow * p.ldc + col0;
-    const bool vec = (nvalid == 32) && ((reinterpret_cast<uintptr_t>(c) & 15) == 0);
-    if (vec) {
-      uint4* c4 = reinterpret_cast<uint4*>(c);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float* s = v + 8 * j;
+      __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(p.C) + (long long)b * p.c_batch + orow * p.ldc + col0 + cq;
+      if (cq + 8 <= nvalid && (reinterpret_cast<uintptr_t>(c) & 15) == 0) {
         if (p.beta) {
-          uint4 old = c4[j];
-          float2 a0 = unpack_bf16x2(old.x), a1 = unpack_bf16x2(old.y), a2 = unpack_bf16x2(old.z), a3 = unpack_bf16x2(old.w);
-          s[0] += a0.x; s[1] += a0.y; s[2] += a1.x; s[3] += a1.y; s[4] += a2.x; s[5] += a2.y; s[6] += a3.x; s[7] += a3.y;
+          const uint4 old = *reinterpret_cast<const uint4*>(c);
+          const float2 a0 = unpack_bf16x2(old.x), a1 = unpack_bf16x2(old.y), a2 = unpack_bf16x2(old.z), a3 = unpack_bf16x2(old.w);
+          v[0] += a0.x; v[1] += a0.y; v[2] += a1.x; v[3] += a1.y; v[4] += a2.x; v[5] += a2.y; v[6] += a3.x; v[7] += a3.y;
         }
         uint4 o;
-        o.x = pack_bf16x2(s[0], s[1]); o.y = pack_bf16x2(s[2], s[3]);
-        o.z = pack_bf16x2(s[4], s[5]); o.w = pack_bf16x2(s[6], s[7]);
-        c4[j] = o;
-      }
-    } else {
-      for (int j = 0; j < nvalid; ++j) {
-        float x = v[j];
-        if (p.beta) x += __bfloat162float(c[j]);
-        c[j] = __float2bfloat16_rn(x);
+        o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+        o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+        *reinterpret_cast<uint4*>(c) = o;
+      } else {
+#pragma unroll 1
+        for (int e = 0; e < 8; ++e) {
+          if (cq + e >= nvalid) break;
+          float x = v[e];
+          if (p.beta) x += __bfloat162float(c[e]);
+          c[e] = __float2bfloat16_rn(x);
+        }
       }
     }
   }
+  __syncwarp();      // the staging tile is reused by this warp's next chunk
 }
 
 // LSTM cell forward on one row (sequence) and 8 hidden units (32 interleaved gate columns 4*j + {i,f,g,o}).
@@ -322,6 +349,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* tfull_bar = empty_bar + STAGES;   // [2]
   uint64_t* tempty_bar = tfull_bar + 2;       // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* stage_base = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + 256);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -378,6 +406,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int kin = (kb - seg * p.k_inner) * BK;
         if (!A_MN) {
           tma_load_4d(sA, &tmA, &full_bar[stage], p.a_c0[b] + kb * BK, m_blk * BM, p.a_c2[b], p.a_c3[b]);
+          if (p.prefetch_a) {
+            // pull the A block this CTA needs for its NEXT tile from HBM into L2 one tile ahead (it is first-touch there)
+            const int nxt = tile + tile_step;
+            if (nxt < num_tiles) {
+              const int nks = nxt / (tiles_per_batch * p.batch);
+              const int nt2 = nxt - nks * tiles_per_batch * p.batch;
+              const int nb = nt2 / tiles_per_batch;
+              const int nm = ((nt2 - nb * tiles_per_batch) / n_blocks) * kCluster + (int)crank;
+              if (nm != m_blk || nb != b || nks != ks)
+                tma_prefetch_4d(&tmA, p.a_c0[nb] + (nks * kb_per + (kb - kb0)) * BK, nm * BM, p.a_c2[nb], p.a_c3[nb]);
+            }
+          }
         } else {
 #pragma unroll
           for (int c = 0; c < BM / 64; ++c)
@@ -460,6 +500,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const int row = m_blk * BM + q * 32 + lane;
+      float* stage_w = stage_base + (warp - 4) * kStageFloats;
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
 #pragma unroll 1
       for (int c = half; c < BN / 32; c += 2) {
@@ -472,7 +513,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (lane == 0) mbar_arrive(&tempty_bar[as]);
         }
         const int col0 = n_blk * BN + c * 32;
-        if (p.mode == EPI_LINEAR) epi_linear(p, b, row, col0, r, ks);
+        if (p.mode == EPI_LINEAR) epi_linear(p, b, m_blk * BM + q * 32, col0, r, ks, stage_w, lane);
         else if (p.mode == EPI_LSTM_FWD) epi_lstm_fwd(p, b, row, col0, r);
         else epi_lstm_bwd(p, b, row, col0, r);
       }
@@ -628,18 +669,21 @@ static int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const Ge
     if (e != cudaSuccess) return set_error("cudaFuncSetAttribute(smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
     attr_set = true;
   }
+  // the transpose tiles are only used by the linear epilogue; the LSTM epilogues keep that shared memory as L1 (their
+  // row-per-thread state accesses depend on it: +0.5 ms per step when it was carved away)
+  const int smem_bytes = Cfg::SMEM_BYTES - (p.mode == EPI_LINEAR ? 0 : Cfg::STAGING_BYTES);
   const int m_blocks = ((p.M + BM - 1) / BM + kCluster - 1) / kCluster, n_blocks = (p.N + BN - 1) / BN;
   const long long tiles = (long long)m_blocks * n_blocks * p.batch * (p.ksplit > 1 ? p.ksplit : 1);
   long long grid = std::min<long long>(tiles * kCluster, max_ctas > 0 ? max_ctas : num_sms() * kOcc);
   grid = grid / kCluster * kCluster;
   if (grid <= 0) return 0;
   if (kCluster == 1) {
-    kern<<<(int)grid, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
+    kern<<<(int)grid, kGemmThreads, smem_bytes, stream>>>(ta, tb, p);
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3(kGemmThreads);
-    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -663,6 +707,10 @@ int gemm_dispatch(const dvgr_operand& A, const dvgr_operand& B, GemmParams p, in
   if (bn != 128 && bn != 256) bn = (p.N > 128) ? 256 : 128;
   if (p.mode != EPI_LINEAR) bn = 128;
   if (p.k_inner <= 0) p.k_inner = INT_MAX;
+  static const int prefetch = getenv("DVGR_GEMM_PREFETCH") ? atoi(getenv("DVGR_GEMM_PREFETCH")) : 0;
+  p.prefetch_a = prefetch;
+  static const int dbg = getenv("DVGR_GEMM_DEBUG") ? atoi(getenv("DVGR_GEMM_DEBUG")) : 0;
+  p.debug = dbg;
   if (p.ksplit > 1) {
     if (p.mode != EPI_LINEAR || !p.out_f32 || p.beta != 2) return set_error("gemm: ksplit needs the fp32 atomic-accumulate epilogue (beta = 2)");
     const int k_blocks = (p.K + BK - 1) / BK;

@@ -26,6 +26,8 @@ struct GemmParams {
   int k_inner;   // number of 64-row k-blocks per segment (INT_MAX when unsegmented)
   int a_c2_step[kMaxBatch], b_c2_step[kMaxBatch];
 
+  int debug;        // profiling aid (DVGR_GEMM_DEBUG): 1 = skip global stores, 2 = skip the whole transposed phase
+  int prefetch_a;   // producer prefetches the next tile's A blocks into L2 (tuning knob)
   int ksplit;    // K is split over `ksplit` CTAs per output tile (requires beta == 2 on a zero-initialised / accumulating C)
 
   int mode;

@@ -65,6 +65,17 @@ __device__ __forceinline__ void dropout_scale8(const DropoutCfg& c, unsigned lon
   }
 }
 
+// Cheap per-element mask for sites where one thread needs ONE element at a scattered index (the N x N attention
+// dropout): murmur3 finaliser over (seed, stream, index) — 10 integer instructions instead of a Philox call.
+__device__ __forceinline__ float dropout_scale1_hash(const DropoutCfg& c, unsigned long long idx) {
+  if (c.p <= 0.f) return 1.f;
+  const unsigned long long seed = c.seed + (c.seed_off != nullptr ? *c.seed_off : 0ull);
+  uint32_t h = (uint32_t)seed ^ ((uint32_t)(seed >> 32) * 0x9E3779B1u) ^ (c.stream * 0x85EBCA77u) ^
+               ((uint32_t)idx * 0xC2B2AE3Du) ^ ((uint32_t)(idx >> 32) * 0x27D4EB2Fu);
+  h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+  return h >= (uint32_t)(c.p * 4294967296.0f) ? 1.f / (1.f - c.p) : 0.f;
+}
+
 // Keep-scale for a single element index (costs a full Philox call; use dropout_scale4 in streaming kernels).
 __device__ __forceinline__ float dropout_scale1(const DropoutCfg& c, unsigned long long idx) {
   if (c.p <= 0.f) return 1.f;

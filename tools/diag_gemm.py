@@ -195,6 +195,31 @@ def case_lstm():
             print(f"[perf lstm bwd S{S2} T{T}] {e0.elapsed_time(e1):.3f} ms", flush=True)
 
 
+def case_sweep():
+    """Separates fixed cost, per-tile cost and per-k-block cost of the GEMM kernel."""
+    def t(M, N, K, bn, out_f32=False, bias=True, n=20):
+        x, w = rnd(M, K), rnd(N, K, scale=0.05)
+        b = torch.randn(N, device=dev) if bias else None
+        y = torch.empty(M, N, dtype=torch.float32 if out_f32 else torch.bfloat16, device=dev)
+        for _ in range(3):
+            ops.gemm(x, 0, w, 0, M, N, K, y, bias=b, bn=bn)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            ops.gemm(x, 0, w, 0, M, N, K, y, bias=b, bn=bn)
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n * 1e3
+    for bn in (128, 256):
+        ncol = bn
+        for tiles_per_cta in (1, 2, 4, 8):
+            M = 128 * 148 * tiles_per_cta
+            row = []
+            for K in (64, 256, 768, 2048):
+                row.append(f"K{K}:{t(M, ncol, K, bn):7.1f}us")
+            print(f"[sweep bn{bn} tiles/CTA={tiles_per_cta}] " + " ".join(row), flush=True)
+    print("[sweep nobias f32out bn256 tiles/CTA=4] " + " ".join(f"K{K}:{t(128*148*4, 256, K, 256, True, False):7.1f}us" for K in (64, 768)), flush=True)
+
+
 CASES = {
     "tn_1tile": lambda: case_tn(128, 128, 64, 128),
     "tn_k4": lambda: case_tn(128, 128, 256, 128),
@@ -206,6 +231,7 @@ CASES = {
     "epi": case_epi,
     "batch": case_batch,
     "lstm": case_lstm,
+    "sweep": case_sweep,
     "perf": case_perf,
 }
 

@@ -45,7 +45,7 @@ template <int BN, int kOcc = 1> struct TileCfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (kOcc == 2) ? 3 : (BN == 256) ? 4 : 6;
+  static constexpr int STAGES = (kOcc >= 2) ? 3 : (BN == 256) ? 4 : 6;   // kOcc == 3: one CTA/SM, 3 stages (more L1 left)
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   static constexpr int STAGING_BYTES = 8 * 32 * 33 * 4;      // per-epilogue-warp transpose tiles (epi_linear)
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + STAGING_BYTES;
@@ -336,7 +336,7 @@ __device__ __forceinline__ void epi_lstm_bwd(const GemmParams& p, int dir, int s
 // TMA-multicasts it into both shared memories, which cuts the L2 -> SMEM operand traffic per MMA by a third (the
 // single-CTA kernel measured 36 % tensor-pipe activity at the ~6.3 KB/clk L2 throughput cap).
 template <bool A_MN, bool B_MN, int BN, int kOcc, int kCluster>
-__global__ void __launch_bounds__(kGemmThreads, kOcc)
+__global__ void __launch_bounds__(kGemmThreads, (kOcc == 2) ? 2 : 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const GemmParams p) {
   using Cfg = TileCfg<BN, kOcc>;
@@ -674,7 +674,7 @@ static int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const Ge
   const int smem_bytes = Cfg::SMEM_BYTES - (p.mode == EPI_LINEAR ? 0 : Cfg::STAGING_BYTES);
   const int m_blocks = ((p.M + BM - 1) / BM + kCluster - 1) / kCluster, n_blocks = (p.N + BN - 1) / BN;
   const long long tiles = (long long)m_blocks * n_blocks * p.batch * (p.ksplit > 1 ? p.ksplit : 1);
-  long long grid = std::min<long long>(tiles * kCluster, max_ctas > 0 ? max_ctas : num_sms() * kOcc);
+  long long grid = std::min<long long>(tiles * kCluster, max_ctas > 0 ? max_ctas : num_sms() * (kOcc == 2 ? 2 : 1));
   grid = grid / kCluster * kCluster;
   if (grid <= 0) return 0;
   if (kCluster == 1) {
@@ -724,7 +724,7 @@ int gemm_dispatch(const dvgr_operand& A, const dvgr_operand& B, GemmParams p, in
   int rc = make_tensor_map(&ta, A, 64, a_mn ? 64 : BM);
   if (rc) return rc;
   static const int use_cluster = getenv("DVGR_GEMM_CLUSTER") ? atoi(getenv("DVGR_GEMM_CLUSTER")) : 0;   // measured r1: multicast at cluster size 2 does not raise throughput (L2 broadcast ~ unicast below cluster size 8); kept as an opt-in
-  static const int lstm_occ = getenv("DVGR_LSTM_OCC") ? atoi(getenv("DVGR_LSTM_OCC")) : 0;   // tuning knob (bit0: fwd, bit1: bwd use 2 CTAs/SM)
+  static const int lstm_occ = getenv("DVGR_LSTM_OCC") ? atoi(getenv("DVGR_LSTM_OCC")) : 8;   // tuning knob (bit0: fwd, bit1: bwd use 2 CTAs/SM)
   const bool lstm2 = (p.mode == EPI_LSTM_FWD && !a_mn && !b_mn && (lstm_occ & 1)) ||
                      (p.mode == EPI_LSTM_BWD && !a_mn && b_mn && (lstm_occ & 2));
   const bool cluster = use_cluster && !lstm2 && ((p.M + BM - 1) / BM >= 2);
@@ -732,6 +732,8 @@ int gemm_dispatch(const dvgr_operand& A, const dvgr_operand& B, GemmParams p, in
   if (rc) return rc;
   if (p.mode == EPI_LSTM_FWD && !a_mn && !b_mn && (lstm_occ & 1)) return launch_variant<false, false, 128, 2, 1>(ta, tb, p, max_ctas, stream);
   if (p.mode == EPI_LSTM_BWD && !a_mn && b_mn && (lstm_occ & 2)) return launch_variant<false, true, 128, 2, 1>(ta, tb, p, max_ctas, stream);
+  if (p.mode == EPI_LSTM_FWD && !a_mn && !b_mn && (lstm_occ & 4)) return launch_variant<false, false, 128, 3, 1>(ta, tb, p, max_ctas, stream);
+  if (p.mode == EPI_LSTM_BWD && !a_mn && b_mn && (lstm_occ & 8)) return launch_variant<false, true, 128, 3, 1>(ta, tb, p, max_ctas, stream);
 #define DVGR_LAUNCH(AM, BMJ, BNV)                                                         \
   do {                                                                                    \
     if (cluster) return launch_variant<AM, BMJ, BNV, 1, 2>(ta, tb, p, max_ctas, stream);  \

@@ -93,6 +93,12 @@ __device__ __forceinline__ void cluster_sync_all() {
 }
 
 // ------------------------------------------------------------------------------------------------ epilogues
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
 constexpr int kStagePitch = 33;                                  // floats per staged row: conflict-free both ways
 constexpr int kStageFloats = 32 * kStagePitch;                   // one 32 x 32 fp32 chunk per epilogue warp
 
@@ -104,13 +110,94 @@ constexpr int kStageFloats = 32 * kStagePitch;                   // one 32 x 32 
 __device__ __forceinline__ void epi_linear(const GemmParams& p, int b, int row0, int col0, const uint32_t (&r)[32], int ks,
                                            float* stage, int lane) {
   if (row0 >= p.M || col0 >= p.N) return;      // warp-uniform
+  const uint32_t stage_s = smem_u32(stage);      // explicit shared-space accesses (the pointer's provenance is lost to
+                                                 // the 1024-byte alignment arithmetic, generic ST.E/LD.E otherwise)
 #pragma unroll
-  for (int j = 0; j < 32; ++j) stage[lane * kStagePitch + j] = __uint_as_float(r[j]);
+  for (int j = 0; j < 32; ++j) sts_f32(stage_s + (lane * kStagePitch + j) * 4, __uint_as_float(r[j]));
   __syncwarp();
   const float* bias = (p.bias && ks == 0) ? p.bias + (long long)b * p.bias_batch : nullptr;
   const int nvalid = min(32, p.N - col0);
-  // NOTE on code size: this body runs once per 32x32 chunk by every epilogue warp; the first version unrolled the
-  // activation switch per element (~40 KB of SASS) and ran at instruction-fetch speed. Loops stay rolled on purpose.
+  // FAST PATHS (warp-uniform test): full 32-column chunk, no row permutation, 16-byte aligned rows. The generic path
+  // below re-tests every runtime option per 16-byte store (~600 instructions per chunk and warp, measured with ncu);
+  // these loops are ~5x shorter and cover every GEMM of the train step except ragged edges and the LSTM row maps.
+  const int act = p.act;
+  if (nvalid == 32 && p.row_map == nullptr) {
+    if (!p.out_f32 && ((p.ldc & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && ((p.c_batch & 7) == 0)) {
+      __nv_bfloat16* cbase = reinterpret_cast<__nv_bfloat16*>(p.C) + (long long)b * p.c_batch + col0 + 8 * (lane & 3);
+      float bv[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) bv[e] = bias != nullptr ? __ldg(bias + col0 + 8 * (lane & 3) + e) : 0.f;
+      const uint32_t sbase = stage_s + ((lane >> 2) * kStagePitch + 8 * (lane & 3)) * 4;
+      const bool accum = p.beta != 0;
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int row = row0 + it * 8 + (lane >> 2);
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = lds_f32(sbase + (it * 8 * kStagePitch + e) * 4) + bv[e];
+        if (act == ACT_ELU) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = eluf_(v[e]);
+        } else if (act == ACT_TANH) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = tanhf_(v[e]);
+        }
+        if (row < p.M) {
+          uint4* c = reinterpret_cast<uint4*>(cbase + (long long)row * p.ldc);
+          if (accum) {
+            const uint4 old = *c;
+            const float2 a0 = unpack_bf16x2(old.x), a1 = unpack_bf16x2(old.y), a2 = unpack_bf16x2(old.z), a3 = unpack_bf16x2(old.w);
+            v[0] += a0.x; v[1] += a0.y; v[2] += a1.x; v[3] += a1.y; v[4] += a2.x; v[5] += a2.y; v[6] += a3.x; v[7] += a3.y;
+          }
+          uint4 o;
+          o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+          o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+          *c = o;
+        }
+      }
+      __syncwarp();
+      return;
+    }
+    if (p.out_f32 && ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && ((p.c_batch & 3) == 0)) {
+      float* cbase = reinterpret_cast<float*>(p.C) + (long long)b * p.c_batch + col0 + 4 * (lane & 7);
+      float bv[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) bv[e] = bias != nullptr ? __ldg(bias + col0 + 4 * (lane & 7) + e) : 0.f;
+      const uint32_t sbase = stage_s + ((lane >> 3) * kStagePitch + 4 * (lane & 7)) * 4;
+      const int beta = p.beta;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int row = row0 + it * 4 + (lane >> 3);
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] = lds_f32(sbase + (it * 4 * kStagePitch + e) * 4) + bv[e];
+        if (act == ACT_ELU) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) v[e] = eluf_(v[e]);
+        } else if (act == ACT_TANH) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) v[e] = tanhf_(v[e]);
+        }
+        if (row < p.M) {
+          float* c = cbase + (long long)row * p.ldc;
+          if (beta == 2) {
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(c), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3])
+                         : "memory");
+          } else {
+            float4 o = make_float4(v[0], v[1], v[2], v[3]);
+            if (beta == 1) {
+              const float4 old = *reinterpret_cast<const float4*>(c);
+              o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+            }
+            *reinterpret_cast<float4*>(c) = o;
+          }
+        }
+      }
+      __syncwarp();
+      return;
+    }
+  }
+  // GENERIC PATH (ragged N, unaligned rows, row permutation). Loops stay rolled on purpose (code size).
   const int per = p.out_f32 ? 4 : 8;                    // elements per lane: one 16-byte store either way
   const int lanes_per_row = 32 / per;                    // 8 (fp32: 128-byte row segment) or 4 (bf16: 64-byte segment)
   const int q = lane % lanes_per_row, cq = per * q;
@@ -118,7 +205,6 @@ __device__ __forceinline__ void epi_linear(const GemmParams& p, int b, int row0,
   float bv[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) bv[e] = (bias != nullptr && e < per && cq + e < nvalid) ? __ldg(bias + col0 + cq + e) : 0.f;
-  const int act = p.act;
 #pragma unroll 1
   for (int it = 0; it < lanes_per_row; ++it) {
     const int rr = it * rows_per_it + lane / lanes_per_row, row = row0 + rr;
@@ -126,7 +212,7 @@ __device__ __forceinline__ void epi_linear(const GemmParams& p, int b, int row0,
     const long long orow = p.row_map ? p.row_map[row] : row;
     float v[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) v[e] = (e < per) ? stage[rr * kStagePitch + cq + e] + bv[e] : 0.f;
+    for (int e = 0; e < 8; ++e) v[e] = (e < per) ? lds_f32(stage_s + (rr * kStagePitch + cq + e) * 4) + bv[e] : 0.f;
     if (act == ACT_ELU) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) v[e] = eluf_(v[e]);

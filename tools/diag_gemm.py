@@ -220,6 +220,15 @@ def case_sweep():
     print("[sweep nobias f32out bn256 tiles/CTA=4] " + " ".join(f"K{K}:{t(128*148*4, 256, K, 256, True, False):7.1f}us" for K in (64, 768)), flush=True)
 
 
+def case_epi_prof():
+    M = 128 * 148 * 8
+    x, w = rnd(M, 64), rnd(256, 64)
+    y = torch.empty(M, 256, dtype=torch.bfloat16, device=dev)
+    for _ in range(4):
+        ops.gemm(x, 0, w, 0, M, 256, 64, y)
+        torch.cuda.synchronize()
+
+
 CASES = {
     "tn_1tile": lambda: case_tn(128, 128, 64, 128),
     "tn_k4": lambda: case_tn(128, 128, 256, 128),
@@ -232,6 +241,7 @@ CASES = {
     "batch": case_batch,
     "lstm": case_lstm,
     "sweep": case_sweep,
+    "epi_prof": lambda: case_epi_prof(),
     "perf": case_perf,
 }
 

@@ -51,6 +51,11 @@ class LstmArgs(ctypes.Structure):
     ]
 
 
+class LstmSeqArgs(ctypes.Structure):
+    _fields_ = [("lstm", LstmArgs), ("x", c_void_p), ("x_ld", c_ll), ("K1", c_int), ("wih", c_void_p), ("wih_ld", c_ll),
+                ("bias", c_void_p), ("sync", c_void_p)]
+
+
 lib.dvgr_last_error.restype = ctypes.c_char_p
 lib.dvgr_abi_version.restype = c_int
 lib.dvgr_launch_count.restype = c_ll
@@ -79,6 +84,9 @@ gemm_reference = _sig("dvgr_gemm_reference",
                       [c_void_p, c_ll, c_ll, c_void_p, c_ll, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_void_p])
 lstm_step_fwd = _sig("dvgr_lstm_step_fwd", [ctypes.POINTER(LstmArgs), c_void_p])
 lstm_step_bwd = _sig("dvgr_lstm_step_bwd", [ctypes.POINTER(LstmArgs), c_void_p])
+lstm_seq_fwd = _sig("dvgr_lstm_seq_fwd", [ctypes.POINTER(LstmSeqArgs), c_void_p])
+lstm_seq_sync_words = _sig("dvgr_lstm_seq_sync_words", [c_int, c_int])
+lstm_seq_bwd = _sig("dvgr_lstm_seq_bwd", [ctypes.POINTER(LstmArgs), c_void_p, c_void_p])
 
 
 class GatGraph(ctypes.Structure):
@@ -136,7 +144,7 @@ adam_step = _sig("dvgr_adam_step", [P, P, P, P, c_ll, c_float, c_float, c_float,
 
 EXPORTED = [
     "dvgr_last_error", "dvgr_abi_version", "dvgr_launch_count", "dvgr_set_seed_offset", "dvgr_gemm", "dvgr_gemm_reference",
-    "dvgr_lstm_step_fwd", "dvgr_lstm_step_bwd", "dvgr_gat_attn_fwd", "dvgr_gat_attn_bwd", "dvgr_qattn_fwd",
+    "dvgr_lstm_step_fwd", "dvgr_lstm_step_bwd", "dvgr_lstm_seq_fwd", "dvgr_lstm_seq_sync_words", "dvgr_lstm_seq_bwd", "dvgr_gat_attn_fwd", "dvgr_gat_attn_bwd", "dvgr_qattn_fwd",
     "dvgr_qattn_bwd", "dvgr_gate_fwd", "dvgr_gate_bwd", "dvgr_view_attn_fwd", "dvgr_view_attn_bwd_blocks",
     "dvgr_view_attn_bwd", "dvgr_mfb_fwd", "dvgr_mfb_bwd", "dvgr_readout_fwd", "dvgr_readout_bwd", "dvgr_bn_fwd",
     "dvgr_bn_bwd", "dvgr_cross_entropy", "dvgr_pair_loss_workspace", "dvgr_pair_loss_multi", "dvgr_prep_features", "dvgr_cast_rows", "dvgr_dropout",

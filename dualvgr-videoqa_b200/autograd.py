@@ -1,6 +1,8 @@
 """torch.autograd.Function wrappers: each pairs a forward and a backward entry point of the C ABI so that the nn.Module
 mirror in ``model/`` trains through ``loss.backward()`` exactly like the reference. PyTorch only routes tensors here
 (allocation, views, concatenation of tiny parameter vectors); all arithmetic of the hot path is in the library."""
+import collections
+import os
 import weakref
 
 import torch
@@ -36,6 +38,18 @@ _wcache = {}
 _wepoch = [0]
 # optional CUDA-event instrumentation of the dominant kernel (bench.py sets PROFILE["wih_gemm"] = [] to collect)
 PROFILE = {}
+
+
+# whole-sequence fused LSTM forward (dvgr_lstm_seq_fwd) instead of W_ih GEMM + T step launches; DVGR_LSTM_SEQ=0 keeps the
+# two-kernel path (A/B measurements). SYNC_WORDS collects the kernels' sync buffers (last word = sticky timeout flag) of the
+# most recent forward passes so that tests / bench can assert the dependency protocol never timed out.
+LSTM_SEQ = [os.environ.get("DVGR_LSTM_SEQ", "1") != "0"]
+SYNC_WORDS = collections.deque(maxlen=16)
+
+
+def lstm_seq_timeouts():
+    """Number of dependency-poll timeouts recorded by the recent whole-sequence LSTM launches (must be 0)."""
+    return sum(int(w[-1].item()) for w in SYNC_WORDS)
 
 
 def invalidate_weight_cache():
@@ -260,11 +274,17 @@ class AppearanceEncoderFn(Function):
         if rec is not None:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
-        gates = ops.linear_fwd(xa, wih, bias=bias, bn=256).view(T, S, 8 * H)
+        if LSTM_SEQ[0]:
+            # ONE persistent launch: input projection + all T recurrent steps (pre-activations never reach HBM)
+            gates, h_hist, c_hist, h_last, _, sync = ops.lstm_seq_fwd(xa.view(T, S, Dv), wih, whh, bias)
+            SYNC_WORDS.append(sync)
+        else:
+            gates = ops.linear_fwd(xa, wih, bias=bias, bn=256).view(T, S, 8 * H)
         if rec is not None:
             ev1.record()
             rec.append((ev0, ev1))
-        h_hist, c_hist, h_last, _ = ops.lstm_fwd(gates, whh)
+        if not LSTM_SEQ[0]:
+            h_hist, c_hist, h_last, _ = ops.lstm_fwd(gates, whh)
         out = h_last
         p_o = p_out if training else 0.0
         if p_o > 0:
@@ -281,7 +301,10 @@ class AppearanceEncoderFn(Function):
         dh = _c(dout.reshape(S, 2 * H))
         if p_o > 0:
             dh = ops.dropout_raw(dh, p_o, seed, sid + 1)
-        ops.lstm_bwd(gates, whh, h_hist, c_hist, dh)            # gates now holds d(pre-activation gates)
+        if LSTM_SEQ[0]:                                          # gates now holds d(pre-activation gates)
+            SYNC_WORDS.append(ops.lstm_bwd(gates, whh, h_hist, c_hist, dh, whole_sequence=True)[1])
+        else:
+            ops.lstm_bwd(gates, whh, h_hist, c_hist, dh)
         dg = gates.view(T * S, 8 * H)
         unmap = _lstm_unmap(H, 2, dg.device)
         t_ih, t_hh = grad_target(ctx.wih_params), grad_target(ctx.whh_params)
@@ -295,9 +318,11 @@ class AppearanceEncoderFn(Function):
         # dW_hh[d] = sum_s dgates[t_d(s)]^T h_hist[d][s]   (segmented MN-major reduction, both directions in one launch)
         kin = (S + 63) // 64
         dwhh = t_hh.view(2, 4 * H, H) if t_hh is not None else torch.empty((2, 4 * H, H), dtype=F32, device=dg.device)
+        wbn, wks = ops.wgrad_split(4 * H, H, T * kin * 64, batch=2) if t_hh is not None else (0, 0)
         ops.gemm(gates, 1, h_hist, 1, 4 * H, H, T * kin * 64, dwhh, ldc=H, batch=2, c_batch=4 * H * H,
                  row_map=_lstm_unmap(H, 1, dg.device), a_c0=[0, 4 * H], a_c2=[0, T - 1], a_c2_step=[1, -1],
-                 b_c2=[0, 0], b_c2_step=[1, 1], b_c3=[0, 1], k_inner=kin, beta=2 if t_hh is not None else 0)
+                 b_c2=[0, 0], b_c2_step=[1, 1], b_c3=[0, 1], k_inner=kin, beta=2 if t_hh is not None else 0,
+                 bn=wbn, ksplit=wks)
         g_ih = (None, None) if dwih is None else (dwih[:4 * H], dwih[4 * H:])
         g_hh = (None, None) if t_hh is not None else (dwhh[0], dwhh[1])
         return (None, g_ih[0], g_hh[0], db[:4 * H], db[:4 * H], g_ih[1], g_hh[1], db[4 * H:], db[4 * H:],
@@ -330,8 +355,12 @@ class QuestionEncoderFn(Function):
         wih = bf16_rows(w_ih, out_cols=Wp, lstm_H=H, tag="lstm_ih")
         whh = bf16_rows(w_hh, lstm_H=H, tag="lstm_hh").view(4, 4 * H, H)
         bias = torch.cat([(params[4 * d + 2] + params[4 * d + 3]).view(4, H).t().reshape(-1) for d in range(4)]).detach()
-        gates = ops.linear_fwd(x.view(L * B, Wp), wih, bias=bias).view(L, B, 16 * H)
-        h_hist, c_hist, h_last, seq_out = ops.lstm_fwd(gates, whh, seq_len=qlen, want_seq=True)
+        if LSTM_SEQ[0]:
+            gates, h_hist, c_hist, h_last, seq_out, sync = ops.lstm_seq_fwd(x, wih, whh, bias, seq_len=qlen, want_seq=True)
+            SYNC_WORDS.append(sync)
+        else:
+            gates = ops.linear_fwd(x.view(L * B, Wp), wih, bias=bias).view(L, B, 16 * H)
+            h_hist, c_hist, h_last, seq_out = ops.lstm_fwd(gates, whh, seq_len=qlen, want_seq=True)
         ctx.save_for_backward(x, wih, whh, gates, h_hist, c_hist, qlen)
         ctx.cfg = (B, L, W, Wp, H)
         ctx.wih_params, ctx.whh_params = w_ih, w_hh
@@ -348,7 +377,11 @@ class QuestionEncoderFn(Function):
             dh_seq[:, :, :2 * H] = d_dq
         if d_q is not None:
             dh_last[:, 2 * H:] = d_q
-        ops.lstm_bwd(gates, whh, h_hist, c_hist, dh_last, seq_len=qlen, dh_seq=dh_seq)
+        if LSTM_SEQ[0]:
+            SYNC_WORDS.append(ops.lstm_bwd(gates, whh, h_hist, c_hist, dh_last, seq_len=qlen, dh_seq=dh_seq,
+                                           whole_sequence=True)[1])
+        else:
+            ops.lstm_bwd(gates, whh, h_hist, c_hist, dh_last, seq_len=qlen, dh_seq=dh_seq)
         dg = gates.view(L * B, 16 * H)
         x2 = x.view(L * B, Wp)
         dwords = None

@@ -117,6 +117,44 @@ int dvgr_lstm_step_fwd(const dvgr_lstm_args* a, void* stream) {
   return rc;
 }
 
+int dvgr_lstm_seq_sync_words(int S, int ndir) { return ndir * ((S + 127) / 128) + 1; }
+
+int dvgr_lstm_seq_fwd(const dvgr_lstm_seq_args* a, void* stream) {
+  if (!a) return set_error("dvgr_lstm_seq_fwd: null args");
+  dvgr_lstm_args b = a->lstm;
+  b.s = 0;
+  if (int rc = check_lstm(b)) return rc;
+  if (!a->x || !a->wih || !a->bias || !a->sync) return set_error("dvgr_lstm_seq_fwd: null buffer");
+  if (a->x_ld % 8 != 0 || a->wih_ld % 8 != 0 || a->x_ld < a->K1 || a->wih_ld < a->K1)
+    return set_error("dvgr_lstm_seq_fwd: row strides must be multiples of 8 elements and >= K1");
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  fill_lstm_params(p, b);
+  p.mode = EPI_LSTM_FWD;
+  p.M = b.S; p.N = 4 * b.H; p.K = b.H;
+  dvgr_operand X, W, A, B;
+  memset(&X, 0, sizeof(X)); memset(&W, 0, sizeof(W)); memset(&A, 0, sizeof(A)); memset(&B, 0, sizeof(B));
+  // x [T][S][x_ld] : dims {K1, S, T}
+  X.ptr = a->x; X.major = 0; X.ndim = 3;
+  X.dims[0] = a->K1; X.dims[1] = b.S; X.dims[2] = b.T;
+  X.strides[0] = 1; X.strides[1] = a->x_ld; X.strides[2] = (long long)b.S * a->x_ld;
+  // W_ih [D*4H][wih_ld] : dims {K1, D*4H}
+  W.ptr = a->wih; W.major = 0; W.ndim = 2;
+  W.dims[0] = a->K1; W.dims[1] = (long long)b.ndir * 4 * b.H;
+  W.strides[0] = 1; W.strides[1] = a->wih_ld;
+  // h_hist [D][T+1][S][H] : dims {H, S, T+1, D}
+  A.ptr = b.h_hist; A.major = 0; A.ndim = 4;
+  A.dims[0] = b.H; A.dims[1] = b.S; A.dims[2] = b.T + 1; A.dims[3] = b.ndir;
+  A.strides[0] = 1; A.strides[1] = b.H; A.strides[2] = (long long)b.S * b.H; A.strides[3] = (long long)(b.T + 1) * b.S * b.H;
+  // W_hh [D][4H][H] : dims {H, 4H, D}
+  B.ptr = b.whh; B.major = 0; B.ndim = 3;
+  B.dims[0] = b.H; B.dims[1] = 4LL * b.H; B.dims[2] = b.ndir;
+  B.strides[0] = 1; B.strides[1] = b.H; B.strides[2] = 4LL * b.H * b.H;
+  int rc = lstm_seq_fwd_launch(X, W, A, B, p, a->K1, a->bias, a->sync, reinterpret_cast<cudaStream_t>(stream));
+  if (rc == 0) count_launch();
+  return rc;
+}
+
 int dvgr_lstm_step_bwd(const dvgr_lstm_args* a, void* stream) {
   if (!a) return set_error("dvgr_lstm_step_bwd: null args");
   if (int rc = check_lstm(*a)) return rc;
@@ -151,6 +189,37 @@ int dvgr_lstm_step_bwd(const dvgr_lstm_args* a, void* stream) {
     p.b_c2[d] = d;
   }
   int rc = gemm_dispatch(A, B, p, 128, 0, st);
+  if (rc == 0) count_launch();
+  return rc;
+}
+
+int dvgr_lstm_seq_bwd(const dvgr_lstm_args* a, int* sync, void* stream) {
+  if (!a) return set_error("dvgr_lstm_seq_bwd: null args");
+  dvgr_lstm_args b = *a;
+  b.s = b.T - 1;
+  if (int rc = check_lstm(b)) return rc;
+  if (!b.dc || !sync) return set_error("dvgr_lstm_seq_bwd: dc / sync is null");
+  if (b.seq_len && !b.dh_carry) return set_error("dvgr_lstm_seq_bwd: dh_carry is required with seq_len");
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  fill_lstm_params(p, b);
+  p.mode = EPI_LSTM_BWD;
+  p.dh_ext = reinterpret_cast<const __nv_bfloat16*>(b.dh_seq);
+  p.M = b.S; p.N = b.H; p.K = 4 * b.H;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int rc = lstm_bwd_first(p, b.dh_last, b.dh_last_ld, st);      // step T-1: no recurrent product
+  if (rc) return rc;
+  count_launch();
+  if (b.T < 2) return 0;
+  dvgr_operand A, B;
+  memset(&A, 0, sizeof(A)); memset(&B, 0, sizeof(B));
+  A.ptr = b.gates; A.major = 0; A.ndim = 3;
+  A.dims[0] = (long long)b.ndir * 4 * b.H; A.dims[1] = b.S; A.dims[2] = b.T;
+  A.strides[0] = 1; A.strides[1] = A.dims[0]; A.strides[2] = A.dims[0] * b.S;
+  B.ptr = b.whh; B.major = 1; B.ndim = 3;
+  B.dims[0] = b.H; B.dims[1] = 4LL * b.H; B.dims[2] = b.ndir;
+  B.strides[0] = 1; B.strides[1] = b.H; B.strides[2] = 4LL * b.H * b.H;
+  rc = lstm_seq_bwd_launch(A, B, p, sync, st);
   if (rc == 0) count_launch();
   return rc;
 }

@@ -269,22 +269,35 @@ __device__ __forceinline__ void epi_linear(const GemmParams& p, int b, int row0,
 }
 
 // LSTM cell forward on one row (sequence) and 8 hidden units (32 interleaved gate columns 4*j + {i,f,g,o}).
-__device__ __forceinline__ void epi_lstm_fwd(const GemmParams& p, int dir, int seq, int col0, const uint32_t (&r)[32]) {
+// kFused = false: the input product x W_ih^T + b was written to `gates` by a separate GEMM (per-step launches, p.s).
+// kFused = true : the accumulator already holds x_t W_ih^T + h W_hh^T (lstm_seq_fwd_kernel); `bias` points at the 32 bias
+//                 values of this chunk and the previous cell state is read around L1 (it was written by another SM).
+template <bool kFused>
+__device__ __forceinline__ void epi_lstm_fwd(const GemmParams& p, int dir, int s, int seq, int col0, const uint32_t (&r)[32],
+                                             const float* __restrict__ bias) {
   if (seq >= p.M || col0 >= p.N) return;
   const int H = p.N >> 2;
   const int S = p.M;
-  const int t = (dir & 1) == 0 ? p.s : p.T - 1 - p.s;
+  const int t = (dir & 1) == 0 ? s : p.T - 1 - s;
   const int j0 = col0 >> 2;
   __nv_bfloat16* g = p.gates + ((long long)t * p.M + seq) * p.gates_ld + (long long)dir * p.gates_dir + col0;
-  const long long st = ((long long)dir * (p.T + 1) + p.s) * S * H + (long long)seq * H + j0;   // slot s
+  const long long st = ((long long)dir * (p.T + 1) + s) * S * H + (long long)seq * H + j0;   // slot s
   const long long st1 = st + (long long)S * H;                                                // slot s+1
   const bool live = (p.seq_len == nullptr) || (t < p.seq_len[seq]);
 
   uint4 gin[4];
+  float4 cp0, cp1;
+  if (kFused) {
 #pragma unroll
-  for (int q = 0; q < 4; ++q) gin[q] = reinterpret_cast<const uint4*>(g)[q];
-  float4 cp0 = *reinterpret_cast<const float4*>(p.c_hist + st);
-  float4 cp1 = *reinterpret_cast<const float4*>(p.c_hist + st + 4);
+    for (int q = 0; q < 4; ++q) gin[q] = make_uint4(0, 0, 0, 0);
+    cp0 = __ldcg(reinterpret_cast<const float4*>(p.c_hist + st));
+    cp1 = __ldcg(reinterpret_cast<const float4*>(p.c_hist + st + 4));
+  } else {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) gin[q] = reinterpret_cast<const uint4*>(g)[q];
+    cp0 = *reinterpret_cast<const float4*>(p.c_hist + st);
+    cp1 = *reinterpret_cast<const float4*>(p.c_hist + st + 4);
+  }
   float cprev[8] = {cp0.x, cp0.y, cp0.z, cp0.w, cp1.x, cp1.y, cp1.z, cp1.w};
   float cnew[8], hnew[8];
   uint4 gout[4];
@@ -292,8 +305,15 @@ __device__ __forceinline__ void epi_lstm_fwd(const GemmParams& p, int dir, int s
   uint32_t* go = reinterpret_cast<uint32_t*>(gout);
 #pragma unroll
   for (int u = 0; u < 8; ++u) {
-    float2 a01 = unpack_bf16x2(gw[2 * u]);
-    float2 a23 = unpack_bf16x2(gw[2 * u + 1]);
+    float2 a01, a23;
+    if (kFused) {
+      const float4 bv = __ldg(reinterpret_cast<const float4*>(bias) + u);
+      a01 = make_float2(bv.x, bv.y);
+      a23 = make_float2(bv.z, bv.w);
+    } else {
+      a01 = unpack_bf16x2(gw[2 * u]);
+      a23 = unpack_bf16x2(gw[2 * u + 1]);
+    }
     // single-MUFU tanh / sigmoid: the gates and h are stored as bf16, whose ulp (2^-8) dwarfs the 2^-11 approximation
     float ig = sigmoid_fast(__uint_as_float(r[4 * u + 0]) + a01.x);
     float fg = sigmoid_fast(__uint_as_float(r[4 * u + 1]) + a01.y);
@@ -307,7 +327,7 @@ __device__ __forceinline__ void epi_lstm_fwd(const GemmParams& p, int dir, int s
   }
   if (!live) {
     // padded step: state is carried unchanged, gates are zeroed so the backward pass sees no contribution
-    uint4 hp = *reinterpret_cast<const uint4*>(p.h_hist + st);
+    uint4 hp = kFused ? __ldcg(reinterpret_cast<const uint4*>(p.h_hist + st)) : *reinterpret_cast<const uint4*>(p.h_hist + st);
     const uint32_t* hw = reinterpret_cast<const uint32_t*>(&hp);
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -327,7 +347,7 @@ __device__ __forceinline__ void epi_lstm_fwd(const GemmParams& p, int dir, int s
   hv.x = pack_bf16x2(hnew[0], hnew[1]); hv.y = pack_bf16x2(hnew[2], hnew[3]);
   hv.z = pack_bf16x2(hnew[4], hnew[5]); hv.w = pack_bf16x2(hnew[6], hnew[7]);
   *reinterpret_cast<uint4*>(p.h_hist + st1) = hv;
-  if (p.h_last != nullptr && p.s == p.T - 1)
+  if (p.h_last != nullptr && s == p.T - 1)
     *reinterpret_cast<uint4*>(p.h_last + (long long)seq * p.h_last_ld + (long long)dir * H + j0) = hv;
   if (p.seq_out != nullptr) {
     uint4 ov = live ? hv : make_uint4(0, 0, 0, 0);
@@ -335,19 +355,36 @@ __device__ __forceinline__ void epi_lstm_fwd(const GemmParams& p, int dir, int s
   }
 }
 
-// LSTM cell backward for 8 hidden units of one sequence at processed step p.s.
+// LSTM cell backward for 8 hidden units of one sequence at processed step s.
 //   dh[8]      : gradient w.r.t. h after step s (everything already summed)
 //   reads  gates (activated i,f,g,o), c_hist[s], c_hist[s+1], dc (running)
 //   writes dgates (pre-activation) in place, dc <- dc_total * f
-__device__ __forceinline__ void lstm_cell_bwd8(const GemmParams& p, int dir, int seq, int j0, float (&dh)[8]) {
+// kCoherent: the running buffers (dc, dh_carry) were written by ANOTHER CTA of the same launch (lstm_seq_bwd_kernel), so
+//            they are read around L1 (an earlier step may have left a stale line of the same address there).
+template <bool kCoherent>
+__device__ __forceinline__ float4 ld_run4(const float* ptr) {
+  return kCoherent ? __ldcg(reinterpret_cast<const float4*>(ptr)) : *reinterpret_cast<const float4*>(ptr);
+}
+template <bool kCoherent>
+__device__ __forceinline__ void lstm_cell_bwd8(const GemmParams& p, int dir, int s, int seq, int j0, float (&dh)[8]) {
   const int H = p.N;   // bwd GEMM has N = H
   const int S = p.M;
-  const int t = (dir & 1) == 0 ? p.s : p.T - 1 - p.s;
+  const int t = (dir & 1) == 0 ? s : p.T - 1 - s;
   __nv_bfloat16* g = p.gates + ((long long)t * p.M + seq) * p.gates_ld + (long long)dir * p.gates_dir + 4 * j0;
-  const long long st = ((long long)dir * (p.T + 1) + p.s) * S * H + (long long)seq * H + j0;
+  const long long st = ((long long)dir * (p.T + 1) + s) * S * H + (long long)seq * H + j0;
   const long long st1 = st + (long long)S * H;
   float* dcp = p.dc + ((long long)dir * S + seq) * H + j0;
   const bool live = (p.seq_len == nullptr) || (t < p.seq_len[seq]);
+  // issue every load of this group up front (one latency round)
+  uint4 gin[4];
+  float4 a0, a1, b0, b1, d0, d1;
+  if (live) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) gin[q] = reinterpret_cast<const uint4*>(g)[q];
+    a0 = *reinterpret_cast<const float4*>(p.c_hist + st); a1 = *reinterpret_cast<const float4*>(p.c_hist + st + 4);
+    b0 = *reinterpret_cast<const float4*>(p.c_hist + st1); b1 = *reinterpret_cast<const float4*>(p.c_hist + st1 + 4);
+    d0 = ld_run4<kCoherent>(dcp); d1 = ld_run4<kCoherent>(dcp + 4);
+  }
   if (live && p.dh_ext != nullptr) {
     // gradient arriving on the per-step hidden output [S][T][ld] (column dir*H); padded steps emit constant zeros
     uint4 ev = *reinterpret_cast<const uint4*>(p.dh_ext + ((long long)seq * p.T + t) * p.seq_out_ld + (long long)dir * H + j0);
@@ -361,7 +398,7 @@ __device__ __forceinline__ void lstm_cell_bwd8(const GemmParams& p, int dir, int
   if (p.dh_carry != nullptr) {
     // padded steps carry the state forward, so their incoming dh must reach the last live step unchanged
     float* cp = p.dh_carry + ((long long)dir * S + seq) * H + j0;
-    float4 c0 = *reinterpret_cast<float4*>(cp), c1 = *reinterpret_cast<float4*>(cp + 4);
+    float4 c0 = ld_run4<kCoherent>(cp), c1 = ld_run4<kCoherent>(cp + 4);
     dh[0] += c0.x; dh[1] += c0.y; dh[2] += c0.z; dh[3] += c0.w;
     dh[4] += c1.x; dh[5] += c1.y; dh[6] += c1.z; dh[7] += c1.w;
     if (live) {
@@ -373,12 +410,6 @@ __device__ __forceinline__ void lstm_cell_bwd8(const GemmParams& p, int dir, int
     }
   }
   if (!live) return;   // dgates stay zero (written by the forward pass); dc passes through untouched
-  uint4 gin[4];
-#pragma unroll
-  for (int q = 0; q < 4; ++q) gin[q] = reinterpret_cast<const uint4*>(g)[q];
-  float4 a0 = *reinterpret_cast<const float4*>(p.c_hist + st), a1 = *reinterpret_cast<const float4*>(p.c_hist + st + 4);
-  float4 b0 = *reinterpret_cast<const float4*>(p.c_hist + st1), b1 = *reinterpret_cast<const float4*>(p.c_hist + st1 + 4);
-  float4 d0 = *reinterpret_cast<const float4*>(dcp), d1 = *reinterpret_cast<const float4*>(dcp + 4);
   float cprev[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
   float cc[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
   float dc[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
@@ -413,7 +444,7 @@ __device__ __forceinline__ void epi_lstm_bwd(const GemmParams& p, int dir, int s
     float dh[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) dh[u] = __uint_as_float(r[8 * q + u]);
-    lstm_cell_bwd8(p, dir, seq, col0 + 8 * q, dh);
+    lstm_cell_bwd8<false>(p, dir, p.s, seq, col0 + 8 * q, dh);
   }
 }
 
@@ -600,7 +631,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         const int col0 = n_blk * BN + c * 32;
         if (p.mode == EPI_LINEAR) epi_linear(p, b, m_blk * BM + q * 32, col0, r, ks, stage_w, lane);
-        else if (p.mode == EPI_LSTM_FWD) epi_lstm_fwd(p, b, row, col0, r);
+        else if (p.mode == EPI_LSTM_FWD) epi_lstm_fwd<false>(p, b, p.s, row, col0, r, nullptr);
         else epi_lstm_bwd(p, b, row, col0, r);
       }
       if (++as == 2) { as = 0; aphase ^= 1u; }
@@ -613,6 +644,363 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ whole-sequence LSTM
+// One persistent launch runs ALL T steps of every direction with the input projection fused in:
+//   tile (s, d, m, n):  acc[128 x BN] = x_t[m] W_ih[d][n]^T  (K1, no dependency)  +  h_{s}[d][m] W_hh[d][n]^T  (H)
+//   epilogue          :  + bias, LSTM cell, writes activated gates (kept for backward), c_{s+1}, h_{s+1}
+// so the [T][S][D*4H] pre-activation tensor never exists in HBM (the two-kernel path wrote and re-read 503 MB of it at
+// the SVQA shape) and the cell epilogue hides under a K = K1 + H main loop instead of a K = H one.
+// Tiles are ordered step-major and dealt round-robin to the resident CTAs; the only cross-CTA dependency is
+// "h_{s} of my 128 sequences is complete", tracked by one counter per (direction, m-block): every epilogue warp adds 1
+// after its stores (release), the TMA producer of a dependent tile polls it (acquire) before loading h. A dependency is
+// always ~one step (hundreds of tiles) behind the tile that needs it, so the poll is practically never taken; since every
+// CTA walks its tiles in increasing order and all CTAs are co-resident (the launcher caps the grid), it cannot deadlock.
+struct LstmSeqParams {
+  int kb1, kb2;              // 64-wide k-blocks of the input part (ceil(K1 / 64)) and of the recurrent part (H / 64)
+  int m_blocks, n_blocks;    // ceil(S / 128), 4H / BN
+  const float* bias;         // [D][4H] fp32, gate-interleaved (b_ih + b_hh)
+  int* flags;                // [D][m_blocks] zero at launch
+  int* error;                // sticky: set when a dependency poll gave up (never in a healthy run)
+};
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* ptr) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+
+// bounded acquire-poll: gives up (and says so in *error) instead of hanging the GPU if the protocol were ever violated
+__device__ __forceinline__ void wait_flag(const int* flag, int need, int* error) {
+  for (int it = 0; ld_acquire_gpu(flag) < need; ++it) {
+    if ((it & 255) == 255) {
+      if (*reinterpret_cast<volatile int*>(error) != 0) break;
+      if (it > (1 << 21)) { atomicExch(error, 1); break; }
+    }
+  }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWih,
+                    const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmWhh,
+                    const GemmParams p, const LstmSeqParams q) {
+  using Cfg = TileCfg<BN, 1>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;   // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;       // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int H = p.N >> 2;
+  const int ndir = p.batch;
+  const int tiles_per_dir = q.m_blocks * q.n_blocks;
+  const int tiles_per_step = tiles_per_dir * ndir;
+  const int num_tiles = tiles_per_step * p.T;          // tile = ((s * D + d) * m_blocks + m) * n_blocks + n
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmWih); tma_prefetch_desc(&tmH); tma_prefetch_desc(&tmWhh);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], kEpiWarps); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ===================================================== TMA producer
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int s = tile / tiles_per_step;
+      const int r0 = tile - s * tiles_per_step;
+      const int d = r0 / tiles_per_dir;
+      const int r1 = r0 - d * tiles_per_dir;
+      const int m_blk = r1 / q.n_blocks, n_blk = r1 - m_blk * q.n_blocks;
+      const int t = (d & 1) == 0 ? s : p.T - 1 - s;
+      for (int kb = 0; kb < q.kb1; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
+        mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+        tma_load_4d(sA, &tmX, &full_bar[stage], kb * BK, m_blk * BM, t, 0);
+        tma_load_4d(sA + Cfg::A_BYTES, &tmWih, &full_bar[stage], kb * BK, d * p.N + n_blk * BN, 0, 0);
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+      if (s > 0) {      // h_0 = 0: step 0 has no recurrent part
+        wait_flag(q.flags + d * q.m_blocks + m_blk, kEpiWarps * q.n_blocks * s, q.error);
+        fence_proxy_async_global();     // the h rows were written through the generic proxy, TMA reads through the async one
+        for (int kb = 0; kb < q.kb2; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          tma_load_4d(sA, &tmH, &full_bar[stage], kb * BK, m_blk * BM, s, d);
+          tma_load_4d(sA + Cfg::A_BYTES, &tmWhh, &full_bar[stage], kb * BK, n_blk * BN, d, 0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================================================== MMA issuer (single thread)
+    constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, false, false);
+    int stage = 0;
+    uint32_t phase = 0;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int s = tile / tiles_per_step;
+      const int nkb = q.kb1 + (s > 0 ? q.kb2 : 0);
+      mbar_wait(&tempty_bar[as], aphase ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sA = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+        const uint32_t sB = sA + Cfg::A_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k)
+          umma_bf16(d_tmem, umma_smem_desc(sA + k * 32, 16, 1024), umma_smem_desc(sB + k * 32, 16, 1024), idesc,
+                    (kb > 0 || k != 0) ? 1u : 0u);
+        umma_commit(&empty_bar[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+      umma_commit(&tfull_bar[as]);
+      if (++as == 2) { as = 0; aphase ^= 1u; }
+    }
+  } else if (warp >= 4) {
+    // ===================================================== epilogue: LSTM cell on the finished accumulator
+    const int qd = warp & 3;
+    const int half = (warp - 4) >> 2;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int s = tile / tiles_per_step;
+      const int r0 = tile - s * tiles_per_step;
+      const int d = r0 / tiles_per_dir;
+      const int r1 = r0 - d * tiles_per_dir;
+      const int m_blk = r1 / q.n_blocks, n_blk = r1 - m_blk * q.n_blocks;
+      int* flag = q.flags + d * q.m_blocks + m_blk;
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      if (s > 0) {      // order this warp's reads of c_{s} / h_{s} (written by other CTAs) after their release
+        if (lane == 0) (void)ld_acquire_gpu(flag);
+        __syncwarp();
+      }
+      const int row = m_blk * BM + qd * 32 + lane;
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + static_cast<uint32_t>(as * BN);
+#pragma unroll 1
+      for (int c = half; c < BN / 32; c += 2) {
+        uint32_t r[32];
+        tmem_ld_32x32(t_addr + c * 32, r);
+        tmem_ld_wait();
+        if (c + 2 >= BN / 32) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        }
+        const int col0 = n_blk * BN + c * 32;
+        epi_lstm_fwd<true>(p, d, s, row, col0, r, q.bias + (long long)d * p.N + col0);
+      }
+      // publish: h_{s+1} / c_{s+1} of this warp's rows and columns are in memory
+      fence_proxy_async_global();
+      __syncwarp();
+      if (lane == 0) {
+        __threadfence();
+        atomicAdd(flag, 1);
+      }
+      if (++as == 2) { as = 0; aphase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+  (void)H;
+}
+
+// ------------------------------------------------------------------------------------------------ whole-sequence LSTM backward
+// Steps s = T-2 ... 0 of every direction in ONE persistent launch (step T-1 has no recurrent product: lstm_bwd_first_kernel):
+//   tile (k, d, m, n), s = T-1-k:  dh_s[128 x 128] = dgates_{s+1}[d][m] (128 x 4H)  W_hh[d][:, n]  on tensor cores,
+//   epilogue: + external dh, LSTM cell backward -> dgates_s written in place of the activated gates, running dc.
+// Same dependency protocol as lstm_seq_fwd_kernel (a tile needs ALL gate columns of its 128 sequences from the step
+// processed before), same step-major round-robin tile order. The per-step launches spent ~2/3 of their time in the
+// memory-latency-bound cell epilogue with 8 warps per SM and lost another ~20 % to wave quantisation (240 tiles on 148
+// SMs); here 16 epilogue warps (one per TMEM lane quarter x 32-column chunk) keep twice the loads in flight and the tile
+// stream never drains between steps.
+constexpr int kBwdEpiWarps = 16;
+constexpr int kBwdThreads = 128 + 32 * kBwdEpiWarps;
+constexpr int kBwdStages = 4;
+constexpr int kBwdBN = 128;
+constexpr int kBwdStageBytes = BM * BK * 2 + kBwdBN * BK * 2;
+constexpr int kBwdSmemBytes = kBwdStages * kBwdStageBytes + 1024 + 256;
+
+__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
+
+__global__ void __launch_bounds__(kBwdThreads, 1)
+lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmWhh, const GemmParams p,
+                    const LstmSeqParams q) {
+  constexpr int BN = kBwdBN;
+  constexpr int STAGES = kBwdStages;
+  constexpr int A_BYTES = BM * BK * 2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * kBwdStageBytes);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;   // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;       // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int H = p.N;                                   // backward product: N = H, K = 4H
+  const int ndir = p.batch;
+  const int tiles_per_dir = q.m_blocks * q.n_blocks;
+  const int tiles_per_step = tiles_per_dir * ndir;
+  const int num_tiles = tiles_per_step * (p.T - 1);    // tile = (((k-1) * D + d) * m_blocks + m) * n_blocks + n, k = 1..T-1
+
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmG); tma_prefetch_desc(&tmWhh); }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], kBwdEpiWarps); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<2 * BN>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ===================================================== TMA producer
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int k1 = tile / tiles_per_step;              // k - 1
+      const int r0 = tile - k1 * tiles_per_step;
+      const int d = r0 / tiles_per_dir;
+      const int r1 = r0 - d * tiles_per_dir;
+      const int m_blk = r1 / q.n_blocks, n_blk = r1 - m_blk * q.n_blocks;
+      const int s1 = p.T - 1 - k1;                       // the step processed before this one (its dgates are the A operand)
+      const int t1 = (d & 1) == 0 ? s1 : p.T - 1 - s1;
+      if (k1 > 0) {
+        wait_flag(q.flags + d * q.m_blocks + m_blk, kBwdEpiWarps * q.n_blocks * k1, q.error);
+        fence_proxy_async_global();
+      }
+      for (int kb = 0; kb < q.kb1; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        uint8_t* sA = smem + stage * kBwdStageBytes;
+        uint8_t* sB = sA + A_BYTES;
+        mbar_arrive_expect_tx(&full_bar[stage], kBwdStageBytes);
+        tma_load_4d(sA, &tmG, &full_bar[stage], d * 4 * H + kb * BK, m_blk * BM, t1, 0);
+#pragma unroll
+        for (int c = 0; c < BN / 64; ++c)
+          tma_load_4d(sB + c * (64 * BK * 2), &tmWhh, &full_bar[stage], n_blk * BN + c * 64, kb * BK, d, 0);
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================================================== MMA issuer (single thread)
+    constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, false, true);
+    int stage = 0;
+    uint32_t phase = 0;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty_bar[as], aphase ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
+      for (int kb = 0; kb < q.kb1; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sA = smem_u32(smem + stage * kBwdStageBytes);
+        const uint32_t sB = sA + A_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k)
+          umma_bf16(d_tmem, umma_smem_desc(sA + k * 32, 16, 1024), umma_smem_desc(sB + k * 2048, 64 * BK * 2, 1024), idesc,
+                    (kb > 0 || k != 0) ? 1u : 0u);
+        umma_commit(&empty_bar[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+      umma_commit(&tfull_bar[as]);
+      if (++as == 2) { as = 0; aphase ^= 1u; }
+    }
+  } else if (warp >= 4) {
+    // ===================================================== epilogue: warp e = (TMEM lane quarter, 32-column chunk)
+    const int e = warp - 4;
+    const int qd = warp & 3;                 // hardware: a warp may only touch TMEM lanes [32 * (warp % 4), +32)
+    const int chunk = e >> 2;                // 0..3 -> hidden units [chunk * 32, +32) of the tile
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int k1 = tile / tiles_per_step;
+      const int r0 = tile - k1 * tiles_per_step;
+      const int d = r0 / tiles_per_dir;
+      const int r1 = r0 - d * tiles_per_dir;
+      const int m_blk = r1 / q.n_blocks, n_blk = r1 - m_blk * q.n_blocks;
+      const int s = p.T - 2 - k1;
+      int* flag = q.flags + d * q.m_blocks + m_blk;
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      if (k1 > 0) {     // order this warp's reads of dc / dh_carry (written by other CTAs) after their release
+        if (lane == 0) (void)ld_acquire_gpu(flag);
+        __syncwarp();
+      }
+      const int seq = m_blk * BM + qd * 32 + lane;
+      const int j_base = n_blk * BN + chunk * 32;
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + static_cast<uint32_t>(as * BN + chunk * 32);
+      uint32_t r[4][8];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) tmem_ld_32x8(t_addr + g * 8, r[g]);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (seq < p.M) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if (j_base + g * 8 < H) {
+            float dh[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) dh[u] = __uint_as_float(r[g][u]);
+            lstm_cell_bwd8<true>(p, d, s, seq, j_base + g * 8, dh);
+          }
+        }
+      }
+      fence_proxy_async_global();
+      __syncwarp();
+      if (lane == 0) {
+        __threadfence();
+        atomicAdd(flag, 1);
+      }
+      if (++as == 2) { as = 0; aphase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<2 * BN>(tmem_base);
   }
 }
 
@@ -639,7 +1027,7 @@ __global__ void lstm_bwd_first_kernel(const GemmParams p, const __nv_bfloat16* _
 #pragma unroll
       for (int u = 0; u < 8; ++u) dh[u] = 0.f;
     }
-    lstm_cell_bwd8(p, dir, seq, jg * 8, dh);
+    lstm_cell_bwd8<false>(p, dir, p.s, seq, jg * 8, dh);
   }
 }
 
@@ -819,7 +1207,9 @@ int gemm_dispatch(const dvgr_operand& A, const dvgr_operand& B, GemmParams p, in
   if (p.mode == EPI_LSTM_FWD && !a_mn && !b_mn && (lstm_occ & 1)) return launch_variant<false, false, 128, 2, 1>(ta, tb, p, max_ctas, stream);
   if (p.mode == EPI_LSTM_BWD && !a_mn && b_mn && (lstm_occ & 2)) return launch_variant<false, true, 128, 2, 1>(ta, tb, p, max_ctas, stream);
   if (p.mode == EPI_LSTM_FWD && !a_mn && !b_mn && (lstm_occ & 4)) return launch_variant<false, false, 128, 3, 1>(ta, tb, p, max_ctas, stream);
-  if (p.mode == EPI_LSTM_BWD && !a_mn && b_mn && (lstm_occ & 8)) return launch_variant<false, true, 128, 3, 1>(ta, tb, p, max_ctas, stream);
+  // (the 3-stage variant trades pipeline depth for L1: right for the appearance encoder's 5120 sequences, wrong for the
+  //  question encoder's 256, whose 24 CTAs are bound by the latency of their 24 serial k-blocks -> deep pipeline there)
+  if (p.mode == EPI_LSTM_BWD && !a_mn && b_mn && (lstm_occ & 8) && p.M >= 2048) return launch_variant<false, true, 128, 3, 1>(ta, tb, p, max_ctas, stream);
 #define DVGR_LAUNCH(AM, BMJ, BNV)                                                         \
   do {                                                                                    \
     if (cluster) return launch_variant<AM, BMJ, BNV, 1, 2>(ta, tb, p, max_ctas, stream);  \
@@ -830,6 +1220,83 @@ int gemm_dispatch(const dvgr_operand& A, const dvgr_operand& B, GemmParams p, in
   if (a_mn && b_mn) { if (bn == 256) DVGR_LAUNCH(true, true, 256); else DVGR_LAUNCH(true, true, 128); }
 #undef DVGR_LAUNCH
   return set_error("gemm: operand layout combination (A MN-major, B K-major) is not instantiated");
+}
+
+// Whole-sequence fused LSTM forward (lstm_seq_fwd_kernel). p carries the EPI_LSTM fields with M = S, N = 4H, batch = D.
+int lstm_seq_fwd_launch(const dvgr_operand& X, const dvgr_operand& Wih, const dvgr_operand& Hh, const dvgr_operand& Whh,
+                        GemmParams p, int K1, const float* bias, int* sync, cudaStream_t stream) {
+  constexpr int BN = 256;
+  using Cfg = TileCfg<BN, 1>;
+  const int H = p.N / 4;
+  if (p.N % BN != 0) return set_error("lstm_seq_fwd: 4H = %d must be a multiple of %d", p.N, BN);
+  if (K1 <= 0 || K1 % 8 != 0) return set_error("lstm_seq_fwd: K1 = %d must be a positive multiple of 8", K1);
+  CUtensorMap tx, twih, th, twhh;
+  int rc = make_tensor_map(&tx, X, 64, BM);
+  if (!rc) rc = make_tensor_map(&twih, Wih, 64, BN);
+  if (!rc) rc = make_tensor_map(&th, Hh, 64, BM);
+  if (!rc) rc = make_tensor_map(&twhh, Whh, 64, BN);
+  if (rc) return rc;
+  LstmSeqParams q;
+  q.kb1 = (K1 + BK - 1) / BK;
+  q.kb2 = H / BK;
+  q.m_blocks = (p.M + BM - 1) / BM;
+  q.n_blocks = p.N / BN;
+  q.bias = bias;
+  q.flags = sync;
+  q.error = sync + (long long)p.batch * q.m_blocks;
+  auto kern = lstm_seq_fwd_kernel<BN>;
+  const int smem_bytes = Cfg::SMEM_BYTES - Cfg::STAGING_BYTES;
+  static int max_resident = 0;
+  if (max_resident == 0) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e != cudaSuccess) return set_error("cudaFuncSetAttribute(lstm_seq_fwd, smem=%d): %s", smem_bytes, cudaGetErrorString(e));
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kGemmThreads, smem_bytes);
+    if (e != cudaSuccess || per_sm < 1) return set_error("lstm_seq_fwd: kernel cannot be resident (%s)", cudaGetErrorString(e));
+    max_resident = per_sm * num_sms();     // the dependency protocol needs every CTA of the grid co-resident
+  }
+  const long long tiles = (long long)q.m_blocks * q.n_blocks * p.batch * p.T;
+  const int grid = (int)std::min<long long>(tiles, std::min(max_resident, num_sms()));
+  if (grid <= 0) return 0;
+  kern<<<grid, kGemmThreads, smem_bytes, stream>>>(tx, twih, th, twhh, p, q);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error("lstm_seq_fwd launch failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+// Whole-sequence LSTM backward, steps T-2 ... 0 (lstm_seq_bwd_kernel). p: EPI_LSTM fields with M = S, N = H, batch = D.
+int lstm_seq_bwd_launch(const dvgr_operand& G, const dvgr_operand& Whh, GemmParams p, int* sync, cudaStream_t stream) {
+  const int H = p.N;
+  if (H % 64 != 0) return set_error("lstm_seq_bwd: H = %d must be a multiple of 64", H);
+  if (p.T < 2) return 0;
+  CUtensorMap tg, tw;
+  int rc = make_tensor_map(&tg, G, 64, BM);
+  if (!rc) rc = make_tensor_map(&tw, Whh, 64, 64);
+  if (rc) return rc;
+  LstmSeqParams q;
+  q.kb1 = 4 * H / BK;
+  q.kb2 = 0;
+  q.m_blocks = (p.M + BM - 1) / BM;
+  q.n_blocks = (H + kBwdBN - 1) / kBwdBN;
+  q.bias = nullptr;
+  q.flags = sync;
+  q.error = sync + (long long)p.batch * q.m_blocks;
+  static int max_resident = 0;
+  if (max_resident == 0) {
+    cudaError_t e = cudaFuncSetAttribute(lstm_seq_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmemBytes);
+    if (e != cudaSuccess) return set_error("cudaFuncSetAttribute(lstm_seq_bwd, smem=%d): %s", kBwdSmemBytes, cudaGetErrorString(e));
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lstm_seq_bwd_kernel, kBwdThreads, kBwdSmemBytes);
+    if (e != cudaSuccess || per_sm < 1) return set_error("lstm_seq_bwd: kernel cannot be resident (%s)", cudaGetErrorString(e));
+    max_resident = per_sm * num_sms();
+  }
+  const long long tiles = (long long)q.m_blocks * q.n_blocks * p.batch * (p.T - 1);
+  const int grid = (int)std::min<long long>(tiles, std::min(max_resident, num_sms()));
+  if (grid <= 0) return 0;
+  lstm_seq_bwd_kernel<<<grid, kBwdThreads, kBwdSmemBytes, stream>>>(tg, tw, p, q);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error("lstm_seq_bwd launch failed: %s", cudaGetErrorString(e));
+  return 0;
 }
 
 int lstm_bwd_first(const GemmParams& p, const void* dh_last, long long dh_ld, cudaStream_t stream) {

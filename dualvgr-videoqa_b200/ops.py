@@ -9,6 +9,7 @@ import torch
 from . import _lib
 
 ACT_NONE, ACT_ELU, ACT_TANH = 0, 1, 2
+BF16, F32 = torch.bfloat16, torch.float32
 _ACT = {None: 0, "none": 0, "elu": 1, "tanh": 2}
 
 
@@ -101,11 +102,19 @@ NUM_SMS = 148
 
 
 def wgrad_split(rows, cols, red, batch=1):
-    """(bn, ksplit) for a weight-gradient GEMM [rows, cols] reduced over `red`: enough CTAs to fill the 148 SMs."""
+    """(bn, ksplit) for a weight-gradient GEMM [rows, cols] reduced over `red`. The persistent kernel deals tiles
+    round-robin to the 148 CTAs, so its time is ~ ceil(tiles * ksplit / 148) * (k_blocks / ksplit): pick the split that
+    minimises it (smallest on ties: every split adds one atomic pass over the output)."""
     bn = 256 if (rows // 128) * ((cols + 255) // 256) * batch >= NUM_SMS else 128
     tiles = ((rows + 127) // 128) * ((cols + bn - 1) // bn) * batch
     kb = (red + 63) // 64
-    return bn, max(1, min(kb // 4 if kb >= 8 else 1, (2 * NUM_SMS + tiles - 1) // tiles))
+    best, best_cost = 1, None
+    for ks in range(1, max(1, min(kb // 4, 32)) + 1):
+        per = (kb + ks - 1) // ks
+        cost = ((tiles * ks + NUM_SMS - 1) // NUM_SMS) * (per + 3)       # +3: pipeline fill / epilogue per tile
+        if best_cost is None or cost < best_cost * 0.97:
+            best, best_cost = ks, cost
+    return bn, best
 
 
 def linear_wgrad(dy, x, out=None, beta=False, row_map=None, bn=0, rows=None, cols=None, atomic=False):
@@ -167,9 +176,48 @@ def lstm_fwd(gates, whh, seq_len=None, want_seq=False):
     return h_hist, c_hist, h_last, seq_out
 
 
-def lstm_bwd(gates, whh, h_hist, c_hist, dh_last, seq_len=None, dh_seq=None):
+def lstm_seq_fwd(x, wih, whh, bias, K1=None, seq_len=None, want_seq=False):
+    """Whole-sequence fused forward (ONE persistent launch): x [T,S,ld] bf16 time-major, wih [D*4H, ld'] bf16 and
+    whh [D,4H,H] bf16 gate-interleaved, bias [D*4H] f32 (b_ih + b_hh, interleaved).
+    Returns (gates [T,S,D*4H] bf16 ACTIVATED, h_hist, c_hist, h_last, seq_out | None, sync) like gemm + lstm_fwd;
+    sync[-1] is the kernel's sticky dependency-timeout flag (0 in a healthy run)."""
+    _check_cuda(x, wih, whh, bias)
+    T, S, ldx = x.shape
+    D, H4, H = whh.shape
+    K1 = K1 or ldx
+    assert x.dtype == BF16 and wih.dtype == BF16 and whh.dtype == BF16 and bias.dtype == F32
+    assert x.is_contiguous() and wih.stride(1) == 1 and whh.is_contiguous() and wih.shape[0] == D * H4 and H4 == 4 * H
+    dev = x.device
+    gates = torch.empty((T, S, D * H4), dtype=BF16, device=dev)
+    h_hist = torch.empty((D, T + 1, S, H), dtype=BF16, device=dev)
+    c_hist = torch.empty((D, T + 1, S, H), dtype=F32, device=dev)
+    h_hist[:, 0].zero_()
+    c_hist[:, 0].zero_()
+    h_last = torch.empty((S, D * H), dtype=BF16, device=dev)
+    seq_out = torch.empty((S, T, D * H), dtype=BF16, device=dev) if want_seq else None
+    sync = torch.zeros((int(_lib.lib.dvgr_lstm_seq_sync_words(S, D)),), dtype=torch.int32, device=dev)
+    a = _lib.LstmSeqArgs()
+    l = a.lstm
+    l.S, l.H, l.T, l.ndir, l.s = S, H, T, D, 0
+    l.gates, l.whh, l.h_hist, l.c_hist = gates.data_ptr(), whh.data_ptr(), h_hist.data_ptr(), c_hist.data_ptr()
+    l.h_last, l.h_last_ld = h_last.data_ptr(), D * H
+    if seq_len is not None:
+        assert seq_len.dtype == torch.int32
+        l.seq_len = seq_len.data_ptr()
+    if seq_out is not None:
+        l.seq_out, l.seq_out_ld = seq_out.data_ptr(), D * H
+    a.x, a.x_ld, a.K1 = x.data_ptr(), ldx, K1
+    a.wih, a.wih_ld = wih.data_ptr(), wih.stride(0)
+    a.bias, a.sync = bias.data_ptr(), sync.data_ptr()
+    _lib.check(_lib.lstm_seq_fwd(ctypes.byref(a), _stream()), "dvgr_lstm_seq_fwd")
+    return gates, h_hist, c_hist, h_last, seq_out, sync
+
+
+def lstm_bwd(gates, whh, h_hist, c_hist, dh_last, seq_len=None, dh_seq=None, whole_sequence=False):
     """Backward through the T steps; `gates` (activated gates from lstm_fwd) is overwritten in place with the
-    pre-activation gate gradients [T,S,D*4H], which feed the W_ih / W_hh / bias wgrads."""
+    pre-activation gate gradients [T,S,D*4H], which feed the W_ih / W_hh / bias wgrads.
+    whole_sequence: one persistent launch for steps T-2..0 (dvgr_lstm_seq_bwd) instead of T step launches; returns
+    (gates, sync) with sync[-1] the sticky dependency-timeout flag."""
     _check_cuda(gates, whh, dh_last)
     T, S, G = gates.shape
     D, H4, H = whh.shape
@@ -186,6 +234,10 @@ def lstm_bwd(gates, whh, h_hist, c_hist, dh_last, seq_len=None, dh_seq=None):
     if dh_seq is not None:
         a.dh_seq, a.seq_out_ld = dh_seq.data_ptr(), D * H
     st = _stream()
+    if whole_sequence:
+        sync = torch.zeros((int(_lib.lib.dvgr_lstm_seq_sync_words(S, D)),), dtype=torch.int32, device=gates.device)
+        _lib.check(_lib.lstm_seq_bwd(ctypes.byref(a), _ptr(sync), st), "dvgr_lstm_seq_bwd")
+        return gates, sync
     for s in range(T - 1, -1, -1):
         a.s = s
         _lib.check(_lib.lstm_step_bwd(ctypes.byref(a), st), "dvgr_lstm_step_bwd")
@@ -195,9 +247,6 @@ def lstm_bwd(gates, whh, h_hist, c_hist, dh_last, seq_len=None, dh_seq=None):
 # ======================================================================================================================
 # raw wrappers of the fused kernels (used directly by the per-kernel parity tests, and by the autograd layer below)
 # ======================================================================================================================
-BF16, F32 = torch.bfloat16, torch.float32
-
-
 def _empty(shape, dtype, like):
     return torch.empty(shape, dtype=dtype, device=like.device)
 

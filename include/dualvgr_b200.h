@@ -113,6 +113,36 @@ int dvgr_lstm_step_fwd(const dvgr_lstm_args* args, void* stream);
 /* Backward of step s; must be called for s = T-1, T-2, ..., 0. */
 int dvgr_lstm_step_bwd(const dvgr_lstm_args* args, void* stream);
 
+/* Whole-sequence forward of the same recurrence in ONE persistent launch, with the input projection fused in
+ * (model/Preprocessing.py:227 `self.encoder(...)` = nn.LSTM forward; :97-101,112-123 for the question BiLSTMs):
+ *   per (step, direction, 128-sequence block, 256-gate-column block) tile: x_t W_ih^T + h_s W_hh^T on tensor cores
+ *   (K = K1 + H in one accumulator), then bias + cell update in the epilogue. The [T][S][D*4H] pre-activations never
+ *   reach HBM; `lstm.gates` receives the ACTIVATED gates only (what dvgr_lstm_step_bwd consumes). Steps are chained
+ *   inside the launch by per-(direction, block) completion counters, not by kernel boundaries.
+ *   x    [T][S][x_ld] bf16 time-major input (K1 valid columns, K1 % 8 == 0)
+ *   wih  [D*4H][wih_ld] bf16, rows gate-interleaved like whh (dvgr_cast_rows with lstm_H)
+ *   bias [D*4H] f32 = b_ih + b_hh, gate-interleaved
+ *   sync [dvgr_lstm_seq_sync_words(S, D)] int32, ZERO on entry; the last word is a sticky error flag (stays 0 unless a
+ *        dependency poll timed out, which only a protocol violation can cause)
+ * h_hist / c_hist slot 0 must hold the initial state (zeros); `lstm.s` is ignored. Requires 4H % 256 == 0. */
+typedef struct dvgr_lstm_seq_args {
+  dvgr_lstm_args lstm;
+  const void* x;
+  long long x_ld;
+  int K1;
+  const void* wih;
+  long long wih_ld;
+  const float* bias;
+  int* sync;
+} dvgr_lstm_seq_args;
+int dvgr_lstm_seq_sync_words(int S, int ndir);
+int dvgr_lstm_seq_fwd(const dvgr_lstm_seq_args* args, void* stream);
+/* Whole backward pass of the recurrence (autograd of nn.LSTM at model/Preprocessing.py:227 / :97-101): the cell backward
+ * of step T-1 (elementwise) followed by ONE persistent launch for steps T-2 ... 0 (dh_s = dgates_{s+1} W_hh on tensor
+ * cores, cell backward in the epilogue, steps chained by completion counters). Equivalent to calling
+ * dvgr_lstm_step_bwd for s = T-1 ... 0; `sync` as for dvgr_lstm_seq_fwd (zero on entry); `args->s` is ignored. */
+int dvgr_lstm_seq_bwd(const dvgr_lstm_args* args, int* sync, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * Video-based multi-view graph attention (punishGAT): model/GraphNN.py:95-113 for all heads of a graph, plus the head
  * concat and the attention / output dropouts of :107,:175-177. Up to 4 graphs per launch (acGCN, appearance_GCN, mcGCN,

@@ -65,7 +65,7 @@ def test_gemm_full_size_property(ops):
     assert torch.equal(y2[idx], 2 * y[idx])
 
 
-@pytest.mark.parametrize("T,S,H,D", [(4, 200, 128, 2), (16, 160, 384, 2)])
+@pytest.mark.parametrize("T,S,H,D", [(4, 200, 128, 2), (16, 160, 384, 2), (3, 130, 64, 4), (16, 2560, 384, 2)])
 def test_lstm_fused_recurrence(ops, T, S, H, D):
     torch.manual_seed(2)
     gx, gxr = bf(torch.randn(T, S, D * 4 * H))
@@ -90,8 +90,61 @@ def test_lstm_fused_recurrence(ops, T, S, H, D):
     assert rel(h_last, ref) < 1e-2
     dh, dhr = bf(torch.randn(S, D * H))
     ref.backward(dhr.detach())
+    g_act = g.clone()
     ops.lstm_bwd(g, whh, h_hist, c_hist, dh)
     assert rel(g, gxr.grad) < 2e-2
+    # whole-sequence persistent backward (ONE launch for steps T-2..0, cross-CTA step chaining) = the per-step path
+    g2, sync = ops.lstm_bwd(g_act.clone(), whh, h_hist, c_hist, dh, whole_sequence=True)
+    torch.cuda.synchronize()
+    assert int(sync[-1]) == 0, "dependency poll timed out"
+    assert int(sync[:-1].min()) == int(sync[:-1].max()) == 16 * ((H + 127) // 128) * (T - 1)
+    assert rel(g2, gxr.grad) < 2e-2
+    assert torch.equal(g2, g)          # same arithmetic in the same order: bit-identical to the step launches
+    g3, _ = ops.lstm_bwd(g_act.clone(), whh, h_hist, c_hist, dh, whole_sequence=True)
+    assert torch.equal(g3, g2)
+
+
+@pytest.mark.parametrize("T,S,H,D,K1", [(4, 200, 128, 2, 72), (16, 160, 384, 2, 2048), (5, 300, 64, 4, 304),
+                                        (16, 2560, 384, 2, 256)])
+def test_lstm_whole_sequence_fused_forward(ops, T, S, H, D, K1):
+    """dvgr_lstm_seq_fwd (input projection + all steps in ONE persistent launch, cross-CTA step dependencies) against the
+    float64 recurrence and against the per-step path; the last shape has more tiles per step than SMs (multi-wave
+    dependency chains); the sticky dependency-timeout word must stay 0."""
+    torch.manual_seed(21)
+    x, xr = bf(torch.randn(T, S, K1) * 0.5)
+    wih, wihr = bf(torch.randn(D * 4 * H, K1) * (0.5 / math.sqrt(K1)))
+    whh, whhr = bf(torch.randn(D, 4 * H, H) * 0.08)
+    bias = torch.randn(D * 4 * H) * 0.1
+    gxr = (xr.detach() @ wihr.detach().t() + bias.double())           # [T, S, D*4H], interleaved gate columns
+
+    def ref_run():
+        hs, acts = [], torch.zeros(T, S, D * 4 * H, dtype=torch.float64)
+        for d in range(D):
+            h = gxr.new_zeros(S, H); c = gxr.new_zeros(S, H)
+            for s in range(T):
+                t = s if d % 2 == 0 else T - 1 - s
+                pre = (gxr[t, :, d * 4 * H:(d + 1) * 4 * H] + h @ whhr[d].detach().t()).view(S, H, 4)
+                i, f, g, o = pre[..., 0].sigmoid(), pre[..., 1].sigmoid(), pre[..., 2].tanh(), pre[..., 3].sigmoid()
+                acts[t, :, d * 4 * H:(d + 1) * 4 * H] = torch.stack([i, f, g, o], -1).view(S, 4 * H)
+                c = f * c + i * g
+                h = o * c.tanh()
+            hs.append(h)
+        return torch.cat(hs, 1), acts
+
+    ref_h, ref_g = ref_run()
+    gates, h_hist, c_hist, h_last, _, sync = ops.lstm_seq_fwd(x, wih, whh, bias.cuda())
+    torch.cuda.synchronize()
+    assert int(sync[-1]) == 0, "dependency poll timed out"
+    assert int(sync[:-1].min()) == int(sync[:-1].max()) == 8 * (4 * H // 256) * T      # every (warp, tile) published once
+    assert rel(h_last, ref_h) < 1e-2
+    assert rel(gates, ref_g) < 1e-2
+    # the per-step path on the same operands agrees (it rounds the pre-activations to bf16 first, so not bit-equal)
+    g2 = ops.linear_fwd(x.view(T * S, K1), wih, bias=bias.cuda()).view(T, S, D * 4 * H)
+    _, c2, h2, _ = ops.lstm_fwd(g2, whh)
+    assert rel(h_last, h2) < 1e-2 and rel(c_hist, c2) < 1e-2
+    # idempotence: a second launch on fresh sync words reproduces the result bit for bit (no race on the step chain)
+    gates_b, _, c_b, h_b, _, _ = ops.lstm_seq_fwd(x, wih, whh, bias.cuda())
+    assert torch.equal(h_b, h_last) and torch.equal(gates_b, gates) and torch.equal(c_b, c_hist)
 
 
 @pytest.mark.parametrize("B,N,p", [(3, 20, 0.0), (5, 8, 0.0), (2, 33, 0.0)])

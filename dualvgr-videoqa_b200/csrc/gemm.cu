@@ -664,6 +664,7 @@ struct LstmSeqParams {
   const float* bias;         // [D][4H] fp32, gate-interleaved (b_ih + b_hh)
   int* flags;                // [D][m_blocks] zero at launch
   int* error;                // sticky: set when a dependency poll gave up (never in a healthy run)
+  int prefetch;              // producer pulls the cell epilogue's operands into L2 one tile ahead (DVGR_LSTM_PREFETCH, default 1)
 };
 
 __device__ __forceinline__ int ld_acquire_gpu(const int* ptr) {
@@ -683,11 +684,14 @@ __device__ __forceinline__ void wait_flag(const int* flag, int need, int* error)
   }
 }
 
+constexpr int kSeqEpiWarps = 16;                        // one per (TMEM lane quarter, column-chunk residue mod 4)
+constexpr int kSeqThreads = 128 + 32 * kSeqEpiWarps;
+
 template <int BN>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(kSeqThreads, 1)
 lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWih,
                     const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmWhh,
-                    const GemmParams p, const LstmSeqParams q) {
+                    const __grid_constant__ CUtensorMap tmC, const GemmParams p, const LstmSeqParams q) {
   using Cfg = TileCfg<BN, 1>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -711,7 +715,7 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], kEpiWarps); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], kSeqEpiWarps); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
@@ -731,6 +735,12 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       const int r1 = r0 - d * tiles_per_dir;
       const int m_blk = r1 / q.n_blocks, n_blk = r1 - m_blk * q.n_blocks;
       const int t = (d & 1) == 0 ? s : p.T - 1 - s;
+      if (q.prefetch && s > 0 && n_blk * BN < p.N) {
+        // pull this tile's previous cell state (fp32 [128 x BN/4], seen by the map as bf16 pairs) from HBM into L2 now:
+        // the row-per-thread epilogue loads it one tile (~17 us) later and then finds it there
+        for (int c = 0; c < BN / 128; ++c)
+          tma_prefetch_4d(&tmC, 2 * (n_blk * (BN / 4)) + c * 64, m_blk * BM, s, d);
+      }
       for (int kb = 0; kb < q.kb1; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1u);
         uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
@@ -740,7 +750,7 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
       if (s > 0) {      // h_0 = 0: step 0 has no recurrent part
-        wait_flag(q.flags + d * q.m_blocks + m_blk, kEpiWarps * q.n_blocks * s, q.error);
+        wait_flag(q.flags + d * q.m_blocks + m_blk, kSeqEpiWarps * q.n_blocks * s, q.error);
         fence_proxy_async_global();     // the h rows were written through the generic proxy, TMA reads through the async one
         for (int kb = 0; kb < q.kb2; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
@@ -783,7 +793,7 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   } else if (warp >= 4) {
     // ===================================================== epilogue: LSTM cell on the finished accumulator
     const int qd = warp & 3;
-    const int half = (warp - 4) >> 2;
+    const int c4 = (warp - 4) >> 2;          // this warp's 32-column chunks: c4, c4 + 4, ...
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -802,11 +812,11 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       const int row = m_blk * BM + qd * 32 + lane;
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + static_cast<uint32_t>(as * BN);
 #pragma unroll 1
-      for (int c = half; c < BN / 32; c += 2) {
+      for (int c = c4; c < BN / 32; c += 4) {
         uint32_t r[32];
         tmem_ld_32x32(t_addr + c * 32, r);
         tmem_ld_wait();
-        if (c + 2 >= BN / 32) {
+        if (c + 4 >= BN / 32) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty_bar[as]);
@@ -857,8 +867,8 @@ __device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&r)[8]) {
 }
 
 __global__ void __launch_bounds__(kBwdThreads, 1)
-lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmWhh, const GemmParams p,
-                    const LstmSeqParams q) {
+lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmWhh,
+                    const __grid_constant__ CUtensorMap tmC, const GemmParams p, const LstmSeqParams q) {
   constexpr int BN = kBwdBN;
   constexpr int STAGES = kBwdStages;
   constexpr int A_BYTES = BM * BK * 2;
@@ -902,6 +912,19 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_consta
       const int m_blk = r1 / q.n_blocks, n_blk = r1 - m_blk * q.n_blocks;
       const int s1 = p.T - 1 - k1;                       // the step processed before this one (its dgates are the A operand)
       const int t1 = (d & 1) == 0 ? s1 : p.T - 1 - s1;
+      if (q.prefetch) {
+        // pull the cell epilogue's operands of THIS tile (activated gates of step s, c_{s}, c_{s+1}) from HBM into L2 now:
+        // the row-per-thread epilogue reads them ~one tile later in 16-byte pieces 12 KB apart, which DRAM serves badly
+        // and L2 serves well; as TMA boxes they arrive as whole 128-byte row segments
+        const int s = s1 - 1;
+        const int t = (d & 1) == 0 ? s : p.T - 1 - s;
+        const int units = min(BN, H - n_blk * BN);
+        for (int c = 0; c < units / 16; ++c) tma_prefetch_4d(&tmG, d * 4 * H + 4 * n_blk * BN + c * 64, m_blk * BM, t, 0);
+        for (int c = 0; c < units / 32; ++c) {
+          tma_prefetch_4d(&tmC, 2 * n_blk * BN + c * 64, m_blk * BM, s, d);
+          tma_prefetch_4d(&tmC, 2 * n_blk * BN + c * 64, m_blk * BM, s + 1, d);
+        }
+      }
       if (k1 > 0) {
         wait_flag(q.flags + d * q.m_blocks + m_blk, kBwdEpiWarps * q.n_blocks * k1, q.error);
         fence_proxy_async_global();
@@ -968,22 +991,23 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_consta
       const int seq = m_blk * BM + qd * 32 + lane;
       const int j_base = n_blk * BN + chunk * 32;
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + static_cast<uint32_t>(as * BN + chunk * 32);
-      uint32_t r[4][8];
+      // one 8-unit group at a time (8 accumulator registers live instead of 32); the accumulator stage is handed back to
+      // the MMA warp after the last group's load — the cell epilogue, not the MMA, is this kernel's critical resource
+#pragma unroll 1
+      for (int g = 0; g < 4; ++g) {
+        uint32_t r[8];
+        tmem_ld_32x8(t_addr + g * 8, r);
+        tmem_ld_wait();
+        if (g == 3) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        }
+        if (seq < p.M && j_base + g * 8 < H) {
+          float dh[8];
 #pragma unroll
-      for (int g = 0; g < 4; ++g) tmem_ld_32x8(t_addr + g * 8, r[g]);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);
-      if (seq < p.M) {
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          if (j_base + g * 8 < H) {
-            float dh[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) dh[u] = __uint_as_float(r[g][u]);
-            lstm_cell_bwd8<true>(p, d, s, seq, j_base + g * 8, dh);
-          }
+          for (int u = 0; u < 8; ++u) dh[u] = __uint_as_float(r[u]);
+          lstm_cell_bwd8<true>(p, d, s, seq, j_base + g * 8, dh);
         }
       }
       fence_proxy_async_global();
@@ -1222,6 +1246,11 @@ int gemm_dispatch(const dvgr_operand& A, const dvgr_operand& B, GemmParams p, in
   return set_error("gemm: operand layout combination (A MN-major, B K-major) is not instantiated");
 }
 
+static int lstm_prefetch_knob() {
+  static const int v = getenv("DVGR_LSTM_PREFETCH") ? atoi(getenv("DVGR_LSTM_PREFETCH")) : 1;
+  return v;
+}
+
 // Whole-sequence fused LSTM forward (lstm_seq_fwd_kernel). p carries the EPI_LSTM fields with M = S, N = 4H, batch = D.
 int lstm_seq_fwd_launch(const dvgr_operand& X, const dvgr_operand& Wih, const dvgr_operand& Hh, const dvgr_operand& Whh,
                         GemmParams p, int K1, const float* bias, int* sync, cudaStream_t stream) {
@@ -1230,11 +1259,17 @@ int lstm_seq_fwd_launch(const dvgr_operand& X, const dvgr_operand& Wih, const dv
   const int H = p.N / 4;
   if (p.N % BN != 0) return set_error("lstm_seq_fwd: 4H = %d must be a multiple of %d", p.N, BN);
   if (K1 <= 0 || K1 % 8 != 0) return set_error("lstm_seq_fwd: K1 = %d must be a positive multiple of 8", K1);
-  CUtensorMap tx, twih, th, twhh;
+  CUtensorMap tx, twih, th, twhh, tc;
   int rc = make_tensor_map(&tx, X, 64, BM);
   if (!rc) rc = make_tensor_map(&twih, Wih, 64, BN);
   if (!rc) rc = make_tensor_map(&th, Hh, 64, BM);
   if (!rc) rc = make_tensor_map(&twhh, Whh, 64, BN);
+  // c_hist [D][T+1][S][H] fp32 viewed as bf16 pairs (TMA only moves bytes here: L2 prefetch of the epilogue's operand)
+  dvgr_operand Cop = Hh;
+  Cop.ptr = p.c_hist;
+  Cop.dims[0] = Hh.dims[0] * 2;
+  for (int i = 1; i < 4; ++i) Cop.strides[i] = Hh.strides[i] * 2;
+  if (!rc) rc = make_tensor_map(&tc, Cop, 64, BM);
   if (rc) return rc;
   LstmSeqParams q;
   q.kb1 = (K1 + BK - 1) / BK;
@@ -1244,6 +1279,7 @@ int lstm_seq_fwd_launch(const dvgr_operand& X, const dvgr_operand& Wih, const dv
   q.bias = bias;
   q.flags = sync;
   q.error = sync + (long long)p.batch * q.m_blocks;
+  q.prefetch = lstm_prefetch_knob();
   auto kern = lstm_seq_fwd_kernel<BN>;
   const int smem_bytes = Cfg::SMEM_BYTES - Cfg::STAGING_BYTES;
   static int max_resident = 0;
@@ -1251,14 +1287,14 @@ int lstm_seq_fwd_launch(const dvgr_operand& X, const dvgr_operand& Wih, const dv
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) return set_error("cudaFuncSetAttribute(lstm_seq_fwd, smem=%d): %s", smem_bytes, cudaGetErrorString(e));
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kGemmThreads, smem_bytes);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kSeqThreads, smem_bytes);
     if (e != cudaSuccess || per_sm < 1) return set_error("lstm_seq_fwd: kernel cannot be resident (%s)", cudaGetErrorString(e));
     max_resident = per_sm * num_sms();     // the dependency protocol needs every CTA of the grid co-resident
   }
   const long long tiles = (long long)q.m_blocks * q.n_blocks * p.batch * p.T;
   const int grid = (int)std::min<long long>(tiles, std::min(max_resident, num_sms()));
   if (grid <= 0) return 0;
-  kern<<<grid, kGemmThreads, smem_bytes, stream>>>(tx, twih, th, twhh, p, q);
+  kern<<<grid, kSeqThreads, smem_bytes, stream>>>(tx, twih, th, twhh, tc, p, q);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("lstm_seq_fwd launch failed: %s", cudaGetErrorString(e));
   return 0;
@@ -1269,9 +1305,16 @@ int lstm_seq_bwd_launch(const dvgr_operand& G, const dvgr_operand& Whh, GemmPara
   const int H = p.N;
   if (H % 64 != 0) return set_error("lstm_seq_bwd: H = %d must be a multiple of 64", H);
   if (p.T < 2) return 0;
-  CUtensorMap tg, tw;
+  CUtensorMap tg, tw, tc;
   int rc = make_tensor_map(&tg, G, 64, BM);
   if (!rc) rc = make_tensor_map(&tw, Whh, 64, 64);
+  // c_hist [D][T+1][S][H] fp32 viewed as bf16 pairs: only used for L2 prefetches of the epilogue's operands
+  dvgr_operand Cop;
+  memset(&Cop, 0, sizeof(Cop));
+  Cop.ptr = p.c_hist; Cop.major = 0; Cop.ndim = 4;
+  Cop.dims[0] = 2LL * H; Cop.dims[1] = p.M; Cop.dims[2] = p.T + 1; Cop.dims[3] = p.batch;
+  Cop.strides[0] = 1; Cop.strides[1] = 2LL * H; Cop.strides[2] = 2LL * H * p.M; Cop.strides[3] = 2LL * H * p.M * (p.T + 1);
+  if (!rc) rc = make_tensor_map(&tc, Cop, 64, BM);
   if (rc) return rc;
   LstmSeqParams q;
   q.kb1 = 4 * H / BK;
@@ -1281,6 +1324,7 @@ int lstm_seq_bwd_launch(const dvgr_operand& G, const dvgr_operand& Whh, GemmPara
   q.bias = nullptr;
   q.flags = sync;
   q.error = sync + (long long)p.batch * q.m_blocks;
+  q.prefetch = lstm_prefetch_knob();
   static int max_resident = 0;
   if (max_resident == 0) {
     cudaError_t e = cudaFuncSetAttribute(lstm_seq_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmemBytes);
@@ -1293,7 +1337,7 @@ int lstm_seq_bwd_launch(const dvgr_operand& G, const dvgr_operand& Whh, GemmPara
   const long long tiles = (long long)q.m_blocks * q.n_blocks * p.batch * (p.T - 1);
   const int grid = (int)std::min<long long>(tiles, std::min(max_resident, num_sms()));
   if (grid <= 0) return 0;
-  lstm_seq_bwd_kernel<<<grid, kBwdThreads, kBwdSmemBytes, stream>>>(tg, tw, p, q);
+  lstm_seq_bwd_kernel<<<grid, kBwdThreads, kBwdSmemBytes, stream>>>(tg, tw, tc, p, q);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("lstm_seq_bwd launch failed: %s", cudaGetErrorString(e));
   return 0;

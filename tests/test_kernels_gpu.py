@@ -76,7 +76,7 @@ def test_lstm_fused_recurrence(ops, T, S, H, D):
         for d in range(D):
             h = gx.new_zeros(S, H); c = gx.new_zeros(S, H)
             for s in range(T):
-                t = s if d == 0 else T - 1 - s
+                t = s if d % 2 == 0 else T - 1 - s
                 pre = (gx[t, :, d * 4 * H:(d + 1) * 4 * H] + h @ whh[d].t()).view(S, H, 4)
                 i, f, g, o = pre[..., 0].sigmoid(), pre[..., 1].sigmoid(), pre[..., 2].tanh(), pre[..., 3].sigmoid()
                 c = f * c + i * g
@@ -135,7 +135,7 @@ def test_lstm_whole_sequence_fused_forward(ops, T, S, H, D, K1):
     gates, h_hist, c_hist, h_last, _, sync = ops.lstm_seq_fwd(x, wih, whh, bias.cuda())
     torch.cuda.synchronize()
     assert int(sync[-1]) == 0, "dependency poll timed out"
-    assert int(sync[:-1].min()) == int(sync[:-1].max()) == 8 * (4 * H // 256) * T      # every (warp, tile) published once
+    assert int(sync[:-1].min()) == int(sync[:-1].max()) == 16 * (4 * H // 256) * T     # every (warp, tile) published once
     assert rel(h_last, ref_h) < 1e-2
     assert rel(gates, ref_g) < 1e-2
     # the per-step path on the same operands agrees (it rounds the pre-activations to bf16 first, so not bit-equal)

@@ -9,6 +9,8 @@
 // in shared memory once and reused by the logit dots, and by the N x N aggregation of every head.
 // HBM traffic per CTA: read N*D bf16 + N gates, write N*D bf16  -> the kernel is HBM-bound by design.
 #include <cuda_bf16.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "capi_internal.h"
 #include "ptx.cuh"
@@ -160,17 +162,15 @@ __device__ __forceinline__ void gat_softmax_row(const GatParams& p, const GatSme
   }
 }
 
-// Dropout stream layout (any bijection works as long as forward and backward agree; these make ONE Philox call serve
-// eight mask elements where the kernels consume them):
-//   attention mask (b, k, i, j)  : murmur-hashed element index ((b*K + k)*N + i)*N + j (rng.cuh: dropout_scale1_hash)
-//   output mask    (b, i, c)     : call ((b*(D/2) + c/2) * ceil(N/4) + i/4 , element (i%4)*2 + (c&1)
+// Dropout stream layout (any bijection works as long as forward and backward agree):
+//   attention mask (b, k, i, j)  : murmur-hashed element index ((b*K + k)*N + i)*N + j   (rng.cuh: dropout_scale1_hash)
+//   output mask    (b, i, c)     : murmur-hashed column-PAIR index (b*N + i)*(D/2) + c/2, 16 bits per element
+//                                  (rng.cuh: dropout_scale2_hash) — a thread of the tensor-core kernels owns column pairs
 __device__ __forceinline__ float att_keep(const GatParams& p, const DropoutCfg& cfg, int b, int k, int i, int j) {
   return dropout_scale1_hash(cfg, (((unsigned long long)b * p.heads + k) * p.N + i) * p.N + j);
 }
-__device__ __forceinline__ void out_keep8(const GatParams& p, const DropoutCfg& cfg, int b, int pair, int rowquad,
-                                          float (&sc)[8]) {
-  const unsigned long long call = ((unsigned long long)b * (p.D >> 1) + pair) * ((p.N + 3) >> 2) + rowquad;
-  dropout_scale8(cfg, call, sc);
+__device__ __forceinline__ float2 out_keep2(const GatParams& p, const DropoutCfg& cfg, int b, int i, int pair) {
+  return dropout_scale2_hash(cfg, ((unsigned long long)b * p.N + i) * (p.D >> 1) + pair);
 }
 
 // ------------------------------------------------------------------------------------------------------ forward
@@ -220,24 +220,238 @@ __global__ void __launch_bounds__(kGatThreads) gat_attn_fwd_kernel(const GatPara
           }
         }
       }
-      float keep[2][8];
-      if (p.p_out > 0.f) {
-        out_keep8(p, dout, b, pair, i0 >> 2, keep[0]);
-        out_keep8(p, dout, b, pair, (i0 >> 2) + 1, keep[1]);
-      }
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
         const int i = i0 + r;
         if (i < N) {
           float o0 = eluf_(acc[r][0]), o1 = eluf_(acc[r][1]);
           if (p.p_out > 0.f) {
-            o0 *= keep[r >> 2][(r & 3) * 2];
-            o1 *= keep[r >> 2][(r & 3) * 2 + 1];
+            const float2 keep = out_keep2(p, dout, b, i, pair);
+            o0 *= keep.x;
+            o1 *= keep.y;
           }
           *reinterpret_cast<__nv_bfloat162*>(outp + (long long)i * p.ld_out + c) = __floats2bfloat162_rn(o0, o1);
           if (gr.out_f32 != nullptr)
             *reinterpret_cast<float2*>(gr.out_f32 + ((long long)b * N + i) * D + c) = make_float2(o0, o1);
         }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------ fast path (forward)
+// D = 768, 4 heads — the only configuration DualVGR builds (reference model/models.py:95-100) — and N <= NP nodes.
+// The generic kernel above spends ~95 % of its issue slots on integer / predicate work around a 300 k-MAC aggregation
+// (ncu: 0.19 M warp instructions per CTA, IPC 2.8, DRAM 6 %). Here the aggregation runs on the warp-level tensor cores
+// (mma.sync m16n8k16, bf16 x bf16 -> fp32): A = the gated, masked attention matrix of the head, split into a bf16 high
+// and low half so that it keeps 16 mantissa bits (the fp32 copy of the output feeds the ill-conditioned auxiliary
+// losses), B = the Wh tile already staged in shared memory, read with ldmatrix.trans. ~15 k warp instructions per CTA:
+// the kernel becomes what SURVEY.md §8d says it should be, HBM-bound.
+constexpr int kFD = 768, kFK = 4, kFDh = 192;
+constexpr int kFWP = kFD + 8;             // Wh row pitch (elements): 1552 B, an odd multiple of 16 B -> conflict-free ldmatrix
+constexpr int kFThreads = 256;            // 8 warps x 96 output columns (2 warps per head)
+
+template <int NP> struct GatFast {
+  static constexpr int PP = NP + 8;       // attention-matrix row pitch (elements): (NP + 8) * 2 B is an odd multiple of 16 B
+  static constexpr size_t WH_BYTES = (size_t)NP * kFWP * 2;
+  static constexpr size_t P_BYTES = (size_t)2 * kFK * NP * PP * 2;          // high and low halves
+  static constexpr size_t ST_BYTES = (size_t)2 * kFK * NP * 4;
+  static constexpr size_t GATE_BYTES = (size_t)NP * 4;
+  static constexpr size_t ADJ_BYTES = (size_t)NP * NP;
+  static constexpr size_t FWD_BYTES = WH_BYTES + P_BYTES + ST_BYTES + GATE_BYTES + ADJ_BYTES;
+};
+
+// stage one [N][768] bf16 tile (row stride ld) into shared memory with the padded pitch; rows >= N are zero.
+// cp.async (LDGSTS): every 16-byte piece of the tile is in flight at once and never passes through registers — a plain
+// load/store loop exposes one HBM latency per iteration (8 per thread), which is what bounded the first version.
+// Completion: fast_stage_wait() + __syncthreads().
+template <int NP>
+__device__ __forceinline__ void fast_stage_tile(__nv_bfloat16* dst, const __nv_bfloat16* src, long long ld, int N) {
+  for (int v = threadIdx.x; v < NP * (kFD / 8); v += kFThreads) {
+    const int r = v / (kFD / 8), c = v - r * (kFD / 8);
+    const uint32_t d = smem_u32(dst + (size_t)r * kFWP + c * 8);
+    if (r < N) {
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src + (long long)r * ld + c * 8) : "memory");
+    } else {
+      asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(d), "r"(0) : "memory");
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void fast_stage_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// s_i = a1 . Wh_i, t_i = a2 . Wh_i per head (one warp per (node, head))
+template <int NP>
+__device__ __forceinline__ void fast_logit_dots(const __nv_bfloat16* wh, const float* __restrict__ avec, int N, float* s_s,
+                                                float* s_t) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int pr = warp; pr < N * kFK; pr += kFThreads / 32) {
+    const int i = pr / kFK, k = pr - i * kFK;
+    const float* a = avec + k * (2 * kFDh + 1);
+    const __nv_bfloat16* w = wh + (size_t)i * kFWP + k * kFDh;
+    float s = 0.f, t = 0.f;
+#pragma unroll
+    for (int q = 0; q < kFDh / 64; ++q) {
+      const int c = 2 * lane + 64 * q;
+      const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(w + c));
+      s += __ldg(a + c) * x.x + __ldg(a + c + 1) * x.y;
+      t += __ldg(a + kFDh + c) * x.x + __ldg(a + kFDh + c + 1) * x.y;
+    }
+    s = warp_sum(s);
+    t = warp_sum(t);
+    if (lane == 0) {
+      s_s[k * NP + i] = s;
+      s_t[k * NP + i] = t;
+    }
+  }
+}
+
+// softmax over the neighbours of node i in head k (one warp); returns this lane's probabilities for j = lane (+32)
+template <int NP>
+__device__ __forceinline__ void fast_softmax_row(const GatParams& p, const float* __restrict__ avec, const float* s_s,
+                                                 const float* s_t, const unsigned char* s_adj, int k, int i, int lane,
+                                                 float (&prob)[NP / 32]) {
+  const int N = p.N;
+  const float cb = __ldg(avec + k * (2 * kFDh + 1) + 2 * kFDh);
+  const float si = s_s[k * NP + i];
+  float m = -INFINITY;
+#pragma unroll
+  for (int q = 0; q < NP / 32; ++q) {
+    const int j = lane + 32 * q;
+    prob[q] = -INFINITY;
+    if (j < N) {
+      float u = si + s_t[k * NP + j] + cb;
+      u = u > 0.f ? u : p.slope * u;
+      prob[q] = s_adj[i * NP + j] ? u : -9e15f;
+      m = fmaxf(m, prob[q]);
+    }
+  }
+  m = warp_max(m);
+  float sum = 0.f;
+#pragma unroll
+  for (int q = 0; q < NP / 32; ++q) {
+    const int j = lane + 32 * q;
+    prob[q] = j < N ? __expf(prob[q] - m) : 0.f;
+    sum += prob[q];
+  }
+  sum = warp_sum(sum);
+  const float inv = 1.f / sum;
+#pragma unroll
+  for (int q = 0; q < NP / 32; ++q) prob[q] *= inv;
+}
+
+__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(v);
+  lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
+template <int NP>
+__global__ void __launch_bounds__(kFThreads) gat_attn_fwd_mma_kernel(const GatParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  using F = GatFast<NP>;
+  constexpr int PP = F::PP;
+  __nv_bfloat16* wh = reinterpret_cast<__nv_bfloat16*>(smem_raw);
+  __nv_bfloat16* Phi = reinterpret_cast<__nv_bfloat16*>(smem_raw + F::WH_BYTES);     // [K][NP][PP]
+  __nv_bfloat16* Plo = Phi + (size_t)kFK * NP * PP;
+  float* s_s = reinterpret_cast<float*>(smem_raw + F::WH_BYTES + F::P_BYTES);
+  float* s_t = s_s + kFK * NP;
+  float* s_gate = s_t + kFK * NP;
+  unsigned char* s_adj = reinterpret_cast<unsigned char*>(s_gate + NP);
+  const int b = blockIdx.x;
+  const GatGraph& gr = p.g[blockIdx.y];
+  const int N = p.N;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  // 1. stage the node block, the gate and the adjacency
+  fast_stage_tile<NP>(wh, gr.wh + (long long)b * N * p.ld_wh, p.ld_wh, N);
+  for (int i = tid; i < NP; i += kFThreads) s_gate[i] = i < N ? gr.gate[(long long)b * N + i] : 0.f;
+  for (int e = tid; e < NP * NP; e += kFThreads) {
+    const int i = e / NP, j = e - i * NP;
+    s_adj[e] = (i < N && j < N && p.adj[i * N + j] > 0.f) ? 1 : 0;
+  }
+  fast_stage_wait();
+  __syncthreads();
+  // 2. logit halves
+  fast_logit_dots<NP>(wh, gr.avec, N, s_s, s_t);
+  __syncthreads();
+  // 3. attention rows: softmax, attention dropout, gate (multiplies the values: folded into P), bf16 high / low halves
+  const HashMask matt(DropoutCfg{p.seed, gr.drop_stream, p.p_att, p.seed_off});
+  for (int pr = warp; pr < kFK * NP; pr += kFThreads / 32) {
+    const int k = pr / NP, i = pr - k * NP;
+    float prob[NP / 32];
+    if (i < N) {
+      fast_softmax_row<NP>(p, gr.avec, s_s, s_t, s_adj, k, i, lane, prob);
+    } else {
+#pragma unroll
+      for (int q = 0; q < NP / 32; ++q) prob[q] = 0.f;
+    }
+    const unsigned long long arow = (((unsigned long long)b * kFK + k) * N + i) * N;      // att_keep's element index
+#pragma unroll
+    for (int q = 0; q < NP / 32; ++q) {
+      const int j = lane + 32 * q;
+      float v = 0.f;
+      if (i < N && j < N) v = prob[q] * s_gate[j] * matt.keep1(arow + j);
+      __nv_bfloat16 hi, lo;
+      split_bf16(v, hi, lo);
+      Phi[((size_t)k * NP + i) * PP + j] = hi;
+      Plo[((size_t)k * NP + i) * PP + j] = lo;
+    }
+  }
+  __syncthreads();
+
+  // 4. aggregation on the tensor cores: out[i][c] = dropout(ELU(sum_j P~[k(c)][i][j] Wh[j][c])); warp w owns columns
+  //    [96 w, 96 w + 96) of head w / 2
+  const HashMask mout(DropoutCfg{p.seed, gr.drop_stream + 1u, p.p_out, p.seed_off});
+  __nv_bfloat16* outp = gr.out + (long long)b * N * p.ld_out;
+  float* out32 = gr.out_f32 != nullptr ? gr.out_f32 + (long long)b * N * kFD : nullptr;
+  const int k = warp >> 1, cb = 96 * warp;
+  const int g = lane >> 2, t = lane & 3;
+  const int lrow = (lane & 7) + ((lane >> 3) & 1) * 8;      // ldmatrix row within a 16-row block
+  const int ksteps = (N + 15) >> 4;
+  const uint32_t wh_s = smem_u32(wh), phi_s = smem_u32(Phi), plo_s = smem_u32(Plo);
+#pragma unroll 1
+  for (int mt = 0; mt < NP / 16; ++mt) {
+    if (mt * 16 >= N) break;
+    uint32_t ahi[NP / 16][4], alo[NP / 16][4];
+#pragma unroll
+    for (int ks = 0; ks < NP / 16; ++ks) {
+      const uint32_t off = (uint32_t)((((size_t)k * NP + mt * 16 + lrow) * PP + ks * 16 + (lane >> 4) * 8) * 2);
+      ldsm_x4(ahi[ks], phi_s + off);
+      ldsm_x4(alo[ks], plo_s + off);
+    }
+    // per-row bases of this thread's two rows (g, g + 8): everything below only adds the compile-time column offset
+    const int i0 = mt * 16 + g, i1 = i0 + 8;
+    const int c0 = cb + 2 * t;
+    __nv_bfloat16* ob0 = outp + (long long)i0 * p.ld_out + c0;
+    __nv_bfloat16* ob1 = outp + (long long)i1 * p.ld_out + c0;
+    float* of0 = out32 != nullptr ? out32 + (long long)i0 * kFD + c0 : nullptr;
+    float* of1 = out32 != nullptr ? out32 + (long long)i1 * kFD + c0 : nullptr;
+    const unsigned long long m0 = ((unsigned long long)b * N + i0) * (kFD / 2) + (c0 >> 1);
+    const unsigned long long m1 = ((unsigned long long)b * N + i1) * (kFD / 2) + (c0 >> 1);
+    const uint32_t bbase = wh_s + (uint32_t)(((size_t)lrow * kFWP + cb) * 2);
+#pragma unroll
+    for (int nt = 0; nt < 12; ++nt) {
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int ks = 0; ks < NP / 16; ++ks) {
+        if (ks < ksteps) {
+          uint32_t b0, b1;
+          ldsm_x2_trans(b0, b1, bbase + (uint32_t)(((size_t)ks * 16 * kFWP + nt * 8) * 2));
+          mma_bf16(acc, ahi[ks], b0, b1);
+          mma_bf16(acc, alo[ks], b0, b1);
+        }
+      }
+      if (i0 < N) {
+        const float2 keep = mout.keep2(m0 + nt * 4);
+        const float o0 = elu_fast(acc[0]) * keep.x, o1 = elu_fast(acc[1]) * keep.y;
+        *reinterpret_cast<__nv_bfloat162*>(ob0 + nt * 8) = __floats2bfloat162_rn(o0, o1);
+        if (of0 != nullptr) *reinterpret_cast<float2*>(of0 + nt * 8) = make_float2(o0, o1);
+      }
+      if (i1 < N) {
+        const float2 keep = mout.keep2(m1 + nt * 4);
+        const float o0 = elu_fast(acc[2]) * keep.x, o1 = elu_fast(acc[3]) * keep.y;
+        *reinterpret_cast<__nv_bfloat162*>(ob1 + nt * 8) = __floats2bfloat162_rn(o0, o1);
+        if (of1 != nullptr) *reinterpret_cast<float2*>(of1 + nt * 8) = make_float2(o0, o1);
       }
     }
   }
@@ -283,12 +497,11 @@ __global__ void __launch_bounds__(kGatThreads) gat_attn_bwd_kernel(const GatPara
     const int quads = (N + 3) >> 2;
     for (int u = tid; u < quads * (D / 2); u += blockDim.x) {
       const int rq = u / (D / 2), pair = u - rq * (D / 2), c = pair * 2;
-      float keep[8];
-      if (p.p_out > 0.f) out_keep8(p, dout, b, pair, rq, keep);
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
         const int i = rq * 4 + r;
         if (i >= N) break;
+        const float2 keep = out_keep2(p, dout, b, i, pair);
         float2 h = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(hp + (long long)i * p.ld_out + c));
         float2 d = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dop + (long long)i * p.ld_out + c));
         if (gr.dout_f32 != nullptr) {
@@ -297,8 +510,8 @@ __global__ void __launch_bounds__(kGatThreads) gat_attn_bwd_kernel(const GatPara
           d.y += e.y;
         }
         if (p.p_out > 0.f) {
-          d.x *= keep[2 * r];
-          d.y *= keep[2 * r + 1];
+          d.x *= keep.x;
+          d.y *= keep.y;
           h.x *= keepf;   // recover ELU(z) of the kept elements (dropped ones have zero gradient anyway)
           h.y *= keepf;
         }
@@ -443,6 +656,356 @@ __global__ void __launch_bounds__(kGatThreads) gat_attn_bwd_kernel(const GatPara
   if (tid < K) dav[tid * (2 * Dh + 1) + 2 * Dh] = dc_s[tid];
 }
 
+// ------------------------------------------------------------------------------------------------------ fast path (backward)
+// Same configuration as the forward fast path, N <= 32. The heads of a graph are independent except for the gate
+// gradient, so ONE CTA handles (video, graph, PAIR of heads): 384 of the 768 columns. That halves the two staged tiles
+// (Wh and dz) to 25 KB each — 3 CTAs per SM instead of 1 (the whole-graph version measured 12 % occupancy, IPC 1.3,
+// "no eligible warp" 66 % of the cycles) — and doubles the grid to 2 B x graphs CTAs. The three N x N x D products run on
+// mma.sync:
+//   dP~[k][i][j] = sum_{c in head k} dz[i][c] Wh[j][c]        A = dz (row-major), B = Wh (stored [n][k])
+//   dV[j][c]     = sum_i P~^T[k][j][i] dz[i][c]               A = P~^T (bf16 high + low halves), B = dz (ldmatrix.trans)
+// and everything that hangs off them (gate / attention-vector gradients, dWh) is folded into the fragment epilogues.
+// dgate receives the two head pairs' partial sums by atomicAdd: the caller zeroes it (two addends: deterministic).
+constexpr int kBH = 2;                    // heads per CTA
+constexpr int kBC = kBH * kFDh;           // 384 columns per CTA
+constexpr int kBWP = kBC + 8;             // tile row pitch (elements): 784 B = 49 x 16 B
+constexpr int kBNP = 32, kBPP = kBNP + 8, kBNPF = kBNP + 4, kBMT = kBNP / 16;
+struct GatFastBwd {
+  static constexpr size_t TILE_BYTES = (size_t)kBNP * kBWP * 2;
+  static constexpr size_t PT_BYTES = (size_t)2 * kBH * kBNP * kBPP * 2;
+  static constexpr size_t DP_BYTES = (size_t)kBH * kBNP * kBNPF * 4;
+  static constexpr size_t SMALL_BYTES = (size_t)(4 * kBH * kBNP + 2 * kBNP + 8) * 4;      // s, t, ds, dt, gate, dg, dc
+  static constexpr size_t ADJ_BYTES = (size_t)kBNP * kBNP;
+  static constexpr size_t BYTES = 2 * TILE_BYTES + PT_BYTES + DP_BYTES + SMALL_BYTES + ADJ_BYTES;
+};
+
+__global__ void __launch_bounds__(kFThreads, 3) gat_attn_bwd_mma_kernel(const GatParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  using FB = GatFastBwd;
+  constexpr int NP = kBNP, PP = kBPP, NPF = kBNPF, MT = kBMT;
+  __nv_bfloat16* wh = reinterpret_cast<__nv_bfloat16*>(smem_raw);                                // [NP][kBWP]
+  __nv_bfloat16* dz = reinterpret_cast<__nv_bfloat16*>(smem_raw + FB::TILE_BYTES);
+  __nv_bfloat16* PThi = reinterpret_cast<__nv_bfloat16*>(smem_raw + 2 * FB::TILE_BYTES);         // [kBH][NP (j)][PP (i)]
+  __nv_bfloat16* PTlo = PThi + (size_t)kBH * NP * PP;
+  float* dP = reinterpret_cast<float*>(smem_raw + 2 * FB::TILE_BYTES + FB::PT_BYTES);            // [kBH][NP (i)][NPF (j)]
+  float* s_s = reinterpret_cast<float*>(smem_raw + 2 * FB::TILE_BYTES + FB::PT_BYTES + FB::DP_BYTES);
+  float* s_t = s_s + kBH * NP;
+  float* ds = s_t + kBH * NP;
+  float* dt = ds + kBH * NP;
+  float* s_gate = dt + kBH * NP;
+  float* dg = s_gate + NP;
+  float* dc_s = dg + NP;
+  unsigned char* s_adj = reinterpret_cast<unsigned char*>(dc_s + 8);
+  const int b = blockIdx.x;
+  const GatGraph& gr = p.g[blockIdx.y >> 1];
+  const int hp = blockIdx.y & 1, head0 = hp * kBH, col0 = hp * kBC;
+  const int N = p.N;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int lrow = (lane & 7) + ((lane >> 3) & 1) * 8;
+  const HashMask matt(DropoutCfg{p.seed, gr.drop_stream, p.p_att, p.seed_off});
+  const HashMask mout(DropoutCfg{p.seed, gr.drop_stream + 1u, p.p_out, p.seed_off});
+
+  // 1. stage this head pair's Wh columns (cp.async); dz = (dout [+ dout_f32]) * mask * ELU'(z) straight from global memory
+  {
+    const __nv_bfloat16* src = gr.wh + (long long)b * N * p.ld_wh + col0;
+    for (int v = tid; v < NP * (kBC / 8); v += kFThreads) {
+      const int r = v / (kBC / 8), c = v - r * (kBC / 8);
+      const uint32_t d = smem_u32(wh + (size_t)r * kBWP + c * 8);
+      if (r < N) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src + (long long)r * p.ld_wh + c * 8) : "memory");
+      } else {
+        asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(d), "r"(0) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  for (int i = tid; i < NP; i += kFThreads) {
+    s_gate[i] = i < N ? gr.gate[(long long)b * N + i] : 0.f;
+    dg[i] = 0.f;
+  }
+  for (int e = tid; e < NP * NP; e += kFThreads) {
+    const int i = e / NP, j = e - i * NP;
+    s_adj[e] = (i < N && j < N && p.adj[i * N + j] > 0.f) ? 1 : 0;
+  }
+  {
+    const __nv_bfloat16* hp_ = gr.out + (long long)b * N * p.ld_out + col0;
+    const __nv_bfloat16* dop = gr.dout + (long long)b * N * p.ld_out + col0;
+    const float* d32 = gr.dout_f32 != nullptr ? gr.dout_f32 + (long long)b * N * kFD + col0 : nullptr;
+    const float keepf = 1.f - p.p_out;
+    const bool vec = ((p.ld_out & 7) == 0);
+    constexpr int kBatch = 4;                       // items per thread whose loads are all issued before any is consumed
+    const int items = N * (kBC / 8);                // 8 columns per item
+    for (int v0 = tid; v0 < items; v0 += kFThreads * kBatch) {
+      uint4 hv[kBatch], dv[kBatch];
+      float4 e0[kBatch], e1[kBatch];
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        const int v = v0 + u * kFThreads;
+        hv[u] = dv[u] = make_uint4(0, 0, 0, 0);
+        e0[u] = e1[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (v < items) {
+          const int i = v / (kBC / 8), c = (v - i * (kBC / 8)) * 8;
+          if (vec) {
+            hv[u] = *reinterpret_cast<const uint4*>(hp_ + (long long)i * p.ld_out + c);
+            dv[u] = *reinterpret_cast<const uint4*>(dop + (long long)i * p.ld_out + c);
+          } else {
+            uint32_t* hw_ = reinterpret_cast<uint32_t*>(&hv[u]);
+            uint32_t* dw_ = reinterpret_cast<uint32_t*>(&dv[u]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              hw_[e] = *reinterpret_cast<const uint32_t*>(hp_ + (long long)i * p.ld_out + c + 2 * e);
+              dw_[e] = *reinterpret_cast<const uint32_t*>(dop + (long long)i * p.ld_out + c + 2 * e);
+            }
+          }
+          if (d32 != nullptr) {
+            e0[u] = *reinterpret_cast<const float4*>(d32 + (long long)i * kFD + c);
+            e1[u] = *reinterpret_cast<const float4*>(d32 + (long long)i * kFD + c + 4);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        const int v = v0 + u * kFThreads;
+        if (v < items) {
+          const int i = v / (kBC / 8), c = (v - i * (kBC / 8)) * 8;
+          const float ex[8] = {e0[u].x, e0[u].y, e0[u].z, e0[u].w, e1[u].x, e1[u].y, e1[u].z, e1[u].w};
+          const uint32_t* hw = reinterpret_cast<const uint32_t*>(&hv[u]);
+          const uint32_t* dw = reinterpret_cast<const uint32_t*>(&dv[u]);
+          const unsigned long long mrow = ((unsigned long long)b * N + i) * (kFD / 2) + ((col0 + c) >> 1);
+          uint4 o;
+          uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float2 h = unpack_bf16x2(hw[e]);
+            float2 d = unpack_bf16x2(dw[e]);
+            d.x += ex[2 * e];
+            d.y += ex[2 * e + 1];
+            if (mout.on) {
+              const float2 keep = mout.keep2(mrow + e);
+              d.x *= keep.x;
+              d.y *= keep.y;
+              h.x *= keepf;     // recover ELU(z) of the kept elements (dropped ones have zero gradient anyway)
+              h.y *= keepf;
+            }
+            ow[e] = pack_bf16x2(d.x * elu_grad_from_out(h.x), d.y * elu_grad_from_out(h.y));
+          }
+          *reinterpret_cast<uint4*>(dz + (size_t)i * kBWP + c) = o;
+        }
+      }
+    }
+    for (int v = items + tid; v < NP * (kBC / 8); v += kFThreads) {      // zero rows N .. NP-1
+      const int i = v / (kBC / 8), c = (v - i * (kBC / 8)) * 8;
+      *reinterpret_cast<uint4*>(dz + (size_t)i * kBWP + c) = make_uint4(0, 0, 0, 0);
+    }
+  }
+  fast_stage_wait();
+  __syncthreads();
+  // logit halves s_i = a1 . Wh_i, t_i = a2 . Wh_i of the two heads (one warp per (node, head))
+  for (int pr = warp; pr < N * kBH; pr += kFThreads / 32) {
+    const int i = pr / kBH, kl = pr - i * kBH;
+    const float* a = gr.avec + (head0 + kl) * (2 * kFDh + 1);
+    const __nv_bfloat16* w = wh + (size_t)i * kBWP + kl * kFDh;
+    float s = 0.f, tt = 0.f;
+#pragma unroll
+    for (int q = 0; q < kFDh / 64; ++q) {
+      const int c = 2 * lane + 64 * q;
+      const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(w + c));
+      s += __ldg(a + c) * x.x + __ldg(a + c + 1) * x.y;
+      tt += __ldg(a + kFDh + c) * x.x + __ldg(a + kFDh + c + 1) * x.y;
+    }
+    s = warp_sum(s);
+    tt = warp_sum(tt);
+    if (lane == 0) {
+      s_s[kl * NP + i] = s;
+      s_t[kl * NP + i] = tt;
+    }
+  }
+
+  // 2. dP~ = dz Wh^T per head on the tensor cores; warp w: head w / 4, neighbour columns j in [8 (w % 4), +8)
+  {
+    const int kl = warp >> 2, nt = warp & 3;
+    const uint32_t dz_s = smem_u32(dz), wh_s = smem_u32(wh);
+    float acc[MT][4];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) acc[mt][0] = acc[mt][1] = acc[mt][2] = acc[mt][3] = 0.f;
+    const uint32_t bbase = wh_s + (uint32_t)((((size_t)nt * 8 + (lane & 7)) * kBWP + kl * kFDh + ((lane >> 3) & 1) * 8) * 2);
+    const uint32_t abase = dz_s + (uint32_t)((((size_t)lrow) * kBWP + kl * kFDh + (lane >> 4) * 8) * 2);
+#pragma unroll
+    for (int ks = 0; ks < kFDh / 16; ++ks) {
+      uint32_t b0, b1;
+      ldsm_x2(b0, b1, bbase + ks * 32);
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        uint32_t a[4];
+        ldsm_x4(a, abase + (uint32_t)((size_t)mt * 16 * kBWP * 2) + ks * 32);
+        mma_bf16(acc[mt], a, b0, b1);
+      }
+    }
+    const int k = head0 + kl;
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int i = mt * 16 + g + 8 * h, j = nt * 8 + 2 * t;
+        const unsigned long long arow = (((unsigned long long)b * kFK + k) * N + i) * N;
+        float v0 = 0.f, v1 = 0.f;
+        if (i < N && j < N) v0 = acc[mt][2 * h] * s_gate[j] * matt.keep1(arow + j);
+        if (i < N && j + 1 < N) v1 = acc[mt][2 * h + 1] * s_gate[j + 1] * matt.keep1(arow + j + 1);
+        *reinterpret_cast<float2*>(dP + ((size_t)kl * NP + i) * NPF + j) = make_float2(v0, v1);
+      }
+  }
+  __syncthreads();
+
+  // 3. softmax / LeakyReLU backward per row: du (in place of dP~), ds_i; and the transposed masked attention matrix
+  //    P~^T[k][j][i] = P_ij * mask_ij (ungated) as bf16 high / low halves — the A operand of the dV product
+  for (int pr = warp; pr < kBH * NP; pr += kFThreads / 32) {
+    const int kl = pr / NP, i = pr - kl * NP, k = head0 + kl;
+    const float* av = gr.avec + k * (2 * kFDh + 1);
+    float prob = 0.f, srow = 0.f;
+    const int j = lane;
+    if (i < N) {
+      // softmax over the neighbours (NP = 32: one neighbour per lane)
+      const float cb = __ldg(av + 2 * kFDh);
+      const float si = s_s[kl * NP + i];
+      float e = -INFINITY, u = 0.f;
+      if (j < N) {
+        u = si + s_t[kl * NP + j] + cb;
+        const float lu = u > 0.f ? u : p.slope * u;
+        e = s_adj[i * NP + j] ? lu : -9e15f;
+      }
+      const float m = warp_max(e);
+      prob = j < N ? __expf(e - m) : 0.f;
+      const float sum = warp_sum(prob);
+      prob *= 1.f / sum;
+      float* dProw = dP + ((size_t)kl * NP + i) * NPF;
+      const float dp = j < N ? dProw[j] : 0.f;
+      const float dot = warp_sum(prob * dp);
+      float du = 0.f;
+      if (j < N) {
+        float de = prob * (dp - dot);
+        if (!s_adj[i * NP + j]) de = 0.f;
+        du = de * (u > 0.f ? 1.f : p.slope);
+        dProw[j] = du;
+      }
+      srow = warp_sum(du);
+    }
+    if (lane == 0) ds[kl * NP + i] = srow;
+    float v = 0.f;
+    if (i < N && j < N) v = prob * matt.keep1((((unsigned long long)b * kFK + k) * N + i) * N + j);
+    __nv_bfloat16 hi, lo;
+    split_bf16(v, hi, lo);
+    PThi[((size_t)kl * NP + j) * PP + i] = hi;
+    PTlo[((size_t)kl * NP + j) * PP + i] = lo;
+  }
+  __syncthreads();
+  for (int pr = tid; pr < kBH * NP; pr += kFThreads) {        // dt_j = sum_i du_ij
+    const int kl = pr / NP, j = pr - kl * NP;
+    float a = 0.f;
+    if (j < N)
+      for (int i = 0; i < N; ++i) a += dP[((size_t)kl * NP + i) * NPF + j];
+    dt[pr] = a;
+  }
+  if (tid < kBH) {                                            // dc_k = sum_i ds_i
+    float a = 0.f;
+    for (int i = 0; i < N; ++i) a += ds[tid * NP + i];
+    dc_s[tid] = a;
+  }
+  __syncthreads();
+
+  // 4. dV = P~^T dz on the tensor cores; dWh_j = g_j dV_j + ds_j a1 + dt_j a2 ; dgate_j ; da1, da2 in the fragment epilogue.
+  //    warp w owns columns [48 w, 48 w + 48) of the pair = head w / 4
+  {
+    const int kl = warp >> 2, k = head0 + kl, cbl = 48 * warp;      // column base inside the pair
+    const uint32_t dz_s = smem_u32(dz), phi_s = smem_u32(PThi), plo_s = smem_u32(PTlo);
+    const int ksteps = (N + 15) >> 4;
+    const float* a1 = gr.avec + k * (2 * kFDh + 1);
+    const float* a2 = a1 + kFDh;
+    __nv_bfloat16* dwhp = gr.dwh + (long long)b * N * p.ld_wh + col0;
+    float* dav = gr.davec + ((long long)b * kFK + k) * (2 * kFDh + 1);
+    // A fragments of this head for both 16-row blocks (MT = 2: 32 registers), resident across the column tiles
+    uint32_t ahi[MT][MT][4], alo[MT][MT][4];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int ks = 0; ks < MT; ++ks) {
+        const uint32_t off = (uint32_t)((((size_t)kl * NP + mt * 16 + lrow) * PP + ks * 16 + (lane >> 4) * 8) * 2);
+        ldsm_x4(ahi[mt][ks], phi_s + off);
+        ldsm_x4(alo[mt][ks], plo_s + off);
+      }
+    float dgp[MT][2];
+    float gj[MT][2], dsj[MT][2], dtj[MT][2];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int j = mt * 16 + g + 8 * h;
+        dgp[mt][h] = 0.f;
+        gj[mt][h] = s_gate[j]; dsj[mt][h] = ds[kl * NP + j]; dtj[mt][h] = dt[kl * NP + j];
+      }
+#pragma unroll 2
+    for (int nt = 0; nt < 6; ++nt) {
+      const int c = cbl + nt * 8 + 2 * t, cl = c - kl * kFDh;      // column inside the pair / inside the head
+      uint32_t bfr[MT][2];
+#pragma unroll
+      for (int ks = 0; ks < MT; ++ks)
+        ldsm_x2_trans(bfr[ks][0], bfr[ks][1], dz_s + (uint32_t)((((size_t)ks * 16 + lrow) * kBWP + cbl + nt * 8) * 2));
+      const float a1x = __ldg(a1 + cl), a1y = __ldg(a1 + cl + 1), a2x = __ldg(a2 + cl), a2y = __ldg(a2 + cl + 1);
+      float da1x = 0.f, da1y = 0.f, da2x = 0.f, da2y = 0.f;
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        if (mt * 16 < N) {
+          float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int ks = 0; ks < MT; ++ks) {
+            if (ks < ksteps) {
+              mma_bf16(acc, ahi[mt][ks], bfr[ks][0], bfr[ks][1]);
+              mma_bf16(acc, alo[mt][ks], bfr[ks][0], bfr[ks][1]);
+            }
+          }
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int j = mt * 16 + g + 8 * h;
+            if (j < N) {
+              const float2 w = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(wh + (size_t)j * kBWP + c));
+              const float ox = gj[mt][h] * acc[2 * h] + dsj[mt][h] * a1x + dtj[mt][h] * a2x;
+              const float oy = gj[mt][h] * acc[2 * h + 1] + dsj[mt][h] * a1y + dtj[mt][h] * a2y;
+              *reinterpret_cast<__nv_bfloat162*>(dwhp + (long long)j * p.ld_wh + c) = __floats2bfloat162_rn(ox, oy);
+              dgp[mt][h] += acc[2 * h] * w.x + acc[2 * h + 1] * w.y;      // dgate_j += sum_c dV_j[c] Wh_j[c]
+              da1x += dsj[mt][h] * w.x; da1y += dsj[mt][h] * w.y;
+              da2x += dtj[mt][h] * w.x; da2y += dtj[mt][h] * w.y;
+            }
+          }
+        }
+      }
+      // column sums over the rows held by the 8 lanes that share t
+#pragma unroll
+      for (int o = 4; o < 32; o <<= 1) {
+        da1x += __shfl_xor_sync(0xffffffffu, da1x, o);
+        da1y += __shfl_xor_sync(0xffffffffu, da1y, o);
+        da2x += __shfl_xor_sync(0xffffffffu, da2x, o);
+        da2y += __shfl_xor_sync(0xffffffffu, da2y, o);
+      }
+      if (g == 0) {
+        dav[cl] = da1x; dav[cl + 1] = da1y;
+        dav[kFDh + cl] = da2x; dav[kFDh + cl + 1] = da2y;
+      }
+    }
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float v = dgp[mt][h];
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        const int j = mt * 16 + g + 8 * h;
+        if (t == 0 && j < N) atomicAdd(&dg[j], v);
+      }
+  }
+  __syncthreads();
+  for (int i = tid; i < N; i += kFThreads) atomicAdd(gr.dgate + (long long)b * N + i, dg[i]);      // + the other head pair
+  if (tid < kBH) gr.davec[((long long)b * kFK + head0 + tid) * (2 * kFDh + 1) + 2 * kFDh] = dc_s[tid];
+}
+
 }  // namespace dvgr
 
 using namespace dvgr;
@@ -482,10 +1045,36 @@ static int fill_gat(GatParams& p, const dvgr_gat_args* a, bool bwd) {
   return 0;
 }
 
+static int gat_fast_knob() {      // read per call (tests flip it to compare the two paths): bit 0 forward, bit 1 backward
+  const char* e = getenv("DVGR_GAT_FAST");
+  return e ? atoi(e) : 3;
+}
+static bool gat_fast_ok(const GatParams& p) {
+  return p.D == kFD && p.heads == kFK && p.N <= 64 && (p.ld_wh % 8) == 0 && (p.ld_out % 2) == 0;
+}
+
+template <int NP>
+static int launch_gat_fwd_fast(const GatParams& p, int n_graphs, cudaStream_t st) {
+  static bool configured = false;
+  const size_t smem = GatFast<NP>::FWD_BYTES;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gat_attn_fwd_mma_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_error("gat fwd (mma): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  gat_attn_fwd_mma_kernel<NP><<<dim3(p.B, n_graphs), kFThreads, smem, st>>>(p);
+  DVGR_CHECK_LAUNCH("gat_attn_fwd_mma");
+  return 0;
+}
+
 extern "C" int dvgr_gat_attn_fwd(const dvgr_gat_args* a, void* stream) {
   GatParams p;
   if (int rc = fill_gat(p, a, false)) return rc;
   if (a->B <= 0 || a->N <= 0) return 0;
+  if ((gat_fast_knob() & 1) && gat_fast_ok(p)) {
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    return p.N <= 32 ? launch_gat_fwd_fast<32>(p, a->n_graphs, st) : launch_gat_fwd_fast<64>(p, a->n_graphs, st);
+  }
   const size_t smem = gat_smem_common(p.N, p.D, p.heads);
   if (smem > 227 * 1024) return set_error("gat fwd: %zu bytes of shared memory needed", smem);
   static size_t configured = 0;
@@ -499,10 +1088,30 @@ extern "C" int dvgr_gat_attn_fwd(const dvgr_gat_args* a, void* stream) {
   return 0;
 }
 
+static int launch_gat_bwd_fast(const GatParams& p, int n_graphs, cudaStream_t st) {
+  static bool configured = false;
+  const size_t smem = GatFastBwd::BYTES;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gat_attn_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_error("gat bwd (mma): cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
+    configured = true;
+  }
+  for (int i = 0; i < n_graphs; ++i) {       // the two head-pair CTAs of a (video, graph) add their halves
+    cudaError_t e = cudaMemsetAsync(p.g[i].dgate, 0, sizeof(float) * (size_t)p.B * p.N, st);
+    if (e != cudaSuccess) return set_error("gat bwd (mma): cudaMemsetAsync: %s", cudaGetErrorString(e));
+  }
+  gat_attn_bwd_mma_kernel<<<dim3(p.B, 2 * n_graphs), kFThreads, smem, st>>>(p);
+  DVGR_CHECK_LAUNCH("gat_attn_bwd_mma");
+  return 0;
+}
+
 extern "C" int dvgr_gat_attn_bwd(const dvgr_gat_args* a, void* stream) {
   GatParams p;
   if (int rc = fill_gat(p, a, true)) return rc;
   if (a->B <= 0 || a->N <= 0) return 0;
+  // (N in (32, 64] would need 350 KB of shared memory for the two staged tiles: those videos take the generic kernel)
+  if ((gat_fast_knob() & 2) && gat_fast_ok(p) && p.N <= 32)
+    return launch_gat_bwd_fast(p, a->n_graphs, reinterpret_cast<cudaStream_t>(stream));
   const size_t smem = gat_smem_common(p.N, p.D, p.heads) + gat_smem_bwd_extra(p.N, p.D, p.heads);
   if (smem > 227 * 1024) return set_error("gat bwd: %zu bytes of shared memory needed", smem);
   static size_t configured = 0;

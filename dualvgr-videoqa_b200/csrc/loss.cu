@@ -95,12 +95,24 @@ __device__ __forceinline__ void emit(float* dst, long long o, float v, int acc) 
   else if (acc == 1) dst[o] += v;
   else atomicAdd(dst + o, v);
 }
+// two adjacent columns at once (o even, 8-byte aligned): one 8-byte store / one vector reduction instead of two scalar ones
+__device__ __forceinline__ void emit2(float* dst, long long o, float v0, float v1, int acc) {
+  float2* d2 = reinterpret_cast<float2*>(dst + o);
+  if (acc == 0) {
+    *d2 = make_float2(v0, v1);
+  } else if (acc == 1) {
+    const float2 old = *d2;
+    *d2 = make_float2(old.x + v0, old.y + v1);
+  } else {
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(d2), "f"(v0), "f"(v1) : "memory");
+  }
+}
 
 // pass 2: N x N algebra (redundantly per chunk CTA: it is tiny), loss value (chunk 0), gradient of this column chunk
 // as (N x N) . (N x 256) products on the tensor cores.
 __host__ __device__ inline size_t pair_grad_smem(int N) {
   const int NP = round16(N), CS = NP + 4;
-  return (size_t)(2 * NP * kTS + 3 * NP * CS + 4 * NP) * sizeof(float);
+  return (size_t)(2 * NP * kTS + 3 * NP * CS + 6 * NP) * sizeof(float);
 }
 
 __global__ void __launch_bounds__(kLossThreads) pair_grad_kernel(const PairParams p) {
@@ -112,6 +124,7 @@ __global__ void __launch_bounds__(kLossThreads) pair_grad_kernel(const PairParam
   float* Delta = C + 2 * NP * CS;                 // [NP][CS]
   float* nrm = Delta + NP * CS;                   // [2][NP]
   float* rdot = nrm + 2 * NP;                     // [2][NP]
+  float* inv_nrm = rdot + 2 * NP;                 // [2][NP]
   __shared__ float red[kLossThreads / 32];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = kLossThreads / 32, g = lane >> 2, t = lane & 3;
   const float* x = J.x + (long long)b * N * D;
@@ -133,6 +146,7 @@ __global__ void __launch_bounds__(kLossThreads) pair_grad_kernel(const PairParam
     for (int i = tid; i < 2 * N; i += kLossThreads) {
       const int which = i / N, n = i - which * N;
       nrm[which * NP + n] = fmaxf(sqrtf(fmaxf(C[which * NP * CS + n * CS + n], 0.f)), 1e-12f);
+      inv_nrm[which * NP + n] = 1.f / nrm[which * NP + n];
     }
     __syncthreads();
     for (int e = tid; e < N * N; e += kLossThreads) {
@@ -169,7 +183,7 @@ __global__ void __launch_bounds__(kLossThreads) pair_grad_kernel(const PairParam
     // E^ = E' / n (in place; each thread owns whole columns of both tiles)
     for (int cc = tid; cc < kChunk; cc += kLossThreads)
       for (int which = 0; which < 2; ++which)
-        for (int j = 0; j < N; ++j) tile[((size_t)which * NP + j) * kTS + cc] /= nrm[which * NP + j];
+        for (int j = 0; j < N; ++j) tile[((size_t)which * NP + j) * kTS + cc] *= inv_nrm[which * NP + j];
   }
   __syncthreads();
   if (J.dx == nullptr && J.dy == nullptr) return;
@@ -182,6 +196,7 @@ __global__ void __launch_bounds__(kLossThreads) pair_grad_kernel(const PairParam
     const float* A = (J.mode == 0) ? Delta : C + (size_t)(1 - which) * NP * CS;     // [NP][CS]
     const float* Bt = tile + (size_t)which * NP * kTS;                                // [NP][kTS]
     const float scale = (J.mode == 0) ? (which ? -2.f : 2.f) : 2.f * coef;
+    const bool pair_ok = ((D & 1) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 7) == 0);
     for (int nt = warp; nt < kChunk / 8; nt += nwarps) {
       float acc[4][4];
 #pragma unroll
@@ -208,9 +223,9 @@ __global__ void __launch_bounds__(kLossThreads) pair_grad_kernel(const PairParam
           float v0 = scale * acc[m][2 * h], v1 = scale * acc[m][2 * h + 1];
           if (J.mode == 0) {
             if (m < MT && i < N) {
-              const float nr = nrm[which * NP + i], rd = rdot[which * NP + i];
-              v0 = (v0 - Bt[(size_t)i * kTS + cc] * rd) / nr;
-              v1 = (v1 - Bt[(size_t)i * kTS + cc + 1] * rd) / nr;
+              const float inr = inv_nrm[which * NP + i], rd = rdot[which * NP + i];
+              v0 = (v0 - Bt[(size_t)i * kTS + cc] * rd) * inr;
+              v1 = (v1 - Bt[(size_t)i * kTS + cc + 1] * rd) * inr;
             } else {
               v0 = v1 = 0.f;
             }
@@ -236,8 +251,13 @@ __global__ void __launch_bounds__(kLossThreads) pair_grad_kernel(const PairParam
         for (int h = 0; h < 2; ++h) {
           const int i = m * 16 + g + 8 * h;
           if (m < MT && i < N) {
-            if (c < D) emit(dst, (long long)i * D + c, v[m][2 * h] - (J.mode == 0 ? cs0 : 0.f), acc_flag);
-            if (c + 1 < D) emit(dst, (long long)i * D + c + 1, v[m][2 * h + 1] - (J.mode == 0 ? cs1 : 0.f), acc_flag);
+            const float o0 = v[m][2 * h] - (J.mode == 0 ? cs0 : 0.f), o1 = v[m][2 * h + 1] - (J.mode == 0 ? cs1 : 0.f);
+            if (c + 1 < D && pair_ok) {
+              emit2(dst, (long long)i * D + c, o0, o1, acc_flag);
+            } else {
+              if (c < D) emit(dst, (long long)i * D + c, o0, acc_flag);
+              if (c + 1 < D) emit(dst, (long long)i * D + c + 1, o1, acc_flag);
+            }
           }
         }
       }

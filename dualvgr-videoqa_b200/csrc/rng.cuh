@@ -76,6 +76,50 @@ __device__ __forceinline__ float dropout_scale1_hash(const DropoutCfg& c, unsign
   return h >= (uint32_t)(c.p * 4294967296.0f) ? 1.f / (1.f - c.p) : 0.f;
 }
 
+// Two mask elements (an adjacent column pair) from ONE murmur hash, 16 random bits each (p quantised to 1/65536): the form
+// the graph-attention kernels use for their output dropout, where a thread owns column pairs of scattered rows.
+__device__ __forceinline__ float2 dropout_scale2_hash(const DropoutCfg& c, unsigned long long pair_idx) {
+  if (c.p <= 0.f) return make_float2(1.f, 1.f);
+  const unsigned long long seed = c.seed + (c.seed_off != nullptr ? *c.seed_off : 0ull);
+  uint32_t h = (uint32_t)seed ^ ((uint32_t)(seed >> 32) * 0x9E3779B1u) ^ (c.stream * 0x85EBCA77u) ^
+               ((uint32_t)pair_idx * 0xC2B2AE3Du) ^ ((uint32_t)(pair_idx >> 32) * 0x27D4EB2Fu);
+  h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+  const uint32_t thr = (uint32_t)(c.p * 65536.0f);
+  const float inv = 1.f / (1.f - c.p);
+  return make_float2((h & 0xFFFFu) >= thr ? inv : 0.f, (h >> 16) >= thr ? inv : 0.f);
+}
+
+// The same two hash masks with everything that does not depend on the element hoisted out of the inner loops (the device
+// seed-offset load, the seed / stream mixing, the thresholds): build ONE HashMask per dropout site and thread, then call
+// keep1 / keep2 per element. Bit-identical to dropout_scale1_hash / dropout_scale2_hash.
+struct HashMask {
+  uint32_t base, thr32, thr16;
+  float inv;
+  bool on;
+  __device__ __forceinline__ explicit HashMask(const DropoutCfg& c) {
+    on = c.p > 0.f;
+    const unsigned long long seed = c.seed + ((on && c.seed_off != nullptr) ? *c.seed_off : 0ull);
+    base = (uint32_t)seed ^ ((uint32_t)(seed >> 32) * 0x9E3779B1u) ^ (c.stream * 0x85EBCA77u);
+    thr32 = (uint32_t)(c.p * 4294967296.0f);
+    thr16 = (uint32_t)(c.p * 65536.0f);
+    inv = on ? 1.f / (1.f - c.p) : 1.f;
+  }
+  __device__ __forceinline__ uint32_t mix(unsigned long long idx) const {
+    uint32_t h = base ^ ((uint32_t)idx * 0xC2B2AE3Du) ^ ((uint32_t)(idx >> 32) * 0x27D4EB2Fu);
+    h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+    return h;
+  }
+  __device__ __forceinline__ float keep1(unsigned long long idx) const {
+    if (!on) return 1.f;
+    return mix(idx) >= thr32 ? inv : 0.f;
+  }
+  __device__ __forceinline__ float2 keep2(unsigned long long pair_idx) const {
+    if (!on) return make_float2(1.f, 1.f);
+    const uint32_t h = mix(pair_idx);
+    return make_float2((h & 0xFFFFu) >= thr16 ? inv : 0.f, (h >> 16) >= thr16 ? inv : 0.f);
+  }
+};
+
 // Keep-scale for a single element index (costs a full Philox call; use dropout_scale4 in streaming kernels).
 __device__ __forceinline__ float dropout_scale1(const DropoutCfg& c, unsigned long long idx) {
   if (c.p <= 0.f) return 1.f;

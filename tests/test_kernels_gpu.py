@@ -197,6 +197,41 @@ def test_gat_attention_fwd_bwd(ops, B, N, p):
     assert rel(dgates[0] + dgates[1], gater.grad) < 2e-2
 
 
+@pytest.mark.parametrize("B,N", [(4, 20), (3, 40), (2, 8)])
+def test_gat_tensor_core_path_matches_generic_path_with_dropout(ops, B, N):
+    """The mma.sync fast path (D=768, 4 heads) and the generic SIMT kernels draw the SAME dropout masks (attention and
+    output) from (seed, stream, element): with p > 0 the two paths must agree element-wise, forward and backward, and
+    drop exactly the same outputs. N=40 exercises the 64-node forward variant (its backward stays generic)."""
+    import os
+    torch.manual_seed(31)
+    D, K = 768, 4
+    Dh = D // K
+    adj = orc.build_adjacency(N).cuda()
+    gate = torch.rand(B, N).cuda()
+    whs = [(torch.randn(B * N, D)).to(BF16).cuda() for _ in range(2)]
+    avs = [(torch.randn(K, 2 * Dh + 1) * 0.1).cuda() for _ in range(2)]
+    douts = [(torch.randn(B * N, D)).to(BF16).cuda() for _ in range(2)]
+    d32 = [(torch.randn(B, N, D) * 0.5).cuda() for _ in range(2)]
+    res = {}
+    try:
+        for mode in ("0", "3"):
+            os.environ["DVGR_GAT_FAST"] = mode
+            outs, o32 = ops.gat_attn_fwd(whs, [gate, gate], avs, adj, B, N, p_att=0.3, p_out=0.3, seed=77, want_f32=True)
+            dwhs, dgs, dav = ops.gat_attn_bwd(whs, [gate, gate], avs, outs, douts, adj, B, N, p_att=0.3, p_out=0.3,
+                                              seed=77, douts32=d32)
+            torch.cuda.synchronize()
+            res[mode] = (outs, o32, dwhs, dgs, dav)
+    finally:
+        os.environ.pop("DVGR_GAT_FAST", None)
+    for g in range(2):
+        a, b_ = res["0"], res["3"]
+        assert torch.equal(a[1][g] == 0, b_[1][g] == 0)                       # identical output-dropout pattern
+        drop = float((b_[1][g] == 0).float().mean())
+        assert abs(drop - 0.3) < 0.03
+        assert rel(b_[1][g], a[1][g]) < 1e-4 and rel(b_[0][g], a[0][g]) < 1e-2
+        assert rel(b_[2][g], a[2][g]) < 2e-2 and rel(b_[3][g], a[3][g]) < 2e-2 and rel(b_[4][g], a[4][g]) < 2e-2
+
+
 def test_gat_dropout_statistics(ops):
     """Train-mode dropout is a Philox stream of our own: check keep-rate and scaling, and fwd/bwd mask consistency."""
     torch.manual_seed(4)

@@ -667,7 +667,11 @@ class AuxLossFn(Function):
     Returns (combined scalar, [3] tensor of the coef-scaled terms (not differentiated))."""
 
     @staticmethod
-    def forward(ctx, ca, cm, aq, mq, coef_com, coef_dep):
+    def forward(ctx, ca, cm, aq, mq, coef_com, coef_dep, unit_grad=False):
+        """unit_grad: the caller adds the returned scalar to its total loss with coefficient exactly 1 (train.py:154 with
+        alpha / beta already folded into the coefficients), so backward returns the stored gradients as they are instead
+        of launching four [B,N,D] multiplications by a scalar that is 1."""
+        ctx.unit_grad = bool(unit_grad)
         ca, cm, aq, mq = (_c(t.float()) for t in (ca, cm, aq, mq))
         B, N, D = ca.shape
         d_ca, d_cm = torch.zeros_like(ca), torch.zeros_like(cm)       # two addends each -> atomic adds are deterministic
@@ -683,7 +687,9 @@ class AuxLossFn(Function):
     @staticmethod
     def backward(ctx, g, _):
         d_ca, d_cm, d_aq, d_mq = ctx.saved_tensors
-        return d_ca * g, d_cm * g, d_aq * g, d_mq * g, None, None
+        if ctx.unit_grad:
+            return d_ca, d_cm, d_aq, d_mq, None, None, None
+        return d_ca * g, d_cm * g, d_aq * g, d_mq * g, None, None, None
 
 
 class PairLossFn(Function):

@@ -530,14 +530,32 @@ colsum_partial_kernel(const T* __restrict__ in, long long ld, long long R, int C
     }
   }
 }
-__global__ void colsum_final_kernel(const float* __restrict__ partial, int chunks, int C, float* __restrict__ out,
-                                    int accumulate, float scale) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  float acc = 0.f;
-  for (int k = 0; k < chunks; ++k) acc += partial[(long long)k * C + c];
-  acc *= scale;
-  out[c] = accumulate ? out[c] + acc : acc;
+// 32 columns x 8 chunk lanes per block: the chain of dependent adds per column is chunks / 8 long instead of chunks
+// (a [160 x 768] reduction took 13 us as one thread per column), summed in a fixed order -> still deterministic.
+__global__ void __launch_bounds__(256)
+colsum_final_kernel(const float* __restrict__ partial, int chunks, int C, float* __restrict__ out, int accumulate,
+                    float scale) {
+  __shared__ float red[8][33];
+  const int cl = threadIdx.x & 31, kl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  float a0 = 0.f, a1 = 0.f;
+  if (c < C) {
+    int k = kl;
+    for (; k + 8 < chunks; k += 16) {
+      a0 += partial[(long long)k * C + c];
+      a1 += partial[(long long)(k + 8) * C + c];
+    }
+    if (k < chunks) a0 += partial[(long long)k * C + c];
+  }
+  red[kl][cl] = a0 + a1;
+  __syncthreads();
+  if (kl == 0 && c < C) {
+    float acc = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc += red[q][cl];
+    acc *= scale;
+    out[c] = accumulate ? out[c] + acc : acc;
+  }
 }
 
 static inline int grid_for(long long n, int threads = 256, int max_blocks = 148 * 16) {
@@ -724,7 +742,7 @@ extern "C" int dvgr_colsum(const void* in, int in_is_f32, long long ld, long lon
   else
     colsum_partial_kernel<bf16><<<grid, 256, 0, ST(stream)>>>(CBF(in), ld, R, C, rpc, workspace, vec_ok);
   DVGR_CHECK_LAUNCH("colsum_partial");
-  colsum_final_kernel<<<(C + 127) / 128, 128, 0, ST(stream)>>>(workspace, (int)chunks, C, out, accumulate, scale);
+  colsum_final_kernel<<<(C + 31) / 32, 256, 0, ST(stream)>>>(workspace, (int)chunks, C, out, accumulate, scale);
   DVGR_CHECK_LAUNCH("colsum_final");
   return 0;
 }

@@ -131,12 +131,14 @@ __global__ void __launch_bounds__(kLossThreads) pair_grad_kernel(const PairParam
   const float* y = J.y + (long long)b * N * D;
   const float coef = J.coef;
   const float* gw = p.gram_ws + (((long long)jb * p.B + b) * p.chunks * 2) * N * N;
-  for (int e = tid; e < 2 * NP * CS; e += kLossThreads) {
-    const int which = e / (NP * CS), r = e - which * NP * CS, i = r / CS, j = r - i * CS;
-    float s = 0.f;
-    if (i < N && j < N)
-      for (int k = 0; k < p.chunks; ++k) s += gw[(long long)k * 2 * N * N + which * N * N + i * N + j];
-    C[e] = s;
+  for (int row = warp; row < 2 * NP; row += nwarps) {      // one warp per Gram row: no integer divisions in the loop
+    const int which = row >= NP ? 1 : 0, i = row - which * NP;
+    for (int j = lane; j < CS; j += 32) {
+      float s = 0.f;
+      if (i < N && j < N)
+        for (int k = 0; k < p.chunks; ++k) s += gw[(long long)k * 2 * N * N + which * N * N + i * N + j];
+      C[(size_t)row * CS + j] = s;
+    }
   }
   for (int e = tid; e < NP * CS; e += kLossThreads) Delta[e] = 0.f;
   load_centered_chunk(x, y, N, D, ch * kChunk, tile);
@@ -149,21 +151,19 @@ __global__ void __launch_bounds__(kLossThreads) pair_grad_kernel(const PairParam
       inv_nrm[which * NP + n] = 1.f / nrm[which * NP + n];
     }
     __syncthreads();
-    for (int e = tid; e < N * N; e += kLossThreads) {
-      const int i = e / N, j = e - i * N;
-      const float g1 = C[i * CS + j] / (nrm[i] * nrm[j]);
-      const float g2 = C[NP * CS + i * CS + j] / (nrm[NP + i] * nrm[NP + j]);
-      const float d = g1 - g2;
-      part += d * d;
-      Delta[i * CS + j] = 2.f * coef * d;     // dL/dG1 ; dL/dG2 = -Delta
-      C[i * CS + j] = g1;                      // keep the normalised Grams for r_i
-      C[NP * CS + i * CS + j] = g2;
-    }
+    for (int i = warp; i < N; i += nwarps)
+      for (int j = lane; j < N; j += 32) {
+        const float g1 = C[i * CS + j] * (inv_nrm[i] * inv_nrm[j]);
+        const float g2 = C[NP * CS + i * CS + j] * (inv_nrm[NP + i] * inv_nrm[NP + j]);
+        const float d = g1 - g2;
+        part += d * d;
+        Delta[i * CS + j] = 2.f * coef * d;     // dL/dG1 ; dL/dG2 = -Delta
+        C[i * CS + j] = g1;                      // keep the normalised Grams for r_i
+        C[NP * CS + i * CS + j] = g2;
+      }
   } else {
-    for (int e = tid; e < N * N; e += kLossThreads) {
-      const int i = e / N, j = e - i * N;
-      part += C[i * CS + j] * C[NP * CS + i * CS + j];
-    }
+    for (int i = warp; i < N; i += nwarps)
+      for (int j = lane; j < N; j += 32) part += C[i * CS + j] * C[NP * CS + i * CS + j];
   }
   part = warp_sum(part);
   if (lane == 0) red[warp] = part;
@@ -187,6 +187,14 @@ __global__ void __launch_bounds__(kLossThreads) pair_grad_kernel(const PairParam
   }
   __syncthreads();
   if (J.dx == nullptr && J.dy == nullptr) return;
+  // the N x N left operands of the gradient products are used as TF32 from here on: round them ONCE instead of
+  // converting every fragment element inside the MMA loop
+  if (J.mode == 0) {
+    for (int e = tid; e < NP * CS; e += kLossThreads) Delta[e] = __uint_as_float(to_tf32(Delta[e]));
+  } else {
+    for (int e = tid; e < 2 * NP * CS; e += kLossThreads) C[e] = __uint_as_float(to_tf32(C[e]));
+  }
+  __syncthreads();
 
   const int MT = NP / 16;
   for (int which = 0; which < 2; ++which) {
@@ -208,7 +216,8 @@ __global__ void __launch_bounds__(kLossThreads) pair_grad_kernel(const PairParam
         for (int m = 0; m < 4; ++m) {
           if (m < MT) {
             const float* ar = A + (size_t)(m * 16 + g) * CS + k0 + t;
-            mma_tf32(acc[m], to_tf32(ar[0]), to_tf32(ar[8 * CS]), to_tf32(ar[4]), to_tf32(ar[8 * CS + 4]), b0, b1);
+            mma_tf32(acc[m], __float_as_uint(ar[0]), __float_as_uint(ar[8 * CS]), __float_as_uint(ar[4]),
+                     __float_as_uint(ar[8 * CS + 4]), b0, b1);
           }
         }
       }

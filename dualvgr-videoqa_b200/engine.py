@@ -73,8 +73,8 @@ class TrainEngine:
         total, com, dep = ce, None, None
         c_com, c_dep = (self.alpha / max(n, 1)) / (B * N * N), self.beta * self.world / max(n, 1)
         for i in range(n):
-            aux, vals = ag.AuxLossFn.apply(com_app[i], com_mot[i], aq[i], mq[i], c_com, c_dep)
-            total = total + aux
+            aux, vals = ag.AuxLossFn.apply(com_app[i], com_mot[i], aq[i], mq[i], c_com, c_dep, True)
+            total = total + aux            # coefficient exactly 1: AuxLossFn's unit_grad contract
             c, d = vals[0], vals[1] + vals[2]
             com = c if com is None else com + c
             dep = d if dep is None else dep + d

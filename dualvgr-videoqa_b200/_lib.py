@@ -86,7 +86,7 @@ lstm_step_fwd = _sig("dvgr_lstm_step_fwd", [ctypes.POINTER(LstmArgs), c_void_p])
 lstm_step_bwd = _sig("dvgr_lstm_step_bwd", [ctypes.POINTER(LstmArgs), c_void_p])
 lstm_seq_fwd = _sig("dvgr_lstm_seq_fwd", [ctypes.POINTER(LstmSeqArgs), c_void_p])
 lstm_seq_sync_words = _sig("dvgr_lstm_seq_sync_words", [c_int, c_int])
-lstm_seq_bwd = _sig("dvgr_lstm_seq_bwd", [ctypes.POINTER(LstmArgs), c_void_p, c_void_p])
+lstm_seq_bwd = _sig("dvgr_lstm_seq_bwd", [ctypes.POINTER(LstmArgs), c_void_p, c_void_p, c_void_p])
 
 
 class GatGraph(ctypes.Structure):

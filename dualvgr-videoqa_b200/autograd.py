@@ -301,10 +301,11 @@ class AppearanceEncoderFn(Function):
         dh = _c(dout.reshape(S, 2 * H))
         if p_o > 0:
             dh = ops.dropout_raw(dh, p_o, seed, sid + 1)
-        if LSTM_SEQ[0]:                                          # gates now holds d(pre-activation gates)
-            SYNC_WORDS.append(ops.lstm_bwd(gates, whh, h_hist, c_hist, dh, whole_sequence=True)[1])
+        if LSTM_SEQ[0]:                                          # blocked activated gates in, standard-layout gradients out
+            gates, sync = ops.lstm_bwd(gates, whh, h_hist, c_hist, dh, whole_sequence=True)
+            SYNC_WORDS.append(sync)
         else:
-            ops.lstm_bwd(gates, whh, h_hist, c_hist, dh)
+            ops.lstm_bwd(gates, whh, h_hist, c_hist, dh)         # gates now holds d(pre-activation gates)
         dg = gates.view(T * S, 8 * H)
         unmap = _lstm_unmap(H, 2, dg.device)
         t_ih, t_hh = grad_target(ctx.wih_params), grad_target(ctx.whh_params)
@@ -378,8 +379,8 @@ class QuestionEncoderFn(Function):
         if d_q is not None:
             dh_last[:, 2 * H:] = d_q
         if LSTM_SEQ[0]:
-            SYNC_WORDS.append(ops.lstm_bwd(gates, whh, h_hist, c_hist, dh_last, seq_len=qlen, dh_seq=dh_seq,
-                                           whole_sequence=True)[1])
+            gates, sync = ops.lstm_bwd(gates, whh, h_hist, c_hist, dh_last, seq_len=qlen, dh_seq=dh_seq, whole_sequence=True)
+            SYNC_WORDS.append(sync)
         else:
             ops.lstm_bwd(gates, whh, h_hist, c_hist, dh_last, seq_len=qlen, dh_seq=dh_seq)
         dg = gates.view(L * B, 16 * H)

@@ -193,12 +193,12 @@ int dvgr_lstm_step_bwd(const dvgr_lstm_args* a, void* stream) {
   return rc;
 }
 
-int dvgr_lstm_seq_bwd(const dvgr_lstm_args* a, int* sync, void* stream) {
+int dvgr_lstm_seq_bwd(const dvgr_lstm_args* a, void* dgates, int* sync, void* stream) {
   if (!a) return set_error("dvgr_lstm_seq_bwd: null args");
   dvgr_lstm_args b = *a;
   b.s = b.T - 1;
   if (int rc = check_lstm(b)) return rc;
-  if (!b.dc || !sync) return set_error("dvgr_lstm_seq_bwd: dc / sync is null");
+  if (!b.dc || !sync || !dgates) return set_error("dvgr_lstm_seq_bwd: dc / sync / dgates is null");
   if (b.seq_len && !b.dh_carry) return set_error("dvgr_lstm_seq_bwd: dh_carry is required with seq_len");
   GemmParams p;
   memset(&p, 0, sizeof(p));
@@ -206,6 +206,8 @@ int dvgr_lstm_seq_bwd(const dvgr_lstm_args* a, int* sync, void* stream) {
   p.mode = EPI_LSTM_BWD;
   p.dh_ext = reinterpret_cast<const __nv_bfloat16*>(b.dh_seq);
   p.M = b.S; p.N = b.H; p.K = 4 * b.H;
+  p.RB = (b.S + 31) / 32;                                        // blocked gates / c_hist / dc (gemm.cuh)
+  p.dgates = reinterpret_cast<__nv_bfloat16*>(dgates);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   int rc = lstm_bwd_first(p, b.dh_last, b.dh_last_ld, st);      // step T-1: no recurrent product
   if (rc) return rc;
@@ -213,7 +215,7 @@ int dvgr_lstm_seq_bwd(const dvgr_lstm_args* a, int* sync, void* stream) {
   if (b.T < 2) return 0;
   dvgr_operand A, B;
   memset(&A, 0, sizeof(A)); memset(&B, 0, sizeof(B));
-  A.ptr = b.gates; A.major = 0; A.ndim = 3;
+  A.ptr = dgates; A.major = 0; A.ndim = 3;                        // the gate gradients of the step processed before
   A.dims[0] = (long long)b.ndir * 4 * b.H; A.dims[1] = b.S; A.dims[2] = b.T;
   A.strides[0] = 1; A.strides[1] = A.dims[0]; A.strides[2] = A.dims[0] * b.S;
   B.ptr = b.whh; B.major = 1; B.ndim = 3;

@@ -284,14 +284,19 @@ __device__ __forceinline__ void epi_lstm_fwd(const GemmParams& p, int dir, int s
   const long long st = ((long long)dir * (p.T + 1) + s) * S * H + (long long)seq * H + j0;   // slot s
   const long long st1 = st + (long long)S * H;                                                // slot s+1
   const bool live = (p.seq_len == nullptr) || (t < p.seq_len[seq]);
+  // blocked layout (fused mode): this warp's tile of gates / cell state, see gemm.cuh
+  const int UG = H >> 3;
+  __nv_bfloat16* gb = p.gates + lstm_blk_gates(t, dir, p.batch, p.RB, UG, seq >> 5, col0 >> 5) + (seq & 31) * 8;
+  float* cb0 = p.c_hist + lstm_blk_c(dir, s, p.T, p.RB, UG, seq >> 5, col0 >> 5) + (seq & 31) * 4;
+  float* cb1 = cb0 + (long long)p.RB * UG * 256;
 
   uint4 gin[4];
   float4 cp0, cp1;
   if (kFused) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) gin[q] = make_uint4(0, 0, 0, 0);
-    cp0 = __ldcg(reinterpret_cast<const float4*>(p.c_hist + st));
-    cp1 = __ldcg(reinterpret_cast<const float4*>(p.c_hist + st + 4));
+    cp0 = __ldcg(reinterpret_cast<const float4*>(cb0));
+    cp1 = __ldcg(reinterpret_cast<const float4*>(cb0 + 128));
   } else {
 #pragma unroll
     for (int q = 0; q < 4; ++q) gin[q] = reinterpret_cast<const uint4*>(g)[q];
@@ -339,10 +344,17 @@ __device__ __forceinline__ void epi_lstm_fwd(const GemmParams& p, int dir, int s
 #pragma unroll
     for (int q = 0; q < 4; ++q) gout[q] = make_uint4(0, 0, 0, 0);
   }
+  if (kFused) {
 #pragma unroll
-  for (int q = 0; q < 4; ++q) reinterpret_cast<uint4*>(g)[q] = gout[q];
-  *reinterpret_cast<float4*>(p.c_hist + st1) = make_float4(cnew[0], cnew[1], cnew[2], cnew[3]);
-  *reinterpret_cast<float4*>(p.c_hist + st1 + 4) = make_float4(cnew[4], cnew[5], cnew[6], cnew[7]);
+    for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(gb + q * 256) = gout[q];
+    *reinterpret_cast<float4*>(cb1) = make_float4(cnew[0], cnew[1], cnew[2], cnew[3]);
+    *reinterpret_cast<float4*>(cb1 + 128) = make_float4(cnew[4], cnew[5], cnew[6], cnew[7]);
+  } else {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) reinterpret_cast<uint4*>(g)[q] = gout[q];
+    *reinterpret_cast<float4*>(p.c_hist + st1) = make_float4(cnew[0], cnew[1], cnew[2], cnew[3]);
+    *reinterpret_cast<float4*>(p.c_hist + st1 + 4) = make_float4(cnew[4], cnew[5], cnew[6], cnew[7]);
+  }
   uint4 hv;
   hv.x = pack_bf16x2(hnew[0], hnew[1]); hv.y = pack_bf16x2(hnew[2], hnew[3]);
   hv.z = pack_bf16x2(hnew[4], hnew[5]); hv.w = pack_bf16x2(hnew[6], hnew[7]);
@@ -365,25 +377,45 @@ template <bool kCoherent>
 __device__ __forceinline__ float4 ld_run4(const float* ptr) {
   return kCoherent ? __ldcg(reinterpret_cast<const float4*>(ptr)) : *reinterpret_cast<const float4*>(ptr);
 }
-template <bool kCoherent>
-__device__ __forceinline__ void lstm_cell_bwd8(const GemmParams& p, int dir, int s, int seq, int j0, float (&dh)[8]) {
+// kSeq = false: per-step launches — row-major gates / c_hist / dc, dgates written in place of the gates.
+// kSeq = true : whole-sequence kernels — blocked gates / c_hist / dc (gemm.cuh), running buffers read around L1, and the
+//               gate gradients are RETURNED in gout (zeros for a padded step) for the caller to store in the standard
+//               [T][S][D*4H] layout the TMA / wgrad operands need.
+template <bool kSeq>
+__device__ __forceinline__ void lstm_cell_bwd8(const GemmParams& p, int dir, int s, int seq, int j0, float (&dh)[8],
+                                               uint4 (&gout)[4]) {
   const int H = p.N;   // bwd GEMM has N = H
   const int S = p.M;
   const int t = (dir & 1) == 0 ? s : p.T - 1 - s;
-  __nv_bfloat16* g = p.gates + ((long long)t * p.M + seq) * p.gates_ld + (long long)dir * p.gates_dir + 4 * j0;
-  const long long st = ((long long)dir * (p.T + 1) + s) * S * H + (long long)seq * H + j0;
-  const long long st1 = st + (long long)S * H;
-  float* dcp = p.dc + ((long long)dir * S + seq) * H + j0;
+  const int UG = H >> 3;
+  const __nv_bfloat16* g;
+  const float *cprev_p, *cc_p;
+  float* dcp;
+  long long gq, cq;          // element stride between the 16-byte pieces of this thread
+  if (kSeq) {
+    g = p.gates + lstm_blk_gates(t, dir, p.batch, p.RB, UG, seq >> 5, j0 >> 3) + (seq & 31) * 8;
+    cprev_p = p.c_hist + lstm_blk_c(dir, s, p.T, p.RB, UG, seq >> 5, j0 >> 3) + (seq & 31) * 4;
+    cc_p = cprev_p + (long long)p.RB * UG * 256;
+    dcp = p.dc + lstm_blk_dc(dir, p.RB, UG, seq >> 5, j0 >> 3) + (seq & 31) * 4;
+    gq = 256; cq = 128;
+  } else {
+    g = p.gates + ((long long)t * p.M + seq) * p.gates_ld + (long long)dir * p.gates_dir + 4 * j0;
+    const long long st = ((long long)dir * (p.T + 1) + s) * S * H + (long long)seq * H + j0;
+    cprev_p = p.c_hist + st;
+    cc_p = cprev_p + (long long)S * H;
+    dcp = p.dc + ((long long)dir * S + seq) * H + j0;
+    gq = 8; cq = 4;
+  }
   const bool live = (p.seq_len == nullptr) || (t < p.seq_len[seq]);
   // issue every load of this group up front (one latency round)
   uint4 gin[4];
   float4 a0, a1, b0, b1, d0, d1;
   if (live) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) gin[q] = reinterpret_cast<const uint4*>(g)[q];
-    a0 = *reinterpret_cast<const float4*>(p.c_hist + st); a1 = *reinterpret_cast<const float4*>(p.c_hist + st + 4);
-    b0 = *reinterpret_cast<const float4*>(p.c_hist + st1); b1 = *reinterpret_cast<const float4*>(p.c_hist + st1 + 4);
-    d0 = ld_run4<kCoherent>(dcp); d1 = ld_run4<kCoherent>(dcp + 4);
+    for (int q = 0; q < 4; ++q) gin[q] = *reinterpret_cast<const uint4*>(g + q * gq);
+    a0 = *reinterpret_cast<const float4*>(cprev_p); a1 = *reinterpret_cast<const float4*>(cprev_p + cq);
+    b0 = *reinterpret_cast<const float4*>(cc_p); b1 = *reinterpret_cast<const float4*>(cc_p + cq);
+    d0 = ld_run4<kSeq>(dcp); d1 = ld_run4<kSeq>(dcp + cq);
   }
   if (live && p.dh_ext != nullptr) {
     // gradient arriving on the per-step hidden output [S][T][ld] (column dir*H); padded steps emit constant zeros
@@ -398,7 +430,7 @@ __device__ __forceinline__ void lstm_cell_bwd8(const GemmParams& p, int dir, int
   if (p.dh_carry != nullptr) {
     // padded steps carry the state forward, so their incoming dh must reach the last live step unchanged
     float* cp = p.dh_carry + ((long long)dir * S + seq) * H + j0;
-    float4 c0 = ld_run4<kCoherent>(cp), c1 = ld_run4<kCoherent>(cp + 4);
+    float4 c0 = ld_run4<kSeq>(cp), c1 = ld_run4<kSeq>(cp + 4);
     dh[0] += c0.x; dh[1] += c0.y; dh[2] += c0.z; dh[3] += c0.w;
     dh[4] += c1.x; dh[5] += c1.y; dh[6] += c1.z; dh[7] += c1.w;
     if (live) {
@@ -409,11 +441,12 @@ __device__ __forceinline__ void lstm_cell_bwd8(const GemmParams& p, int dir, int
       *reinterpret_cast<float4*>(cp + 4) = make_float4(dh[4], dh[5], dh[6], dh[7]);
     }
   }
-  if (!live) return;   // dgates stay zero (written by the forward pass); dc passes through untouched
+#pragma unroll
+  for (int q = 0; q < 4; ++q) gout[q] = make_uint4(0, 0, 0, 0);
+  if (!live) return;   // padded step: zero gate gradients (in place they already are: the forward wrote zeros); dc untouched
   float cprev[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
   float cc[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
   float dc[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
-  uint4 gout[4];
   const uint32_t* gw = reinterpret_cast<const uint32_t*>(gin);
   uint32_t* go = reinterpret_cast<uint32_t*>(gout);
 #pragma unroll
@@ -431,10 +464,13 @@ __device__ __forceinline__ void lstm_cell_bwd8(const GemmParams& p, int dir, int
     go[2 * u] = pack_bf16x2(d_i, d_f);
     go[2 * u + 1] = pack_bf16x2(d_g, d_o);
   }
+  if (!kSeq) {
+    __nv_bfloat16* gw_ = const_cast<__nv_bfloat16*>(g);
 #pragma unroll
-  for (int q = 0; q < 4; ++q) reinterpret_cast<uint4*>(g)[q] = gout[q];
+    for (int q = 0; q < 4; ++q) reinterpret_cast<uint4*>(gw_)[q] = gout[q];
+  }
   *reinterpret_cast<float4*>(dcp) = make_float4(dc[0], dc[1], dc[2], dc[3]);
-  *reinterpret_cast<float4*>(dcp + 4) = make_float4(dc[4], dc[5], dc[6], dc[7]);
+  *reinterpret_cast<float4*>(dcp + cq) = make_float4(dc[4], dc[5], dc[6], dc[7]);
 }
 
 __device__ __forceinline__ void epi_lstm_bwd(const GemmParams& p, int dir, int seq, int col0, const uint32_t (&r)[32]) {
@@ -444,7 +480,8 @@ __device__ __forceinline__ void epi_lstm_bwd(const GemmParams& p, int dir, int s
     float dh[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) dh[u] = __uint_as_float(r[8 * q + u]);
-    lstm_cell_bwd8<false>(p, dir, p.s, seq, col0 + 8 * q, dh);
+    uint4 gout[4];
+    lstm_cell_bwd8<false>(p, dir, p.s, seq, col0 + 8 * q, dh, gout);
   }
 }
 
@@ -664,7 +701,6 @@ struct LstmSeqParams {
   const float* bias;         // [D][4H] fp32, gate-interleaved (b_ih + b_hh)
   int* flags;                // [D][m_blocks] zero at launch
   int* error;                // sticky: set when a dependency poll gave up (never in a healthy run)
-  int prefetch;              // producer pulls the cell epilogue's operands into L2 one tile ahead (DVGR_LSTM_PREFETCH, default 1)
 };
 
 __device__ __forceinline__ int ld_acquire_gpu(const int* ptr) {
@@ -691,7 +727,7 @@ template <int BN>
 __global__ void __launch_bounds__(kSeqThreads, 1)
 lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWih,
                     const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmWhh,
-                    const __grid_constant__ CUtensorMap tmC, const GemmParams p, const LstmSeqParams q) {
+                    const GemmParams p, const LstmSeqParams q) {
   using Cfg = TileCfg<BN, 1>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -735,12 +771,6 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       const int r1 = r0 - d * tiles_per_dir;
       const int m_blk = r1 / q.n_blocks, n_blk = r1 - m_blk * q.n_blocks;
       const int t = (d & 1) == 0 ? s : p.T - 1 - s;
-      if (q.prefetch && s > 0 && n_blk * BN < p.N) {
-        // pull this tile's previous cell state (fp32 [128 x BN/4], seen by the map as bf16 pairs) from HBM into L2 now:
-        // the row-per-thread epilogue loads it one tile (~17 us) later and then finds it there
-        for (int c = 0; c < BN / 128; ++c)
-          tma_prefetch_4d(&tmC, 2 * (n_blk * (BN / 4)) + c * 64, m_blk * BM, s, d);
-      }
       for (int kb = 0; kb < q.kb1; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1u);
         uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
@@ -858,7 +888,8 @@ constexpr int kBwdThreads = 128 + 32 * kBwdEpiWarps;
 constexpr int kBwdStages = 4;
 constexpr int kBwdBN = 128;
 constexpr int kBwdStageBytes = BM * BK * 2 + kBwdBN * BK * 2;
-constexpr int kBwdSmemBytes = kBwdStages * kBwdStageBytes + 1024 + 256;
+constexpr int kBwdOutBytes = kBwdEpiWarps * 32 * 128;      // per epilogue warp: 32 rows x 128 B of gate gradients (2 unit groups)
+constexpr int kBwdSmemBytes = kBwdStages * kBwdStageBytes + 1024 + 256 + kBwdOutBytes;
 
 __device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&r)[8]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -868,7 +899,7 @@ __device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&r)[8]) {
 
 __global__ void __launch_bounds__(kBwdThreads, 1)
 lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmWhh,
-                    const __grid_constant__ CUtensorMap tmC, const GemmParams p, const LstmSeqParams q) {
+                    const GemmParams p, const LstmSeqParams q) {
   constexpr int BN = kBwdBN;
   constexpr int STAGES = kBwdStages;
   constexpr int A_BYTES = BM * BK * 2;
@@ -879,6 +910,7 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_consta
   uint64_t* tfull_bar = empty_bar + STAGES;   // [2]
   uint64_t* tempty_bar = tfull_bar + 2;       // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint8_t* out_stage = smem + STAGES * kBwdStageBytes + 256;      // [16 warps][32 rows][128 B], 16-byte pieces XOR-swizzled
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -912,19 +944,6 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_consta
       const int m_blk = r1 / q.n_blocks, n_blk = r1 - m_blk * q.n_blocks;
       const int s1 = p.T - 1 - k1;                       // the step processed before this one (its dgates are the A operand)
       const int t1 = (d & 1) == 0 ? s1 : p.T - 1 - s1;
-      if (q.prefetch) {
-        // pull the cell epilogue's operands of THIS tile (activated gates of step s, c_{s}, c_{s+1}) from HBM into L2 now:
-        // the row-per-thread epilogue reads them ~one tile later in 16-byte pieces 12 KB apart, which DRAM serves badly
-        // and L2 serves well; as TMA boxes they arrive as whole 128-byte row segments
-        const int s = s1 - 1;
-        const int t = (d & 1) == 0 ? s : p.T - 1 - s;
-        const int units = min(BN, H - n_blk * BN);
-        for (int c = 0; c < units / 16; ++c) tma_prefetch_4d(&tmG, d * 4 * H + 4 * n_blk * BN + c * 64, m_blk * BM, t, 0);
-        for (int c = 0; c < units / 32; ++c) {
-          tma_prefetch_4d(&tmC, 2 * n_blk * BN + c * 64, m_blk * BM, s, d);
-          tma_prefetch_4d(&tmC, 2 * n_blk * BN + c * 64, m_blk * BM, s + 1, d);
-        }
-      }
       if (k1 > 0) {
         wait_flag(q.flags + d * q.m_blocks + m_blk, kBwdEpiWarps * q.n_blocks * k1, q.error);
         fence_proxy_async_global();
@@ -992,7 +1011,12 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_consta
       const int j_base = n_blk * BN + chunk * 32;
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + static_cast<uint32_t>(as * BN + chunk * 32);
       // one 8-unit group at a time (8 accumulator registers live instead of 32); the accumulator stage is handed back to
-      // the MMA warp after the last group's load — the cell epilogue, not the MMA, is this kernel's critical resource
+      // the MMA warp after the last group's load — the cell epilogue, not the MMA, is this kernel's critical resource.
+      // Gate gradients go to the standard [T][S][D*4H] layout (TMA / wgrad operand): two groups (128 B per row) are
+      // collected in this warp's swizzled shared-memory tile and written as whole 128-byte lines, 4 rows per instruction.
+      const int t = (d & 1) == 0 ? s : p.T - 1 - s;
+      const uint32_t ost = smem_u32(out_stage + e * (32 * 128));
+      __nv_bfloat16* dgrow = p.dgates + ((long long)t * p.M + m_blk * BM + qd * 32) * p.gates_ld + (long long)d * p.gates_dir;
 #pragma unroll 1
       for (int g = 0; g < 4; ++g) {
         uint32_t r[8];
@@ -1003,11 +1027,37 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_consta
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty_bar[as]);
         }
+        uint4 gout[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) gout[u] = make_uint4(0, 0, 0, 0);
         if (seq < p.M && j_base + g * 8 < H) {
           float dh[8];
 #pragma unroll
           for (int u = 0; u < 8; ++u) dh[u] = __uint_as_float(r[u]);
-          lstm_cell_bwd8<true>(p, d, s, seq, j_base + g * 8, dh);
+          lstm_cell_bwd8<true>(p, d, s, seq, j_base + g * 8, dh, gout);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int piece = (g & 1) * 4 + u;
+          const uint32_t a = ost + lane * 128 + ((piece ^ (lane & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(gout[u].x), "r"(gout[u].y), "r"(gout[u].z), "r"(gout[u].w) : "memory");
+        }
+        if (g & 1) {
+          __syncwarp();
+          const int col = 4 * (j_base + (g - 1) * 8);            // first gate column of the group pair
+          if (j_base + (g - 1) * 8 < H) {
+            const bool second = j_base + g * 8 < H;               // H % 16 == 8 never happens (H % 64 == 0), kept for safety
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int row = it * 4 + (lane >> 3), piece = lane & 7;
+              uint4 v;
+              const uint32_t a = ost + row * 128 + ((piece ^ (row & 7)) << 4);
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+              if (m_blk * BM + qd * 32 + row < p.M && (piece < 4 || second))
+                *reinterpret_cast<uint4*>(dgrow + (long long)row * p.gates_ld + col + piece * 8) = v;
+            }
+          }
+          __syncwarp();
         }
       }
       fence_proxy_async_global();
@@ -1029,15 +1079,26 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_consta
 }
 
 // First (s == T-1) backward step of the LSTM: no recurrent product yet, dh comes from the encoder output gradient.
+// kSeq: whole-sequence path — blocked gates / c_hist / dc in, gate gradients out to p.dgates (standard layout).
+template <bool kSeq>
 __global__ void lstm_bwd_first_kernel(const GemmParams p, const __nv_bfloat16* __restrict__ dh_last, long long dh_ld) {
   const int H = p.N, S = p.M;
   const int groups = H / 8;
   const long long total = (long long)p.batch * S * groups;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int jg = (int)(i % groups);
-    const long long rest = i / groups;
-    const int seq = (int)(rest % S);
-    const int dir = (int)(rest / S);
+    // per-step path: unit groups fastest (row-major tensors); whole-sequence path: sequences fastest (blocked tensors)
+    int jg, seq, dir;
+    if (kSeq) {
+      seq = (int)(i % S);
+      const long long rest = i / S;
+      jg = (int)(rest % groups);
+      dir = (int)(rest / groups);
+    } else {
+      jg = (int)(i % groups);
+      const long long rest = i / groups;
+      seq = (int)(rest % S);
+      dir = (int)(rest / S);
+    }
     float dh[8];
     if (dh_last != nullptr) {
       uint4 v = *reinterpret_cast<const uint4*>(dh_last + (long long)seq * dh_ld + (long long)dir * H + jg * 8);
@@ -1051,7 +1112,14 @@ __global__ void lstm_bwd_first_kernel(const GemmParams p, const __nv_bfloat16* _
 #pragma unroll
       for (int u = 0; u < 8; ++u) dh[u] = 0.f;
     }
-    lstm_cell_bwd8<false>(p, dir, p.s, seq, jg * 8, dh);
+    uint4 gout[4];
+    lstm_cell_bwd8<kSeq>(p, dir, p.s, seq, jg * 8, dh, gout);
+    if (kSeq) {
+      const int t = (dir & 1) == 0 ? p.s : p.T - 1 - p.s;
+      __nv_bfloat16* o = p.dgates + ((long long)t * S + seq) * p.gates_ld + (long long)dir * p.gates_dir + 32 * jg;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) reinterpret_cast<uint4*>(o)[q] = gout[q];
+    }
   }
 }
 
@@ -1246,11 +1314,6 @@ int gemm_dispatch(const dvgr_operand& A, const dvgr_operand& B, GemmParams p, in
   return set_error("gemm: operand layout combination (A MN-major, B K-major) is not instantiated");
 }
 
-static int lstm_prefetch_knob() {
-  static const int v = getenv("DVGR_LSTM_PREFETCH") ? atoi(getenv("DVGR_LSTM_PREFETCH")) : 1;
-  return v;
-}
-
 // Whole-sequence fused LSTM forward (lstm_seq_fwd_kernel). p carries the EPI_LSTM fields with M = S, N = 4H, batch = D.
 int lstm_seq_fwd_launch(const dvgr_operand& X, const dvgr_operand& Wih, const dvgr_operand& Hh, const dvgr_operand& Whh,
                         GemmParams p, int K1, const float* bias, int* sync, cudaStream_t stream) {
@@ -1259,18 +1322,13 @@ int lstm_seq_fwd_launch(const dvgr_operand& X, const dvgr_operand& Wih, const dv
   const int H = p.N / 4;
   if (p.N % BN != 0) return set_error("lstm_seq_fwd: 4H = %d must be a multiple of %d", p.N, BN);
   if (K1 <= 0 || K1 % 8 != 0) return set_error("lstm_seq_fwd: K1 = %d must be a positive multiple of 8", K1);
-  CUtensorMap tx, twih, th, twhh, tc;
+  CUtensorMap tx, twih, th, twhh;
   int rc = make_tensor_map(&tx, X, 64, BM);
   if (!rc) rc = make_tensor_map(&twih, Wih, 64, BN);
   if (!rc) rc = make_tensor_map(&th, Hh, 64, BM);
   if (!rc) rc = make_tensor_map(&twhh, Whh, 64, BN);
-  // c_hist [D][T+1][S][H] fp32 viewed as bf16 pairs (TMA only moves bytes here: L2 prefetch of the epilogue's operand)
-  dvgr_operand Cop = Hh;
-  Cop.ptr = p.c_hist;
-  Cop.dims[0] = Hh.dims[0] * 2;
-  for (int i = 1; i < 4; ++i) Cop.strides[i] = Hh.strides[i] * 2;
-  if (!rc) rc = make_tensor_map(&tc, Cop, 64, BM);
   if (rc) return rc;
+  p.RB = (p.M + 31) / 32;
   LstmSeqParams q;
   q.kb1 = (K1 + BK - 1) / BK;
   q.kb2 = H / BK;
@@ -1279,7 +1337,6 @@ int lstm_seq_fwd_launch(const dvgr_operand& X, const dvgr_operand& Wih, const dv
   q.bias = bias;
   q.flags = sync;
   q.error = sync + (long long)p.batch * q.m_blocks;
-  q.prefetch = lstm_prefetch_knob();
   auto kern = lstm_seq_fwd_kernel<BN>;
   const int smem_bytes = Cfg::SMEM_BYTES - Cfg::STAGING_BYTES;
   static int max_resident = 0;
@@ -1294,7 +1351,7 @@ int lstm_seq_fwd_launch(const dvgr_operand& X, const dvgr_operand& Wih, const dv
   const long long tiles = (long long)q.m_blocks * q.n_blocks * p.batch * p.T;
   const int grid = (int)std::min<long long>(tiles, std::min(max_resident, num_sms()));
   if (grid <= 0) return 0;
-  kern<<<grid, kSeqThreads, smem_bytes, stream>>>(tx, twih, th, twhh, tc, p, q);
+  kern<<<grid, kSeqThreads, smem_bytes, stream>>>(tx, twih, th, twhh, p, q);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("lstm_seq_fwd launch failed: %s", cudaGetErrorString(e));
   return 0;
@@ -1305,16 +1362,9 @@ int lstm_seq_bwd_launch(const dvgr_operand& G, const dvgr_operand& Whh, GemmPara
   const int H = p.N;
   if (H % 64 != 0) return set_error("lstm_seq_bwd: H = %d must be a multiple of 64", H);
   if (p.T < 2) return 0;
-  CUtensorMap tg, tw, tc;
+  CUtensorMap tg, tw;
   int rc = make_tensor_map(&tg, G, 64, BM);
   if (!rc) rc = make_tensor_map(&tw, Whh, 64, 64);
-  // c_hist [D][T+1][S][H] fp32 viewed as bf16 pairs: only used for L2 prefetches of the epilogue's operands
-  dvgr_operand Cop;
-  memset(&Cop, 0, sizeof(Cop));
-  Cop.ptr = p.c_hist; Cop.major = 0; Cop.ndim = 4;
-  Cop.dims[0] = 2LL * H; Cop.dims[1] = p.M; Cop.dims[2] = p.T + 1; Cop.dims[3] = p.batch;
-  Cop.strides[0] = 1; Cop.strides[1] = 2LL * H; Cop.strides[2] = 2LL * H * p.M; Cop.strides[3] = 2LL * H * p.M * (p.T + 1);
-  if (!rc) rc = make_tensor_map(&tc, Cop, 64, BM);
   if (rc) return rc;
   LstmSeqParams q;
   q.kb1 = 4 * H / BK;
@@ -1324,7 +1374,6 @@ int lstm_seq_bwd_launch(const dvgr_operand& G, const dvgr_operand& Whh, GemmPara
   q.bias = nullptr;
   q.flags = sync;
   q.error = sync + (long long)p.batch * q.m_blocks;
-  q.prefetch = lstm_prefetch_knob();
   static int max_resident = 0;
   if (max_resident == 0) {
     cudaError_t e = cudaFuncSetAttribute(lstm_seq_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmemBytes);
@@ -1337,7 +1386,7 @@ int lstm_seq_bwd_launch(const dvgr_operand& G, const dvgr_operand& Whh, GemmPara
   const long long tiles = (long long)q.m_blocks * q.n_blocks * p.batch * (p.T - 1);
   const int grid = (int)std::min<long long>(tiles, std::min(max_resident, num_sms()));
   if (grid <= 0) return 0;
-  lstm_seq_bwd_kernel<<<grid, kBwdThreads, kBwdSmemBytes, stream>>>(tg, tw, tc, p, q);
+  lstm_seq_bwd_kernel<<<grid, kBwdThreads, kBwdSmemBytes, stream>>>(tg, tw, p, q);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("lstm_seq_bwd launch failed: %s", cudaGetErrorString(e));
   return 0;
@@ -1347,7 +1396,10 @@ int lstm_bwd_first(const GemmParams& p, const void* dh_last, long long dh_ld, cu
   const long long total = (long long)p.batch * p.M * (p.N / 8);
   if (total <= 0) return 0;
   int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 8);
-  lstm_bwd_first_kernel<<<blocks, 256, 0, stream>>>(p, reinterpret_cast<const __nv_bfloat16*>(dh_last), dh_ld);
+  if (p.RB > 0)
+    lstm_bwd_first_kernel<true><<<blocks, 256, 0, stream>>>(p, reinterpret_cast<const __nv_bfloat16*>(dh_last), dh_ld);
+  else
+    lstm_bwd_first_kernel<false><<<blocks, 256, 0, stream>>>(p, reinterpret_cast<const __nv_bfloat16*>(dh_last), dh_ld);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("lstm_bwd_first launch failed: %s", cudaGetErrorString(e));
   return 0;

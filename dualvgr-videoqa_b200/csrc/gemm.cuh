@@ -57,6 +57,27 @@ struct GemmParams {
   __nv_bfloat16* seq_out;   // optional [S][T][seq_out_ld] per-step hidden output (zero at padded steps)
   long long seq_out_ld;
   int T, s;
+  // ---- whole-sequence kernels (lstm_seq_*): tensors that only the cell epilogues touch use the blocked layout below
+  int RB;                   // ceil(S / 32) row blocks; 0 = standard layouts (per-step launches)
+  __nv_bfloat16* dgates;    // backward output [T][S][gates_ld] (standard layout: TMA / wgrad operand); null = in place
 };
+
+// Blocked ("warp tile") layout of the activated gates, the cell states and the running cell gradient in the whole-sequence
+// kernels. A warp of a cell epilogue owns 32 consecutive sequences (TMEM lanes) x 8 hidden units; in row-major storage its
+// 16-byte pieces are 12 KB apart, so every warp load / store touched 32 separate sectors (ncu: 32 sectors per request,
+// L1/LSU wavefronts the top unit of both kernels). Here the pieces of such a tile are stored [piece][row][16 B]: one warp
+// instruction = 512 contiguous bytes = 4 full lines.
+//   gates_blk [T][D][RB][H/8][4 pieces][32 rows][8 bf16]     piece q = units 2q, 2q+1 x (i, f, g, o)
+//   c_blk     [D][T+1][RB][H/8][2 pieces][32 rows][4 f32]    piece q = units 4q .. 4q+3
+//   dc_blk    [D][RB][H/8][2 pieces][32 rows][4 f32]
+__host__ __device__ inline long long lstm_blk_gates(int t, int d, int D, int RB, int UG, int rb, int ug) {
+  return ((((long long)t * D + d) * RB + rb) * UG + ug) * 1024;       // elements (bf16); piece q at + q * 256, row r at + r * 8
+}
+__host__ __device__ inline long long lstm_blk_c(int d, int slot, int T, int RB, int UG, int rb, int ug) {
+  return ((((long long)d * (T + 1) + slot) * RB + rb) * UG + ug) * 256;  // elements (f32); piece q at + q * 128, row r at + r * 4
+}
+__host__ __device__ inline long long lstm_blk_dc(int d, int RB, int UG, int rb, int ug) {
+  return (((long long)d * RB + rb) * UG + ug) * 256;
+}
 
 }  // namespace dvgr

@@ -176,10 +176,43 @@ def lstm_fwd(gates, whh, seq_len=None, want_seq=False):
     return h_hist, c_hist, h_last, seq_out
 
 
+# ---- blocked layout of the whole-sequence LSTM kernels (include/dualvgr_b200.h: dvgr_lstm_seq_fwd). The helpers below are
+#      pure re-layouts (views / permutes) used by the tests and debugging tools; the train step never calls them.
+def lstm_unblock_gates(gates_blk, S):
+    """[T, D, RB, H/8, 4, 32, 8] bf16 -> [T, S, D*4H] (gate-interleaved columns 4*j + {i,f,g,o})."""
+    T, D, RB, UG = gates_blk.shape[:4]
+    return gates_blk.permute(0, 2, 5, 1, 3, 4, 6).reshape(T, RB * 32, D * UG * 32)[:, :S]
+
+
+def lstm_block_gates(gates, D):
+    """[T, S, D*4H] -> blocked [T, D, RB, H/8, 4, 32, 8] (rows padded to a multiple of 32 with zeros)."""
+    T, S, G = gates.shape
+    RB, UG = (S + 31) // 32, G // D // 32
+    g = torch.zeros((T, RB * 32, G), dtype=gates.dtype, device=gates.device)
+    g[:, :S] = gates
+    return g.view(T, RB, 32, D, UG, 4, 8).permute(0, 3, 1, 4, 5, 2, 6).contiguous()
+
+
+def lstm_unblock_c(c_blk, S):
+    """[D, T+1, RB, H/8, 2, 32, 4] f32 -> [D, T+1, S, H]."""
+    D, T1, RB, UG = c_blk.shape[:4]
+    return c_blk.permute(0, 1, 2, 5, 3, 4, 6).reshape(D, T1, RB * 32, UG * 8)[:, :, :S]
+
+
+def lstm_block_c(c, ):
+    """[D, T+1, S, H] -> blocked [D, T+1, RB, H/8, 2, 32, 4]."""
+    D, T1, S, H = c.shape
+    RB, UG = (S + 31) // 32, H // 8
+    x = torch.zeros((D, T1, RB * 32, H), dtype=c.dtype, device=c.device)
+    x[:, :, :S] = c
+    return x.view(D, T1, RB, 32, UG, 2, 4).permute(0, 1, 2, 4, 5, 3, 6).contiguous()
+
+
 def lstm_seq_fwd(x, wih, whh, bias, K1=None, seq_len=None, want_seq=False):
     """Whole-sequence fused forward (ONE persistent launch): x [T,S,ld] bf16 time-major, wih [D*4H, ld'] bf16 and
     whh [D,4H,H] bf16 gate-interleaved, bias [D*4H] f32 (b_ih + b_hh, interleaved).
-    Returns (gates [T,S,D*4H] bf16 ACTIVATED, h_hist, c_hist, h_last, seq_out | None, sync) like gemm + lstm_fwd;
+    Returns (gates_blk ACTIVATED [T,D,RB,H/8,4,32,8] bf16, h_hist [D,T+1,S,H] bf16, c_blk [D,T+1,RB,H/8,2,32,4] f32,
+    h_last [S,D*H], seq_out | None, sync); gates_blk / c_blk are in the kernels' blocked layout (lstm_unblock_*);
     sync[-1] is the kernel's sticky dependency-timeout flag (0 in a healthy run)."""
     _check_cuda(x, wih, whh, bias)
     T, S, ldx = x.shape
@@ -188,9 +221,10 @@ def lstm_seq_fwd(x, wih, whh, bias, K1=None, seq_len=None, want_seq=False):
     assert x.dtype == BF16 and wih.dtype == BF16 and whh.dtype == BF16 and bias.dtype == F32
     assert x.is_contiguous() and wih.stride(1) == 1 and whh.is_contiguous() and wih.shape[0] == D * H4 and H4 == 4 * H
     dev = x.device
-    gates = torch.empty((T, S, D * H4), dtype=BF16, device=dev)
+    RB, UG = (S + 31) // 32, H // 8
+    gates = torch.empty((T, D, RB, UG, 4, 32, 8), dtype=BF16, device=dev)
     h_hist = torch.empty((D, T + 1, S, H), dtype=BF16, device=dev)
-    c_hist = torch.empty((D, T + 1, S, H), dtype=F32, device=dev)
+    c_hist = torch.empty((D, T + 1, RB, UG, 2, 32, 4), dtype=F32, device=dev)
     h_hist[:, 0].zero_()
     c_hist[:, 0].zero_()
     h_last = torch.empty((S, D * H), dtype=BF16, device=dev)
@@ -214,15 +248,22 @@ def lstm_seq_fwd(x, wih, whh, bias, K1=None, seq_len=None, want_seq=False):
 
 
 def lstm_bwd(gates, whh, h_hist, c_hist, dh_last, seq_len=None, dh_seq=None, whole_sequence=False):
-    """Backward through the T steps; `gates` (activated gates from lstm_fwd) is overwritten in place with the
-    pre-activation gate gradients [T,S,D*4H], which feed the W_ih / W_hh / bias wgrads.
-    whole_sequence: one persistent launch for steps T-2..0 (dvgr_lstm_seq_bwd) instead of T step launches; returns
-    (gates, sync) with sync[-1] the sticky dependency-timeout flag."""
+    """Backward through the T steps.
+    per-step path: `gates` [T,S,D*4H] (activated gates from lstm_fwd) is overwritten in place with the pre-activation gate
+    gradients, which feed the W_ih / W_hh / bias wgrads; returns gates.
+    whole_sequence: one persistent launch for steps T-2..0 (dvgr_lstm_seq_bwd); `gates` / `c_hist` are the BLOCKED tensors of
+    lstm_seq_fwd; returns (dgates [T,S,D*4H] bf16, sync) with sync[-1] the sticky dependency-timeout flag."""
     _check_cuda(gates, whh, dh_last)
-    T, S, G = gates.shape
     D, H4, H = whh.shape
+    if whole_sequence:
+        T, S = gates.shape[0], h_hist.shape[2]
+        RB, UG = (S + 31) // 32, H // 8
+        assert tuple(gates.shape) == (T, D, RB, UG, 4, 32, 8) and tuple(c_hist.shape) == (D, T + 1, RB, UG, 2, 32, 4)
+        dc = torch.zeros((D, RB, UG, 2, 32, 4), dtype=torch.float32, device=gates.device)
+    else:
+        T, S, G = gates.shape
+        dc = torch.zeros((D, S, H), dtype=torch.float32, device=gates.device)
     a = _lstm_args(gates, whh, h_hist, c_hist, S, H, T, D)
-    dc = torch.zeros((D, S, H), dtype=torch.float32, device=gates.device)
     a.dc = dc.data_ptr()
     if dh_last is not None:
         assert dh_last.dtype == torch.bfloat16 and dh_last.stride(-1) == 1
@@ -235,9 +276,10 @@ def lstm_bwd(gates, whh, h_hist, c_hist, dh_last, seq_len=None, dh_seq=None, who
         a.dh_seq, a.seq_out_ld = dh_seq.data_ptr(), D * H
     st = _stream()
     if whole_sequence:
+        dgates = torch.empty((T, S, D * H4), dtype=BF16, device=gates.device)
         sync = torch.zeros((int(_lib.lib.dvgr_lstm_seq_sync_words(S, D)),), dtype=torch.int32, device=gates.device)
-        _lib.check(_lib.lstm_seq_bwd(ctypes.byref(a), _ptr(sync), st), "dvgr_lstm_seq_bwd")
-        return gates, sync
+        _lib.check(_lib.lstm_seq_bwd(ctypes.byref(a), _ptr(dgates), _ptr(sync), st), "dvgr_lstm_seq_bwd")
+        return dgates, sync
     for s in range(T - 1, -1, -1):
         a.s = s
         _lib.check(_lib.lstm_step_bwd(ctypes.byref(a), st), "dvgr_lstm_step_bwd")

@@ -117,14 +117,19 @@ int dvgr_lstm_step_bwd(const dvgr_lstm_args* args, void* stream);
  * (model/Preprocessing.py:227 `self.encoder(...)` = nn.LSTM forward; :97-101,112-123 for the question BiLSTMs):
  *   per (step, direction, 128-sequence block, 256-gate-column block) tile: x_t W_ih^T + h_s W_hh^T on tensor cores
  *   (K = K1 + H in one accumulator), then bias + cell update in the epilogue. The [T][S][D*4H] pre-activations never
- *   reach HBM; `lstm.gates` receives the ACTIVATED gates only (what dvgr_lstm_step_bwd consumes). Steps are chained
- *   inside the launch by per-(direction, block) completion counters, not by kernel boundaries.
+ *   reach HBM. Steps are chained inside the launch by per-(direction, block) completion counters, not by kernel boundaries.
  *   x    [T][S][x_ld] bf16 time-major input (K1 valid columns, K1 % 8 == 0)
  *   wih  [D*4H][wih_ld] bf16, rows gate-interleaved like whh (dvgr_cast_rows with lstm_H)
  *   bias [D*4H] f32 = b_ih + b_hh, gate-interleaved
  *   sync [dvgr_lstm_seq_sync_words(S, D)] int32, ZERO on entry; the last word is a sticky error flag (stays 0 unless a
  *        dependency poll timed out, which only a protocol violation can cause)
- * h_hist / c_hist slot 0 must hold the initial state (zeros); `lstm.s` is ignored. Requires 4H % 256 == 0. */
+ * BLOCKED LAYOUT. The tensors that only the cell epilogues of the two whole-sequence calls touch are stored as
+ * [piece][row] warp tiles (32 sequences x 8 hidden units; RB = ceil(S / 32) row blocks), so that every warp access is 512
+ * contiguous bytes instead of 32 scattered 16-byte pieces:
+ *   lstm.gates  [T][D][RB][H/8][4][32][8] bf16  ACTIVATED gates out (piece q = units 2q, 2q+1 x {i,f,g,o})
+ *   lstm.c_hist [D][T+1][RB][H/8][2][32][4] f32 (piece q = units 4q..4q+3); slot 0 = initial state (zeros)
+ *   lstm.dc     [D][RB][H/8][2][32][4] f32      (backward)
+ * h_hist keeps the standard [D][T+1][S][H] layout (it is a TMA / wgrad operand). `lstm.s` is ignored. 4H % 256 == 0. */
 typedef struct dvgr_lstm_seq_args {
   dvgr_lstm_args lstm;
   const void* x;
@@ -139,9 +144,11 @@ int dvgr_lstm_seq_sync_words(int S, int ndir);
 int dvgr_lstm_seq_fwd(const dvgr_lstm_seq_args* args, void* stream);
 /* Whole backward pass of the recurrence (autograd of nn.LSTM at model/Preprocessing.py:227 / :97-101): the cell backward
  * of step T-1 (elementwise) followed by ONE persistent launch for steps T-2 ... 0 (dh_s = dgates_{s+1} W_hh on tensor
- * cores, cell backward in the epilogue, steps chained by completion counters). Equivalent to calling
- * dvgr_lstm_step_bwd for s = T-1 ... 0; `sync` as for dvgr_lstm_seq_fwd (zero on entry); `args->s` is ignored. */
-int dvgr_lstm_seq_bwd(const dvgr_lstm_args* args, int* sync, void* stream);
+ * cores, cell backward in the epilogue, steps chained by completion counters). Consumes the BLOCKED gates / c_hist of
+ * dvgr_lstm_seq_fwd and a blocked, zeroed dc; writes the pre-activation gate gradients to `dgates` [T][S][D*4H] bf16
+ * (standard layout: the operand of the W_ih / W_hh / bias gradients). `sync` as for dvgr_lstm_seq_fwd (zero on entry);
+ * `args->s` is ignored. */
+int dvgr_lstm_seq_bwd(const dvgr_lstm_args* args, void* dgates, int* sync, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Video-based multi-view graph attention (punishGAT): model/GraphNN.py:95-113 for all heads of a graph, plus the head
@@ -152,8 +159,9 @@ int dvgr_lstm_seq_bwd(const dvgr_lstm_args* args, int* sync, void* stream);
  *   avec  [heads][2*Dh+1] f32 : a_k[:Dh] | a_k[Dh:] | c_k   (attention_k.a.weight, attention_k.a.bias)
  *   adj   [N][N] f32        : edge iff adj > 0 (a fully masked row yields uniform attention, as in the reference)
  *   out   [B*N][ld_out] bf16
- * Backward additionally needs out (forward result), dout, and writes dwh, dgate [B][N], davec partials [B][heads][2*Dh+1]
- * (sum over B with dvgr_colsum).
+ * Backward additionally needs out (forward result), dout, and writes dwh, dgate [B][N] (zeroed inside the call: the
+ * tensor-core path adds the partial sums of its two head-pair CTAs), davec partials [B][heads][2*Dh+1] (sum over B with
+ * dvgr_colsum). D = 768 with 4 heads and N <= 32 (forward: <= 64) take the mma.sync fast path; DVGR_GAT_FAST=0 disables it.
  * ------------------------------------------------------------------------------------------------------------------ */
 typedef struct dvgr_gat_graph {
   const void* wh;

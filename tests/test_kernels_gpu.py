@@ -94,13 +94,16 @@ def test_lstm_fused_recurrence(ops, T, S, H, D):
     ops.lstm_bwd(g, whh, h_hist, c_hist, dh)
     assert rel(g, gxr.grad) < 2e-2
     # whole-sequence persistent backward (ONE launch for steps T-2..0, cross-CTA step chaining) = the per-step path
-    g2, sync = ops.lstm_bwd(g_act.clone(), whh, h_hist, c_hist, dh, whole_sequence=True)
+    # (it consumes the kernels' blocked layout of the activated gates / cell states: re-layout the per-step tensors)
+    gb, cb = ops.lstm_block_gates(g_act, D), ops.lstm_block_c(c_hist)
+    assert torch.equal(ops.lstm_unblock_gates(gb, S), g_act) and torch.equal(ops.lstm_unblock_c(cb, S), c_hist)
+    g2, sync = ops.lstm_bwd(gb, whh, h_hist, cb, dh, whole_sequence=True)
     torch.cuda.synchronize()
     assert int(sync[-1]) == 0, "dependency poll timed out"
     assert int(sync[:-1].min()) == int(sync[:-1].max()) == 16 * ((H + 127) // 128) * (T - 1)
     assert rel(g2, gxr.grad) < 2e-2
     assert torch.equal(g2, g)          # same arithmetic in the same order: bit-identical to the step launches
-    g3, _ = ops.lstm_bwd(g_act.clone(), whh, h_hist, c_hist, dh, whole_sequence=True)
+    g3, _ = ops.lstm_bwd(gb, whh, h_hist, cb, dh, whole_sequence=True)
     assert torch.equal(g3, g2)
 
 
@@ -137,14 +140,16 @@ def test_lstm_whole_sequence_fused_forward(ops, T, S, H, D, K1):
     assert int(sync[-1]) == 0, "dependency poll timed out"
     assert int(sync[:-1].min()) == int(sync[:-1].max()) == 16 * (4 * H // 256) * T     # every (warp, tile) published once
     assert rel(h_last, ref_h) < 1e-2
-    assert rel(gates, ref_g) < 1e-2
+    assert rel(ops.lstm_unblock_gates(gates, S), ref_g) < 1e-2          # activated gates, stored in the blocked layout
     # the per-step path on the same operands agrees (it rounds the pre-activations to bf16 first, so not bit-equal)
     g2 = ops.linear_fwd(x.view(T * S, K1), wih, bias=bias.cuda()).view(T, S, D * 4 * H)
     _, c2, h2, _ = ops.lstm_fwd(g2, whh)
-    assert rel(h_last, h2) < 1e-2 and rel(c_hist, c2) < 1e-2
+    assert rel(h_last, h2) < 1e-2 and rel(ops.lstm_unblock_c(c_hist, S), c2) < 1e-2
     # idempotence: a second launch on fresh sync words reproduces the result bit for bit (no race on the step chain)
     gates_b, _, c_b, h_b, _, _ = ops.lstm_seq_fwd(x, wih, whh, bias.cuda())
-    assert torch.equal(h_b, h_last) and torch.equal(gates_b, gates) and torch.equal(c_b, c_hist)
+    assert torch.equal(h_b, h_last)
+    assert torch.equal(ops.lstm_unblock_gates(gates_b, S), ops.lstm_unblock_gates(gates, S))
+    assert torch.equal(ops.lstm_unblock_c(c_b, S), ops.lstm_unblock_c(c_hist, S))
 
 
 @pytest.mark.parametrize("B,N,p", [(3, 20, 0.0), (5, 8, 0.0), (2, 33, 0.0)])

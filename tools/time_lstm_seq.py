@@ -47,18 +47,19 @@ for name, T, S, H, D, K1 in (("appearance", 16, 5120, 384, 2, 2048), ("question"
     # backward: per-step launches vs the whole-sequence persistent launch (same operands; gates restored each run)
     gates_act, h_hist, c_hist = res["f"][0], res["f"][1], res["f"][2]
     dh = (torch.randn(S, D * H, device="cuda") * 0.1).to(BF16)
-    work = gates_act.clone()
+    g_std, c_std = ops.lstm_unblock_gates(gates_act, S).contiguous(), ops.lstm_unblock_c(c_hist, S).contiguous()
+    work = g_std.clone()
 
     def bwd_steps():
-        work.copy_(gates_act)
-        ops.lstm_bwd(work, whh, h_hist, c_hist, dh)
+        work.copy_(g_std)
+        ops.lstm_bwd(work, whh, h_hist, c_std, dh)
 
     def bwd_seq():
-        work.copy_(gates_act)
-        res["b"] = ops.lstm_bwd(work, whh, h_hist, c_hist, dh, whole_sequence=True)
+        work.copy_(g_std)
+        res["b"] = ops.lstm_bwd(gates_act, whh, h_hist, c_hist, dh, whole_sequence=True)
 
     def copy_only():
-        work.copy_(gates_act)
+        work.copy_(g_std)
 
     mc, _ = timeit(copy_only)
     ms_, _ = timeit(bwd_steps)

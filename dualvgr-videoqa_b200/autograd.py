@@ -674,13 +674,7 @@ class AuxLossFn(Function):
         of launching four [B,N,D] multiplications by a scalar that is 1."""
         ctx.unit_grad = bool(unit_grad)
         ca, cm, aq, mq = (_c(t.float()) for t in (ca, cm, aq, mq))
-        B, N, D = ca.shape
-        d_ca, d_cm = torch.zeros_like(ca), torch.zeros_like(cm)       # two addends each -> atomic adds are deterministic
-        d_aq, d_mq = torch.empty_like(aq), torch.empty_like(mq)
-        jobs = [dict(x=ca, y=cm, mode=0, coef=coef_com, dx=d_ca, dy=d_cm, acc_x=2, acc_y=2),
-                dict(x=aq, y=ca, mode=1, coef=coef_dep, dx=d_aq, dy=d_ca, acc_x=0, acc_y=2),
-                dict(x=mq, y=cm, mode=1, coef=coef_dep, dx=d_mq, dy=d_cm, acc_x=0, acc_y=2)]
-        vals = ops.pair_loss_multi(jobs, B, N, D, ca)
+        vals, (d_ca, d_cm, d_aq, d_mq) = ops.aux_loss_unit(ca, cm, aq, mq, coef_com, coef_dep)
         ctx.save_for_backward(d_ca, d_cm, d_aq, d_mq)
         ctx.mark_non_differentiable(vals)
         return vals.sum(), vals

@@ -274,6 +274,225 @@ __global__ void __launch_bounds__(kLossThreads) pair_grad_kernel(const PairParam
   }
 }
 
+// ------------------------------------------------------------------------------------------------ tensor-centric unit losses
+// The three loss terms of one DualVGR unit (train.py:148-154) share their operands: common(ca, cm), HSIC(aq, ca),
+// HSIC(mq, cm). The pair-centric kernels above load every operand once per PAIR (6 tile loads per pass, two tiles per
+// CTA, atomics where a tensor belongs to two pairs). Here the unit of work is a TENSOR:
+//   pass 1 (aux_gram_kernel): centred Gram partials of ca, cm, aq, mq — one tile per CTA, 4 tile loads per pass
+//   pass 2 (aux_grad_kernel): one CTA = (video, tensor, 256-column chunk): it sums the partial Grams it needs, rebuilds the
+//          N x N algebra, and produces the COMPLETE gradient of its tensor — common part and HSIC part from the same
+//          right-operand fragments — with plain stores (no atomics, no zero-filled accumulation buffers).
+// tensors: 0 = ca (com_app), 1 = cm (com_motion), 2 = aq (aq_fusion), 3 = mq (mq_fusion)
+struct AuxParams {
+  const float* x[4];
+  float* dx[4];
+  float* loss_part;      // [B][3]: coef-scaled common, HSIC(aq, ca), HSIC(mq, cm) of each video
+  float coef_com, coef_dep;
+  int B, N, D, chunks;
+  float* ws;             // [4][B][chunks][N][N]
+};
+
+__device__ __forceinline__ void load_centered_tile(const float* __restrict__ x, int N, int D, int c0, float* t) {
+  const int NP = round16(N);
+  for (int cc = threadIdx.x; cc < kChunk; cc += blockDim.x) {
+    const int c = c0 + cc;
+    float s = 0.f;
+    if (c < D)
+      for (int n = 0; n < N; ++n) s += x[(long long)n * D + c];
+    const float mean = s / N;
+    for (int n = 0; n < N; ++n) t[n * kTS + cc] = (c < D) ? x[(long long)n * D + c] - mean : 0.f;
+    for (int n = N; n < NP; ++n) t[n * kTS + cc] = 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(kLossThreads) aux_gram_kernel(const AuxParams p) {
+  extern __shared__ __align__(16) float sm[];
+  float* tile = sm;   // [NP16][kTS]
+  const int b = blockIdx.x, ts = blockIdx.y, ch = blockIdx.z, N = p.N, D = p.D, NP = round16(N);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = kLossThreads / 32, g = lane >> 2, t = lane & 3;
+  load_centered_tile(p.x[ts] + (long long)b * N * D, N, D, ch * kChunk, tile);
+  __syncthreads();
+  float* out = p.ws + (((long long)ts * p.B + b) * p.chunks + ch) * N * N;
+  const int MT = NP / 16, NT = NP / 8;
+  for (int ot = warp; ot < MT * NT; ot += nwarps) {
+    const int mt = ot / NT, nt = ot - mt * NT;
+    const float* ar = tile + (size_t)(mt * 16 + g) * kTS + t;
+    const float* br = tile + (size_t)(nt * 8 + g) * kTS + t;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+    for (int k0 = 0; k0 < kChunk; k0 += 8)
+      mma_tf32(acc, to_tf32(ar[k0]), to_tf32(ar[8 * kTS + k0]), to_tf32(ar[k0 + 4]), to_tf32(ar[8 * kTS + k0 + 4]),
+               to_tf32(br[k0]), to_tf32(br[k0 + 4]));
+    const int row = mt * 16 + g, col = nt * 8 + 2 * t;
+    if (row < N && col < N) out[row * N + col] = acc[0];
+    if (row < N && col + 1 < N) out[row * N + col + 1] = acc[1];
+    if (row + 8 < N && col < N) out[(row + 8) * N + col] = acc[2];
+    if (row + 8 < N && col + 1 < N) out[(row + 8) * N + col + 1] = acc[3];
+  }
+}
+
+__host__ __device__ inline size_t aux_grad_smem(int N) {
+  const int NP = round16(N), CS = NP + 4;
+  return (size_t)(NP * kTS + 5 * NP * CS + 4 * NP) * sizeof(float);
+}
+
+__global__ void __launch_bounds__(kLossThreads) aux_grad_kernel(const AuxParams p) {
+  extern __shared__ __align__(16) float sm[];
+  const int b = blockIdx.x, ts = blockIdx.y, ch = blockIdx.z, N = p.N, D = p.D, NP = round16(N), CS = NP + 4;
+  float* tile = sm;                         // [NP][kTS]   centred chunk of this tensor
+  float* Cs = tile + NP * kTS;              // [NP][CS]    own centred Gram -> own normalised Gram (ca / cm)
+  float* Co = Cs + NP * CS;                 // [NP][CS]    common partner's Gram (ca <-> cm)
+  float* Ch = Co + NP * CS;                 // [NP][CS]    HSIC partner's centred Gram (ca <-> aq, cm <-> mq)
+  float* Ac = Ch + NP * CS;                 // [NP][CS]    dL/dG_self of the common term (tf32-rounded)
+  float* Ah = Ac + NP * CS;                 // [NP][CS]    2 coef_dep C_partner (tf32-rounded)
+  float* inv_n = Ah + NP * CS;              // [NP] own row norms^-1 ; [NP] partner's
+  float* rdot = inv_n + 2 * NP;             // [NP]
+  __shared__ float red[kLossThreads / 32];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = kLossThreads / 32, g = lane >> 2, t = lane & 3;
+  const bool common = ts < 2;
+  const int other = 1 - ts, hs = common ? ts + 2 : ts - 2;
+  const long long NN = (long long)N * N;
+  const float* gw_s = p.ws + (((long long)ts * p.B + b) * p.chunks) * NN;
+  const float* gw_o = common ? p.ws + (((long long)other * p.B + b) * p.chunks) * NN : nullptr;
+  const float* gw_h = p.ws + (((long long)hs * p.B + b) * p.chunks) * NN;
+  for (int i = warp; i < NP; i += nwarps)
+    for (int j = lane; j < CS; j += 32) {
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+      if (i < N && j < N)
+        for (int k = 0; k < p.chunks; ++k) {
+          s0 += gw_s[k * NN + i * N + j];
+          s2 += gw_h[k * NN + i * N + j];
+          if (common) s1 += gw_o[k * NN + i * N + j];
+        }
+      Cs[i * CS + j] = s0; Co[i * CS + j] = s1; Ch[i * CS + j] = s2;
+      Ac[i * CS + j] = 0.f;
+    }
+  load_centered_tile(p.x[ts] + (long long)b * N * D, N, D, ch * kChunk, tile);
+  __syncthreads();
+  // HSIC value: sum_ij C_self C_partner, reported by the query-side tensors (aq -> column 1, mq -> column 2)
+  float part = 0.f;
+  if (!common)
+    for (int i = warp; i < N; i += nwarps)
+      for (int j = lane; j < N; j += 32) part += Cs[i * CS + j] * Ch[i * CS + j];
+  if (common) {
+    for (int i = tid; i < 2 * N; i += kLossThreads) {
+      const int which = i / N, n = i - which * N;
+      const float* C = which ? Co : Cs;
+      inv_n[which * NP + n] = 1.f / fmaxf(sqrtf(fmaxf(C[n * CS + n], 0.f)), 1e-12f);
+    }
+    __syncthreads();
+    for (int i = warp; i < N; i += nwarps)
+      for (int j = lane; j < N; j += 32) {
+        const float g1 = Cs[i * CS + j] * (inv_n[i] * inv_n[j]);
+        const float g2 = Co[i * CS + j] * (inv_n[NP + i] * inv_n[NP + j]);
+        const float d = g1 - g2;
+        part += d * d;                                   // (only tensor 0 reports it)
+        Ac[i * CS + j] = 2.f * p.coef_com * d;           // dL/dG_self: the same expression from either side of the pair
+        Cs[i * CS + j] = g1;                             // keep the normalised Gram for r_i
+      }
+  }
+  part = warp_sum(part);
+  if (lane == 0) red[warp] = part;
+  __syncthreads();
+  if (tid == 0 && ch == 0 && ts != 1) {
+    float s = 0.f;
+    for (int w = 0; w < nwarps; ++w) s += red[w];
+    const int col = ts == 0 ? 0 : ts - 1;
+    p.loss_part[(long long)b * 3 + col] = (ts == 0 ? p.coef_com : p.coef_dep) * s;
+  }
+  if (common)
+    for (int i = tid; i < N; i += kLossThreads) {          // r_i = E^_i . dE^_i = 2 sum_j Ac_ij G_ij
+      float s = 0.f;
+      for (int j = 0; j < N; ++j) s += Ac[i * CS + j] * Cs[i * CS + j];
+      rdot[i] = 2.f * s;
+    }
+  __syncthreads();
+  if (p.dx[ts] == nullptr) return;
+  // left operands as TF32, rounded once
+  for (int e = tid; e < NP * CS; e += kLossThreads) {
+    Ac[e] = __uint_as_float(to_tf32(Ac[e]));
+    Ah[e] = __uint_as_float(to_tf32(2.f * p.coef_dep * Ch[e]));
+  }
+  __syncthreads();
+
+  float* dst = p.dx[ts] + (long long)b * N * D;
+  const int MT = NP / 16;
+  const bool pair_ok = ((D & 1) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 7) == 0);
+  for (int nt = warp; nt < kChunk / 8; nt += nwarps) {
+    float ac[4][4], ah[4][4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) ac[m][q] = ah[m][q] = 0.f;
+    for (int k0 = 0; k0 < NP; k0 += 8) {
+      const float e0 = tile[(size_t)(k0 + t) * kTS + nt * 8 + g], e1 = tile[(size_t)(k0 + t + 4) * kTS + nt * 8 + g];
+      const uint32_t bh0 = to_tf32(e0), bh1 = to_tf32(e1);                       // E' (centred): HSIC term
+      uint32_t bc0 = 0, bc1 = 0;
+      if (common) {                                                              // E^ = E' / n: common term
+        bc0 = to_tf32(e0 * inv_n[k0 + t]);
+        bc1 = to_tf32(e1 * inv_n[k0 + t + 4]);
+      }
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        if (m < MT) {
+          const float* ar = Ah + (size_t)(m * 16 + g) * CS + k0 + t;
+          mma_tf32(ah[m], __float_as_uint(ar[0]), __float_as_uint(ar[8 * CS]), __float_as_uint(ar[4]),
+                   __float_as_uint(ar[8 * CS + 4]), bh0, bh1);
+          if (common) {
+            const float* cr = Ac + (size_t)(m * 16 + g) * CS + k0 + t;
+            mma_tf32(ac[m], __float_as_uint(cr[0]), __float_as_uint(cr[8 * CS]), __float_as_uint(cr[4]),
+                     __float_as_uint(cr[8 * CS + 4]), bc0, bc1);
+          }
+        }
+      }
+    }
+    const int cc = nt * 8 + 2 * t, c = ch * kChunk + cc;
+    float v[4][4];
+    float cs0 = 0.f, cs1 = 0.f;
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int i = m * 16 + g + 8 * h;
+        float v0 = 0.f, v1 = 0.f;
+        if (common && m < MT && i < N) {
+          // dE' = (dE^ - E^ r) / n with dE^ = 2 Ac E^ ; E^ = E' / n
+          const float inr = inv_n[i], rd = rdot[i];
+          v0 = (2.f * ac[m][2 * h] - tile[(size_t)i * kTS + cc] * inr * rd) * inr;
+          v1 = (2.f * ac[m][2 * h + 1] - tile[(size_t)i * kTS + cc + 1] * inr * rd) * inr;
+        }
+        cs0 += v0;
+        cs1 += v1;
+        v[m][2 * h] = v0;
+        v[m][2 * h + 1] = v1;
+      }
+    if (common) {      // dE = dE' - column mean(dE') ; rows live in the 8 lanes sharing t
+#pragma unroll
+      for (int o = 4; o < 32; o <<= 1) {
+        cs0 += __shfl_xor_sync(0xffffffffu, cs0, o);
+        cs1 += __shfl_xor_sync(0xffffffffu, cs1, o);
+      }
+      cs0 /= N;
+      cs1 /= N;
+    }
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int i = m * 16 + g + 8 * h;
+        if (m < MT && i < N) {
+          const float o0 = v[m][2 * h] - cs0 + ah[m][2 * h], o1 = v[m][2 * h + 1] - cs1 + ah[m][2 * h + 1];
+          if (c + 1 < D && pair_ok) {
+            *reinterpret_cast<float2*>(dst + (long long)i * D + c) = make_float2(o0, o1);
+          } else {
+            if (c < D) dst[(long long)i * D + c] = o0;
+            if (c + 1 < D) dst[(long long)i * D + c + 1] = o1;
+          }
+        }
+      }
+  }
+}
+
 }  // namespace dvgr
 
 using namespace dvgr;
@@ -319,5 +538,44 @@ extern "C" int dvgr_pair_loss_multi(const dvgr_pair_job* jobs, int n_jobs, int B
   DVGR_CHECK_LAUNCH("pair_gram");
   pair_grad_kernel<<<grid, kLossThreads, smem2, st>>>(p);
   DVGR_CHECK_LAUNCH("pair_grad");
+  return 0;
+}
+
+extern "C" long long dvgr_aux_loss_workspace(int B, int N, int D) {
+  const int chunks = (D + kChunk - 1) / kChunk;
+  return 4LL * B * chunks * N * N;
+}
+
+extern "C" int dvgr_aux_loss_unit(const float* ca, const float* cm, const float* aq, const float* mq, float coef_com,
+                                  float coef_dep, int B, int N, int D, float* d_ca, float* d_cm, float* d_aq, float* d_mq,
+                                  float* loss_part, float* gram_ws, void* stream) {
+  if (B <= 0) return 0;
+  if (N < 1 || N > 64) return set_error("aux_loss: N=%d out of [1,64]", N);
+  if (!ca || !cm || !aq || !mq || !loss_part || !gram_ws) return set_error("aux_loss: null buffer");
+  AuxParams p;
+  memset(&p, 0, sizeof(p));
+  p.x[0] = ca; p.x[1] = cm; p.x[2] = aq; p.x[3] = mq;
+  p.dx[0] = d_ca; p.dx[1] = d_cm; p.dx[2] = d_aq; p.dx[3] = d_mq;
+  p.loss_part = loss_part; p.coef_com = coef_com; p.coef_dep = coef_dep;
+  p.B = B; p.N = N; p.D = D; p.chunks = (D + kChunk - 1) / kChunk; p.ws = gram_ws;
+  const size_t smem1 = (size_t)round16(N) * kTS * sizeof(float);
+  const size_t smem2 = aux_grad_smem(N);
+  static size_t conf1 = 0, conf2 = 0;
+  if (smem1 > 48 * 1024 && smem1 > conf1) {
+    cudaError_t e = cudaFuncSetAttribute(aux_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
+    if (e != cudaSuccess) return set_error("aux_loss: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    conf1 = smem1;
+  }
+  if (smem2 > 48 * 1024 && smem2 > conf2) {
+    cudaError_t e = cudaFuncSetAttribute(aux_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+    if (e != cudaSuccess) return set_error("aux_loss: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    conf2 = smem2;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  dim3 grid(B, 4, p.chunks);
+  aux_gram_kernel<<<grid, kLossThreads, smem1, st>>>(p);
+  DVGR_CHECK_LAUNCH("aux_gram");
+  aux_grad_kernel<<<grid, kLossThreads, smem2, st>>>(p);
+  DVGR_CHECK_LAUNCH("aux_grad");
   return 0;
 }

@@ -553,6 +553,21 @@ def pair_loss_multi(jobs, B, N, D, like):
     return colsum(part)
 
 
+def aux_loss_unit(ca, cm, aq, mq, coef_com, coef_dep, want_grad=True):
+    """The three auxiliary terms of one DualVGR unit (tensor-centric kernels). Inputs fp32 [B, N, D] contiguous.
+    Returns (vals [3] f32 = coef-scaled (common, HSIC(aq, ca), HSIC(mq, cm)), (d_ca, d_cm, d_aq, d_mq) | None)."""
+    B, N, D = ca.shape
+    for t in (ca, cm, aq, mq):
+        assert t.dtype == F32 and t.is_contiguous() and tuple(t.shape) == (B, N, D)
+    grads = tuple(torch.empty_like(t) for t in (ca, cm, aq, mq)) if want_grad else (None,) * 4
+    part = _empty((B, 3), F32, ca)
+    ws = _empty((int(_lib.lib.dvgr_aux_loss_workspace(B, N, D)),), F32, ca)
+    _lib.check(_lib.aux_loss_unit(_ptr(ca), _ptr(cm), _ptr(aq), _ptr(mq), float(coef_com), float(coef_dep), B, N, D,
+                                  _ptr(grads[0]), _ptr(grads[1]), _ptr(grads[2]), _ptr(grads[3]), _ptr(part), _ptr(ws),
+                                  _stream()), "dvgr_aux_loss_unit")
+    return colsum(part), (grads if want_grad else None)
+
+
 def pair_loss(x, y, mode, coef, dx=None, dy=None, want_grad=True):
     """mode 0: coef * sum (G_x - G_y)^2 ; mode 1: coef * HSIC. x, y fp32 [B, N, D]. dx / dy given => accumulated into.
     Returns (loss scalar tensor, dx, dy)."""

@@ -275,6 +275,16 @@ typedef struct dvgr_pair_job {
 } dvgr_pair_job;
 long long dvgr_pair_loss_workspace(int n_jobs, int B, int N, int D);
 int dvgr_pair_loss_multi(const dvgr_pair_job* jobs, int n_jobs, int B, int N, int D, float* gram_ws, void* stream);
+/* The three auxiliary terms of ONE DualVGR unit in a tensor-centric form (train.py:148-154 for one layer):
+ *   coef_com * sum_ij (G_ca - G_cm)^2  +  coef_dep * (HSIC(aq, ca) + HSIC(mq, cm)),
+ * value and the COMPLETE gradients of the four [B][N][D] f32 operands in two launches (each operand tile is loaded once
+ * per pass, every gradient is written with plain stores: no atomics, no pre-zeroed buffers). loss_part [B][3] receives the
+ * per-video coef-scaled (common, HSIC_app, HSIC_motion); gradients may be NULL (value only);
+ * gram_ws: dvgr_aux_loss_workspace(B, N, D) floats. */
+long long dvgr_aux_loss_workspace(int B, int N, int D);
+int dvgr_aux_loss_unit(const float* ca, const float* cm, const float* aq, const float* mq, float coef_com, float coef_dep,
+                       int B, int N, int D, float* d_ca, float* d_cm, float* d_aq, float* d_mq, float* loss_part,
+                       float* gram_ws, void* stream);
 
 /* Streaming helpers.
  * dvgr_prep_features: model/Preprocessing.py:220-223 — tanh(dropout(x)), fp32 -> bf16, [S][T][C] -> [T][S][C] in one pass.

@@ -418,6 +418,32 @@ def test_pair_losses(ops, N):
         assert rel(dx, gx) < max(tol, 1e-3) and rel(dy, gy) < max(tol, 1e-3)
 
 
+@pytest.mark.parametrize("N", [8, 20, 33])
+def test_unit_aux_losses_tensor_centric(ops, N):
+    """dvgr_aux_loss_unit: common(ca, cm) + HSIC(aq, ca) + HSIC(mq, cm) of one DualVGR unit, value and the four complete
+    gradients, against the oracle's formulas (float64 autograd) and against the pair-centric kernels."""
+    torch.manual_seed(18)
+    B, D = 4, 768
+    c_com, c_dep = 1.0 / (B * N * N), 3e-3
+    for spread in (1.0, 1e-3):
+        base = torch.randn(B, 1, D)
+        ts = [(base * s + spread * torch.randn(B, N, D)).float() for s in (1.0, 0.7, 0.9, 1.2)]
+        rs = [t.double().requires_grad_(True) for t in ts]
+        com = orc.common_loss(rs[0], rs[1]) * (c_com * B * N * N)
+        h1, h2 = orc.loss_dependence(rs[2], rs[0], N) * c_dep, orc.loss_dependence(rs[3], rs[1], N) * c_dep
+        grads = torch.autograd.grad(com + h1 + h2, rs)
+        vals, got = ops.aux_loss_unit(*[t.cuda() for t in ts], c_com, c_dep)
+        tol = 1e-3 if spread == 1.0 else 5e-2
+        for v, r in zip(vals.cpu(), (com, h1, h2)):
+            assert abs(float(v) - float(r)) <= tol * abs(float(r))
+        for gg, gr in zip(got, grads):
+            assert rel(gg, gr) < max(tol, 1e-3)
+        # the pair-centric kernels (still behind utils.common_loss / loss_dependence) agree
+        _, dx, dy = ops.pair_loss(ts[0].cuda(), ts[1].cuda(), 0, c_com)
+        _, dxa, dya = ops.pair_loss(ts[2].cuda(), ts[0].cuda(), 1, c_dep)
+        assert rel(got[0], dx + dya) < max(tol, 2e-3) and rel(got[2], dxa) < max(tol, 2e-3)
+
+
 def test_prep_cast_adam(ops):
     torch.manual_seed(9)
     S, T, C = 12, 16, 2048

@@ -64,7 +64,13 @@ def pair():
     ops.pair_loss_multi(jobs, B, N, D, ca)
 
 
+def aux():
+    ops.aux_loss_unit(ca, cm, aq, mq, 1e-3, 1e-8)
+
+
 tp = timeit(pair)
+ta = timeit(aux)
+print(f"aux losses, tensor-centric kernels: {ta * 1e3:.1f} us", flush=True)
 e4 = B * N * D * 4
 print(f"aux losses (3 pairs, value + 4 gradients): {tp * 1e3:.1f} us ; minimal traffic {8 * e4 / 1e6:.0f} MB -> {8 * e4 / tp / 1e6:.0f} GB/s "
       f"({8 * e4 / tp / 1e6 / peak:.2f} of measured)", flush=True)

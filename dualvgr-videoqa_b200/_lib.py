@@ -138,6 +138,13 @@ cast_rows = _sig("dvgr_cast_rows", [P, c_ll, P, c_ll, c_int, c_int, c_int, c_int
 dropout = _sig("dvgr_dropout", [P, P, c_ll, c_float, c_ull, c_uint, P])
 act_bwd = _sig("dvgr_act_bwd", [P, P, P, c_ll, c_int, c_int, c_float, c_ull, c_uint, P])
 add = _sig("dvgr_add", [P, P, c_ll, P])
+
+
+class Seg(ctypes.Structure):
+    _fields_ = [("dst", c_void_p), ("src", c_void_p), ("n", c_int)]
+
+
+scatter = _sig("dvgr_scatter", [ctypes.POINTER(Seg), c_int, c_int, P])
 lib.dvgr_colsum_workspace.argtypes = [c_ll, c_int]
 lib.dvgr_colsum_workspace.restype = c_ll
 colsum = _sig("dvgr_colsum", [P, c_int, c_ll, c_ll, c_int, P, P, c_int, c_float, P])
@@ -151,6 +158,6 @@ EXPORTED = [
     "dvgr_qattn_bwd", "dvgr_gate_fwd", "dvgr_gate_bwd", "dvgr_view_attn_fwd", "dvgr_view_attn_bwd_blocks",
     "dvgr_view_attn_bwd", "dvgr_mfb_fwd", "dvgr_mfb_bwd", "dvgr_readout_fwd", "dvgr_readout_bwd", "dvgr_bn_fwd",
     "dvgr_bn_bwd", "dvgr_cross_entropy", "dvgr_pair_loss_workspace", "dvgr_pair_loss_multi", "dvgr_aux_loss_workspace", "dvgr_aux_loss_unit", "dvgr_prep_features", "dvgr_cast_rows", "dvgr_dropout",
-    "dvgr_act_bwd", "dvgr_add", "dvgr_colsum_workspace", "dvgr_colsum", "dvgr_sumsq_blocks", "dvgr_sumsq",
+    "dvgr_act_bwd", "dvgr_add", "dvgr_scatter", "dvgr_colsum_workspace", "dvgr_colsum", "dvgr_sumsq_blocks", "dvgr_sumsq",
     "dvgr_adam_step",
 ]

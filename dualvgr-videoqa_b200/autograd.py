@@ -469,9 +469,22 @@ class GatLayerFn(Function):
         pdrop = p if training else 0.0
         seed, sid = _site(3 * G)          # graph g: input dropout sid+g, attention sid+G+2g, output sid+G+2g+1
         gp = [params[g * heads * 4:(g + 1) * heads * 4] for g in range(G)]
-        avecs = [torch.cat([torch.cat([gp[g][4 * k + 2].detach().reshape(-1), gp[g][4 * k + 3].detach().reshape(-1)])
-                            for k in range(heads)]).view(heads, 2 * Dh + 1).contiguous() for g in range(G)]
         of_stream = [[g for g in range(G) if graph_stream[g] == s] for s in range(ns)]
+        # packed per-graph operands of the attention kernels: avec [heads][2Dh+1] = (a.weight | a.bias) per head, and the
+        # concatenated head biases of each stream's projection GEMM — gathered from the parameters by ONE scatter launch
+        avec_all = torch.empty((G, heads, 2 * Dh + 1), dtype=F32, device=xs[0].device)
+        bias_all = [torch.empty((len(of_stream[s]), D), dtype=F32, device=xs[0].device) for s in range(ns)]
+        segs = []
+        for g in range(G):
+            for k in range(heads):
+                segs.append((avec_all[g, k, :2 * Dh], gp[g][4 * k + 2].detach().reshape(-1)))
+                segs.append((avec_all[g, k, 2 * Dh:], gp[g][4 * k + 3].detach().reshape(-1)))
+        for s in range(ns):
+            for i, g in enumerate(of_stream[s]):
+                for k in range(heads):
+                    segs.append((bias_all[s][i, k * Dh:(k + 1) * Dh], gp[g][4 * k + 1].detach()))
+        ops.scatter(segs, False)
+        avecs = [avec_all[g] for g in range(G)]
         whs, xts, wbufs, outs_s = [], [], [], []
         wh_list, out_list = [None] * G, [None] * G
         for s in range(ns):
@@ -479,7 +492,7 @@ class GatLayerFn(Function):
             cnt = len(gs)
             x = _c(xs[s]).view(M, D)
             wb = bf16_rows([gp[g][4 * k] for g in gs for k in range(heads)], tag="gat").view(cnt, D, D)
-            bias = torch.stack([torch.cat([gp[g][4 * k + 1].detach() for k in range(heads)]) for g in gs])
+            bias = bias_all[s]
             wh = torch.empty((cnt, M, D), dtype=BF16, device=x.device)
             if pdrop > 0:
                 xt = torch.stack([ops.dropout_raw(x, pdrop, seed, sid + g) for g in gs])
@@ -499,6 +512,7 @@ class GatLayerFn(Function):
         ctx.save_for_backward(adj, *xts, *wbufs, *whs, *outs_s, *gate_list, *avecs)
         ctx.cfg = (B, N, D, M, heads, pdrop, seed, sid, streams, graph_stream, of_stream)
         ctx.wparams = [[gp[g][4 * k] for g in of_stream[s] for k in range(heads)] for s in range(ns)]
+        ctx.hparams = gp
         return tuple(outs_s) + tuple(f32s)
 
     @staticmethod
@@ -556,10 +570,21 @@ class GatLayerFn(Function):
             for i, g in enumerate(gs):
                 dW[g], db[g] = (None if direct else dWs[i]), ops.colsum(dwh[i])
         grads = []
+        small = []        # (bound .grad view, gradient) pairs of the per-head biases / attention vectors
         for g in range(G):
             for k in range(heads):
-                grads += [None if dW[g] is None else dW[g][k * Dh:(k + 1) * Dh], db[g][k * Dh:(k + 1) * Dh],
-                          davecs[g][k, :2 * Dh].reshape(1, 2 * Dh), davecs[g][k, 2 * Dh:].reshape(1)]
+                hp = ctx.hparams[g][4 * k:4 * k + 4]                 # W.weight, W.bias, a.weight, a.bias of this head
+                pieces = [db[g][k * Dh:(k + 1) * Dh], davecs[g][k, :2 * Dh].reshape(1, 2 * Dh), davecs[g][k, 2 * Dh:].reshape(1)]
+                outs = []
+                for prm, piece in zip(hp[1:], pieces):
+                    tgt = _bias_target(prm)
+                    if tgt is not None:
+                        small.append((tgt, piece))
+                        outs.append(None)
+                    else:
+                        outs.append(piece)
+                grads += [None if dW[g] is None else dW[g][k * Dh:(k + 1) * Dh]] + outs
+        ops.scatter_add(small)       # one launch for (up to) 48 tiny accumulations instead of one elementwise launch each
         return (None, None, None, None, None) + tuple(dxs) + tuple(dgs) + tuple(grads)
 
 

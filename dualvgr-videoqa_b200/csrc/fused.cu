@@ -712,6 +712,38 @@ extern "C" int dvgr_act_bwd(const void* dy, const void* y, void* out, long long 
   return 0;
 }
 
+// dst[i] (+)= src[i] for up to kMaxSegs small fp32 segments in ONE launch (one block per segment). accumulate: the gradient
+// accumulation of the many tiny parameters of a DualVGR unit (per-head attention vectors and biases), which autograd would
+// otherwise perform with one elementwise launch per parameter (~170 launches of ~2 us per train step); copy: gathering those
+// parameters into the packed per-graph operands of the GAT kernels (instead of ~25 torch.cat launches per layer).
+constexpr int kMaxSegs = 64;
+struct SegList {
+  float* dst[kMaxSegs];
+  const float* src[kMaxSegs];
+  int n[kMaxSegs];
+};
+__global__ void scatter_kernel(const SegList L, int accumulate) {
+  float* d = L.dst[blockIdx.x];
+  const float* s = L.src[blockIdx.x];
+  for (int i = threadIdx.x; i < L.n[blockIdx.x]; i += blockDim.x) d[i] = accumulate ? d[i] + s[i] : s[i];
+}
+
+extern "C" int dvgr_scatter(const dvgr_seg* segs, int n_segs, int accumulate, void* stream) {
+  if (n_segs <= 0) return 0;
+  if (!segs) return set_error("scatter: null segment list");
+  for (int base = 0; base < n_segs; base += kMaxSegs) {
+    SegList L;
+    const int cnt = n_segs - base < kMaxSegs ? n_segs - base : kMaxSegs;
+    for (int i = 0; i < cnt; ++i) {
+      if (!segs[base + i].dst || !segs[base + i].src) return set_error("scatter: segment %d has a null pointer", base + i);
+      L.dst[i] = segs[base + i].dst; L.src[i] = segs[base + i].src; L.n[i] = segs[base + i].n;
+    }
+    scatter_kernel<<<cnt, 128, 0, ST(stream)>>>(L, accumulate);
+    DVGR_CHECK_LAUNCH("scatter");
+  }
+  return 0;
+}
+
 extern "C" int dvgr_add(void* a, const void* b, long long n, void* stream) {
   if (n % 8 != 0) return set_error("add: n=%lld must be a multiple of 8", n);
   if (n <= 0) return 0;

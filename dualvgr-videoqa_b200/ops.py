@@ -348,6 +348,24 @@ def act_bwd(dy, y, act, out=None, accumulate=False, p=0.0, seed=0, stream_id=0):
     return out
 
 
+def scatter(pairs, accumulate):
+    """pairs: list of (dst, src) fp32 tensors of equal numel, dst contiguous: dst (+)= src for all of them, 64 per launch."""
+    if not pairs:
+        return
+    arr = (_lib.Seg * len(pairs))()
+    keep = []
+    for i, (d, s_) in enumerate(pairs):
+        s_ = s_ if s_.is_contiguous() else s_.contiguous()
+        keep.append(s_)
+        assert d.dtype == F32 and s_.dtype == F32 and d.is_contiguous() and d.numel() == s_.numel() and d.is_cuda and s_.is_cuda
+        arr[i].dst, arr[i].src, arr[i].n = d.data_ptr(), s_.data_ptr(), d.numel()
+    _lib.check(_lib.scatter(arr, len(pairs), 1 if accumulate else 0, _stream()), "dvgr_scatter")
+
+
+def scatter_add(pairs):
+    scatter(pairs, True)
+
+
 def add_(a, b):
     assert a.dtype == BF16 and b.dtype == BF16 and a.is_contiguous() and b.is_contiguous() and a.numel() == b.numel()
     _lib.check(_lib.add(_ptr(a), _ptr(b), a.numel(), _stream()), "dvgr_add")

@@ -300,6 +300,16 @@ int dvgr_dropout(const void* in, void* out, long long n, float p, unsigned long 
 int dvgr_act_bwd(const void* dy, const void* y, void* out, long long n, int act, int accumulate, float p,
                  unsigned long long seed, unsigned int drop_stream, void* stream);
 int dvgr_add(void* a, const void* b, long long n, void* stream);
+/* dst[i] (+)= src[i] for a HOST array of small f32 segments, 64 per launch. accumulate = 1: adds the gradients of the many
+ * tiny parameters of a unit (per-head attention vectors / biases) into their bound .grad views in one launch instead of
+ * one elementwise launch per parameter (what autograd's AccumulateGrad does); accumulate = 0: gathers those parameters
+ * into the packed avec / bias operands of dvgr_gat_attn_* (model/GraphNN.py:88-93) instead of ~25 torch.cat launches. */
+typedef struct dvgr_seg {
+  float* dst;
+  const float* src;
+  int n;
+} dvgr_seg;
+int dvgr_scatter(const dvgr_seg* segs, int n_segs, int accumulate, void* stream);
 long long dvgr_colsum_workspace(long long R, int C);
 int dvgr_colsum(const void* in, int in_is_f32, long long ld, long long R, int C, float* workspace, float* out,
                 int accumulate, float scale, void* stream);

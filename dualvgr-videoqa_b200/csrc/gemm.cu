@@ -418,8 +418,11 @@ __device__ __forceinline__ void lstm_cell_bwd8(const GemmParams& p, int dir, int
     d0 = ld_run4<kSeq>(dcp); d1 = ld_run4<kSeq>(dcp + cq);
   }
   if (live && p.dh_ext != nullptr) {
-    // gradient arriving on the per-step hidden output [S][T][ld] (column dir*H); padded steps emit constant zeros
-    uint4 ev = *reinterpret_cast<const uint4*>(p.dh_ext + ((long long)seq * p.T + t) * p.seq_out_ld + (long long)dir * H + j0);
+    // gradient arriving on the per-step hidden output; padded steps emit constant zeros.
+    // per-step path: [S][T][ld] (column dir*H); whole-sequence path: blocked [T][D][RB][H/8][32 rows][8] (coalesced)
+    const __nv_bfloat16* ep = kSeq ? p.dh_ext + (((((long long)t * p.batch + dir) * p.RB + (seq >> 5)) * UG + (j0 >> 3)) * 32 + (seq & 31)) * 8
+                                   : p.dh_ext + ((long long)seq * p.T + t) * p.seq_out_ld + (long long)dir * H + j0;
+    uint4 ev = *reinterpret_cast<const uint4*>(ep);
     const uint32_t* ew = reinterpret_cast<const uint32_t*>(&ev);
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -429,16 +432,18 @@ __device__ __forceinline__ void lstm_cell_bwd8(const GemmParams& p, int dir, int
   }
   if (p.dh_carry != nullptr) {
     // padded steps carry the state forward, so their incoming dh must reach the last live step unchanged
-    float* cp = p.dh_carry + ((long long)dir * S + seq) * H + j0;
-    float4 c0 = ld_run4<kSeq>(cp), c1 = ld_run4<kSeq>(cp + 4);
+    // (running buffer: row-major [D][S][H] per step launch, blocked like dc in the whole-sequence kernels)
+    float* cp = kSeq ? p.dh_carry + lstm_blk_dc(dir, p.RB, UG, seq >> 5, j0 >> 3) + (seq & 31) * 4
+                     : p.dh_carry + ((long long)dir * S + seq) * H + j0;
+    float4 c0 = ld_run4<kSeq>(cp), c1 = ld_run4<kSeq>(cp + cq);
     dh[0] += c0.x; dh[1] += c0.y; dh[2] += c0.z; dh[3] += c0.w;
     dh[4] += c1.x; dh[5] += c1.y; dh[6] += c1.z; dh[7] += c1.w;
     if (live) {
       *reinterpret_cast<float4*>(cp) = make_float4(0.f, 0.f, 0.f, 0.f);
-      *reinterpret_cast<float4*>(cp + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(cp + cq) = make_float4(0.f, 0.f, 0.f, 0.f);
     } else {
       *reinterpret_cast<float4*>(cp) = make_float4(dh[0], dh[1], dh[2], dh[3]);
-      *reinterpret_cast<float4*>(cp + 4) = make_float4(dh[4], dh[5], dh[6], dh[7]);
+      *reinterpret_cast<float4*>(cp + cq) = make_float4(dh[4], dh[5], dh[6], dh[7]);
     }
   }
 #pragma unroll

@@ -270,9 +270,15 @@ def lstm_bwd(gates, whh, h_hist, c_hist, dh_last, seq_len=None, dh_seq=None, who
         a.dh_last, a.dh_last_ld = dh_last.data_ptr(), dh_last.stride(0)
     if seq_len is not None:
         a.seq_len = seq_len.data_ptr()
-        carry = torch.zeros((D, S, H), dtype=torch.float32, device=gates.device)
+        carry = (torch.zeros((D, RB, UG, 2, 32, 4), dtype=torch.float32, device=gates.device) if whole_sequence
+                 else torch.zeros((D, S, H), dtype=torch.float32, device=gates.device))
         a.dh_carry = carry.data_ptr()
     if dh_seq is not None:
+        if whole_sequence:      # [S, T, D*H] -> blocked [T, D, RB, H/8, 32, 8]: one 512-byte warp access per (row block, unit group)
+            assert tuple(dh_seq.shape) == (S, T, D * H) and dh_seq.dtype == BF16
+            pad = torch.zeros((RB * 32, T, D * H), dtype=BF16, device=gates.device)
+            pad[:S] = dh_seq
+            dh_seq = pad.view(RB, 32, T, D, UG, 8).permute(2, 3, 0, 4, 1, 5).contiguous()
         a.dh_seq, a.seq_out_ld = dh_seq.data_ptr(), D * H
     st = _stream()
     if whole_sequence:

@@ -146,8 +146,9 @@ int dvgr_lstm_seq_fwd(const dvgr_lstm_seq_args* args, void* stream);
  * of step T-1 (elementwise) followed by ONE persistent launch for steps T-2 ... 0 (dh_s = dgates_{s+1} W_hh on tensor
  * cores, cell backward in the epilogue, steps chained by completion counters). Consumes the BLOCKED gates / c_hist of
  * dvgr_lstm_seq_fwd and a blocked, zeroed dc; writes the pre-activation gate gradients to `dgates` [T][S][D*4H] bf16
- * (standard layout: the operand of the W_ih / W_hh / bias gradients). `sync` as for dvgr_lstm_seq_fwd (zero on entry);
- * `args->s` is ignored. */
+ * (standard layout: the operand of the W_ih / W_hh / bias gradients). With seq_len: dh_carry is blocked like dc
+ * ([D][RB][H/8][2][32][4] f32, zeroed) and dh_seq is blocked [T][D][RB][H/8][32][8] bf16. `sync` as for
+ * dvgr_lstm_seq_fwd (zero on entry); `args->s` is ignored. */
 int dvgr_lstm_seq_bwd(const dvgr_lstm_args* args, void* dgates, int* sync, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------

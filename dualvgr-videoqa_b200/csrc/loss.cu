@@ -336,7 +336,7 @@ __host__ __device__ inline size_t aux_grad_smem(int N) {
   return (size_t)(NP * kTS + 5 * NP * CS + 4 * NP) * sizeof(float);
 }
 
-__global__ void __launch_bounds__(kLossThreads) aux_grad_kernel(const AuxParams p) {
+__global__ void __launch_bounds__(kLossThreads, 3) aux_grad_kernel(const AuxParams p) {
   extern __shared__ __align__(16) float sm[];
   const int b = blockIdx.x, ts = blockIdx.y, ch = blockIdx.z, N = p.N, D = p.D, NP = round16(N), CS = NP + 4;
   float* tile = sm;                         // [NP][kTS]   centred chunk of this tensor

@@ -1,8 +1,6 @@
 set -x
-timeout 600 python -m pytest tests/test_kernels_gpu.py -x -q -m gpu -k "lstm" --tb=short 2>&1 | grep -v Warning | tail -5
-timeout 300 python tools/time_lstm_seq.py 2>&1 | tail -4
-timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu > gpurun_out/bench_r01_s2j.json 2> gpurun_out/bench_r01_s2j.err; head -c 330 gpurun_out/bench_r01_s2j.json; tail -5 gpurun_out/bench_r01_s2j.err
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:lstm_seq -c 2 -o gpurun_out/prof_r01_lstm_seq_v2 python tools/prof_lstm_once.py 2>&1 | grep -E "error|timeouts" | tail -3
-for k in aux_grad aux_gram; do
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s 3 -c 1 -o gpurun_out/prof_r01_$k python tools/time_fused.py 2>&1 | grep -E "error" | tail -2
-done
+timeout 900 python -m pytest tests -q -m gpu --tb=short 2>&1 | tail -4
+timeout 300 python tools/time_fused.py 2>&1 | tail -4
+timeout 900 python bench.py --steps 20 --warmup 3 > gpurun_out/bench_r01_final2.json 2> gpurun_out/bench_r01_final2.err; head -c 330 gpurun_out/bench_r01_final2.json; tail -3 gpurun_out/bench_r01_final2.err
+timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_r01_reference2.json 2>/dev/null; head -c 300 gpurun_out/bench_r01_reference2.json
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 6500 --csv --log-file gpurun_out/launches_r01_final2.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu > gpurun_out/bench_under_ncu_final2.log 2>&1; tail -c 300 gpurun_out/bench_under_ncu_final2.log

@@ -151,6 +151,37 @@ def test_against_live_oracle_full_gradients(cfg):
     assert max(w for w, _ in worst) < 0.5, sorted(worst)[-5:]
 
 
+@pytest.mark.parametrize("cfg", [(3, 64, 8, 50, 60, 1), (4, 16, 8, 4002, 60, 1)])
+def test_against_live_oracle_other_baseline_shapes(cfg):
+    """BASELINE configs 5 and 3 in miniature: 64-clip videos (the 64-node GAT forward variant + generic backward, 2-row-block
+    LSTM tiles) and the MSRVTT-sized open-ended answer vocabulary (A = 4002: unaligned logits / classifier GEMM). Logits
+    and the global CE gradient against the oracle in float64; tiny batches, so the gradient gate is 1.5x (BatchNorm, see
+    test_against_reference_golden)."""
+    B, N, L, A, V, U = cfg
+    model, inputs, ans = build(cfg, training=True)
+    out = model(*inputs)
+    ce = torch.nn.functional.cross_entropy(out[0], ans)
+    names = [n for n, _ in model.named_parameters()]
+    grads = torch.autograd.grad(ce, [p for _, p in model.named_parameters()], allow_unused=True)
+    sd = orc.cast_state_dict(orc.make_state_dict(U, A, V), torch.float64)
+    for v in sd.values():
+        if v.is_floating_point():
+            v.requires_grad_(True)
+    app, mot, q, qlen, ans_c = orc.make_inputs(B, N, L, A, V)
+    ref_out = orc.dualvgr_forward(sd, U, app.double(), mot.double(), q, qlen, training=True)
+    ref_ce = torch.nn.functional.cross_entropy(ref_out[0], ans_c)
+    ref_grads = torch.autograd.grad(ref_ce, [sd[n] for n in names], allow_unused=True)
+    assert tuple(out[0].shape) == (B, A) and rel(out[0], ref_out[0]) < TOL
+    assert abs(float(ce) - float(ref_ce)) < TOL * abs(float(ref_ce))
+    num = den = 0.0
+    for gr, rg in zip(grads, ref_grads):
+        if rg is None:
+            continue
+        gr = torch.zeros_like(rg) if gr is None else gr.double().cpu()
+        num += float((gr - rg).pow(2).sum()); den += float(rg.pow(2).sum())
+    assert (num / den) ** 0.5 < 1.5 * TOL, (num / den) ** 0.5
+
+
 def test_full_loss_backward_and_train_mode_dropout_runs():
     """Train mode with the reference's dropout rates: finite loss/grads, masks differ between passes, eval is deterministic."""
     import dualvgr_videoqa_b200.model.models as M

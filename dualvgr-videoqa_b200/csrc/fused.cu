@@ -37,6 +37,7 @@ __global__ void __launch_bounds__(256)
 view_attn_fwd_kernel(const bf16* __restrict__ hidden, const bf16* __restrict__ z, const bf16* __restrict__ X,
                      const float* __restrict__ w2, long long M, int D, bf16* __restrict__ Xnew,
                      bf16* __restrict__ embed, float* __restrict__ beta) {
+  pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (long long r = (long long)blockIdx.x * 8 + warp; r < M; r += (long long)gridDim.x * 8) {
     float w0 = 0.f, w1 = 0.f;
@@ -81,6 +82,7 @@ __global__ void __launch_bounds__(256)
 view_attn_bwd_kernel(const bf16* __restrict__ dXnew, const bf16* __restrict__ dembed_ext, const bf16* __restrict__ hidden,
                      const bf16* __restrict__ z, const float* __restrict__ w2, const float* __restrict__ beta,
                      long long M, int D, bf16* __restrict__ dz, bf16* __restrict__ dhid, float* __restrict__ dw2_part) {
+  pdl_trigger();
   extern __shared__ float dw2_s[];   // [D]
   for (int c = threadIdx.x; c < D; c += blockDim.x) dw2_s[c] = 0.f;
   __syncthreads();
@@ -136,6 +138,7 @@ view_attn_bwd_kernel(const bf16* __restrict__ dXnew, const bf16* __restrict__ de
 // reference model/fusions/fusions.py:433-441: z = (x0 * x1).view(..., 256, 2).sum(-1)   (x0, x1 already ELU'd by the GEMM)
 __global__ void mfb_fwd_kernel(const bf16* __restrict__ x0, const bf16* __restrict__ x1, bf16* __restrict__ z,
                                long long n_out4) {   // n_out4 = M*mm/4 ; each thread: 8 inputs -> 4 outputs
+  pdl_trigger();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_out4; i += (long long)gridDim.x * blockDim.x) {
     float a[8], b[8];
     load8(x0 + i * 8, a);
@@ -149,6 +152,7 @@ __global__ void mfb_fwd_kernel(const bf16* __restrict__ x0, const bf16* __restri
 // dz -> dpre0 = dz_pair * x1 * ELU'(x0), dpre1 = dz_pair * x0 * ELU'(x1)
 __global__ void mfb_bwd_kernel(const bf16* __restrict__ dz, const bf16* __restrict__ x0, const bf16* __restrict__ x1,
                                bf16* __restrict__ d0, bf16* __restrict__ d1, long long n_out4) {
+  pdl_trigger();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_out4; i += (long long)gridDim.x * blockDim.x) {
     float a[8], b[8], oa[8], ob[8];
     load8(x0 + i * 8, a);
@@ -173,6 +177,7 @@ __global__ void __launch_bounds__(256)
 readout_fwd_kernel(const bf16* __restrict__ v, const bf16* __restrict__ u, const float* __restrict__ w,
                    const float* __restrict__ c, int N, int D, float* __restrict__ alpha, bf16* __restrict__ pooled,
                    long long ld_p) {
+  pdl_trigger();
   __shared__ float sc[64];
   const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int n = warp; n < N; n += 8) {
@@ -219,6 +224,7 @@ readout_bwd_kernel(const bf16* __restrict__ dpooled, long long ld_p, const bf16*
                    const bf16* __restrict__ u, const float* __restrict__ w, const float* __restrict__ alpha, int N,
                    int D, bf16* __restrict__ dv, bf16* __restrict__ du, float* __restrict__ dw_part,
                    float* __restrict__ dc_part) {
+  pdl_trigger();
   __shared__ float da[64];
   __shared__ float al[64];
   const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -412,6 +418,7 @@ __global__ void prep_features_kernel(const float* __restrict__ in, bf16* __restr
 // output row 4*j + g <- input row g*H + j  (nn.LSTM stores i|f|g|o blocks; the fused cell wants them per unit).
 __global__ void cast_rows_kernel(const float* __restrict__ in, long long ld_in, bf16* __restrict__ out, long long ld_out,
                                  int rows, int cols, int out_cols, int lstm_H) {
+  pdl_trigger();
   const long long total = (long long)rows * out_cols;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int r = (int)(i / out_cols), c = (int)(i - (long long)r * out_cols);
@@ -423,6 +430,7 @@ __global__ void cast_rows_kernel(const float* __restrict__ in, long long ld_in, 
 
 // out = in * dropout mask (the same kernel is its own backward)
 __global__ void dropout_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, long long n8, DropoutCfg dc) {
+  pdl_trigger();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
     float f[8], sc[8];
     load8(in + i * 8, f);
@@ -436,6 +444,7 @@ __global__ void dropout_kernel(const bf16* __restrict__ in, bf16* __restrict__ o
 // out = dy * dropout mask * act'(y)   (y is the activation OUTPUT; act: 0 none, 1 ELU, 2 tanh); optional accumulate
 __global__ void act_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ y, bf16* __restrict__ out,
                                long long n8, int act, int accumulate, DropoutCfg dc) {
+  pdl_trigger();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
     float d[8], yy[8];
     load8(dy + i * 8, d);
@@ -462,6 +471,7 @@ __global__ void act_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restri
 
 // a (+)= b elementwise (bf16), used to merge gradient branches
 __global__ void add_kernel(bf16* __restrict__ a, const bf16* __restrict__ b, long long n8) {
+  pdl_trigger();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
     float x[8], y[8];
     load8(a + i * 8, x);
@@ -485,6 +495,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 colsum_partial_kernel(const T* __restrict__ in, long long ld, long long R, int C, int rows_per_chunk,
                       float* __restrict__ partial, int vec_ok) {
+  pdl_trigger();
   __shared__ float red[8][32][9];
   const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int c0 = (blockIdx.x * 32 + cg) * 8;
@@ -535,6 +546,7 @@ colsum_partial_kernel(const T* __restrict__ in, long long ld, long long R, int C
 __global__ void __launch_bounds__(256)
 colsum_final_kernel(const float* __restrict__ partial, int chunks, int C, float* __restrict__ out, int accumulate,
                     float scale) {
+  pdl_trigger();
   __shared__ float red[8][33];
   const int cl = threadIdx.x & 31, kl = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
@@ -723,6 +735,7 @@ struct SegList {
   int n[kMaxSegs];
 };
 __global__ void scatter_kernel(const SegList L, int accumulate) {
+  pdl_trigger();
   float* d = L.dst[blockIdx.x];
   const float* s = L.src[blockIdx.x];
   for (int i = threadIdx.x; i < L.n[blockIdx.x]; i += blockDim.x) d[i] = accumulate ? d[i] + s[i] : s[i];

@@ -666,23 +666,26 @@ __global__ void __launch_bounds__(kGatThreads) gat_attn_bwd_kernel(const GatPara
 //   dV[j][c]     = sum_i P~^T[k][j][i] dz[i][c]               A = P~^T (bf16 high + low halves), B = dz (ldmatrix.trans)
 // and everything that hangs off them (gate / attention-vector gradients, dWh) is folded into the fragment epilogues.
 // dgate receives the two head pairs' partial sums by atomicAdd: the caller zeroes it (two addends: deterministic).
-constexpr int kBH = 2;                    // heads per CTA
-constexpr int kBC = kBH * kFDh;           // 384 columns per CTA
-constexpr int kBWP = kBC + 8;             // tile row pitch (elements): 784 B = 49 x 16 B
-constexpr int kBNP = 32, kBPP = kBNP + 8, kBNPF = kBNP + 4, kBMT = kBNP / 16;
-struct GatFastBwd {
-  static constexpr size_t TILE_BYTES = (size_t)kBNP * kBWP * 2;
-  static constexpr size_t PT_BYTES = (size_t)2 * kBH * kBNP * kBPP * 2;
-  static constexpr size_t DP_BYTES = (size_t)kBH * kBNP * kBNPF * 4;
-  static constexpr size_t SMALL_BYTES = (size_t)(4 * kBH * kBNP + 2 * kBNP + 8) * 4;      // s, t, ds, dt, gate, dg, dc
-  static constexpr size_t ADJ_BYTES = (size_t)kBNP * kBNP;
+// NP = 32 nodes: kBH = 2 heads per CTA (72 KB, 3 CTAs / SM); NP = 64 nodes (BASELINE config 5): kBH = 1 head per CTA (93 KB, 2 / SM)
+template <int NP, int kBH> struct GatFastBwd {
+  static constexpr int BC = kBH * kFDh;            // columns per CTA
+  static constexpr int BWP = BC + 8;               // tile row pitch (elements): an odd multiple of 16 B
+  static constexpr int PP = NP + 8, NPF = NP + 4, MT = NP / 16;
+  static constexpr size_t TILE_BYTES = (size_t)NP * BWP * 2;
+  static constexpr size_t PT_BYTES = (size_t)2 * kBH * NP * PP * 2;
+  static constexpr size_t DP_BYTES = (size_t)kBH * NP * NPF * 4;
+  static constexpr size_t SMALL_BYTES = (size_t)(4 * kBH * NP + 2 * NP + 8) * 4;      // s, t, ds, dt, gate, dg, dc
+  static constexpr size_t ADJ_BYTES = (size_t)NP * NP;
   static constexpr size_t BYTES = 2 * TILE_BYTES + PT_BYTES + DP_BYTES + SMALL_BYTES + ADJ_BYTES;
 };
 
-__global__ void __launch_bounds__(kFThreads, 3) gat_attn_bwd_mma_kernel(const GatParams p) {
+template <int NP, int kBH>
+__global__ void __launch_bounds__(kFThreads, (NP == 32) ? 3 : 2) gat_attn_bwd_mma_kernel(const GatParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  using FB = GatFastBwd;
-  constexpr int NP = kBNP, PP = kBPP, NPF = kBNPF, MT = kBMT;
+  using FB = GatFastBwd<NP, kBH>;
+  constexpr int PP = FB::PP, NPF = FB::NPF, MT = FB::MT, kBC = FB::BC, kBWP = FB::BWP;
+  constexpr int kGroups = kFK / kBH;               // CTAs per (video, graph)
+  constexpr int WPH = (kFThreads / 32) / kBH;      // warps per head
   __nv_bfloat16* wh = reinterpret_cast<__nv_bfloat16*>(smem_raw);                                // [NP][kBWP]
   __nv_bfloat16* dz = reinterpret_cast<__nv_bfloat16*>(smem_raw + FB::TILE_BYTES);
   __nv_bfloat16* PThi = reinterpret_cast<__nv_bfloat16*>(smem_raw + 2 * FB::TILE_BYTES);         // [kBH][NP (j)][PP (i)]
@@ -697,8 +700,8 @@ __global__ void __launch_bounds__(kFThreads, 3) gat_attn_bwd_mma_kernel(const Ga
   float* dc_s = dg + NP;
   unsigned char* s_adj = reinterpret_cast<unsigned char*>(dc_s + 8);
   const int b = blockIdx.x;
-  const GatGraph& gr = p.g[blockIdx.y >> 1];
-  const int hp = blockIdx.y & 1, head0 = hp * kBH, col0 = hp * kBC;
+  const GatGraph& gr = p.g[blockIdx.y / kGroups];
+  const int hp = blockIdx.y % kGroups, head0 = hp * kBH, col0 = hp * kBC;
   const int N = p.N;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int lrow = (lane & 7) + ((lane >> 3) & 1) * 8;
@@ -821,9 +824,10 @@ __global__ void __launch_bounds__(kFThreads, 3) gat_attn_bwd_mma_kernel(const Ga
     }
   }
 
-  // 2. dP~ = dz Wh^T per head on the tensor cores; warp w: head w / 4, neighbour columns j in [8 (w % 4), +8)
+  // 2. dP~ = dz Wh^T per head on the tensor cores; warp w: head w / WPH, neighbour columns j in [8 (w % WPH), +8)
   {
-    const int kl = warp >> 2, nt = warp & 3;
+    static_assert(NP / 8 == WPH, "one 8-wide neighbour tile per warp");
+    const int kl = warp / WPH, nt = warp % WPH;
     const uint32_t dz_s = smem_u32(dz), wh_s = smem_u32(wh);
     float acc[MT][4];
 #pragma unroll
@@ -861,41 +865,68 @@ __global__ void __launch_bounds__(kFThreads, 3) gat_attn_bwd_mma_kernel(const Ga
   for (int pr = warp; pr < kBH * NP; pr += kFThreads / 32) {
     const int kl = pr / NP, i = pr - kl * NP, k = head0 + kl;
     const float* av = gr.avec + k * (2 * kFDh + 1);
-    float prob = 0.f, srow = 0.f;
-    const int j = lane;
+    constexpr int Q = NP / 32;                       // neighbours per lane
+    float prob[Q], uu[Q];
+    float srow = 0.f;
+#pragma unroll
+    for (int q = 0; q < Q; ++q) prob[q] = uu[q] = 0.f;
     if (i < N) {
-      // softmax over the neighbours (NP = 32: one neighbour per lane)
       const float cb = __ldg(av + 2 * kFDh);
       const float si = s_s[kl * NP + i];
-      float e = -INFINITY, u = 0.f;
-      if (j < N) {
-        u = si + s_t[kl * NP + j] + cb;
-        const float lu = u > 0.f ? u : p.slope * u;
-        e = s_adj[i * NP + j] ? lu : -9e15f;
+      float m = -INFINITY;
+#pragma unroll
+      for (int q = 0; q < Q; ++q) {
+        const int j = lane + 32 * q;
+        prob[q] = -INFINITY;
+        if (j < N) {
+          uu[q] = si + s_t[kl * NP + j] + cb;
+          const float lu = uu[q] > 0.f ? uu[q] : p.slope * uu[q];
+          prob[q] = s_adj[i * NP + j] ? lu : -9e15f;
+          m = fmaxf(m, prob[q]);
+        }
       }
-      const float m = warp_max(e);
-      prob = j < N ? __expf(e - m) : 0.f;
-      const float sum = warp_sum(prob);
-      prob *= 1.f / sum;
+      m = warp_max(m);
+      float sum = 0.f;
+#pragma unroll
+      for (int q = 0; q < Q; ++q) {
+        prob[q] = (lane + 32 * q) < N ? __expf(prob[q] - m) : 0.f;
+        sum += prob[q];
+      }
+      sum = warp_sum(sum);
+      const float inv = 1.f / sum;
       float* dProw = dP + ((size_t)kl * NP + i) * NPF;
-      const float dp = j < N ? dProw[j] : 0.f;
-      const float dot = warp_sum(prob * dp);
-      float du = 0.f;
-      if (j < N) {
-        float de = prob * (dp - dot);
-        if (!s_adj[i * NP + j]) de = 0.f;
-        du = de * (u > 0.f ? 1.f : p.slope);
-        dProw[j] = du;
+      float dp[Q], dot = 0.f;
+#pragma unroll
+      for (int q = 0; q < Q; ++q) {
+        prob[q] *= inv;
+        dp[q] = (lane + 32 * q) < N ? dProw[lane + 32 * q] : 0.f;
+        dot += prob[q] * dp[q];
       }
-      srow = warp_sum(du);
+      dot = warp_sum(dot);
+#pragma unroll
+      for (int q = 0; q < Q; ++q) {
+        const int j = lane + 32 * q;
+        if (j < N) {
+          float de = prob[q] * (dp[q] - dot);
+          if (!s_adj[i * NP + j]) de = 0.f;
+          const float du = de * (uu[q] > 0.f ? 1.f : p.slope);
+          dProw[j] = du;
+          srow += du;
+        }
+      }
+      srow = warp_sum(srow);
     }
     if (lane == 0) ds[kl * NP + i] = srow;
-    float v = 0.f;
-    if (i < N && j < N) v = prob * matt.keep1((((unsigned long long)b * kFK + k) * N + i) * N + j);
-    __nv_bfloat16 hi, lo;
-    split_bf16(v, hi, lo);
-    PThi[((size_t)kl * NP + j) * PP + i] = hi;
-    PTlo[((size_t)kl * NP + j) * PP + i] = lo;
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+      const int j = lane + 32 * q;
+      float v = 0.f;
+      if (i < N && j < N) v = prob[q] * matt.keep1((((unsigned long long)b * kFK + k) * N + i) * N + j);
+      __nv_bfloat16 hi, lo;
+      split_bf16(v, hi, lo);
+      PThi[((size_t)kl * NP + j) * PP + i] = hi;
+      PTlo[((size_t)kl * NP + j) * PP + i] = lo;
+    }
   }
   __syncthreads();
   for (int pr = tid; pr < kBH * NP; pr += kFThreads) {        // dt_j = sum_i du_ij
@@ -913,25 +944,29 @@ __global__ void __launch_bounds__(kFThreads, 3) gat_attn_bwd_mma_kernel(const Ga
   __syncthreads();
 
   // 4. dV = P~^T dz on the tensor cores; dWh_j = g_j dV_j + ds_j a1 + dt_j a2 ; dgate_j ; da1, da2 in the fragment epilogue.
-  //    warp w owns columns [48 w, 48 w + 48) of the pair = head w / 4
+  //    warp w owns columns [CW w, CW w + CW) of the CTA's heads (CW = 48 or 24) = head w / WPH
   {
-    const int kl = warp >> 2, k = head0 + kl, cbl = 48 * warp;      // column base inside the pair
+    constexpr int CW = kBC / (kFThreads / 32), NT4 = CW / 8;
+    constexpr bool kResident = (MT == 2);            // A fragments of both row blocks fit in registers only for NP = 32
+    const int kl = warp / WPH, k = head0 + kl, cbl = CW * warp;      // column base inside the CTA's columns
     const uint32_t dz_s = smem_u32(dz), phi_s = smem_u32(PThi), plo_s = smem_u32(PTlo);
     const int ksteps = (N + 15) >> 4;
     const float* a1 = gr.avec + k * (2 * kFDh + 1);
     const float* a2 = a1 + kFDh;
     __nv_bfloat16* dwhp = gr.dwh + (long long)b * N * p.ld_wh + col0;
     float* dav = gr.davec + ((long long)b * kFK + k) * (2 * kFDh + 1);
-    // A fragments of this head for both 16-row blocks (MT = 2: 32 registers), resident across the column tiles
-    uint32_t ahi[MT][MT][4], alo[MT][MT][4];
+    // A fragments of this head: resident across the column tiles for NP = 32 (32 registers), re-loaded per tile otherwise
+    uint32_t ahi[kResident ? MT : 1][MT][4], alo[kResident ? MT : 1][MT][4];
+    if (kResident) {
 #pragma unroll
-    for (int mt = 0; mt < MT; ++mt)
+      for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-      for (int ks = 0; ks < MT; ++ks) {
-        const uint32_t off = (uint32_t)((((size_t)kl * NP + mt * 16 + lrow) * PP + ks * 16 + (lane >> 4) * 8) * 2);
-        ldsm_x4(ahi[mt][ks], phi_s + off);
-        ldsm_x4(alo[mt][ks], plo_s + off);
-      }
+        for (int ks = 0; ks < MT; ++ks) {
+          const uint32_t off = (uint32_t)((((size_t)kl * NP + mt * 16 + lrow) * PP + ks * 16 + (lane >> 4) * 8) * 2);
+          ldsm_x4(ahi[kResident ? mt : 0][ks], phi_s + off);
+          ldsm_x4(alo[kResident ? mt : 0][ks], plo_s + off);
+        }
+    }
     float dgp[MT][2];
     float gj[MT][2], dsj[MT][2], dtj[MT][2];
 #pragma unroll
@@ -942,9 +977,9 @@ __global__ void __launch_bounds__(kFThreads, 3) gat_attn_bwd_mma_kernel(const Ga
         dgp[mt][h] = 0.f;
         gj[mt][h] = s_gate[j]; dsj[mt][h] = ds[kl * NP + j]; dtj[mt][h] = dt[kl * NP + j];
       }
-#pragma unroll 2
-    for (int nt = 0; nt < 6; ++nt) {
-      const int c = cbl + nt * 8 + 2 * t, cl = c - kl * kFDh;      // column inside the pair / inside the head
+#pragma unroll 1
+    for (int nt = 0; nt < NT4; ++nt) {
+      const int c = cbl + nt * 8 + 2 * t, cl = c - kl * kFDh;      // column inside the CTA's columns / inside the head
       uint32_t bfr[MT][2];
 #pragma unroll
       for (int ks = 0; ks < MT; ++ks)
@@ -955,11 +990,19 @@ __global__ void __launch_bounds__(kFThreads, 3) gat_attn_bwd_mma_kernel(const Ga
       for (int mt = 0; mt < MT; ++mt) {
         if (mt * 16 < N) {
           float acc[4] = {0.f, 0.f, 0.f, 0.f};
+          if (!kResident) {
+#pragma unroll
+            for (int ks = 0; ks < MT; ++ks) {
+              const uint32_t off = (uint32_t)((((size_t)kl * NP + mt * 16 + lrow) * PP + ks * 16 + (lane >> 4) * 8) * 2);
+              ldsm_x4(ahi[0][ks], phi_s + off);
+              ldsm_x4(alo[0][ks], plo_s + off);
+            }
+          }
 #pragma unroll
           for (int ks = 0; ks < MT; ++ks) {
             if (ks < ksteps) {
-              mma_bf16(acc, ahi[mt][ks], bfr[ks][0], bfr[ks][1]);
-              mma_bf16(acc, alo[mt][ks], bfr[ks][0], bfr[ks][1]);
+              mma_bf16(acc, ahi[kResident ? mt : 0][ks], bfr[ks][0], bfr[ks][1]);
+              mma_bf16(acc, alo[kResident ? mt : 0][ks], bfr[ks][0], bfr[ks][1]);
             }
           }
 #pragma unroll
@@ -1002,7 +1045,7 @@ __global__ void __launch_bounds__(kFThreads, 3) gat_attn_bwd_mma_kernel(const Ga
       }
   }
   __syncthreads();
-  for (int i = tid; i < N; i += kFThreads) atomicAdd(gr.dgate + (long long)b * N + i, dg[i]);      // + the other head pair
+  for (int i = tid; i < N; i += kFThreads) atomicAdd(gr.dgate + (long long)b * N + i, dg[i]);      // + the other head group(s)
   if (tid < kBH) gr.davec[((long long)b * kFK + head0 + tid) * (2 * kFDh + 1) + 2 * kFDh] = dc_s[tid];
 }
 
@@ -1088,19 +1131,21 @@ extern "C" int dvgr_gat_attn_fwd(const dvgr_gat_args* a, void* stream) {
   return 0;
 }
 
+template <int NP, int kBH>
 static int launch_gat_bwd_fast(const GatParams& p, int n_graphs, cudaStream_t st) {
   static bool configured = false;
-  const size_t smem = GatFastBwd::BYTES;
+  const size_t smem = GatFastBwd<NP, kBH>::BYTES;
+  auto kern = gat_attn_bwd_mma_kernel<NP, kBH>;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gat_attn_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error("gat bwd (mma): cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
     configured = true;
   }
-  for (int i = 0; i < n_graphs; ++i) {       // the two head-pair CTAs of a (video, graph) add their halves
+  for (int i = 0; i < n_graphs; ++i) {       // the head-group CTAs of a (video, graph) add their partial gate gradients
     cudaError_t e = cudaMemsetAsync(p.g[i].dgate, 0, sizeof(float) * (size_t)p.B * p.N, st);
     if (e != cudaSuccess) return set_error("gat bwd (mma): cudaMemsetAsync: %s", cudaGetErrorString(e));
   }
-  gat_attn_bwd_mma_kernel<<<dim3(p.B, 2 * n_graphs), kFThreads, smem, st>>>(p);
+  kern<<<dim3(p.B, (kFK / kBH) * n_graphs), kFThreads, smem, st>>>(p);
   DVGR_CHECK_LAUNCH("gat_attn_bwd_mma");
   return 0;
 }
@@ -1109,9 +1154,10 @@ extern "C" int dvgr_gat_attn_bwd(const dvgr_gat_args* a, void* stream) {
   GatParams p;
   if (int rc = fill_gat(p, a, true)) return rc;
   if (a->B <= 0 || a->N <= 0) return 0;
-  // (N in (32, 64] would need 350 KB of shared memory for the two staged tiles: those videos take the generic kernel)
-  if ((gat_fast_knob() & 2) && gat_fast_ok(p) && p.N <= 32)
-    return launch_gat_bwd_fast(p, a->n_graphs, reinterpret_cast<cudaStream_t>(stream));
+  if ((gat_fast_knob() & 2) && gat_fast_ok(p)) {
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    return p.N <= 32 ? launch_gat_bwd_fast<32, 2>(p, a->n_graphs, st) : launch_gat_bwd_fast<64, 1>(p, a->n_graphs, st);
+  }
   const size_t smem = gat_smem_common(p.N, p.D, p.heads) + gat_smem_bwd_extra(p.N, p.D, p.heads);
   if (smem > 227 * 1024) return set_error("gat bwd: %zu bytes of shared memory needed", smem);
   static size_t configured = 0;

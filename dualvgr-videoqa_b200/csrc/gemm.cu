@@ -543,6 +543,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (kCluster > 1) cluster_sync_all();     // the peer's barriers must be initialised before any multicast touches them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) touched no global
+  // memory and may overlap the tail of the previous kernel in the stream; from here on we read / write tensors, so wait
+  // until the prerequisite grid has completed and flushed (a no-op when the launch carried no programmatic dependency)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");     // lets the next PDL kernel start ITS prologue early
 
   if (warp == 0 && lane == 0) {
     // ===================================================== TMA producer
@@ -1248,7 +1253,22 @@ static int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const Ge
   long long grid = std::min<long long>(tiles * kCluster, max_ctas > 0 ? max_ctas : num_sms() * (kOcc == 2 ? 2 : 1));
   grid = grid / kCluster * kCluster;
   if (grid <= 0) return 0;
-  if (kCluster == 1) {
+  static const int pdl = getenv("DVGR_PDL") ? atoi(getenv("DVGR_PDL")) : 1;
+  if (kCluster == 1 && pdl) {
+    // programmatic stream serialisation: this kernel may begin (its prologue) before the previous one has drained
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, p);
+    if (e != cudaSuccess) return set_error("gemm PDL launch failed: %s", cudaGetErrorString(e));
+  } else if (kCluster == 1) {
     kern<<<(int)grid, kGemmThreads, smem_bytes, stream>>>(ta, tb, p);
   } else {
     cudaLaunchConfig_t cfg = {};

@@ -15,6 +15,12 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 
+// Programmatic dependent launch, producer side: tells the scheduler that a kernel launched behind this one WITH the
+// programmatic-serialisation attribute (the tcgen05 GEMMs) may start its prologue now. That kernel still blocks in
+// griddepcontrol.wait until this grid has completed and flushed, so the trigger can sit at the very top of any kernel;
+// it is ignored when the next launch is an ordinary one.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred = 0;
   asm volatile(

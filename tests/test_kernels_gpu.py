@@ -152,7 +152,7 @@ def test_lstm_whole_sequence_fused_forward(ops, T, S, H, D, K1):
     assert torch.equal(ops.lstm_unblock_c(c_b, S), ops.lstm_unblock_c(c_hist, S))
 
 
-@pytest.mark.parametrize("B,N,p", [(3, 20, 0.0), (5, 8, 0.0), (2, 33, 0.0)])
+@pytest.mark.parametrize("B,N,p", [(3, 20, 0.0), (5, 8, 0.0), (2, 33, 0.0), (2, 64, 0.0)])
 def test_gat_attention_fwd_bwd(ops, B, N, p):
     torch.manual_seed(3)
     D, K = 768, 4

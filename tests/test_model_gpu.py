@@ -151,12 +151,12 @@ def test_against_live_oracle_full_gradients(cfg):
     assert max(w for w, _ in worst) < 0.5, sorted(worst)[-5:]
 
 
-@pytest.mark.parametrize("cfg", [(3, 64, 8, 50, 60, 1), (4, 16, 8, 4002, 60, 1)])
+@pytest.mark.parametrize("cfg", [(8, 64, 8, 50, 60, 1), (8, 16, 8, 4002, 60, 1)])
 def test_against_live_oracle_other_baseline_shapes(cfg):
     """BASELINE configs 5 and 3 in miniature: 64-clip videos (the 64-node GAT forward variant + generic backward, 2-row-block
     LSTM tiles) and the MSRVTT-sized open-ended answer vocabulary (A = 4002: unaligned logits / classifier GEMM). Logits
-    and the global CE gradient against the oracle in float64; tiny batches, so the gradient gate is 1.5x (BatchNorm, see
-    test_against_reference_golden)."""
+    and the global CE gradient against the oracle in float64; B = 8 is still a small batch for the train-mode BatchNorm, so
+    the gradient gate is 1.5x (see test_against_reference_golden; measured 3.8e-2 at B = 3, 1.9e-2 at B = 6, 1.3e-2 at B = 24)."""
     B, N, L, A, V, U = cfg
     model, inputs, ans = build(cfg, training=True)
     out = model(*inputs)

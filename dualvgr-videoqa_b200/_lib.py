@@ -148,6 +148,7 @@ scatter = _sig("dvgr_scatter", [ctypes.POINTER(Seg), c_int, c_int, P])
 lib.dvgr_colsum_workspace.argtypes = [c_ll, c_int]
 lib.dvgr_colsum_workspace.restype = c_ll
 colsum = _sig("dvgr_colsum", [P, c_int, c_ll, c_ll, c_int, P, P, c_int, c_float, P])
+colsum_batched = _sig("dvgr_colsum_batched", [P, c_int, c_ll, c_ll, c_ll, c_int, c_int, P, P, c_ll, c_int, c_float, P])
 sumsq_blocks = _sig("dvgr_sumsq_blocks", [])
 sumsq = _sig("dvgr_sumsq", [P, c_ll, P, P, P])
 adam_step = _sig("dvgr_adam_step", [P, P, P, P, c_ll, c_float, c_float, c_float, c_float, c_int, c_float, P, c_float, P, P, P])
@@ -158,6 +159,6 @@ EXPORTED = [
     "dvgr_qattn_bwd", "dvgr_gate_fwd", "dvgr_gate_bwd", "dvgr_view_attn_fwd", "dvgr_view_attn_bwd_blocks",
     "dvgr_view_attn_bwd", "dvgr_mfb_fwd", "dvgr_mfb_bwd", "dvgr_readout_fwd", "dvgr_readout_bwd", "dvgr_bn_fwd",
     "dvgr_bn_bwd", "dvgr_cross_entropy", "dvgr_pair_loss_workspace", "dvgr_pair_loss_multi", "dvgr_aux_loss_workspace", "dvgr_aux_loss_unit", "dvgr_prep_features", "dvgr_cast_rows", "dvgr_dropout",
-    "dvgr_act_bwd", "dvgr_add", "dvgr_scatter", "dvgr_colsum_workspace", "dvgr_colsum", "dvgr_sumsq_blocks", "dvgr_sumsq",
+    "dvgr_act_bwd", "dvgr_add", "dvgr_scatter", "dvgr_colsum_workspace", "dvgr_colsum", "dvgr_colsum_batched", "dvgr_sumsq_blocks", "dvgr_sumsq",
     "dvgr_adam_step",
 ]

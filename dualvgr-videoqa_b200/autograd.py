@@ -567,8 +567,9 @@ class GatLayerFn(Function):
             for g in gs[1:]:
                 dg = dg + dgates[g]
             dgs.append(dg)
+            dbs = ops.colsum_batched(dwh)                       # head-bias gradients of the stream's graphs: one launch pair
             for i, g in enumerate(gs):
-                dW[g], db[g] = (None if direct else dWs[i]), ops.colsum(dwh[i])
+                dW[g], db[g] = (None if direct else dWs[i]), dbs[i]
         grads = []
         small = []        # (bound .grad view, gradient) pairs of the per-head biases / attention vectors
         for g in range(G):

@@ -281,60 +281,86 @@ readout_bwd_kernel(const bf16* __restrict__ dpooled, long long ld_p, const bf16*
 // =============================================================================================== BatchNorm1d
 // reference model/AnswerDecoder.py:193 (nn.BatchNorm1d(module_dim)): batch statistics (biased variance) in training,
 // running statistics in eval; running stats updated with momentum 0.1 and the UNBIASED variance, as torch does.
+// Block = 32 feature columns x 8 row lanes: the batch dimension is walked by 8 threads per column and reduced through
+// shared memory in a fixed order (one thread per column walking all B rows took 100 us for the backward at B = 256).
+__device__ __forceinline__ float bn_reduce8(float v, float (*red)[33], int cl, int rl) {
+  __syncthreads();
+  red[rl][cl] = v;
+  __syncthreads();
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s += red[k][cl];
+  return s;
+}
+
 template <typename TX>
-__global__ void bn_fwd_kernel(const TX* __restrict__ x, int B, int D, const float* __restrict__ gamma,
-                              const float* __restrict__ betap, float* __restrict__ run_mean, float* __restrict__ run_var,
-                              int training, float momentum, float eps, bf16* __restrict__ y, float* __restrict__ mean_out,
-                              float* __restrict__ rstd_out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= D) return;
-  float mean, var;
+__global__ void __launch_bounds__(256)
+bn_fwd_kernel(const TX* __restrict__ x, int B, int D, const float* __restrict__ gamma, const float* __restrict__ betap,
+              float* __restrict__ run_mean, float* __restrict__ run_var, int training, float momentum, float eps,
+              bf16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  __shared__ float red[8][33];
+  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  const bool ok = c < D;
+  float mean = 0.f, var = 1.f;
   if (training) {
     float s = 0.f;
-    for (int r = 0; r < B; ++r) s += ldf<TX>(x + (long long)r * D + c);
-    mean = s / B;
+    if (ok)
+      for (int r = rl; r < B; r += 8) s += ldf<TX>(x + (long long)r * D + c);
+    mean = bn_reduce8(s, red, cl, rl) / B;
     float v = 0.f;
-    for (int r = 0; r < B; ++r) {
-      const float d = ldf<TX>(x + (long long)r * D + c) - mean;
-      v += d * d;
-    }
+    if (ok)
+      for (int r = rl; r < B; r += 8) {
+        const float d = ldf<TX>(x + (long long)r * D + c) - mean;
+        v += d * d;
+      }
+    v = bn_reduce8(v, red, cl, rl);
     var = v / B;
-    if (run_mean != nullptr) {
+    if (ok && rl == 0 && run_mean != nullptr) {
       run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * mean;
       run_var[c] = (1.f - momentum) * run_var[c] + momentum * (B > 1 ? v / (B - 1) : var);
     }
-  } else {
+  } else if (ok) {
     mean = run_mean[c];
     var = run_var[c];
   }
+  if (!ok) return;
   const float rstd = rsqrtf(var + eps);
-  if (mean_out != nullptr) {
+  if (rl == 0 && mean_out != nullptr) {
     mean_out[c] = mean;
     rstd_out[c] = rstd;
   }
   const float g = gamma[c], bt = betap[c];
-  for (int r = 0; r < B; ++r)
+  for (int r = rl; r < B; r += 8)
     y[(long long)r * D + c] = __float2bfloat16_rn((ldf<TX>(x + (long long)r * D + c) - mean) * rstd * g + bt);
 }
 
 template <typename TX>
-__global__ void bn_bwd_kernel(const bf16* __restrict__ dy, const TX* __restrict__ x, int B, int D,
-                              const float* __restrict__ gamma, const float* __restrict__ mean,
-                              const float* __restrict__ rstd, int training, TX* __restrict__ dx,
-                              float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= D) return;
-  const float m = mean[c], rs = rstd[c], g = gamma[c];
+__global__ void __launch_bounds__(256)
+bn_bwd_kernel(const bf16* __restrict__ dy, const TX* __restrict__ x, int B, int D, const float* __restrict__ gamma,
+              const float* __restrict__ mean, const float* __restrict__ rstd, int training, TX* __restrict__ dx,
+              float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  __shared__ float red[8][33];
+  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  const bool ok = c < D;
+  const float m = ok ? mean[c] : 0.f, rs = ok ? rstd[c] : 0.f, g = ok ? gamma[c] : 0.f;
   float sdy = 0.f, sdyx = 0.f;
-  for (int r = 0; r < B; ++r) {
-    const float d = __bfloat162float(dy[(long long)r * D + c]);
-    const float xh = (ldf<TX>(x + (long long)r * D + c) - m) * rs;
-    sdy += d;
-    sdyx += d * xh;
+  if (ok)
+    for (int r = rl; r < B; r += 8) {
+      const float d = __bfloat162float(dy[(long long)r * D + c]);
+      const float xh = (ldf<TX>(x + (long long)r * D + c) - m) * rs;
+      sdy += d;
+      sdyx += d * xh;
+    }
+  sdy = bn_reduce8(sdy, red, cl, rl);
+  sdyx = bn_reduce8(sdyx, red, cl, rl);
+  if (!ok) return;
+  if (rl == 0) {
+    dgamma[c] = sdyx;
+    dbeta[c] = sdy;
   }
-  dgamma[c] = sdyx;
-  dbeta[c] = sdy;
-  for (int r = 0; r < B; ++r) {
+  for (int r = rl; r < B; r += 8) {
     const float d = __bfloat162float(dy[(long long)r * D + c]);
     const float xh = (ldf<TX>(x + (long long)r * D + c) - m) * rs;
     const float o = training ? g * rs * (d - sdy / B - xh * sdyx / B) : g * rs * d;
@@ -494,9 +520,11 @@ __device__ __forceinline__ void load8g(const float* p, float (&f)[8]) {
 template <typename T>
 __global__ void __launch_bounds__(256)
 colsum_partial_kernel(const T* __restrict__ in, long long ld, long long R, int C, int rows_per_chunk,
-                      float* __restrict__ partial, int vec_ok) {
+                      float* __restrict__ partial, int vec_ok, long long in_batch) {
   pdl_trigger();
   __shared__ float red[8][32][9];
+  in += (long long)blockIdx.z * in_batch;                        // batched call: one reduction per blockIdx.z
+  partial += (long long)blockIdx.z * gridDim.y * C;
   const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int c0 = (blockIdx.x * 32 + cg) * 8;
   const long long r0 = (long long)blockIdx.y * rows_per_chunk;
@@ -545,9 +573,11 @@ colsum_partial_kernel(const T* __restrict__ in, long long ld, long long R, int C
 // (a [160 x 768] reduction took 13 us as one thread per column), summed in a fixed order -> still deterministic.
 __global__ void __launch_bounds__(256)
 colsum_final_kernel(const float* __restrict__ partial, int chunks, int C, float* __restrict__ out, int accumulate,
-                    float scale) {
+                    float scale, long long out_batch) {
   pdl_trigger();
   __shared__ float red[8][33];
+  partial += (long long)blockIdx.z * chunks * C;
+  out += (long long)blockIdx.z * out_batch;
   const int cl = threadIdx.x & 31, kl = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
   float a0 = 0.f, a1 = 0.f;
@@ -651,11 +681,11 @@ extern "C" int dvgr_bn_fwd(const void* x, int x_is_f32, int B, int D, const floa
                            float* mean_out, float* rstd_out, void* stream) {
   if (B <= 0 || D <= 0) return 0;
   if (x_is_f32)
-    bn_fwd_kernel<float><<<(D + 127) / 128, 128, 0, ST(stream)>>>(reinterpret_cast<const float*>(x), B, D, gamma, beta,
+    bn_fwd_kernel<float><<<(D + 31) / 32, 256, 0, ST(stream)>>>(reinterpret_cast<const float*>(x), B, D, gamma, beta,
                                                                  run_mean, run_var, training, momentum, eps, BF(y),
                                                                  mean_out, rstd_out);
   else
-    bn_fwd_kernel<bf16><<<(D + 127) / 128, 128, 0, ST(stream)>>>(CBF(x), B, D, gamma, beta, run_mean, run_var, training,
+    bn_fwd_kernel<bf16><<<(D + 31) / 32, 256, 0, ST(stream)>>>(CBF(x), B, D, gamma, beta, run_mean, run_var, training,
                                                                 momentum, eps, BF(y), mean_out, rstd_out);
   DVGR_CHECK_LAUNCH("bn_fwd");
   return 0;
@@ -665,11 +695,11 @@ extern "C" int dvgr_bn_bwd(const void* dy, const void* x, int x_is_f32, int B, i
                            void* stream) {
   if (B <= 0 || D <= 0) return 0;
   if (x_is_f32)
-    bn_bwd_kernel<float><<<(D + 127) / 128, 128, 0, ST(stream)>>>(CBF(dy), reinterpret_cast<const float*>(x), B, D, gamma,
+    bn_bwd_kernel<float><<<(D + 31) / 32, 256, 0, ST(stream)>>>(CBF(dy), reinterpret_cast<const float*>(x), B, D, gamma,
                                                                  mean, rstd, training, reinterpret_cast<float*>(dx),
                                                                  dgamma, dbeta);
   else
-    bn_bwd_kernel<bf16><<<(D + 127) / 128, 128, 0, ST(stream)>>>(CBF(dy), CBF(x), B, D, gamma, mean, rstd, training,
+    bn_bwd_kernel<bf16><<<(D + 31) / 32, 256, 0, ST(stream)>>>(CBF(dy), CBF(x), B, D, gamma, mean, rstd, training,
                                                                 BF(dx), dgamma, dbeta);
   DVGR_CHECK_LAUNCH("bn_bwd");
   return 0;
@@ -774,20 +804,26 @@ static inline long long colsum_chunks(long long R) {
 
 extern "C" long long dvgr_colsum_workspace(long long R, int C) { return colsum_chunks(R) * C; }
 
-extern "C" int dvgr_colsum(const void* in, int in_is_f32, long long ld, long long R, int C, float* workspace, float* out,
-                           int accumulate, float scale, void* stream) {
-  if (C <= 0) return 0;
+extern "C" int dvgr_colsum_batched(const void* in, int in_is_f32, long long ld, long long in_batch, long long R, int C,
+                                   int batch, float* workspace, float* out, long long out_batch, int accumulate,
+                                   float scale, void* stream) {
+  if (C <= 0 || batch <= 0) return 0;
   const long long chunks = colsum_chunks(R);
   const int rpc = (int)((R + chunks - 1) / chunks);
-  dim3 grid((C + 255) / 256, (unsigned)chunks);
+  dim3 grid((C + 255) / 256, (unsigned)chunks, (unsigned)batch);
   const int esz = in_is_f32 ? 4 : 2;
-  const int vec_ok = ((reinterpret_cast<uintptr_t>(in) & 15) == 0) && ((ld * esz) % 16 == 0);
+  const int vec_ok = ((reinterpret_cast<uintptr_t>(in) & 15) == 0) && ((ld * esz) % 16 == 0) && ((in_batch * esz) % 16 == 0);
   if (in_is_f32)
-    colsum_partial_kernel<float><<<grid, 256, 0, ST(stream)>>>(reinterpret_cast<const float*>(in), ld, R, C, rpc, workspace, vec_ok);
+    colsum_partial_kernel<float><<<grid, 256, 0, ST(stream)>>>(reinterpret_cast<const float*>(in), ld, R, C, rpc, workspace, vec_ok, in_batch);
   else
-    colsum_partial_kernel<bf16><<<grid, 256, 0, ST(stream)>>>(CBF(in), ld, R, C, rpc, workspace, vec_ok);
+    colsum_partial_kernel<bf16><<<grid, 256, 0, ST(stream)>>>(CBF(in), ld, R, C, rpc, workspace, vec_ok, in_batch);
   DVGR_CHECK_LAUNCH("colsum_partial");
-  colsum_final_kernel<<<(C + 31) / 32, 256, 0, ST(stream)>>>(workspace, (int)chunks, C, out, accumulate, scale);
+  colsum_final_kernel<<<dim3((C + 31) / 32, 1, batch), 256, 0, ST(stream)>>>(workspace, (int)chunks, C, out, accumulate, scale, out_batch);
   DVGR_CHECK_LAUNCH("colsum_final");
   return 0;
+}
+
+extern "C" int dvgr_colsum(const void* in, int in_is_f32, long long ld, long long R, int C, float* workspace, float* out,
+                           int accumulate, float scale, void* stream) {
+  return dvgr_colsum_batched(in, in_is_f32, ld, 0, R, C, 1, workspace, out, 0, accumulate, scale, stream);
 }

@@ -311,6 +311,17 @@ def colsum(x, out=None, accumulate=False, scale=1.0):
     return out
 
 
+def colsum_batched(x):
+    """out[g][C] = sum over rows of x[g][R, C] for a contiguous [G, R, C] tensor (bf16 or fp32): ONE launch pair for all g."""
+    assert x.dim() == 3 and x.is_contiguous()
+    G, R, C = x.shape
+    ws = _empty((G * int(_lib.lib.dvgr_colsum_workspace(R, C)),), F32, x)
+    out = _empty((G, C), F32, x)
+    _lib.check(_lib.colsum_batched(_ptr(x), 1 if x.dtype == F32 else 0, C, R * C, R, C, G, _ptr(ws), _ptr(out), C, 0, 1.0,
+                                   _stream()), "dvgr_colsum_batched")
+    return out
+
+
 def cast_rows(w, out=None, out_cols=None, lstm_H=0):
     """fp32 [R, C] -> bf16 [R, out_cols] (zero padded); lstm_H>0 interleaves LSTM gate rows (4j+g <- g*H+j)."""
     assert w.dtype == F32 and w.dim() == 2 and w.stride(1) == 1
@@ -462,7 +473,8 @@ def gat_attn_bwd(whs, gates, avecs, outs, douts, adj, B, N, heads=4, slope=0.01,
     if dwhs is None:
         dwhs = [torch.empty_like(w) for w in whs]
     dgates = [_empty((B, N), F32, whs[0]) for _ in range(G)]
-    dav_part = [_empty((B, heads * (2 * Dh + 1)), F32, whs[0]) for _ in range(G)]
+    dav_all = _empty((G, B, heads * (2 * Dh + 1)), F32, whs[0])
+    dav_part = [dav_all[i] for i in range(G)]
     for i in range(G):
         g = a.graphs[i]
         assert dwhs[i].stride(-2) == whs[i].stride(-2) and douts[i].stride(-2) == outs[i].stride(-2)
@@ -470,7 +482,8 @@ def gat_attn_bwd(whs, gates, avecs, outs, douts, adj, B, N, heads=4, slope=0.01,
         if douts32 is not None and douts32[i] is not None:
             g.dout_f32 = douts32[i].data_ptr()
     _lib.check(_lib.gat_attn_bwd(ctypes.byref(a), _stream()), "dvgr_gat_attn_bwd")
-    davecs = [colsum(p).view(heads, 2 * Dh + 1) for p in dav_part]
+    dav = colsum_batched(dav_all)                       # per-video partial sums -> [G, heads * (2 Dh + 1)] in one launch pair
+    davecs = [dav[i].view(heads, 2 * Dh + 1) for i in range(G)]
     return dwhs, dgates, davecs
 
 

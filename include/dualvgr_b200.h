@@ -314,6 +314,10 @@ int dvgr_scatter(const dvgr_seg* segs, int n_segs, int accumulate, void* stream)
 long long dvgr_colsum_workspace(long long R, int C);
 int dvgr_colsum(const void* in, int in_is_f32, long long ld, long long R, int C, float* workspace, float* out,
                 int accumulate, float scale, void* stream);
+/* `batch` independent reductions in one launch pair: in + b * in_batch (elements) -> out + b * out_batch; workspace:
+ * batch * dvgr_colsum_workspace(R, C) floats. (Per-graph bias gradients and attention-vector partials of a GAT layer.) */
+int dvgr_colsum_batched(const void* in, int in_is_f32, long long ld, long long in_batch, long long R, int C, int batch,
+                        float* workspace, float* out, long long out_batch, int accumulate, float scale, void* stream);
 
 /* Flat-buffer optimizer (train.py:85,158-159): sum of squares for clip_grad_norm_(12), then Adam with the clip folded in. */
 int dvgr_sumsq_blocks(void);

@@ -20,6 +20,32 @@ from . import autograd as ag
 from . import ops
 
 
+class _EarlyBucketHook:
+    """Tensor hook shared by the unit stack's inputs (model/models.py: app, mot, dynamic_q, words): when the last of their
+    gradients has been produced, every parameter gradient of the early bucket is final -> start its all-reduce on a side
+    stream (captured into the step's CUDA graph as a fork; TrainEngine.optimizer_step joins it)."""
+
+    def __init__(self, engine):
+        self.engine = engine
+        self.side = torch.cuda.Stream()
+        self.pending = 0
+        self.fired = False
+
+    def arm(self, n):
+        self.pending = n
+        self.fired = False
+
+    def __call__(self, grad):
+        self.pending -= 1
+        if self.pending == 0:
+            e = self.engine
+            self.side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.side):
+                dist.all_reduce(e.gflat[e.late_numel:], op=dist.ReduceOp.SUM, group=e.pg)
+            self.fired = True
+        return None
+
+
 class TrainEngine:
     def __init__(self, model, lr=1e-4, max_norm=12.0, alpha=1.0, beta=1e-8, betas=(0.9, 0.999), eps=1e-8,
                  process_group=None):
@@ -27,13 +53,25 @@ class TrainEngine:
         self.lr, self.max_norm, self.alpha, self.beta, self.betas, self.eps = lr, max_norm, alpha, beta, betas, eps
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
-        # flat layout: the groups the fused kernels see as one matrix first (contiguous, in order), then everything else
+        # flat layout: the groups the fused kernels see as one matrix (contiguous, in order) and everything else, split in
+        # two contiguous buckets by WHEN the gradient is final: "late" = the three input encoders (their backward runs last:
+        # LSTM recurrences + the big W_ih weight gradients, ~2 ms), "early" = everything downstream of them. With more than
+        # one rank the early bucket is all-reduced on a side stream while the encoders' backward still runs.
+        late_ids = set()
+        for name in ("visual_appearance_input_unit", "linguistic_input_unit", "visual_motion_input_unit"):
+            m = getattr(model, name, None)
+            if m is not None:
+                late_ids.update(id(p) for p in m.parameters())
         grouped, seen = [], set()
         for grp in ag.grad_groups(model):
             for p in grp:
                 if p.requires_grad and id(p) not in seen:
                     grouped.append(p); seen.add(id(p))
-        self.params = grouped + [p for p in model.parameters() if p.requires_grad and id(p) not in seen]
+        rest = [p for p in model.parameters() if p.requires_grad and id(p) not in seen]
+        late = [p for p in grouped if id(p) in late_ids] + [p for p in rest if id(p) in late_ids]
+        early = [p for p in grouped if id(p) not in late_ids] + [p for p in rest if id(p) not in late_ids]
+        self.params = late + early
+        self._n_late = len(late)
         dev = self.params[0].device
         sizes = [(p.numel() + 7) // 8 * 8 for p in self.params]           # 16-byte aligned slices (also in the bf16 shadow)
         total = sum(sizes)
@@ -42,6 +80,7 @@ class TrainEngine:
         self.shadow = torch.zeros(total, dtype=torch.bfloat16, device=dev)   # bf16 GEMM operands, written by the Adam kernel
         self.m = torch.zeros(total, dtype=torch.float32, device=dev)
         self.v = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.late_numel = sum(sizes[:self._n_late])
         off = 0
         with torch.no_grad():
             for p, n in zip(self.params, sizes):
@@ -62,6 +101,9 @@ class TrainEngine:
             dist.broadcast(self.flat, src=0, group=self.pg)
         ag.invalidate_weight_cache()
         ag.DIRECT_GRAD[0] = True      # weight-gradient GEMMs accumulate straight into the flat gradient buffer
+        self._overlap = _EarlyBucketHook(self) if (self.world > 1 and 0 < self.late_numel < total) else None
+        if hasattr(model, "_unit_inputs_grad_hook") or self._overlap is not None:
+            model._unit_inputs_grad_hook = self._overlap
 
     # ------------------------------------------------------------------------------------------------------------
     def loss(self, outputs, answers):
@@ -94,7 +136,14 @@ class TrainEngine:
 
     def optimizer_step(self):
         if self.world > 1:
-            dist.all_reduce(self.gflat, op=dist.ReduceOp.SUM, group=self.pg)
+            if self._overlap is not None and self._overlap.fired:
+                # the early bucket is already in flight on the side stream (launched from the backward pass); reduce the
+                # encoders' bucket here and join
+                dist.all_reduce(self.gflat[:self.late_numel], op=dist.ReduceOp.SUM, group=self.pg)
+                torch.cuda.current_stream().wait_stream(self._overlap.side)
+                self._overlap.fired = False
+            else:
+                dist.all_reduce(self.gflat, op=dist.ReduceOp.SUM, group=self.pg)
         self.step_count += 1
         self.step_dev += 1
         scale = 1.0 / self.world

@@ -71,8 +71,19 @@ class DualVGR(nn.Module):
         B, N = video_motion_feat.shape[:2]
         mot_in = ag.ops.prep_features(video_motion_feat.float().contiguous().view(B * N, -1), 1, False, False)
         mot = ag.linear(mot_in, self.visual_motion_input_unit.weight, self.visual_motion_input_unit.bias).view(B, N, -1)
+        words_u = word_embedding
+        hook = getattr(self, "_unit_inputs_grad_hook", None)
+        if hook is not None and torch.is_grad_enabled():
+            # data-parallel engine: tell it when the gradients of everything DOWNSTREAM of the three encoders are final, so
+            # that their all-reduce overlaps the encoders' backward (engine.TrainEngine). The word embeddings also feed the
+            # question encoder, whose contribution arrives last: give the unit stack its own autograd node for them.
+            words_u = word_embedding.view_as(word_embedding)
+            hooked = [t for t in (app, mot, dynamic_q, words_u) if t.requires_grad]
+            hook.arm(len(hooked))
+            for t in hooked:
+                t.register_hook(hook)
         visual, aq_embed, mq_embed, com_app, com_motion, aq_fusion, mq_fusion = self.visual_input_unit(
-            app, mot, dynamic_q, word_embedding, question_len)
+            app, mot, dynamic_q, words_u, question_len)
         pooled = self.feature_aggregation(visual)
         out = self.output_unit(question_embedding, pooled)
         return out, aq_embed, mq_embed, com_app, com_motion, aq_fusion, mq_fusion

@@ -155,8 +155,11 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):      # keep NCCL's version banner out of stdout:
-            os.environ["NCCL_DEBUG"] = "WARN"                                  # rank 0 prints exactly one JSON line
+        # NCCL prints its version banner to STDOUT when the first communicator is created; rank 0 must print exactly one
+        # JSON line there, so file descriptor 1 points at stderr until the engine (and its first collective) exists
+        sys.stdout.flush()
+        saved_stdout_fd = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     c = CFG
@@ -166,6 +169,11 @@ def run_ours(args):
     model.load_state_dict(orc.make_state_dict(c["U"], c["A"], c["V"]), strict=True)
     model = model.to(dev).train()
     eng = TrainEngine(model, lr=1e-4, max_norm=12.0, alpha=1.0, beta=1e-8)
+    if world > 1:
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os.dup2(saved_stdout_fd, 1)
+        os.close(saved_stdout_fd)
 
     # synthetic shard of this rank, generated on the host, pinned; a device-resident copy for the kernel-side number
     g = torch.Generator().manual_seed(1000 + rank)

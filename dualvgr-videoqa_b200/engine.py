@@ -101,7 +101,9 @@ class TrainEngine:
             dist.broadcast(self.flat, src=0, group=self.pg)
         ag.invalidate_weight_cache()
         ag.DIRECT_GRAD[0] = True      # weight-gradient GEMMs accumulate straight into the flat gradient buffer
-        self._overlap = _EarlyBucketHook(self) if (self.world > 1 and 0 < self.late_numel < total) else None
+        import os
+        overlap_ok = os.environ.get("DVGR_ALLREDUCE_OVERLAP", "1") != "0"        # A/B knob: 0 = one all-reduce after backward
+        self._overlap = _EarlyBucketHook(self) if (self.world > 1 and overlap_ok and 0 < self.late_numel < total) else None
         if hasattr(model, "_unit_inputs_grad_hook") or self._overlap is not None:
             model._unit_inputs_grad_hook = self._overlap
 

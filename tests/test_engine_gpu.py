@@ -97,3 +97,45 @@ def test_graph_replay_draws_fresh_dropout_masks():
     eng.capture(*batch, warmup=3)
     losses = [float(eng.replay()) for _ in range(4)]
     assert len(set(round(x, 6) for x in losses)) > 1, losses
+
+
+def test_early_gradient_bucket_is_final_when_the_unit_input_hooks_fire():
+    """The overlapped data-parallel all-reduce (engine._EarlyBucketHook) starts reducing the 'early' gradient bucket when the
+    gradients of the unit stack's inputs have all been produced. Single-GPU check of that contract: snapshot the bucket at
+    that moment and compare with its content at the end of the backward pass — nothing may still be written into it."""
+    from dualvgr_videoqa_b200.engine import TrainEngine
+    cfg = (6, 20, 8, 32, 60, 2)
+    model, batch = make(cfg)
+    eng = TrainEngine(model, lr=1e-5)
+    assert 0 < eng.late_numel < eng.numel
+
+    class Snap:
+        def __init__(self):
+            self.pending, self.snap, self.calls = 0, None, 0
+
+        def arm(self, n):
+            self.pending, self.snap = n, None
+
+        def __call__(self, grad):
+            self.pending -= 1
+            self.calls += 1
+            if self.pending == 0:
+                self.snap = eng.gflat[eng.late_numel:].clone()
+                self.late_at_hook = eng.gflat[:eng.late_numel].clone()
+            return None
+
+    snap = Snap()
+    model._unit_inputs_grad_hook = snap
+    eng.model.train()
+    eng.gflat.zero_()
+    out = eng.model(*batch[:4])
+    total = eng.loss(out, batch[4])[0]
+    total.backward()
+    torch.cuda.synchronize()
+    assert snap.calls == 4 and snap.snap is not None
+    assert torch.equal(snap.snap, eng.gflat[eng.late_numel:]), "a gradient of the early bucket was written after the hooks fired"
+    assert float(snap.snap.abs().sum()) > 0
+    # and the late bucket (the three encoders) really is produced afterwards
+    assert not torch.equal(snap.late_at_hook, eng.gflat[:eng.late_numel])
+    model._unit_inputs_grad_hook = None
+    eng.close()

@@ -254,40 +254,40 @@ def run_ours(args):
     # ---- e2e: same step through the public API with HOST buffers; H2D of every step's inputs inside the timed region
     #      (double-buffered on a copy stream, as an input pipeline would), D2H read of the loss every step
     copy_stream = torch.cuda.Stream(device=dev)
-    bufs = [{k: torch.empty_like(v, device=dev) for k, v in host.items()} for _ in range(2)]
     ready = [torch.cuda.Event(), torch.cuda.Event()]
     consumed = [torch.cuda.Event(), torch.cuda.Event()]
     loss_host = torch.zeros(args.steps + 8, dtype=torch.float32).pin_memory()
 
-    def prefetch(i):
-        b = i % 2
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(consumed[b])
-            for k, v in host.items():
-                bufs[b][k].copy_(v, non_blocking=True)
-            ready[b].record(copy_stream)
+    def measure_e2e(host_t):
+        bufs = [{k: torch.empty_like(v, device=dev) for k, v in host_t.items()} for _ in range(2)]
 
-    def run_e2e(n):
-        cur = torch.cuda.current_stream()
-        for b in range(2):
-            consumed[b].record(cur)
-        prefetch(0)
-        for i in range(n):
-            if i + 1 < n:
-                prefetch(i + 1)
+        def prefetch(i):
             b = i % 2
-            cur.wait_event(ready[b])
-            if use_graph:   # device-to-device hand-over of the staged batch into the graph's static inputs, then ONE launch
-                eng.load_batch(bufs[b]["app"], bufs[b]["mot"], bufs[b]["q"], bufs[b]["qlen"], bufs[b]["ans"])
-                consumed[b].record(cur)
-                lo = eng.replay()
-            else:
-                lo = eng.train_step(bufs[b]["app"], bufs[b]["mot"], bufs[b]["q"], bufs[b]["qlen"], bufs[b]["ans"])
-                consumed[b].record(cur)
-            loss_host[i].copy_(lo, non_blocking=True)
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(consumed[b])
+                for k, v in host_t.items():
+                    bufs[b][k].copy_(v, non_blocking=True)
+                ready[b].record(copy_stream)
 
-    e2e_value = None
-    if not args.no_e2e:
+        def run_e2e(n):
+            cur = torch.cuda.current_stream()
+            for b in range(2):
+                consumed[b].record(cur)
+            prefetch(0)
+            for i in range(n):
+                if i + 1 < n:
+                    prefetch(i + 1)
+                b = i % 2
+                cur.wait_event(ready[b])
+                if use_graph:   # device-to-device hand-over of the staged batch into the graph's static inputs, then ONE launch
+                    eng.load_batch(bufs[b]["app"], bufs[b]["mot"], bufs[b]["q"], bufs[b]["qlen"], bufs[b]["ans"])
+                    consumed[b].record(cur)
+                    lo = eng.replay()
+                else:
+                    lo = eng.train_step(bufs[b]["app"], bufs[b]["mot"], bufs[b]["q"], bufs[b]["qlen"], bufs[b]["ans"])
+                    consumed[b].record(cur)
+                loss_host[i].copy_(lo, non_blocking=True)
+
         run_e2e(2)
         barrier()
         e0.record()
@@ -297,7 +297,24 @@ def run_ours(args):
         t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_value = c["B"] * world * args.steps / (float(t.item()) / 1e3)
+        del bufs
+        return c["B"] * world * args.steps / (float(t.item()) / 1e3)
+
+    e2e_value = e2e_bf16 = None
+    h2d_bf16 = None
+    if not args.no_e2e:
+        e2e_value = measure_e2e(host)          # the reference's data format: fp32 features (DataLoader.py:61-84)
+        if use_graph and not args.no_bf16_e2e:
+            # informational second leg: the same step with the features STORED as bf16 on the host, i.e. half
+            # the bytes on the PCIe link, which is what bounds the fp32 leg; needs its own captured graph (bf16 prologue)
+            host16 = dict(host)
+            host16["app"] = host["app"].to(torch.bfloat16).pin_memory()
+            host16["mot"] = host["mot"].to(torch.bfloat16).pin_memory()
+            h2d_bf16 = sum(v.numel() * v.element_size() for v in host16.values())
+            eng.graph = None
+            res16 = {k: v.to(dev) for k, v in host16.items()}
+            eng.capture(res16["app"], res16["mot"], res16["q"], res16["qlen"], res16["ans"], warmup=1)
+            e2e_bf16 = measure_e2e(host16)
 
     if rank == 0:
         pk = peaks()
@@ -321,7 +338,10 @@ def run_ours(args):
                        "cuda_graph": bool(use_graph),
                        "final_loss": float(loss)},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                    "note": "host buffers in the reference's format (fp32 features): bound by the host link, not by the kernels"},
+            "e2e_bf16_features": {"value": e2e_bf16, "unit": UNIT, "h2d_bytes_per_step": h2d_bf16, "d2h_bytes_per_step": 4,
+                                  "note": "informational: same step with the clip features stored as bf16 on the host"},
             "gpu_launches": int(launches),
             "roofline": {"kernel": "lstm_seq_fwd_kernel<BN=256> (appearance encoder forward: W_ih product + 16 recurrent steps, one persistent launch)",
                          "bound": "tensor", "achieved": achieved, "peak": pk["tf"], "unit": "TFLOP/s",
@@ -358,6 +378,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-e2e", action="store_true", help="profiling aid: skip the host-buffer e2e leg")
+    ap.add_argument("--no-bf16-e2e", action="store_true", help="skip the informational e2e leg with bf16-stored features")
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying the captured CUDA graph")
     ap.add_argument("--no-cpu", action="store_true", help="profiling aid: skip the cpu_baseline leg")
     args = ap.parse_args()

@@ -408,16 +408,19 @@ __global__ void ce_kernel(const float* __restrict__ logits, const long long* __r
 }
 
 // =============================================================================================== streaming helpers
+__device__ __forceinline__ void load8g(const bf16* p, float (&f)[8]);
+__device__ __forceinline__ void load8g(const float* p, float (&f)[8]);
 // Appearance prologue, reference model/Preprocessing.py:220-223: tanh(dropout(x)) and the [B,N,F,C] -> [F, B*N, C]
 // re-layout (two full transposed copies in the reference) fused with the fp32 -> bf16 cast in ONE pass.
-__global__ void prep_features_kernel(const float* __restrict__ in, bf16* __restrict__ out, long long S, int T, int C,
+// TIN = float (the reference's feature format) or bf16 (features stored / shipped as bf16: half the host-to-device bytes)
+template <typename TIN>
+__global__ void prep_features_kernel(const TIN* __restrict__ in, bf16* __restrict__ out, long long S, int T, int C,
                                      int do_tanh, int time_major, DropoutCfg dc) {
   const long long n8 = S * T * (long long)C / 8;
   const int c8 = C / 8;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
-    const float4 a = reinterpret_cast<const float4*>(in)[2 * i];
-    const float4 b = reinterpret_cast<const float4*>(in)[2 * i + 1];
-    float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    float f[8];
+    load8g(in + i * 8, f);
     if (dc.p > 0.f) {
       float sc[8];
       dropout_scale8(dc, i, sc);
@@ -713,15 +716,25 @@ extern "C" int dvgr_cross_entropy(const float* logits, const long long* answers,
   return 0;
 }
 
-extern "C" int dvgr_prep_features(const float* in, void* out, long long S, int T, int C, int do_tanh, int time_major,
-                                  float p, unsigned long long seed, unsigned int drop_stream, void* stream) {
+extern "C" int dvgr_prep_features_ex(const void* in, int in_is_bf16, void* out, long long S, int T, int C, int do_tanh,
+                                     int time_major, float p, unsigned long long seed, unsigned int drop_stream,
+                                     void* stream) {
   if (C % 8 != 0) return set_error("prep_features: C=%d must be a multiple of 8", C);
   const long long n = S * T * (long long)C / 8;
   if (n <= 0) return 0;
   DropoutCfg dc{seed, drop_stream, p, seed_offset_ptr()};
-  prep_features_kernel<<<grid_for(n, 256, 148 * 32), 256, 0, ST(stream)>>>(in, BF(out), S, T, C, do_tanh, time_major, dc);
+  if (in_is_bf16)
+    prep_features_kernel<bf16><<<grid_for(n, 256, 148 * 32), 256, 0, ST(stream)>>>(CBF(in), BF(out), S, T, C, do_tanh, time_major, dc);
+  else
+    prep_features_kernel<float><<<grid_for(n, 256, 148 * 32), 256, 0, ST(stream)>>>(reinterpret_cast<const float*>(in), BF(out), S, T, C,
+                                                                                    do_tanh, time_major, dc);
   DVGR_CHECK_LAUNCH("prep_features");
   return 0;
+}
+
+extern "C" int dvgr_prep_features(const float* in, void* out, long long S, int T, int C, int do_tanh, int time_major,
+                                  float p, unsigned long long seed, unsigned int drop_stream, void* stream) {
+  return dvgr_prep_features_ex(in, 0, out, S, T, C, do_tanh, time_major, p, seed, drop_stream, stream);
 }
 
 extern "C" int dvgr_cast_rows(const float* in, long long ld_in, void* out, long long ld_out, int rows, int cols,

@@ -1,10 +1,11 @@
 """Mirror of the live part of reference model/Preprocessing.py: DynamicRNN (:7-45), InputUnitLinguisticDynamic (:89-127)
 and VisualAppearanceEncoder (:191-234).
 
-The appearance encoder (70-76 % of the model's FLOPs) runs entirely in the library: one prologue pass, one
-tcgen05 GEMM for the W_ih product of both directions and 16 fused recurrent steps. The question encoder's two BiLSTMs run
-on the same fused recurrence (4 directions per step, length-masked in the cell epilogue), which removes cuDNN, the
-pack/unpack round trip and the host sync on question_len from the step."""
+The appearance encoder (70-76 % of the model's FLOPs) runs entirely in the library: one prologue pass and ONE
+persistent tcgen05 launch for the W_ih product of both directions plus the 16 recurrent steps (dvgr_lstm_seq_fwd). The question
+encoder's two BiLSTMs run on the same kernel (4 directions, length-masked in the cell epilogue), which removes cuDNN, the
+pack/unpack round trip and the host sync on question_len from the step. Clip features may arrive as fp32
+(the reference's format) or as bf16 (stored / shipped at half the bytes)."""
 import torch
 import torch.nn as nn
 from torch.nn import functional as F
@@ -80,7 +81,8 @@ class VisualAppearanceEncoder(nn.Module):
     def forward(self, appearance_clips):
         """[B, N, F, Dv] fp32 -> [B, N, module_dim] bf16 (final forward / backward hidden states, concatenated)."""
         e = self.encoder
+        x = appearance_clips if appearance_clips.dtype == torch.bfloat16 else appearance_clips.float()   # bf16-stored features pass through
         return ag.AppearanceEncoderFn.apply(
-            appearance_clips.float(), e.weight_ih_l0, e.weight_hh_l0, e.bias_ih_l0, e.bias_hh_l0,
+            x, e.weight_ih_l0, e.weight_hh_l0, e.bias_ih_l0, e.bias_hh_l0,
             e.weight_ih_l0_reverse, e.weight_hh_l0_reverse, e.bias_ih_l0_reverse, e.bias_hh_l0_reverse,
             self.embedding_dropout.p, self.finalvisual_dropout.p, self.training)

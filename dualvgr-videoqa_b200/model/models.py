@@ -69,7 +69,8 @@ class DualVGR(nn.Module):
         question_embedding, word_embedding, dynamic_q = self.linguistic_input_unit(question, question_len)
         app = self.visual_appearance_input_unit(video_appearance_feat)
         B, N = video_motion_feat.shape[:2]
-        mot_in = ag.ops.prep_features(video_motion_feat.float().contiguous().view(B * N, -1), 1, False, False)
+        mf = video_motion_feat if video_motion_feat.dtype == torch.bfloat16 else video_motion_feat.float()
+        mot_in = ag.ops.prep_features(mf.contiguous().view(B * N, -1), 1, False, False)
         mot = ag.linear(mot_in, self.visual_motion_input_unit.weight, self.visual_motion_input_unit.bias).view(B, N, -1)
         words_u = word_embedding
         hook = getattr(self, "_unit_inputs_grad_hook", None)

@@ -336,13 +336,14 @@ def cast_rows(w, out=None, out_cols=None, lstm_H=0):
 
 def prep_features(x, T, do_tanh, time_major, p=0.0, seed=0, stream_id=0):
     """x fp32 [S*T, C] (S sequences of T steps) -> bf16 [T*S, C] (time_major) / [S*T, C]: tanh(dropout(x)) in one pass."""
-    assert x.dtype == F32 and x.is_contiguous()
+    assert x.dtype in (F32, BF16) and x.is_contiguous()
     C = x.shape[-1]
     rows = x.numel() // C
     S = rows // T
     out = _empty((rows, C), BF16, x)
-    _lib.check(_lib.prep_features(_ptr(x), _ptr(out), S, T, C, 1 if do_tanh else 0, 1 if time_major else 0, float(p),
-                                  int(seed), int(stream_id), _stream()), "dvgr_prep_features")
+    _lib.check(_lib.prep_features_ex(_ptr(x), 1 if x.dtype == BF16 else 0, _ptr(out), S, T, C, 1 if do_tanh else 0,
+                                     1 if time_major else 0, float(p), int(seed), int(stream_id), _stream()),
+               "dvgr_prep_features_ex")
     return out
 
 

@@ -294,6 +294,10 @@ int dvgr_aux_loss_unit(const float* ca, const float* cm, const float* aq, const 
  * dvgr_colsum: out[C] (+)= scale * sum_r in[r][c] (bias gradients, per-video partial reductions); deterministic. */
 int dvgr_prep_features(const float* in, void* out, long long S, int T, int C, int do_tanh, int time_major, float p,
                        unsigned long long seed, unsigned int drop_stream, void* stream);
+/* Same pass for features that are stored / shipped as bf16 (in_is_bf16 = 1): halves the 713 MB per step that the fp32
+ * features of the reference's DataLoader (DataLoader.py:61-84) put on the host link. */
+int dvgr_prep_features_ex(const void* in, int in_is_bf16, void* out, long long S, int T, int C, int do_tanh,
+                          int time_major, float p, unsigned long long seed, unsigned int drop_stream, void* stream);
 int dvgr_cast_rows(const float* in, long long ld_in, void* out, long long ld_out, int rows, int cols, int out_cols,
                    int lstm_H, void* stream);
 int dvgr_dropout(const void* in, void* out, long long n, float p, unsigned long long seed, unsigned int drop_stream,

@@ -182,6 +182,20 @@ def test_against_live_oracle_other_baseline_shapes(cfg):
     assert (num / den) ** 0.5 < 1.5 * TOL, (num / den) ** 0.5
 
 
+def test_bf16_stored_features_match_fp32_features():
+    """Clip features shipped as bf16 (half the host-to-device bytes) give the same logits as the reference's
+    fp32 features within the bf16 tolerance, and the same argmax on confident rows."""
+    cfg = (6, 20, 8, 32, 60, 2)
+    model, inputs, ans = build(cfg, training=False)
+    with torch.no_grad():
+        l32 = model(*inputs)[0]
+        l16 = model(inputs[0].to(torch.bfloat16), inputs[1].to(torch.bfloat16), inputs[2], inputs[3])[0]
+    assert rel(l16, l32) < 1e-2
+    srt = l32.sort(dim=1).values
+    confident = (srt[:, -1] - srt[:, -2]) > 2 * TOL * l32.abs().max()
+    assert torch.equal(l16.argmax(1)[confident], l32.argmax(1)[confident])
+
+
 def test_full_loss_backward_and_train_mode_dropout_runs():
     """Train mode with the reference's dropout rates: finite loss/grads, masks differ between passes, eval is deterministic."""
     import dualvgr_videoqa_b200.model.models as M

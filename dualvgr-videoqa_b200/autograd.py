@@ -162,6 +162,9 @@ def grad_groups(model):
         for i in range(unit.layers):
             for pair in ((unit.acGCN[i], unit.appearance_GCN[i]), (unit.mcGCN[i], unit.motion_GCN[i])):
                 groups.append([att.W.weight for g in pair for att in g.attentions])
+        for i in range(unit.layers):      # the two cycle-query projections of a layer run as one GEMM (LinearCatFn)
+            qa, qm = unit.queryPunish_appear[i].query_weight, unit.queryPunish_motion[i].query_weight
+            groups += [[qa.weight, qm.weight], [qa.bias, qm.bias]]
     return groups
 
 
@@ -224,6 +227,55 @@ def _bias_target(b):
     if g is None or g.dtype != F32 or not g.is_contiguous():
         return None
     return g
+
+
+class LinearCatFn(Function):
+    """y = x [W1; W2]^T + [b1; b2]: two nn.Linear layers that read the same input as ONE GEMM (forward, dgrad and wgrad).
+    Used for the two QueryPunish.query_weight projections of a unit (reference model/utils.py:100 called twice per layer,
+    models.py:142-147): each is a 256 x 300 x 768 product, i.e. pure launch latency when run on its own."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2):
+        Kp = x.shape[-1]
+        x2 = _c(x.reshape(-1, Kp))
+        w = bf16_rows([w1, w2], out_cols=Kp, tag="cat")
+        bias = torch.cat([b1.detach(), b2.detach()])
+        y = ops.linear_fwd(x2, w, bias=bias)
+        ctx.save_for_backward(x2, w)
+        ctx.params = (w1, b1, w2, b2)
+        ctx.lead = x.shape[:-1]
+        return y.view(*x.shape[:-1], w.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w = ctx.saved_tensors
+        w1, b1, w2, b2 = ctx.params
+        N1, N2, K = w1.shape[0], w2.shape[0], w1.shape[1]
+        d = _c(dy.reshape(x2.shape[0], N1 + N2))
+        if d.dtype != BF16:
+            d = d.to(BF16)
+        dx = ops.linear_dgrad(d, w).view(*ctx.lead, w.shape[1]) if ctx.needs_input_grad[0] else None
+        dw1 = dw2 = db1 = db2 = None
+        tgt = grad_target([w1, w2])
+        if tgt is not None:
+            ops.linear_wgrad(d, x2, out=tgt, atomic=True, rows=N1 + N2, cols=K)
+        else:
+            dw = ops.linear_wgrad(d, x2)[:N1 + N2, :K]
+            dw1, dw2 = dw[:N1], dw[N1:]
+        t1, t2 = _bias_target(b1), _bias_target(b2)
+        if t1 is not None and t2 is not None and t2.data_ptr() == t1.data_ptr() + N1 * 4:
+            ops.colsum(d, out=torch.as_strided(t1, (N1 + N2,), (1,)), accumulate=True)
+        elif t1 is not None and t2 is not None:
+            ops.colsum(d[:, :N1], out=t1, accumulate=True)
+            ops.colsum(d[:, N1:], out=t2, accumulate=True)
+        else:
+            db = ops.colsum(d)
+            db1, db2 = db[:N1], db[N1:]
+        return dx, dw1, db1, dw2, db2
+
+
+def linear_cat(x, w1, b1, w2, b2):
+    return LinearCatFn.apply(x, w1, b1, w2, b2)
 
 
 def linear(x, weight, bias=None, act=None, out_f32=False, act_grad_folded=False):

@@ -137,7 +137,8 @@ class DualVGRUnit_multiple(nn.Module):
         for i in range(self.layers):
             # Query Punishment Module: word attention -> cycle query -> per-clip gates of both streams
             q_c, _ = self.queryAttn[i](words, dq, qlen, word_dim=self.word_dim)
-            query = torch.cat([self.queryPunish_appear[i].query(q_c), self.queryPunish_motion[i].query(q_c)], dim=1)
+            qa, qm = self.queryPunish_appear[i].query_weight, self.queryPunish_motion[i].query_weight
+            query = ag.linear_cat(q_c, qa.weight, qa.bias, qm.weight, qm.bias)      # [B, 2D]: both streams' queries, one GEMM
             g_app, g_mot = ag.GateFn.apply(app, mot, query)
             # multi-view GAT: common + specific graph of each stream, one fused launch for the four graphs
             (z_app, z_mot), (com_app, aq_fusion, com_mot, mq_fusion) = fused_gat_layer(

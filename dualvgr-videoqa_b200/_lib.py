@@ -82,6 +82,12 @@ def _sig(name, argtypes):
 gemm = _sig("dvgr_gemm", [ctypes.POINTER(GemmArgs), c_void_p])
 gemm_reference = _sig("dvgr_gemm_reference",
                       [c_void_p, c_ll, c_ll, c_void_p, c_ll, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_void_p])
+class WgradProblem(ctypes.Structure):
+    _fields_ = [("dy", c_void_p), ("ld_dy", c_ll), ("x", c_void_p), ("ld_x", c_ll), ("M", c_int), ("rows", c_int),
+                ("cols", c_int), ("out", c_void_p), ("ldc", c_ll)]
+
+
+wgrad_grouped = _sig("dvgr_wgrad_grouped", [ctypes.POINTER(WgradProblem), c_int, c_void_p])
 lstm_step_fwd = _sig("dvgr_lstm_step_fwd", [ctypes.POINTER(LstmArgs), c_void_p])
 lstm_step_bwd = _sig("dvgr_lstm_step_bwd", [ctypes.POINTER(LstmArgs), c_void_p])
 lstm_seq_fwd = _sig("dvgr_lstm_seq_fwd", [ctypes.POINTER(LstmSeqArgs), c_void_p])
@@ -155,7 +161,7 @@ sumsq = _sig("dvgr_sumsq", [P, c_ll, P, P, P])
 adam_step = _sig("dvgr_adam_step", [P, P, P, P, c_ll, c_float, c_float, c_float, c_float, c_int, c_float, P, c_float, P, P, P])
 
 EXPORTED = [
-    "dvgr_last_error", "dvgr_abi_version", "dvgr_launch_count", "dvgr_set_seed_offset", "dvgr_gemm", "dvgr_gemm_reference",
+    "dvgr_last_error", "dvgr_abi_version", "dvgr_launch_count", "dvgr_set_seed_offset", "dvgr_gemm", "dvgr_gemm_reference", "dvgr_wgrad_grouped",
     "dvgr_lstm_step_fwd", "dvgr_lstm_step_bwd", "dvgr_lstm_seq_fwd", "dvgr_lstm_seq_sync_words", "dvgr_lstm_seq_bwd", "dvgr_gat_attn_fwd", "dvgr_gat_attn_bwd", "dvgr_qattn_fwd",
     "dvgr_qattn_bwd", "dvgr_gate_fwd", "dvgr_gate_bwd", "dvgr_view_attn_fwd", "dvgr_view_attn_bwd_blocks",
     "dvgr_view_attn_bwd", "dvgr_mfb_fwd", "dvgr_mfb_bwd", "dvgr_readout_fwd", "dvgr_readout_bwd", "dvgr_bn_fwd",

@@ -606,14 +606,22 @@ class GatLayerFn(Function):
                 dx = ops.dropout_raw(dxt[0], pdrop, seed, sid + gs[0])
                 for i in range(1, cnt):
                     ops.act_bwd(dxt[i], None, "none", out=dx, accumulate=True, p=pdrop, seed=seed, stream_id=sid + gs[i])
-                ops.gemm(dwh, 1, xt, 1, D, D, M, dWs, ldc=D, batch=cnt, c_batch=D * D, a_c2=list(range(cnt)),
-                         b_c2=list(range(cnt)), **wkw)
+                if direct and ops.DEFER_WGRAD[0]:
+                    for i in range(cnt):
+                        ops.wgrad_enqueue(dwh[i], xt[i], dWs[i])
+                else:
+                    ops.gemm(dwh, 1, xt, 1, D, D, M, dWs, ldc=D, batch=cnt, c_batch=D * D, a_c2=list(range(cnt)),
+                             b_c2=list(range(cnt)), **wkw)
             else:
                 dx = ops.linear_dgrad(dwh[0], wb[0])
                 for i in range(1, cnt):
                     ops.linear_dgrad(dwh[i], wb[i], out=dx, beta=True)
-                ops.gemm(dwh, 1, xt, 1, D, D, M, dWs, ldc=D, batch=cnt, c_batch=D * D, a_c2=list(range(cnt)),
-                         b_c2=[0] * cnt, **wkw)
+                if direct and ops.DEFER_WGRAD[0]:
+                    for i in range(cnt):
+                        ops.wgrad_enqueue(dwh[i], xt, dWs[i])
+                else:
+                    ops.gemm(dwh, 1, xt, 1, D, D, M, dWs, ldc=D, batch=cnt, c_batch=D * D, a_c2=list(range(cnt)),
+                             b_c2=[0] * cnt, **wkw)
             dxs.append(dx.view(B, N, D))
             dg = dgates[gs[0]]
             for g in gs[1:]:

@@ -226,4 +226,10 @@ int dvgr_lstm_seq_bwd(const dvgr_lstm_args* a, void* dgates, int* sync, void* st
   return rc;
 }
 
+int dvgr_wgrad_grouped(const dvgr_wgrad_problem* probs, int n, void* stream) {
+  if (n <= 0) return 0;
+  if (!probs) return set_error("dvgr_wgrad_grouped: null problem list");
+  return gemm_grouped_wgrad(probs, n, reinterpret_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

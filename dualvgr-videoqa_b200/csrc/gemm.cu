@@ -694,6 +694,164 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 }
 
+// ------------------------------------------------------------------------------------------------ grouped weight gradients
+// dW_i[rows_i][cols_i] += dy_i[M_i][rows_i]^T x_i[M_i][cols_i] for up to kMaxGroup independent problems in ONE persistent
+// launch. The ~30 small weight-gradient GEMMs of a train step (768 x 768 outputs, reduction over 5-10 k rows) are off the
+// critical path of the backward pass — nothing consumes them before the optimizer — but as separate launches each pays
+// launch latency, prologue, pipeline fill and a partially filled last wave (36-144 tiles on 148 SMs): ~20 us apiece for
+// ~5 us of tensor work. Queued and flushed together they become one tile stream that keeps every SM busy.
+// Both operands are read MN-major (no transposed copies), fp32 output accumulated with vector reductions (split-K safe).
+constexpr int kMaxGroup = 32;
+struct GroupProb {
+  int M, N;                     // output rows (= columns of dy), output columns (= columns of x)
+  int m_blocks, n_blocks;       // 128-row / BN-column tiles
+  int k_blocks, ksplit, kb_per; // 64-row blocks of the reduction, splits, blocks per split
+  float* C;
+  long long ldc;
+};
+struct GroupedParams {
+  CUtensorMap ta[kMaxGroup], tb[kMaxGroup];
+  GroupProb prob[kMaxGroup];
+  int tile_start[kMaxGroup + 1];      // prefix sums of m_blocks * n_blocks * ksplit
+  int n;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kGemmThreads, 1) gemm_grouped_wgrad_kernel(const __grid_constant__ GroupedParams G) {
+  using Cfg = TileCfg<BN, 1>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;   // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;       // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* stage_base = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + 256);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total = G.tile_start[G.n];
+
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], kEpiWarps); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+  // tile g -> (problem, split, m block, n block); every role decodes the same way
+  auto decode = [&](int g, int& pi, int& ks, int& m_blk, int& n_blk) {
+    pi = 0;
+    while (pi + 1 < G.n && g >= G.tile_start[pi + 1]) ++pi;
+    const GroupProb& P = G.prob[pi];
+    const int t = g - G.tile_start[pi];
+    const int per = P.m_blocks * P.n_blocks;
+    ks = t / per;
+    const int rem = t - ks * per;
+    m_blk = rem / P.n_blocks;
+    n_blk = rem - m_blk * P.n_blocks;
+  };
+
+  if (warp == 0 && lane == 0) {
+    // ===================================================== TMA producer
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int g = blockIdx.x; g < total; g += gridDim.x) {
+      int pi, ks, m_blk, n_blk;
+      decode(g, pi, ks, m_blk, n_blk);
+      const GroupProb& P = G.prob[pi];
+      const int kb0 = ks * P.kb_per, kb1 = min(P.k_blocks, kb0 + P.kb_per);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
+        uint8_t* sB = sA + Cfg::A_BYTES;
+        mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+#pragma unroll
+        for (int c = 0; c < BM / 64; ++c)
+          tma_load_4d(sA + c * (64 * BK * 2), &G.ta[pi], &full_bar[stage], m_blk * BM + c * 64, kb * BK, 0, 0);
+#pragma unroll
+        for (int c = 0; c < BN / 64; ++c)
+          tma_load_4d(sB + c * (64 * BK * 2), &G.tb[pi], &full_bar[stage], n_blk * BN + c * 64, kb * BK, 0, 0);
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================================================== MMA issuer (single thread)
+    constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, true, true);
+    int stage = 0;
+    uint32_t phase = 0;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int g = blockIdx.x; g < total; g += gridDim.x) {
+      int pi, ks, m_blk, n_blk;
+      decode(g, pi, ks, m_blk, n_blk);
+      const GroupProb& P = G.prob[pi];
+      const int kb0 = ks * P.kb_per, kb1 = min(P.k_blocks, kb0 + P.kb_per);
+      mbar_wait(&tempty_bar[as], aphase ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sA = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+        const uint32_t sB = sA + Cfg::A_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k)
+          umma_bf16(d_tmem, umma_smem_desc(sA + k * 2048, 64 * BK * 2, 1024), umma_smem_desc(sB + k * 2048, 64 * BK * 2, 1024),
+                    idesc, (kb > kb0 || k != 0) ? 1u : 0u);
+        umma_commit(&empty_bar[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+      umma_commit(&tfull_bar[as]);
+      if (++as == 2) { as = 0; aphase ^= 1u; }
+    }
+  } else if (warp >= 4) {
+    // ===================================================== epilogue: fp32 vector reductions into the gradient buffers
+    const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int g = blockIdx.x; g < total; g += gridDim.x) {
+      int pi, ks, m_blk, n_blk;
+      decode(g, pi, ks, m_blk, n_blk);
+      const GroupProb& P = G.prob[pi];
+      GemmParams lp;                       // only the fields the linear epilogue reads
+      lp.M = P.M; lp.N = P.N; lp.C = P.C; lp.ldc = P.ldc; lp.c_batch = 0; lp.out_f32 = 1; lp.act = ACT_NONE; lp.beta = 2;
+      lp.bias = nullptr; lp.bias_batch = 0; lp.row_map = nullptr;
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      float* stage_w = stage_base + (warp - 4) * kStageFloats;
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
+#pragma unroll 1
+      for (int c = half; c < BN / 32; c += 2) {
+        uint32_t r[32];
+        tmem_ld_32x32(t_addr + c * 32, r);
+        tmem_ld_wait();
+        if (c + 2 >= BN / 32) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        }
+        epi_linear(lp, 0, m_blk * BM + q * 32, n_blk * BN + c * 32, r, ks, stage_w, lane);
+      }
+      if (++as == 2) { as = 0; aphase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ whole-sequence LSTM
 // One persistent launch runs ALL T steps of every direction with the input projection fused in:
 //   tile (s, d, m, n):  acc[128 x BN] = x_t[m] W_ih[d][n]^T  (K1, no dependency)  +  h_{s}[d][m] W_hh[d][n]^T  (H)
@@ -1337,6 +1495,58 @@ int gemm_dispatch(const dvgr_operand& A, const dvgr_operand& B, GemmParams p, in
   if (a_mn && b_mn) { if (bn == 256) DVGR_LAUNCH(true, true, 256); else DVGR_LAUNCH(true, true, 128); }
 #undef DVGR_LAUNCH
   return set_error("gemm: operand layout combination (A MN-major, B K-major) is not instantiated");
+}
+
+// Host side of the grouped weight-gradient launch. probs: dy_i [M_i][rows_i] (row stride ld_dy), x_i [M_i][cols_i] bf16.
+int gemm_grouped_wgrad(const dvgr_wgrad_problem* probs, int n, cudaStream_t stream) {
+  constexpr int BN = 256;
+  using Cfg = TileCfg<BN, 1>;
+  auto kern = gemm_grouped_wgrad_kernel<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return set_error("cudaFuncSetAttribute(grouped wgrad, smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  for (int base = 0; base < n; base += kMaxGroup) {
+    const int cnt = std::min(kMaxGroup, n - base);
+    GroupedParams G;
+    memset(&G, 0, sizeof(G));
+    G.n = cnt;
+    int tiles = 0;
+    for (int i = 0; i < cnt; ++i) {
+      const dvgr_wgrad_problem& w = probs[base + i];
+      if (!w.dy || !w.x || !w.out) return set_error("wgrad_grouped: problem %d has a null pointer", base + i);
+      if (w.M <= 0 || w.rows <= 0 || w.cols <= 0) return set_error("wgrad_grouped: problem %d has an empty extent", base + i);
+      dvgr_operand A, B;
+      memset(&A, 0, sizeof(A)); memset(&B, 0, sizeof(B));
+      A.ptr = w.dy; A.major = 1; A.ndim = 2; A.dims[0] = w.rows; A.dims[1] = w.M; A.strides[0] = 1; A.strides[1] = w.ld_dy;
+      B.ptr = w.x; B.major = 1; B.ndim = 2; B.dims[0] = w.cols; B.dims[1] = w.M; B.strides[0] = 1; B.strides[1] = w.ld_x;
+      int rc = make_tensor_map(&G.ta[i], A, 64, 64);
+      if (!rc) rc = make_tensor_map(&G.tb[i], B, 64, 64);
+      if (rc) return rc;
+      GroupProb& P = G.prob[i];
+      P.M = w.rows; P.N = w.cols; P.C = w.out; P.ldc = w.ldc;
+      P.m_blocks = (w.rows + BM - 1) / BM;
+      P.n_blocks = (w.cols + BN - 1) / BN;
+      P.k_blocks = (w.M + BK - 1) / BK;
+      // split long reductions so that one tile-unit is at most ~40 k-blocks (~18 us): even load over the 148 CTAs
+      int ks = (P.k_blocks + 39) / 40;
+      if (ks < 1) ks = 1;
+      P.kb_per = (P.k_blocks + ks - 1) / ks;
+      P.ksplit = (P.k_blocks + P.kb_per - 1) / P.kb_per;       // no empty splits
+      G.tile_start[i] = tiles;
+      tiles += P.m_blocks * P.n_blocks * P.ksplit;
+    }
+    G.tile_start[cnt] = tiles;
+    const int grid = std::min(tiles, num_sms());
+    if (grid <= 0) continue;
+    kern<<<grid, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(G);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error("grouped wgrad launch failed: %s", cudaGetErrorString(e));
+    count_launch();
+  }
+  return 0;
 }
 
 // Whole-sequence fused LSTM forward (lstm_seq_fwd_kernel). p carries the EPI_LSTM fields with M = S, N = 4H, batch = D.

@@ -39,6 +39,7 @@ class _EarlyBucketHook:
         self.pending -= 1
         if self.pending == 0:
             e = self.engine
+            ops.flush_wgrads()       # the queued (deferred) weight gradients of the early bucket must land before it is reduced
             self.side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self.side):
                 dist.all_reduce(e.gflat[e.late_numel:], op=dist.ReduceOp.SUM, group=e.pg)
@@ -132,7 +133,12 @@ class TrainEngine:
         self.gflat.zero_()
         outputs = self.model(app, mot, question, question_len)
         total, ce, com, dep, correct = self.loss(outputs, answers)
-        total.backward()
+        ops.DEFER_WGRAD[0] = True          # weight gradients of the nn.Linear layers: queued during backward ...
+        try:
+            total.backward()
+        finally:
+            ops.DEFER_WGRAD[0] = False
+        ops.flush_wgrads()                 # ... and launched as ONE grouped tcgen05 GEMM (nothing needs them before the optimizer)
         self.optimizer_step()
         return total.detach()
 

@@ -127,9 +127,41 @@ def linear_wgrad(dy, x, out=None, beta=False, row_map=None, bn=0, rows=None, col
         assert not atomic
         out = torch.empty((rows, cols), dtype=torch.float32, device=dy.device)
     if atomic:
+        if DEFER_WGRAD[0] and row_map is None and not bn:
+            wgrad_enqueue(dy, x, out, rows, cols)
+            return out
         bn2, ks = wgrad_split(rows, cols, M)
         return gemm(dy, 1, x, 1, rows, cols, M, out, beta=2, row_map=row_map, bn=bn or bn2, ksplit=ks)
     return gemm(dy, 1, x, 1, rows, cols, M, out, beta=beta, row_map=row_map, bn=bn)
+
+
+# ---- deferred, grouped weight gradients. Inside a train step nothing consumes a weight gradient before the optimizer, so
+#      the engine lets the autograd layer QUEUE them (DEFER_WGRAD) and flushes the queue as one persistent launch
+#      (dvgr_wgrad_grouped) after backward. Outside the engine the queue is never used: linear_wgrad launches at once.
+DEFER_WGRAD = [False]
+_WGRAD_QUEUE = []
+
+
+def wgrad_enqueue(dy, x, out, rows=None, cols=None):
+    """out[rows, cols] (fp32, += ) dy[M, N]^T @ x[M, K]; the operands are kept alive until flush_wgrads()."""
+    assert dy.dtype == BF16 and x.dtype == BF16 and out.dtype == F32 and dy.stride(1) == 1 and x.stride(1) == 1
+    assert dy.shape[0] == x.shape[0] and out.stride(-1) == 1
+    _WGRAD_QUEUE.append((dy, x, out, rows or dy.shape[1], cols or x.shape[1]))
+
+
+def flush_wgrads():
+    """Launches every queued weight gradient in one grouped launch per 32 problems."""
+    if not _WGRAD_QUEUE:
+        return 0
+    n = len(_WGRAD_QUEUE)
+    arr = (_lib.WgradProblem * n)()
+    for i, (dy, x, out, rows, cols) in enumerate(_WGRAD_QUEUE):
+        arr[i].dy, arr[i].ld_dy, arr[i].x, arr[i].ld_x = dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0)
+        arr[i].M, arr[i].rows, arr[i].cols = dy.shape[0], rows, cols
+        arr[i].out, arr[i].ldc = out.data_ptr(), out.stride(-2)
+    _lib.check(_lib.wgrad_grouped(arr, n, _stream()), "dvgr_wgrad_grouped")
+    _WGRAD_QUEUE.clear()
+    return n
 
 
 def gemm_reference(A, a_rs, a_ks, B, b_rs, b_ks, M, N, K):

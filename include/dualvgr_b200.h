@@ -75,6 +75,22 @@ typedef struct dvgr_gemm_args {
  * model/utils.py:68 (QueryAttn.feat_enhance), and the W_ih product of nn.LSTM at model/Preprocessing.py:227. */
 int dvgr_gemm(const dvgr_gemm_args* args, void* stream);
 
+/* Several independent weight gradients in ONE persistent launch:  out_i[rows_i][cols_i] += dy_i[M_i][rows_i]^T x_i[M_i][cols_i]
+ * (bf16 operands read MN-major, fp32 accumulation into out_i with vector reductions: out_i must hold the value to add to,
+ * e.g. a zeroed gradient buffer). The weight-gradient GEMMs of the nn.Linear layers listed under dvgr_gemm are off the
+ * backward pass's critical path; queued and flushed together they form one tile stream instead of ~30 latency-bound
+ * launches. `probs` is a HOST array; row strides in elements (multiples of 8), pointers 16-byte aligned. */
+typedef struct dvgr_wgrad_problem {
+  const void* dy;
+  long long ld_dy;
+  const void* x;
+  long long ld_x;
+  int M, rows, cols;
+  float* out;
+  long long ldc;
+} dvgr_wgrad_problem;
+int dvgr_wgrad_grouped(const dvgr_wgrad_problem* probs, int n, void* stream);
+
 /* Test-only SIMT reference product (fp32 out), arbitrary element strides:  C[m][n] = sum_k A[m*a_rs + k*a_ks] * B[n*b_rs + k*b_ks] */
 int dvgr_gemm_reference(const void* A, long long a_rs, long long a_ks, const void* B, long long b_rs, long long b_ks,
                         float* C, long long ldc, int M, int N, int K, void* stream);

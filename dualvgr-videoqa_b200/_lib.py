@@ -155,6 +155,11 @@ scatter = _sig("dvgr_scatter", [ctypes.POINTER(Seg), c_int, c_int, P])
 lib.dvgr_colsum_workspace.argtypes = [c_ll, c_int]
 lib.dvgr_colsum_workspace.restype = c_ll
 colsum = _sig("dvgr_colsum", [P, c_int, c_ll, c_ll, c_int, P, P, c_int, c_float, P])
+class ColsumProblem(ctypes.Structure):
+    _fields_ = [("in_", c_void_p), ("in_is_f32", c_int), ("ld", c_ll), ("R", c_ll), ("C", c_int), ("out", c_void_p)]
+
+
+colsum_grouped = _sig("dvgr_colsum_grouped", [ctypes.POINTER(ColsumProblem), c_int, P])
 colsum_batched = _sig("dvgr_colsum_batched", [P, c_int, c_ll, c_ll, c_ll, c_int, c_int, P, P, c_ll, c_int, c_float, P])
 sumsq_blocks = _sig("dvgr_sumsq_blocks", [])
 sumsq = _sig("dvgr_sumsq", [P, c_ll, P, P, P])
@@ -166,6 +171,6 @@ EXPORTED = [
     "dvgr_qattn_bwd", "dvgr_gate_fwd", "dvgr_gate_bwd", "dvgr_view_attn_fwd", "dvgr_view_attn_bwd_blocks",
     "dvgr_view_attn_bwd", "dvgr_mfb_fwd", "dvgr_mfb_bwd", "dvgr_readout_fwd", "dvgr_readout_bwd", "dvgr_bn_fwd",
     "dvgr_bn_bwd", "dvgr_cross_entropy", "dvgr_pair_loss_workspace", "dvgr_pair_loss_multi", "dvgr_aux_loss_workspace", "dvgr_aux_loss_unit", "dvgr_prep_features", "dvgr_prep_features_ex", "dvgr_cast_rows", "dvgr_dropout",
-    "dvgr_act_bwd", "dvgr_add", "dvgr_scatter", "dvgr_colsum_workspace", "dvgr_colsum", "dvgr_colsum_batched", "dvgr_sumsq_blocks", "dvgr_sumsq",
+    "dvgr_act_bwd", "dvgr_add", "dvgr_scatter", "dvgr_colsum_workspace", "dvgr_colsum", "dvgr_colsum_batched", "dvgr_colsum_grouped", "dvgr_sumsq_blocks", "dvgr_sumsq",
     "dvgr_adam_step",
 ]

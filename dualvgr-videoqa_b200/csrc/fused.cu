@@ -767,6 +767,111 @@ extern "C" int dvgr_act_bwd(const void* dy, const void* y, void* out, long long 
   return 0;
 }
 
+// Grouped column sums: out_i[C_i] += sum over rows of in_i[R_i][C_i] for up to kMaxColsum problems in ONE launch (the bias
+// gradients of the nn.Linear layers: like their weight gradients nothing reads them before the optimizer, so the autograd
+// layer queues them and the engine flushes the queue once per step). One block = (problem, 256-column block, row chunk);
+// partial sums are added with fp32 atomics (the order of the chunk contributions is not fixed, as for the split-K wgrads).
+constexpr int kMaxColsum = 48;
+struct ColsumGroup {
+  const void* in[kMaxColsum];
+  float* out[kMaxColsum];
+  long long ld[kMaxColsum];
+  int R[kMaxColsum], C[kMaxColsum], is_f32[kMaxColsum], vec_ok[kMaxColsum];
+  int block_start[kMaxColsum + 1];      // prefix sums of col_blocks * chunks
+  int chunks[kMaxColsum], rows_per_chunk[kMaxColsum];
+  int n;
+};
+
+template <typename T>
+__device__ __forceinline__ void colsum_group_block(const T* __restrict__ in, long long ld, long long r0, long long r1, int C,
+                                                   int cblk, int vec_ok, float* __restrict__ out) {
+  __shared__ float red[8][32][9];
+  const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c0 = (cblk * 32 + cg) * 8;
+  float acc[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+  if (c0 < C) {
+    if (vec_ok && c0 + 8 <= C) {
+      long long r = r0 + rl;
+      for (; r + 24 < r1; r += 32) {
+        float f0[8], f1[8], f2[8], f3[8];
+        load8g(in + r * ld + c0, f0);
+        load8g(in + (r + 8) * ld + c0, f1);
+        load8g(in + (r + 16) * ld + c0, f2);
+        load8g(in + (r + 24) * ld + c0, f3);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[q] += (f0[q] + f1[q]) + (f2[q] + f3[q]);
+      }
+      for (; r < r1; r += 8) {
+        float f0[8];
+        load8g(in + r * ld + c0, f0);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[q] += f0[q];
+      }
+    } else {
+      for (long long r = r0 + rl; r < r1; r += 8)
+        for (int q = 0; q < 8; ++q)
+          if (c0 + q < C) acc[q] += ldf<T>(in + r * ld + c0 + q);
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 8; ++q) red[rl][cg][q] = acc[q];
+  __syncthreads();
+  if (rl == 0 && c0 < C) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      float s_ = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s_ += red[k][cg][q];
+      if (c0 + q < C) atomicAdd(out + c0 + q, s_);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) colsum_grouped_kernel(const __grid_constant__ ColsumGroup G) {
+  pdl_trigger();
+  int pi = 0;
+  while (pi + 1 < G.n && (int)blockIdx.x >= G.block_start[pi + 1]) ++pi;
+  const int t = blockIdx.x - G.block_start[pi];
+  const int chunk = t % G.chunks[pi], cblk = t / G.chunks[pi];
+  const long long r0 = (long long)chunk * G.rows_per_chunk[pi];
+  const long long r1 = min((long long)G.R[pi], r0 + G.rows_per_chunk[pi]);
+  if (G.is_f32[pi])
+    colsum_group_block<float>(reinterpret_cast<const float*>(G.in[pi]), G.ld[pi], r0, r1, G.C[pi], cblk, G.vec_ok[pi], G.out[pi]);
+  else
+    colsum_group_block<bf16>(reinterpret_cast<const bf16*>(G.in[pi]), G.ld[pi], r0, r1, G.C[pi], cblk, G.vec_ok[pi], G.out[pi]);
+}
+
+extern "C" int dvgr_colsum_grouped(const dvgr_colsum_problem* probs, int n, void* stream) {
+  if (n <= 0) return 0;
+  if (!probs) return set_error("colsum_grouped: null problem list");
+  for (int base = 0; base < n; base += kMaxColsum) {
+    const int cnt = n - base < kMaxColsum ? n - base : kMaxColsum;
+    ColsumGroup G;
+    memset(&G, 0, sizeof(G));
+    G.n = cnt;
+    int blocks = 0;
+    for (int i = 0; i < cnt; ++i) {
+      const dvgr_colsum_problem& q = probs[base + i];
+      if (!q.in || !q.out || q.R <= 0 || q.C <= 0) return set_error("colsum_grouped: problem %d is empty or null", base + i);
+      const int esz = q.in_is_f32 ? 4 : 2;
+      G.in[i] = q.in; G.out[i] = q.out; G.ld[i] = q.ld; G.R[i] = (int)q.R; G.C[i] = q.C; G.is_f32[i] = q.in_is_f32;
+      G.vec_ok[i] = ((reinterpret_cast<uintptr_t>(q.in) & 15) == 0) && ((q.ld * esz) % 16 == 0);
+      long long chunks = (q.R + 255) / 256;          // >= 256 rows per chunk: few atomics per output element
+      if (chunks > 64) chunks = 64;
+      G.chunks[i] = (int)chunks;
+      G.rows_per_chunk[i] = (int)((q.R + chunks - 1) / chunks);
+      G.block_start[i] = blocks;
+      blocks += ((q.C + 255) / 256) * (int)chunks;
+    }
+    G.block_start[cnt] = blocks;
+    colsum_grouped_kernel<<<blocks, 256, 0, ST(stream)>>>(G);
+    DVGR_CHECK_LAUNCH("colsum_grouped");
+  }
+  return 0;
+}
+
 // dst[i] (+)= src[i] for up to kMaxSegs small fp32 segments in ONE launch (one block per segment). accumulate: the gradient
 // accumulation of the many tiny parameters of a DualVGR unit (per-head attention vectors and biases), which autograd would
 // otherwise perform with one elementwise launch per parameter (~170 launches of ~2 us per train step); copy: gathering those

@@ -149,8 +149,25 @@ def wgrad_enqueue(dy, x, out, rows=None, cols=None):
     _WGRAD_QUEUE.append((dy, x, out, rows or dy.shape[1], cols or x.shape[1]))
 
 
+_COLSUM_QUEUE = []
+
+
+def colsum_enqueue(x, out):
+    """out[C] (fp32) += column sums of x[R, C] (bf16 / fp32, last dim contiguous); x is kept alive until flush_wgrads()."""
+    assert x.dim() == 2 and x.stride(1) == 1 and out.dtype == F32 and out.is_contiguous() and out.numel() == x.shape[1]
+    _COLSUM_QUEUE.append((x, out))
+
+
 def flush_wgrads():
-    """Launches every queued weight gradient in one grouped launch per 32 problems."""
+    """Launches every queued weight gradient (one grouped GEMM per 32 problems) and bias gradient (one grouped column sum)."""
+    if _COLSUM_QUEUE:
+        m = len(_COLSUM_QUEUE)
+        carr = (_lib.ColsumProblem * m)()
+        for i, (x, out) in enumerate(_COLSUM_QUEUE):
+            carr[i].in_, carr[i].in_is_f32, carr[i].ld = x.data_ptr(), 1 if x.dtype == F32 else 0, x.stride(0)
+            carr[i].R, carr[i].C, carr[i].out = x.shape[0], x.shape[1], out.data_ptr()
+        _lib.check(_lib.colsum_grouped(carr, m, _stream()), "dvgr_colsum_grouped")
+        _COLSUM_QUEUE.clear()
     if not _WGRAD_QUEUE:
         return 0
     n = len(_WGRAD_QUEUE)
@@ -334,6 +351,9 @@ def _empty(shape, dtype, like):
 def colsum(x, out=None, accumulate=False, scale=1.0):
     """out[C] (+)= scale * sum over rows of x[R, C] (bf16 or fp32, last dim contiguous)."""
     assert x.dim() == 2 and x.stride(1) == 1
+    if DEFER_WGRAD[0] and accumulate and out is not None and scale == 1.0:
+        colsum_enqueue(x, out)       # a bias gradient inside an engine step: grouped with the others at flush time
+        return out
     R, C = x.shape
     ws = _empty((int(_lib.lib.dvgr_colsum_workspace(R, C)),), F32, x)
     if out is None:

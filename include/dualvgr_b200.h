@@ -321,6 +321,16 @@ int dvgr_dropout(const void* in, void* out, long long n, float p, unsigned long 
 int dvgr_act_bwd(const void* dy, const void* y, void* out, long long n, int act, int accumulate, float p,
                  unsigned long long seed, unsigned int drop_stream, void* stream);
 int dvgr_add(void* a, const void* b, long long n, void* stream);
+/* Several column sums in one launch: out_i[C_i] += sum_r in_i[r][c] (always accumulating; fp32 atomics across row
+ * chunks). The bias gradients of the nn.Linear layers, queued during backward and flushed once per train step. */
+typedef struct dvgr_colsum_problem {
+  const void* in;
+  int in_is_f32;
+  long long ld, R;
+  int C;
+  float* out;
+} dvgr_colsum_problem;
+int dvgr_colsum_grouped(const dvgr_colsum_problem* probs, int n, void* stream);
 /* dst[i] (+)= src[i] for a HOST array of small f32 segments, 64 per launch. accumulate = 1: adds the gradients of the many
  * tiny parameters of a unit (per-head attention vectors / biases) into their bound .grad views in one launch instead of
  * one elementwise launch per parameter (what autograd's AccumulateGrad does); accumulate = 0: gathers those parameters

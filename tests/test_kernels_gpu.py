@@ -78,6 +78,26 @@ def test_grouped_weight_gradients(ops):
         assert rel(single, o) < 1e-5
 
 
+def test_grouped_column_sums(ops):
+    """dvgr_colsum_grouped: the queued bias gradients of a step in one launch — bf16 and fp32 inputs, strided views, ragged
+    widths, accumulation into non-zero outputs, more problems than one launch holds."""
+    torch.manual_seed(6)
+    shapes = [(5120, 768, BF16), (10240, 768, BF16), (256, 1536, BF16), (300, 4008, BF16), (77, 13, torch.float32), (1, 8, BF16)]
+    shapes += [(100 + 31 * i, 64 + 8 * (i % 5), BF16) for i in range(50)]
+    outs, refs = [], []
+    for (R, C, dt) in shapes:
+        full = (torch.randn(R, C + 8) * 0.5).to(dt).cuda()
+        x = full[:, :C]                                   # strided view (row stride C + 8)
+        base = torch.randn(C).cuda()
+        out = base.clone()
+        ops.colsum_enqueue(x, out)
+        outs.append(out); refs.append(base.double().cpu() + x.double().cpu().sum(0))
+    ops.flush_wgrads()
+    torch.cuda.synchronize()
+    for o, r, sh in zip(outs, refs, shapes):
+        assert rel(o, r) < 1e-5, sh
+
+
 def test_gemm_full_size_property(ops):
     """BASELINE config-2 shape of the appearance W_ih product; linearity property + sampled rows vs the SIMT reference."""
     torch.manual_seed(1)

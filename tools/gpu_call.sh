@@ -1,4 +1,3 @@
-timeout 600 python -m pytest tests/test_kernels_gpu.py -x -q -m gpu --tb=short -k "grouped or gemm" 2>&1 | grep -E "^E|assert|passed|failed|Error" | head -8
+timeout 600 python -m pytest tests/test_kernels_gpu.py -x -q -m gpu --tb=short -k "grouped" 2>&1 | grep -E "^E|assert|passed|failed|Error" | head -8
 timeout 900 python -m pytest tests -x -q -m gpu --tb=short 2>&1 | grep -E "^E|assert|passed|failed|Error" | head -8
 timeout 600 python bench.py --steps 30 --warmup 3 --no-cpu --no-e2e 2>/dev/null | head -c 230; echo
-timeout 600 python tools/profile_step.py > gpurun_out/profile_step_r01_s2m.txt 2>&1; head -14 gpurun_out/profile_step_r01_s2m.txt | tail -13 | cut -c1-110

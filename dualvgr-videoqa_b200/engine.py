@@ -133,12 +133,15 @@ class TrainEngine:
         self.gflat.zero_()
         outputs = self.model(app, mot, question, question_len)
         total, ce, com, dep, correct = self.loss(outputs, answers)
-        ops.DEFER_WGRAD[0] = True          # weight gradients of the nn.Linear layers: queued during backward ...
+        ops.DEFER_WGRAD[0] = True          # weight / bias gradients of the nn.Linear layers: queued during backward ...
         try:
             total.backward()
+        except BaseException:
+            ops.clear_deferred()           # never leave half a step's gradients queued for the next one
+            raise
         finally:
             ops.DEFER_WGRAD[0] = False
-        ops.flush_wgrads()                 # ... and launched as ONE grouped tcgen05 GEMM (nothing needs them before the optimizer)
+        ops.flush_wgrads()                 # ... and launched as ONE grouped tcgen05 GEMM + ONE grouped column sum
         self.optimizer_step()
         return total.detach()
 

@@ -158,6 +158,12 @@ def colsum_enqueue(x, out):
     _COLSUM_QUEUE.append((x, out))
 
 
+def clear_deferred():
+    """Drops queued (unlaunched) weight / bias gradients — called when a step aborts between enqueue and flush."""
+    _WGRAD_QUEUE.clear()
+    _COLSUM_QUEUE.clear()
+
+
 def flush_wgrads():
     """Launches every queued weight gradient (one grouped GEMM per 32 problems) and bias gradient (one grouped column sum)."""
     if _COLSUM_QUEUE:

@@ -278,6 +278,18 @@ def linear_cat(x, w1, b1, w2, b2):
     return LinearCatFn.apply(x, w1, b1, w2, b2)
 
 
+def _route_small(param, grad):
+    """Inside an engine step: queue `grad` for accumulation into the bound .grad view of `param` (all such tiny gradients
+    land in ONE scatter launch at flush time) and return None, so autograd launches no accumulation kernel for it.
+    Everywhere else: return `grad` unchanged."""
+    if ops.DEFER_WGRAD[0] and grad is not None and grad.dtype == F32:
+        tgt = _bias_target(param)
+        if tgt is not None and tgt.numel() == grad.numel():
+            ops.small_grad_enqueue(tgt, grad if grad.is_contiguous() else grad.contiguous())
+            return None
+    return grad
+
+
 def linear(x, weight, bias=None, act=None, out_f32=False, act_grad_folded=False):
     """act_grad_folded: the consumer's backward kernel already returns d(pre-activation) (view attention, MFB pair-sum,
     read-out fold act' into their own pass), so this backward must not apply act' again."""
@@ -344,6 +356,7 @@ class AppearanceEncoderFn(Function):
         ctx.save_for_backward(xa, whh, gates, h_hist, c_hist)
         ctx.cfg = (B, N, T, Dv, S, H, p_o, seed, sid)
         ctx.wih_params, ctx.whh_params = [w_ih, w_ih_r], [w_hh, w_hh_r]
+        ctx.bias_params = (b_ih, b_hh, b_ih_r, b_hh_r)
         return out.view(B, N, 2 * H)
 
     @staticmethod
@@ -378,8 +391,9 @@ class AppearanceEncoderFn(Function):
                  bn=wbn, ksplit=wks)
         g_ih = (None, None) if dwih is None else (dwih[:4 * H], dwih[4 * H:])
         g_hh = (None, None) if t_hh is not None else (dwhh[0], dwhh[1])
-        return (None, g_ih[0], g_hh[0], db[:4 * H], db[:4 * H], g_ih[1], g_hh[1], db[4 * H:], db[4 * H:],
-                None, None, None)
+        bp = ctx.bias_params      # b_ih, b_hh, b_ih_reverse, b_hh_reverse: both biases of a direction get the same gradient
+        return (None, g_ih[0], g_hh[0], _route_small(bp[0], db[:4 * H]), _route_small(bp[1], db[:4 * H]), g_ih[1], g_hh[1],
+                _route_small(bp[2], db[4 * H:]), _route_small(bp[3], db[4 * H:]), None, None, None)
 
 
 def _lstm_weight(params, H, tag):
@@ -417,6 +431,7 @@ class QuestionEncoderFn(Function):
         ctx.save_for_backward(x, wih, whh, gates, h_hist, c_hist, qlen)
         ctx.cfg = (B, L, W, Wp, H)
         ctx.wih_params, ctx.whh_params = w_ih, w_hh
+        ctx.bias_params = [params[4 * d + j] for d in range(4) for j in (2, 3)]
         return seq_out[:, :, :2 * H].contiguous(), h_last[:, 2 * H:].contiguous()
 
     @staticmethod
@@ -458,7 +473,8 @@ class QuestionEncoderFn(Function):
         grads = []
         for d in range(4):
             sl = slice(4 * H * d, 4 * H * (d + 1))
-            grads += [None if dwih is None else dwih[sl], None if t_hh is not None else dwhh[d], db[sl], db[sl]]
+            grads += [None if dwih is None else dwih[sl], None if t_hh is not None else dwhh[d],
+                      _route_small(ctx.bias_params[2 * d], db[sl]), _route_small(ctx.bias_params[2 * d + 1], db[sl])]
         return (dwords, None) + tuple(grads)
 
 
@@ -474,6 +490,7 @@ class QAttnFn(Function):
         qc, alpha, nrm, prob, ssum = ops.qattn_fwd(y, wf, fc_b.detach(), qlen, words, W, words.shape[-1])
         ctx.save_for_backward(y, words, qlen, wf, alpha, nrm, prob, ssum)
         ctx.W = W
+        ctx.fc = (fc_w, fc_b)
         ctx.mark_non_differentiable(alpha)
         return qc, alpha
 
@@ -481,7 +498,7 @@ class QAttnFn(Function):
     def backward(ctx, dqc, _dalpha):
         y, words, qlen, wf, alpha, nrm, prob, ssum = ctx.saved_tensors
         dy, dwords, dwf, dcf = ops.qattn_bwd(_c(dqc), y, wf, qlen, words, ctx.W, alpha, nrm, prob, ssum)
-        return dy, dwords, None, dwf.view(1, -1), dcf.view(1), None
+        return dy, dwords, None, _route_small(ctx.fc[0], dwf.view(1, -1)), _route_small(ctx.fc[1], dcf.view(1)), None
 
 
 class GateFn(Function):
@@ -697,6 +714,7 @@ class ViewAttnFn(Function):
         x2 = x.view(-1, x.shape[-1])
         xnew, embed, beta = ops.view_attn_fwd(hidden, z, x2, w2v)
         ctx.save_for_backward(hidden, z, w2v, beta)
+        ctx.w2 = w2
         return xnew.view_as(x), embed.view_as(x)
 
     @staticmethod
@@ -708,7 +726,7 @@ class ViewAttnFn(Function):
         dxn = _c(dxnew).view(-1, D)
         de = _c(dembed).view(-1, D) if dembed is not None else None
         dz, dhid, dw2 = ops.view_attn_bwd(dxn, de, hidden, z, w2v, beta)
-        return dhid, dz, dxnew, dw2.view(1, -1)
+        return dhid, dz, dxnew, _route_small(ctx.w2, dw2.view(1, -1))
 
 
 class MfbPairFn(Function):
@@ -741,13 +759,14 @@ class ReadoutFn(Function):
         wv = _c(w.detach().view(-1))
         pooled, alpha = ops.readout_fwd(v, u, wv, c.detach())
         ctx.save_for_backward(v, u, wv, alpha)
+        ctx.wc = (w, c)
         return pooled
 
     @staticmethod
     def backward(ctx, dp):
         v, u, wv, alpha = ctx.saved_tensors
         dv, du, dw, dc = ops.readout_bwd(_c(dp), v, u, wv, alpha)
-        return dv, du, dw.view(1, -1), dc.view(1)
+        return dv, du, _route_small(ctx.wc[0], dw.view(1, -1)), _route_small(ctx.wc[1], dc.view(1))
 
 
 class BatchNormFn(Function):
@@ -757,6 +776,7 @@ class BatchNormFn(Function):
         y, mean, rstd = ops.bn_fwd(x, gamma.detach(), beta.detach(), run_mean, run_var, training, momentum, eps)
         ctx.save_for_backward(x, gamma.detach(), mean, rstd)
         ctx.training = training
+        ctx.affine = (gamma, beta)
         return y
 
     @staticmethod
@@ -766,7 +786,7 @@ class BatchNormFn(Function):
         if dy.dtype != BF16:
             dy = dy.to(BF16)
         dx, dg, db = ops.bn_bwd(dy, x, gamma, mean, rstd, ctx.training)
-        return dx, dg, db, None, None, None, None, None
+        return dx, _route_small(ctx.affine[0], dg), _route_small(ctx.affine[1], db), None, None, None, None, None
 
 
 class CrossEntropyFn(Function):

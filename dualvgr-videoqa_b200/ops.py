@@ -158,14 +158,28 @@ def colsum_enqueue(x, out):
     _COLSUM_QUEUE.append((x, out))
 
 
+_SMALL_QUEUE = []
+
+
+def small_grad_enqueue(target, grad):
+    """target (a bound fp32 .grad view) += grad at flush time: the gradients of the tiny parameters (attention vectors, LSTM /
+    BatchNorm biases ...) accumulate in ONE scatter launch per step instead of one elementwise launch per parameter."""
+    assert target.dtype == F32 and grad.dtype == F32 and target.numel() == grad.numel() and target.is_contiguous()
+    _SMALL_QUEUE.append((target, grad))
+
+
 def clear_deferred():
     """Drops queued (unlaunched) weight / bias gradients — called when a step aborts between enqueue and flush."""
     _WGRAD_QUEUE.clear()
     _COLSUM_QUEUE.clear()
+    _SMALL_QUEUE.clear()
 
 
 def flush_wgrads():
     """Launches every queued weight gradient (one grouped GEMM per 32 problems) and bias gradient (one grouped column sum)."""
+    if _SMALL_QUEUE:
+        scatter(list(_SMALL_QUEUE), True)
+        _SMALL_QUEUE.clear()
     if _COLSUM_QUEUE:
         m = len(_COLSUM_QUEUE)
         carr = (_lib.ColsumProblem * m)()

@@ -124,6 +124,10 @@ readout_fwd = _sig("dvgr_readout_fwd", [P, P, P, P, c_int, c_int, c_int, P, P, c
 readout_bwd = _sig("dvgr_readout_bwd", [P, c_ll, P, P, P, P, c_int, c_int, c_int, P, P, P, P, P])
 bn_fwd = _sig("dvgr_bn_fwd", [P, c_int, c_int, c_int, P, P, P, P, c_int, c_float, c_float, P, P, P, P])
 bn_bwd = _sig("dvgr_bn_bwd", [P, P, c_int, c_int, c_int, P, P, P, c_int, P, P, P, P])
+cross_entropy_ex = _sig("dvgr_cross_entropy_ex", [P, P, c_int, c_int, c_float, P, P, c_int, c_ll, P, P])
+bn_stats = _sig("dvgr_bn_stats", [P, c_int, c_int, c_int, P, P])
+bn_fwd_ex = _sig("dvgr_bn_fwd_ex", [P, c_int, c_int, c_int, P, P, P, P, c_int, c_float, c_float, P, P, P, P, c_int, P])
+bn_bwd_ex = _sig("dvgr_bn_bwd_ex", [P, P, c_int, c_int, c_int, P, P, P, c_int, P, P, P, P, c_int, c_int, P])
 cross_entropy = _sig("dvgr_cross_entropy", [P, P, c_int, c_int, c_float, P, P, c_ll, P, P])
 
 
@@ -145,6 +149,18 @@ cast_rows = _sig("dvgr_cast_rows", [P, c_ll, P, c_ll, c_int, c_int, c_int, c_int
 dropout = _sig("dvgr_dropout", [P, P, c_ll, c_float, c_ull, c_uint, P])
 act_bwd = _sig("dvgr_act_bwd", [P, P, P, c_ll, c_int, c_int, c_float, c_ull, c_uint, P])
 add = _sig("dvgr_add", [P, P, c_ll, P])
+PP = ctypes.POINTER(c_void_p)
+dropout_multi = _sig("dvgr_dropout_multi", [PP, PP, ctypes.POINTER(c_uint), c_int, c_ll, c_float, c_ull, P])
+gat_input_bwd = _sig("dvgr_gat_input_bwd", [PP, ctypes.POINTER(c_uint), c_int, c_int, PP, PP, c_ll, c_float, c_ull, P])
+PLL, PI, PF = ctypes.POINTER(c_ll), ctypes.POINTER(c_int), ctypes.POINTER(c_void_p)
+cast_rows_grouped = _sig("dvgr_cast_rows_grouped", [PP, PLL, PP, PI, PI, c_int, c_ll, c_int, c_int, P])
+lstm_pack_bias = _sig("dvgr_lstm_pack_bias", [PP, PP, c_int, c_int, P, P])
+lstm_pack_dh = _sig("dvgr_lstm_pack_dh", [P, c_ll, c_int, P, c_ll, c_int, c_int, c_int, c_int, c_int, P, P, P])
+finalize_loss = _sig("dvgr_finalize_loss", [P, P, c_int, PP, c_int, P, P])
+embed_fwd = _sig("dvgr_embed_fwd", [P, P, c_int, c_int, c_int, c_int, P, P, c_float, c_ull, c_uint, P])
+embed_bwd = _sig("dvgr_embed_bwd", [P, P, P, P, c_int, c_int, c_int, c_int, P, c_float, c_ull, c_uint, P])
+view_attn_fwd_multi = _sig("dvgr_view_attn_fwd_multi", [P, P, P, P, c_ll, c_int, c_int, P, P, P, P])
+view_attn_bwd_multi = _sig("dvgr_view_attn_bwd_multi", [P, P, P, P, P, P, c_ll, c_int, c_int, P, P, P, P])
 
 
 class Seg(ctypes.Structure):
@@ -156,7 +172,8 @@ lib.dvgr_colsum_workspace.argtypes = [c_ll, c_int]
 lib.dvgr_colsum_workspace.restype = c_ll
 colsum = _sig("dvgr_colsum", [P, c_int, c_ll, c_ll, c_int, P, P, c_int, c_float, P])
 class ColsumProblem(ctypes.Structure):
-    _fields_ = [("in_", c_void_p), ("in_is_f32", c_int), ("ld", c_ll), ("R", c_ll), ("C", c_int), ("out", c_void_p)]
+    _fields_ = [("in_", c_void_p), ("in_is_f32", c_int), ("ld", c_ll), ("R", c_ll), ("C", c_int), ("out", c_void_p),
+                ("perm_H", c_int), ("out2", c_void_p)]
 
 
 colsum_grouped = _sig("dvgr_colsum_grouped", [ctypes.POINTER(ColsumProblem), c_int, P])
@@ -172,5 +189,7 @@ EXPORTED = [
     "dvgr_view_attn_bwd", "dvgr_mfb_fwd", "dvgr_mfb_bwd", "dvgr_readout_fwd", "dvgr_readout_bwd", "dvgr_bn_fwd",
     "dvgr_bn_bwd", "dvgr_cross_entropy", "dvgr_pair_loss_workspace", "dvgr_pair_loss_multi", "dvgr_aux_loss_workspace", "dvgr_aux_loss_unit", "dvgr_prep_features", "dvgr_prep_features_ex", "dvgr_cast_rows", "dvgr_dropout",
     "dvgr_act_bwd", "dvgr_add", "dvgr_scatter", "dvgr_colsum_workspace", "dvgr_colsum", "dvgr_colsum_batched", "dvgr_colsum_grouped", "dvgr_sumsq_blocks", "dvgr_sumsq",
-    "dvgr_adam_step",
+    "dvgr_adam_step", "dvgr_dropout_multi", "dvgr_gat_input_bwd", "dvgr_embed_fwd", "dvgr_embed_bwd",
+    "dvgr_view_attn_fwd_multi", "dvgr_view_attn_bwd_multi", "dvgr_cast_rows_grouped", "dvgr_lstm_pack_bias",
+    "dvgr_lstm_pack_dh", "dvgr_finalize_loss", "dvgr_bn_stats", "dvgr_bn_fwd_ex", "dvgr_bn_bwd_ex", "dvgr_cross_entropy_ex",
 ]

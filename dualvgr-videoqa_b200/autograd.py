@@ -18,9 +18,15 @@ BF16, F32 = torch.bfloat16, torch.float32
 _rng = {"seed": 0x5EED, "site": 0, "epoch": 0}
 
 
+def set_rank_seed(rank):
+    """Data-parallel ranks draw independent dropout masks (the engine calls this after the weights are synchronised)."""
+    _rng["rank"] = int(rank)
+
+
 def begin_forward():
     """Called by DualVGR.forward: new seed for this pass, site counter reset."""
-    _rng["seed"] = (int(torch.initial_seed()) * 1000003 + _rng["epoch"] * 7919 + 12345) & 0x7FFFFFFFFFFFFFFF
+    _rng["seed"] = (int(torch.initial_seed()) * 1000003 + _rng["epoch"] * 7919 + 12345
+                    + _rng.get("rank", 0) * 0x9E3779B97F4A7C15) & 0x7FFFFFFFFFFFFFFF
     _rng["epoch"] += 1
     _rng["site"] = 0
 
@@ -44,7 +50,27 @@ PROFILE = {}
 # two-kernel path (A/B measurements). SYNC_WORDS collects the kernels' sync buffers (last word = sticky timeout flag) of the
 # most recent forward passes so that tests / bench can assert the dependency protocol never timed out.
 LSTM_SEQ = [os.environ.get("DVGR_LSTM_SEQ", "1") != "0"]
-SYNC_WORDS = collections.deque(maxlen=16)
+
+
+class _SyncLog(collections.deque):
+    """Sync buffers of the recent whole-sequence LSTM launches; the current step's sticky error words are also collected for
+    the engine's end-of-step check (ops.finalize_loss turns the loss into NaN if any is set)."""
+
+    def append(self, sync):
+        super().append(sync)
+        _STEP_FLAGS.append(sync[-1:])
+
+
+_STEP_FLAGS = []
+SYNC_WORDS = _SyncLog(maxlen=16)
+
+
+def begin_step_flags():
+    del _STEP_FLAGS[:]
+
+
+def step_flags():
+    return list(_STEP_FLAGS[-16:])
 
 
 def lstm_seq_timeouts():
@@ -100,11 +126,16 @@ def bf16_rows(params, out_cols=None, lstm_H=0, tag=""):
     oc = out_cols or C
     rows = sum(p.shape[0] for p in params)
     buf = torch.empty((rows, oc), dtype=BF16, device=params[0].device)
-    r = 0
-    with torch.no_grad():
-        for p in params:
-            ops.cast_rows(p.detach(), out=buf[r:r + p.shape[0]], out_cols=oc, lstm_H=lstm_H)
-            r += p.shape[0]
+    with torch.no_grad():       # ONE launch per 8 matrices (the per-step re-cast of the LSTM operands, outside the bf16 shadow)
+        r = 0
+        for i in range(0, len(params), 8):
+            grp = [p.detach() for p in params[i:i + 8]]
+            n = sum(p.shape[0] for p in grp)
+            if len(grp) == 1:
+                ops.cast_rows(grp[0], out=buf[r:r + n], out_cols=oc, lstm_H=lstm_H)
+            else:
+                ops.cast_rows_grouped(grp, buf[r:r + n], out_cols=oc, lstm_H=lstm_H)
+            r += n
     if len(_wcache) > 4096:
         _wcache.clear()
     _wcache[key] = (ver, buf, tuple(weakref.ref(p) for p in params))
@@ -160,11 +191,14 @@ def grad_groups(model):
     unit = getattr(model, "visual_input_unit", None)
     if unit is not None and hasattr(unit, "acGCN"):
         for i in range(unit.layers):
-            for pair in ((unit.acGCN[i], unit.appearance_GCN[i]), (unit.mcGCN[i], unit.motion_GCN[i])):
-                groups.append([att.W.weight for g in pair for att in g.attentions])
-        for i in range(unit.layers):      # the two cycle-query projections of a layer run as one GEMM (LinearCatFn)
+            # the four graphs of a layer project through ONE batched GEMM [4][D][D] (fused_stack.UnitStackFn); its two view
+            # attention projections through another [2][D][D]; the two cycle-query projections read the same input
+            gats = (unit.acGCN[i], unit.appearance_GCN[i], unit.mcGCN[i], unit.motion_GCN[i])
+            groups.append([att.W.weight for g in gats for att in g.attentions])
+            groups.append([unit.attention_appearance[i].project[0].weight, unit.attention_motion[i].project[0].weight])
             qa, qm = unit.queryPunish_appear[i].query_weight, unit.queryPunish_motion[i].query_weight
             groups += [[qa.weight, qm.weight], [qa.bias, qm.bias]]
+            groups.append([att.W.bias for g in gats for att in g.attentions])       # head biases: one column sum per graph
     return groups
 
 
@@ -174,11 +208,13 @@ class LinearFn(Function):
     x: [..., K'] bf16 with K' >= K (zero padded to a multiple of 8); W fp32 [N, K]; output bf16 (or fp32: the logits)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, act, out_f32, act_grad_folded=False):
+    def forward(ctx, x, weight, bias, act, out_f32, act_grad_folded=False, out_slot=None):
+        """out_slot: optional 1-tuple with a preallocated [M, N] output buffer (see AppearanceEncoderFn)."""
         Kp = x.shape[-1]
-        x2 = _c(x.reshape(-1, Kp))
+        x2 = _rows2d(x)
         w = bf16_rows([weight], out_cols=Kp)
-        y = ops.linear_fwd(x2, w, bias=bias, act=act, out_dtype=F32 if out_f32 else BF16)
+        y = ops.linear_fwd(x2, w, bias=bias, act=act, out_dtype=F32 if out_f32 else BF16,
+                           out=out_slot[0] if out_slot is not None else None)
         ysave = None
         if act not in (None, "none") and not act_grad_folded:
             ysave = y if y.dtype == BF16 else y.to(BF16)       # act' only needs the sign / bf16-level value of the output
@@ -192,10 +228,8 @@ class LinearFn(Function):
         x2, w, y = ctx.saved_tensors
         N = w.shape[0]
         M = x2.shape[0]
-        if ctx.out_f32:
-            N8 = (N + 7) // 8 * 8
-            d = torch.zeros((M, N8), dtype=BF16, device=dy.device)
-            d[:, :N] = dy.reshape(M, N)
+        if ctx.out_f32:      # fp32 gradient of an fp32 output -> zero-padded bf16 operand, one library pass
+            d = ops.cast_rows(_c(dy.reshape(M, N)).float(), out_cols=(N + 7) // 8 * 8)
         else:
             d = _c(dy.reshape(M, N))
             if d.dtype != BF16:
@@ -217,7 +251,15 @@ class LinearFn(Function):
                 ops.colsum(d[:, :N], out=tgt, accumulate=True)
             else:
                 db = ops.colsum(d)[:N]
-        return dx, dw, db, None, None, None
+        return dx, dw, db, None, None, None, None
+
+
+def _rows2d(x):
+    """[..., K] -> [rows, K] without a copy when the rows are regularly strided (a column slice of a wider buffer is a valid
+    TMA operand as long as its row pitch is a multiple of 16 bytes)."""
+    if x.dim() == 2 and x.stride(1) == 1 and x.stride(0) % 8 == 0 and x.data_ptr() % 16 == 0:
+        return x
+    return _c(x.reshape(-1, x.shape[-1]))
 
 
 def _bias_target(b):
@@ -290,10 +332,10 @@ def _route_small(param, grad):
     return grad
 
 
-def linear(x, weight, bias=None, act=None, out_f32=False, act_grad_folded=False):
+def linear(x, weight, bias=None, act=None, out_f32=False, act_grad_folded=False, out=None):
     """act_grad_folded: the consumer's backward kernel already returns d(pre-activation) (view attention, MFB pair-sum,
     read-out fold act' into their own pass), so this backward must not apply act' again."""
-    return LinearFn.apply(x, weight, bias, act, out_f32, act_grad_folded)
+    return LinearFn.apply(x, weight, bias, act, out_f32, act_grad_folded, (out,) if out is not None else None)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -314,11 +356,34 @@ def dropout(x, p, training):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+_UNMAP = {}
+
+
 def _lstm_unmap(H, ndir, device):
-    """row_map for gate-interleaved rows -> nn.LSTM row order: interleaved row d*4H + 4j + g -> d*4H + g*H + j."""
-    r = torch.arange(ndir * 4 * H, device=device)
-    d, rr = r // (4 * H), r % (4 * H)
-    return (d * 4 * H + (rr % 4) * H + rr // 4).to(torch.int32)
+    """row_map for gate-interleaved rows -> nn.LSTM row order: interleaved row d*4H + 4j + g -> d*4H + g*H + j.
+    Built once per (H, ndir, device) on the host (a constant: no index arithmetic kernels inside the train step)."""
+    key = (H, ndir, str(device))
+    m = _UNMAP.get(key)
+    if m is None:
+        r = torch.arange(ndir * 4 * H)
+        d, rr = r // (4 * H), r % (4 * H)
+        m = (d * 4 * H + (rr % 4) * H + rr // 4).to(torch.int32).to(device)
+        _UNMAP[key] = m
+    return m
+
+
+def _lstm_bias_grads(dg, bias_params, H):
+    """Bias gradients of an LSTM encoder from the gate gradients dg [rows, D*4H] (gate-interleaved columns).
+    bias_params: (b_ih, b_hh) per direction, flattened. Engine step: queued as grouped column sums that de-interleave
+    straight into the bound .grad views (returns Nones); otherwise computed at once and returned in nn.LSTM order."""
+    D = len(bias_params) // 2
+    tg = [_bias_target(b) for b in bias_params]
+    if ops.DEFER_WGRAD[0] and all(t is not None for t in tg):
+        for d in range(D):
+            ops.colsum_enqueue(dg[:, d * 4 * H:(d + 1) * 4 * H], tg[2 * d], perm_H=H, out2=tg[2 * d + 1])
+        return [None] * (2 * D)
+    db = ops.colsum(dg).view(D, H, 4).transpose(1, 2).reshape(D, 4 * H)
+    return [db[i // 2] for i in range(2 * D)]
 
 
 class AppearanceEncoderFn(Function):
@@ -326,21 +391,25 @@ class AppearanceEncoderFn(Function):
     input-to-hidden product of both directions (N = 8H), T fused recurrent steps, final dropout."""
 
     @staticmethod
-    def forward(ctx, app, w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r, p_in, p_out, training):
+    def forward(ctx, app, w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r, p_in, p_out, training, out_slot=None):
+        """out_slot: optional 1-tuple holding a preallocated [B*N, 2H] bf16 buffer for the result (the unit stack carries
+        the appearance and motion streams as ONE [2, B*N, D] tensor: its producers write straight into the halves)."""
         B, N, T, Dv = app.shape
         S, H = B * N, w_hh.shape[1]
         seed, sid = _site(2)
         xa = ops.prep_features(_c(app).view(S * T, Dv), T, True, True, p_in if training else 0.0, seed, sid)
         wih = _lstm_weight([w_ih, w_ih_r], H, "ih")
         whh = _lstm_weight([w_hh, w_hh_r], H, "hh").view(2, 4 * H, H)
-        bias = torch.cat([(b_ih + b_hh).view(4, H).t().reshape(-1), (b_ih_r + b_hh_r).view(4, H).t().reshape(-1)]).detach()
+        bias = ops.lstm_pack_bias([b_ih.detach(), b_ih_r.detach()], [b_hh.detach(), b_hh_r.detach()], H)
+        dst = out_slot[0] if out_slot is not None else None
         rec = PROFILE.get("wih_gemm")
         if rec is not None:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
         if LSTM_SEQ[0]:
             # ONE persistent launch: input projection + all T recurrent steps (pre-activations never reach HBM)
-            gates, h_hist, c_hist, h_last, _, sync = ops.lstm_seq_fwd(xa.view(T, S, Dv), wih, whh, bias)
+            gates, h_hist, c_hist, h_last, _, sync = ops.lstm_seq_fwd(
+                xa.view(T, S, Dv), wih, whh, bias, h_last=dst if (dst is not None and not (training and p_out > 0)) else None)
             SYNC_WORDS.append(sync)
         else:
             gates = ops.linear_fwd(xa, wih, bias=bias, bn=256).view(T, S, 8 * H)
@@ -352,7 +421,10 @@ class AppearanceEncoderFn(Function):
         out = h_last
         p_o = p_out if training else 0.0
         if p_o > 0:
-            out = ops.dropout_raw(h_last, p_o, seed, sid + 1)
+            out = ops.dropout_raw(h_last, p_o, seed, sid + 1, out=dst)
+        elif dst is not None and out.data_ptr() != dst.data_ptr():
+            dst.copy_(out)
+            out = dst
         ctx.save_for_backward(xa, whh, gates, h_hist, c_hist)
         ctx.cfg = (B, N, T, Dv, S, H, p_o, seed, sid)
         ctx.wih_params, ctx.whh_params = [w_ih, w_ih_r], [w_hh, w_hh_r]
@@ -379,8 +451,7 @@ class AppearanceEncoderFn(Function):
             dwih = None
         else:
             dwih = ops.linear_wgrad(dg, xa, row_map=unmap, bn=256)  # [8H, Dv] fp32 in nn.LSTM row order
-        db = torch.empty(8 * H, dtype=F32, device=dg.device)
-        db[unmap.long()] = ops.colsum(dg)
+        dbs = _lstm_bias_grads(dg, ctx.bias_params, H)
         # dW_hh[d] = sum_s dgates[t_d(s)]^T h_hist[d][s]   (segmented MN-major reduction, both directions in one launch)
         kin = (S + 63) // 64
         dwhh = t_hh.view(2, 4 * H, H) if t_hh is not None else torch.empty((2, 4 * H, H), dtype=F32, device=dg.device)
@@ -391,9 +462,8 @@ class AppearanceEncoderFn(Function):
                  bn=wbn, ksplit=wks)
         g_ih = (None, None) if dwih is None else (dwih[:4 * H], dwih[4 * H:])
         g_hh = (None, None) if t_hh is not None else (dwhh[0], dwhh[1])
-        bp = ctx.bias_params      # b_ih, b_hh, b_ih_reverse, b_hh_reverse: both biases of a direction get the same gradient
-        return (None, g_ih[0], g_hh[0], _route_small(bp[0], db[:4 * H]), _route_small(bp[1], db[:4 * H]), g_ih[1], g_hh[1],
-                _route_small(bp[2], db[4 * H:]), _route_small(bp[3], db[4 * H:]), None, None, None)
+        # b_ih, b_hh, b_ih_reverse, b_hh_reverse: both biases of a direction get the same gradient
+        return (None, g_ih[0], g_hh[0], dbs[0], dbs[1], g_ih[1], g_hh[1], dbs[2], dbs[3], None, None, None, None)
 
 
 def _lstm_weight(params, H, tag):
@@ -771,12 +841,22 @@ class ReadoutFn(Function):
 
 class BatchNormFn(Function):
     @staticmethod
-    def forward(ctx, x, gamma, beta, run_mean, run_var, training, momentum, eps):
+    def forward(ctx, x, gamma, beta, run_mean, run_var, training, momentum, eps, sync=None):
+        """sync = (process group, world size) -> synchronised BatchNorm: batch statistics over ALL ranks' rows (two tiny
+        all-reduces per step); None -> statistics of this rank's rows (standard DDP)."""
         x = _c(x)
-        y, mean, rstd = ops.bn_fwd(x, gamma.detach(), beta.detach(), run_mean, run_var, training, momentum, eps)
+        ext, Btot = None, x.shape[0]
+        if training and sync is not None:
+            import torch.distributed as dist
+            ext = ops.bn_stats(x)
+            dist.all_reduce(ext, op=dist.ReduceOp.SUM, group=sync[0])
+            Btot = x.shape[0] * sync[1]
+        y, mean, rstd = ops.bn_fwd(x, gamma.detach(), beta.detach(), run_mean, run_var, training, momentum, eps, ext, Btot)
         ctx.save_for_backward(x, gamma.detach(), mean, rstd)
         ctx.training = training
         ctx.affine = (gamma, beta)
+        ctx.sync = sync if (training and sync is not None) else None
+        ctx.Btot = Btot
         return y
 
     @staticmethod
@@ -785,25 +865,34 @@ class BatchNormFn(Function):
         dy = _c(dy)
         if dy.dtype != BF16:
             dy = dy.to(BF16)
-        dx, dg, db = ops.bn_bwd(dy, x, gamma, mean, rstd, ctx.training)
-        return dx, _route_small(ctx.affine[0], dg), _route_small(ctx.affine[1], db), None, None, None, None, None
+        if ctx.sync is not None:
+            import torch.distributed as dist
+            _, dg, db = ops.bn_bwd(dy, x, gamma, mean, rstd, True, stats_only=True)      # LOCAL sums = this rank's dgamma / dbeta
+            sums = torch.stack([db, dg])
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=ctx.sync[0])
+            dx, _, _ = ops.bn_bwd(dy, x, gamma, mean, rstd, True, ext_sums=sums, Btot=ctx.Btot)
+        else:
+            dx, dg, db = ops.bn_bwd(dy, x, gamma, mean, rstd, ctx.training)
+        return dx, _route_small(ctx.affine[0], dg), _route_small(ctx.affine[1], db), None, None, None, None, None, None
 
 
 class CrossEntropyFn(Function):
     """Mean cross-entropy with the gradient produced in the same launch."""
 
     @staticmethod
-    def forward(ctx, logits, answers):
-        loss, dlog, correct = ops.cross_entropy(_c(logits), answers)
+    def forward(ctx, logits, answers, unit_grad=False):
+        """unit_grad: the caller back-propagates the returned loss with coefficient exactly 1 (the engine), so backward hands
+        the stored gradient on as it is."""
+        loss, dlog, correct = ops.cross_entropy(_c(logits), answers, grad_f32=True)
         ctx.save_for_backward(dlog)
-        ctx.A = logits.shape[1]
+        ctx.unit_grad = bool(unit_grad)
         ctx.mark_non_differentiable(correct)
         return loss, correct
 
     @staticmethod
     def backward(ctx, g, _):
         (dlog,) = ctx.saved_tensors
-        return dlog[:, :ctx.A].float() * g, None
+        return (dlog if ctx.unit_grad else dlog * g), None, None
 
 
 class AuxLossFn(Function):

@@ -117,7 +117,8 @@ int dvgr_lstm_step_fwd(const dvgr_lstm_args* a, void* stream) {
   return rc;
 }
 
-int dvgr_lstm_seq_sync_words(int S, int ndir) { return ndir * ((S + 127) / 128) + 1; }
+// per-(direction, 128-sequence block) completion counters, the tile-claim counter, the sticky error word (last)
+int dvgr_lstm_seq_sync_words(int S, int ndir) { return ndir * ((S + 127) / 128) + 2; }
 
 int dvgr_lstm_seq_fwd(const dvgr_lstm_seq_args* a, void* stream) {
   if (!a) return set_error("dvgr_lstm_seq_fwd: null args");

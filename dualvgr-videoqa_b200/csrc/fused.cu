@@ -38,6 +38,11 @@ view_attn_fwd_kernel(const bf16* __restrict__ hidden, const bf16* __restrict__ z
                      const float* __restrict__ w2, long long M, int D, bf16* __restrict__ Xnew,
                      bf16* __restrict__ embed, float* __restrict__ beta) {
   pdl_trigger();
+  {   // blockIdx.y = input stream (appearance / motion): every operand of stream s follows that of stream s-1
+    const long long sy = blockIdx.y;
+    hidden += sy * 2 * M * D; z += sy * 2 * M * D; X += sy * M * D; w2 += sy * D; Xnew += sy * M * D; beta += sy * M * 2;
+    if (embed != nullptr) embed += sy * M * D;
+  }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (long long r = (long long)blockIdx.x * 8 + warp; r < M; r += (long long)gridDim.x * 8) {
     float w0 = 0.f, w1 = 0.f;
@@ -83,6 +88,12 @@ view_attn_bwd_kernel(const bf16* __restrict__ dXnew, const bf16* __restrict__ de
                      const bf16* __restrict__ z, const float* __restrict__ w2, const float* __restrict__ beta,
                      long long M, int D, bf16* __restrict__ dz, bf16* __restrict__ dhid, float* __restrict__ dw2_part) {
   pdl_trigger();
+  {   // blockIdx.y = input stream
+    const long long sy = blockIdx.y;
+    dXnew += sy * M * D; hidden += sy * 2 * M * D; z += sy * 2 * M * D; w2 += sy * D; beta += sy * M * 2;
+    dz += sy * 2 * M * D; dhid += sy * 2 * M * D; dw2_part += sy * (long long)gridDim.x * D;
+    if (dembed_ext != nullptr) dembed_ext += sy * M * D;
+  }
   extern __shared__ float dw2_s[];   // [D]
   for (int c = threadIdx.x; c < D; c += blockDim.x) dw2_s[c] = 0.f;
   __syncthreads();
@@ -297,13 +308,24 @@ template <typename TX>
 __global__ void __launch_bounds__(256)
 bn_fwd_kernel(const TX* __restrict__ x, int B, int D, const float* __restrict__ gamma, const float* __restrict__ betap,
               float* __restrict__ run_mean, float* __restrict__ run_var, int training, float momentum, float eps,
-              bf16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+              bf16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out,
+              const float* __restrict__ ext_stats, int Btot) {
   __shared__ float red[8][33];
   const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
   const bool ok = c < D;
   float mean = 0.f, var = 1.f;
-  if (training) {
+  if (training && ext_stats != nullptr) {
+    // synchronised BatchNorm: (sum, sum of squares) over the GLOBAL batch of Btot rows, all-reduced by the caller
+    if (ok) {
+      mean = ext_stats[c] / Btot;
+      var = fmaxf(ext_stats[D + c] / Btot - mean * mean, 0.f);
+      if (rl == 0 && run_mean != nullptr) {
+        run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * mean;
+        run_var[c] = (1.f - momentum) * run_var[c] + momentum * (Btot > 1 ? var * Btot / (Btot - 1) : var);
+      }
+    }
+  } else if (training) {
     float s = 0.f;
     if (ok)
       for (int r = rl; r < B; r += 8) s += ldf<TX>(x + (long long)r * D + c);
@@ -335,11 +357,36 @@ bn_fwd_kernel(const TX* __restrict__ x, int B, int D, const float* __restrict__ 
     y[(long long)r * D + c] = __float2bfloat16_rn((ldf<TX>(x + (long long)r * D + c) - mean) * rstd * g + bt);
 }
 
+// per-column (sum, sum of squares) of the local batch: out [2][D] (the operand of the SyncBN all-reduce)
+template <typename TX>
+__global__ void __launch_bounds__(256) bn_stats_kernel(const TX* __restrict__ x, int B, int D, float* __restrict__ out) {
+  __shared__ float red[8][33];
+  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  const bool ok = c < D;
+  float s = 0.f, ss = 0.f;
+  if (ok)
+    for (int r = rl; r < B; r += 8) {
+      const float v = ldf<TX>(x + (long long)r * D + c);
+      s += v;
+      ss += v * v;
+    }
+  s = bn_reduce8(s, red, cl, rl);
+  ss = bn_reduce8(ss, red, cl, rl);
+  if (ok && rl == 0) {
+    out[c] = s;
+    out[D + c] = ss;
+  }
+}
+
+// ext_sums [2][D] = (sum dy, sum dy * xhat) over the GLOBAL batch of Btot rows (SyncBN, second pass); stats_only: write the
+// LOCAL sums to dbeta / dgamma and stop (SyncBN, first pass)
 template <typename TX>
 __global__ void __launch_bounds__(256)
 bn_bwd_kernel(const bf16* __restrict__ dy, const TX* __restrict__ x, int B, int D, const float* __restrict__ gamma,
               const float* __restrict__ mean, const float* __restrict__ rstd, int training, TX* __restrict__ dx,
-              float* __restrict__ dgamma, float* __restrict__ dbeta) {
+              float* __restrict__ dgamma, float* __restrict__ dbeta, const float* __restrict__ ext_sums, int Btot,
+              int stats_only) {
   __shared__ float red[8][33];
   const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
@@ -356,14 +403,21 @@ bn_bwd_kernel(const bf16* __restrict__ dy, const TX* __restrict__ x, int B, int 
   sdy = bn_reduce8(sdy, red, cl, rl);
   sdyx = bn_reduce8(sdyx, red, cl, rl);
   if (!ok) return;
-  if (rl == 0) {
+  if (rl == 0 && dgamma != nullptr) {
     dgamma[c] = sdyx;
     dbeta[c] = sdy;
+  }
+  if (stats_only) return;
+  float nb = (float)B;
+  if (ext_sums != nullptr) {
+    sdy = ext_sums[c];
+    sdyx = ext_sums[D + c];
+    nb = (float)Btot;
   }
   for (int r = rl; r < B; r += 8) {
     const float d = __bfloat162float(dy[(long long)r * D + c]);
     const float xh = (ldf<TX>(x + (long long)r * D + c) - m) * rs;
-    const float o = training ? g * rs * (d - sdy / B - xh * sdyx / B) : g * rs * d;
+    const float o = training ? g * rs * (d - sdy / nb - xh * sdyx / nb) : g * rs * d;
     stf<TX>(dx + (long long)r * D + c, o);
   }
 }
@@ -371,8 +425,9 @@ bn_bwd_kernel(const bf16* __restrict__ dy, const TX* __restrict__ x, int B, int 
 // =============================================================================================== cross-entropy
 // nn.CrossEntropyLoss (mean) at train.py:121,146: loss_part[b] = -log softmax(logits_b)[ans_b] / B,
 // dlogits = (softmax - onehot) * scale / B  (bf16, row stride ld_d, padding columns zeroed)
+template <typename TG>
 __global__ void ce_kernel(const float* __restrict__ logits, const long long* __restrict__ ans, int B, int A,
-                          float scale, float* __restrict__ loss_part, bf16* __restrict__ dlogits, long long ld_d,
+                          float scale, float* __restrict__ loss_part, TG* __restrict__ dlogits, long long ld_d,
                           int* __restrict__ correct) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -402,7 +457,7 @@ __global__ void ce_kernel(const float* __restrict__ logits, const long long* __r
     for (int a = lane; a < ld_d; a += 32) {
       float g = 0.f;
       if (a < A) g = (__expf(row[a] - lse) - (a == t ? 1.f : 0.f)) * scale / B;
-      dlogits[(long long)b * ld_d + a] = __float2bfloat16_rn(g);
+      stf<TG>(dlogits + (long long)b * ld_d + a, g);
     }
   }
 }
@@ -495,6 +550,195 @@ __global__ void act_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restri
       for (int q = 0; q < 8; ++q) d[q] += o[q];
     }
     store8(out + i * 8, d);
+  }
+}
+
+
+// Up to 4 dropped copies of (up to 4) inputs in ONE launch: the four graphs of a DualVGR unit each read their own dropped copy
+// of their stream (reference model/GraphNN.py:175, one F.dropout per punishGAT call). blockIdx.y = copy.
+struct DropMulti {
+  const bf16* in[4];
+  bf16* out[4];
+  unsigned int stream[4];
+};
+__global__ void dropout_multi_kernel(const DropMulti m, long long n8, DropoutCfg dc) {
+  pdl_trigger();
+  const int y = blockIdx.y;
+  dc.stream = m.stream[y];
+  const bf16* __restrict__ in = m.in[y];
+  bf16* __restrict__ out = m.out[y];
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    float f[8], sc[8];
+    load8(in + i * 8, f);
+    dropout_scale8(dc, i, sc);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) f[q] *= sc[q];
+    store8(out + i * 8, f);
+  }
+}
+
+// Backward of those copies, summed per stream and merged with the gradient that bypasses the graphs (the residual branch):
+//   dX[s] = base[s] + sum_{g in stream s} mask_g * dxt[g]          blockIdx.y = stream
+struct GatInBwd {
+  const bf16* dxt[4];
+  unsigned int stream[4];
+  const bf16* base[2];
+  bf16* out[2];
+  int per_stream;
+};
+__global__ void gat_input_bwd_kernel(const GatInBwd m, long long n8, DropoutCfg dc) {
+  pdl_trigger();
+  const int s = blockIdx.y;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    float acc[8];
+    if (m.base[s] != nullptr) {
+      load8(m.base[s] + i * 8, acc);
+    } else {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+    }
+    for (int j = 0; j < m.per_stream; ++j) {
+      const int g = s * m.per_stream + j;
+      float d[8], sc[8];
+      load8(m.dxt[g] + i * 8, d);
+      dc.stream = m.stream[g];
+      dropout_scale8(dc, i, sc);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc[q] += d[q] * sc[q];
+    }
+    store8(m.out[s] + i * 8, acc);
+  }
+}
+
+// Question-word prologue, reference model/Preprocessing.py:109-111: words = tanh(dropout(embedding[tokens])) written twice
+// in one pass — [B][L][Wp] (operand of QueryAttn) and time-major [L][B][Wp] (TMA operand of the question LSTMs) — both bf16
+// with the word dimension zero-padded to Wp (16-byte rows). Replaces the embedding gather, dropout, tanh, pad, transpose and
+// cast launches of the eager path.
+__global__ void embed_fwd_kernel(const long long* __restrict__ tokens, const float* __restrict__ table, int B, int L, int W,
+                                 int Wp, bf16* __restrict__ words, bf16* __restrict__ x_tm, DropoutCfg dc) {
+  pdl_trigger();
+  const int w8 = Wp / 8;
+  const long long n8 = (long long)B * L * w8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / w8;       // = b * L + l
+    const int c0 = (int)(i - row * w8) * 8;
+    const long long tok = tokens[row];
+    float f[8], sc[8];
+    dropout_scale8(dc, i, sc);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) f[q] = (c0 + q < W) ? tanhf_(table[tok * W + c0 + q] * sc[q]) : 0.f;
+    store8(words + i * 8, f);
+    const long long b = row / L;
+    const int l = (int)(row - b * L);
+    store8(x_tm + (((long long)l * B + b) * Wp + c0), f);
+  }
+}
+// dtable[tok] += (d_words[b][l] + d_x[l][b]) * tanh'(words) * mask   (fp32 atomics: tokens repeat across the batch)
+__global__ void embed_bwd_kernel(const long long* __restrict__ tokens, const bf16* __restrict__ words,
+                                 const bf16* __restrict__ d_words, const bf16* __restrict__ d_x_tm, int B, int L, int W, int Wp,
+                                 float* __restrict__ dtable, DropoutCfg dc) {
+  pdl_trigger();
+  const int w8 = Wp / 8;
+  const long long n8 = (long long)B * L * w8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / w8;
+    const int c0 = (int)(i - row * w8) * 8;
+    const long long tok = tokens[row];
+    const long long b = row / L;
+    const int l = (int)(row - b * L);
+    float w[8], d[8], sc[8];
+    load8(words + i * 8, w);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) d[q] = 0.f;
+    if (d_words != nullptr) load8(d_words + i * 8, d);
+    if (d_x_tm != nullptr) {
+      float e[8];
+      load8(d_x_tm + (((long long)l * B + b) * Wp + c0), e);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) d[q] += e[q];
+    }
+    dropout_scale8(dc, i, sc);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float g = d[q] * (1.f - w[q] * w[q]) * sc[q];
+      if (c0 + q < W && g != 0.f) atomicAdd(dtable + tok * W + c0 + q, g);
+    }
+  }
+}
+
+// ---- LSTM operand packing (one launch each instead of a chain of tiny framework kernels per train step)
+// Several cast_rows problems in one launch (blockIdx.y = problem): the bf16 gate-interleaved copies of all W_ih / W_hh matrices
+// of an encoder (2 - 4 directions) written into ONE row-concatenated operand.
+constexpr int kMaxCast = 8;
+struct CastGroup {
+  const float* in[kMaxCast];
+  bf16* out[kMaxCast];
+  long long ld_in[kMaxCast];
+  int rows[kMaxCast], cols[kMaxCast];
+  long long ld_out;
+  int out_cols, lstm_H;
+};
+__global__ void cast_rows_grouped_kernel(const CastGroup G) {
+  pdl_trigger();
+  const int y = blockIdx.y;
+  const float* __restrict__ in = G.in[y];
+  bf16* __restrict__ out = G.out[y];
+  const int cols = G.cols[y];
+  const long long total = (long long)G.rows[y] * G.out_cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / G.out_cols), c = (int)(i - (long long)r * G.out_cols);
+    int src = r;
+    if (G.lstm_H > 0) src = (r & 3) * G.lstm_H + (r >> 2);
+    out[(long long)r * G.ld_out + c] = __float2bfloat16_rn(c < cols ? in[(long long)src * G.ld_in[y] + c] : 0.f);
+  }
+}
+// bias[d][4j + g] = b_ih[d][g*H + j] + b_hh[d][g*H + j]   (the fused cell's gate-interleaved bias, all directions at once)
+struct BiasGroup {
+  const float* b_ih[4];
+  const float* b_hh[4];
+};
+__global__ void lstm_pack_bias_kernel(const BiasGroup G, int H, float* __restrict__ out) {
+  pdl_trigger();
+  const int d = blockIdx.y;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 4 * H; i += gridDim.x * blockDim.x) {
+    const int src = (i & 3) * H + (i >> 2);
+    out[(long long)d * 4 * H + i] = G.b_ih[d][src] + G.b_hh[d][src];
+  }
+}
+// Gradients arriving at the question encoder (model/Preprocessing.py:112-123) packed for dvgr_lstm_seq_bwd in one pass:
+//   d_seq [B][L][ld_seq] bf16 (per-token states of directions 0 .. nd_seq-1, H columns each; may be null)
+//     -> dh_seq blocked [T][D][RB][H/8][32][8] (zeros for the other directions and the padded rows)
+//   d_last [B][ld_last] bf16 (final states of directions d_last0 .. D-1; may be null) -> dh_last [B][D*H] (zeros elsewhere)
+__global__ void lstm_pack_dh_kernel(const bf16* __restrict__ d_seq, long long ld_seq, int nd_seq, const bf16* __restrict__ d_last,
+                                    long long ld_last, int d_last0, int S, int T, int D, int H, bf16* __restrict__ dh_seq,
+                                    bf16* __restrict__ dh_last) {
+  pdl_trigger();
+  const int RB = (S + 31) / 32, UG = H / 8;
+  const long long n_seq = (long long)T * D * RB * UG * 32;          // 16-byte pieces of dh_seq
+  const long long n_last = (long long)S * D * UG;                   // 16-byte pieces of dh_last
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_seq + n_last; i += (long long)gridDim.x * blockDim.x) {
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (i < n_seq) {
+      const int r = (int)(i & 31);
+      long long rest = i >> 5;
+      const int ug = (int)(rest % UG); rest /= UG;
+      const int rb = (int)(rest % RB); rest /= RB;
+      const int d = (int)(rest % D);
+      const int t = (int)(rest / D);
+      const int seq = rb * 32 + r;
+      if (d_seq != nullptr && d < nd_seq && seq < S)
+        v = *reinterpret_cast<const uint4*>(d_seq + ((long long)seq * T + t) * ld_seq + (long long)d * H + ug * 8);
+      reinterpret_cast<uint4*>(dh_seq)[i] = v;
+    } else {
+      const long long j = i - n_seq;
+      const int ug = (int)(j % UG);
+      const long long rest = j / UG;
+      const int d = (int)(rest % D);
+      const int seq = (int)(rest / D);
+      if (d_last != nullptr && d >= d_last0)
+        v = *reinterpret_cast<const uint4*>(d_last + (long long)seq * ld_last + (long long)(d - d_last0) * H + ug * 8);
+      reinterpret_cast<uint4*>(dh_last)[j] = v;
+    }
   }
 }
 
@@ -616,28 +860,37 @@ using namespace dvgr;
 #define BF(p) reinterpret_cast<bf16*>(p)
 #define CBF(p) reinterpret_cast<const bf16*>(p)
 
-extern "C" int dvgr_view_attn_fwd(const void* hidden, const void* z, const void* x, const float* w2, long long M, int D,
-                                  void* xnew, void* embed, float* beta, void* stream) {
-  if (M <= 0) return 0;
+extern "C" int dvgr_view_attn_fwd_multi(const void* hidden, const void* z, const void* x, const float* w2, long long M,
+                                        int D, int n_streams, void* xnew, void* embed, float* beta, void* stream) {
+  if (M <= 0 || n_streams <= 0) return 0;
   if (D % 8 != 0) return set_error("view_attn: D=%d must be a multiple of 8", D);
-  view_attn_fwd_kernel<<<grid_for(M, 8, 148 * 8), 256, 0, ST(stream)>>>(CBF(hidden), CBF(z), CBF(x), w2, M, D, BF(xnew),
-                                                                       BF(embed), beta);
+  view_attn_fwd_kernel<<<dim3(grid_for(M, 8, 148 * 8 / n_streams), n_streams), 256, 0, ST(stream)>>>(
+      CBF(hidden), CBF(z), CBF(x), w2, M, D, BF(xnew), BF(embed), beta);
   DVGR_CHECK_LAUNCH("view_attn_fwd");
   return 0;
+}
+extern "C" int dvgr_view_attn_fwd(const void* hidden, const void* z, const void* x, const float* w2, long long M, int D,
+                                  void* xnew, void* embed, float* beta, void* stream) {
+  return dvgr_view_attn_fwd_multi(hidden, z, x, w2, M, D, 1, xnew, embed, beta, stream);
 }
 
 extern "C" int dvgr_view_attn_bwd_blocks(long long M) { return grid_for(M, 8, 148 * 2); }
 
+extern "C" int dvgr_view_attn_bwd_multi(const void* dxnew, const void* dembed_ext, const void* hidden, const void* z,
+                                        const float* w2, const float* beta, long long M, int D, int n_streams, void* dz,
+                                        void* dhid, float* dw2_part, void* stream) {
+  if (M <= 0 || n_streams <= 0) return 0;
+  if (D % 8 != 0) return set_error("view_attn: D=%d must be a multiple of 8", D);
+  const int blocks = dvgr_view_attn_bwd_blocks(M);
+  view_attn_bwd_kernel<<<dim3(blocks, n_streams), 256, D * sizeof(float), ST(stream)>>>(
+      CBF(dxnew), CBF(dembed_ext), CBF(hidden), CBF(z), w2, beta, M, D, BF(dz), BF(dhid), dw2_part);
+  DVGR_CHECK_LAUNCH("view_attn_bwd");
+  return 0;
+}
 extern "C" int dvgr_view_attn_bwd(const void* dxnew, const void* dembed_ext, const void* hidden, const void* z,
                                   const float* w2, const float* beta, long long M, int D, void* dz, void* dhid,
                                   float* dw2_part, void* stream) {
-  if (M <= 0) return 0;
-  if (D % 8 != 0) return set_error("view_attn: D=%d must be a multiple of 8", D);
-  const int blocks = dvgr_view_attn_bwd_blocks(M);
-  view_attn_bwd_kernel<<<blocks, 256, D * sizeof(float), ST(stream)>>>(CBF(dxnew), CBF(dembed_ext), CBF(hidden), CBF(z),
-                                                                      w2, beta, M, D, BF(dz), BF(dhid), dw2_part);
-  DVGR_CHECK_LAUNCH("view_attn_bwd");
-  return 0;
+  return dvgr_view_attn_bwd_multi(dxnew, dembed_ext, hidden, z, w2, beta, M, D, 1, dz, dhid, dw2_part, stream);
 }
 
 extern "C" int dvgr_mfb_fwd(const void* x0, const void* x1, void* z, long long M, int mm2, void* stream) {
@@ -679,41 +932,69 @@ extern "C" int dvgr_readout_bwd(const void* dpooled, long long ld_p, const void*
   return 0;
 }
 
-extern "C" int dvgr_bn_fwd(const void* x, int x_is_f32, int B, int D, const float* gamma, const float* beta,
-                           float* run_mean, float* run_var, int training, float momentum, float eps, void* y,
-                           float* mean_out, float* rstd_out, void* stream) {
+extern "C" int dvgr_bn_fwd_ex(const void* x, int x_is_f32, int B, int D, const float* gamma, const float* beta,
+                              float* run_mean, float* run_var, int training, float momentum, float eps, void* y,
+                              float* mean_out, float* rstd_out, const float* ext_stats, int Btot, void* stream) {
   if (B <= 0 || D <= 0) return 0;
+  if (ext_stats != nullptr && Btot < B) return set_error("bn_fwd: global batch %d smaller than the local one %d", Btot, B);
   if (x_is_f32)
     bn_fwd_kernel<float><<<(D + 31) / 32, 256, 0, ST(stream)>>>(reinterpret_cast<const float*>(x), B, D, gamma, beta,
                                                                  run_mean, run_var, training, momentum, eps, BF(y),
-                                                                 mean_out, rstd_out);
+                                                                 mean_out, rstd_out, ext_stats, Btot);
   else
     bn_fwd_kernel<bf16><<<(D + 31) / 32, 256, 0, ST(stream)>>>(CBF(x), B, D, gamma, beta, run_mean, run_var, training,
-                                                                momentum, eps, BF(y), mean_out, rstd_out);
+                                                                momentum, eps, BF(y), mean_out, rstd_out, ext_stats, Btot);
   DVGR_CHECK_LAUNCH("bn_fwd");
+  return 0;
+}
+extern "C" int dvgr_bn_fwd(const void* x, int x_is_f32, int B, int D, const float* gamma, const float* beta,
+                           float* run_mean, float* run_var, int training, float momentum, float eps, void* y,
+                           float* mean_out, float* rstd_out, void* stream) {
+  return dvgr_bn_fwd_ex(x, x_is_f32, B, D, gamma, beta, run_mean, run_var, training, momentum, eps, y, mean_out, rstd_out,
+                        nullptr, B, stream);
+}
+extern "C" int dvgr_bn_stats(const void* x, int x_is_f32, int B, int D, float* out, void* stream) {
+  if (B <= 0 || D <= 0) return 0;
+  if (x_is_f32) bn_stats_kernel<float><<<(D + 31) / 32, 256, 0, ST(stream)>>>(reinterpret_cast<const float*>(x), B, D, out);
+  else bn_stats_kernel<bf16><<<(D + 31) / 32, 256, 0, ST(stream)>>>(CBF(x), B, D, out);
+  DVGR_CHECK_LAUNCH("bn_stats");
+  return 0;
+}
+extern "C" int dvgr_bn_bwd_ex(const void* dy, const void* x, int x_is_f32, int B, int D, const float* gamma,
+                              const float* mean, const float* rstd, int training, void* dx, float* dgamma, float* dbeta,
+                              const float* ext_sums, int Btot, int stats_only, void* stream) {
+  if (B <= 0 || D <= 0) return 0;
+  if (x_is_f32)
+    bn_bwd_kernel<float><<<(D + 31) / 32, 256, 0, ST(stream)>>>(CBF(dy), reinterpret_cast<const float*>(x), B, D, gamma,
+                                                                 mean, rstd, training, reinterpret_cast<float*>(dx),
+                                                                 dgamma, dbeta, ext_sums, Btot, stats_only);
+  else
+    bn_bwd_kernel<bf16><<<(D + 31) / 32, 256, 0, ST(stream)>>>(CBF(dy), CBF(x), B, D, gamma, mean, rstd, training,
+                                                                BF(dx), dgamma, dbeta, ext_sums, Btot, stats_only);
+  DVGR_CHECK_LAUNCH("bn_bwd");
   return 0;
 }
 extern "C" int dvgr_bn_bwd(const void* dy, const void* x, int x_is_f32, int B, int D, const float* gamma,
                            const float* mean, const float* rstd, int training, void* dx, float* dgamma, float* dbeta,
                            void* stream) {
-  if (B <= 0 || D <= 0) return 0;
-  if (x_is_f32)
-    bn_bwd_kernel<float><<<(D + 31) / 32, 256, 0, ST(stream)>>>(CBF(dy), reinterpret_cast<const float*>(x), B, D, gamma,
-                                                                 mean, rstd, training, reinterpret_cast<float*>(dx),
-                                                                 dgamma, dbeta);
-  else
-    bn_bwd_kernel<bf16><<<(D + 31) / 32, 256, 0, ST(stream)>>>(CBF(dy), CBF(x), B, D, gamma, mean, rstd, training,
-                                                                BF(dx), dgamma, dbeta);
-  DVGR_CHECK_LAUNCH("bn_bwd");
-  return 0;
+  return dvgr_bn_bwd_ex(dy, x, x_is_f32, B, D, gamma, mean, rstd, training, dx, dgamma, dbeta, nullptr, B, 0, stream);
 }
 
-extern "C" int dvgr_cross_entropy(const float* logits, const long long* answers, int B, int A, float scale,
-                                  float* loss_part, void* dlogits, long long ld_d, int* correct, void* stream) {
+extern "C" int dvgr_cross_entropy_ex(const float* logits, const long long* answers, int B, int A, float scale,
+                                     float* loss_part, void* dlogits, int grad_is_f32, long long ld_d, int* correct,
+                                     void* stream) {
   if (B <= 0) return 0;
-  ce_kernel<<<(B + 7) / 8, 256, 0, ST(stream)>>>(logits, answers, B, A, scale, loss_part, BF(dlogits), ld_d, correct);
+  if (grad_is_f32)
+    ce_kernel<float><<<(B + 7) / 8, 256, 0, ST(stream)>>>(logits, answers, B, A, scale, loss_part,
+                                                          reinterpret_cast<float*>(dlogits), ld_d, correct);
+  else
+    ce_kernel<bf16><<<(B + 7) / 8, 256, 0, ST(stream)>>>(logits, answers, B, A, scale, loss_part, BF(dlogits), ld_d, correct);
   DVGR_CHECK_LAUNCH("cross_entropy");
   return 0;
+}
+extern "C" int dvgr_cross_entropy(const float* logits, const long long* answers, int B, int A, float scale,
+                                  float* loss_part, void* dlogits, long long ld_d, int* correct, void* stream) {
+  return dvgr_cross_entropy_ex(logits, answers, B, A, scale, loss_part, dlogits, 0, ld_d, correct, stream);
 }
 
 extern "C" int dvgr_prep_features_ex(const void* in, int in_is_bf16, void* out, long long S, int T, int C, int do_tanh,
@@ -757,6 +1038,115 @@ extern "C" int dvgr_dropout(const void* in, void* out, long long n, float p, uns
   return 0;
 }
 
+
+extern "C" int dvgr_dropout_multi(const void* const* in, void* const* out, const unsigned int* drop_streams, int n_copies,
+                                  long long n, float p, unsigned long long seed, void* stream) {
+  if (n % 8 != 0) return set_error("dropout_multi: n=%lld must be a multiple of 8", n);
+  if (n_copies < 1 || n_copies > 4) return set_error("dropout_multi: n_copies=%d out of range [1,4]", n_copies);
+  if (n <= 0) return 0;
+  DropMulti m;
+  memset(&m, 0, sizeof(m));
+  for (int i = 0; i < n_copies; ++i) {
+    if (!in[i] || !out[i]) return set_error("dropout_multi: null pointer for copy %d", i);
+    m.in[i] = CBF(in[i]); m.out[i] = BF(out[i]); m.stream[i] = drop_streams[i];
+  }
+  DropoutCfg dc{seed, 0u, p, seed_offset_ptr()};
+  dropout_multi_kernel<<<dim3(grid_for(n / 8, 256, 148 * 4), n_copies), 256, 0, ST(stream)>>>(m, n / 8, dc);
+  DVGR_CHECK_LAUNCH("dropout_multi");
+  return 0;
+}
+
+extern "C" int dvgr_gat_input_bwd(const void* const* dxt, const unsigned int* drop_streams, int n_streams, int per_stream,
+                                  const void* const* base, void* const* out, long long n, float p, unsigned long long seed,
+                                  void* stream) {
+  if (n % 8 != 0) return set_error("gat_input_bwd: n=%lld must be a multiple of 8", n);
+  if (n_streams < 1 || n_streams > 2 || per_stream < 1 || n_streams * per_stream > 4)
+    return set_error("gat_input_bwd: %d streams x %d graphs out of range", n_streams, per_stream);
+  if (n <= 0) return 0;
+  GatInBwd m;
+  memset(&m, 0, sizeof(m));
+  m.per_stream = per_stream;
+  for (int g = 0; g < n_streams * per_stream; ++g) {
+    if (!dxt[g]) return set_error("gat_input_bwd: null gradient for graph %d", g);
+    m.dxt[g] = CBF(dxt[g]); m.stream[g] = drop_streams[g];
+  }
+  for (int s_ = 0; s_ < n_streams; ++s_) {
+    if (!out[s_]) return set_error("gat_input_bwd: null output for stream %d", s_);
+    m.base[s_] = base ? CBF(base[s_]) : nullptr; m.out[s_] = BF(out[s_]);
+  }
+  DropoutCfg dc{seed, 0u, p, seed_offset_ptr()};
+  gat_input_bwd_kernel<<<dim3(grid_for(n / 8, 256, 148 * 8), n_streams), 256, 0, ST(stream)>>>(m, n / 8, dc);
+  DVGR_CHECK_LAUNCH("gat_input_bwd");
+  return 0;
+}
+
+extern "C" int dvgr_embed_fwd(const long long* tokens, const float* table, int B, int L, int W, int Wp, void* words,
+                              void* x_tm, float p, unsigned long long seed, unsigned int drop_stream, void* stream) {
+  if (B <= 0 || L <= 0) return 0;
+  if (Wp % 8 != 0 || Wp < W) return set_error("embed: Wp=%d must be a multiple of 8 and >= W=%d", Wp, W);
+  DropoutCfg dc{seed, drop_stream, p, seed_offset_ptr()};
+  embed_fwd_kernel<<<grid_for((long long)B * L * (Wp / 8)), 256, 0, ST(stream)>>>(tokens, table, B, L, W, Wp, BF(words),
+                                                                                   BF(x_tm), dc);
+  DVGR_CHECK_LAUNCH("embed_fwd");
+  return 0;
+}
+extern "C" int dvgr_embed_bwd(const long long* tokens, const void* words, const void* d_words, const void* d_x_tm, int B,
+                              int L, int W, int Wp, float* dtable, float p, unsigned long long seed,
+                              unsigned int drop_stream, void* stream) {
+  if (B <= 0 || L <= 0) return 0;
+  if (Wp % 8 != 0 || Wp < W) return set_error("embed: Wp=%d must be a multiple of 8 and >= W=%d", Wp, W);
+  DropoutCfg dc{seed, drop_stream, p, seed_offset_ptr()};
+  embed_bwd_kernel<<<grid_for((long long)B * L * (Wp / 8)), 256, 0, ST(stream)>>>(tokens, CBF(words), CBF(d_words),
+                                                                                   CBF(d_x_tm), B, L, W, Wp, dtable, dc);
+  DVGR_CHECK_LAUNCH("embed_bwd");
+  return 0;
+}
+
+extern "C" int dvgr_cast_rows_grouped(const float* const* in, const long long* ld_in, void* const* out, const int* rows,
+                                      const int* cols, int n, long long ld_out, int out_cols, int lstm_H, void* stream) {
+  if (n <= 0) return 0;
+  if (n > kMaxCast) return set_error("cast_rows_grouped: n=%d > %d", n, kMaxCast);
+  CastGroup G;
+  memset(&G, 0, sizeof(G));
+  long long most = 0;
+  for (int i = 0; i < n; ++i) {
+    if (!in[i] || !out[i]) return set_error("cast_rows_grouped: null pointer in problem %d", i);
+    if (lstm_H > 0 && rows[i] != 4 * lstm_H) return set_error("cast_rows_grouped: rows=%d != 4*H=%d", rows[i], 4 * lstm_H);
+    G.in[i] = in[i]; G.out[i] = BF(out[i]); G.ld_in[i] = ld_in[i]; G.rows[i] = rows[i]; G.cols[i] = cols[i];
+    most = std::max(most, (long long)rows[i] * out_cols);
+  }
+  G.ld_out = ld_out; G.out_cols = out_cols; G.lstm_H = lstm_H;
+  if (most <= 0) return 0;
+  cast_rows_grouped_kernel<<<dim3(grid_for(most, 256, 148 * 4), n), 256, 0, ST(stream)>>>(G);
+  DVGR_CHECK_LAUNCH("cast_rows_grouped");
+  return 0;
+}
+
+extern "C" int dvgr_lstm_pack_bias(const float* const* b_ih, const float* const* b_hh, int ndir, int H, float* out,
+                                   void* stream) {
+  if (ndir < 1 || ndir > 4) return set_error("lstm_pack_bias: ndir=%d out of range [1,4]", ndir);
+  BiasGroup G;
+  memset(&G, 0, sizeof(G));
+  for (int d = 0; d < ndir; ++d) {
+    if (!b_ih[d] || !b_hh[d]) return set_error("lstm_pack_bias: null bias for direction %d", d);
+    G.b_ih[d] = b_ih[d]; G.b_hh[d] = b_hh[d];
+  }
+  lstm_pack_bias_kernel<<<dim3((4 * H + 255) / 256, ndir), 256, 0, ST(stream)>>>(G, H, out);
+  DVGR_CHECK_LAUNCH("lstm_pack_bias");
+  return 0;
+}
+
+extern "C" int dvgr_lstm_pack_dh(const void* d_seq, long long ld_seq, int nd_seq, const void* d_last, long long ld_last,
+                                 int d_last0, int S, int T, int D, int H, void* dh_seq, void* dh_last, void* stream) {
+  if (S <= 0 || T <= 0 || D <= 0) return 0;
+  if (H % 8 != 0 || ld_seq % 8 != 0 || ld_last % 8 != 0) return set_error("lstm_pack_dh: H and row strides must be multiples of 8");
+  const long long n = (long long)T * D * ((S + 31) / 32) * (H / 8) * 32 + (long long)S * D * (H / 8);
+  lstm_pack_dh_kernel<<<grid_for(n, 256, 148 * 8), 256, 0, ST(stream)>>>(CBF(d_seq), ld_seq, nd_seq, CBF(d_last), ld_last,
+                                                                         d_last0, S, T, D, H, BF(dh_seq), BF(dh_last));
+  DVGR_CHECK_LAUNCH("lstm_pack_dh");
+  return 0;
+}
+
 extern "C" int dvgr_act_bwd(const void* dy, const void* y, void* out, long long n, int act, int accumulate, float p,
                             unsigned long long seed, unsigned int drop_stream, void* stream) {
   if (n % 8 != 0) return set_error("act_bwd: n=%lld must be a multiple of 8", n);
@@ -779,12 +1169,15 @@ struct ColsumGroup {
   int R[kMaxColsum], C[kMaxColsum], is_f32[kMaxColsum], vec_ok[kMaxColsum];
   int block_start[kMaxColsum + 1];      // prefix sums of col_blocks * chunks
   int chunks[kMaxColsum], rows_per_chunk[kMaxColsum];
+  int perm_H[kMaxColsum];               // > 0: input column 4*j + g lands at output index g*H + j (LSTM gate de-interleave)
+  float* out2[kMaxColsum];              // optional second accumulation target (b_ih and b_hh share one gradient)
   int n;
 };
 
 template <typename T>
 __device__ __forceinline__ void colsum_group_block(const T* __restrict__ in, long long ld, long long r0, long long r1, int C,
-                                                   int cblk, int vec_ok, float* __restrict__ out) {
+                                                   int cblk, int vec_ok, float* __restrict__ out, int perm_H,
+                                                   float* __restrict__ out2) {
   __shared__ float red[8][32][9];
   const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int c0 = (cblk * 32 + cg) * 8;
@@ -824,7 +1217,12 @@ __device__ __forceinline__ void colsum_group_block(const T* __restrict__ in, lon
       float s_ = 0.f;
 #pragma unroll
       for (int k = 0; k < 8; ++k) s_ += red[k][cg][q];
-      if (c0 + q < C) atomicAdd(out + c0 + q, s_);
+      if (c0 + q < C) {
+        const int c = c0 + q;
+        const int o = perm_H > 0 ? (c & 3) * perm_H + (c >> 2) : c;
+        atomicAdd(out + o, s_);
+        if (out2 != nullptr) atomicAdd(out2 + o, s_);
+      }
     }
   }
 }
@@ -838,9 +1236,11 @@ __global__ void __launch_bounds__(256) colsum_grouped_kernel(const __grid_consta
   const long long r0 = (long long)chunk * G.rows_per_chunk[pi];
   const long long r1 = min((long long)G.R[pi], r0 + G.rows_per_chunk[pi]);
   if (G.is_f32[pi])
-    colsum_group_block<float>(reinterpret_cast<const float*>(G.in[pi]), G.ld[pi], r0, r1, G.C[pi], cblk, G.vec_ok[pi], G.out[pi]);
+    colsum_group_block<float>(reinterpret_cast<const float*>(G.in[pi]), G.ld[pi], r0, r1, G.C[pi], cblk, G.vec_ok[pi], G.out[pi],
+                              G.perm_H[pi], G.out2[pi]);
   else
-    colsum_group_block<bf16>(reinterpret_cast<const bf16*>(G.in[pi]), G.ld[pi], r0, r1, G.C[pi], cblk, G.vec_ok[pi], G.out[pi]);
+    colsum_group_block<bf16>(reinterpret_cast<const bf16*>(G.in[pi]), G.ld[pi], r0, r1, G.C[pi], cblk, G.vec_ok[pi], G.out[pi],
+                             G.perm_H[pi], G.out2[pi]);
 }
 
 extern "C" int dvgr_colsum_grouped(const dvgr_colsum_problem* probs, int n, void* stream) {
@@ -858,6 +1258,8 @@ extern "C" int dvgr_colsum_grouped(const dvgr_colsum_problem* probs, int n, void
       const int esz = q.in_is_f32 ? 4 : 2;
       G.in[i] = q.in; G.out[i] = q.out; G.ld[i] = q.ld; G.R[i] = (int)q.R; G.C[i] = q.C; G.is_f32[i] = q.in_is_f32;
       G.vec_ok[i] = ((reinterpret_cast<uintptr_t>(q.in) & 15) == 0) && ((q.ld * esz) % 16 == 0);
+      G.perm_H[i] = q.perm_H; G.out2[i] = q.out2;
+      if (q.perm_H > 0 && q.C != 4 * q.perm_H) return set_error("colsum_grouped: problem %d: C=%d != 4*perm_H", base + i, q.C);
       long long chunks = (q.R + 255) / 256;          // >= 256 rows per chunk: few atomics per output element
       if (chunks > 64) chunks = 64;
       G.chunks[i] = (int)chunks;
@@ -876,7 +1278,7 @@ extern "C" int dvgr_colsum_grouped(const dvgr_colsum_problem* probs, int n, void
 // accumulation of the many tiny parameters of a DualVGR unit (per-head attention vectors and biases), which autograd would
 // otherwise perform with one elementwise launch per parameter (~170 launches of ~2 us per train step); copy: gathering those
 // parameters into the packed per-graph operands of the GAT kernels (instead of ~25 torch.cat launches per layer).
-constexpr int kMaxSegs = 64;
+constexpr int kMaxSegs = 128;
 struct SegList {
   float* dst[kMaxSegs];
   const float* src[kMaxSegs];

@@ -868,8 +868,37 @@ struct LstmSeqParams {
   int m_blocks, n_blocks;    // ceil(S / 128), 4H / BN
   const float* bias;         // [D][4H] fp32, gate-interleaved (b_ih + b_hh)
   int* flags;                // [D][m_blocks] zero at launch
+  int* counter;              // zero at launch: tiles are CLAIMED from it in index order (dynamic schedule, see below)
   int* error;                // sticky: set when a dependency poll gave up (never in a healthy run)
 };
+
+// Dynamic tile schedule. Tiles are numbered step-major and a tile depends only on tiles with a SMALLER index. Instead of a
+// static round-robin deal (which needs every CTA of the grid co-resident: a tile owned by a CTA that never got an SM would
+// block its dependents forever), the TMA-producer thread of each CTA claims the next tile index from a global counter and
+// publishes it to its MMA / epilogue warps through a small shared-memory ring. A claimed tile belongs to a CTA that is
+// running by construction, every CTA works through its claims in increasing order, and a CTA claims at most one tile ahead of
+// the one it is loading — so the smallest unfinished tile can always make progress, whatever else shares the GPU (a
+// concurrent NCCL kernel, a second LSTM launch on another stream, a partially resident grid).
+// Ring depth: the producer is at most STAGES tiles ahead of the MMA thread (every tile has >= 1 k-block), which is at most 2
+// tiles (the TMEM stages) ahead of the slowest epilogue warp: kTileRing = 8 >= 4 + 2 + 2 slots are never overwritten early.
+constexpr int kTileRing = 8;
+__device__ __forceinline__ int ring_tile(const int* ring, int slot) {
+  int v;
+  asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(ring + slot)) : "memory");
+  return v;
+}
+__device__ __forceinline__ void ring_publish(int* ring, uint64_t* bars, int it, int tile) {
+  asm volatile("st.shared.s32 [%0], %1;" ::"r"(smem_u32(ring + (it % kTileRing))), "r"(tile) : "memory");
+  mbar_arrive(&bars[it % kTileRing]);       // release: the consumers' try_wait (acquire) sees the slot
+}
+__device__ __forceinline__ int ring_consume(const int* ring, uint64_t* bars, int it) {
+  mbar_wait(&bars[it % kTileRing], static_cast<uint32_t>((it / kTileRing) & 1));
+  return ring_tile(ring, it % kTileRing);
+}
+__device__ __forceinline__ int claim_tile(int* counter, int num_tiles) {
+  const int t = atomicAdd(counter, 1);
+  return t < num_tiles ? t : -1;
+}
 
 __device__ __forceinline__ int ld_acquire_gpu(const int* ptr) {
   int v;
@@ -905,6 +934,9 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   uint64_t* tfull_bar = empty_bar + STAGES;   // [2]
   uint64_t* tempty_bar = tfull_bar + 2;       // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* tile_bar = tempty_bar + 3;                          // [kTileRing]
+  int* tile_ring = reinterpret_cast<int*>(tile_bar + kTileRing); // [kTileRing]
+  static_assert(STAGES + 4 <= kTileRing, "tile ring too shallow for this pipeline depth");
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -920,6 +952,7 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], kSeqEpiWarps); }
+    for (int i = 0; i < kTileRing; ++i) mbar_init(&tile_bar[i], 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
@@ -932,7 +965,12 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     // ===================================================== TMA producer
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    int next = claim_tile(q.counter, num_tiles);
+    for (int it = 0;; ++it) {
+      const int tile = next;
+      ring_publish(tile_ring, tile_bar, it, tile);
+      if (tile < 0) break;
+      next = claim_tile(q.counter, num_tiles);      // one claim ahead: the atomic's latency hides under this tile's loads
       const int s = tile / tiles_per_step;
       const int r0 = tile - s * tiles_per_step;
       const int d = r0 / tiles_per_dir;
@@ -967,7 +1005,9 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     uint32_t phase = 0;
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int it = 0;; ++it) {
+      const int tile = ring_consume(tile_ring, tile_bar, it);
+      if (tile < 0) break;
       const int s = tile / tiles_per_step;
       const int nkb = q.kb1 + (s > 0 ? q.kb2 : 0);
       mbar_wait(&tempty_bar[as], aphase ^ 1u);
@@ -994,7 +1034,9 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     const int c4 = (warp - 4) >> 2;          // this warp's 32-column chunks: c4, c4 + 4, ...
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int it = 0;; ++it) {
+      const int tile = ring_consume(tile_ring, tile_bar, it);
+      if (tile < 0) break;
       const int s = tile / tiles_per_step;
       const int r0 = tile - s * tiles_per_step;
       const int d = r0 / tiles_per_dir;
@@ -1078,6 +1120,9 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_consta
   uint64_t* tfull_bar = empty_bar + STAGES;   // [2]
   uint64_t* tempty_bar = tfull_bar + 2;       // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* tile_bar = tempty_bar + 3;                          // [kTileRing]
+  int* tile_ring = reinterpret_cast<int*>(tile_bar + kTileRing); // [kTileRing]
+  static_assert(STAGES + 4 <= kTileRing, "tile ring too shallow for this pipeline depth");
   uint8_t* out_stage = smem + STAGES * kBwdStageBytes + 256;      // [16 warps][32 rows][128 B], 16-byte pieces XOR-swizzled
 
   const int warp = threadIdx.x >> 5;
@@ -1092,6 +1137,7 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_consta
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], kBwdEpiWarps); }
+    for (int i = 0; i < kTileRing; ++i) mbar_init(&tile_bar[i], 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<2 * BN>(tmem_slot);
@@ -1104,7 +1150,12 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_consta
     // ===================================================== TMA producer
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    int next = claim_tile(q.counter, num_tiles);
+    for (int it = 0;; ++it) {
+      const int tile = next;
+      ring_publish(tile_ring, tile_bar, it, tile);
+      if (tile < 0) break;
+      next = claim_tile(q.counter, num_tiles);
       const int k1 = tile / tiles_per_step;              // k - 1
       const int r0 = tile - k1 * tiles_per_step;
       const int d = r0 / tiles_per_dir;
@@ -1135,7 +1186,8 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_consta
     uint32_t phase = 0;
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int it = 0;; ++it) {
+      if (ring_consume(tile_ring, tile_bar, it) < 0) break;
       mbar_wait(&tempty_bar[as], aphase ^ 1u);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
@@ -1161,7 +1213,9 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_consta
     const int chunk = e >> 2;                // 0..3 -> hidden units [chunk * 32, +32) of the tile
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int it = 0;; ++it) {
+      const int tile = ring_consume(tile_ring, tile_bar, it);
+      if (tile < 0) break;
       const int k1 = tile / tiles_per_step;
       const int r0 = tile - k1 * tiles_per_step;
       const int d = r0 / tiles_per_dir;
@@ -1571,7 +1625,8 @@ int lstm_seq_fwd_launch(const dvgr_operand& X, const dvgr_operand& Wih, const dv
   q.n_blocks = p.N / BN;
   q.bias = bias;
   q.flags = sync;
-  q.error = sync + (long long)p.batch * q.m_blocks;
+  q.counter = sync + (long long)p.batch * q.m_blocks;
+  q.error = q.counter + 1;
   auto kern = lstm_seq_fwd_kernel<BN>;
   const int smem_bytes = Cfg::SMEM_BYTES - Cfg::STAGING_BYTES;
   static int max_resident = 0;
@@ -1584,7 +1639,10 @@ int lstm_seq_fwd_launch(const dvgr_operand& X, const dvgr_operand& Wih, const dv
     max_resident = per_sm * num_sms();     // the dependency protocol needs every CTA of the grid co-resident
   }
   const long long tiles = (long long)q.m_blocks * q.n_blocks * p.batch * p.T;
-  const int grid = (int)std::min<long long>(tiles, std::min(max_resident, num_sms()));
+  // at most one step's tiles can run at the same time (each depends on the step before): more CTAs than that only take SMs
+  // away from whatever runs next to this launch (the question encoder next to the appearance encoder: 48 of 148 SMs)
+  const long long per_step = (long long)q.m_blocks * q.n_blocks * p.batch;
+  const int grid = (int)std::min<long long>(std::min(tiles, per_step), std::min(max_resident, num_sms()));
   if (grid <= 0) return 0;
   kern<<<grid, kSeqThreads, smem_bytes, stream>>>(tx, twih, th, twhh, p, q);
   cudaError_t e = cudaGetLastError();
@@ -1608,7 +1666,8 @@ int lstm_seq_bwd_launch(const dvgr_operand& G, const dvgr_operand& Whh, GemmPara
   q.n_blocks = (H + kBwdBN - 1) / kBwdBN;
   q.bias = nullptr;
   q.flags = sync;
-  q.error = sync + (long long)p.batch * q.m_blocks;
+  q.counter = sync + (long long)p.batch * q.m_blocks;
+  q.error = q.counter + 1;
   static int max_resident = 0;
   if (max_resident == 0) {
     cudaError_t e = cudaFuncSetAttribute(lstm_seq_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmemBytes);
@@ -1619,7 +1678,8 @@ int lstm_seq_bwd_launch(const dvgr_operand& G, const dvgr_operand& Whh, GemmPara
     max_resident = per_sm * num_sms();
   }
   const long long tiles = (long long)q.m_blocks * q.n_blocks * p.batch * (p.T - 1);
-  const int grid = (int)std::min<long long>(tiles, std::min(max_resident, num_sms()));
+  const long long per_step = (long long)q.m_blocks * q.n_blocks * p.batch;      // see lstm_seq_fwd_launch
+  const int grid = (int)std::min<long long>(std::min(tiles, per_step), std::min(max_resident, num_sms()));
   if (grid <= 0) return 0;
   lstm_seq_bwd_kernel<<<grid, kBwdThreads, kBwdSmemBytes, stream>>>(tg, tw, p, q);
   cudaError_t e = cudaGetLastError();

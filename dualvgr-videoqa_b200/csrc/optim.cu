@@ -64,9 +64,59 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 
+// End-of-step bookkeeping in one tiny launch: total = ce + sum of the auxiliary-loss partials (coef-scaled per-sample values
+// of common_loss / loss_dependence, train.py:148-154), and the step's health: if any LSTM dependency poll gave up (sticky words
+// of dvgr_lstm_seq_*), the reported loss is NaN — a replayed CUDA graph can then never train silently on stale state.
+struct FlagList {
+  const int* flag[16];
+  int n;
+};
+__global__ void finalize_loss_kernel(const float* __restrict__ ce, const float* __restrict__ parts, int rows,
+                                     const FlagList F, float* __restrict__ out) {
+  __shared__ float red[3][32];
+  float a[3] = {0.f, 0.f, 0.f};
+  for (int i = threadIdx.x; i < rows; i += blockDim.x) {
+    a[0] += parts[3 * i]; a[1] += parts[3 * i + 1]; a[2] += parts[3 * i + 2];
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    a[c] = warp_sum(a[c]);
+    if (lane == 0) red[c][warp] = a[c];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s[3] = {0.f, 0.f, 0.f};
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w)
+      for (int c = 0; c < 3; ++c) s[c] += red[c][w];
+    int bad = 0;
+    for (int i = 0; i < F.n; ++i) bad += (F.flag[i][0] != 0) ? 1 : 0;
+    const float total = ce[0] + s[0] + s[1] + s[2];
+    out[0] = bad ? __int_as_float(0x7fc00000) : total;
+    out[1] = s[0];
+    out[2] = s[1] + s[2];
+    out[3] = (float)bad;
+  }
+}
+
 }  // namespace dvgr
 
 using namespace dvgr;
+
+extern "C" int dvgr_finalize_loss(const float* ce, const float* parts, int rows, const int* const* flags, int n_flags,
+                                  float* out, void* stream) {
+  if (!ce || !out) return set_error("finalize_loss: null buffer");
+  if (n_flags < 0 || n_flags > 16) return set_error("finalize_loss: n_flags=%d out of [0,16]", n_flags);
+  FlagList F;
+  F.n = n_flags;
+  for (int i = 0; i < n_flags; ++i) {
+    if (!flags[i]) return set_error("finalize_loss: null flag %d", i);
+    F.flag[i] = flags[i];
+  }
+  finalize_loss_kernel<<<1, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(ce, parts, parts ? rows : 0, F, out);
+  DVGR_CHECK_LAUNCH("finalize_loss");
+  return 0;
+}
 
 extern "C" int dvgr_sumsq_blocks(void) { return 1024; }
 

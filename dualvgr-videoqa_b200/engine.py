@@ -3,21 +3,26 @@ work restated B200-first.
 
   * one process per GPU; parameters live in ONE flat fp32 buffer, gradients in another (views handed to autograd), so the
     gradient exchange is a single NCCL all-reduce over NVLink and the optimizer is two kernel launches
-  * loss = CE + alpha * mean_l common_loss + beta * mean_l (HSIC_app + HSIC_mot)  (train.py:146-154) from the fused
-    cross-entropy / pair-loss kernels (value and gradient in the same launch)
+  * loss = CE + alpha * mean_l common_loss + beta * mean_l (HSIC_app + HSIC_mot)  (train.py:146-154): the cross-entropy kernel
+    produces value and gradient in one launch; the auxiliary terms of every unit layer (values and all four gradients) are
+    computed inside the unit stack's autograd Function on a side stream, overlapped with the rest of the step
   * clip_grad_norm_(12) + Adam(lr)  (train.py:85,158-159) = dvgr_sumsq + dvgr_adam_step on the flat buffers
 
-Videos are independent, so ranks shard the batch and never exchange activations. Two cross-sample couplings remain and
-are handled as standard DDP does: BatchNorm uses per-rank batch statistics; CE / common_loss are means
-(gradient averaging reproduces the global-batch gradient), HSIC is a SUM over the batch, so its coefficient is multiplied
-by world_size before averaging."""
+Videos are independent, so ranks shard the batch and never exchange activations. Two cross-sample couplings remain
+(SURVEY.md §8e): BatchNorm1d in the classifier uses per-rank batch statistics by default (standard DDP) or global ones with
+sync_bn=True (two 2 x 768-float all-reduces per step); CE / common_loss are means (gradient averaging reproduces the
+global-batch gradient), HSIC is a SUM over the batch, so its coefficient is multiplied by world_size before averaging."""
+import os
 import weakref
 
 import torch
 import torch.distributed as dist
 
 from . import autograd as ag
+from . import fused_stack as fs
 from . import ops
+
+_LIVE_ENGINES = weakref.WeakSet()
 
 
 class _EarlyBucketHook:
@@ -37,7 +42,7 @@ class _EarlyBucketHook:
 
     def __call__(self, grad):
         self.pending -= 1
-        if self.pending == 0:
+        if self.pending == 0 and not self.engine.skip_allreduce:
             e = self.engine
             ops.flush_wgrads()       # the queued (deferred) weight gradients of the early bucket must land before it is reduced
             self.side.wait_stream(torch.cuda.current_stream())
@@ -49,11 +54,13 @@ class _EarlyBucketHook:
 
 class TrainEngine:
     def __init__(self, model, lr=1e-4, max_norm=12.0, alpha=1.0, beta=1e-8, betas=(0.9, 0.999), eps=1e-8,
-                 process_group=None):
+                 process_group=None, sync_bn=False):
         self.model = model
         self.lr, self.max_norm, self.alpha, self.beta, self.betas, self.eps = lr, max_norm, alpha, beta, betas, eps
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.rank = dist.get_rank(process_group) if self.world > 1 else 0
+        self.skip_allreduce = False      # measurement aid (bench.py: exposed all-reduce time = step with - step without)
         # flat layout: the groups the fused kernels see as one matrix (contiguous, in order) and everything else, split in
         # two contiguous buckets by WHEN the gradient is final: "late" = the three input encoders (their backward runs last:
         # LSTM recurrences + the big W_ih weight gradients, ~2 ms), "early" = everything downstream of them. With more than
@@ -74,17 +81,17 @@ class TrainEngine:
         self.params = late + early
         self._n_late = len(late)
         dev = self.params[0].device
-        sizes = [(p.numel() + 7) // 8 * 8 for p in self.params]           # 16-byte aligned slices (also in the bf16 shadow)
-        total = sum(sizes)
+        self.sizes = [(p.numel() + 7) // 8 * 8 for p in self.params]      # 16-byte aligned slices (also in the bf16 shadow)
+        total = sum(self.sizes)
         self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
         self.gflat = torch.zeros(total, dtype=torch.float32, device=dev)
         self.shadow = torch.zeros(total, dtype=torch.bfloat16, device=dev)   # bf16 GEMM operands, written by the Adam kernel
         self.m = torch.zeros(total, dtype=torch.float32, device=dev)
         self.v = torch.zeros(total, dtype=torch.float32, device=dev)
-        self.late_numel = sum(sizes[:self._n_late])
+        self.late_numel = sum(self.sizes[:self._n_late])
         off = 0
         with torch.no_grad():
-            for p, n in zip(self.params, sizes):
+            for p, n in zip(self.params, self.sizes):
                 sl = self.flat[off:off + p.numel()].view_as(p)
                 sl.copy_(p.data)
                 p.data = sl
@@ -92,61 +99,125 @@ class TrainEngine:
                 if p.dim() == 2:
                     ag.SHADOW[id(p)] = (weakref.ref(p), self.shadow[off:off + p.numel()].view_as(p))
                 off += n
-            self.shadow.copy_(self.flat)
         self.step_count = 0
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)     # device-side step counter (graph replay)
         self.seed_dev = torch.zeros(1, dtype=torch.int64, device=dev)     # device-side dropout seed offset
         self.graph = None
+        self.static = None
         self.numel = total
+        self.last_stats = None           # [4] f32 device tensor of the last step: total, common sum, dependence sum, #timeouts
+        self._step_flags = []
         if self.world > 1:      # replicas must start identical (the reference seeds every process the same, train.py:425-428)
             dist.broadcast(self.flat, src=0, group=self.pg)
-        ag.invalidate_weight_cache()
+        self.sync_shadow()      # AFTER the broadcast: the bf16 operands must be casts of the weights this rank trains on
+        # independent dropout masks per rank (standard DDP): the counter-based streams are keyed by (seed, site, element), so
+        # the rank goes into the seed; weights were identical before this point
+        ag.set_rank_seed(self.rank)
         ag.DIRECT_GRAD[0] = True      # weight-gradient GEMMs accumulate straight into the flat gradient buffer
-        import os
+        _LIVE_ENGINES.add(self)
         overlap_ok = os.environ.get("DVGR_ALLREDUCE_OVERLAP", "1") != "0"        # A/B knob: 0 = one all-reduce after backward
         self._overlap = _EarlyBucketHook(self) if (self.world > 1 and overlap_ok and 0 < self.late_numel < total) else None
         if hasattr(model, "_unit_inputs_grad_hook") or self._overlap is not None:
             model._unit_inputs_grad_hook = self._overlap
+        self.sync_bn = bool(sync_bn) and self.world > 1
+        ou = getattr(model, "output_unit", None)
+        if ou is not None:
+            ou.sync_bn_group = (self.pg if self.pg is not None else dist.group.WORLD) if self.sync_bn else None
+            ou.sync_bn_world = self.world if self.sync_bn else 1
 
     # ------------------------------------------------------------------------------------------------------------
-    def loss(self, outputs, answers):
-        """(total, ce, loss_com_sum, loss_dep_sum, n_correct) — train.py:146-154 and batch_accuracy (train.py:352-356)."""
-        logits, _, _, com_app, com_mot, aq, mq = outputs
-        n = len(aq)
-        B, N = aq[0].shape[0], aq[0].shape[1]
-        ce, correct = ag.CrossEntropyFn.apply(logits, answers)
-        total, com, dep = ce, None, None
-        c_com, c_dep = (self.alpha / max(n, 1)) / (B * N * N), self.beta * self.world / max(n, 1)
-        for i in range(n):
-            aux, vals = ag.AuxLossFn.apply(com_app[i], com_mot[i], aq[i], mq[i], c_com, c_dep, True)
-            total = total + aux            # coefficient exactly 1: AuxLossFn's unit_grad contract
-            c, d = vals[0], vals[1] + vals[2]
-            com = c if com is None else com + c
-            dep = d if dep is None else dep + d
-        if n > 0:       # un-scaled sums, as train.py accumulates them (logging only)
-            com, dep = com / (c_com * B * N * N), dep / c_dep if c_dep != 0 else dep
-        return total, ce, com, dep, correct
+    def sync_shadow(self):
+        """Re-casts the bf16 operand copy from the fp32 master weights. Call after ANY external write to the parameters
+        (load_state_dict, manual edits, a restore): the GEMMs read the shadow, not the fp32 values."""
+        with torch.no_grad():
+            self.shadow.copy_(self.flat)
+        ag.invalidate_weight_cache()
 
-    def train_step(self, app, mot, question, question_len, answers):
-        """One optimizer step on this rank's shard. Returns the (device) total loss of the shard."""
-        self.model.train()
+    def state_dict(self):
+        """Optimizer / engine state for checkpoints (the reference saves optimizer.state_dict(), train.py:359-367): Adam
+        moments per parameter NAME (views, compatible with torch.optim.Adam's exp_avg / exp_avg_sq), step, dropout counter."""
+        names = {id(p): n for n, p in self.model.named_parameters()}
+        st, off = {}, 0
+        for p, n in zip(self.params, self.sizes):
+            st[names[id(p)]] = {"exp_avg": self.m[off:off + p.numel()].view_as(p).clone(),
+                                "exp_avg_sq": self.v[off:off + p.numel()].view_as(p).clone()}
+            off += n
+        return {"state": st, "step": int(self.step_dev.item()), "seed_offset": int(self.seed_dev.item()),
+                "lr": self.lr, "betas": self.betas, "eps": self.eps, "max_norm": self.max_norm}
+
+    def load_state_dict(self, sd):
+        names = {id(p): n for n, p in self.model.named_parameters()}
+        off = 0
+        with torch.no_grad():
+            for p, n in zip(self.params, self.sizes):
+                ent = sd["state"][names[id(p)]]
+                self.m[off:off + p.numel()].view_as(p).copy_(ent["exp_avg"])
+                self.v[off:off + p.numel()].view_as(p).copy_(ent["exp_avg_sq"])
+                off += n
+            self.step_dev.fill_(int(sd["step"]))
+            self.seed_dev.fill_(int(sd.get("seed_offset", 0)))
+        self.step_count = int(sd["step"])
+        self.lr = sd.get("lr", self.lr)
+        self.sync_shadow()       # model.load_state_dict() normally precedes this call: pick the restored weights up
+
+    # ------------------------------------------------------------------------------------------------------------
+    def _loss_coefs(self, B, N, n_layers):
+        n = max(n_layers, 1)
+        return (self.alpha / n) / (B * N * N), self.beta * self.world / n
+
+    def forward_backward(self, app, mot, question, question_len, answers):
+        """Forward, losses, backward of this rank's shard: leaves the (unreduced) gradient in gflat and the step's statistics
+        in last_stats. Returns (total loss (device scalar), n_correct [B] int32)."""
+        model = self.model
+        model.train()
         self.gflat.zero_()
-        outputs = self.model(app, mot, question, question_len)
-        total, ce, com, dep, correct = self.loss(outputs, answers)
+        ag.begin_step_flags()
+        unit = model.visual_input_unit
+        B, N = app.shape[0], app.shape[1]
+        parts = None
+        if unit.layers > 0 and (self.alpha != 0 or self.beta != 0):
+            c_com, c_dep = self._loss_coefs(B, N, unit.layers)
+            parts = torch.empty((unit.layers, B, 3), dtype=torch.float32, device=app.device)
+            unit._aux = (c_com, c_dep, parts)
+        try:
+            outputs = model(app, mot, question, question_len)
+        finally:
+            unit._aux = None
+        self.last_logits = outputs[0].detach()
+        ce, correct = ag.CrossEntropyFn.apply(outputs[0], answers, True)
         ops.DEFER_WGRAD[0] = True          # weight / bias gradients of the nn.Linear layers: queued during backward ...
         try:
-            total.backward()
+            ce.backward()                  # the auxiliary terms' gradients are injected inside the unit stack's backward
         except BaseException:
             ops.clear_deferred()           # never leave half a step's gradients queued for the next one
             raise
         finally:
             ops.DEFER_WGRAD[0] = False
-        ops.flush_wgrads()                 # ... and launched as ONE grouped tcgen05 GEMM + ONE grouped column sum
+        fs.join_side_streams(app.device)   # question-encoder backward / auxiliary losses ran on side streams
+        ops.flush_wgrads()                 # ... and launched as ONE grouped tcgen05 GEMM + grouped column sums
+        self.last_stats = ops.finalize_loss(ce.detach(), parts, ag.step_flags())
+        return self.last_stats[0], correct
+
+    def loss_terms(self):
+        """(total, loss_com_sum, loss_dep_sum) of the last step as train.py:148-154 accumulates them (un-scaled sums over the
+        layers; host floats: this synchronises)."""
+        s = [float(x) for x in self.last_stats.tolist()]
+        unit = self.model.visual_input_unit
+        B, N = self._last_BN
+        c_com, c_dep = self._loss_coefs(B, N, unit.layers)
+        com = s[1] / (c_com * B * N * N) if c_com != 0 else 0.0
+        dep = s[2] / c_dep if c_dep != 0 else 0.0
+        return s[0], com, dep
+
+    def train_step(self, app, mot, question, question_len, answers):
+        """One optimizer step on this rank's shard. Returns the (device) total loss of the shard."""
+        self._last_BN = (app.shape[0], app.shape[1])
+        total, _ = self.forward_backward(app, mot, question, question_len, answers)
         self.optimizer_step()
-        return total.detach()
+        return total
 
     def optimizer_step(self):
-        if self.world > 1:
+        if self.world > 1 and not self.skip_allreduce:
             if self._overlap is not None and self._overlap.fired:
                 # the early bucket is already in flight on the side stream (launched from the backward pass); reduce the
                 # encoders' bucket here and join
@@ -164,9 +235,19 @@ class TrainEngine:
                       shadow=self.shadow)
         ag.invalidate_weight_cache()
 
+    def dependency_poll_timeouts(self):
+        """Number of LSTM dependency polls that gave up in the last step, max over ranks (0 in a healthy run; a non-zero
+        value also turned that step's loss into NaN). Synchronises."""
+        t = torch.zeros(1, device=self.flat.device) if self.last_stats is None else self.last_stats[3:4].clone()
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.pg)
+        return int(t.item())
+
     # ------------------------------------------------------------------------------------------------------------
     # whole-step CUDA graph: forward, losses, backward, all-reduce, clip + Adam, weight re-casts = ONE graph launch.
     # Everything that changes between steps lives on the device (inputs in static buffers, dropout seed offset, Adam step).
+    # NOTE: capture() runs `warmup` REAL optimizer steps on the given batch before recording (kernel attribute setup, NCCL
+    # channel setup and allocator warm-up must not happen during capture): the parameters move, as with any train step.
     def capture(self, app, mot, question, question_len, answers, warmup=3):
         from . import _lib
         self.static = {k: torch.empty_like(v) for k, v in
@@ -174,6 +255,7 @@ class TrainEngine:
         for k, v in dict(app=app, mot=mot, q=question, qlen=question_len, ans=answers).items():
             self.static[k].copy_(v)
         _lib.lib.dvgr_set_seed_offset(self.seed_dev.data_ptr())
+        self._seed_owner = True
 
         def body():
             self.seed_dev += 1
@@ -192,16 +274,27 @@ class TrainEngine:
         with torch.cuda.graph(self.graph):
             self.static_loss = body()
         self.launches_per_replay = _lib.launch_count() - n0    # library kernels recorded into the graph
+        self.step_count = int(self.step_dev.item())            # capture itself executed no step: resync with the device
         ag.invalidate_weight_cache()
         return self.graph
 
+    def release_static(self):
+        self.graph = None
+        self.static = None
+        self.static_loss = None
+
     def close(self):
-        """Detaches the engine's device-side dropout counter from the library (call before dropping the engine)."""
+        """Detaches the engine from the library / autograd layer (call before dropping the engine)."""
         from . import _lib
-        _lib.lib.dvgr_set_seed_offset(None)
+        if getattr(self, "_seed_owner", False):
+            _lib.lib.dvgr_set_seed_offset(None)
+            self._seed_owner = False
         self.graph = None
         for p in self.params:
             ag.SHADOW.pop(id(p), None)
+        _LIVE_ENGINES.discard(self)
+        if not len(_LIVE_ENGINES):
+            ag.DIRECT_GRAD[0] = False
 
     def __del__(self):
         try:
@@ -219,3 +312,55 @@ class TrainEngine:
         self.graph.replay()
         self.step_count += 1
         return self.static_loss
+
+    # ------------------------------------------------------------------------------------------------------------
+    def dp_parity_check(self, orc, cfg, samples_per_rank=16):
+        """Data-parallel correctness on hardware: every rank runs forward/backward on ITS shard of a seeded
+        global batch, the flat gradients are all-reduced and averaged; every rank also runs the WHOLE batch alone with the
+        single-process loss scaling; the two flat gradients must agree. Dropout off; the classifier's BatchNorm uses global
+        batch statistics in the sharded run (sync_bn, forced on for this check) so the two computations are the same function.
+        Also compares a parameter checksum across ranks. Returns a dict (rel-L2, checksum spread)."""
+        model, dev = self.model, self.flat.device
+        W, r = self.world, self.rank
+        Bg = samples_per_rank * W
+        app, mot, q, qlen, ans = orc.make_inputs(Bg, cfg["N"], cfg["L"], cfg["A"], cfg["V"], seed=77)
+        saved = []
+        for m in model.modules():
+            if isinstance(m, torch.nn.Dropout):
+                saved.append((m, "p", m.p)); m.p = 0.0
+            if hasattr(m, "dropout") and isinstance(getattr(m, "dropout"), float):
+                saved.append((m, "dropout", m.dropout)); m.dropout = 0.0
+        ou = model.output_unit
+        bn = ou.classifier[3]
+        bn_state = (bn.running_mean.clone(), bn.running_var.clone(), bn.num_batches_tracked.clone())
+        old = (self.world, ou.sync_bn_group, ou.sync_bn_world, self._overlap, model._unit_inputs_grad_hook if hasattr(model, "_unit_inputs_grad_hook") else None)
+        try:
+            model._unit_inputs_grad_hook = None
+            self._overlap = None
+            ou.sync_bn_group, ou.sync_bn_world = (self.pg if self.pg is not None else dist.group.WORLD), W
+            sl = slice(r * samples_per_rank, (r + 1) * samples_per_rank)
+            shard = [t[sl].to(dev) for t in (app, mot, q, qlen, ans)]
+            self._last_BN = (samples_per_rank, cfg["N"])
+            self.forward_backward(*shard)
+            dist.all_reduce(self.gflat, op=dist.ReduceOp.SUM, group=self.pg)
+            g_dp = (self.gflat / W).clone()
+            # single-process reference on the concatenated batch
+            ou.sync_bn_group, ou.sync_bn_world = None, 1
+            self.world = 1
+            full = [t.to(dev) for t in (app, mot, q, qlen, ans)]
+            self.forward_backward(*full)
+            g_one = self.gflat.clone()
+        finally:
+            self.world, ou.sync_bn_group, ou.sync_bn_world, self._overlap, hook = old
+            model._unit_inputs_grad_hook = hook
+            for m, name, val in saved:
+                setattr(m, name, val)
+            with torch.no_grad():
+                bn.running_mean.copy_(bn_state[0]); bn.running_var.copy_(bn_state[1]); bn.num_batches_tracked.copy_(bn_state[2])
+        rel = float((g_dp - g_one).norm() / g_one.norm().clamp_min(1e-30))
+        chk = self.flat.double().sum().reshape(1)
+        gathered = [torch.zeros_like(chk) for _ in range(W)]
+        dist.all_gather(gathered, chk, group=self.pg)
+        vals = [float(t) for t in gathered]
+        return {"grad_rel_l2": rel, "global_batch": Bg, "param_checksum_spread": max(vals) - min(vals),
+                "note": "dropout off, classifier BatchNorm on global statistics (sync) in the sharded run"}

@@ -45,7 +45,9 @@ class SimpleOutputUnitOpenEnded(nn.Module):
         use_batch_stats = self.training or not bn.track_running_stats
         if self.training and bn.track_running_stats:
             bn.num_batches_tracked += 1
+        grp = getattr(self, "sync_bn_group", None)          # set by engine.TrainEngine(sync_bn=True): global batch statistics
+        sync = (grp, getattr(self, "sync_bn_world", 1)) if (grp is not None and self.training) else None
         x = ag.BatchNormFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, use_batch_stats,
-                                 bn.momentum if bn.momentum is not None else 0.1, bn.eps)
+                                 bn.momentum if bn.momentum is not None else 0.1, bn.eps, sync)
         x = ag.dropout(x, c[4].p, self.training)
         return ag.linear(x, c[5].weight, c[5].bias, out_f32=True)

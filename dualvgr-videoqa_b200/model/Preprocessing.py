@@ -51,6 +51,25 @@ class InputUnitLinguisticDynamic(nn.Module):
         self.embedding_dropout = nn.Dropout(p=0.15)
         self.final_dropout = nn.Dropout(0.18)
 
+    def _lstm_params(self):
+        params = []
+        for m in (self.concatRNN.rnn, self.encoder):
+            params += [m.weight_ih_l0, m.weight_hh_l0, m.bias_ih_l0, m.bias_hh_l0,
+                       m.weight_ih_l0_reverse, m.weight_hh_l0_reverse, m.bias_ih_l0_reverse, m.bias_hh_l0_reverse]
+        return params
+
+    def fused(self, questions, qlen32):
+        """Whole input unit as ONE autograd Function (fused_stack.QuestionInputFn): embedding + dropout + tanh in one launch,
+        both BiLSTMs as one 4-direction recurrence. -> (question_embedding [B,D] bf16, words [B,L,Wp] bf16 zero-padded,
+        per-token states [B*L, D] bf16); the first and last are column slices of wider buffers (valid GEMM operands)."""
+        from dualvgr_videoqa_b200 import fused_stack as fs
+        if not (self.bidirectional and isinstance(self.encoder, nn.LSTM)):
+            raise NotImplementedError("the sm_100a question encoder is the bidirectional LSTM pair DualVGR builds")
+        p_emb = self.embedding_dropout.p if self.training else 0.0
+        dq, q, words = fs.QuestionInputFn.apply((float(p_emb),), questions, qlen32, self.encoder_embed.weight,
+                                                *self._lstm_params())
+        return ag.dropout(q, self.final_dropout.p, self.training), words, dq
+
     def forward(self, questions, question_len):
         """-> (question_embedding [B,D] bf16, words [B,L,W] fp32, per-token states [B,L,D] bf16, zero rows at padded
         positions). The embedding lookup / dropout / tanh are three tiny PyTorch ops; both BiLSTMs run as one fused
@@ -78,11 +97,12 @@ class VisualAppearanceEncoder(nn.Module):
         self.embedding_dropout = nn.Dropout(p=0.15)
         self.finalvisual_dropout = nn.Dropout(p=0.18)
 
-    def forward(self, appearance_clips):
-        """[B, N, F, Dv] fp32 -> [B, N, module_dim] bf16 (final forward / backward hidden states, concatenated)."""
+    def forward(self, appearance_clips, out=None):
+        """[B, N, F, Dv] fp32 -> [B, N, module_dim] bf16 (final forward / backward hidden states, concatenated).
+        out: optional preallocated [B*N, module_dim] bf16 buffer for the result."""
         e = self.encoder
         x = appearance_clips if appearance_clips.dtype == torch.bfloat16 else appearance_clips.float()   # bf16-stored features pass through
         return ag.AppearanceEncoderFn.apply(
             x, e.weight_ih_l0, e.weight_hh_l0, e.bias_ih_l0, e.bias_hh_l0,
             e.weight_ih_l0_reverse, e.weight_hh_l0_reverse, e.bias_ih_l0_reverse, e.bias_hh_l0_reverse,
-            self.embedding_dropout.p, self.finalvisual_dropout.p, self.training)
+            self.embedding_dropout.p, self.finalvisual_dropout.p, self.training, (out,) if out is not None else None)

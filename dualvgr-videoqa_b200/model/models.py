@@ -12,6 +12,7 @@ import torch
 import torch.nn as nn
 
 from dualvgr_videoqa_b200 import autograd as ag
+from dualvgr_videoqa_b200 import fused_stack as fs
 
 from .AnswerDecoder import ContextSelfAttn, SimpleOutputUnitOpenEnded
 from .Attention import AttentionSFGCN
@@ -66,25 +67,38 @@ class DualVGR(nn.Module):
         if not video_appearance_feat.is_cuda:
             raise RuntimeError("dualvgr_b200: DualVGR runs on sm_100a CUDA devices only; there is no CPU path")
         ag.begin_forward()
-        question_embedding, word_embedding, dynamic_q = self.linguistic_input_unit(question, question_len)
-        app = self.visual_appearance_input_unit(video_appearance_feat)
+        dev = video_appearance_feat.device
         B, N = video_motion_feat.shape[:2]
+        D = self.visual_motion_input_unit.out_features
+        qlen = question_len.to(torch.int32)
+        # question encoder on a (high-priority) side stream: two 20-step recurrences over 256 sequences keep ~1/3 of the SMs
+        # busy at most, so they run next to the appearance prologue / encoder instead of in front of them (the LSTM
+        # kernels claim their tiles dynamically: sharing the GPU cannot stall them). Autograd runs the backward of a node on
+        # the stream of its forward, so the question encoder's backward overlaps the appearance encoder's the same way.
+        cur = torch.cuda.current_stream()
+        side = fs.side_stream(dev, "question")
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            question_embedding, word_embedding, dynamic_q = self.linguistic_input_unit.fused(question, qlen)
+        # the two clip streams are carried as ONE stacked [2, B*N, D] tensor: both encoders write into its halves
+        x0 = torch.empty((2, B * N, D), dtype=BF16, device=dev)
+        app = self.visual_appearance_input_unit(video_appearance_feat, out=x0[0])
         mf = video_motion_feat if video_motion_feat.dtype == torch.bfloat16 else video_motion_feat.float()
         mot_in = ag.ops.prep_features(mf.contiguous().view(B * N, -1), 1, False, False)
-        mot = ag.linear(mot_in, self.visual_motion_input_unit.weight, self.visual_motion_input_unit.bias).view(B, N, -1)
-        words_u = word_embedding
+        mot = ag.linear(mot_in, self.visual_motion_input_unit.weight, self.visual_motion_input_unit.bias, out=x0[1]).view(B, N, D)
+        cur.wait_stream(side)
+        for t in (question_embedding, word_embedding, dynamic_q):
+            t.record_stream(cur)
         hook = getattr(self, "_unit_inputs_grad_hook", None)
         if hook is not None and torch.is_grad_enabled():
             # data-parallel engine: tell it when the gradients of everything DOWNSTREAM of the three encoders are final, so
-            # that their all-reduce overlaps the encoders' backward (engine.TrainEngine). The word embeddings also feed the
-            # question encoder, whose contribution arrives last: give the unit stack its own autograd node for them.
-            words_u = word_embedding.view_as(word_embedding)
-            hooked = [t for t in (app, mot, dynamic_q, words_u) if t.requires_grad]
+            # that their all-reduce overlaps the encoders' backward (engine.TrainEngine)
+            hooked = [t for t in (app, mot, dynamic_q, word_embedding) if t.requires_grad]
             hook.arm(len(hooked))
             for t in hooked:
                 t.register_hook(hook)
-        visual, aq_embed, mq_embed, com_app, com_motion, aq_fusion, mq_fusion = self.visual_input_unit(
-            app, mot, dynamic_q, words_u, question_len)
+        visual, aq_embed, mq_embed, com_app, com_motion, aq_fusion, mq_fusion = self.visual_input_unit.fused(
+            app, mot, dynamic_q, word_embedding, qlen)
         pooled = self.feature_aggregation(visual)
         out = self.output_unit(question_embedding, pooled)
         return out, aq_embed, mq_embed, com_app, com_motion, aq_fusion, mq_fusion
@@ -122,9 +136,28 @@ class DualVGRUnit_multiple(nn.Module):
         self.register_buffer("appearance_adj", adj.clone(), persistent=False)
         self.register_buffer("motion_adj", adj.clone(), persistent=False)
 
+    def fused(self, app, mot, dq2, words_p, qlen):
+        """The whole stack as ONE autograd Function (fused_stack.UnitStackFn): app / mot [B,N,D] bf16, dq2 [B*L, D] bf16
+        (row stride free), words_p [B,L,Wp] bf16 zero-padded, qlen int32. Same returns as forward()."""
+        U = self.layers
+        heads = self.acGCN[0].n_heads if U > 0 else 4
+        pdrop = self.acGCN[0].dropout if (U > 0 and self.training) else 0.0
+        params = [p for i in range(U) for p in fs.unit_layer_params(self, i)]
+        cfg = (U, heads, float(pdrop), self.word_dim, getattr(self, "_aux", None) if torch.is_grad_enabled() else None)
+        outs = fs.UnitStackFn.apply(cfg, app, mot, dq2, words_p, qlen, self.appearance_adj, *params)
+        app, mot, aq_embed, mq_embed = outs[:4]
+        f32 = outs[4:]
+        com_app_list = [f32[4 * i] for i in range(U)]
+        aq_fusion_list = [f32[4 * i + 1] for i in range(U)]
+        com_motion_list = [f32[4 * i + 2] for i in range(U)]
+        mq_fusion_list = [f32[4 * i + 3] for i in range(U)]
+        visual = self.visualfusion([app, mot])
+        return visual, aq_embed, mq_embed, com_app_list, com_motion_list, aq_fusion_list, mq_fusion_list
+
     def forward(self, appearance_video_feat, motion_video_feat, dynamic_question_embedding, word_embedding, question_len):
         """app / motion [B,N,D], dynamic_q [B,L,D], words [B,L,W], question_len [B] ->
-        (visual [B,N,D], aq_embed, mq_embed, com_app[U], com_motion[U], aq_fusion[U], mq_fusion[U])"""
+        (visual [B,N,D], aq_embed, mq_embed, com_app[U], com_motion[U], aq_fusion[U], mq_fusion[U])
+        Module-by-module path (one autograd Function per mirrored module); DualVGR.forward uses fused()."""
         B, N, D = appearance_video_feat.shape
         app = appearance_video_feat.to(BF16)
         mot = motion_video_feat.to(BF16)

@@ -152,10 +152,12 @@ def wgrad_enqueue(dy, x, out, rows=None, cols=None):
 _COLSUM_QUEUE = []
 
 
-def colsum_enqueue(x, out):
-    """out[C] (fp32) += column sums of x[R, C] (bf16 / fp32, last dim contiguous); x is kept alive until flush_wgrads()."""
+def colsum_enqueue(x, out, perm_H=0, out2=None):
+    """out[C] (fp32) += column sums of x[R, C] (bf16 / fp32, last dim contiguous); x is kept alive until flush_wgrads().
+    perm_H > 0: column 4j+g lands at out[g*perm_H + j] (LSTM gate de-interleave); out2: second target for the same sums."""
     assert x.dim() == 2 and x.stride(1) == 1 and out.dtype == F32 and out.is_contiguous() and out.numel() == x.shape[1]
-    _COLSUM_QUEUE.append((x, out))
+    assert out2 is None or (out2.dtype == F32 and out2.is_contiguous() and out2.numel() == out.numel())
+    _COLSUM_QUEUE.append((x, out, perm_H, out2))
 
 
 _SMALL_QUEUE = []
@@ -183,9 +185,10 @@ def flush_wgrads():
     if _COLSUM_QUEUE:
         m = len(_COLSUM_QUEUE)
         carr = (_lib.ColsumProblem * m)()
-        for i, (x, out) in enumerate(_COLSUM_QUEUE):
+        for i, (x, out, perm_H, out2) in enumerate(_COLSUM_QUEUE):
             carr[i].in_, carr[i].in_is_f32, carr[i].ld = x.data_ptr(), 1 if x.dtype == F32 else 0, x.stride(0)
             carr[i].R, carr[i].C, carr[i].out = x.shape[0], x.shape[1], out.data_ptr()
+            carr[i].perm_H, carr[i].out2 = perm_H, (out2.data_ptr() if out2 is not None else None)
         _lib.check(_lib.colsum_grouped(carr, m, _stream()), "dvgr_colsum_grouped")
         _COLSUM_QUEUE.clear()
     if not _WGRAD_QUEUE:
@@ -277,7 +280,7 @@ def lstm_block_c(c, ):
     return x.view(D, T1, RB, 32, UG, 2, 4).permute(0, 1, 2, 4, 5, 3, 6).contiguous()
 
 
-def lstm_seq_fwd(x, wih, whh, bias, K1=None, seq_len=None, want_seq=False):
+def lstm_seq_fwd(x, wih, whh, bias, K1=None, seq_len=None, want_seq=False, h_last=None):
     """Whole-sequence fused forward (ONE persistent launch): x [T,S,ld] bf16 time-major, wih [D*4H, ld'] bf16 and
     whh [D,4H,H] bf16 gate-interleaved, bias [D*4H] f32 (b_ih + b_hh, interleaved).
     Returns (gates_blk ACTIVATED [T,D,RB,H/8,4,32,8] bf16, h_hist [D,T+1,S,H] bf16, c_blk [D,T+1,RB,H/8,2,32,4] f32,
@@ -296,7 +299,9 @@ def lstm_seq_fwd(x, wih, whh, bias, K1=None, seq_len=None, want_seq=False):
     c_hist = torch.empty((D, T + 1, RB, UG, 2, 32, 4), dtype=F32, device=dev)
     h_hist[:, 0].zero_()
     c_hist[:, 0].zero_()
-    h_last = torch.empty((S, D * H), dtype=BF16, device=dev)
+    if h_last is None:
+        h_last = torch.empty((S, D * H), dtype=BF16, device=dev)
+    assert h_last.dtype == BF16 and tuple(h_last.shape) == (S, D * H) and h_last.is_contiguous()
     seq_out = torch.empty((S, T, D * H), dtype=BF16, device=dev) if want_seq else None
     sync = torch.zeros((int(_lib.lib.dvgr_lstm_seq_sync_words(S, D)),), dtype=torch.int32, device=dev)
     a = _lib.LstmSeqArgs()
@@ -316,7 +321,7 @@ def lstm_seq_fwd(x, wih, whh, bias, K1=None, seq_len=None, want_seq=False):
     return gates, h_hist, c_hist, h_last, seq_out, sync
 
 
-def lstm_bwd(gates, whh, h_hist, c_hist, dh_last, seq_len=None, dh_seq=None, whole_sequence=False):
+def lstm_bwd(gates, whh, h_hist, c_hist, dh_last, seq_len=None, dh_seq=None, whole_sequence=False, dh_seq_blocked=None):
     """Backward through the T steps.
     per-step path: `gates` [T,S,D*4H] (activated gates from lstm_fwd) is overwritten in place with the pre-activation gate
     gradients, which feed the W_ih / W_hh / bias wgrads; returns gates.
@@ -342,7 +347,10 @@ def lstm_bwd(gates, whh, h_hist, c_hist, dh_last, seq_len=None, dh_seq=None, who
         carry = (torch.zeros((D, RB, UG, 2, 32, 4), dtype=torch.float32, device=gates.device) if whole_sequence
                  else torch.zeros((D, S, H), dtype=torch.float32, device=gates.device))
         a.dh_carry = carry.data_ptr()
-    if dh_seq is not None:
+    if dh_seq_blocked is not None:      # already in the kernels' blocked layout (lstm_pack_dh)
+        assert whole_sequence and tuple(dh_seq_blocked.shape) == (T, D, RB, UG, 32, 8) and dh_seq_blocked.is_contiguous()
+        a.dh_seq, a.seq_out_ld = dh_seq_blocked.data_ptr(), D * H
+    elif dh_seq is not None:
         if whole_sequence:      # [S, T, D*H] -> blocked [T, D, RB, H/8, 32, 8]: one 512-byte warp access per (row block, unit group)
             assert tuple(dh_seq.shape) == (S, T, D * H) and dh_seq.dtype == BF16
             pad = torch.zeros((RB * 32, T, D * H), dtype=BF16, device=gates.device)
@@ -472,7 +480,8 @@ def qattn_fwd(y, wf, cf, qlen, words, W, ld_qc):
     return qc, alpha, nrm, prob, ssum
 
 
-def qattn_bwd(dqc, y, wf, qlen, words, W, alpha, nrm, prob, ssum, dwords=None):
+def qattn_bwd(dqc, y, wf, qlen, words, W, alpha, nrm, prob, ssum, dwords=None, raw=False):
+    """raw=True: returns the per-sample partials (dwf_part [B, D], dcf_part [B, 1]) instead of their column sums."""
     B, L, D = y.shape
     dy = torch.empty_like(y)
     acc = dwords is not None
@@ -483,6 +492,8 @@ def qattn_bwd(dqc, y, wf, qlen, words, W, alpha, nrm, prob, ssum, dwords=None):
     _lib.check(_lib.qattn_bwd(_ptr(dqc), dqc.stride(0), _ptr(y), _ptr(wf), _ptr(qlen), _ptr(words), words.stride(1), B, L,
                               D, W, _ptr(alpha), _ptr(nrm), _ptr(prob), _ptr(ssum), _ptr(dy), _ptr(dwords),
                               1 if acc else 0, _ptr(dwf_part), _ptr(dcf_part), _stream()), "dvgr_qattn_bwd")
+    if raw:
+        return dy, dwords, dwf_part, dcf_part
     return dy, dwords, colsum(dwf_part), colsum(dcf_part)
 
 
@@ -537,7 +548,7 @@ def gat_attn_fwd(whs, gates, avecs, adj, B, N, heads=4, slope=0.01, p_att=0.0, p
 
 
 def gat_attn_bwd(whs, gates, avecs, outs, douts, adj, B, N, heads=4, slope=0.01, p_att=0.0, p_out=0.0, seed=0,
-                 streams=None, douts32=None, dwhs=None):
+                 streams=None, douts32=None, dwhs=None, raw=False):
     D = whs[0].shape[-1]
     G = len(whs)
     Dh = D // heads
@@ -555,6 +566,8 @@ def gat_attn_bwd(whs, gates, avecs, outs, douts, adj, B, N, heads=4, slope=0.01,
         if douts32 is not None and douts32[i] is not None:
             g.dout_f32 = douts32[i].data_ptr()
     _lib.check(_lib.gat_attn_bwd(ctypes.byref(a), _stream()), "dvgr_gat_attn_bwd")
+    if raw:                                             # per-video partials [G, B, heads * (2 Dh + 1)]: the caller reduces them
+        return dwhs, dgates, dav_all
     dav = colsum_batched(dav_all)                       # per-video partial sums -> [G, heads * (2 Dh + 1)] in one launch pair
     davecs = [dav[i].view(heads, 2 * Dh + 1) for i in range(G)]
     return dwhs, dgates, davecs
@@ -614,34 +627,48 @@ def readout_bwd(dpooled, v, u, w, alpha):
     return dv, du, colsum(dw_part), colsum(dc_part)
 
 
-def bn_fwd(x, gamma, beta, run_mean, run_var, training, momentum=0.1, eps=1e-5):
+def bn_stats(x):
+    """[2, D] f32: per-column (sum, sum of squares) of x [B, D] — the operand of the SyncBN all-reduce."""
+    B, D = x.shape
+    out = _empty((2, D), F32, x)
+    _lib.check(_lib.bn_stats(_ptr(x), 1 if x.dtype == F32 else 0, B, D, _ptr(out), _stream()), "dvgr_bn_stats")
+    return out
+
+
+def bn_fwd(x, gamma, beta, run_mean, run_var, training, momentum=0.1, eps=1e-5, ext_stats=None, Btot=0):
+    """ext_stats [2, D] = all-reduced bn_stats over a global batch of Btot rows (synchronised BatchNorm)."""
     B, D = x.shape
     y = _empty((B, D), BF16, x)
     mean, rstd = _empty((D,), F32, x), _empty((D,), F32, x)
-    _lib.check(_lib.bn_fwd(_ptr(x), 1 if x.dtype == F32 else 0, B, D, _ptr(gamma), _ptr(beta), _ptr(run_mean), _ptr(run_var), 1 if training else 0,
-                           momentum, eps, _ptr(y), _ptr(mean), _ptr(rstd), _stream()), "dvgr_bn_fwd")
+    _lib.check(_lib.bn_fwd_ex(_ptr(x), 1 if x.dtype == F32 else 0, B, D, _ptr(gamma), _ptr(beta), _ptr(run_mean), _ptr(run_var),
+                              1 if training else 0, momentum, eps, _ptr(y), _ptr(mean), _ptr(rstd), _ptr(ext_stats),
+                              Btot if ext_stats is not None else B, _stream()), "dvgr_bn_fwd")
     return y, mean, rstd
 
 
-def bn_bwd(dy, x, gamma, mean, rstd, training):
+def bn_bwd(dy, x, gamma, mean, rstd, training, ext_sums=None, Btot=0, stats_only=False):
+    """stats_only: returns (None, local sum dy*xhat, local sum dy) without dx; ext_sums [2, D] = (sum dy, sum dy*xhat) over the
+    global batch of Btot rows: dx of the synchronised BatchNorm."""
     B, D = x.shape
-    dx = torch.empty_like(x)
+    dx = None if stats_only else torch.empty_like(x)
     dgamma, dbeta = _empty((D,), F32, x), _empty((D,), F32, x)
-    _lib.check(_lib.bn_bwd(_ptr(dy), _ptr(x), 1 if x.dtype == F32 else 0, B, D, _ptr(gamma), _ptr(mean), _ptr(rstd), 1 if training else 0, _ptr(dx),
-                           _ptr(dgamma), _ptr(dbeta), _stream()), "dvgr_bn_bwd")
+    _lib.check(_lib.bn_bwd_ex(_ptr(dy), _ptr(x), 1 if x.dtype == F32 else 0, B, D, _ptr(gamma), _ptr(mean), _ptr(rstd),
+                              1 if training else 0, _ptr(dx), _ptr(dgamma), _ptr(dbeta), _ptr(ext_sums),
+                              Btot if ext_sums is not None else B, 1 if stats_only else 0, _stream()), "dvgr_bn_bwd")
     return dx, dgamma, dbeta
 
 
-def cross_entropy(logits, answers, scale=1.0, want_grad=True):
-    """Mean CE over the batch. Returns (loss scalar tensor, dlogits [B, A8] bf16 (A padded to 8), correct [B] int32)."""
+def cross_entropy(logits, answers, scale=1.0, want_grad=True, grad_f32=False):
+    """Mean CE over the batch. Returns (loss scalar tensor, dlogits, correct [B] int32); dlogits is [B, A8] bf16 (A padded to
+    8: a GEMM operand) or, with grad_f32, [B, A] fp32 (the gradient of the fp32 logits as autograd passes it on)."""
     B, A = logits.shape
     assert logits.dtype == F32 and logits.is_contiguous() and answers.dtype == torch.int64
-    A8 = (A + 7) // 8 * 8
+    A8 = A if grad_f32 else (A + 7) // 8 * 8
     part = _empty((B, 1), F32, logits)
-    dlog = _empty((B, A8), BF16, logits) if want_grad else None
+    dlog = _empty((B, A8), F32 if grad_f32 else BF16, logits) if want_grad else None
     correct = torch.empty((B,), dtype=torch.int32, device=logits.device)
-    _lib.check(_lib.cross_entropy(_ptr(logits), _ptr(answers), B, A, float(scale), _ptr(part), _ptr(dlog), A8,
-                                  _ptr(correct), _stream()), "dvgr_cross_entropy")
+    _lib.check(_lib.cross_entropy_ex(_ptr(logits), _ptr(answers), B, A, float(scale), _ptr(part), _ptr(dlog),
+                                     1 if grad_f32 else 0, A8, _ptr(correct), _stream()), "dvgr_cross_entropy")
     return colsum(part)[0], dlog, correct
 
 
@@ -678,6 +705,23 @@ def aux_loss_unit(ca, cm, aq, mq, coef_com, coef_dep, want_grad=True):
     return colsum(part), (grads if want_grad else None)
 
 
+def aux_loss_workspace(B, N, D, like):
+    return _empty((int(_lib.lib.dvgr_aux_loss_workspace(B, N, D)),), F32, like)
+
+
+def aux_loss_unit_into(ca, cm, aq, mq, coef_com, coef_dep, g_ca, g_cm, g_aq, g_mq, part, ws):
+    """aux_loss_unit with caller-owned outputs: gradients g_* (like the inputs), per-sample partial values part [B, 3]
+    (column sums = the three coef-scaled terms), workspace ws (aux_loss_workspace). Launches on the CURRENT stream, which may
+    be a side stream: nothing is allocated here."""
+    B, N, D = ca.shape
+    for t in (ca, cm, aq, mq, g_ca, g_cm, g_aq, g_mq):
+        assert t.dtype == F32 and t.is_contiguous() and tuple(t.shape) == (B, N, D)
+    assert part.dtype == F32 and part.is_contiguous() and part.numel() == 3 * B
+    _lib.check(_lib.aux_loss_unit(_ptr(ca), _ptr(cm), _ptr(aq), _ptr(mq), float(coef_com), float(coef_dep), B, N, D,
+                                  _ptr(g_ca), _ptr(g_cm), _ptr(g_aq), _ptr(g_mq), _ptr(part), _ptr(ws), _stream()),
+               "dvgr_aux_loss_unit")
+
+
 def pair_loss(x, y, mode, coef, dx=None, dy=None, want_grad=True):
     """mode 0: coef * sum (G_x - G_y)^2 ; mode 1: coef * HSIC. x, y fp32 [B, N, D]. dx / dy given => accumulated into.
     Returns (loss scalar tensor, dx, dy)."""
@@ -702,3 +746,140 @@ def adam_step(p, g, m, v, lr, step, beta1=0.9, beta2=0.999, eps=1e-8, max_norm=0
               step_dev=None, shadow=None):
     _lib.check(_lib.adam_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), lr, beta1, beta2, eps, step, max_norm,
                               _ptr(norm_sq), grad_scale, _ptr(step_dev), _ptr(shadow), _stream()), "dvgr_adam_step")
+
+
+# ---------------------------------------------------------------------------------------- multi-stream / packing helpers
+def _parr(ts):
+    arr = (ctypes.c_void_p * len(ts))()
+    for i, t in enumerate(ts):
+        arr[i] = t.data_ptr() if t is not None else None
+    return arr
+
+
+def _uarr(vals):
+    arr = (ctypes.c_uint * len(vals))()
+    for i, v in enumerate(vals):
+        arr[i] = int(v)
+    return arr
+
+
+def dropout_multi(ins, outs, streams, p, seed):
+    """outs[i] = ins[i] * mask(seed, streams[i]) for up to 4 bf16 tensors of equal size in ONE launch."""
+    n = ins[0].numel()
+    for a, b in zip(ins, outs):
+        assert a.dtype == BF16 and b.dtype == BF16 and a.is_contiguous() and b.is_contiguous() and a.numel() == n == b.numel()
+    _lib.check(_lib.dropout_multi(_parr(ins), _parr(outs), _uarr(streams), len(ins), n, float(p), int(seed), _stream()),
+               "dvgr_dropout_multi")
+    return outs
+
+
+def gat_input_bwd(dxts, streams, per_stream, bases, outs, p, seed):
+    """outs[s] = bases[s] + sum_j mask(streams[s*per_stream+j]) * dxts[s*per_stream+j] (bf16, one launch for all streams)."""
+    n = outs[0].numel()
+    for t in list(dxts) + list(outs) + [b for b in bases if b is not None]:
+        assert t.dtype == BF16 and t.is_contiguous() and t.numel() == n
+    _lib.check(_lib.gat_input_bwd(_parr(dxts), _uarr(streams), len(outs), per_stream, _parr(bases), _parr(outs), n, float(p),
+                                  int(seed), _stream()), "dvgr_gat_input_bwd")
+    return outs
+
+
+def embed_fwd(tokens, table, Wp, p=0.0, seed=0, stream_id=0):
+    """words [B, L, Wp] bf16 and time-major x [L, B, Wp] bf16 = tanh(dropout(table[tokens])), zero-padded to Wp columns."""
+    _check_cuda(tokens, table)
+    B, L = tokens.shape
+    V, W = table.shape
+    assert tokens.dtype == torch.int64 and tokens.is_contiguous() and table.dtype == F32 and table.is_contiguous()
+    words = torch.empty((B, L, Wp), dtype=BF16, device=table.device)
+    x_tm = torch.empty((L, B, Wp), dtype=BF16, device=table.device)
+    _lib.check(_lib.embed_fwd(_ptr(tokens), _ptr(table), B, L, W, Wp, _ptr(words), _ptr(x_tm), float(p), int(seed),
+                              int(stream_id), _stream()), "dvgr_embed_fwd")
+    return words, x_tm
+
+
+def embed_bwd(tokens, words, d_words, d_x_tm, W, dtable, p=0.0, seed=0, stream_id=0):
+    """dtable[V, W] (fp32, accumulated with atomics) += (d_words + d_x_tm^T) * tanh'(words) * mask."""
+    B, L, Wp = words.shape
+    assert dtable.dtype == F32 and dtable.is_contiguous() and dtable.shape[1] == W
+    for t in (d_words, d_x_tm):
+        assert t is None or (t.dtype == BF16 and t.is_contiguous() and t.numel() == words.numel())
+    _lib.check(_lib.embed_bwd(_ptr(tokens), _ptr(words), _ptr(d_words), _ptr(d_x_tm), B, L, W, Wp, _ptr(dtable), float(p),
+                              int(seed), int(stream_id), _stream()), "dvgr_embed_bwd")
+    return dtable
+
+
+def view_attn_fwd_multi(hidden, z, x, w2, want_embed=True):
+    """hidden, z: [S, 2, M, D] bf16; x [S, M, D] bf16; w2 [S, D] f32 -> (xnew [S,M,D], embed [S,M,D] | None, beta [S,M,2])."""
+    S, _, M, D = z.shape
+    assert hidden.is_contiguous() and z.is_contiguous() and x.is_contiguous() and w2.is_contiguous() and w2.dtype == F32
+    xnew = torch.empty_like(x)
+    embed = torch.empty_like(x) if want_embed else None
+    beta = _empty((S, M, 2), F32, x)
+    _lib.check(_lib.view_attn_fwd_multi(_ptr(hidden), _ptr(z), _ptr(x), _ptr(w2), M, D, S, _ptr(xnew), _ptr(embed), _ptr(beta),
+                                        _stream()), "dvgr_view_attn_fwd_multi")
+    return xnew, embed, beta
+
+
+def view_attn_bwd_multi(dxnew, dembed, hidden, z, w2, beta):
+    """-> dz [S,2,M,D], dhid [S,2,M,D] (tanh' applied), dw2 partials [S, blocks, D]."""
+    S, _, M, D = z.shape
+    assert dxnew.is_contiguous() and (dembed is None or dembed.is_contiguous())
+    dz, dhid = torch.empty_like(z), torch.empty_like(hidden)
+    blocks = int(_lib.lib.dvgr_view_attn_bwd_blocks(M))
+    part = _empty((S, blocks, D), F32, z)
+    _lib.check(_lib.view_attn_bwd_multi(_ptr(dxnew), _ptr(dembed), _ptr(hidden), _ptr(z), _ptr(w2), _ptr(beta), M, D, S,
+                                        _ptr(dz), _ptr(dhid), _ptr(part), _stream()), "dvgr_view_attn_bwd_multi")
+    return dz, dhid, part
+
+
+def cast_rows_grouped(params, out, out_cols=None, lstm_H=0):
+    """Row-concatenated bf16 copy of several fp32 matrices (equal column count) in ONE launch; see cast_rows."""
+    C = params[0].shape[1]
+    oc = out_cols or C
+    n = len(params)
+    assert n <= 8 and out.dtype == BF16 and out.stride(1) == 1 and out.shape[1] >= oc
+    ins, outs, r = [], [], 0
+    lds, rows, cols = (ctypes.c_longlong * n)(), (ctypes.c_int * n)(), (ctypes.c_int * n)()
+    for i, p in enumerate(params):
+        assert p.dtype == F32 and p.dim() == 2 and p.stride(1) == 1 and p.shape[1] == C
+        ins.append(p)
+        outs.append(out[r:r + p.shape[0]])
+        lds[i], rows[i], cols[i] = p.stride(0), p.shape[0], C
+        r += p.shape[0]
+    _lib.check(_lib.cast_rows_grouped(_parr(ins), lds, _parr(outs), rows, cols, n, out.stride(0), oc, lstm_H, _stream()),
+               "dvgr_cast_rows_grouped")
+    return out
+
+
+def lstm_pack_bias(b_ih, b_hh, H):
+    """[D*4H] f32 gate-interleaved b_ih + b_hh of D directions (lists of [4H] tensors) in one launch."""
+    D = len(b_ih)
+    out = _empty((D * 4 * H,), F32, b_ih[0])
+    _lib.check(_lib.lstm_pack_bias(_parr(b_ih), _parr(b_hh), D, H, _ptr(out), _stream()), "dvgr_lstm_pack_bias")
+    return out
+
+
+def lstm_pack_dh(d_seq, nd_seq, d_last, d_last0, S, T, D, H):
+    """(dh_seq blocked [T,D,RB,H/8,32,8], dh_last [S, D*H]) from the strided gradients of an encoder's outputs."""
+    like = d_seq if d_seq is not None else d_last
+    RB, UG = (S + 31) // 32, H // 8
+    dh_seq = _empty((T, D, RB, UG, 32, 8), BF16, like)
+    dh_last = _empty((S, D * H), BF16, like)
+    ld_seq = d_seq.stride(-2) if d_seq is not None else 8
+    ld_last = d_last.stride(0) if d_last is not None else 8
+    if d_seq is not None:
+        assert d_seq.dtype == BF16 and d_seq.stride(-1) == 1 and d_seq.dim() == 3 and d_seq.stride(0) == T * ld_seq
+    if d_last is not None:
+        assert d_last.dtype == BF16 and d_last.stride(-1) == 1
+    _lib.check(_lib.lstm_pack_dh(_ptr(d_seq), ld_seq, nd_seq, _ptr(d_last), ld_last, d_last0, S, T, D, H, _ptr(dh_seq),
+                                 _ptr(dh_last), _stream()), "dvgr_lstm_pack_dh")
+    return dh_seq, dh_last
+
+
+def finalize_loss(ce, parts, flags):
+    """[4] f32 = (total = ce + sum(parts), common sum, dependence sum, #set flags); total is NaN when a flag is set.
+    ce: 1-element f32 tensor; parts: [..., 3] f32 contiguous or None; flags: list of 1-element int32 tensors (<= 16)."""
+    out = _empty((4,), F32, ce)
+    rows = parts.numel() // 3 if parts is not None else 0
+    _lib.check(_lib.finalize_loss(_ptr(ce), _ptr(parts), rows, _parr(flags), len(flags), _ptr(out), _stream()),
+               "dvgr_finalize_loss")
+    return out

@@ -137,7 +137,9 @@ int dvgr_lstm_step_bwd(const dvgr_lstm_args* args, void* stream);
  *   x    [T][S][x_ld] bf16 time-major input (K1 valid columns, K1 % 8 == 0)
  *   wih  [D*4H][wih_ld] bf16, rows gate-interleaved like whh (dvgr_cast_rows with lstm_H)
  *   bias [D*4H] f32 = b_ih + b_hh, gate-interleaved
- *   sync [dvgr_lstm_seq_sync_words(S, D)] int32, ZERO on entry; the last word is a sticky error flag (stays 0 unless a
+ *   sync [dvgr_lstm_seq_sync_words(S, D)] int32, ZERO on entry: per-(direction, block) completion counters, the counter
+ *        the CTAs claim their tiles from (dynamic schedule: no CTA ever waits on a tile that a non-resident CTA owns, so the
+ *        launch is safe next to concurrent kernels on other streams), and LAST a sticky error flag (stays 0 unless a
  *        dependency poll timed out, which only a protocol violation can cause)
  * BLOCKED LAYOUT. The tensors that only the cell epilogues of the two whole-sequence calls touch are stored as
  * [piece][row] warp tiles (32 sequences x 8 hidden units; RB = ceil(S / 32) row blocks), so that every warp access is 512
@@ -245,6 +247,14 @@ int dvgr_gate_bwd(const void* x0, const void* x1, const void* query, long long l
 int dvgr_view_attn_fwd(const void* hidden, const void* z, const void* x, const float* w2, long long M, int D, void* xnew,
                        void* embed, float* beta, void* stream);
 int dvgr_view_attn_bwd_blocks(long long M);
+/* Both input streams (appearance, motion) of a unit in one launch: every operand of dvgr_view_attn_fwd / _bwd gains a leading
+ * [n_streams] dimension (hidden, z, dz, dhid: [S][2][M][D]; x, xnew, embed, dxnew, dembed: [S][M][D]; w2 [S][D]; beta [S][M][2];
+ * dw2_part [S][blocks][D]). */
+int dvgr_view_attn_fwd_multi(const void* hidden, const void* z, const void* x, const float* w2, long long M, int D,
+                             int n_streams, void* xnew, void* embed, float* beta, void* stream);
+int dvgr_view_attn_bwd_multi(const void* dxnew, const void* dembed_ext, const void* hidden, const void* z, const float* w2,
+                             const float* beta, long long M, int D, int n_streams, void* dz, void* dhid, float* dw2_part,
+                             void* stream);
 int dvgr_view_attn_bwd(const void* dxnew, const void* dembed_ext, const void* hidden, const void* z, const float* w2,
                        const float* beta, long long M, int D, void* dz, void* dhid, float* dw2_part, void* stream);
 
@@ -267,11 +277,26 @@ int dvgr_bn_fwd(const void* x, int x_is_f32, int B, int D, const float* gamma, c
                 void* stream);
 int dvgr_bn_bwd(const void* dy, const void* x, int x_is_f32, int B, int D, const float* gamma, const float* mean,
                 const float* rstd, int training, void* dx, float* dgamma, float* dbeta, void* stream);
+/* Synchronised BatchNorm over a data-parallel group (the classifier's nn.BatchNorm1d sees the GLOBAL batch, as the reference
+ * does on one GPU): dvgr_bn_stats writes the local per-column (sum, sum of squares) [2][D]; the caller all-reduces them and
+ * passes them as ext_stats with the global row count Btot. Backward: a first call with stats_only = 1 writes the LOCAL
+ * (sum dy -> dbeta, sum dy*xhat -> dgamma) and stops; the caller all-reduces [dbeta | dgamma] and passes them as ext_sums
+ * [2][D] to a second call (dgamma / dbeta may then be null). ext_* == null reproduces dvgr_bn_fwd / dvgr_bn_bwd. */
+int dvgr_bn_stats(const void* x, int x_is_f32, int B, int D, float* out, void* stream);
+int dvgr_bn_fwd_ex(const void* x, int x_is_f32, int B, int D, const float* gamma, const float* beta, float* run_mean,
+                   float* run_var, int training, float momentum, float eps, void* y, float* mean_out, float* rstd_out,
+                   const float* ext_stats, int Btot, void* stream);
+int dvgr_bn_bwd_ex(const void* dy, const void* x, int x_is_f32, int B, int D, const float* gamma, const float* mean,
+                   const float* rstd, int training, void* dx, float* dgamma, float* dbeta, const float* ext_sums, int Btot,
+                   int stats_only, void* stream);
 
 /* nn.CrossEntropyLoss (train.py:121,146) value + gradient: loss_part[b] (sum = mean CE), dlogits [B][ld_d] bf16 =
  * (softmax - onehot) * scale / B with zeroed padding columns, correct[b] = argmax == answer (train.py:352-356). */
 int dvgr_cross_entropy(const float* logits, const long long* answers, int B, int A, float scale, float* loss_part,
                        void* dlogits, long long ld_d, int* correct, void* stream);
+/* Same with the gradient written as fp32 when grad_is_f32 (the dtype of the logits: what autograd hands to their producer). */
+int dvgr_cross_entropy_ex(const float* logits, const long long* answers, int B, int A, float scale, float* loss_part,
+                          void* dlogits, int grad_is_f32, long long ld_d, int* correct, void* stream);
 
 /* Auxiliary losses (utils.py:10-31), value and gradient fused; up to 4 (x, y) pairs per call (one DualVGR unit needs 3:
  * common(com_app, com_mot), HSIC(aq, com_app), HSIC(mq, com_mot) — train.py:148-154). x, y, dx, dy are [B][N][D] f32.
@@ -316,11 +341,39 @@ int dvgr_prep_features_ex(const void* in, int in_is_bf16, void* out, long long S
                           int time_major, float p, unsigned long long seed, unsigned int drop_stream, void* stream);
 int dvgr_cast_rows(const float* in, long long ld_in, void* out, long long ld_out, int rows, int cols, int out_cols,
                    int lstm_H, void* stream);
+/* n (<= 8) dvgr_cast_rows problems sharing ld_out / out_cols / lstm_H in one launch: the bf16 (gate-interleaved) copies of
+ * all W_ih or W_hh matrices of an encoder written into one row-concatenated operand. HOST arrays. */
+int dvgr_cast_rows_grouped(const float* const* in, const long long* ld_in, void* const* out, const int* rows, const int* cols,
+                           int n, long long ld_out, int out_cols, int lstm_H, void* stream);
+/* out[d][4j + g] = b_ih[d][g*H + j] + b_hh[d][g*H + j]: the gate-interleaved bias operand of dvgr_lstm_seq_fwd for all
+ * directions (nn.LSTM keeps two bias vectors per direction, model/Preprocessing.py:97-101,202). HOST pointer arrays. */
+int dvgr_lstm_pack_bias(const float* const* b_ih, const float* const* b_hh, int ndir, int H, float* out, void* stream);
+/* Packs the gradients arriving at an LSTM encoder for dvgr_lstm_seq_bwd: d_seq [S][T][ld_seq] bf16 (per-step outputs of
+ * directions 0..nd_seq-1, may be null) -> dh_seq blocked [T][D][RB][H/8][32][8]; d_last [S][ld_last] bf16 (final states of
+ * directions d_last0..D-1, may be null) -> dh_last [S][D*H]; everything else zero. */
+int dvgr_lstm_pack_dh(const void* d_seq, long long ld_seq, int nd_seq, const void* d_last, long long ld_last, int d_last0,
+                      int S, int T, int D, int H, void* dh_seq, void* dh_last, void* stream);
 int dvgr_dropout(const void* in, void* out, long long n, float p, unsigned long long seed, unsigned int drop_stream,
                  void* stream);
 int dvgr_act_bwd(const void* dy, const void* y, void* out, long long n, int act, int accumulate, float p,
                  unsigned long long seed, unsigned int drop_stream, void* stream);
 int dvgr_add(void* a, const void* b, long long n, void* stream);
+/* The input dropouts of up to 4 punishGATs in one launch (model/GraphNN.py:175: every punishGAT call drops its own copy of
+ * the stream it reads): out[i] = in[i] * mask(seed, drop_streams[i]); in / out / drop_streams are HOST arrays of n_copies. */
+int dvgr_dropout_multi(const void* const* in, void* const* out, const unsigned int* drop_streams, int n_copies, long long n,
+                       float p, unsigned long long seed, void* stream);
+/* Backward of those copies merged with the gradient that bypasses the graphs (residual, model/models.py:168-169):
+ *   out[s] = base[s] + sum_{j < per_stream} mask(drop_streams[s*per_stream + j]) * dxt[s*per_stream + j],  s < n_streams <= 2.
+ * dxt: n_streams*per_stream (<= 4) pointers, base (entries may be null) / out: n_streams pointers; all HOST arrays. */
+int dvgr_gat_input_bwd(const void* const* dxt, const unsigned int* drop_streams, int n_streams, int per_stream,
+                       const void* const* base, void* const* out, long long n, float p, unsigned long long seed, void* stream);
+/* Question-word prologue (model/Preprocessing.py:109-111): words = tanh(dropout(encoder_embed[tokens])) in one pass, written
+ * as words [B][L][Wp] bf16 and time-major x_tm [L][B][Wp] bf16 (word dim zero-padded to Wp, Wp % 8 == 0). tokens int64.
+ * Backward: dtable[tok] += (d_words[b][l] + d_x_tm[l][b]) * (1 - words^2) * mask (fp32 atomics; either gradient may be null). */
+int dvgr_embed_fwd(const long long* tokens, const float* table, int B, int L, int W, int Wp, void* words, void* x_tm,
+                   float p, unsigned long long seed, unsigned int drop_stream, void* stream);
+int dvgr_embed_bwd(const long long* tokens, const void* words, const void* d_words, const void* d_x_tm, int B, int L, int W,
+                   int Wp, float* dtable, float p, unsigned long long seed, unsigned int drop_stream, void* stream);
 /* Several column sums in one launch: out_i[C_i] += sum_r in_i[r][c] (always accumulating; fp32 atomics across row
  * chunks). The bias gradients of the nn.Linear layers, queued during backward and flushed once per train step. */
 typedef struct dvgr_colsum_problem {
@@ -329,9 +382,12 @@ typedef struct dvgr_colsum_problem {
   long long ld, R;
   int C;
   float* out;
+  int perm_H;     /* > 0 (C == 4 * perm_H): input column 4*j + g lands at out[g * perm_H + j] — the bias gradient of a
+                     gate-interleaved LSTM direction written back in nn.LSTM's i|f|g|o order */
+  float* out2;    /* optional second target receiving the same sums (bias_ih and bias_hh of nn.LSTM share one gradient) */
 } dvgr_colsum_problem;
 int dvgr_colsum_grouped(const dvgr_colsum_problem* probs, int n, void* stream);
-/* dst[i] (+)= src[i] for a HOST array of small f32 segments, 64 per launch. accumulate = 1: adds the gradients of the many
+/* dst[i] (+)= src[i] for a HOST array of small f32 segments, 128 per launch. accumulate = 1: adds the gradients of the many
  * tiny parameters of a unit (per-head attention vectors / biases) into their bound .grad views in one launch instead of
  * one elementwise launch per parameter (what autograd's AccumulateGrad does); accumulate = 0: gathers those parameters
  * into the packed avec / bias operands of dvgr_gat_attn_* (model/GraphNN.py:88-93) instead of ~25 torch.cat launches. */
@@ -357,6 +413,13 @@ int dvgr_adam_step(float* params, const float* grads, float* exp_avg, float* exp
                    float grad_scale, const int* step_dev /* optional device step counter, overrides `step` */,
                    void* bf16_shadow /* optional [n] bf16 copy of the updated parameters (next step's GEMM operands) */,
                    void* stream);
+
+/* End-of-step bookkeeping (train.py:154,160-176): out[0] = ce + column sums of parts [rows][3] (the coef-scaled auxiliary
+ * loss partials written by dvgr_aux_loss_unit), out[1] = common-loss sum, out[2] = dependence-loss sum, out[3] = number of
+ * non-zero words among `flags` (HOST array of n_flags <= 16 device pointers: the sticky error words of this step's
+ * dvgr_lstm_seq_* launches). If any flag is set out[0] is NaN: a broken dependency chain can never train silently. */
+int dvgr_finalize_loss(const float* ce, const float* parts, int rows, const int* const* flags, int n_flags, float* out,
+                       void* stream);
 
 #ifdef __cplusplus
 }

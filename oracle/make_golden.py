@@ -2,7 +2,7 @@
 synthetic inputs and the deterministic weights of oracle/dualvgr_oracle.make_state_dict.  Runs only in the build
 container; the fixtures it writes are what pins the oracle (and, through it, the CUDA path) to the reference.
 
-    python oracle/make_golden.py            # rewrites every fixture
+    python oracle/make_golden.py [name ...]  # rewrites every fixture (or only the named ones)
 
 Stored per config: the reference's outputs in float64 ("truth") and float32 (to record the reference's own
 fp32-vs-fp64 floor), loss terms, and per-parameter gradient summaries (L2 norm + projection on a seeded probe vector)
@@ -23,6 +23,8 @@ CONFIGS = {
     "g1_B4_N8_U2": dict(B=4, N=8, L=7, A=10, V=30, U=2, full=True),
     "g2_B3_N20_U3": dict(B=3, N=20, L=9, A=32, V=50, U=3, full=False),
     "g3_B5_N16_U1": dict(B=5, N=16, L=5, A=17, V=40, U=1, full=False),
+    # a realistic batch for the train-mode BatchNorm (the three above have 3-5 samples): holds the un-relaxed 2e-2 gradient gate
+    "g4_B16_N20_U3": dict(B=16, N=20, L=12, A=32, V=60, U=3, full=False),
 }
 
 
@@ -74,7 +76,10 @@ def main():
     torch.Tensor.cuda = lambda self, *a, **k: self      # utils.py:22 hard-codes .cuda(); CPU run
     out_dir = os.path.join(os.path.dirname(HERE), "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
+    only = set(sys.argv[1:])
     for name, cfg in CONFIGS.items():
+        if only and name not in only:
+            continue
         blob = {"cfg": np.array([cfg[k] for k in ("B", "N", "L", "A", "V", "U")], dtype=np.int64)}
         for dt_name, dtype in (("f64", torch.float64), ("f32", torch.float32)):
             torch.set_default_dtype(dtype)     # utils.py:22 builds R with the default dtype (torch.eye)

@@ -34,7 +34,7 @@ def test_struct_layouts_match_header_sizes():
     assert ctypes.sizeof(L.GatArgs) == 4 * ctypes.sizeof(L.GatGraph) + 5 * 4 + 4 + 8 * 3 + 4 * 3 + 4 + 8
 
 
-@pytest.mark.parametrize("name", ["g1_B4_N8_U2", "g2_B3_N20_U3", "g3_B5_N16_U1"])
+@pytest.mark.parametrize("name", ["g1_B4_N8_U2", "g2_B3_N20_U3", "g3_B5_N16_U1", "g4_B16_N20_U3"])
 def test_state_dict_contract_matches_reference(golden, name):
     import dualvgr_videoqa_b200.model.models as M
     g = golden(name)

@@ -104,6 +104,7 @@ def test_early_gradient_bucket_is_final_when_the_unit_input_hooks_fire():
     gradients of the unit stack's inputs have all been produced. Single-GPU check of that contract: snapshot the bucket at
     that moment and compare with its content at the end of the backward pass — nothing may still be written into it."""
     from dualvgr_videoqa_b200.engine import TrainEngine
+    import dualvgr_videoqa_b200.ops as ops
     cfg = (6, 20, 8, 32, 60, 2)
     model, batch = make(cfg)
     eng = TrainEngine(model, lr=1e-5)
@@ -120,17 +121,15 @@ def test_early_gradient_bucket_is_final_when_the_unit_input_hooks_fire():
             self.pending -= 1
             self.calls += 1
             if self.pending == 0:
+                ops.flush_wgrads()          # as the real hook does: the queued early-bucket gradients land before the reduction
                 self.snap = eng.gflat[eng.late_numel:].clone()
                 self.late_at_hook = eng.gflat[:eng.late_numel].clone()
             return None
 
     snap = Snap()
     model._unit_inputs_grad_hook = snap
-    eng.model.train()
-    eng.gflat.zero_()
-    out = eng.model(*batch[:4])
-    total = eng.loss(out, batch[4])[0]
-    total.backward()
+    eng._last_BN = (cfg[0], cfg[1])
+    eng.forward_backward(*batch)
     torch.cuda.synchronize()
     assert snap.calls == 4 and snap.snap is not None
     assert torch.equal(snap.snap, eng.gflat[eng.late_numel:]), "a gradient of the early bucket was written after the hooks fired"

@@ -57,7 +57,7 @@ def total_loss(out, ans, N):
     return ce + 1.0 * com / n + 1e-8 * dep / n, ce, com, dep
 
 
-@pytest.mark.parametrize("name", ["g1_B4_N8_U2", "g2_B3_N20_U3", "g3_B5_N16_U1"])
+@pytest.mark.parametrize("name", ["g1_B4_N8_U2", "g2_B3_N20_U3", "g3_B5_N16_U1", "g4_B16_N20_U3"])
 def test_against_reference_golden(golden, name):
     g = golden(name)
     cfg = [int(x) for x in g["cfg"]]
@@ -76,7 +76,13 @@ def test_against_reference_golden(golden, name):
     assert rel(logits, ref_logits) < TOL
     srt = np.sort(ref_logits, axis=1)
     confident = (srt[:, -1] - srt[:, -2]) > 2 * TOL * np.abs(ref_logits).max()
-    assert np.array_equal(logits.argmax(1).cpu().numpy()[confident], ref_logits.argmax(1)[confident])
+    got_arg = logits.argmax(1).cpu().numpy()
+    assert np.array_equal(got_arg[confident], ref_logits.argmax(1)[confident])
+    agree = int((got_arg == ref_logits.argmax(1)).sum())
+    print(f"{name}: argmax agreement with the reference (fp64), unconditional: {agree}/{len(got_arg)}; "
+          f"rows whose top-2 margin exceeds the tolerance: {int(confident.sum())}")
+    # a flip is only tolerated on a row the reference itself decides by less than the stated tolerance (asserted above)
+    assert agree >= len(got_arg) - int((~confident).sum())
     assert rel(out[1], g["f64_aq_embed"]) < TOL and rel(out[2], g["f64_mq_embed"]) < TOL
     if "f64_com_app_0" in g.files:
         for i in range(len(out[3])):
@@ -92,7 +98,7 @@ def test_against_reference_golden(golden, name):
     # ---- CE-only gradients vs the reference (per-parameter norm + probe projection, global relative error)
     names = [str(n) for n in g["grad_names"]]
     params = dict(model.named_parameters())
-    grads = torch.autograd.grad(ce, [params[n] for n in names], retain_graph=False, allow_unused=True)
+    grads = torch.autograd.grad(ce, [params[n] for n in names], retain_graph=True, allow_unused=True)
     got_norm = np.array([0.0 if gr is None else float(gr.double().norm()) for gr in grads])
     got_proj = np.array([0.0 if gr is None else float((gr.double().cpu() * _probe(n, gr.shape)).sum())
                          for n, gr in zip(names, grads)])
@@ -108,6 +114,17 @@ def test_against_reference_golden(golden, name):
     assert np.linalg.norm(got_proj - ref[:, 1]) / np.linalg.norm(ref[:, 1]) < 0.15
     for n, gr in zip(names, grads):
         assert gr is None or bool(torch.isfinite(gr).all()), n
+    # ---- FULL-loss gradients (CE + alpha common + beta HSIC, train.py:146-154) vs the fixture's f64_grad_full. The auxiliary
+    # terms are ill-conditioned: the reference's own fp32 run misses its fp64 run by `floor` on this very
+    # fixture, so the gate is max(the bf16 tolerance, 4 x that floor) and both numbers are printed.
+    grads_f = torch.autograd.grad(total, [params[n] for n in names], retain_graph=False, allow_unused=True)
+    got_f = np.array([0.0 if gr is None else float(gr.double().norm()) for gr in grads_f])
+    ref_f, f32_f = g["f64_grad_full"], g["f32_grad_full"]
+    floor = np.linalg.norm(f32_f[:, 0] - ref_f[:, 0]) / np.linalg.norm(ref_f[:, 0])
+    err_f = np.linalg.norm(got_f - ref_f[:, 0]) / np.linalg.norm(ref_f[:, 0])
+    print(f"{name}: full-loss per-parameter gradient-norm vector rel-L2 {err_f:.3e} (reference fp32 vs fp64: {floor:.3e}); "
+          f"CE-only {np.linalg.norm(got_norm - ref[:, 0]) / np.linalg.norm(ref[:, 0]):.3e}")
+    assert err_f < max(grad_tol, 4 * floor), (err_f, floor)
 
 
 @pytest.mark.parametrize("cfg", [(6, 20, 8, 32, 60, 3), (24, 8, 8, 32, 60, 2)])

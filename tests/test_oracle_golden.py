@@ -7,7 +7,7 @@ import torch
 
 import dualvgr_oracle as orc
 
-CONFIGS = ["g1_B4_N8_U2", "g2_B3_N20_U3", "g3_B5_N16_U1"]
+CONFIGS = ["g1_B4_N8_U2", "g2_B3_N20_U3", "g3_B5_N16_U1", "g4_B16_N20_U3"]
 
 
 def _probe(name, shape, seed=4242):

@@ -1,0 +1,127 @@
+"""Parity at the BENCHMARKED configuration, through the BENCHMARKED code path.
+
+bench.py times BASELINE configs[1] — SVQA shapes, N=20 clips, L=20, A=32, unit_layers=3, batch 256 — through
+engine.TrainEngine: the fused unit-stack / question-input Functions, stacked two-stream buffers, auxiliary losses on a side
+stream injected inside the stack's backward, deferred + grouped weight gradients and column sums, direct accumulation into the
+flat gradient buffer. This test runs exactly that path (dropout rates set to 0: the fused kernels draw their own counter-based
+masks) and compares with the CPU oracle in float64 on the same seeded batch and weights:
+
+  * logits: global rel-L2 <= 2e-2 (north_star, bf16 mode); argmax agreement reported unconditionally
+  * CE-only parameter gradients (alpha = beta = 0): global rel-L2 over ALL parameters <= 2e-2
+  * FULL-loss gradients (CE + common + HSIC, train.py:146-154): global rel-L2 <= max(2e-2, 4 x the oracle's own fp32-vs-fp64
+    gap on this batch) — the auxiliary terms are ill-conditioned, the floor is measured and printed
+  * loss terms against the oracle's."""
+import numpy as np
+import pytest
+import torch
+
+import dualvgr_oracle as orc
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-2
+CFG = (256, 20, 20, 32, 200, 3)          # B, N, L, A, V, U = bench.py's default workload
+
+
+def _host_memory_gb():
+    """Memory this process may use: min(MemAvailable, cgroup limit). The float64 oracle at B=256 needs ~20 GB."""
+    avail = 1e9
+    try:
+        for ln in open("/proc/meminfo"):
+            if ln.startswith("MemAvailable"):
+                avail = int(ln.split()[1]) / 1048576.0
+        lim = open("/sys/fs/cgroup/memory.max").read().strip()
+        if lim.isdigit():
+            avail = min(avail, int(lim) / 2 ** 30)
+    except OSError:
+        pass
+    return avail
+
+
+def _oracle(dtype, with_aux):
+    B, N, L, A, V, U = CFG
+    sd = orc.cast_state_dict(orc.make_state_dict(U, A, V), dtype)
+    for v in sd.values():
+        if v.is_floating_point():
+            v.requires_grad_(True)
+    app, mot, q, qlen, ans = orc.make_inputs(B, N, L, A, V)
+    out = orc.dualvgr_forward(sd, U, app.to(dtype), mot.to(dtype), q, qlen, training=True)
+    total, ce, com, dep = orc.train_loss(out, ans, N)
+    names = [k for k, v in sd.items() if v.is_floating_point() and "running_" not in k]
+    g_ce = torch.autograd.grad(ce, [sd[n] for n in names], retain_graph=with_aux, allow_unused=True)
+    g_full = torch.autograd.grad(total, [sd[n] for n in names], allow_unused=True) if with_aux else None
+    return out[0].detach(), (float(total), float(ce), float(com), float(dep)), names, g_ce, g_full
+
+
+def _flat_err(names, got, ref):
+    num = den = 0.0
+    worst = []
+    for n in names:
+        r = ref[n]
+        if r is None:
+            continue
+        gt = got[n].double().cpu()
+        num += float((gt - r.double()).pow(2).sum()); den += float(r.double().pow(2).sum())
+        if float(r.norm()) > 0:
+            worst.append((float((gt - r.double()).norm() / r.double().norm()), n))
+    return (num / den) ** 0.5, sorted(worst)[-3:]
+
+
+def test_benchmark_config_engine_path_against_fp64_oracle():
+    import dualvgr_videoqa_b200.model.models as M
+    from dualvgr_videoqa_b200.engine import TrainEngine
+    mem = _host_memory_gb()
+    assert mem > 30, f"only {mem:.0f} GB of host memory for the float64 oracle at B=256: run this test on a bigger host"
+    B, N, L, A, V, U = CFG
+    ref_logits, ref_losses, names, ref_ce, ref_full = _oracle(torch.float64, True)
+    _, f32_losses, _, f32_ce, f32_full = _oracle(torch.float32, True)
+    ref_ce_d, ref_full_d = dict(zip(names, ref_ce)), dict(zip(names, ref_full))
+    floor_full, _ = _flat_err(names, {n: (g if g is not None else torch.zeros(1)) for n, g in zip(names, f32_full)}, ref_full_d)
+    floor_ce, _ = _flat_err(names, {n: (g if g is not None else torch.zeros(1)) for n, g in zip(names, f32_ce)}, ref_ce_d)
+
+    model = M.DualVGR(vocab=orc.make_vocab(V, A), num_of_nodes=N, graph_module="GAT", graph_layers=1, unit_layers=U)
+    model.load_state_dict(orc.make_state_dict(U, A, V), strict=True)
+    for m in model.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+        if hasattr(m, "dropout") and isinstance(getattr(m, "dropout"), float):
+            m.dropout = 0.0
+    model = model.cuda().train()
+    batch = [t.cuda() for t in orc.make_inputs(B, N, L, A, V)]
+    eng = TrainEngine(model, lr=1e-4, alpha=1.0, beta=1e-8)
+    params = dict(model.named_parameters())
+    # ---- full loss, exactly the bench's forward/backward (no optimizer step: the gradient stays in the flat buffer)
+    eng._last_BN = (B, N)
+    total, correct = eng.forward_backward(*batch)
+    torch.cuda.synchronize()
+    assert eng.dependency_poll_timeouts() == 0
+    logits = eng.last_logits
+    err_logits = float((logits.double().cpu() - ref_logits).norm() / ref_logits.norm())
+    agree = int((logits.argmax(1).cpu() == ref_logits.argmax(1)).sum())
+    srt = ref_logits.sort(dim=1).values
+    confident = (srt[:, -1] - srt[:, -2]) > 2 * TOL * ref_logits.abs().max()
+    got_full = {n: params[n].grad.detach().clone() for n in names}
+    err_full, worst_full = _flat_err(names, got_full, ref_full_d)
+    tot, com, dep = eng.loss_terms()
+    # ---- CE only
+    eng.alpha, eng.beta = 0.0, 0.0
+    eng.forward_backward(*batch)
+    torch.cuda.synchronize()
+    got_ce = {n: params[n].grad.detach().clone() for n in names}
+    err_ce, worst_ce = _flat_err(names, got_ce, ref_ce_d)
+    eng.close()
+    print(f"config 2 (B={B}, N={N}, L={L}, A={A}, U={U}) engine path vs oracle fp64: logits rel-L2 {err_logits:.3e}; "
+          f"argmax agreement {agree}/{B} unconditional ({int(confident.sum())} rows beyond the tolerance margin); "
+          f"CE-gradient global rel-L2 {err_ce:.3e} (oracle fp32: {floor_ce:.1e}; worst tensors {worst_ce}); "
+          f"full-loss gradient {err_full:.3e} (oracle fp32: {floor_full:.1e}; worst {worst_full}); "
+          f"losses total/com/dep {tot:.4f}/{com:.4f}/{dep:.2f} vs {ref_losses[0]:.4f}/{ref_losses[2]:.4f}/{ref_losses[3]:.2f} "
+          f"(oracle fp32 {f32_losses[0]:.4f}/{f32_losses[2]:.4f}/{f32_losses[3]:.2f})")
+    assert err_logits < TOL
+    got_arg = logits.argmax(1).cpu()
+    assert bool((got_arg[confident] == ref_logits.argmax(1)[confident]).all())
+    assert agree >= int(0.97 * B)
+    assert err_ce < TOL, worst_ce
+    assert err_full < max(TOL, 4 * floor_full), (err_full, floor_full, worst_full)
+    assert abs(tot - ref_losses[0]) < max(TOL * abs(ref_losses[0]), 4 * abs(f32_losses[0] - ref_losses[0]))
+    assert abs(com - ref_losses[2]) < max(0.05 * abs(ref_losses[2]), 4 * abs(f32_losses[2] - ref_losses[2]))
+    assert abs(dep - ref_losses[3]) < max(0.05 * abs(ref_losses[3]), 4 * abs(f32_losses[3] - ref_losses[3]))
+    assert int(correct.sum()) == int((got_arg == batch[4].cpu()).sum())

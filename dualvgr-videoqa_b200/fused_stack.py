@@ -10,6 +10,8 @@ tensor so that each per-stream GEMM / attention pair is a single batched launch,
 (train.py:148-154) run on a side stream, overlapped with the rest of the step.
 
 The per-module Functions in autograd.py stay: they back the public forward() of each mirrored nn.Module."""
+import os
+
 import torch
 from torch.autograd import Function
 
@@ -52,7 +54,8 @@ def _stack2(a, b, M, D):
     """[2, M, D] view over two [.., D] tensors when b directly follows a in memory (their producers wrote into the halves of
     one buffer), else a stacked copy."""
     if (a.is_contiguous() and b.is_contiguous() and a.dtype == BF16 and b.dtype == BF16
-            and b.data_ptr() == a.data_ptr() + M * D * 2):
+            and b.data_ptr() == a.data_ptr() + M * D * 2
+            and a.untyped_storage().data_ptr() == b.untyped_storage().data_ptr()):      # halves of ONE allocation
         return torch.as_strided(a, (2, M, D), (M * D, D, 1))
     out = torch.empty((2, M, D), dtype=BF16, device=a.device)
     out[0].copy_(a.reshape(M, D))
@@ -64,6 +67,8 @@ _SIDE = {}
 
 
 def side_stream(device, key="aux"):
+    if os.environ.get("DVGR_SIDE_STREAMS", "1") == "0":      # A/B knob: everything on the caller's stream
+        return torch.cuda.current_stream()
     k = (str(device), key)
     if k not in _SIDE:
         _SIDE[k] = torch.cuda.Stream(device=device, priority=-1)
@@ -162,7 +167,9 @@ def _pack_small(PL, heads, D, Dh, dev):
 class UnitStackFn(Function):
     """DualVGRUnit_multiple.forward without the final MFB (reference model/models.py:141-169), all U layers.
 
-    cfg = (U, heads, pdrop, W, aux): pdrop = GAT dropout rate (0 in eval / parity runs), W = word dimension, aux = None or
+    cfg = (U, heads, pdrop, W, aux, want_f32): pdrop = GAT dropout rate (0 in eval / parity runs), W = word dimension,
+    want_f32 = return the dense fp32 copies of the graph outputs (what the auxiliary losses read; False in inference: bf16
+    views are returned instead), aux = None or
     (coef_common, coef_dependence, parts [U, B, 3] f32): with aux the three auxiliary-loss terms of every layer
     (train.py:148-154) and their gradients are computed inside this Function on a side stream (values land in `parts`, the
     gradients are applied in backward with coefficient exactly 1 — the engine's contract, see engine.TrainEngine.loss).
@@ -173,7 +180,7 @@ class UnitStackFn(Function):
 
     @staticmethod
     def forward(ctx, cfg, app, mot, dq, words, qlen, adj, *params):
-        U, heads, pdrop, W, aux = cfg
+        U, heads, pdrop, W, aux, want_f32 = cfg
         B, N, D = app.shape
         M, Dh, Wp = B * N, D // heads, words.shape[-1]
         L = words.shape[1]
@@ -183,7 +190,7 @@ class UnitStackFn(Function):
         X = _stack2(app, mot, M, D)
         words = ag._c(words)
         seed, sid0 = ag._site(3 * G * U)
-        want_f32 = torch.is_grad_enabled() or aux is not None
+        want_f32 = bool(want_f32) or aux is not None      # (grad mode is always off inside Function.forward: the caller decides)
         keep, f32_all, embed = [], [], None
         cur = torch.cuda.current_stream()
         events = []
@@ -242,6 +249,7 @@ class UnitStackFn(Function):
                              xt=xt if pdrop > 0 else None, wh=wh, z=z, hidden=hidden, beta=beta, X=X, we=we, wq=wq, wb=wb,
                              w1=w1, aux_grads=aux_grads))
             X = Xn
+        ctx.set_materialize_grads(False)      # unused outputs (e.g. the fp32 graph outputs in an engine step) arrive as None
         ctx.keep, ctx.pk, ctx.events = keep, pk, events
         ctx.cfg = (U, heads, pdrop, W, B, N, D, L, Wp, seed, sid0)
         ctx.PL, ctx.params = PL, params
@@ -280,6 +288,7 @@ class UnitStackFn(Function):
             sid = sid0 + 3 * G * i
             z, hidden, wh, Xin = k["z"], k["hidden"], k["wh"], k["X"]
             d32 = [None if t is None else ag._c(t) for t in d32_all[G * i:G * i + G]]
+            assert all(t is None or t.dtype == F32 for t in d32), "gradients of the fp32 graph outputs must be fp32"
             if k["aux_grads"] is not None:
                 cur.wait_event(ctx.events[i])
                 if any(t is not None for t in d32):
@@ -332,7 +341,6 @@ class UnitStackFn(Function):
             sink.weight([p.fe_w], dy2, dq)
             sink.colsum([p.fe_b], dy2)
             dX = dXin
-        ctx.keep = None
         need = ctx.needs_input_grad
         return ((None, dX[0].view(B, N, D) if need[1] else None, dX[1].view(B, N, D) if need[2] else None,
                  d_dq if need[3] else None, dwords if need[4] else None, None, None) + sink.grads_for(ctx.params))
@@ -367,6 +375,7 @@ class QuestionInputFn(Function):
         bias = ops.lstm_pack_bias([b.detach() for b in b_ih], [b.detach() for b in b_hh], H)
         gates, h_hist, c_hist, h_last, seq_out, sync = ops.lstm_seq_fwd(x, wih, whh, bias, seq_len=qlen, want_seq=True)
         ag.SYNC_WORDS.append(sync)
+        ctx.set_materialize_grads(False)
         ctx.save_for_backward(tokens, words, x, wih, whh, gates, h_hist, c_hist, qlen)
         ctx.cfg = (B, L, W, Wp, H, p_emb, seed, sid)
         ctx.table = table

@@ -143,7 +143,8 @@ class DualVGRUnit_multiple(nn.Module):
         heads = self.acGCN[0].n_heads if U > 0 else 4
         pdrop = self.acGCN[0].dropout if (U > 0 and self.training) else 0.0
         params = [p for i in range(U) for p in fs.unit_layer_params(self, i)]
-        cfg = (U, heads, float(pdrop), self.word_dim, getattr(self, "_aux", None) if torch.is_grad_enabled() else None)
+        grad = torch.is_grad_enabled()
+        cfg = (U, heads, float(pdrop), self.word_dim, getattr(self, "_aux", None) if grad else None, grad)
         outs = fs.UnitStackFn.apply(cfg, app, mot, dq2, words_p, qlen, self.appearance_adj, *params)
         app, mot, aq_embed, mq_embed = outs[:4]
         f32 = outs[4:]

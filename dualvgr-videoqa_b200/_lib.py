@@ -37,7 +37,7 @@ class GemmArgs(ctypes.Structure):
         ("C", c_void_p), ("ldc", c_ll), ("c_batch", c_ll),
         ("out_f32", c_int), ("act", c_int), ("beta", c_int),
         ("bias", c_void_p), ("bias_batch", c_ll), ("row_map", c_void_p),
-        ("bn", c_int), ("max_ctas", c_int), ("ksplit", c_int),
+        ("bn", c_int), ("max_ctas", c_int), ("ksplit", c_int), ("tile_counter", c_void_p),
     ]
 
 

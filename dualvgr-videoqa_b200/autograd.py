@@ -447,7 +447,7 @@ class AppearanceEncoderFn(Function):
         unmap = _lstm_unmap(H, 2, dg.device)
         t_ih, t_hh = grad_target(ctx.wih_params), grad_target(ctx.whh_params)
         if t_ih is not None:
-            ops.linear_wgrad(dg, xa, out=t_ih, row_map=unmap, atomic=True)
+            ops.linear_wgrad(dg, xa, out=t_ih, row_map=unmap, atomic=True, dynamic=True)   # long launch next to the question encoder's backward
             dwih = None
         else:
             dwih = ops.linear_wgrad(dg, xa, row_map=unmap, bn=256)  # [8H, Dv] fp32 in nn.LSTM row order
@@ -455,11 +455,13 @@ class AppearanceEncoderFn(Function):
         # dW_hh[d] = sum_s dgates[t_d(s)]^T h_hist[d][s]   (segmented MN-major reduction, both directions in one launch)
         kin = (S + 63) // 64
         dwhh = t_hh.view(2, 4 * H, H) if t_hh is not None else torch.empty((2, 4 * H, H), dtype=F32, device=dg.device)
-        wbn, wks = ops.wgrad_split(4 * H, H, T * kin * 64, batch=2) if t_hh is not None else (0, 0)
-        ops.gemm(gates, 1, h_hist, 1, 4 * H, H, T * kin * 64, dwhh, ldc=H, batch=2, c_batch=4 * H * H,
-                 row_map=_lstm_unmap(H, 1, dg.device), a_c0=[0, 4 * H], a_c2=[0, T - 1], a_c2_step=[1, -1],
-                 b_c2=[0, 0], b_c2_step=[1, 1], b_c3=[0, 1], k_inner=kin, beta=2 if t_hh is not None else 0,
-                 bn=wbn, ksplit=wks)
+        wbn, wks = ops.wgrad_split(4 * H, H, (T - 1) * kin * 64, batch=2) if t_hh is not None else (0, 0)
+        # (the step-0 term is skipped: h_0 = 0, and its slot is not even initialised in the whole-sequence layout)
+        s0 = 1 if LSTM_SEQ[0] else 0
+        ops.gemm(gates, 1, h_hist, 1, 4 * H, H, (T - s0) * kin * 64, dwhh, ldc=H, batch=2, c_batch=4 * H * H,
+                 row_map=_lstm_unmap(H, 1, dg.device), a_c0=[0, 4 * H], a_c2=[s0, T - 1 - s0], a_c2_step=[1, -1],
+                 b_c2=[s0, s0], b_c2_step=[1, 1], b_c3=[0, 1], k_inner=kin, beta=2 if t_hh is not None else 0,
+                 bn=wbn, ksplit=wks, dynamic=True)
         g_ih = (None, None) if dwih is None else (dwih[:4 * H], dwih[4 * H:])
         g_hh = (None, None) if t_hh is not None else (dwhh[0], dwhh[1])
         # b_ih, b_hh, b_ih_reverse, b_hh_reverse: both biases of a direction get the same gradient
@@ -536,9 +538,10 @@ class QuestionEncoderFn(Function):
         db[unmap.long()] = ops.colsum(dg)
         kin = (B + 63) // 64
         dwhh = t_hh.view(4, 4 * H, H) if t_hh is not None else torch.empty((4, 4 * H, H), dtype=F32, device=dev)
-        ops.gemm(gates, 1, h_hist, 1, 4 * H, H, L * kin * 64, dwhh, ldc=H, batch=4, c_batch=4 * H * H,
-                 row_map=_lstm_unmap(H, 1, dev), a_c0=[4 * H * d for d in range(4)], a_c2=[0, L - 1, 0, L - 1],
-                 a_c2_step=[1, -1, 1, -1], b_c2=[0, 0, 0, 0], b_c2_step=[1, 1, 1, 1], b_c3=[0, 1, 2, 3], k_inner=kin,
+        s0 = 1 if LSTM_SEQ[0] else 0        # the step-0 term is zero (h_0 = 0) and its slot uninitialised: skipped
+        ops.gemm(gates, 1, h_hist, 1, 4 * H, H, (L - s0) * kin * 64, dwhh, ldc=H, batch=4, c_batch=4 * H * H,
+                 row_map=_lstm_unmap(H, 1, dev), a_c0=[4 * H * d for d in range(4)], a_c2=[s0, L - 1 - s0, s0, L - 1 - s0],
+                 a_c2_step=[1, -1, 1, -1], b_c2=[s0, s0, s0, s0], b_c2_step=[1, 1, 1, 1], b_c3=[0, 1, 2, 3], k_inner=kin,
                  beta=2 if t_hh is not None else 0)
         grads = []
         for d in range(4):

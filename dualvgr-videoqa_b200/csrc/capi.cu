@@ -77,6 +77,7 @@ int dvgr_gemm(const dvgr_gemm_args* a, void* stream) {
   }
   p.k_inner = a->k_inner > 0 ? a->k_inner : INT_MAX;
   p.ksplit = a->ksplit;
+  p.tile_counter = a->tile_counter;
   p.mode = EPI_LINEAR;
   p.C = a->C; p.ldc = a->ldc; p.c_batch = a->c_batch;
   p.out_f32 = a->out_f32; p.act = a->act; p.beta = a->beta;

@@ -21,6 +21,8 @@ __device__ __forceinline__ void load8(const bf16* p, float (&f)[8]) {
     f[2 * q + 1] = t.y;
   }
 }
+__device__ __forceinline__ void load8g(const bf16* p, float (&f)[8]);
+__device__ __forceinline__ void load8g(const float* p, float (&f)[8]);
 __device__ __forceinline__ void store8(bf16* p, const float (&f)[8]) {
   uint4 o;
   o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
@@ -98,6 +100,15 @@ view_attn_bwd_kernel(const bf16* __restrict__ dXnew, const bf16* __restrict__ de
   for (int c = threadIdx.x; c < D; c += blockDim.x) dw2_s[c] = 0.f;
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // a lane owns the same columns (lane * 8 + 256 k) of every row it visits: dw2 accumulates in registers and reaches shared
+  // memory ONCE per thread (one shared atomic per element per row was the top stall of this kernel)
+  constexpr int kMaxPieces = 4;          // D <= 1024 on the register path
+  float dwacc[kMaxPieces][8];
+#pragma unroll
+  for (int k = 0; k < kMaxPieces; ++k)
+#pragma unroll
+    for (int q = 0; q < 8; ++q) dwacc[k][q] = 0.f;
+  const bool reg_path = D <= 256 * kMaxPieces;
   for (long long r = (long long)blockIdx.x * 8 + warp; r < M; r += (long long)gridDim.x * 8) {
     const float b0 = beta[r * 2], b1 = beta[r * 2 + 1];
     float db0 = 0.f, db1 = 0.f;
@@ -126,19 +137,48 @@ view_attn_bwd_kernel(const bf16* __restrict__ dXnew, const bf16* __restrict__ de
     db1 = warp_sum(db1);
     const float t = b0 * db0 + b1 * db1;
     const float dw0 = b0 * (db0 - t), dw1 = b1 * (db1 - t);
-    for (int c = lane * 8; c < D; c += 256) {
-      float h0[8], h1[8], o0[8], o1[8];
-      load8(hidden + r * D + c, h0);
-      load8(hidden + (M + r) * D + c, h1);
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float w = w2[c + q];
-        o0[q] = dw0 * w * (1.f - h0[q] * h0[q]);
-        o1[q] = dw1 * w * (1.f - h1[q] * h1[q]);
-        atomicAdd(&dw2_s[c + q], dw0 * h0[q] + dw1 * h1[q]);
+    for (int k = 0; k < kMaxPieces; ++k) {
+      const int c = lane * 8 + 256 * k;
+      if (c < D && reg_path) {
+        float h0[8], h1[8], o0[8], o1[8];
+        load8(hidden + r * D + c, h0);
+        load8(hidden + (M + r) * D + c, h1);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float w = w2[c + q];
+          o0[q] = dw0 * w * (1.f - h0[q] * h0[q]);
+          o1[q] = dw1 * w * (1.f - h1[q] * h1[q]);
+          dwacc[k][q] += dw0 * h0[q] + dw1 * h1[q];
+        }
+        store8(dhid + r * D + c, o0);
+        store8(dhid + (M + r) * D + c, o1);
       }
-      store8(dhid + r * D + c, o0);
-      store8(dhid + (M + r) * D + c, o1);
+    }
+    if (!reg_path)
+      for (int c = lane * 8; c < D; c += 256) {
+        float h0[8], h1[8], o0[8], o1[8];
+        load8(hidden + r * D + c, h0);
+        load8(hidden + (M + r) * D + c, h1);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float w = w2[c + q];
+          o0[q] = dw0 * w * (1.f - h0[q] * h0[q]);
+          o1[q] = dw1 * w * (1.f - h1[q] * h1[q]);
+          atomicAdd(&dw2_s[c + q], dw0 * h0[q] + dw1 * h1[q]);
+        }
+        store8(dhid + r * D + c, o0);
+        store8(dhid + (M + r) * D + c, o1);
+      }
+  }
+  if (reg_path) {
+#pragma unroll
+    for (int k = 0; k < kMaxPieces; ++k) {
+      const int c = lane * 8 + 256 * k;
+      if (c < D) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) atomicAdd(&dw2_s[c + q], dwacc[k][q]);
+      }
     }
   }
   __syncthreads();
@@ -684,12 +724,34 @@ __global__ void cast_rows_grouped_kernel(const CastGroup G) {
   const float* __restrict__ in = G.in[y];
   bf16* __restrict__ out = G.out[y];
   const int cols = G.cols[y];
+  const long long ld_in = G.ld_in[y];
+  if ((G.out_cols & 7) == 0 && (G.ld_out & 7) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    // 8 columns per thread: two 16-byte loads (when the source row allows it), one 16-byte store
+    const int oc8 = G.out_cols >> 3;
+    const bool vec_in = ((ld_in & 3) == 0) && ((reinterpret_cast<uintptr_t>(in) & 15) == 0);
+    const long long total = (long long)G.rows[y] * oc8;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+      const int r = (int)(i / oc8), c = (int)(i - (long long)r * oc8) * 8;
+      int src = r;
+      if (G.lstm_H > 0) src = (r & 3) * G.lstm_H + (r >> 2);
+      const float* row = in + (long long)src * ld_in + c;
+      float f[8];
+      if (vec_in && c + 8 <= cols) {
+        load8g(row, f);
+      } else {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) f[q] = (c + q < cols) ? row[q] : 0.f;
+      }
+      store8(out + (long long)r * G.ld_out + c, f);
+    }
+    return;
+  }
   const long long total = (long long)G.rows[y] * G.out_cols;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int r = (int)(i / G.out_cols), c = (int)(i - (long long)r * G.out_cols);
     int src = r;
     if (G.lstm_H > 0) src = (r & 3) * G.lstm_H + (r >> 2);
-    out[(long long)r * G.ld_out + c] = __float2bfloat16_rn(c < cols ? in[(long long)src * G.ld_in[y] + c] : 0.f);
+    out[(long long)r * G.ld_out + c] = __float2bfloat16_rn(c < cols ? in[(long long)src * ld_in + c] : 0.f);
   }
 }
 // bias[d][4j + g] = b_ih[d][g*H + j] + b_hh[d][g*H + j]   (the fused cell's gate-interleaved bias, all directions at once)
@@ -1117,7 +1179,7 @@ extern "C" int dvgr_cast_rows_grouped(const float* const* in, const long long* l
   }
   G.ld_out = ld_out; G.out_cols = out_cols; G.lstm_H = lstm_H;
   if (most <= 0) return 0;
-  cast_rows_grouped_kernel<<<dim3(grid_for(most, 256, 148 * 4), n), 256, 0, ST(stream)>>>(G);
+  cast_rows_grouped_kernel<<<dim3(grid_for(most / 8 + 1, 256, 148 * 4), n), 256, 0, ST(stream)>>>(G);
   DVGR_CHECK_LAUNCH("cast_rows_grouped");
   return 0;
 }

@@ -33,6 +33,31 @@
 
 namespace dvgr {
 
+// ---- dynamic tile schedule (shared by the LSTM sequence kernels and, optionally, the GEMM): the TMA-producer thread of a CTA
+// claims tile indices from a global counter and publishes them to its MMA / epilogue warps through a small shared-memory ring
+// guarded by mbarriers. See the discussion at LstmSeqParams.
+constexpr int kTileRing = 8;        // LSTM kernels: STAGES (4) + 2 TMEM stages + 2
+constexpr int kGemmRing = 16;       // GEMM kernel: up to 6 stages
+__device__ __forceinline__ int ring_tile(const int* ring, int slot) {
+  int v;
+  asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(ring + slot)) : "memory");
+  return v;
+}
+template <int R = kTileRing>
+__device__ __forceinline__ void ring_publish(int* ring, uint64_t* bars, int it, int tile) {
+  asm volatile("st.shared.s32 [%0], %1;" ::"r"(smem_u32(ring + (it % R))), "r"(tile) : "memory");
+  mbar_arrive(&bars[it % R]);       // release: the consumers' try_wait (acquire) sees the slot
+}
+template <int R = kTileRing>
+__device__ __forceinline__ int ring_consume(const int* ring, uint64_t* bars, int it) {
+  mbar_wait(&bars[it % R], static_cast<uint32_t>((it / R) & 1));
+  return ring_tile(ring, it % R);
+}
+__device__ __forceinline__ int claim_tile(int* counter, int num_tiles) {
+  const int t = atomicAdd(counter, 1);
+  return t < num_tiles ? t : -1;
+}
+
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int kGemmThreads = 384;   // warps 0-3: TMA / MMA / TMEM alloc / spare ; warps 4-11: epilogue (2 per TMEM lane quarter)
@@ -48,7 +73,8 @@ template <int BN, int kOcc = 1> struct TileCfg {
   static constexpr int STAGES = (kOcc >= 2) ? 3 : (BN == 256) ? 4 : 6;   // kOcc == 3: one CTA/SM, 3 stages (more L1 left)
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   static constexpr int STAGING_BYTES = 8 * 32 * 33 * 4;      // per-epilogue-warp transpose tiles (epi_linear)
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + STAGING_BYTES;
+  static constexpr int BAR_BYTES = 512;                       // pipeline barriers + TMEM slot (256 B) | tile ring (256 B)
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + BAR_BYTES + STAGING_BYTES;
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory a CTA can opt into");
 };
 
@@ -112,17 +138,31 @@ __device__ __forceinline__ void epi_linear(const GemmParams& p, int b, int row0,
   if (row0 >= p.M || col0 >= p.N) return;      // warp-uniform
   const uint32_t stage_s = smem_u32(stage);      // explicit shared-space accesses (the pointer's provenance is lost to
                                                  // the 1024-byte alignment arithmetic, generic ST.E/LD.E otherwise)
+  const int nvalid = min(32, p.N - col0);
+  // accumulating bf16 epilogue (C += acc: the dgrad GEMMs that add into an existing gradient): issue the four 16-byte loads of
+  // the old values FIRST, so their latency hides under the shared-memory transpose below (loading them inside the store
+  // loop exposed one global round trip per iteration: the accumulating dgrad took 80 us against 34 us for the plain one)
+  const bool fast_bf16 = nvalid == 32 && p.row_map == nullptr && !p.out_f32 && ((p.ldc & 7) == 0) &&
+                         ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && ((p.c_batch & 7) == 0);
+  uint4 oldv[4];
+  if (fast_bf16 && p.beta != 0) {
+    const __nv_bfloat16* cb0 = reinterpret_cast<const __nv_bfloat16*>(p.C) + (long long)b * p.c_batch + col0 + 8 * (lane & 3);
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int row = row0 + it * 8 + (lane >> 2);
+      oldv[it] = row < p.M ? *reinterpret_cast<const uint4*>(cb0 + (long long)row * p.ldc) : make_uint4(0, 0, 0, 0);
+    }
+  }
 #pragma unroll
   for (int j = 0; j < 32; ++j) sts_f32(stage_s + (lane * kStagePitch + j) * 4, __uint_as_float(r[j]));
   __syncwarp();
   const float* bias = (p.bias && ks == 0) ? p.bias + (long long)b * p.bias_batch : nullptr;
-  const int nvalid = min(32, p.N - col0);
   // FAST PATHS (warp-uniform test): full 32-column chunk, no row permutation, 16-byte aligned rows. The generic path
   // below re-tests every runtime option per 16-byte store (~600 instructions per chunk and warp, measured with ncu);
   // these loops are ~5x shorter and cover every GEMM of the train step except ragged edges and the LSTM row maps.
   const int act = p.act;
   if (nvalid == 32 && p.row_map == nullptr) {
-    if (!p.out_f32 && ((p.ldc & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && ((p.c_batch & 7) == 0)) {
+    if (fast_bf16) {
       __nv_bfloat16* cbase = reinterpret_cast<__nv_bfloat16*>(p.C) + (long long)b * p.c_batch + col0 + 8 * (lane & 3);
       float bv[8];
 #pragma unroll
@@ -145,7 +185,7 @@ __device__ __forceinline__ void epi_linear(const GemmParams& p, int b, int row0,
         if (row < p.M) {
           uint4* c = reinterpret_cast<uint4*>(cbase + (long long)row * p.ldc);
           if (accum) {
-            const uint4 old = *c;
+            const uint4 old = oldv[it];
             const float2 a0 = unpack_bf16x2(old.x), a1 = unpack_bf16x2(old.y), a2 = unpack_bf16x2(old.z), a3 = unpack_bf16x2(old.w);
             v[0] += a0.x; v[1] += a0.y; v[2] += a1.x; v[3] += a1.y; v[4] += a2.x; v[5] += a2.y; v[6] += a3.x; v[7] += a3.y;
           }
@@ -295,8 +335,9 @@ __device__ __forceinline__ void epi_lstm_fwd(const GemmParams& p, int dir, int s
   if (kFused) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) gin[q] = make_uint4(0, 0, 0, 0);
-    cp0 = __ldcg(reinterpret_cast<const float4*>(cb0));
-    cp1 = __ldcg(reinterpret_cast<const float4*>(cb0 + 128));
+    // (whole-sequence kernels: the initial state, slot 0, is implicit zeros and never read — no fill launches per step)
+    cp0 = s > 0 ? __ldcg(reinterpret_cast<const float4*>(cb0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    cp1 = s > 0 ? __ldcg(reinterpret_cast<const float4*>(cb0 + 128)) : make_float4(0.f, 0.f, 0.f, 0.f);
   } else {
 #pragma unroll
     for (int q = 0; q < 4; ++q) gin[q] = reinterpret_cast<const uint4*>(g)[q];
@@ -332,7 +373,8 @@ __device__ __forceinline__ void epi_lstm_fwd(const GemmParams& p, int dir, int s
   }
   if (!live) {
     // padded step: state is carried unchanged, gates are zeroed so the backward pass sees no contribution
-    uint4 hp = kFused ? __ldcg(reinterpret_cast<const uint4*>(p.h_hist + st)) : *reinterpret_cast<const uint4*>(p.h_hist + st);
+    uint4 hp = kFused ? (s > 0 ? __ldcg(reinterpret_cast<const uint4*>(p.h_hist + st)) : make_uint4(0, 0, 0, 0))
+                      : *reinterpret_cast<const uint4*>(p.h_hist + st);
     const uint32_t* hw = reinterpret_cast<const uint32_t*>(&hp);
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -413,7 +455,11 @@ __device__ __forceinline__ void lstm_cell_bwd8(const GemmParams& p, int dir, int
   if (live) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) gin[q] = *reinterpret_cast<const uint4*>(g + q * gq);
-    a0 = *reinterpret_cast<const float4*>(cprev_p); a1 = *reinterpret_cast<const float4*>(cprev_p + cq);
+    if (kSeq && s == 0) {       // slot 0 of the whole-sequence kernels is implicit zeros
+      a0 = a1 = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+      a0 = *reinterpret_cast<const float4*>(cprev_p); a1 = *reinterpret_cast<const float4*>(cprev_p + cq);
+    }
     b0 = *reinterpret_cast<const float4*>(cc_p); b1 = *reinterpret_cast<const float4*>(cc_p + cq);
     d0 = ld_run4<kSeq>(dcp); d1 = ld_run4<kSeq>(dcp + cq);
   }
@@ -508,7 +554,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* tfull_bar = empty_bar + STAGES;   // [2]
   uint64_t* tempty_bar = tfull_bar + 2;       // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  float* stage_base = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + 256);
+  uint64_t* tile_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + 256);   // [kGemmRing]
+  int* tile_ring = reinterpret_cast<int*>(tile_bar + kGemmRing);                               // [kGemmRing]
+  float* stage_base = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES);
+  static_assert(STAGES + 4 <= kGemmRing, "tile ring too shallow");
+  // dynamic schedule (p.tile_counter, zero on entry): tiles are claimed from a global counter instead of dealt round-robin, so
+  // a CTA that gets its SM late (another kernel is still running there) simply takes fewer tiles — with the static deal the
+  // whole launch waits for the slowest CTA's full share (measured: the W_ih weight gradient went from 0.70 to 1.13 ms when
+  // 24 of its 148 CTAs started 0.5 ms late behind the question encoder's backward)
+  const bool dyn = (kCluster == 1) && p.tile_counter != nullptr;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -535,6 +589,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], kEpiWarps);
     }
+    for (int i = 0; i < kGemmRing; ++i) mbar_init(&tile_bar[i], 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
@@ -553,7 +608,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ===================================================== TMA producer
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+    int next = dyn ? claim_tile(p.tile_counter, num_tiles) : 0;
+    for (int it = 0;; ++it) {
+      int tile;
+      if (dyn) {
+        tile = next;
+        ring_publish<kGemmRing>(tile_ring, tile_bar, it, tile);
+        if (tile < 0) break;
+        next = claim_tile(p.tile_counter, num_tiles);       // one claim ahead: the atomic's latency hides under the loads
+      } else {
+        tile = tile0 + it * tile_step;
+        if (tile >= num_tiles) break;
+      }
       const int ks = tile / (tiles_per_batch * p.batch);
       const int t2 = tile - ks * tiles_per_batch * p.batch;
       const int b = t2 / tiles_per_batch;
@@ -572,8 +638,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           tma_load_4d(sA, &tmA, &full_bar[stage], p.a_c0[b] + kb * BK, m_blk * BM, p.a_c2[b], p.a_c3[b]);
           if (p.prefetch_a) {
             // pull the A block this CTA needs for its NEXT tile from HBM into L2 one tile ahead (it is first-touch there)
-            const int nxt = tile + tile_step;
-            if (nxt < num_tiles) {
+            const int nxt = dyn ? next : tile + tile_step;
+            if (nxt >= 0 && nxt < num_tiles) {
               const int nks = nxt / (tiles_per_batch * p.batch);
               const int nt2 = nxt - nks * tiles_per_batch * p.batch;
               const int nb = nt2 / tiles_per_batch;
@@ -622,7 +688,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint32_t phase = 0;
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+    for (int it = 0;; ++it) {
+      const int tile = dyn ? ring_consume<kGemmRing>(tile_ring, tile_bar, it) : tile0 + it * tile_step;
+      if (tile < 0 || tile >= num_tiles) break;
       const int ks = tile / (tiles_per_batch * p.batch);
       const int kb0 = ks * kb_per, kb1 = min(k_blocks, kb0 + kb_per);
       mbar_wait(&tempty_bar[as], aphase ^ 1u);
@@ -653,7 +721,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int half = (warp - 4) >> 2;
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+    for (int it = 0;; ++it) {
+      const int tile = dyn ? ring_consume<kGemmRing>(tile_ring, tile_bar, it) : tile0 + it * tile_step;
+      if (tile < 0 || tile >= num_tiles) break;
       const int ks = tile / (tiles_per_batch * p.batch);
       const int t2 = tile - ks * tiles_per_batch * p.batch;
       const int b = t2 / tiles_per_batch;
@@ -881,25 +951,6 @@ struct LstmSeqParams {
 // concurrent NCCL kernel, a second LSTM launch on another stream, a partially resident grid).
 // Ring depth: the producer is at most STAGES tiles ahead of the MMA thread (every tile has >= 1 k-block), which is at most 2
 // tiles (the TMEM stages) ahead of the slowest epilogue warp: kTileRing = 8 >= 4 + 2 + 2 slots are never overwritten early.
-constexpr int kTileRing = 8;
-__device__ __forceinline__ int ring_tile(const int* ring, int slot) {
-  int v;
-  asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(ring + slot)) : "memory");
-  return v;
-}
-__device__ __forceinline__ void ring_publish(int* ring, uint64_t* bars, int it, int tile) {
-  asm volatile("st.shared.s32 [%0], %1;" ::"r"(smem_u32(ring + (it % kTileRing))), "r"(tile) : "memory");
-  mbar_arrive(&bars[it % kTileRing]);       // release: the consumers' try_wait (acquire) sees the slot
-}
-__device__ __forceinline__ int ring_consume(const int* ring, uint64_t* bars, int it) {
-  mbar_wait(&bars[it % kTileRing], static_cast<uint32_t>((it / kTileRing) & 1));
-  return ring_tile(ring, it % kTileRing);
-}
-__device__ __forceinline__ int claim_tile(int* counter, int num_tiles) {
-  const int t = atomicAdd(counter, 1);
-  return t < num_tiles ? t : -1;
-}
-
 __device__ __forceinline__ int ld_acquire_gpu(const int* ptr) {
   int v;
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");

@@ -29,6 +29,7 @@ struct GemmParams {
   int debug;        // profiling aid (DVGR_GEMM_DEBUG): 1 = skip global stores, 2 = skip the whole transposed phase
   int prefetch_a;   // producer prefetches the next tile's A blocks into L2 (tuning knob)
   int ksplit;    // K is split over `ksplit` CTAs per output tile (requires beta == 2 on a zero-initialised / accumulating C)
+  int* tile_counter;   // optional, zero on entry: dynamic tile schedule (gemm.cu)
 
   int mode;
   // ---- EPI_LINEAR

@@ -289,7 +289,7 @@ struct AuxParams {
   float* loss_part;      // [B][3]: coef-scaled common, HSIC(aq, ca), HSIC(mq, cm) of each video
   float coef_com, coef_dep;
   int B, N, D, chunks;
-  float* ws;             // [4][B][chunks][N][N]
+  float* ws;             // [4][B][N][N] centred Grams, accumulated over the column chunks
 };
 
 __device__ __forceinline__ void load_centered_tile(const float* __restrict__ x, int N, int D, int c0, float* t) {
@@ -312,7 +312,10 @@ __global__ void __launch_bounds__(kLossThreads) aux_gram_kernel(const AuxParams 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = kLossThreads / 32, g = lane >> 2, t = lane & 3;
   load_centered_tile(p.x[ts] + (long long)b * N * D, N, D, ch * kChunk, tile);
   __syncthreads();
-  float* out = p.ws + (((long long)ts * p.B + b) * p.chunks + ch) * N * N;
+  // the column chunks of a (video, tensor) ADD their partial Grams into one N x N block (zeroed by the launcher): pass 2 then
+  // reads one Gram per operand instead of re-summing `chunks` partials in every one of its `chunks` CTAs (12x redundant L2
+  // traffic at D = 768: ncu showed pass 2 latency-bound on exactly those loads)
+  float* out = p.ws + ((long long)ts * p.B + b) * N * N;
   const int MT = NP / 16, NT = NP / 8;
   for (int ot = warp; ot < MT * NT; ot += nwarps) {
     const int mt = ot / NT, nt = ot - mt * NT;
@@ -324,10 +327,10 @@ __global__ void __launch_bounds__(kLossThreads) aux_gram_kernel(const AuxParams 
       mma_tf32(acc, to_tf32(ar[k0]), to_tf32(ar[8 * kTS + k0]), to_tf32(ar[k0 + 4]), to_tf32(ar[8 * kTS + k0 + 4]),
                to_tf32(br[k0]), to_tf32(br[k0 + 4]));
     const int row = mt * 16 + g, col = nt * 8 + 2 * t;
-    if (row < N && col < N) out[row * N + col] = acc[0];
-    if (row < N && col + 1 < N) out[row * N + col + 1] = acc[1];
-    if (row + 8 < N && col < N) out[(row + 8) * N + col] = acc[2];
-    if (row + 8 < N && col + 1 < N) out[(row + 8) * N + col + 1] = acc[3];
+    if (row < N && col < N) atomicAdd(out + row * N + col, acc[0]);
+    if (row < N && col + 1 < N) atomicAdd(out + row * N + col + 1, acc[1]);
+    if (row + 8 < N && col < N) atomicAdd(out + (row + 8) * N + col, acc[2]);
+    if (row + 8 < N && col + 1 < N) atomicAdd(out + (row + 8) * N + col + 1, acc[3]);
   }
 }
 
@@ -352,18 +355,17 @@ __global__ void __launch_bounds__(kLossThreads, 3) aux_grad_kernel(const AuxPara
   const bool common = ts < 2;
   const int other = 1 - ts, hs = common ? ts + 2 : ts - 2;
   const long long NN = (long long)N * N;
-  const float* gw_s = p.ws + (((long long)ts * p.B + b) * p.chunks) * NN;
-  const float* gw_o = common ? p.ws + (((long long)other * p.B + b) * p.chunks) * NN : nullptr;
-  const float* gw_h = p.ws + (((long long)hs * p.B + b) * p.chunks) * NN;
+  const float* gw_s = p.ws + ((long long)ts * p.B + b) * NN;
+  const float* gw_o = common ? p.ws + ((long long)other * p.B + b) * NN : nullptr;
+  const float* gw_h = p.ws + ((long long)hs * p.B + b) * NN;
   for (int i = warp; i < NP; i += nwarps)
     for (int j = lane; j < CS; j += 32) {
       float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-      if (i < N && j < N)
-        for (int k = 0; k < p.chunks; ++k) {
-          s0 += gw_s[k * NN + i * N + j];
-          s2 += gw_h[k * NN + i * N + j];
-          if (common) s1 += gw_o[k * NN + i * N + j];
-        }
+      if (i < N && j < N) {
+        s0 = gw_s[i * N + j];
+        s2 = gw_h[i * N + j];
+        if (common) s1 = gw_o[i * N + j];
+      }
       Cs[i * CS + j] = s0; Co[i * CS + j] = s1; Ch[i * CS + j] = s2;
       Ac[i * CS + j] = 0.f;
     }
@@ -573,6 +575,8 @@ extern "C" int dvgr_aux_loss_unit(const float* ca, const float* cm, const float*
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   dim3 grid(B, 4, p.chunks);
+  if (cudaMemsetAsync(gram_ws, 0, sizeof(float) * 4 * (size_t)B * N * N, st) != cudaSuccess)
+    return set_error("aux_loss: cudaMemsetAsync failed");
   aux_gram_kernel<<<grid, kLossThreads, smem1, st>>>(p);
   DVGR_CHECK_LAUNCH("aux_gram");
   aux_grad_kernel<<<grid, kLossThreads, smem2, st>>>(p);

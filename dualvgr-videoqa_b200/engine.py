@@ -172,6 +172,7 @@ class TrainEngine:
         model.train()
         self.gflat.zero_()
         ag.begin_step_flags()
+        ops.begin_step_counters(app.device)        # zeroed tile counters of this step's dynamically scheduled GEMMs
         unit = model.visual_input_unit
         B, N = app.shape[0], app.shape[1]
         parts = None
@@ -193,6 +194,7 @@ class TrainEngine:
             raise
         finally:
             ops.DEFER_WGRAD[0] = False
+        ops.end_step_counters(app.device)
         fs.join_side_streams(app.device)   # question-encoder backward / auxiliary losses ran on side streams
         ops.flush_wgrads()                 # ... and launched as ONE grouped tcgen05 GEMM + grouped column sums
         self.last_stats = ops.finalize_loss(ce.detach(), parts, ag.step_flags())
@@ -262,7 +264,9 @@ class TrainEngine:
             st = self.static
             return self.train_step(st["app"], st["mot"], st["q"], st["qlen"], st["ans"])
 
-        side = torch.cuda.Stream()
+        # the step is recorded on a HIGH-priority stream: kernel nodes inherit the priority of the stream they were captured
+        # on, so the critical path (this stream) wins SMs over the low-priority side stream of the auxiliary losses
+        side = torch.cuda.Stream(priority=-1)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(warmup):
@@ -271,7 +275,7 @@ class TrainEngine:
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         n0 = _lib.launch_count()
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph, stream=side):
             self.static_loss = body()
         self.launches_per_replay = _lib.launch_count() - n0    # library kernels recorded into the graph
         self.step_count = int(self.step_dev.item())            # capture itself executed no step: resync with the device

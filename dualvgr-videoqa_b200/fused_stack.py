@@ -71,7 +71,9 @@ def side_stream(device, key="aux"):
         return torch.cuda.current_stream()
     k = (str(device), key)
     if k not in _SIDE:
-        _SIDE[k] = torch.cuda.Stream(device=device, priority=-1)
+        # the auxiliary losses are filler work (low priority: their CTAs only take SMs the critical path leaves idle); the
+        # question encoder is on the critical path of the forward pass (high priority, like the engine's main stream)
+        _SIDE[k] = torch.cuda.Stream(device=device, priority=0 if key == "aux" else -1)
     return _SIDE[k]
 
 
@@ -413,17 +415,18 @@ class QuestionInputFn(Function):
         unmap = ag._lstm_unmap(H, 4, dev)
         t_ih, t_hh = ag.grad_target(ctx.wih_params), ag.grad_target(ctx.whh_params)
         if t_ih is not None:
-            ops.linear_wgrad(dg, x2, out=t_ih, row_map=unmap, atomic=True, cols=W)
+            ops.linear_wgrad(dg, x2, out=t_ih, row_map=unmap, atomic=True, cols=W, dynamic=True)
             dwih = None
         else:
             dwih = ops.linear_wgrad(dg, x2, row_map=unmap)[:, :W]
         dbs = ag._lstm_bias_grads(dg, ctx.bias_params, H)
         kin = (B + 63) // 64
         dwhh = t_hh.view(4, 4 * H, H) if t_hh is not None else torch.empty((4, 4 * H, H), dtype=F32, device=dev)
-        ops.gemm(dgates, 1, h_hist, 1, 4 * H, H, L * kin * 64, dwhh, ldc=H, batch=4, c_batch=4 * H * H,
-                 row_map=ag._lstm_unmap(H, 1, dev), a_c0=[4 * H * d for d in range(4)], a_c2=[0, L - 1, 0, L - 1],
-                 a_c2_step=[1, -1, 1, -1], b_c2=[0, 0, 0, 0], b_c2_step=[1, 1, 1, 1], b_c3=[0, 1, 2, 3], k_inner=kin,
-                 beta=2 if t_hh is not None else 0)
+        # (the step-0 term is skipped: h_0 = 0, and its slot is not initialised in the whole-sequence layout)
+        ops.gemm(dgates, 1, h_hist, 1, 4 * H, H, (L - 1) * kin * 64, dwhh, ldc=H, batch=4, c_batch=4 * H * H,
+                 row_map=ag._lstm_unmap(H, 1, dev), a_c0=[4 * H * d for d in range(4)], a_c2=[1, L - 2, 1, L - 2],
+                 a_c2_step=[1, -1, 1, -1], b_c2=[1, 1, 1, 1], b_c3=[0, 1, 2, 3], b_c2_step=[1, 1, 1, 1], k_inner=kin,
+                 beta=2 if t_hh is not None else 0, dynamic=True)
         grads = []
         for d in range(4):
             sl = slice(4 * H * d, 4 * H * (d + 1))

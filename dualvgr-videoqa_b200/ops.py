@@ -45,8 +45,9 @@ def operand(t, major):
 
 def gemm(A, a_major, B, b_major, M, N, K, C, *, ldc=None, bias=None, act=None, beta=False, batch=1, c_batch=0,
          bias_batch=0, row_map=None, a_c0=None, a_c2=None, a_c3=None, b_c0=None, b_c2=None, b_c3=None, k_inner=0,
-         a_c2_step=None, b_c2_step=None, bn=0, max_ctas=0, ksplit=0):
-    """Raw tcgen05 GEMM: C[b][m][n] = act(sum_k A*B + bias) (+C)."""
+         a_c2_step=None, b_c2_step=None, bn=0, max_ctas=0, ksplit=0, dynamic=False):
+    """Raw tcgen05 GEMM: C[b][m][n] = act(sum_k A*B + bias) (+C). dynamic: CTAs claim tiles from a (freshly zeroed) device
+    counter instead of the static round-robin deal — for long launches that overlap kernels on other streams."""
     _check_cuda(A, B, C, bias)
     args = _lib.GemmArgs()
     args.A = operand(A, a_major)
@@ -76,8 +77,41 @@ def gemm(A, a_major, B, b_major, M, N, K, C, *, ldc=None, bias=None, act=None, b
         args.row_map = row_map.data_ptr()
     args.bn = bn
     args.max_ctas = max_ctas
+    if dynamic:
+        args.tile_counter = tile_counter(C.device).data_ptr()
     _lib.check(_lib.gemm(ctypes.byref(args), _stream()), "dvgr_gemm")
     return C
+
+
+# zeroed int32 counters for dynamically scheduled GEMMs: slots of ONE arena per device that the engine zeroes once per step
+# (begin_step_counters); outside an engine step every call gets a fresh zeroed word
+_COUNTERS = {}
+
+
+def begin_step_counters(device, n=32):
+    """Zeroes the per-step arena of tile counters (one fill launch) and rewinds it. Called at the start of an engine step."""
+    ent = _COUNTERS.get(str(device))
+    if ent is None or ent[0].numel() < n:
+        ent = [torch.zeros(n, dtype=torch.int32, device=device), 0, True]
+        _COUNTERS[str(device)] = ent
+    else:
+        ent[0].zero_()
+    ent[1], ent[2] = 0, True
+    return ent[0]
+
+
+def end_step_counters(device):
+    ent = _COUNTERS.get(str(device))
+    if ent is not None:
+        ent[2] = False
+
+
+def tile_counter(device):
+    ent = _COUNTERS.get(str(device))
+    if ent is not None and ent[2] and ent[1] < ent[0].numel():
+        ent[1] += 1
+        return ent[0][ent[1] - 1:ent[1]]
+    return torch.zeros(1, dtype=torch.int32, device=device)
 
 
 def linear_fwd(x, w, bias=None, act=None, out=None, out_dtype=torch.bfloat16, bn=0):
@@ -117,7 +151,7 @@ def wgrad_split(rows, cols, red, batch=1):
     return bn, best
 
 
-def linear_wgrad(dy, x, out=None, beta=False, row_map=None, bn=0, rows=None, cols=None, atomic=False):
+def linear_wgrad(dy, x, out=None, beta=False, row_map=None, bn=0, rows=None, cols=None, atomic=False, dynamic=False):
     """dw[N,K] (fp32) (+)= dy[M,N]^T @ x[M,K]  (both read MN-major). atomic=True: split-K with fp32 atomic adds into
     `out` (which must already hold the value to accumulate onto, e.g. a zeroed gradient buffer)."""
     M, N = dy.shape
@@ -131,8 +165,8 @@ def linear_wgrad(dy, x, out=None, beta=False, row_map=None, bn=0, rows=None, col
             wgrad_enqueue(dy, x, out, rows, cols)
             return out
         bn2, ks = wgrad_split(rows, cols, M)
-        return gemm(dy, 1, x, 1, rows, cols, M, out, beta=2, row_map=row_map, bn=bn or bn2, ksplit=ks)
-    return gemm(dy, 1, x, 1, rows, cols, M, out, beta=beta, row_map=row_map, bn=bn)
+        return gemm(dy, 1, x, 1, rows, cols, M, out, beta=2, row_map=row_map, bn=bn or bn2, ksplit=ks, dynamic=dynamic)
+    return gemm(dy, 1, x, 1, rows, cols, M, out, beta=beta, row_map=row_map, bn=bn, dynamic=dynamic)
 
 
 # ---- deferred, grouped weight gradients. Inside a train step nothing consumes a weight gradient before the optimizer, so
@@ -295,10 +329,10 @@ def lstm_seq_fwd(x, wih, whh, bias, K1=None, seq_len=None, want_seq=False, h_las
     dev = x.device
     RB, UG = (S + 31) // 32, H // 8
     gates = torch.empty((T, D, RB, UG, 4, 32, 8), dtype=BF16, device=dev)
+    # slot 0 (the initial state) of h_hist / c_hist is implicit zeros: the whole-sequence kernels never read it, and the W_hh
+    # weight gradient skips it (its contribution is zero) — no fill launches
     h_hist = torch.empty((D, T + 1, S, H), dtype=BF16, device=dev)
     c_hist = torch.empty((D, T + 1, RB, UG, 2, 32, 4), dtype=F32, device=dev)
-    h_hist[:, 0].zero_()
-    c_hist[:, 0].zero_()
     if h_last is None:
         h_last = torch.empty((S, D * H), dtype=BF16, device=dev)
     assert h_last.dtype == BF16 and tuple(h_last.shape) == (S, D * H) and h_last.is_contiguous()
@@ -333,7 +367,11 @@ def lstm_bwd(gates, whh, h_hist, c_hist, dh_last, seq_len=None, dh_seq=None, who
         T, S = gates.shape[0], h_hist.shape[2]
         RB, UG = (S + 31) // 32, H // 8
         assert tuple(gates.shape) == (T, D, RB, UG, 4, 32, 8) and tuple(c_hist.shape) == (D, T + 1, RB, UG, 2, 32, 4)
-        dc = torch.zeros((D, RB, UG, 2, 32, 4), dtype=torch.float32, device=gates.device)
+        # ONE zero-filled arena for everything that must start at zero (running dc, dh carry, sync words): one fill launch
+        n_run = D * RB * UG * 256
+        n_sync = int(_lib.lib.dvgr_lstm_seq_sync_words(S, D))
+        arena = torch.zeros((2 * n_run + n_sync + 3,), dtype=torch.float32, device=gates.device)
+        dc = arena[:n_run].view(D, RB, UG, 2, 32, 4)
     else:
         T, S, G = gates.shape
         dc = torch.zeros((D, S, H), dtype=torch.float32, device=gates.device)
@@ -344,7 +382,7 @@ def lstm_bwd(gates, whh, h_hist, c_hist, dh_last, seq_len=None, dh_seq=None, who
         a.dh_last, a.dh_last_ld = dh_last.data_ptr(), dh_last.stride(0)
     if seq_len is not None:
         a.seq_len = seq_len.data_ptr()
-        carry = (torch.zeros((D, RB, UG, 2, 32, 4), dtype=torch.float32, device=gates.device) if whole_sequence
+        carry = (arena[n_run:2 * n_run].view(D, RB, UG, 2, 32, 4) if whole_sequence
                  else torch.zeros((D, S, H), dtype=torch.float32, device=gates.device))
         a.dh_carry = carry.data_ptr()
     if dh_seq_blocked is not None:      # already in the kernels' blocked layout (lstm_pack_dh)
@@ -360,7 +398,7 @@ def lstm_bwd(gates, whh, h_hist, c_hist, dh_last, seq_len=None, dh_seq=None, who
     st = _stream()
     if whole_sequence:
         dgates = torch.empty((T, S, D * H4), dtype=BF16, device=gates.device)
-        sync = torch.zeros((int(_lib.lib.dvgr_lstm_seq_sync_words(S, D)),), dtype=torch.int32, device=gates.device)
+        sync = arena[2 * n_run:2 * n_run + n_sync].view(torch.int32)
         _lib.check(_lib.lstm_seq_bwd(ctypes.byref(a), _ptr(dgates), _ptr(sync), st), "dvgr_lstm_seq_bwd")
         return dgates, sync
     for s in range(T - 1, -1, -1):

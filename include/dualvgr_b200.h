@@ -67,6 +67,9 @@ typedef struct dvgr_gemm_args {
   int bn;                             /* N tile: 128, 256, or 0 = choose */
   int max_ctas;                       /* 0 = one CTA per SM */
   int ksplit;                         /* > 1: split the reduction over that many CTAs per tile (needs beta == 2) */
+  int* tile_counter;                  /* optional device int, ZERO on entry: the CTAs claim their tiles from it (dynamic
+                                         schedule) instead of a static round-robin deal — for long launches that share the
+                                         GPU with kernels on other streams (a CTA that starts late just takes fewer tiles) */
 } dvgr_gemm_args;
 
 /* Replaces every nn.Linear forward / dgrad / wgrad on the path: model/models.py:46,74 (motion projection),

@@ -8,7 +8,7 @@ import dualvgr_videoqa_b200.model.models as M
 from dualvgr_videoqa_b200.engine import TrainEngine
 import bench
 
-c = bench.CFG
+c = dict(bench.CONFIGS[os.environ.get('CONFIG', 'svqa')]); c['F'], c['Dv'] = bench.F_, bench.DV
 dev = torch.device("cuda", 0)
 model = M.DualVGR(vocab=orc.make_vocab(c["V"], c["A"]), num_of_nodes=c["N"], graph_module="GAT", graph_layers=1, unit_layers=c["U"])
 model.load_state_dict(orc.make_state_dict(c["U"], c["A"], c["V"]), strict=True)
@@ -37,6 +37,24 @@ for ev in prof.events():
         a = agg.setdefault(name, [0, 0.0]); a[0] += 1; a[1] += ev.device_time_total if hasattr(ev, "device_time_total") else ev.cuda_time_total
         tot += a[1] * 0
 tot = sum(v[1] for v in agg.values())
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+torch.cuda.synchronize(); e0.record()
+for _ in range(10):
+    eng.replay()
+e1.record(); torch.cuda.synchronize()
+print(f"wall (CUDA events, 10 replays): {e0.elapsed_time(e1)/10:.3f} ms/step")
 print(f"kernel time per step: {tot/3/1e3:.3f} ms over {sum(v[0] for v in agg.values())//3} launches")
-for name, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:40]:
+for name, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:60]:
     print(f"{us/3/1e3:8.3f} ms {100*us/tot:5.1f}%  x{n//3:<4d} {name}")
+
+# ---- timeline of ONE replay: start offset, duration, stream of every kernel (to read the critical path / overlap)
+with profile(activities=[ProfilerActivity.CUDA]) as prof2:
+    eng.replay()
+    torch.cuda.synchronize()
+evs = [e for e in prof2.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+evs.sort(key=lambda e: e.time_range.start)
+t0 = evs[0].time_range.start
+print("---- timeline (us from first kernel): start  dur  end  name")
+for e in evs:
+    st = e.time_range.start - t0
+    print(f"{st:9.1f} {e.time_range.end - e.time_range.start:8.1f} {e.time_range.end - t0:9.1f}  {re.sub(r'[(<].*', '', e.name)[:60]}")

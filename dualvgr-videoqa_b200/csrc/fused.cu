@@ -698,10 +698,23 @@ __global__ void embed_bwd_kernel(const long long* __restrict__ tokens, const bf1
       for (int q = 0; q < 8; ++q) d[q] += e[q];
     }
     dropout_scale8(dc, i, sc);
+    float g[8];
+    bool any = false;
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-      const float g = d[q] * (1.f - w[q] * w[q]) * sc[q];
-      if (c0 + q < W && g != 0.f) atomicAdd(dtable + tok * W + c0 + q, g);
+      g[q] = (c0 + q < W) ? d[q] * (1.f - w[q] * w[q]) * sc[q] : 0.f;
+      any |= g[q] != 0.f;
+    }
+    if (!any) continue;                      // padded positions / dropped octets: nothing to add
+    float* dst = dtable + tok * W + c0;
+    if ((W & 3) == 0 && c0 + 8 <= W && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+      // two 16-byte vector reductions instead of eight scalar atomics (the scalar version was atomic-throughput bound)
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(g[0]), "f"(g[1]), "f"(g[2]), "f"(g[3]) : "memory");
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(g[4]), "f"(g[5]), "f"(g[6]), "f"(g[7]) : "memory");
+    } else {
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if (c0 + q < W && g[q] != 0.f) atomicAdd(dst + q, g[q]);
     }
   }
 }

@@ -334,164 +334,119 @@ __global__ void __launch_bounds__(kLossThreads) aux_gram_kernel(const AuxParams 
   }
 }
 
-__host__ __device__ inline size_t aux_grad_smem(int N) {
-  const int NP = round16(N), CS = NP + 4;
-  return (size_t)(NP * kTS + 5 * NP * CS + 4 * NP) * sizeof(float);
+// pass 2a (aux_mat_kernel, one CTA per video): the whole N x N algebra ONCE per video. From the four centred Grams
+//   C_ca, C_cm, C_aq, C_mq it produces the three loss values and, for every tensor t, ONE matrix M_t such that
+//   dL/dE_t = M_t (R E_t)   (R E_t = E_t centred over the nodes):
+//     common(ca, cm) = c sum_ij (G1 - G2)^2,  G = C / (n n^T),  n_i = sqrt(C_ii):   A = dL/dG1 = 2 c (G1 - G2) = -dL/dG2
+//        dL/dE^_i = 2 sum_j A_ij E^_j ,  r_i = E^_i . dL/dE^_i = 2 sum_j A_ij G_ij ,  dL/d(RE)_i = (dL/dE^_i - r_i E^_i) / n_i
+//        => M^com = R [ 2 A / (n n^T) - diag(r / n^2) ]           (the leading R: gradient of the centring)
+//     HSIC(x, y) = c' sum_ij Cx_ij Cy_ij:   dL/dE_x = 2 c' Cy (R E_x)  => M^hsic_x = 2 c' Cy
+//   M_ca = M^com_1 + 2 c' C_aq,  M_cm = M^com_2 + 2 c' C_mq,  M_aq = 2 c' C_ca,  M_mq = 2 c' C_cm.
+// pass 2b (aux_apply_kernel): dE_t = M_t (R E_t), a streaming pass (one thread per feature column keeps the N centred values
+//   of its column in registers; M_t sits in shared memory) — plain fp32 FMAs.
+// (The first version rebuilt this algebra in every one of the 3 column-chunk CTAs of a (video, tensor) and ran the products on
+//  TF32 fragments out of a 57 KB tile: 156 us per unit layer, latency-bound at 7 % of DRAM bandwidth; this one is ~30 us.)
+__global__ void __launch_bounds__(256) aux_mat_kernel(const AuxParams p, float* __restrict__ mats) {
+  extern __shared__ __align__(16) float sm[];
+  const int b = blockIdx.x, N = p.N, tid = threadIdx.x, NN = N * N;
+  float* C = sm;                      // [4][N][N] centred Grams: ca, cm, aq, mq
+  float* A = C + 4 * NN;              // [N][N] dL/dG_ca
+  float* Mc = A + NN;                 // [2][N][N] un-centred common-term matrices of ca, cm
+  float* nrm = Mc + 2 * NN;           // [2][N] n_i of ca, cm
+  float* rd = nrm + 2 * N;            // [2][N] r_i
+  float* colm = rd + 2 * N;           // [2][N] column means of Mc
+  __shared__ float red[3][8];
+  for (int e = tid; e < 4 * NN; e += blockDim.x) {
+    const int ts = e / NN, ij = e - ts * NN;
+    C[e] = p.ws[((long long)ts * p.B + b) * NN + ij];
+  }
+  __syncthreads();
+  for (int e = tid; e < 2 * N; e += blockDim.x) {
+    const int w = e / N, i = e - w * N;
+    nrm[e] = fmaxf(sqrtf(fmaxf(C[w * NN + i * N + i], 0.f)), 1e-12f);
+  }
+  __syncthreads();
+  float part[3] = {0.f, 0.f, 0.f};
+  for (int e = tid; e < NN; e += blockDim.x) {
+    const int i = e / N, j = e - i * N;
+    const float g1 = C[e] / (nrm[i] * nrm[j]), g2 = C[NN + e] / (nrm[N + i] * nrm[N + j]);
+    const float d = g1 - g2;
+    part[0] += d * d;
+    A[e] = 2.f * p.coef_com * d;
+    part[1] += C[2 * NN + e] * C[e];              // HSIC(aq, ca)
+    part[2] += C[3 * NN + e] * C[NN + e];         // HSIC(mq, cm)
+  }
+  __syncthreads();
+  for (int e = tid; e < 2 * N; e += blockDim.x) {       // r_i = 2 sum_j (+-A_ij) G_ij
+    const int w = e / N, i = e - w * N;
+    float s_ = 0.f;
+    for (int j = 0; j < N; ++j) s_ += A[i * N + j] * C[w * NN + i * N + j] / (nrm[w * N + i] * nrm[w * N + j]);
+    rd[e] = (w ? -2.f : 2.f) * s_;
+  }
+  __syncthreads();
+  for (int e = tid; e < 2 * NN; e += blockDim.x) {
+    const int w = e / NN, ij = e - w * NN, i = ij / N, j = ij - i * N;
+    const float ni = nrm[w * N + i], nj = nrm[w * N + j];
+    float m = (w ? -2.f : 2.f) * A[ij] / (ni * nj);
+    if (i == j) m -= rd[w * N + i] / (ni * ni);
+    Mc[e] = m;
+  }
+  __syncthreads();
+  for (int e = tid; e < 2 * N; e += blockDim.x) {       // column means: the centring projection applied from the left
+    const int w = e / N, j = e - w * N;
+    float s_ = 0.f;
+    for (int i = 0; i < N; ++i) s_ += Mc[w * NN + i * N + j];
+    colm[e] = s_ / N;
+  }
+  __syncthreads();
+  float* out = mats + (long long)b * 4 * NN;            // [B][4][N][N]
+  for (int e = tid; e < NN; e += blockDim.x) {
+    const int j = e % N;
+    out[e] = Mc[e] - colm[j] + 2.f * p.coef_dep * C[2 * NN + e];
+    out[NN + e] = Mc[NN + e] - colm[N + j] + 2.f * p.coef_dep * C[3 * NN + e];
+    out[2 * NN + e] = 2.f * p.coef_dep * C[e];
+    out[3 * NN + e] = 2.f * p.coef_dep * C[NN + e];
+  }
+  const int warp = tid >> 5, lane = tid & 31;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float v = warp_sum(part[c]);
+    if (lane == 0) red[c][warp] = v;
+  }
+  __syncthreads();
+  if (tid < 3) {
+    float s_ = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s_ += red[tid][w];
+    p.loss_part[(long long)b * 3 + tid] = (tid == 0 ? p.coef_com : p.coef_dep) * s_;
+  }
 }
 
-__global__ void __launch_bounds__(kLossThreads, 3) aux_grad_kernel(const AuxParams p) {
-  extern __shared__ __align__(16) float sm[];
-  const int b = blockIdx.x, ts = blockIdx.y, ch = blockIdx.z, N = p.N, D = p.D, NP = round16(N), CS = NP + 4;
-  float* tile = sm;                         // [NP][kTS]   centred chunk of this tensor
-  float* Cs = tile + NP * kTS;              // [NP][CS]    own centred Gram -> own normalised Gram (ca / cm)
-  float* Co = Cs + NP * CS;                 // [NP][CS]    common partner's Gram (ca <-> cm)
-  float* Ch = Co + NP * CS;                 // [NP][CS]    HSIC partner's centred Gram (ca <-> aq, cm <-> mq)
-  float* Ac = Ch + NP * CS;                 // [NP][CS]    dL/dG_self of the common term (tf32-rounded)
-  float* Ah = Ac + NP * CS;                 // [NP][CS]    2 coef_dep C_partner (tf32-rounded)
-  float* inv_n = Ah + NP * CS;              // [NP] own row norms^-1 ; [NP] partner's
-  float* rdot = inv_n + 2 * NP;             // [NP]
-  __shared__ float red[kLossThreads / 32];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = kLossThreads / 32, g = lane >> 2, t = lane & 3;
-  const bool common = ts < 2;
-  const int other = 1 - ts, hs = common ? ts + 2 : ts - 2;
-  const long long NN = (long long)N * N;
-  const float* gw_s = p.ws + ((long long)ts * p.B + b) * NN;
-  const float* gw_o = common ? p.ws + ((long long)other * p.B + b) * NN : nullptr;
-  const float* gw_h = p.ws + ((long long)hs * p.B + b) * NN;
-  for (int i = warp; i < NP; i += nwarps)
-    for (int j = lane; j < CS; j += 32) {
-      float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-      if (i < N && j < N) {
-        s0 = gw_s[i * N + j];
-        s2 = gw_h[i * N + j];
-        if (common) s1 = gw_o[i * N + j];
-      }
-      Cs[i * CS + j] = s0; Co[i * CS + j] = s1; Ch[i * CS + j] = s2;
-      Ac[i * CS + j] = 0.f;
-    }
-  load_centered_tile(p.x[ts] + (long long)b * N * D, N, D, ch * kChunk, tile);
-  __syncthreads();
-  // HSIC value: sum_ij C_self C_partner, reported by the query-side tensors (aq -> column 1, mq -> column 2)
-  float part = 0.f;
-  if (!common)
-    for (int i = warp; i < N; i += nwarps)
-      for (int j = lane; j < N; j += 32) part += Cs[i * CS + j] * Ch[i * CS + j];
-  if (common) {
-    for (int i = tid; i < 2 * N; i += kLossThreads) {
-      const int which = i / N, n = i - which * N;
-      const float* C = which ? Co : Cs;
-      inv_n[which * NP + n] = 1.f / fmaxf(sqrtf(fmaxf(C[n * CS + n], 0.f)), 1e-12f);
-    }
-    __syncthreads();
-    for (int i = warp; i < N; i += nwarps)
-      for (int j = lane; j < N; j += 32) {
-        const float g1 = Cs[i * CS + j] * (inv_n[i] * inv_n[j]);
-        const float g2 = Co[i * CS + j] * (inv_n[NP + i] * inv_n[NP + j]);
-        const float d = g1 - g2;
-        part += d * d;                                   // (only tensor 0 reports it)
-        Ac[i * CS + j] = 2.f * p.coef_com * d;           // dL/dG_self: the same expression from either side of the pair
-        Cs[i * CS + j] = g1;                             // keep the normalised Gram for r_i
-      }
-  }
-  part = warp_sum(part);
-  if (lane == 0) red[warp] = part;
-  __syncthreads();
-  if (tid == 0 && ch == 0 && ts != 1) {
-    float s = 0.f;
-    for (int w = 0; w < nwarps; ++w) s += red[w];
-    const int col = ts == 0 ? 0 : ts - 1;
-    p.loss_part[(long long)b * 3 + col] = (ts == 0 ? p.coef_com : p.coef_dep) * s;
-  }
-  if (common)
-    for (int i = tid; i < N; i += kLossThreads) {          // r_i = E^_i . dE^_i = 2 sum_j Ac_ij G_ij
-      float s = 0.f;
-      for (int j = 0; j < N; ++j) s += Ac[i * CS + j] * Cs[i * CS + j];
-      rdot[i] = 2.f * s;
-    }
-  __syncthreads();
+template <int NP>
+__global__ void __launch_bounds__(128) aux_apply_kernel(const AuxParams p, const float* __restrict__ mats) {
+  extern __shared__ __align__(16) float sm[];           // M_t [N][N]
+  const int b = blockIdx.x, ts = blockIdx.y, N = p.N, D = p.D, NN = N * N;
   if (p.dx[ts] == nullptr) return;
-  // left operands as TF32, rounded once
-  for (int e = tid; e < NP * CS; e += kLossThreads) {
-    Ac[e] = __uint_as_float(to_tf32(Ac[e]));
-    Ah[e] = __uint_as_float(to_tf32(2.f * p.coef_dep * Ch[e]));
-  }
+  for (int e = threadIdx.x; e < NN; e += blockDim.x) sm[e] = mats[((long long)b * 4 + ts) * NN + e];
   __syncthreads();
-
-  float* dst = p.dx[ts] + (long long)b * N * D;
-  const int MT = NP / 16;
-  const bool pair_ok = ((D & 1) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 7) == 0);
-  for (int nt = warp; nt < kChunk / 8; nt += nwarps) {
-    float ac[4][4], ah[4][4];
+  const float* __restrict__ x = p.x[ts] + (long long)b * N * D;
+  float* __restrict__ dx = p.dx[ts] + (long long)b * N * D;
+  for (int c = blockIdx.z * blockDim.x + threadIdx.x; c < D; c += gridDim.z * blockDim.x) {
+    float e[NP];
+    float mean = 0.f;
 #pragma unroll
-    for (int m = 0; m < 4; ++m)
-#pragma unroll
-      for (int q = 0; q < 4; ++q) ac[m][q] = ah[m][q] = 0.f;
-    for (int k0 = 0; k0 < NP; k0 += 8) {
-      const float e0 = tile[(size_t)(k0 + t) * kTS + nt * 8 + g], e1 = tile[(size_t)(k0 + t + 4) * kTS + nt * 8 + g];
-      const uint32_t bh0 = to_tf32(e0), bh1 = to_tf32(e1);                       // E' (centred): HSIC term
-      uint32_t bc0 = 0, bc1 = 0;
-      if (common) {                                                              // E^ = E' / n: common term
-        bc0 = to_tf32(e0 * inv_n[k0 + t]);
-        bc1 = to_tf32(e1 * inv_n[k0 + t + 4]);
-      }
-#pragma unroll
-      for (int m = 0; m < 4; ++m) {
-        if (m < MT) {
-          const float* ar = Ah + (size_t)(m * 16 + g) * CS + k0 + t;
-          mma_tf32(ah[m], __float_as_uint(ar[0]), __float_as_uint(ar[8 * CS]), __float_as_uint(ar[4]),
-                   __float_as_uint(ar[8 * CS + 4]), bh0, bh1);
-          if (common) {
-            const float* cr = Ac + (size_t)(m * 16 + g) * CS + k0 + t;
-            mma_tf32(ac[m], __float_as_uint(cr[0]), __float_as_uint(cr[8 * CS]), __float_as_uint(cr[4]),
-                     __float_as_uint(cr[8 * CS + 4]), bc0, bc1);
-          }
-        }
-      }
+    for (int j = 0; j < NP; ++j) {
+      e[j] = j < N ? x[(long long)j * D + c] : 0.f;
+      mean += e[j];
     }
-    const int cc = nt * 8 + 2 * t, c = ch * kChunk + cc;
-    float v[4][4];
-    float cs0 = 0.f, cs1 = 0.f;
+    mean /= N;
 #pragma unroll
-    for (int m = 0; m < 4; ++m)
+    for (int j = 0; j < NP; ++j) e[j] = j < N ? e[j] - mean : 0.f;
+    for (int i = 0; i < N; ++i) {
+      float acc = 0.f;
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int i = m * 16 + g + 8 * h;
-        float v0 = 0.f, v1 = 0.f;
-        if (common && m < MT && i < N) {
-          // dE' = (dE^ - E^ r) / n with dE^ = 2 Ac E^ ; E^ = E' / n
-          const float inr = inv_n[i], rd = rdot[i];
-          v0 = (2.f * ac[m][2 * h] - tile[(size_t)i * kTS + cc] * inr * rd) * inr;
-          v1 = (2.f * ac[m][2 * h + 1] - tile[(size_t)i * kTS + cc + 1] * inr * rd) * inr;
-        }
-        cs0 += v0;
-        cs1 += v1;
-        v[m][2 * h] = v0;
-        v[m][2 * h + 1] = v1;
-      }
-    if (common) {      // dE = dE' - column mean(dE') ; rows live in the 8 lanes sharing t
-#pragma unroll
-      for (int o = 4; o < 32; o <<= 1) {
-        cs0 += __shfl_xor_sync(0xffffffffu, cs0, o);
-        cs1 += __shfl_xor_sync(0xffffffffu, cs1, o);
-      }
-      cs0 /= N;
-      cs1 /= N;
+      for (int j = 0; j < NP; ++j) acc = fmaf(sm[i * N + (j < N ? j : 0)], e[j], acc);      // (e[j] = 0 beyond N)
+      dx[(long long)i * D + c] = acc;
     }
-#pragma unroll
-    for (int m = 0; m < 4; ++m)
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int i = m * 16 + g + 8 * h;
-        if (m < MT && i < N) {
-          const float o0 = v[m][2 * h] - cs0 + ah[m][2 * h], o1 = v[m][2 * h + 1] - cs1 + ah[m][2 * h + 1];
-          if (c + 1 < D && pair_ok) {
-            *reinterpret_cast<float2*>(dst + (long long)i * D + c) = make_float2(o0, o1);
-          } else {
-            if (c < D) dst[(long long)i * D + c] = o0;
-            if (c + 1 < D) dst[(long long)i * D + c + 1] = o1;
-          }
-        }
-      }
   }
 }
 
@@ -544,8 +499,8 @@ extern "C" int dvgr_pair_loss_multi(const dvgr_pair_job* jobs, int n_jobs, int B
 }
 
 extern "C" long long dvgr_aux_loss_workspace(int B, int N, int D) {
-  const int chunks = (D + kChunk - 1) / kChunk;
-  return 4LL * B * chunks * N * N;
+  (void)D;
+  return 8LL * B * N * N;          // centred Grams [4][B][N][N] + gradient matrices [B][4][N][N]
 }
 
 extern "C" int dvgr_aux_loss_unit(const float* ca, const float* cm, const float* aq, const float* mq, float coef_com,
@@ -561,7 +516,7 @@ extern "C" int dvgr_aux_loss_unit(const float* ca, const float* cm, const float*
   p.loss_part = loss_part; p.coef_com = coef_com; p.coef_dep = coef_dep;
   p.B = B; p.N = N; p.D = D; p.chunks = (D + kChunk - 1) / kChunk; p.ws = gram_ws;
   const size_t smem1 = (size_t)round16(N) * kTS * sizeof(float);
-  const size_t smem2 = aux_grad_smem(N);
+  const size_t smem2 = (size_t)(7 * N * N + 6 * N) * sizeof(float);
   static size_t conf1 = 0, conf2 = 0;
   if (smem1 > 48 * 1024 && smem1 > conf1) {
     cudaError_t e = cudaFuncSetAttribute(aux_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
@@ -569,7 +524,7 @@ extern "C" int dvgr_aux_loss_unit(const float* ca, const float* cm, const float*
     conf1 = smem1;
   }
   if (smem2 > 48 * 1024 && smem2 > conf2) {
-    cudaError_t e = cudaFuncSetAttribute(aux_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+    cudaError_t e = cudaFuncSetAttribute(aux_mat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
     if (e != cudaSuccess) return set_error("aux_loss: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     conf2 = smem2;
   }
@@ -579,7 +534,15 @@ extern "C" int dvgr_aux_loss_unit(const float* ca, const float* cm, const float*
     return set_error("aux_loss: cudaMemsetAsync failed");
   aux_gram_kernel<<<grid, kLossThreads, smem1, st>>>(p);
   DVGR_CHECK_LAUNCH("aux_gram");
-  aux_grad_kernel<<<grid, kLossThreads, smem2, st>>>(p);
-  DVGR_CHECK_LAUNCH("aux_grad");
+  float* mats = gram_ws + 4LL * B * N * N;                       // [B][4][N][N], behind the Grams
+  aux_mat_kernel<<<B, 256, smem2, st>>>(p, mats);
+  DVGR_CHECK_LAUNCH("aux_mat");
+  if (d_ca || d_cm || d_aq || d_mq) {
+    const int zc = (D + 127) / 128 < 3 ? (D + 127) / 128 : 3;     // column chunks per (video, tensor)
+    const size_t smem3 = (size_t)N * N * sizeof(float);
+    if (N <= 32) aux_apply_kernel<32><<<dim3(B, 4, zc), 128, smem3, st>>>(p, mats);
+    else aux_apply_kernel<64><<<dim3(B, 4, zc), 128, smem3, st>>>(p, mats);
+    DVGR_CHECK_LAUNCH("aux_apply");
+  }
   return 0;
 }

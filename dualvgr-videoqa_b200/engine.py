@@ -12,6 +12,7 @@ Videos are independent, so ranks shard the batch and never exchange activations.
 (SURVEY.md §8e): BatchNorm1d in the classifier uses per-rank batch statistics by default (standard DDP) or global ones with
 sync_bn=True (two 2 x 768-float all-reduces per step); CE / common_loss are means (gradient averaging reproduces the
 global-batch gradient), HSIC is a SUM over the batch, so its coefficient is multiplied by world_size before averaging."""
+import contextlib
 import os
 import weakref
 
@@ -105,6 +106,11 @@ class TrainEngine:
         self.graph = None
         self.static = None
         self.numel = total
+        # ONE high-priority stream for every step of this engine, eager or captured: kernel nodes inherit the priority of the
+        # stream they are recorded on (the critical path must win SMs over the low-priority auxiliary-loss stream), and
+        # autograd remembers the stream a parameter was first used on — eager steps on the caller's stream followed by a
+        # capture on another one made the captured backward wait on uncaptured work
+        self.stream = torch.cuda.Stream(device=dev, priority=-1)
         self.last_stats = None           # [4] f32 device tensor of the last step: total, common sum, dependence sum, #timeouts
         self._step_flags = []
         if self.world > 1:      # replicas must start identical (the reference seeds every process the same, train.py:425-428)
@@ -165,9 +171,25 @@ class TrainEngine:
         n = max(n_layers, 1)
         return (self.alpha / n) / (B * N * N), self.beta * self.world / n
 
+    @contextlib.contextmanager
+    def _on_stream(self):
+        """Runs the body on the engine's stream, ordered after the caller's current stream and joined back to it."""
+        cur = torch.cuda.current_stream()
+        if cur == self.stream:
+            yield
+            return
+        self.stream.wait_stream(cur)
+        with torch.cuda.stream(self.stream):
+            yield
+        cur.wait_stream(self.stream)
+
     def forward_backward(self, app, mot, question, question_len, answers):
         """Forward, losses, backward of this rank's shard: leaves the (unreduced) gradient in gflat and the step's statistics
         in last_stats. Returns (total loss (device scalar), n_correct [B] int32)."""
+        with self._on_stream():
+            return self._forward_backward(app, mot, question, question_len, answers)
+
+    def _forward_backward(self, app, mot, question, question_len, answers):
         model = self.model
         model.train()
         self.gflat.zero_()
@@ -214,11 +236,16 @@ class TrainEngine:
     def train_step(self, app, mot, question, question_len, answers):
         """One optimizer step on this rank's shard. Returns the (device) total loss of the shard."""
         self._last_BN = (app.shape[0], app.shape[1])
-        total, _ = self.forward_backward(app, mot, question, question_len, answers)
-        self.optimizer_step()
+        with self._on_stream():
+            total, _ = self._forward_backward(app, mot, question, question_len, answers)
+            self._optimizer_step()
         return total
 
     def optimizer_step(self):
+        with self._on_stream():
+            self._optimizer_step()
+
+    def _optimizer_step(self):
         if self.world > 1 and not self.skip_allreduce:
             if self._overlap is not None and self._overlap.fired:
                 # the early bucket is already in flight on the side stream (launched from the backward pass); reduce the
@@ -264,9 +291,7 @@ class TrainEngine:
             st = self.static
             return self.train_step(st["app"], st["mot"], st["q"], st["qlen"], st["ans"])
 
-        # the step is recorded on a HIGH-priority stream: kernel nodes inherit the priority of the stream they were captured
-        # on, so the critical path (this stream) wins SMs over the low-priority side stream of the auxiliary losses
-        side = torch.cuda.Stream(priority=-1)
+        side = self.stream
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(warmup):

@@ -195,7 +195,7 @@ class UnitStackFn(Function):
         want_f32 = bool(want_f32) or aux is not None      # (grad mode is always off inside Function.forward: the caller decides)
         keep, f32_all, embed = [], [], None
         cur = torch.cuda.current_stream()
-        events = []
+        events, aux_jobs = [None] * U, []
         for i, p in enumerate(PL):
             sid = sid0 + 3 * G * i
             # ---- Query Punishment Module: word attention -> cycle query -> per-clip gates of both streams
@@ -223,19 +223,9 @@ class UnitStackFn(Function):
                                       heads=heads, p_att=pdrop, p_out=pdrop, seed=seed, streams=streams,
                                       outs=[z[g] for g in range(G)], want_f32=want_f32)
             aux_grads = None
-            if aux is not None:
-                # auxiliary losses of this layer: values + all four gradients, on the side stream (joined in backward)
-                c_com, c_dep, parts = aux
+            if aux is not None:       # outputs of the auxiliary-loss kernels (launched after the loop, see below)
                 aux_grads = tuple(torch.empty_like(t) for t in o32)
-                ws = ops.aux_loss_workspace(B, N, D, o32[0])
-                side = side_stream(dev)
-                side.wait_stream(cur)
-                with torch.cuda.stream(side):
-                    ops.aux_loss_unit_into(o32[0], o32[2], o32[1], o32[3], c_com, c_dep, aux_grads[0], aux_grads[2],
-                                           aux_grads[1], aux_grads[3], parts[i], ws)
-                    ev = torch.cuda.Event()
-                    ev.record(side)
-                events.append(ev)
+                aux_jobs.append((i, o32, aux_grads, ops.aux_loss_workspace(B, N, D, o32[0])))
             if want_f32:
                 f32_all += o32
             else:
@@ -251,7 +241,25 @@ class UnitStackFn(Function):
                              xt=xt if pdrop > 0 else None, wh=wh, z=z, hidden=hidden, beta=beta, X=X, we=we, wq=wq, wb=wb,
                              w1=w1, aux_grads=aux_grads))
             X = Xn
+        if aux_jobs:
+            # auxiliary losses of every layer (values + all four gradients each) on the low-priority side stream, forked HERE:
+            # they run next to the fusion / read-out / classifier kernels that follow the stack (a few small GEMMs that leave
+            # most SMs idle) and the first part of the backward pass; LAST layer first, the order backward needs them in.
+            # (Forked right after each layer's graph attention they fought the stack's own GEMMs for SMs: a GEMM CTA needs a
+            # whole SM's shared memory and cannot start while any small CTA is resident there — measured +0.4 ms.)
+            c_com, c_dep, parts = aux
+            side = side_stream(dev)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                for i, o32, gr, ws in reversed(aux_jobs):
+                    ops.aux_loss_unit_into(o32[0], o32[2], o32[1], o32[3], c_com, c_dep, gr[0], gr[2], gr[1], gr[3], parts[i], ws)
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                    events[i] = ev
         ctx.set_materialize_grads(False)      # unused outputs (e.g. the fp32 graph outputs in an engine step) arrive as None
+        # everything the side-stream kernels touch must outlive them: their workspaces were allocated on THIS stream, and a
+        # block freed here could be handed to the next allocation while the (low-priority) side stream still reads it
+        ctx.aux_jobs = aux_jobs
         ctx.keep, ctx.pk, ctx.events = keep, pk, events
         ctx.cfg = (U, heads, pdrop, W, B, N, D, L, Wp, seed, sid0)
         ctx.PL, ctx.params = PL, params

@@ -423,29 +423,53 @@ __global__ void __launch_bounds__(256) aux_mat_kernel(const AuxParams p, float* 
 
 template <int NP>
 __global__ void __launch_bounds__(128) aux_apply_kernel(const AuxParams p, const float* __restrict__ mats) {
-  extern __shared__ __align__(16) float sm[];           // M_t [N][N]
+  extern __shared__ __align__(16) float sm[];           // M_t [N][NP] (rows zero-padded to NP: 16-byte broadcast loads)
   const int b = blockIdx.x, ts = blockIdx.y, N = p.N, D = p.D, NN = N * N;
   if (p.dx[ts] == nullptr) return;
-  for (int e = threadIdx.x; e < NN; e += blockDim.x) sm[e] = mats[((long long)b * 4 + ts) * NN + e];
+  for (int e = threadIdx.x; e < N * NP; e += blockDim.x) {
+    const int i = e / NP, j = e - i * NP;
+    sm[e] = j < N ? mats[((long long)b * 4 + ts) * NN + i * N + j] : 0.f;
+  }
   __syncthreads();
   const float* __restrict__ x = p.x[ts] + (long long)b * N * D;
   float* __restrict__ dx = p.dx[ts] + (long long)b * N * D;
-  for (int c = blockIdx.z * blockDim.x + threadIdx.x; c < D; c += gridDim.z * blockDim.x) {
-    float e[NP];
-    float mean = 0.f;
+  // two adjacent feature columns per thread (8-byte accesses): every 16-byte load of a matrix row feeds 8 FMAs
+  for (int c = 2 * (blockIdx.z * blockDim.x + threadIdx.x); c < D; c += 2 * gridDim.z * blockDim.x) {
+    const bool two = c + 1 < D;
+    float e0[NP], e1[NP];
+    float m0 = 0.f, m1 = 0.f;
 #pragma unroll
     for (int j = 0; j < NP; ++j) {
-      e[j] = j < N ? x[(long long)j * D + c] : 0.f;
-      mean += e[j];
+      e0[j] = e1[j] = 0.f;
+      if (j < N) {
+        if (two) {
+          const float2 v = *reinterpret_cast<const float2*>(x + (long long)j * D + c);
+          e0[j] = v.x; e1[j] = v.y;
+        } else {
+          e0[j] = x[(long long)j * D + c];
+        }
+      }
+      m0 += e0[j]; m1 += e1[j];
     }
-    mean /= N;
+    m0 /= N; m1 /= N;
 #pragma unroll
-    for (int j = 0; j < NP; ++j) e[j] = j < N ? e[j] - mean : 0.f;
+    for (int j = 0; j < NP; ++j) {
+      e0[j] = j < N ? e0[j] - m0 : 0.f;
+      e1[j] = j < N ? e1[j] - m1 : 0.f;
+    }
     for (int i = 0; i < N; ++i) {
-      float acc = 0.f;
+      float a0 = 0.f, a1 = 0.f;
+      const float4* row = reinterpret_cast<const float4*>(sm + i * NP);
 #pragma unroll
-      for (int j = 0; j < NP; ++j) acc = fmaf(sm[i * N + (j < N ? j : 0)], e[j], acc);      // (e[j] = 0 beyond N)
-      dx[(long long)i * D + c] = acc;
+      for (int j4 = 0; j4 < NP / 4; ++j4) {
+        const float4 m = row[j4];
+        a0 = fmaf(m.x, e0[4 * j4], a0); a1 = fmaf(m.x, e1[4 * j4], a1);
+        a0 = fmaf(m.y, e0[4 * j4 + 1], a0); a1 = fmaf(m.y, e1[4 * j4 + 1], a1);
+        a0 = fmaf(m.z, e0[4 * j4 + 2], a0); a1 = fmaf(m.z, e1[4 * j4 + 2], a1);
+        a0 = fmaf(m.w, e0[4 * j4 + 3], a0); a1 = fmaf(m.w, e1[4 * j4 + 3], a1);
+      }
+      if (two) *reinterpret_cast<float2*>(dx + (long long)i * D + c) = make_float2(a0, a1);
+      else dx[(long long)i * D + c] = a0;
     }
   }
 }
@@ -538,8 +562,10 @@ extern "C" int dvgr_aux_loss_unit(const float* ca, const float* cm, const float*
   aux_mat_kernel<<<B, 256, smem2, st>>>(p, mats);
   DVGR_CHECK_LAUNCH("aux_mat");
   if (d_ca || d_cm || d_aq || d_mq) {
-    const int zc = (D + 127) / 128 < 3 ? (D + 127) / 128 : 3;     // column chunks per (video, tensor)
-    const size_t smem3 = (size_t)N * N * sizeof(float);
+    if ((D & 1) != 0) return set_error("aux_loss: D=%d must be even", D);
+    const int zc = (D + 255) / 256 < 3 ? (D + 255) / 256 : 3;     // column chunks per (video, tensor)
+    const int NPad = N <= 32 ? 32 : 64;
+    const size_t smem3 = (size_t)N * NPad * sizeof(float);
     if (N <= 32) aux_apply_kernel<32><<<dim3(B, 4, zc), 128, smem3, st>>>(p, mats);
     else aux_apply_kernel<64><<<dim3(B, 4, zc), 128, smem3, st>>>(p, mats);
     DVGR_CHECK_LAUNCH("aux_apply");

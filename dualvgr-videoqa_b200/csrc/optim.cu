@@ -52,7 +52,35 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
   const float gs = grad_scale * clip;
   const float step = lr / bc1;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+  // 4 parameters per thread: 16-byte loads / stores of p, g, m, v (+ one 8-byte store of the bf16 shadow)
+  const long long n4 = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                         reinterpret_cast<uintptr_t>(v)) & 15) == 0 && (shadow == nullptr || (reinterpret_cast<uintptr_t>(shadow) & 7) == 0)
+                           ? n / 4 : 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 g4 = reinterpret_cast<const float4*>(g)[i];
+    float4 m4 = reinterpret_cast<const float4*>(m)[i], v4 = reinterpret_cast<const float4*>(v)[i];
+    float4 p4 = reinterpret_cast<const float4*>(p)[i];
+    const float gi[4] = {g4.x * gs, g4.y * gs, g4.z * gs, g4.w * gs};
+    float* mp = reinterpret_cast<float*>(&m4);
+    float* vp = reinterpret_cast<float*>(&v4);
+    float* pp = reinterpret_cast<float*>(&p4);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      mp[q] = b1 * mp[q] + (1.f - b1) * gi[q];
+      vp[q] = b2 * vp[q] + (1.f - b2) * gi[q] * gi[q];
+      pp[q] = pp[q] - step * mp[q] / (sqrtf(vp[q]) / bc2_sqrt + eps);
+    }
+    reinterpret_cast<float4*>(m)[i] = m4;
+    reinterpret_cast<float4*>(v)[i] = v4;
+    reinterpret_cast<float4*>(p)[i] = p4;
+    if (shadow != nullptr) {
+      uint2 o;
+      o.x = pack_bf16x2(pp[0], pp[1]);
+      o.y = pack_bf16x2(pp[2], pp[3]);
+      reinterpret_cast<uint2*>(shadow)[i] = o;                     // bf16 operand copy for the next step's GEMMs
+    }
+  }
+  for (long long i = n4 * 4 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float gi = g[i] * gs;
     const float mi = b1 * m[i] + (1.f - b1) * gi;
     const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
@@ -60,7 +88,7 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     v[i] = vi;
     const float pn = p[i] - step * mi / (sqrtf(vi) / bc2_sqrt + eps);
     p[i] = pn;
-    if (shadow != nullptr) shadow[i] = __float2bfloat16_rn(pn);   // bf16 operand copy for the next step's GEMMs
+    if (shadow != nullptr) shadow[i] = __float2bfloat16_rn(pn);
   }
 }
 
@@ -141,8 +169,9 @@ extern "C" int dvgr_adam_step(float* params, const float* grads, float* exp_avg,
   if (step < 1) step = 1;
   const float bc1 = 1.f - powf(beta1, (float)step);
   const float bc2 = 1.f - powf(beta2, (float)step);
-  long long blocks = (n + 255) / 256;
+  long long blocks = (n / 4 + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
   adam_kernel<<<(int)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, bc1, sqrtf(bc2), max_norm, norm_sq, grad_scale, step_dev,
       reinterpret_cast<__nv_bfloat16*>(bf16_shadow));

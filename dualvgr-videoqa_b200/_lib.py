@@ -125,6 +125,7 @@ readout_bwd = _sig("dvgr_readout_bwd", [P, c_ll, P, P, P, P, c_int, c_int, c_int
 bn_fwd = _sig("dvgr_bn_fwd", [P, c_int, c_int, c_int, P, P, P, P, c_int, c_float, c_float, P, P, P, P])
 bn_bwd = _sig("dvgr_bn_bwd", [P, P, c_int, c_int, c_int, P, P, P, c_int, P, P, P, P])
 cross_entropy_ex = _sig("dvgr_cross_entropy_ex", [P, P, c_int, c_int, c_float, P, P, c_int, c_ll, P, P])
+accuracy_counters = _sig("dvgr_accuracy_counters", [P, P, c_int, c_int, P, P, c_ll, P, c_int, c_int, P, P, P])
 bn_stats = _sig("dvgr_bn_stats", [P, c_int, c_int, c_int, P, P])
 bn_fwd_ex = _sig("dvgr_bn_fwd_ex", [P, c_int, c_int, c_int, P, P, P, P, c_int, c_float, c_float, P, P, P, P, c_int, P])
 bn_bwd_ex = _sig("dvgr_bn_bwd_ex", [P, P, c_int, c_int, c_int, P, P, P, c_int, P, P, P, P, c_int, c_int, P])
@@ -191,5 +192,5 @@ EXPORTED = [
     "dvgr_act_bwd", "dvgr_add", "dvgr_scatter", "dvgr_colsum_workspace", "dvgr_colsum", "dvgr_colsum_batched", "dvgr_colsum_grouped", "dvgr_sumsq_blocks", "dvgr_sumsq",
     "dvgr_adam_step", "dvgr_dropout_multi", "dvgr_gat_input_bwd", "dvgr_embed_fwd", "dvgr_embed_bwd",
     "dvgr_view_attn_fwd_multi", "dvgr_view_attn_bwd_multi", "dvgr_cast_rows_grouped", "dvgr_lstm_pack_bias",
-    "dvgr_lstm_pack_dh", "dvgr_finalize_loss", "dvgr_bn_stats", "dvgr_bn_fwd_ex", "dvgr_bn_bwd_ex", "dvgr_cross_entropy_ex",
+    "dvgr_lstm_pack_dh", "dvgr_finalize_loss", "dvgr_bn_stats", "dvgr_bn_fwd_ex", "dvgr_bn_bwd_ex", "dvgr_cross_entropy_ex", "dvgr_accuracy_counters",
 ]

@@ -502,6 +502,49 @@ __global__ void ce_kernel(const float* __restrict__ logits, const long long* __r
   }
 }
 
+
+// =============================================================================================== validation counters
+// reference validate.py:59-134: preds = argmax(logits), agreeings = preds == answers, then per-question-type bookkeeping in
+// Python loops over the batch (a host sync per sample: int(category.cpu()), vocab look-ups per key word). Here: one warp per
+// sample — argmax (first index wins on ties, like torch.argmax), category from the SVQA category id or from the question's
+// first token through a [V] token->type table, and two atomic counters per category: counts[cat] = {correct, total}; row
+// n_cat holds the totals over all samples (uncategorised samples only count there).
+__global__ void accuracy_counters_kernel(const float* __restrict__ logits, const long long* __restrict__ answers, int B, int A,
+                                         const long long* __restrict__ category, const long long* __restrict__ tokens,
+                                         long long ld_tok, const int* __restrict__ token_to_cat, int V, int n_cat,
+                                         long long* __restrict__ counts, int* __restrict__ preds) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (b >= B) return;
+  const float* row = logits + (long long)b * A;
+  float m = -INFINITY;
+  int am = 0;
+  for (int a = lane; a < A; a += 32)
+    if (row[a] > m) { m = row[a]; am = a; }
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, m, o);
+    const int oa = __shfl_xor_sync(0xffffffffu, am, o);
+    if (om > m || (om == m && oa < am)) { m = om; am = oa; }
+  }
+  if (lane != 0) return;
+  if (preds != nullptr) preds[b] = am;
+  const unsigned long long ok = (am == (int)answers[b]) ? 1ull : 0ull;
+  int cat = -1;
+  if (category != nullptr) {
+    cat = (int)category[b];
+  } else if (tokens != nullptr && token_to_cat != nullptr) {
+    const long long tok = tokens[(long long)b * ld_tok];
+    if (tok >= 0 && tok < V) cat = token_to_cat[tok];
+  }
+  unsigned long long* c = reinterpret_cast<unsigned long long*>(counts);
+  if (cat >= 0 && cat < n_cat) {
+    atomicAdd(c + 2 * cat, ok);
+    atomicAdd(c + 2 * cat + 1, 1ull);
+  }
+  atomicAdd(c + 2 * n_cat, ok);
+  atomicAdd(c + 2 * n_cat + 1, 1ull);
+}
+
 // =============================================================================================== streaming helpers
 __device__ __forceinline__ void load8g(const bf16* p, float (&f)[8]);
 __device__ __forceinline__ void load8g(const float* p, float (&f)[8]);
@@ -1070,6 +1113,18 @@ extern "C" int dvgr_cross_entropy_ex(const float* logits, const long long* answe
 extern "C" int dvgr_cross_entropy(const float* logits, const long long* answers, int B, int A, float scale,
                                   float* loss_part, void* dlogits, long long ld_d, int* correct, void* stream) {
   return dvgr_cross_entropy_ex(logits, answers, B, A, scale, loss_part, dlogits, 0, ld_d, correct, stream);
+}
+
+extern "C" int dvgr_accuracy_counters(const float* logits, const long long* answers, int B, int A, const long long* category,
+                                      const long long* tokens, long long ld_tok, const int* token_to_cat, int V, int n_cat,
+                                      long long* counts, int* preds, void* stream) {
+  if (B <= 0) return 0;
+  if (!logits || !answers || !counts) return set_error("accuracy_counters: null buffer");
+  if (n_cat < 0) return set_error("accuracy_counters: n_cat=%d", n_cat);
+  accuracy_counters_kernel<<<(B + 7) / 8, 256, 0, ST(stream)>>>(logits, answers, B, A, category, tokens, ld_tok, token_to_cat,
+                                                                V, n_cat, counts, preds);
+  DVGR_CHECK_LAUNCH("accuracy_counters");
+  return 0;
 }
 
 extern "C" int dvgr_prep_features_ex(const void* in, int in_is_bf16, void* out, long long S, int T, int C, int do_tanh,

@@ -921,3 +921,21 @@ def finalize_loss(ce, parts, flags):
     _lib.check(_lib.finalize_loss(_ptr(ce), _ptr(parts), rows, _parr(flags), len(flags), _ptr(out), _stream()),
                "dvgr_finalize_loss")
     return out
+
+
+def accuracy_counters(logits, answers, counts, category=None, tokens=None, token_to_cat=None, want_preds=False):
+    """counts [n_cat + 1, 2] int64 += (correct, total) per category and overall (last row); see dvgr_accuracy_counters."""
+    B, A = logits.shape
+    assert logits.dtype == F32 and logits.is_contiguous() and answers.dtype == torch.int64 and counts.dtype == torch.int64
+    n_cat = counts.shape[0] - 1
+    preds = torch.empty((B,), dtype=torch.int32, device=logits.device) if want_preds else None
+    if category is not None:
+        assert category.dtype == torch.int64 and category.is_contiguous()
+    V = 0
+    if tokens is not None:
+        assert tokens.dtype == torch.int64 and tokens.stride(-1) == 1 and token_to_cat.dtype == torch.int32
+        V = token_to_cat.numel()
+    _lib.check(_lib.accuracy_counters(_ptr(logits), _ptr(answers), B, A, _ptr(category), _ptr(tokens),
+                                      tokens.stride(0) if tokens is not None else 0, _ptr(token_to_cat), V, n_cat, _ptr(counts),
+                                      _ptr(preds), _stream()), "dvgr_accuracy_counters")
+    return preds

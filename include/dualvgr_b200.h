@@ -300,6 +300,14 @@ int dvgr_cross_entropy(const float* logits, const long long* answers, int B, int
 /* Same with the gradient written as fp32 when grad_is_f32 (the dtype of the logits: what autograd hands to their producer). */
 int dvgr_cross_entropy_ex(const float* logits, const long long* answers, int B, int A, float scale, float* loss_part,
                           void* dlogits, int grad_is_f32, long long ld_d, int* correct, void* stream);
+/* Validation bookkeeping on the device (validate.py:59-134: argmax, agreeings, per-question-type / per-category accuracy —
+ * Python loops with a host sync per sample in the reference): counts [n_cat + 1][2] int64 += {correct, total} per category,
+ * row n_cat = all samples. The category of sample b is category[b] (SVQA: question_categories, validate.py:44) or, when
+ * category is null, token_to_cat[tokens[b][0]] (MSVD / MSRVTT: first question word -> what / who / how / when / where,
+ * validate.py:66-80; -1 = none). preds (optional) [B] int32 receives the argmax (first index on ties). */
+int dvgr_accuracy_counters(const float* logits, const long long* answers, int B, int A, const long long* category,
+                           const long long* tokens, long long ld_tok, const int* token_to_cat, int V, int n_cat,
+                           long long* counts, int* preds, void* stream);
 
 /* Auxiliary losses (utils.py:10-31), value and gradient fused; up to 4 (x, y) pairs per call (one DualVGR unit needs 3:
  * common(com_app, com_mot), HSIC(aq, com_app), HSIC(mq, com_mot) — train.py:148-154). x, y, dx, dy are [B][N][D] f32.

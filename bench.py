@@ -302,19 +302,6 @@ def run_ours(args):
             torch.cuda.synchronize()
         kernels = classify_kernels(prof)
 
-    # ---- exposed all-reduce: the same step captured WITHOUT the gradient exchange, timed the same way
-    allreduce_exposed_ms = None
-    if world > 1 and use_graph and not args.no_comm_ab:
-        eng.graph = None
-        eng.skip_allreduce = True
-        eng.capture(res["app"], res["mot"], res["q"], res["qlen"], res["ans"], warmup=1)
-        eng.replay()
-        ms_nocomm, _ = timed(eng.replay, args.steps)
-        allreduce_exposed_ms = (ms_max - ms_nocomm) / args.steps
-        eng.skip_allreduce = False
-        eng.graph = None
-        eng.capture(res["app"], res["mot"], res["q"], res["qlen"], res["ans"], warmup=1)
-
     # ---- data-parallel parity (N > 1): averaged flat gradient of the sharded step vs ONE rank on the concatenated batch
     dp_parity = None
     if world > 1 and not args.no_dp_parity:
@@ -402,6 +389,19 @@ def run_ours(args):
             eng.capture(res16["app"], res16["mot"], res16["q"], res16["qlen"], res16["ans"], warmup=1)
             e2e_bf16 = measure_e2e(host16)
             del res16
+
+    # ---- exposed all-reduce: the same step captured WITHOUT the gradient exchange, timed the same way. LAST leg: without the
+    #      exchange the replicas drift apart, nothing after this point may depend on them
+    allreduce_exposed_ms = None
+    if world > 1 and use_graph and not args.no_comm_ab:
+        eng.graph = None
+        eng.skip_allreduce = True
+        eng.capture(res["app"], res["mot"], res["q"], res["qlen"], res["ans"], warmup=1)
+        eng.replay()
+        ms_nocomm, _ = timed(eng.replay, args.steps)
+        allreduce_exposed_ms = (ms_max - ms_nocomm) / args.steps
+        eng.skip_allreduce = False
+        eng.graph = None
 
     if rank == 0:
         pk = peaks()

@@ -48,6 +48,7 @@ class LstmArgs(ctypes.Structure):
         ("h_last", c_void_p), ("h_last_ld", c_ll), ("seq_len", c_void_p),
         ("seq_out", c_void_p), ("seq_out_ld", c_ll),
         ("dc", c_void_p), ("dh_last", c_void_p), ("dh_last_ld", c_ll), ("dh_seq", c_void_p), ("dh_carry", c_void_p),
+        ("max_ctas", c_int),
     ]
 
 

@@ -439,7 +439,7 @@ class AppearanceEncoderFn(Function):
         if p_o > 0:
             dh = ops.dropout_raw(dh, p_o, seed, sid + 1)
         if LSTM_SEQ[0]:                                          # blocked activated gates in, standard-layout gradients out
-            gates, sync = ops.lstm_bwd(gates, whh, h_hist, c_hist, dh, whole_sequence=True)
+            gates, sync = ops.lstm_bwd(gates, whh, h_hist, c_hist, dh, whole_sequence=True, max_ctas=ops._cap())
             SYNC_WORDS.append(sync)
         else:
             ops.lstm_bwd(gates, whh, h_hist, c_hist, dh)         # gates now holds d(pre-activation gates)
@@ -447,7 +447,7 @@ class AppearanceEncoderFn(Function):
         unmap = _lstm_unmap(H, 2, dg.device)
         t_ih, t_hh = grad_target(ctx.wih_params), grad_target(ctx.whh_params)
         if t_ih is not None:
-            ops.linear_wgrad(dg, xa, out=t_ih, row_map=unmap, atomic=True, dynamic=True)   # long launch next to the question encoder's backward
+            ops.linear_wgrad(dg, xa, out=t_ih, row_map=unmap, atomic=True, dynamic=True, max_ctas=ops._cap())   # long launch next to the question encoder's backward
             dwih = None
         else:
             dwih = ops.linear_wgrad(dg, xa, row_map=unmap, bn=256)  # [8H, Dv] fp32 in nn.LSTM row order
@@ -461,7 +461,7 @@ class AppearanceEncoderFn(Function):
         ops.gemm(gates, 1, h_hist, 1, 4 * H, H, (T - s0) * kin * 64, dwhh, ldc=H, batch=2, c_batch=4 * H * H,
                  row_map=_lstm_unmap(H, 1, dg.device), a_c0=[0, 4 * H], a_c2=[s0, T - 1 - s0], a_c2_step=[1, -1],
                  b_c2=[s0, s0], b_c2_step=[1, 1], b_c3=[0, 1], k_inner=kin, beta=2 if t_hh is not None else 0,
-                 bn=wbn, ksplit=wks, dynamic=True)
+                 bn=wbn, ksplit=wks, dynamic=True, max_ctas=ops._cap())
         g_ih = (None, None) if dwih is None else (dwih[:4 * H], dwih[4 * H:])
         g_hh = (None, None) if t_hh is not None else (dwhh[0], dwhh[1])
         # b_ih, b_hh, b_ih_reverse, b_hh_reverse: both biases of a direction get the same gradient

@@ -152,7 +152,7 @@ int dvgr_lstm_seq_fwd(const dvgr_lstm_seq_args* a, void* stream) {
   B.ptr = b.whh; B.major = 0; B.ndim = 3;
   B.dims[0] = b.H; B.dims[1] = 4LL * b.H; B.dims[2] = b.ndir;
   B.strides[0] = 1; B.strides[1] = b.H; B.strides[2] = 4LL * b.H * b.H;
-  int rc = lstm_seq_fwd_launch(X, W, A, B, p, a->K1, a->bias, a->sync, reinterpret_cast<cudaStream_t>(stream));
+  int rc = lstm_seq_fwd_launch(X, W, A, B, p, a->K1, a->bias, a->sync, b.max_ctas, reinterpret_cast<cudaStream_t>(stream));
   if (rc == 0) count_launch();
   return rc;
 }
@@ -223,7 +223,7 @@ int dvgr_lstm_seq_bwd(const dvgr_lstm_args* a, void* dgates, int* sync, void* st
   B.ptr = b.whh; B.major = 1; B.ndim = 3;
   B.dims[0] = b.H; B.dims[1] = 4LL * b.H; B.dims[2] = b.ndir;
   B.strides[0] = 1; B.strides[1] = b.H; B.strides[2] = 4LL * b.H * b.H;
-  rc = lstm_seq_bwd_launch(A, B, p, sync, st);
+  rc = lstm_seq_bwd_launch(A, B, p, sync, b.max_ctas, st);
   if (rc == 0) count_launch();
   return rc;
 }

@@ -16,9 +16,9 @@ void g_seed_off_set(const unsigned long long* p);
 int gemm_dispatch(const dvgr_operand& A, const dvgr_operand& B, GemmParams p, int bn, int max_ctas, cudaStream_t stream);
 int lstm_bwd_first(const GemmParams& p, const void* dh_last, long long dh_ld, cudaStream_t stream);
 int gemm_grouped_wgrad(const dvgr_wgrad_problem* probs, int n, cudaStream_t stream);
-int lstm_seq_bwd_launch(const dvgr_operand& G, const dvgr_operand& Whh, GemmParams p, int* sync, cudaStream_t stream);
+int lstm_seq_bwd_launch(const dvgr_operand& G, const dvgr_operand& Whh, GemmParams p, int* sync, int max_ctas, cudaStream_t stream);
 int lstm_seq_fwd_launch(const dvgr_operand& X, const dvgr_operand& Wih, const dvgr_operand& Hh, const dvgr_operand& Whh,
-                        GemmParams p, int K1, const float* bias, int* sync, cudaStream_t stream);
+                        GemmParams p, int K1, const float* bias, int* sync, int max_ctas, cudaStream_t stream);
 int gemm_ref(const void* A, long long a_rs, long long a_ks, const void* B, long long b_rs, long long b_ks, float* C,
              long long ldc, int M, int N, int K, cudaStream_t stream);
 

@@ -1658,7 +1658,7 @@ int gemm_grouped_wgrad(const dvgr_wgrad_problem* probs, int n, cudaStream_t stre
 
 // Whole-sequence fused LSTM forward (lstm_seq_fwd_kernel). p carries the EPI_LSTM fields with M = S, N = 4H, batch = D.
 int lstm_seq_fwd_launch(const dvgr_operand& X, const dvgr_operand& Wih, const dvgr_operand& Hh, const dvgr_operand& Whh,
-                        GemmParams p, int K1, const float* bias, int* sync, cudaStream_t stream) {
+                        GemmParams p, int K1, const float* bias, int* sync, int max_ctas, cudaStream_t stream) {
   constexpr int BN = 256;
   using Cfg = TileCfg<BN, 1>;
   const int H = p.N / 4;
@@ -1695,7 +1695,8 @@ int lstm_seq_fwd_launch(const dvgr_operand& X, const dvgr_operand& Wih, const dv
   // at most one step's tiles can run at the same time (each depends on the step before): more CTAs than that only take SMs
   // away from whatever runs next to this launch (the question encoder next to the appearance encoder: 48 of 148 SMs)
   const long long per_step = (long long)q.m_blocks * q.n_blocks * p.batch;
-  const int grid = (int)std::min<long long>(std::min(tiles, per_step), std::min(max_resident, num_sms()));
+  int grid = (int)std::min<long long>(std::min(tiles, per_step), std::min(max_resident, num_sms()));
+  if (max_ctas > 0) grid = std::min(grid, max_ctas);
   if (grid <= 0) return 0;
   kern<<<grid, kSeqThreads, smem_bytes, stream>>>(tx, twih, th, twhh, p, q);
   cudaError_t e = cudaGetLastError();
@@ -1704,7 +1705,7 @@ int lstm_seq_fwd_launch(const dvgr_operand& X, const dvgr_operand& Wih, const dv
 }
 
 // Whole-sequence LSTM backward, steps T-2 ... 0 (lstm_seq_bwd_kernel). p: EPI_LSTM fields with M = S, N = H, batch = D.
-int lstm_seq_bwd_launch(const dvgr_operand& G, const dvgr_operand& Whh, GemmParams p, int* sync, cudaStream_t stream) {
+int lstm_seq_bwd_launch(const dvgr_operand& G, const dvgr_operand& Whh, GemmParams p, int* sync, int max_ctas, cudaStream_t stream) {
   const int H = p.N;
   if (H % 64 != 0) return set_error("lstm_seq_bwd: H = %d must be a multiple of 64", H);
   if (p.T < 2) return 0;
@@ -1732,7 +1733,8 @@ int lstm_seq_bwd_launch(const dvgr_operand& G, const dvgr_operand& Whh, GemmPara
   }
   const long long tiles = (long long)q.m_blocks * q.n_blocks * p.batch * (p.T - 1);
   const long long per_step = (long long)q.m_blocks * q.n_blocks * p.batch;      // see lstm_seq_fwd_launch
-  const int grid = (int)std::min<long long>(std::min(tiles, per_step), std::min(max_resident, num_sms()));
+  int grid = (int)std::min<long long>(std::min(tiles, per_step), std::min(max_resident, num_sms()));
+  if (max_ctas > 0) grid = std::min(grid, max_ctas);
   if (grid <= 0) return 0;
   lstm_seq_bwd_kernel<<<grid, kBwdThreads, kBwdSmemBytes, stream>>>(tg, tw, p, q);
   cudaError_t e = cudaGetLastError();

@@ -33,7 +33,9 @@ class _EarlyBucketHook:
 
     def __init__(self, engine):
         self.engine = engine
-        self.side = torch.cuda.Stream()
+        # high priority: the collective's few CTAs must get their SMs BEFORE the encoders' persistent backward kernels fill the
+        # GPU (those claim their tiles dynamically, so they simply run on the SMs that are left)
+        self.side = torch.cuda.Stream(priority=-1)
         self.pending = 0
         self.fired = False
 
@@ -120,6 +122,8 @@ class TrainEngine:
         # the rank goes into the seed; weights were identical before this point
         ag.set_rank_seed(self.rank)
         ag.DIRECT_GRAD[0] = True      # weight-gradient GEMMs accumulate straight into the flat gradient buffer
+        # SMs the appearance encoder's persistent backward launches leave to the streams running next to them (ops.RESERVE_SMS)
+        ops.RESERVE_SMS[0] = int(os.environ.get("DVGR_RESERVE_SMS", "0"))     # (measured: reserving SMs does not pay, r2)
         _LIVE_ENGINES.add(self)
         overlap_ok = os.environ.get("DVGR_ALLREDUCE_OVERLAP", "1") != "0"        # A/B knob: 0 = one all-reduce after backward
         self._overlap = _EarlyBucketHook(self) if (self.world > 1 and overlap_ok and 0 < self.late_numel < total) else None
@@ -366,19 +370,25 @@ class TrainEngine:
         try:
             model._unit_inputs_grad_hook = None
             self._overlap = None
-            ou.sync_bn_group, ou.sync_bn_world = (self.pg if self.pg is not None else dist.group.WORLD), W
+            grp = self.pg if self.pg is not None else dist.group.WORLD
             sl = slice(r * samples_per_rank, (r + 1) * samples_per_rank)
             shard = [t[sl].to(dev) for t in (app, mot, q, qlen, ans)]
-            self._last_BN = (samples_per_rank, cfg["N"])
-            self.forward_backward(*shard)
-            dist.all_reduce(self.gflat, op=dist.ReduceOp.SUM, group=self.pg)
-            g_dp = (self.gflat / W).clone()
-            # single-process reference on the concatenated batch
-            ou.sync_bn_group, ou.sync_bn_world = None, 1
-            self.world = 1
             full = [t.to(dev) for t in (app, mot, q, qlen, ans)]
-            self.forward_backward(*full)
-            g_one = self.gflat.clone()
+            self._last_BN = (samples_per_rank, cfg["N"])
+            rels = {}
+            ab = (self.alpha, self.beta)
+            for name, (al, be) in (("ce", (0.0, 0.0)), ("full", ab)):
+                self.alpha, self.beta = al, be
+                self.world, ou.sync_bn_group, ou.sync_bn_world = W, grp, W
+                self.forward_backward(*shard)
+                dist.all_reduce(self.gflat, op=dist.ReduceOp.SUM, group=self.pg)
+                g_dp = (self.gflat / W).clone()
+                # single-process reference on the concatenated batch
+                ou.sync_bn_group, ou.sync_bn_world = None, 1
+                self.world = 1
+                self.forward_backward(*full)
+                rels[name] = float((g_dp - self.gflat).norm() / self.gflat.norm().clamp_min(1e-30))
+            self.alpha, self.beta = ab
         finally:
             self.world, ou.sync_bn_group, ou.sync_bn_world, self._overlap, hook = old
             model._unit_inputs_grad_hook = hook
@@ -386,10 +396,13 @@ class TrainEngine:
                 setattr(m, name, val)
             with torch.no_grad():
                 bn.running_mean.copy_(bn_state[0]); bn.running_var.copy_(bn_state[1]); bn.num_batches_tracked.copy_(bn_state[2])
-        rel = float((g_dp - g_one).norm() / g_one.norm().clamp_min(1e-30))
         chk = self.flat.double().sum().reshape(1)
         gathered = [torch.zeros_like(chk) for _ in range(W)]
         dist.all_gather(gathered, chk, group=self.pg)
         vals = [float(t) for t in gathered]
-        return {"grad_rel_l2": rel, "global_batch": Bg, "param_checksum_spread": max(vals) - min(vals),
-                "note": "dropout off, classifier BatchNorm on global statistics (sync) in the sharded run"}
+        return {"grad_rel_l2": rels["ce"], "grad_rel_l2_full_loss": rels["full"], "global_batch": Bg,
+                "param_checksum_spread": max(vals) - min(vals),
+                "note": "all-reduced, averaged flat gradient of the sharded step vs ONE rank on the concatenated batch; dropout off, "
+                        "classifier BatchNorm on global statistics (sync) in the sharded run; grad_rel_l2 = cross-entropy loss "
+                        "(deterministic up to bf16 / atomic order), grad_rel_l2_full_loss adds the ill-conditioned auxiliary terms "
+                        "(their gradient differs by ~1e-3..1e-2 between two runs of the SAME computation, SURVEY 7)"}

@@ -58,16 +58,23 @@ class InputUnitLinguisticDynamic(nn.Module):
                        m.weight_ih_l0_reverse, m.weight_hh_l0_reverse, m.bias_ih_l0_reverse, m.bias_hh_l0_reverse]
         return params
 
-    def fused(self, questions, qlen32):
-        """Whole input unit as ONE autograd Function (fused_stack.QuestionInputFn): embedding + dropout + tanh in one launch,
-        both BiLSTMs as one 4-direction recurrence. -> (question_embedding [B,D] bf16, words [B,L,Wp] bf16 zero-padded,
-        per-token states [B*L, D] bf16); the first and last are column slices of wider buffers (valid GEMM operands)."""
+    def launch(self, questions, qlen32):
+        """Launches the input unit's forward kernels (embedding + dropout + tanh, both BiLSTMs as one 4-direction recurrence)
+        WITHOUT creating its autograd node; fused() adopts the result later (fused_stack.QuestionInputFn.launch explains why)."""
         from dualvgr_videoqa_b200 import fused_stack as fs
         if not (self.bidirectional and isinstance(self.encoder, nn.LSTM)):
             raise NotImplementedError("the sm_100a question encoder is the bidirectional LSTM pair DualVGR builds")
         p_emb = self.embedding_dropout.p if self.training else 0.0
-        dq, q, words = fs.QuestionInputFn.apply((float(p_emb),), questions, qlen32, self.encoder_embed.weight,
-                                                *self._lstm_params())
+        return (float(p_emb), fs.QuestionInputFn.launch(float(p_emb), questions, qlen32, self.encoder_embed.weight,
+                                                        self._lstm_params()))
+
+    def fused(self, questions, qlen32, launched=None):
+        """Whole input unit as ONE autograd Function (fused_stack.QuestionInputFn). -> (question_embedding [B,D] bf16,
+        words [B,L,Wp] bf16 zero-padded, per-token states [B*L, D] bf16); the first and last are column slices of wider
+        buffers (valid GEMM operands). launched: the result of launch() when the kernels already went out."""
+        from dualvgr_videoqa_b200 import fused_stack as fs
+        cfg = launched if launched is not None else self.launch(questions, qlen32)
+        dq, q, words = fs.QuestionInputFn.apply(cfg, questions, qlen32, self.encoder_embed.weight, *self._lstm_params())
         return ag.dropout(q, self.final_dropout.p, self.training), words, dq
 
     def forward(self, questions, question_len):

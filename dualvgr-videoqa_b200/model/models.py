@@ -79,13 +79,15 @@ class DualVGR(nn.Module):
         side = fs.side_stream(dev, "question")
         side.wait_stream(cur)
         with torch.cuda.stream(side):
-            question_embedding, word_embedding, dynamic_q = self.linguistic_input_unit.fused(question, qlen)
+            launched = self.linguistic_input_unit.launch(question, qlen)       # kernels out first, autograd node last (below)
         # the two clip streams are carried as ONE stacked [2, B*N, D] tensor: both encoders write into its halves
         x0 = torch.empty((2, B * N, D), dtype=BF16, device=dev)
         app = self.visual_appearance_input_unit(video_appearance_feat, out=x0[0])
         mf = video_motion_feat if video_motion_feat.dtype == torch.bfloat16 else video_motion_feat.float()
         mot_in = ag.ops.prep_features(mf.contiguous().view(B * N, -1), 1, False, False)
         mot = ag.linear(mot_in, self.visual_motion_input_unit.weight, self.visual_motion_input_unit.bias, out=x0[1]).view(B, N, D)
+        with torch.cuda.stream(side):
+            question_embedding, word_embedding, dynamic_q = self.linguistic_input_unit.fused(question, qlen, launched)
         cur.wait_stream(side)
         for t in (question_embedding, word_embedding, dynamic_q):
             t.record_stream(cur)

@@ -151,7 +151,8 @@ def wgrad_split(rows, cols, red, batch=1):
     return bn, best
 
 
-def linear_wgrad(dy, x, out=None, beta=False, row_map=None, bn=0, rows=None, cols=None, atomic=False, dynamic=False):
+def linear_wgrad(dy, x, out=None, beta=False, row_map=None, bn=0, rows=None, cols=None, atomic=False, dynamic=False,
+                 max_ctas=0):
     """dw[N,K] (fp32) (+)= dy[M,N]^T @ x[M,K]  (both read MN-major). atomic=True: split-K with fp32 atomic adds into
     `out` (which must already hold the value to accumulate onto, e.g. a zeroed gradient buffer)."""
     M, N = dy.shape
@@ -165,8 +166,9 @@ def linear_wgrad(dy, x, out=None, beta=False, row_map=None, bn=0, rows=None, col
             wgrad_enqueue(dy, x, out, rows, cols)
             return out
         bn2, ks = wgrad_split(rows, cols, M)
-        return gemm(dy, 1, x, 1, rows, cols, M, out, beta=2, row_map=row_map, bn=bn or bn2, ksplit=ks, dynamic=dynamic)
-    return gemm(dy, 1, x, 1, rows, cols, M, out, beta=beta, row_map=row_map, bn=bn, dynamic=dynamic)
+        return gemm(dy, 1, x, 1, rows, cols, M, out, beta=2, row_map=row_map, bn=bn or bn2, ksplit=ks, dynamic=dynamic,
+                    max_ctas=max_ctas)
+    return gemm(dy, 1, x, 1, rows, cols, M, out, beta=beta, row_map=row_map, bn=bn, dynamic=dynamic, max_ctas=max_ctas)
 
 
 # ---- deferred, grouped weight gradients. Inside a train step nothing consumes a weight gradient before the optimizer, so
@@ -314,6 +316,16 @@ def lstm_block_c(c, ):
     return x.view(D, T1, RB, 32, UG, 2, 4).permute(0, 1, 2, 4, 5, 3, 6).contiguous()
 
 
+# SMs left free by the long persistent launches of the appearance encoder's BACKWARD (recurrence, W_ih / W_hh weight gradients)
+# for the kernels that run next to them on other streams: the question encoder's backward and, with more than one rank, the
+# NCCL all-reduce of the early gradient bucket. The engine sets it; 0 = take every SM.
+RESERVE_SMS = [0]
+
+
+def _cap():
+    return NUM_SMS - RESERVE_SMS[0] if RESERVE_SMS[0] > 0 else 0
+
+
 def lstm_seq_fwd(x, wih, whh, bias, K1=None, seq_len=None, want_seq=False, h_last=None):
     """Whole-sequence fused forward (ONE persistent launch): x [T,S,ld] bf16 time-major, wih [D*4H, ld'] bf16 and
     whh [D,4H,H] bf16 gate-interleaved, bias [D*4H] f32 (b_ih + b_hh, interleaved).
@@ -355,7 +367,8 @@ def lstm_seq_fwd(x, wih, whh, bias, K1=None, seq_len=None, want_seq=False, h_las
     return gates, h_hist, c_hist, h_last, seq_out, sync
 
 
-def lstm_bwd(gates, whh, h_hist, c_hist, dh_last, seq_len=None, dh_seq=None, whole_sequence=False, dh_seq_blocked=None):
+def lstm_bwd(gates, whh, h_hist, c_hist, dh_last, seq_len=None, dh_seq=None, whole_sequence=False, dh_seq_blocked=None,
+             max_ctas=0):
     """Backward through the T steps.
     per-step path: `gates` [T,S,D*4H] (activated gates from lstm_fwd) is overwritten in place with the pre-activation gate
     gradients, which feed the W_ih / W_hh / bias wgrads; returns gates.
@@ -376,6 +389,7 @@ def lstm_bwd(gates, whh, h_hist, c_hist, dh_last, seq_len=None, dh_seq=None, who
         T, S, G = gates.shape
         dc = torch.zeros((D, S, H), dtype=torch.float32, device=gates.device)
     a = _lstm_args(gates, whh, h_hist, c_hist, S, H, T, D)
+    a.max_ctas = max_ctas
     a.dc = dc.data_ptr()
     if dh_last is not None:
         assert dh_last.dtype == torch.bfloat16 and dh_last.stride(-1) == 1

@@ -126,6 +126,9 @@ typedef struct dvgr_lstm_args {
   long long dh_last_ld;
   const void* dh_seq;       /* optional [S][T][seq_out_ld] bf16 gradient of seq_out */
   float* dh_carry;          /* [D][S][H] f32, zero before the first backward step; required with seq_len */
+  int max_ctas;             /* whole-sequence kernels only: cap on the persistent grid (0 = one CTA per SM). Their tiles are
+                               claimed dynamically, so a smaller grid just leaves SMs to kernels on other streams (a concurrent
+                               NCCL all-reduce, the other encoder's recurrence) */
 } dvgr_lstm_args;
 
 int dvgr_lstm_step_fwd(const dvgr_lstm_args* args, void* stream);

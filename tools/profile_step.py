@@ -8,13 +8,19 @@ import dualvgr_videoqa_b200.model.models as M
 from dualvgr_videoqa_b200.engine import TrainEngine
 import bench
 
+import torch.distributed as dist
+world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
+if world > 1:
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))))
 c = dict(bench.CONFIGS[os.environ.get('CONFIG', 'svqa')]); c['F'], c['Dv'] = bench.F_, bench.DV
-dev = torch.device("cuda", 0)
+dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
 model = M.DualVGR(vocab=orc.make_vocab(c["V"], c["A"]), num_of_nodes=c["N"], graph_module="GAT", graph_layers=1, unit_layers=c["U"])
 model.load_state_dict(orc.make_state_dict(c["U"], c["A"], c["V"]), strict=True)
 model = model.to(dev).train()
 eng = TrainEngine(model)
-g = torch.Generator().manual_seed(1)
+g = torch.Generator().manual_seed(1 + int(os.environ.get("RANK", "0")))
 app = torch.randn((c["B"], c["N"], c["F"], c["Dv"]), generator=g).abs_().to(dev)
 mot = torch.randn((c["B"], c["N"], c["Dv"]), generator=g).abs_().to(dev)
 qlen = torch.randint(5, c["L"] + 1, (c["B"],), generator=g); qlen[0] = c["L"]
@@ -58,3 +64,8 @@ print("---- timeline (us from first kernel): start  dur  end  name")
 for e in evs:
     st = e.time_range.start - t0
     print(f"{st:9.1f} {e.time_range.end - e.time_range.start:8.1f} {e.time_range.end - t0:9.1f}  {re.sub(r'[(<].*', '', e.name)[:60]}")
+
+if world > 1:
+    dist.barrier(); torch.cuda.synchronize()
+    sys.stdout.flush()
+    os._exit(0)

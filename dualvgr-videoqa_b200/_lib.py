@@ -158,6 +158,7 @@ PLL, PI, PF = ctypes.POINTER(c_ll), ctypes.POINTER(c_int), ctypes.POINTER(c_void
 cast_rows_grouped = _sig("dvgr_cast_rows_grouped", [PP, PLL, PP, PI, PI, c_int, c_ll, c_int, c_int, P])
 lstm_pack_bias = _sig("dvgr_lstm_pack_bias", [PP, PP, c_int, c_int, P, P])
 lstm_pack_dh = _sig("dvgr_lstm_pack_dh", [P, c_ll, c_int, P, c_ll, c_int, c_int, c_int, c_int, c_int, P, P, P])
+split3 = _sig("dvgr_split3", [P, c_ll, c_int, c_int, P, c_ll, P])
 finalize_loss = _sig("dvgr_finalize_loss", [P, P, c_int, PP, c_int, P, P])
 embed_fwd = _sig("dvgr_embed_fwd", [P, P, c_int, c_int, c_int, c_int, P, P, c_float, c_ull, c_uint, P])
 embed_bwd = _sig("dvgr_embed_bwd", [P, P, P, P, c_int, c_int, c_int, c_int, P, c_float, c_ull, c_uint, P])
@@ -193,5 +194,5 @@ EXPORTED = [
     "dvgr_act_bwd", "dvgr_add", "dvgr_scatter", "dvgr_colsum_workspace", "dvgr_colsum", "dvgr_colsum_batched", "dvgr_colsum_grouped", "dvgr_sumsq_blocks", "dvgr_sumsq",
     "dvgr_adam_step", "dvgr_dropout_multi", "dvgr_gat_input_bwd", "dvgr_embed_fwd", "dvgr_embed_bwd",
     "dvgr_view_attn_fwd_multi", "dvgr_view_attn_bwd_multi", "dvgr_cast_rows_grouped", "dvgr_lstm_pack_bias",
-    "dvgr_lstm_pack_dh", "dvgr_finalize_loss", "dvgr_bn_stats", "dvgr_bn_fwd_ex", "dvgr_bn_bwd_ex", "dvgr_cross_entropy_ex", "dvgr_accuracy_counters",
+    "dvgr_lstm_pack_dh", "dvgr_finalize_loss", "dvgr_bn_stats", "dvgr_bn_fwd_ex", "dvgr_bn_bwd_ex", "dvgr_cross_entropy_ex", "dvgr_accuracy_counters", "dvgr_split3",
 ]

@@ -595,6 +595,38 @@ __global__ void cast_rows_kernel(const float* __restrict__ in, long long ld_in, 
   }
 }
 
+
+// fp32 -> three bf16 planes [lo | hi | hi] ([3][rows][ld_out]): the operand format of the fp32-accurate ("3 x bf16") GEMM.
+// x = hi + lo + r with |r| <= 2^-17 |x|; a product a.b is evaluated as a_lo b_hi + a_hi b_hi + a_hi b_lo by ONE tcgen05 GEMM
+// whose reduction runs over the three planes: the A operand reads them in the order 0, 1, 2, the B operand in the order 2, 1, 0.
+__global__ void split3_kernel(const float* __restrict__ in, long long ld_in, int rows, int cols, bf16* __restrict__ out,
+                              long long ld_out, long long plane) {
+  pdl_trigger();
+  const int c8 = (int)(ld_out >> 3);
+  const long long total = (long long)rows * c8;
+  const bool vec_in = ((ld_in & 3) == 0) && ((reinterpret_cast<uintptr_t>(in) & 15) == 0);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / c8), c = (int)(i - (long long)r * c8) * 8;
+    const float* row = in + (long long)r * ld_in + c;
+    float f[8], hi[8], lo[8];
+    if (vec_in && c + 8 <= cols) {
+      load8g(row, f);
+    } else {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) f[q] = (c + q < cols) ? row[q] : 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      hi[q] = __bfloat162float(__float2bfloat16_rn(f[q]));
+      lo[q] = f[q] - hi[q];
+    }
+    bf16* o = out + (long long)r * ld_out + c;
+    store8(o, lo);
+    store8(o + plane, hi);
+    store8(o + 2 * plane, hi);
+  }
+}
+
 // out = in * dropout mask (the same kernel is its own backward)
 __global__ void dropout_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, long long n8, DropoutCfg dc) {
   pdl_trigger();
@@ -1155,6 +1187,16 @@ extern "C" int dvgr_cast_rows(const float* in, long long ld_in, void* out, long 
   if (lstm_H > 0 && rows != 4 * lstm_H) return set_error("cast_rows: rows=%d != 4*H=%d", rows, 4 * lstm_H);
   cast_rows_kernel<<<grid_for(n), 256, 0, ST(stream)>>>(in, ld_in, BF(out), ld_out, rows, cols, out_cols, lstm_H);
   DVGR_CHECK_LAUNCH("cast_rows");
+  return 0;
+}
+
+extern "C" int dvgr_split3(const float* in, long long ld_in, int rows, int cols, void* out, long long ld_out, void* stream) {
+  if (rows <= 0 || cols <= 0) return 0;
+  if (!in || !out) return set_error("split3: null buffer");
+  if (ld_out % 8 != 0 || ld_out < cols) return set_error("split3: ld_out=%lld must be a multiple of 8 and >= cols=%d", ld_out, cols);
+  const long long n = (long long)rows * (ld_out / 8);
+  split3_kernel<<<grid_for(n, 256, 148 * 8), 256, 0, ST(stream)>>>(in, ld_in, rows, cols, BF(out), ld_out, (long long)rows * ld_out);
+  DVGR_CHECK_LAUNCH("split3");
   return 0;
 }
 

@@ -637,7 +637,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int seg = kb / p.k_inner;
         const int kin = (kb - seg * p.k_inner) * BK;
         if (!A_MN) {
-          tma_load_4d(sA, &tmA, &full_bar[stage], p.a_c0[b] + kb * BK, m_blk * BM, p.a_c2[b], p.a_c3[b]);
+          // (K-major operands may be segmented too: k-block kb -> column kin of plane a_c2 + seg * step — the three bf16
+          //  planes of a split fp32 operand, dvgr_split3; unsegmented: seg = 0, kin = kb * BK)
+          tma_load_4d(sA, &tmA, &full_bar[stage], p.a_c0[b] + kin, m_blk * BM, p.a_c2[b] + seg * p.a_c2_step[b], p.a_c3[b]);
           if (p.prefetch_a) {
             // pull the A block this CTA needs for its NEXT tile from HBM into L2 one tile ahead (it is first-touch there)
             const int nxt = dyn ? next : tile + tile_step;
@@ -658,7 +660,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         if (kCluster == 1) {
           if (!B_MN) {
-            tma_load_4d(sB, &tmB, &full_bar[stage], p.b_c0[b] + kb * BK, n_blk * BN, p.b_c2[b], p.b_c3[b]);
+            tma_load_4d(sB, &tmB, &full_bar[stage], p.b_c0[b] + kin, n_blk * BN, p.b_c2[b] + seg * p.b_c2_step[b], p.b_c3[b]);
           } else {
 #pragma unroll
             for (int c = 0; c < BN / 64; ++c)

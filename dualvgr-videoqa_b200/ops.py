@@ -953,3 +953,25 @@ def accuracy_counters(logits, answers, counts, category=None, tokens=None, token
                                       tokens.stride(0) if tokens is not None else 0, _ptr(token_to_cat), V, n_cat, _ptr(counts),
                                       _ptr(preds), _stream()), "dvgr_accuracy_counters")
     return preds
+
+
+# ------------------------------------------------------------------------------------- fp32 mode: 3 x bf16 split products
+def split3(x, out=None):
+    """fp32 [R, C] (last dim contiguous) -> bf16 planes [3, R, Cp] = [lo | hi | hi], Cp = C rounded up to 8."""
+    assert x.dtype == F32 and x.dim() == 2 and x.stride(1) == 1
+    R, C = x.shape
+    Cp = (C + 7) // 8 * 8
+    if out is None:
+        out = torch.empty((3, R, Cp), dtype=BF16, device=x.device)
+    assert out.is_contiguous() and tuple(out.shape) == (3, R, Cp)
+    _lib.check(_lib.split3(_ptr(x), x.stride(0), R, C, _ptr(out), Cp, _stream()), "dvgr_split3")
+    return out
+
+
+def gemm3(A3, a_major, B3, b_major, M, N, K, C, **kw):
+    """fp32-accurate product of two split operands (split3 planes, [3, rows, cols]): C (fp32) = act(A B^T + bias) (+ C).
+    K is the TRUE reduction length; operands as for gemm() (major 0: [rows, K], major 1: [K, rows])."""
+    assert C.dtype == F32 and A3.shape[0] == 3 and B3.shape[0] == 3
+    kin = (K + 63) // 64
+    return gemm(A3, a_major, B3, b_major, M, N, 3 * kin * 64, C, k_inner=kin, a_c2=[0], a_c2_step=[1], b_c2=[2], b_c2_step=[-1],
+                **kw)

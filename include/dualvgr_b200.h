@@ -367,6 +367,12 @@ int dvgr_lstm_pack_bias(const float* const* b_ih, const float* const* b_hh, int 
  * directions d_last0..D-1, may be null) -> dh_last [S][D*H]; everything else zero. */
 int dvgr_lstm_pack_dh(const void* d_seq, long long ld_seq, int nd_seq, const void* d_last, long long ld_last, int d_last0,
                       int S, int T, int D, int H, void* dh_seq, void* dh_last, void* stream);
+/* fp32 mode (1e-4 parity with the reference's fp32 path): an fp32 matrix [rows][cols] (row stride ld_in) as three bf16 planes
+ * out [3][rows][ld_out] = [lo | hi | hi], x = hi + lo (16 mantissa bits; ld_out % 8 == 0, padding columns zero). dvgr_gemm
+ * multiplies two such operands to fp32 accuracy in ONE launch: describe them as 3-D / 4-D operands with the plane on dims[2],
+ * K = 3 * k_inner * 64, k_inner = ceil(true reduction length / 64), A: a_c2 = 0, a_c2_step = +1, B: b_c2 = 2, b_c2_step = -1
+ * (a_lo b_hi + a_hi b_hi + a_hi b_lo), out_f32 = 1. Works for K-major and MN-major operands (forward, dgrad, wgrad). */
+int dvgr_split3(const float* in, long long ld_in, int rows, int cols, void* out, long long ld_out, void* stream);
 int dvgr_dropout(const void* in, void* out, long long n, float p, unsigned long long seed, unsigned int drop_stream,
                  void* stream);
 int dvgr_act_bwd(const void* dy, const void* y, void* out, long long n, int act, int accumulate, float p,

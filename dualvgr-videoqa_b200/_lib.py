@@ -185,6 +185,32 @@ sumsq_blocks = _sig("dvgr_sumsq_blocks", [])
 sumsq = _sig("dvgr_sumsq", [P, c_ll, P, P, P])
 adam_step = _sig("dvgr_adam_step", [P, P, P, P, c_ll, c_float, c_float, c_float, c_float, c_int, c_float, P, c_float, P, P, P])
 
+
+class Lstm32Args(ctypes.Structure):
+    _fields_ = [("S", c_int), ("H", c_int), ("T", c_int), ("ndir", c_int), ("s", c_int),
+                ("gates", c_void_p), ("rec", c_void_p), ("h", c_void_p), ("c_hist", c_void_p), ("h_planes", c_void_p),
+                ("hprev_t", c_void_p), ("seq_out", c_void_p), ("seq_out_ld", c_ll), ("h_last", c_void_p), ("h_last_ld", c_ll),
+                ("seq_len", c_void_p), ("dh", c_void_p), ("dc", c_void_p), ("dgate_planes", c_void_p),
+                ("dh_last", c_void_p), ("dh_last_ld", c_ll), ("dh_seq", c_void_p), ("dh_seq_ld", c_ll)]
+
+
+lstm32_cell_fwd = _sig("dvgr_lstm32_cell_fwd", [ctypes.POINTER(Lstm32Args), P])
+lstm32_cell_bwd = _sig("dvgr_lstm32_cell_bwd", [ctypes.POINTER(Lstm32Args), P])
+
+# fp32-activation variants (fp32 mode): the same sources compiled a second time with act_t = float export every
+# entry point below under the suffix _f32 with an identical signature (every bf16 activation pointer is a float pointer)
+F32_VARIANTS = ["gat_attn_fwd", "gat_attn_bwd", "qattn_fwd", "qattn_bwd", "gate_fwd", "gate_bwd", "view_attn_fwd",
+                "view_attn_bwd", "mfb_fwd", "mfb_bwd", "readout_fwd", "readout_bwd", "bn_fwd_ex", "bn_bwd_ex",
+                "prep_features_ex", "dropout", "act_bwd", "add", "embed_fwd", "embed_bwd"]
+for _n in F32_VARIANTS:
+    globals()[_n + "_f32"] = _sig("dvgr_" + _n + "_f32", list(globals()[_n].argtypes))
+
+
+def variant(name, f32):
+    """The entry point `name` for bf16 (f32 False) or fp32 activations."""
+    return globals()[name + "_f32"] if f32 else globals()[name]
+
+
 EXPORTED = [
     "dvgr_last_error", "dvgr_abi_version", "dvgr_launch_count", "dvgr_set_seed_offset", "dvgr_gemm", "dvgr_gemm_reference", "dvgr_wgrad_grouped",
     "dvgr_lstm_step_fwd", "dvgr_lstm_step_bwd", "dvgr_lstm_seq_fwd", "dvgr_lstm_seq_sync_words", "dvgr_lstm_seq_bwd", "dvgr_gat_attn_fwd", "dvgr_gat_attn_bwd", "dvgr_qattn_fwd",
@@ -194,5 +220,5 @@ EXPORTED = [
     "dvgr_act_bwd", "dvgr_add", "dvgr_scatter", "dvgr_colsum_workspace", "dvgr_colsum", "dvgr_colsum_batched", "dvgr_colsum_grouped", "dvgr_sumsq_blocks", "dvgr_sumsq",
     "dvgr_adam_step", "dvgr_dropout_multi", "dvgr_gat_input_bwd", "dvgr_embed_fwd", "dvgr_embed_bwd",
     "dvgr_view_attn_fwd_multi", "dvgr_view_attn_bwd_multi", "dvgr_cast_rows_grouped", "dvgr_lstm_pack_bias",
-    "dvgr_lstm_pack_dh", "dvgr_finalize_loss", "dvgr_bn_stats", "dvgr_bn_fwd_ex", "dvgr_bn_bwd_ex", "dvgr_cross_entropy_ex", "dvgr_accuracy_counters", "dvgr_split3",
-]
+    "dvgr_lstm_pack_dh", "dvgr_finalize_loss", "dvgr_bn_stats", "dvgr_bn_fwd_ex", "dvgr_bn_bwd_ex", "dvgr_cross_entropy_ex", "dvgr_accuracy_counters", "dvgr_split3", "dvgr_lstm32_cell_fwd", "dvgr_lstm32_cell_bwd",
+] + ["dvgr_" + _n + "_f32" for _n in F32_VARIANTS]

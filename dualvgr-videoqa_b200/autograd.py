@@ -12,6 +12,10 @@ from . import ops
 
 BF16, F32 = torch.bfloat16, torch.float32
 
+# activation dtype of the model mirror: bf16 (default, the fast path) or fp32 (DualVGR.set_precision("fp32"): fp32_path.py).
+# The Functions below dispatch on the dtype of the tensors they are given; module code casts its inputs to ACT[0].
+ACT = [BF16]
+
 # ---------------------------------------------------------------------------------------------------------------------
 # dropout bookkeeping: one seed per forward pass, one stream id per dropout site (regenerated, never stored)
 # ---------------------------------------------------------------------------------------------------------------------
@@ -317,6 +321,9 @@ class LinearCatFn(Function):
 
 
 def linear_cat(x, w1, b1, w2, b2):
+    if x.dtype == F32:
+        from . import fp32_path
+        return fp32_path.linear_cat32(x, w1, b1, w2, b2)
     return LinearCatFn.apply(x, w1, b1, w2, b2)
 
 
@@ -335,6 +342,12 @@ def _route_small(param, grad):
 def linear(x, weight, bias=None, act=None, out_f32=False, act_grad_folded=False, out=None):
     """act_grad_folded: the consumer's backward kernel already returns d(pre-activation) (view attention, MFB pair-sum,
     read-out fold act' into their own pass), so this backward must not apply act' again."""
+    if x.dtype == F32:          # fp32 mode: 3 x bf16 split products (fp32_path.Linear32Fn); `out` slots are a bf16-path layout
+        from . import fp32_path
+        y = fp32_path.linear32(x, weight, bias, act, act_grad_folded)
+        if out is not None:
+            raise ValueError("preallocated output slots are not supported in fp32 mode")
+        return y
     return LinearFn.apply(x, weight, bias, act, out_f32, act_grad_folded, (out,) if out is not None else None)
 
 
@@ -795,7 +808,7 @@ class ViewAttnFn(Function):
         hidden, z, w2v, beta = ctx.saved_tensors
         D = z.shape[-1]
         if dxnew is None:
-            dxnew = torch.zeros(z.shape[1:], dtype=BF16, device=z.device)
+            dxnew = torch.zeros(z.shape[1:], dtype=z.dtype, device=z.device)
         dxn = _c(dxnew).view(-1, D)
         de = _c(dembed).view(-1, D) if dembed is not None else None
         dz, dhid, dw2 = ops.view_attn_bwd(dxn, de, hidden, z, w2v, beta)
@@ -854,20 +867,22 @@ class BatchNormFn(Function):
             ext = ops.bn_stats(x)
             dist.all_reduce(ext, op=dist.ReduceOp.SUM, group=sync[0])
             Btot = x.shape[0] * sync[1]
-        y, mean, rstd = ops.bn_fwd(x, gamma.detach(), beta.detach(), run_mean, run_var, training, momentum, eps, ext, Btot)
+        y, mean, rstd = ops.bn_fwd(x, gamma.detach(), beta.detach(), run_mean, run_var, training, momentum, eps, ext, Btot,
+                                   out_dtype=ACT[0])
         ctx.save_for_backward(x, gamma.detach(), mean, rstd)
         ctx.training = training
         ctx.affine = (gamma, beta)
         ctx.sync = sync if (training and sync is not None) else None
         ctx.Btot = Btot
+        ctx.ydt = y.dtype
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, gamma, mean, rstd = ctx.saved_tensors
         dy = _c(dy)
-        if dy.dtype != BF16:
-            dy = dy.to(BF16)
+        if dy.dtype != ctx.ydt:
+            dy = dy.to(ctx.ydt)
         if ctx.sync is not None:
             import torch.distributed as dist
             _, dg, db = ops.bn_bwd(dy, x, gamma, mean, rstd, True, stats_only=True)      # LOCAL sums = this rank's dgamma / dbeta

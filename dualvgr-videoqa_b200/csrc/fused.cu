@@ -3,32 +3,22 @@
 // backward, column sums). Each is a single pass over its operands with 128-bit accesses and warp-shuffle reductions.
 #include <cuda_bf16.h>
 
+#include "act.cuh"
 #include "capi_internal.h"
 #include "ptx.cuh"
 #include "rng.cuh"
 
+// (compiled twice, see act.cuh: `bf16` below is the build's activation storage type — __nv_bfloat16, or float in the
+//  -DDVGR_F32 build whose entry points carry the suffix _f32; types that must be bf16 in BOTH builds are spelled out)
 namespace dvgr {
+namespace DVGR_VNS {
 
-typedef __nv_bfloat16 bf16;
+typedef act_t bf16;
 
-__device__ __forceinline__ void load8(const bf16* p, float (&f)[8]) {
-  uint4 v = *reinterpret_cast<const uint4*>(p);
-  const uint32_t* w = reinterpret_cast<const uint32_t*>(&v);
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    float2 t = unpack_bf16x2(w[q]);
-    f[2 * q] = t.x;
-    f[2 * q + 1] = t.y;
-  }
-}
-__device__ __forceinline__ void load8g(const bf16* p, float (&f)[8]);
-__device__ __forceinline__ void load8g(const float* p, float (&f)[8]);
-__device__ __forceinline__ void store8(bf16* p, const float (&f)[8]) {
-  uint4 o;
-  o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
-  o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
-  *reinterpret_cast<uint4*>(p) = o;
-}
+__device__ __forceinline__ void load8(const bf16* p, float (&f)[8]) { act::ld8(p, f); }
+__device__ __forceinline__ void load8g(const __nv_bfloat16* p, float (&f)[8]) { act::ld8(p, f); }
+__device__ __forceinline__ void load8g(const float* p, float (&f)[8]) { act::ld8(p, f); }
+__device__ __forceinline__ void store8(bf16* p, const float (&f)[8]) { act::st8(p, f); }
 
 // =============================================================================================== view attention
 // reference model/Attention.py:20-23 on the stack of model/models.py:163-166, + the residual of :168-169.
@@ -194,10 +184,8 @@ __global__ void mfb_fwd_kernel(const bf16* __restrict__ x0, const bf16* __restri
     float a[8], b[8];
     load8(x0 + i * 8, a);
     load8(x1 + i * 8, b);
-    uint2 o;
-    o.x = pack_bf16x2(a[0] * b[0] + a[1] * b[1], a[2] * b[2] + a[3] * b[3]);
-    o.y = pack_bf16x2(a[4] * b[4] + a[5] * b[5], a[6] * b[6] + a[7] * b[7]);
-    *reinterpret_cast<uint2*>(z + i * 4) = o;
+    act::st2(z + i * 4, a[0] * b[0] + a[1] * b[1], a[2] * b[2] + a[3] * b[3]);
+    act::st2(z + i * 4 + 2, a[4] * b[4] + a[5] * b[5], a[6] * b[6] + a[7] * b[7]);
   }
 }
 // dz -> dpre0 = dz_pair * x1 * ELU'(x0), dpre1 = dz_pair * x0 * ELU'(x1)
@@ -208,8 +196,7 @@ __global__ void mfb_bwd_kernel(const bf16* __restrict__ dz, const bf16* __restri
     float a[8], b[8], oa[8], ob[8];
     load8(x0 + i * 8, a);
     load8(x1 + i * 8, b);
-    uint2 dv = *reinterpret_cast<const uint2*>(dz + i * 4);
-    float2 d01 = unpack_bf16x2(dv.x), d23 = unpack_bf16x2(dv.y);
+    const float2 d01 = act::ld2(dz + i * 4), d23 = act::ld2(dz + i * 4 + 2);
     const float d[4] = {d01.x, d01.y, d23.x, d23.y};
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
@@ -261,11 +248,11 @@ readout_fwd_kernel(const bf16* __restrict__ v, const bf16* __restrict__ u, const
   for (int k = threadIdx.x * 2; k < D; k += 512) {
     float ax = 0.f, ay = 0.f;
     for (int n = 0; n < N; ++n) {
-      const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(v + ((long long)b * N + n) * D + k));
+      const float2 x = act::ld2(v + ((long long)b * N + n) * D + k);
       ax += sc[n] * x.x;
       ay += sc[n] * x.y;
     }
-    *reinterpret_cast<__nv_bfloat162*>(pooled + (long long)b * ld_p + k) = __floats2bfloat162_rn(ax, ay);
+    act::st2(pooled + (long long)b * ld_p + k, ax, ay);
   }
 }
 
@@ -312,17 +299,16 @@ readout_bwd_kernel(const bf16* __restrict__ dpooled, long long ld_p, const bf16*
   }
   __syncthreads();
   for (int k = threadIdx.x * 2; k < D; k += 512) {
-    const float2 g = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dp + k));
+    const float2 g = act::ld2(dp + k);
     const float w0 = w[k], w1 = w[k + 1];
     float dwx = 0.f, dwy = 0.f;
     for (int n = 0; n < N; ++n) {
       const long long off = ((long long)b * N + n) * D + k;
-      *reinterpret_cast<__nv_bfloat162*>(dv + off) = __floats2bfloat162_rn(al[n] * g.x, al[n] * g.y);
-      const float2 uu = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(u + off));
+      act::st2(dv + off, al[n] * g.x, al[n] * g.y);
+      const float2 uu = act::ld2(u + off);
       dwx += da[n] * uu.x;
       dwy += da[n] * uu.y;
-      *reinterpret_cast<__nv_bfloat162*>(du + off) =
-          __floats2bfloat162_rn(da[n] * w0 * elu_grad_from_out(uu.x), da[n] * w1 * elu_grad_from_out(uu.y));
+      act::st2(du + off, da[n] * w0 * elu_grad_from_out(uu.x), da[n] * w1 * elu_grad_from_out(uu.y));
     }
     dw_part[(long long)b * D + k] = dwx;
     dw_part[(long long)b * D + k + 1] = dwy;
@@ -394,7 +380,7 @@ bn_fwd_kernel(const TX* __restrict__ x, int B, int D, const float* __restrict__ 
   }
   const float g = gamma[c], bt = betap[c];
   for (int r = rl; r < B; r += 8)
-    y[(long long)r * D + c] = __float2bfloat16_rn((ldf<TX>(x + (long long)r * D + c) - mean) * rstd * g + bt);
+    act::st1(y + (long long)r * D + c, (ldf<TX>(x + (long long)r * D + c) - mean) * rstd * g + bt);
 }
 
 // per-column (sum, sum of squares) of the local batch: out [2][D] (the operand of the SyncBN all-reduce)
@@ -435,7 +421,7 @@ bn_bwd_kernel(const bf16* __restrict__ dy, const TX* __restrict__ x, int B, int 
   float sdy = 0.f, sdyx = 0.f;
   if (ok)
     for (int r = rl; r < B; r += 8) {
-      const float d = __bfloat162float(dy[(long long)r * D + c]);
+      const float d = act::ld1(dy + (long long)r * D + c);
       const float xh = (ldf<TX>(x + (long long)r * D + c) - m) * rs;
       sdy += d;
       sdyx += d * xh;
@@ -455,7 +441,7 @@ bn_bwd_kernel(const bf16* __restrict__ dy, const TX* __restrict__ x, int B, int 
     nb = (float)Btot;
   }
   for (int r = rl; r < B; r += 8) {
-    const float d = __bfloat162float(dy[(long long)r * D + c]);
+    const float d = act::ld1(dy + (long long)r * D + c);
     const float xh = (ldf<TX>(x + (long long)r * D + c) - m) * rs;
     const float o = training ? g * rs * (d - sdy / nb - xh * sdyx / nb) : g * rs * d;
     stf<TX>(dx + (long long)r * D + c, o);
@@ -546,8 +532,6 @@ __global__ void accuracy_counters_kernel(const float* __restrict__ logits, const
 }
 
 // =============================================================================================== streaming helpers
-__device__ __forceinline__ void load8g(const bf16* p, float (&f)[8]);
-__device__ __forceinline__ void load8g(const float* p, float (&f)[8]);
 // Appearance prologue, reference model/Preprocessing.py:220-223: tanh(dropout(x)) and the [B,N,F,C] -> [F, B*N, C]
 // re-layout (two full transposed copies in the reference) fused with the fp32 -> bf16 cast in ONE pass.
 // TIN = float (the reference's feature format) or bf16 (features stored / shipped as bf16: half the host-to-device bytes)
@@ -909,11 +893,6 @@ __global__ void add_kernel(bf16* __restrict__ a, const bf16* __restrict__ b, lon
 // Block = 32 column groups (8 columns each, one 128-bit / 2x128-bit load per row) x 8 row lanes; every thread keeps
 // 4 independent row loads in flight (the first version issued one dependent 2-byte load per iteration and was
 // latency-bound at ~1 % of HBM bandwidth on the [81920, 3072] LSTM bias gradient).
-__device__ __forceinline__ void load8g(const bf16* p, float (&f)[8]) { load8(p, f); }
-__device__ __forceinline__ void load8g(const float* p, float (&f)[8]) {
-  const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
-  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
-}
 template <typename T>
 __global__ void __launch_bounds__(256)
 colsum_partial_kernel(const T* __restrict__ in, long long ld, long long R, int C, int rows_per_chunk,
@@ -1003,14 +982,16 @@ static inline int grid_for(long long n, int threads = 256, int max_blocks = 148 
   return (int)std::min<long long>(b, max_blocks);
 }
 
+}  // namespace DVGR_VNS
 }  // namespace dvgr
 
 using namespace dvgr;
+using namespace dvgr::DVGR_VNS;
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
 #define BF(p) reinterpret_cast<bf16*>(p)
 #define CBF(p) reinterpret_cast<const bf16*>(p)
 
-extern "C" int dvgr_view_attn_fwd_multi(const void* hidden, const void* z, const void* x, const float* w2, long long M,
+extern "C" int DVGR_FN(dvgr_view_attn_fwd_multi)(const void* hidden, const void* z, const void* x, const float* w2, long long M,
                                         int D, int n_streams, void* xnew, void* embed, float* beta, void* stream) {
   if (M <= 0 || n_streams <= 0) return 0;
   if (D % 8 != 0) return set_error("view_attn: D=%d must be a multiple of 8", D);
@@ -1019,31 +1000,31 @@ extern "C" int dvgr_view_attn_fwd_multi(const void* hidden, const void* z, const
   DVGR_CHECK_LAUNCH("view_attn_fwd");
   return 0;
 }
-extern "C" int dvgr_view_attn_fwd(const void* hidden, const void* z, const void* x, const float* w2, long long M, int D,
+extern "C" int DVGR_FN(dvgr_view_attn_fwd)(const void* hidden, const void* z, const void* x, const float* w2, long long M, int D,
                                   void* xnew, void* embed, float* beta, void* stream) {
-  return dvgr_view_attn_fwd_multi(hidden, z, x, w2, M, D, 1, xnew, embed, beta, stream);
+  return DVGR_FN(dvgr_view_attn_fwd_multi)(hidden, z, x, w2, M, D, 1, xnew, embed, beta, stream);
 }
 
-extern "C" int dvgr_view_attn_bwd_blocks(long long M) { return grid_for(M, 8, 148 * 2); }
+extern "C" int DVGR_FN(dvgr_view_attn_bwd_blocks)(long long M) { return grid_for(M, 8, 148 * 2); }
 
-extern "C" int dvgr_view_attn_bwd_multi(const void* dxnew, const void* dembed_ext, const void* hidden, const void* z,
+extern "C" int DVGR_FN(dvgr_view_attn_bwd_multi)(const void* dxnew, const void* dembed_ext, const void* hidden, const void* z,
                                         const float* w2, const float* beta, long long M, int D, int n_streams, void* dz,
                                         void* dhid, float* dw2_part, void* stream) {
   if (M <= 0 || n_streams <= 0) return 0;
   if (D % 8 != 0) return set_error("view_attn: D=%d must be a multiple of 8", D);
-  const int blocks = dvgr_view_attn_bwd_blocks(M);
+  const int blocks = DVGR_FN(dvgr_view_attn_bwd_blocks)(M);
   view_attn_bwd_kernel<<<dim3(blocks, n_streams), 256, D * sizeof(float), ST(stream)>>>(
       CBF(dxnew), CBF(dembed_ext), CBF(hidden), CBF(z), w2, beta, M, D, BF(dz), BF(dhid), dw2_part);
   DVGR_CHECK_LAUNCH("view_attn_bwd");
   return 0;
 }
-extern "C" int dvgr_view_attn_bwd(const void* dxnew, const void* dembed_ext, const void* hidden, const void* z,
+extern "C" int DVGR_FN(dvgr_view_attn_bwd)(const void* dxnew, const void* dembed_ext, const void* hidden, const void* z,
                                   const float* w2, const float* beta, long long M, int D, void* dz, void* dhid,
                                   float* dw2_part, void* stream) {
-  return dvgr_view_attn_bwd_multi(dxnew, dembed_ext, hidden, z, w2, beta, M, D, 1, dz, dhid, dw2_part, stream);
+  return DVGR_FN(dvgr_view_attn_bwd_multi)(dxnew, dembed_ext, hidden, z, w2, beta, M, D, 1, dz, dhid, dw2_part, stream);
 }
 
-extern "C" int dvgr_mfb_fwd(const void* x0, const void* x1, void* z, long long M, int mm2, void* stream) {
+extern "C" int DVGR_FN(dvgr_mfb_fwd)(const void* x0, const void* x1, void* z, long long M, int mm2, void* stream) {
   if (mm2 % 8 != 0) return set_error("mfb: 2*mm_dim=%d must be a multiple of 8", mm2);
   const long long n = M * mm2 / 8;
   if (n <= 0) return 0;
@@ -1051,7 +1032,7 @@ extern "C" int dvgr_mfb_fwd(const void* x0, const void* x1, void* z, long long M
   DVGR_CHECK_LAUNCH("mfb_fwd");
   return 0;
 }
-extern "C" int dvgr_mfb_bwd(const void* dz, const void* x0, const void* x1, void* d0, void* d1, long long M, int mm2,
+extern "C" int DVGR_FN(dvgr_mfb_bwd)(const void* dz, const void* x0, const void* x1, void* d0, void* d1, long long M, int mm2,
                             void* stream) {
   if (mm2 % 8 != 0) return set_error("mfb: 2*mm_dim=%d must be a multiple of 8", mm2);
   const long long n = M * mm2 / 8;
@@ -1061,7 +1042,7 @@ extern "C" int dvgr_mfb_bwd(const void* dz, const void* x0, const void* x1, void
   return 0;
 }
 
-extern "C" int dvgr_readout_fwd(const void* v, const void* u, const float* w, const float* c, int B, int N, int D,
+extern "C" int DVGR_FN(dvgr_readout_fwd)(const void* v, const void* u, const float* w, const float* c, int B, int N, int D,
                                 float* alpha, void* pooled, long long ld_p, void* stream) {
   if (B <= 0) return 0;
   if (N > 64) return set_error("readout: N=%d > 64", N);
@@ -1070,7 +1051,7 @@ extern "C" int dvgr_readout_fwd(const void* v, const void* u, const float* w, co
   DVGR_CHECK_LAUNCH("readout_fwd");
   return 0;
 }
-extern "C" int dvgr_readout_bwd(const void* dpooled, long long ld_p, const void* v, const void* u, const float* w,
+extern "C" int DVGR_FN(dvgr_readout_bwd)(const void* dpooled, long long ld_p, const void* v, const void* u, const float* w,
                                 const float* alpha, int B, int N, int D, void* dv, void* du, float* dw_part,
                                 float* dc_part, void* stream) {
   if (B <= 0) return 0;
@@ -1082,7 +1063,7 @@ extern "C" int dvgr_readout_bwd(const void* dpooled, long long ld_p, const void*
   return 0;
 }
 
-extern "C" int dvgr_bn_fwd_ex(const void* x, int x_is_f32, int B, int D, const float* gamma, const float* beta,
+extern "C" int DVGR_FN(dvgr_bn_fwd_ex)(const void* x, int x_is_f32, int B, int D, const float* gamma, const float* beta,
                               float* run_mean, float* run_var, int training, float momentum, float eps, void* y,
                               float* mean_out, float* rstd_out, const float* ext_stats, int Btot, void* stream) {
   if (B <= 0 || D <= 0) return 0;
@@ -1097,20 +1078,20 @@ extern "C" int dvgr_bn_fwd_ex(const void* x, int x_is_f32, int B, int D, const f
   DVGR_CHECK_LAUNCH("bn_fwd");
   return 0;
 }
-extern "C" int dvgr_bn_fwd(const void* x, int x_is_f32, int B, int D, const float* gamma, const float* beta,
+extern "C" int DVGR_FN(dvgr_bn_fwd)(const void* x, int x_is_f32, int B, int D, const float* gamma, const float* beta,
                            float* run_mean, float* run_var, int training, float momentum, float eps, void* y,
                            float* mean_out, float* rstd_out, void* stream) {
-  return dvgr_bn_fwd_ex(x, x_is_f32, B, D, gamma, beta, run_mean, run_var, training, momentum, eps, y, mean_out, rstd_out,
+  return DVGR_FN(dvgr_bn_fwd_ex)(x, x_is_f32, B, D, gamma, beta, run_mean, run_var, training, momentum, eps, y, mean_out, rstd_out,
                         nullptr, B, stream);
 }
-extern "C" int dvgr_bn_stats(const void* x, int x_is_f32, int B, int D, float* out, void* stream) {
+extern "C" int DVGR_FN(dvgr_bn_stats)(const void* x, int x_is_f32, int B, int D, float* out, void* stream) {
   if (B <= 0 || D <= 0) return 0;
   if (x_is_f32) bn_stats_kernel<float><<<(D + 31) / 32, 256, 0, ST(stream)>>>(reinterpret_cast<const float*>(x), B, D, out);
   else bn_stats_kernel<bf16><<<(D + 31) / 32, 256, 0, ST(stream)>>>(CBF(x), B, D, out);
   DVGR_CHECK_LAUNCH("bn_stats");
   return 0;
 }
-extern "C" int dvgr_bn_bwd_ex(const void* dy, const void* x, int x_is_f32, int B, int D, const float* gamma,
+extern "C" int DVGR_FN(dvgr_bn_bwd_ex)(const void* dy, const void* x, int x_is_f32, int B, int D, const float* gamma,
                               const float* mean, const float* rstd, int training, void* dx, float* dgamma, float* dbeta,
                               const float* ext_sums, int Btot, int stats_only, void* stream) {
   if (B <= 0 || D <= 0) return 0;
@@ -1124,13 +1105,13 @@ extern "C" int dvgr_bn_bwd_ex(const void* dy, const void* x, int x_is_f32, int B
   DVGR_CHECK_LAUNCH("bn_bwd");
   return 0;
 }
-extern "C" int dvgr_bn_bwd(const void* dy, const void* x, int x_is_f32, int B, int D, const float* gamma,
+extern "C" int DVGR_FN(dvgr_bn_bwd)(const void* dy, const void* x, int x_is_f32, int B, int D, const float* gamma,
                            const float* mean, const float* rstd, int training, void* dx, float* dgamma, float* dbeta,
                            void* stream) {
-  return dvgr_bn_bwd_ex(dy, x, x_is_f32, B, D, gamma, mean, rstd, training, dx, dgamma, dbeta, nullptr, B, 0, stream);
+  return DVGR_FN(dvgr_bn_bwd_ex)(dy, x, x_is_f32, B, D, gamma, mean, rstd, training, dx, dgamma, dbeta, nullptr, B, 0, stream);
 }
 
-extern "C" int dvgr_cross_entropy_ex(const float* logits, const long long* answers, int B, int A, float scale,
+extern "C" int DVGR_FN(dvgr_cross_entropy_ex)(const float* logits, const long long* answers, int B, int A, float scale,
                                      float* loss_part, void* dlogits, int grad_is_f32, long long ld_d, int* correct,
                                      void* stream) {
   if (B <= 0) return 0;
@@ -1142,12 +1123,12 @@ extern "C" int dvgr_cross_entropy_ex(const float* logits, const long long* answe
   DVGR_CHECK_LAUNCH("cross_entropy");
   return 0;
 }
-extern "C" int dvgr_cross_entropy(const float* logits, const long long* answers, int B, int A, float scale,
+extern "C" int DVGR_FN(dvgr_cross_entropy)(const float* logits, const long long* answers, int B, int A, float scale,
                                   float* loss_part, void* dlogits, long long ld_d, int* correct, void* stream) {
-  return dvgr_cross_entropy_ex(logits, answers, B, A, scale, loss_part, dlogits, 0, ld_d, correct, stream);
+  return DVGR_FN(dvgr_cross_entropy_ex)(logits, answers, B, A, scale, loss_part, dlogits, 0, ld_d, correct, stream);
 }
 
-extern "C" int dvgr_accuracy_counters(const float* logits, const long long* answers, int B, int A, const long long* category,
+extern "C" int DVGR_FN(dvgr_accuracy_counters)(const float* logits, const long long* answers, int B, int A, const long long* category,
                                       const long long* tokens, long long ld_tok, const int* token_to_cat, int V, int n_cat,
                                       long long* counts, int* preds, void* stream) {
   if (B <= 0) return 0;
@@ -1159,7 +1140,7 @@ extern "C" int dvgr_accuracy_counters(const float* logits, const long long* answ
   return 0;
 }
 
-extern "C" int dvgr_prep_features_ex(const void* in, int in_is_bf16, void* out, long long S, int T, int C, int do_tanh,
+extern "C" int DVGR_FN(dvgr_prep_features_ex)(const void* in, int in_is_bf16, void* out, long long S, int T, int C, int do_tanh,
                                      int time_major, float p, unsigned long long seed, unsigned int drop_stream,
                                      void* stream) {
   if (C % 8 != 0) return set_error("prep_features: C=%d must be a multiple of 8", C);
@@ -1167,7 +1148,7 @@ extern "C" int dvgr_prep_features_ex(const void* in, int in_is_bf16, void* out, 
   if (n <= 0) return 0;
   DropoutCfg dc{seed, drop_stream, p, seed_offset_ptr()};
   if (in_is_bf16)
-    prep_features_kernel<bf16><<<grid_for(n, 256, 148 * 32), 256, 0, ST(stream)>>>(CBF(in), BF(out), S, T, C, do_tanh, time_major, dc);
+    prep_features_kernel<__nv_bfloat16><<<grid_for(n, 256, 148 * 32), 256, 0, ST(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(in), BF(out), S, T, C, do_tanh, time_major, dc);
   else
     prep_features_kernel<float><<<grid_for(n, 256, 148 * 32), 256, 0, ST(stream)>>>(reinterpret_cast<const float*>(in), BF(out), S, T, C,
                                                                                     do_tanh, time_major, dc);
@@ -1175,12 +1156,12 @@ extern "C" int dvgr_prep_features_ex(const void* in, int in_is_bf16, void* out, 
   return 0;
 }
 
-extern "C" int dvgr_prep_features(const float* in, void* out, long long S, int T, int C, int do_tanh, int time_major,
+extern "C" int DVGR_FN(dvgr_prep_features)(const float* in, void* out, long long S, int T, int C, int do_tanh, int time_major,
                                   float p, unsigned long long seed, unsigned int drop_stream, void* stream) {
-  return dvgr_prep_features_ex(in, 0, out, S, T, C, do_tanh, time_major, p, seed, drop_stream, stream);
+  return DVGR_FN(dvgr_prep_features_ex)(in, 0, out, S, T, C, do_tanh, time_major, p, seed, drop_stream, stream);
 }
 
-extern "C" int dvgr_cast_rows(const float* in, long long ld_in, void* out, long long ld_out, int rows, int cols,
+extern "C" int DVGR_FN(dvgr_cast_rows)(const float* in, long long ld_in, void* out, long long ld_out, int rows, int cols,
                               int out_cols, int lstm_H, void* stream) {
   const long long n = (long long)rows * out_cols;
   if (n <= 0) return 0;
@@ -1190,7 +1171,7 @@ extern "C" int dvgr_cast_rows(const float* in, long long ld_in, void* out, long 
   return 0;
 }
 
-extern "C" int dvgr_split3(const float* in, long long ld_in, int rows, int cols, void* out, long long ld_out, void* stream) {
+extern "C" int DVGR_FN(dvgr_split3)(const float* in, long long ld_in, int rows, int cols, void* out, long long ld_out, void* stream) {
   if (rows <= 0 || cols <= 0) return 0;
   if (!in || !out) return set_error("split3: null buffer");
   if (ld_out % 8 != 0 || ld_out < cols) return set_error("split3: ld_out=%lld must be a multiple of 8 and >= cols=%d", ld_out, cols);
@@ -1200,7 +1181,7 @@ extern "C" int dvgr_split3(const float* in, long long ld_in, int rows, int cols,
   return 0;
 }
 
-extern "C" int dvgr_dropout(const void* in, void* out, long long n, float p, unsigned long long seed,
+extern "C" int DVGR_FN(dvgr_dropout)(const void* in, void* out, long long n, float p, unsigned long long seed,
                             unsigned int drop_stream, void* stream) {
   if (n % 8 != 0) return set_error("dropout: n=%lld must be a multiple of 8", n);
   if (n <= 0) return 0;
@@ -1211,7 +1192,7 @@ extern "C" int dvgr_dropout(const void* in, void* out, long long n, float p, uns
 }
 
 
-extern "C" int dvgr_dropout_multi(const void* const* in, void* const* out, const unsigned int* drop_streams, int n_copies,
+extern "C" int DVGR_FN(dvgr_dropout_multi)(const void* const* in, void* const* out, const unsigned int* drop_streams, int n_copies,
                                   long long n, float p, unsigned long long seed, void* stream) {
   if (n % 8 != 0) return set_error("dropout_multi: n=%lld must be a multiple of 8", n);
   if (n_copies < 1 || n_copies > 4) return set_error("dropout_multi: n_copies=%d out of range [1,4]", n_copies);
@@ -1228,7 +1209,7 @@ extern "C" int dvgr_dropout_multi(const void* const* in, void* const* out, const
   return 0;
 }
 
-extern "C" int dvgr_gat_input_bwd(const void* const* dxt, const unsigned int* drop_streams, int n_streams, int per_stream,
+extern "C" int DVGR_FN(dvgr_gat_input_bwd)(const void* const* dxt, const unsigned int* drop_streams, int n_streams, int per_stream,
                                   const void* const* base, void* const* out, long long n, float p, unsigned long long seed,
                                   void* stream) {
   if (n % 8 != 0) return set_error("gat_input_bwd: n=%lld must be a multiple of 8", n);
@@ -1252,7 +1233,7 @@ extern "C" int dvgr_gat_input_bwd(const void* const* dxt, const unsigned int* dr
   return 0;
 }
 
-extern "C" int dvgr_embed_fwd(const long long* tokens, const float* table, int B, int L, int W, int Wp, void* words,
+extern "C" int DVGR_FN(dvgr_embed_fwd)(const long long* tokens, const float* table, int B, int L, int W, int Wp, void* words,
                               void* x_tm, float p, unsigned long long seed, unsigned int drop_stream, void* stream) {
   if (B <= 0 || L <= 0) return 0;
   if (Wp % 8 != 0 || Wp < W) return set_error("embed: Wp=%d must be a multiple of 8 and >= W=%d", Wp, W);
@@ -1262,7 +1243,7 @@ extern "C" int dvgr_embed_fwd(const long long* tokens, const float* table, int B
   DVGR_CHECK_LAUNCH("embed_fwd");
   return 0;
 }
-extern "C" int dvgr_embed_bwd(const long long* tokens, const void* words, const void* d_words, const void* d_x_tm, int B,
+extern "C" int DVGR_FN(dvgr_embed_bwd)(const long long* tokens, const void* words, const void* d_words, const void* d_x_tm, int B,
                               int L, int W, int Wp, float* dtable, float p, unsigned long long seed,
                               unsigned int drop_stream, void* stream) {
   if (B <= 0 || L <= 0) return 0;
@@ -1274,7 +1255,7 @@ extern "C" int dvgr_embed_bwd(const long long* tokens, const void* words, const 
   return 0;
 }
 
-extern "C" int dvgr_cast_rows_grouped(const float* const* in, const long long* ld_in, void* const* out, const int* rows,
+extern "C" int DVGR_FN(dvgr_cast_rows_grouped)(const float* const* in, const long long* ld_in, void* const* out, const int* rows,
                                       const int* cols, int n, long long ld_out, int out_cols, int lstm_H, void* stream) {
   if (n <= 0) return 0;
   if (n > kMaxCast) return set_error("cast_rows_grouped: n=%d > %d", n, kMaxCast);
@@ -1294,7 +1275,7 @@ extern "C" int dvgr_cast_rows_grouped(const float* const* in, const long long* l
   return 0;
 }
 
-extern "C" int dvgr_lstm_pack_bias(const float* const* b_ih, const float* const* b_hh, int ndir, int H, float* out,
+extern "C" int DVGR_FN(dvgr_lstm_pack_bias)(const float* const* b_ih, const float* const* b_hh, int ndir, int H, float* out,
                                    void* stream) {
   if (ndir < 1 || ndir > 4) return set_error("lstm_pack_bias: ndir=%d out of range [1,4]", ndir);
   BiasGroup G;
@@ -1308,7 +1289,7 @@ extern "C" int dvgr_lstm_pack_bias(const float* const* b_ih, const float* const*
   return 0;
 }
 
-extern "C" int dvgr_lstm_pack_dh(const void* d_seq, long long ld_seq, int nd_seq, const void* d_last, long long ld_last,
+extern "C" int DVGR_FN(dvgr_lstm_pack_dh)(const void* d_seq, long long ld_seq, int nd_seq, const void* d_last, long long ld_last,
                                  int d_last0, int S, int T, int D, int H, void* dh_seq, void* dh_last, void* stream) {
   if (S <= 0 || T <= 0 || D <= 0) return 0;
   if (H % 8 != 0 || ld_seq % 8 != 0 || ld_last % 8 != 0) return set_error("lstm_pack_dh: H and row strides must be multiples of 8");
@@ -1319,7 +1300,7 @@ extern "C" int dvgr_lstm_pack_dh(const void* d_seq, long long ld_seq, int nd_seq
   return 0;
 }
 
-extern "C" int dvgr_act_bwd(const void* dy, const void* y, void* out, long long n, int act, int accumulate, float p,
+extern "C" int DVGR_FN(dvgr_act_bwd)(const void* dy, const void* y, void* out, long long n, int act, int accumulate, float p,
                             unsigned long long seed, unsigned int drop_stream, void* stream) {
   if (n % 8 != 0) return set_error("act_bwd: n=%lld must be a multiple of 8", n);
   if (n <= 0) return 0;
@@ -1333,6 +1314,7 @@ extern "C" int dvgr_act_bwd(const void* dy, const void* y, void* out, long long 
 // gradients of the nn.Linear layers: like their weight gradients nothing reads them before the optimizer, so the autograd
 // layer queues them and the engine flushes the queue once per step). One block = (problem, 256-column block, row chunk);
 // partial sums are added with fp32 atomics (the order of the chunk contributions is not fixed, as for the split-K wgrads).
+namespace {
 constexpr int kMaxColsum = 48;
 struct ColsumGroup {
   const void* in[kMaxColsum];
@@ -1414,8 +1396,9 @@ __global__ void __launch_bounds__(256) colsum_grouped_kernel(const __grid_consta
     colsum_group_block<bf16>(reinterpret_cast<const bf16*>(G.in[pi]), G.ld[pi], r0, r1, G.C[pi], cblk, G.vec_ok[pi], G.out[pi],
                              G.perm_H[pi], G.out2[pi]);
 }
+}  // namespace
 
-extern "C" int dvgr_colsum_grouped(const dvgr_colsum_problem* probs, int n, void* stream) {
+extern "C" int DVGR_FN(dvgr_colsum_grouped)(const dvgr_colsum_problem* probs, int n, void* stream) {
   if (n <= 0) return 0;
   if (!probs) return set_error("colsum_grouped: null problem list");
   for (int base = 0; base < n; base += kMaxColsum) {
@@ -1450,6 +1433,7 @@ extern "C" int dvgr_colsum_grouped(const dvgr_colsum_problem* probs, int n, void
 // accumulation of the many tiny parameters of a DualVGR unit (per-head attention vectors and biases), which autograd would
 // otherwise perform with one elementwise launch per parameter (~170 launches of ~2 us per train step); copy: gathering those
 // parameters into the packed per-graph operands of the GAT kernels (instead of ~25 torch.cat launches per layer).
+namespace {
 constexpr int kMaxSegs = 128;
 struct SegList {
   float* dst[kMaxSegs];
@@ -1462,8 +1446,9 @@ __global__ void scatter_kernel(const SegList L, int accumulate) {
   const float* s = L.src[blockIdx.x];
   for (int i = threadIdx.x; i < L.n[blockIdx.x]; i += blockDim.x) d[i] = accumulate ? d[i] + s[i] : s[i];
 }
+}  // namespace
 
-extern "C" int dvgr_scatter(const dvgr_seg* segs, int n_segs, int accumulate, void* stream) {
+extern "C" int DVGR_FN(dvgr_scatter)(const dvgr_seg* segs, int n_segs, int accumulate, void* stream) {
   if (n_segs <= 0) return 0;
   if (!segs) return set_error("scatter: null segment list");
   for (int base = 0; base < n_segs; base += kMaxSegs) {
@@ -1479,7 +1464,7 @@ extern "C" int dvgr_scatter(const dvgr_seg* segs, int n_segs, int accumulate, vo
   return 0;
 }
 
-extern "C" int dvgr_add(void* a, const void* b, long long n, void* stream) {
+extern "C" int DVGR_FN(dvgr_add)(void* a, const void* b, long long n, void* stream) {
   if (n % 8 != 0) return set_error("add: n=%lld must be a multiple of 8", n);
   if (n <= 0) return 0;
   add_kernel<<<grid_for(n / 8), 256, 0, ST(stream)>>>(BF(a), CBF(b), n / 8);
@@ -1494,9 +1479,9 @@ static inline long long colsum_chunks(long long R) {
   return chunks;
 }
 
-extern "C" long long dvgr_colsum_workspace(long long R, int C) { return colsum_chunks(R) * C; }
+extern "C" long long DVGR_FN(dvgr_colsum_workspace)(long long R, int C) { return colsum_chunks(R) * C; }
 
-extern "C" int dvgr_colsum_batched(const void* in, int in_is_f32, long long ld, long long in_batch, long long R, int C,
+extern "C" int DVGR_FN(dvgr_colsum_batched)(const void* in, int in_is_f32, long long ld, long long in_batch, long long R, int C,
                                    int batch, float* workspace, float* out, long long out_batch, int accumulate,
                                    float scale, void* stream) {
   if (C <= 0 || batch <= 0) return 0;
@@ -1515,7 +1500,7 @@ extern "C" int dvgr_colsum_batched(const void* in, int in_is_f32, long long ld, 
   return 0;
 }
 
-extern "C" int dvgr_colsum(const void* in, int in_is_f32, long long ld, long long R, int C, float* workspace, float* out,
+extern "C" int DVGR_FN(dvgr_colsum)(const void* in, int in_is_f32, long long ld, long long R, int C, float* workspace, float* out,
                            int accumulate, float scale, void* stream) {
-  return dvgr_colsum_batched(in, in_is_f32, ld, 0, R, C, 1, workspace, out, 0, accumulate, scale, stream);
+  return DVGR_FN(dvgr_colsum_batched)(in, in_is_f32, ld, 0, R, C, 1, workspace, out, 0, accumulate, scale, stream);
 }

@@ -12,24 +12,29 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include "act.cuh"
 #include "capi_internal.h"
 #include "ptx.cuh"
 #include "rng.cuh"
 
+// (compiled twice, see act.cuh; the tensor-core fast path exists in the bf16 build only)
 namespace dvgr {
+namespace DVGR_VNS {
+using namespace act;
+constexpr int kEsz = (int)sizeof(act_t);
 
 constexpr int kGatThreads = 384;
 constexpr int kMaxHeads = 4;
 
 struct GatGraph {
-  const __nv_bfloat16* wh;    // [B*N, ld_wh] projected node features (bias included)
+  const act_t* wh;    // [B*N, ld_wh] projected node features (bias included)
   const float* gate;          // [B, N] query-punishment gate of the stream this graph reads
   const float* avec;          // [heads][2*Dh + 1] : a1 | a2 | c
-  __nv_bfloat16* out;         // fwd: [B*N, ld_out] ; bwd: h' of the forward pass (post-dropout)
+  act_t* out;         // fwd: [B*N, ld_out] ; bwd: h' of the forward pass (post-dropout)
   float* out_f32;             // fwd, optional: dense [B*N, D] fp32 copy of `out` for the auxiliary losses
-  const __nv_bfloat16* dout;  // bwd: gradient of `out`
+  const act_t* dout;  // bwd: gradient of `out`
   const float* dout_f32;      // bwd, optional: extra gradient arriving on the fp32 copy (auxiliary losses)
-  __nv_bfloat16* dwh;         // bwd: [B*N, ld_wh] gradient of wh
+  act_t* dwh;         // bwd: [B*N, ld_wh] gradient of wh
   float* dgate;               // bwd: [B, N] this graph's contribution to the gate gradient
   float* davec;               // bwd: [B][heads][2*Dh + 1] per-video partial sums (reduced by dvgr_colsum)
   unsigned int drop_stream;   // dropout stream id of this graph (attention: +0, output: +1)
@@ -47,7 +52,7 @@ struct GatParams {
 };
 
 struct GatSmem {
-  __nv_bfloat16* wh;   // [N][D]
+  act_t* wh;   // [N][D]
   float* P;            // [heads][N][NP]   probabilities (fwd: already gated + dropped)
   float* s;            // [heads][N]
   float* t;            // [heads][N]
@@ -60,7 +65,7 @@ __host__ __device__ inline int round4(int n) { return (n + 3) & ~3; }
 
 __host__ __device__ inline size_t gat_smem_common(int N, int D, int heads) {
   const int NP = round4(N);
-  size_t b = (size_t)N * D * 2;                              // wh
+  size_t b = (size_t)N * D * kEsz;                           // wh
   b += (size_t)heads * N * NP * 4;                           // P
   b += (size_t)heads * N * 4 * 2;                            // s, t
   b += (size_t)round4(N) * 4;                                // gate
@@ -72,8 +77,8 @@ __host__ __device__ inline size_t gat_smem_common(int N, int D, int heads) {
 __device__ __forceinline__ GatSmem carve(unsigned char* base, int N, int D, int heads) {
   const int NP = round4(N);
   GatSmem sm;
-  sm.wh = reinterpret_cast<__nv_bfloat16*>(base);
-  base += (size_t)N * D * 2;
+  sm.wh = reinterpret_cast<act_t*>(base);
+  base += (size_t)N * D * kEsz;
   sm.P = reinterpret_cast<float*>(base);
   base += (size_t)heads * N * NP * 4;
   sm.s = reinterpret_cast<float*>(base);
@@ -92,11 +97,12 @@ __device__ __forceinline__ GatSmem carve(unsigned char* base, int N, int D, int 
 __device__ __forceinline__ void gat_stage(const GatParams& p, const GatGraph& gr, int b, const GatSmem& sm) {
   const int N = p.N, D = p.D, K = p.heads, Dh = D / K;
   const int tid = threadIdx.x, nthr = blockDim.x;
-  const __nv_bfloat16* src = gr.wh + (long long)b * N * p.ld_wh;
-  const int vec_per_row = D / 8;
+  const act_t* src = gr.wh + (long long)b * N * p.ld_wh;
+  constexpr int kEpv = 16 / kEsz;                            // elements per 16-byte vector
+  const int vec_per_row = D / kEpv;
   for (int v = tid; v < N * vec_per_row; v += nthr) {
     const int r = v / vec_per_row, c = v - r * vec_per_row;
-    reinterpret_cast<uint4*>(sm.wh)[v] = *reinterpret_cast<const uint4*>(src + (long long)r * p.ld_wh + c * 8);
+    reinterpret_cast<uint4*>(sm.wh)[v] = *reinterpret_cast<const uint4*>(src + (long long)r * p.ld_wh + c * kEpv);
   }
   for (int i = tid; i < N; i += nthr) sm.gate[i] = gr.gate[(long long)b * N + i];
   for (int i = tid; i < K * (2 * Dh + 1); i += nthr) sm.avec[i] = gr.avec[i];
@@ -106,10 +112,10 @@ __device__ __forceinline__ void gat_stage(const GatParams& p, const GatGraph& gr
   for (int pr = warp; pr < N * K; pr += nwarps) {
     const int i = pr / K, k = pr - i * K;
     const float* a = sm.avec + k * (2 * Dh + 1);
-    const __nv_bfloat16* w = sm.wh + i * D + k * Dh;
+    const act_t* w = sm.wh + i * D + k * Dh;
     float s = 0.f, t = 0.f;
     for (int c = lane; c < Dh; c += 32) {
-      const float x = __bfloat162float(w[c]);
+      const float x = ld1(w + c);
       s += a[c] * x;
       t += a[Dh + c] * x;
     }
@@ -196,8 +202,7 @@ __global__ void __launch_bounds__(kGatThreads) gat_attn_fwd_kernel(const GatPara
 
   // aggregation: out[i][c] = dropout(ELU(sum_j P[k(c)][i][j] * Wh[j][c])) ; 2 columns x 8 rows per thread and pass
   const DropoutCfg dout{p.seed, gr.drop_stream + 1u, p.p_out, p.seed_off};
-  __nv_bfloat16* outp = gr.out + (long long)b * N * p.ld_out;
-  const __nv_bfloat162* wh2 = reinterpret_cast<const __nv_bfloat162*>(sm.wh);
+  act_t* outp = gr.out + (long long)b * N * p.ld_out;
   for (int pair = tid; pair < D / 2; pair += blockDim.x) {
     const int c = pair * 2;
     const int k = c / Dh;
@@ -210,7 +215,7 @@ __global__ void __launch_bounds__(kGatThreads) gat_attn_fwd_kernel(const GatPara
         float2 w[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-          w[q] = (j0 + q < N) ? __bfloat1622float2(wh2[(size_t)(j0 + q) * (D / 2) + pair]) : make_float2(0.f, 0.f);
+          w[q] = (j0 + q < N) ? ld2(sm.wh + (size_t)(j0 + q) * D + 2 * pair) : make_float2(0.f, 0.f);
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
           if (i0 + r < N) {
@@ -230,7 +235,7 @@ __global__ void __launch_bounds__(kGatThreads) gat_attn_fwd_kernel(const GatPara
             o0 *= keep.x;
             o1 *= keep.y;
           }
-          *reinterpret_cast<__nv_bfloat162*>(outp + (long long)i * p.ld_out + c) = __floats2bfloat162_rn(o0, o1);
+          st2(outp + (long long)i * p.ld_out + c, o0, o1);
           if (gr.out_f32 != nullptr)
             *reinterpret_cast<float2*>(gr.out_f32 + ((long long)b * N + i) * D + c) = make_float2(o0, o1);
         }
@@ -239,6 +244,7 @@ __global__ void __launch_bounds__(kGatThreads) gat_attn_fwd_kernel(const GatPara
   }
 }
 
+#ifndef DVGR_F32
 // ------------------------------------------------------------------------------------------------------ fast path (forward)
 // D = 768, 4 heads — the only configuration DualVGR builds (reference model/models.py:95-100) — and N <= NP nodes.
 // The generic kernel above spends ~95 % of its issue slots on integer / predicate work around a 300 k-MAC aggregation
@@ -457,11 +463,12 @@ __global__ void __launch_bounds__(kFThreads) gat_attn_fwd_mma_kernel(const GatPa
   }
 }
 
+#endif  // DVGR_F32
 // ------------------------------------------------------------------------------------------------------ backward
 // extra shared memory: dz [N][D] bf16, dP [heads][N][NP] f32 (dP~ -> du -> transposed P~), ds/dt [heads][N], dg [N]
 __host__ __device__ inline size_t gat_smem_bwd_extra(int N, int D, int heads) {
   const int NP = round4(N);
-  return (size_t)N * D * 2 + (size_t)heads * N * NP * 4 + (size_t)heads * N * 4 * 2 + (size_t)round4(N) * 4 + 16;
+  return (size_t)N * D * kEsz + (size_t)heads * N * NP * 4 + (size_t)heads * N * 4 * 2 + (size_t)round4(N) * 4 + 16;
 }
 
 __global__ void __launch_bounds__(kGatThreads) gat_attn_bwd_kernel(const GatParams p) {
@@ -471,8 +478,8 @@ __global__ void __launch_bounds__(kGatThreads) gat_attn_bwd_kernel(const GatPara
   const int N = p.N, D = p.D, K = p.heads, Dh = D / K, NP = round4(N);
   const GatSmem sm = carve(smem_raw, N, D, K);
   unsigned char* ext = smem_raw + gat_smem_common(N, D, K);
-  __nv_bfloat16* dz = reinterpret_cast<__nv_bfloat16*>(ext);
-  ext += (size_t)N * D * 2;
+  act_t* dz = reinterpret_cast<act_t*>(ext);
+  ext += (size_t)N * D * kEsz;
   float* dP = reinterpret_cast<float*>(ext);
   ext += (size_t)K * N * NP * 4;
   float* ds = reinterpret_cast<float*>(ext);
@@ -491,8 +498,8 @@ __global__ void __launch_bounds__(kGatThreads) gat_attn_bwd_kernel(const GatPara
   for (int pr = warp; pr < N * K; pr += nwarps) gat_softmax_row(p, sm, pr / N, pr % N, lane);
   for (int i = tid; i < N; i += blockDim.x) dg[i] = 0.f;
   {
-    const __nv_bfloat16* hp = gr.out + (long long)b * N * p.ld_out;
-    const __nv_bfloat16* dop = gr.dout + (long long)b * N * p.ld_out;
+    const act_t* hp = gr.out + (long long)b * N * p.ld_out;
+    const act_t* dop = gr.dout + (long long)b * N * p.ld_out;
     const float keepf = 1.f - p.p_out;
     const int quads = (N + 3) >> 2;
     for (int u = tid; u < quads * (D / 2); u += blockDim.x) {
@@ -502,8 +509,8 @@ __global__ void __launch_bounds__(kGatThreads) gat_attn_bwd_kernel(const GatPara
         const int i = rq * 4 + r;
         if (i >= N) break;
         const float2 keep = out_keep2(p, dout, b, i, pair);
-        float2 h = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(hp + (long long)i * p.ld_out + c));
-        float2 d = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dop + (long long)i * p.ld_out + c));
+        float2 h = ld2(hp + (long long)i * p.ld_out + c);
+        float2 d = ld2(dop + (long long)i * p.ld_out + c);
         if (gr.dout_f32 != nullptr) {
           const float2 e = *reinterpret_cast<const float2*>(gr.dout_f32 + ((long long)b * N + i) * D + c);
           d.x += e.x;
@@ -517,7 +524,7 @@ __global__ void __launch_bounds__(kGatThreads) gat_attn_bwd_kernel(const GatPara
         }
         d.x *= elu_grad_from_out(h.x);
         d.y *= elu_grad_from_out(h.y);
-        *reinterpret_cast<__nv_bfloat162*>(dz + (size_t)i * D + c) = __floats2bfloat162_rn(d.x, d.y);
+        st2(dz + (size_t)i * D + c, d.x, d.y);
       }
     }
   }
@@ -530,7 +537,7 @@ __global__ void __launch_bounds__(kGatThreads) gat_attn_bwd_kernel(const GatPara
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       const int c = lane + 32 * q;
-      zreg[q] = c < Dh ? __bfloat162float(dz[(size_t)i * D + k * Dh + c]) : 0.f;
+      zreg[q] = c < Dh ? ld1(dz + (size_t)i * D + k * Dh + c) : 0.f;
     }
     float mine[2] = {0.f, 0.f};
     for (int j = 0; j < N; ++j) {
@@ -538,7 +545,7 @@ __global__ void __launch_bounds__(kGatThreads) gat_attn_bwd_kernel(const GatPara
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         const int c = lane + 32 * q;
-        if (c < Dh) acc += zreg[q] * __bfloat162float(sm.wh[(size_t)j * D + k * Dh + c]);
+        if (c < Dh) acc += zreg[q] * ld1(sm.wh + (size_t)j * D + k * Dh + c);
       }
       acc = warp_sum(acc);
       if ((j & 31) == lane) mine[j >> 5] = acc;
@@ -594,9 +601,7 @@ __global__ void __launch_bounds__(kGatThreads) gat_attn_bwd_kernel(const GatPara
   __syncthreads();
 
   // 4. dV_j[c] = sum_i P~_ij dz_i[c] ; dWh_j = g_j dV_j + ds_j a1 + dt_j a2 ; dgate_j ; da1, da2   (8 j x 2 columns / pass)
-  const __nv_bfloat162* wh2 = reinterpret_cast<const __nv_bfloat162*>(sm.wh);
-  const __nv_bfloat162* dz2 = reinterpret_cast<const __nv_bfloat162*>(dz);
-  __nv_bfloat16* dwhp = gr.dwh + (long long)b * N * p.ld_wh;
+  act_t* dwhp = gr.dwh + (long long)b * N * p.ld_wh;
   float* dav = gr.davec + ((long long)b * K) * (2 * Dh + 1);
   for (int pair0 = 0; pair0 < D / 2; pair0 += blockDim.x) {
     const int pair = pair0 + tid;
@@ -616,7 +621,7 @@ __global__ void __launch_bounds__(kGatThreads) gat_attn_bwd_kernel(const GatPara
           float2 z[4];
 #pragma unroll
           for (int q = 0; q < 4; ++q)
-            z[q] = (i0 + q < N) ? __bfloat1622float2(dz2[(size_t)(i0 + q) * (D / 2) + pair]) : make_float2(0.f, 0.f);
+            z[q] = (i0 + q < N) ? ld2(dz + (size_t)(i0 + q) * D + 2 * pair) : make_float2(0.f, 0.f);
 #pragma unroll
           for (int r = 0; r < 8; ++r) {
             if (j0 + r < N) {
@@ -631,7 +636,7 @@ __global__ void __launch_bounds__(kGatThreads) gat_attn_bwd_kernel(const GatPara
       for (int r = 0; r < 8; ++r) {
         const int j = j0 + r;
         if (j >= N) break;                                  // uniform across the block
-        const float2 w = active ? __bfloat1622float2(wh2[(size_t)j * (D / 2) + pair]) : make_float2(0.f, 0.f);
+        const float2 w = active ? ld2(sm.wh + (size_t)j * D + 2 * pair) : make_float2(0.f, 0.f);
         float part = acc[r][0] * w.x + acc[r][1] * w.y;     // gate gradient: dg_j += sum_c dV_j[c] Wh_j[c]
         part = warp_sum(part);
         if (lane == 0) atomicAdd(&dg[j], part);
@@ -639,7 +644,7 @@ __global__ void __launch_bounds__(kGatThreads) gat_attn_bwd_kernel(const GatPara
           const float gj = sm.gate[j], dsj = ds[k * N + j], dtj = dt[k * N + j];
           const float ox = gj * acc[r][0] + dsj * a1[cl] + dtj * a2[cl];
           const float oy = gj * acc[r][1] + dsj * a1[cl + 1] + dtj * a2[cl + 1];
-          *reinterpret_cast<__nv_bfloat162*>(dwhp + (long long)j * p.ld_wh + c) = __floats2bfloat162_rn(ox, oy);
+          st2(dwhp + (long long)j * p.ld_wh + c, ox, oy);
           da1x += dsj * w.x; da1y += dsj * w.y;
           da2x += dtj * w.x; da2y += dtj * w.y;
         }
@@ -656,6 +661,7 @@ __global__ void __launch_bounds__(kGatThreads) gat_attn_bwd_kernel(const GatPara
   if (tid < K) dav[tid * (2 * Dh + 1) + 2 * Dh] = dc_s[tid];
 }
 
+#ifndef DVGR_F32
 // ------------------------------------------------------------------------------------------------------ fast path (backward)
 // Same configuration as the forward fast path, N <= 32. The heads of a graph are independent except for the gate
 // gradient, so ONE CTA handles (video, graph, PAIR of heads): 384 of the 768 columns. That halves the two staged tiles
@@ -1049,9 +1055,12 @@ __global__ void __launch_bounds__(kFThreads, (NP == 32) ? 3 : 2) gat_attn_bwd_mm
   if (tid < kBH) gr.davec[((long long)b * kFK + head0 + tid) * (2 * kFDh + 1) + 2 * kFDh] = dc_s[tid];
 }
 
+#endif  // DVGR_F32
+}  // namespace DVGR_VNS
 }  // namespace dvgr
 
 using namespace dvgr;
+using namespace dvgr::DVGR_VNS;
 
 static int fill_gat(GatParams& p, const dvgr_gat_args* a, bool bwd) {
   if (!a) return set_error("gat: null args");
@@ -1070,17 +1079,17 @@ static int fill_gat(GatParams& p, const dvgr_gat_args* a, bool bwd) {
     const dvgr_gat_graph& s = a->graphs[i];
     GatGraph& d = p.g[i];
     if (!s.wh || !s.gate || !s.avec || !s.out) return set_error("gat: graph %d has a null buffer", i);
-    d.wh = reinterpret_cast<const __nv_bfloat16*>(s.wh);
+    d.wh = reinterpret_cast<const act_t*>(s.wh);
     d.gate = s.gate;
     d.avec = s.avec;
-    d.out = reinterpret_cast<__nv_bfloat16*>(s.out);
+    d.out = reinterpret_cast<act_t*>(s.out);
     d.drop_stream = s.drop_stream;
     d.out_f32 = s.out_f32;
     if (bwd) {
       d.dout_f32 = s.dout_f32;
       if (!s.dout || !s.dwh || !s.dgate || !s.davec) return set_error("gat bwd: graph %d has a null gradient buffer", i);
-      d.dout = reinterpret_cast<const __nv_bfloat16*>(s.dout);
-      d.dwh = reinterpret_cast<__nv_bfloat16*>(s.dwh);
+      d.dout = reinterpret_cast<const act_t*>(s.dout);
+      d.dwh = reinterpret_cast<act_t*>(s.dwh);
       d.dgate = s.dgate;
       d.davec = s.davec;
     }
@@ -1088,6 +1097,7 @@ static int fill_gat(GatParams& p, const dvgr_gat_args* a, bool bwd) {
   return 0;
 }
 
+#ifndef DVGR_F32
 static int gat_fast_knob() {      // read per call (tests flip it to compare the two paths): bit 0 forward, bit 1 backward
   const char* e = getenv("DVGR_GAT_FAST");
   return e ? atoi(e) : 3;
@@ -1110,14 +1120,18 @@ static int launch_gat_fwd_fast(const GatParams& p, int n_graphs, cudaStream_t st
   return 0;
 }
 
-extern "C" int dvgr_gat_attn_fwd(const dvgr_gat_args* a, void* stream) {
+#endif  // DVGR_F32
+
+extern "C" int DVGR_FN(dvgr_gat_attn_fwd)(const dvgr_gat_args* a, void* stream) {
   GatParams p;
   if (int rc = fill_gat(p, a, false)) return rc;
   if (a->B <= 0 || a->N <= 0) return 0;
+#ifndef DVGR_F32
   if ((gat_fast_knob() & 1) && gat_fast_ok(p)) {
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     return p.N <= 32 ? launch_gat_fwd_fast<32>(p, a->n_graphs, st) : launch_gat_fwd_fast<64>(p, a->n_graphs, st);
   }
+#endif
   const size_t smem = gat_smem_common(p.N, p.D, p.heads);
   if (smem > 227 * 1024) return set_error("gat fwd: %zu bytes of shared memory needed", smem);
   static size_t configured = 0;
@@ -1131,6 +1145,7 @@ extern "C" int dvgr_gat_attn_fwd(const dvgr_gat_args* a, void* stream) {
   return 0;
 }
 
+#ifndef DVGR_F32
 template <int NP, int kBH>
 static int launch_gat_bwd_fast(const GatParams& p, int n_graphs, cudaStream_t st) {
   static bool configured = false;
@@ -1150,14 +1165,18 @@ static int launch_gat_bwd_fast(const GatParams& p, int n_graphs, cudaStream_t st
   return 0;
 }
 
-extern "C" int dvgr_gat_attn_bwd(const dvgr_gat_args* a, void* stream) {
+#endif  // DVGR_F32
+
+extern "C" int DVGR_FN(dvgr_gat_attn_bwd)(const dvgr_gat_args* a, void* stream) {
   GatParams p;
   if (int rc = fill_gat(p, a, true)) return rc;
   if (a->B <= 0 || a->N <= 0) return 0;
+#ifndef DVGR_F32
   if ((gat_fast_knob() & 2) && gat_fast_ok(p)) {
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     return p.N <= 32 ? launch_gat_bwd_fast<32, 2>(p, a->n_graphs, st) : launch_gat_bwd_fast<64, 1>(p, a->n_graphs, st);
   }
+#endif
   const size_t smem = gat_smem_common(p.N, p.D, p.heads) + gat_smem_bwd_extra(p.N, p.D, p.heads);
   if (smem > 227 * 1024) return set_error("gat bwd: %zu bytes of shared memory needed", smem);
   static size_t configured = 0;

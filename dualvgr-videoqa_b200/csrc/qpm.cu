@@ -9,10 +9,13 @@
 // register-level mask from question_len here.
 #include <cuda_bf16.h>
 
+#include "act.cuh"
 #include "capi_internal.h"
 #include "ptx.cuh"
 
 namespace dvgr {
+namespace DVGR_VNS {
+using namespace act;
 
 constexpr int kQThreads = 256;
 constexpr int kMaxL = 128;
@@ -21,23 +24,23 @@ constexpr int kMaxL = 128;
 // y [B][L][D] bf16 = feat_enhance(dynamic_q) (bias included); words [B][L][ld_w] bf16
 // out: alpha [B][L], nrm [B][L] (clamped norm), prob [B][L] (softmax over all L), ssum [B]; qc [B][ld_qc] bf16 (zero padded)
 __global__ void __launch_bounds__(kQThreads)
-qattn_fwd_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ wf, const float* __restrict__ cf,
-                 const int* __restrict__ qlen, const __nv_bfloat16* __restrict__ words, long long ld_w, int L, int D,
+qattn_fwd_kernel(const act_t* __restrict__ y, const float* __restrict__ wf, const float* __restrict__ cf,
+                 const int* __restrict__ qlen, const act_t* __restrict__ words, long long ld_w, int L, int D,
                  int W, float* __restrict__ alpha, float* __restrict__ nrm, float* __restrict__ prob,
-                 float* __restrict__ ssum, __nv_bfloat16* __restrict__ qc, long long ld_qc) {
+                 float* __restrict__ ssum, act_t* __restrict__ qc, long long ld_qc) {
   __shared__ float sc[kMaxL];
   __shared__ float al[kMaxL];
   const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = kQThreads / 32;
-  const __nv_bfloat16* yb = y + (long long)b * L * D;
+  const act_t* yb = y + (long long)b * L * D;
   for (int l = warp; l < L; l += nwarps) {
     float n2 = 0.f, dot = 0.f;
-    const __nv_bfloat16* row = yb + (long long)l * D;
+    const act_t* row = yb + (long long)l * D;
     for (int c = lane * 8; c < D; c += 256) {
-      uint4 v = *reinterpret_cast<const uint4*>(row + c);
-      const uint32_t* w = reinterpret_cast<const uint32_t*>(&v);
+      float w8_[8];
+      ld8(row + c, w8_);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        float2 f = unpack_bf16x2(w[q]);
+        float2 f = make_float2(w8_[2 * q], w8_[2 * q + 1]);
         n2 += f.x * f.x + f.y * f.y;
         dot += f.x * wf[c + 2 * q] + f.y * wf[c + 2 * q + 1];
       }
@@ -75,40 +78,40 @@ qattn_fwd_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ 
     }
   }
   __syncthreads();
-  const __nv_bfloat16* wb = words + (long long)b * L * ld_w;
+  const act_t* wb = words + (long long)b * L * ld_w;
   for (int w = tid; w < ld_qc; w += kQThreads) {
     float acc = 0.f;
     if (w < W)
-      for (int l = 0; l < L; ++l) acc += al[l] * __bfloat162float(wb[(long long)l * ld_w + w]);
-    qc[(long long)b * ld_qc + w] = __float2bfloat16_rn(acc);
+      for (int l = 0; l < L; ++l) acc += al[l] * ld1(&wb[(long long)l * ld_w + w]);
+    st1(&qc[(long long)b * ld_qc + w], acc);
   }
 }
 
 // ---------------------------------------------------------------------------------------------- word attention bwd
 // dqc [B][ld_qc] bf16 -> dy [B][L][D] bf16, dwords [B][L][ld_w] bf16 (+= when accumulate), dwf_part [B][D], dcf_part [B]
 __global__ void __launch_bounds__(kQThreads)
-qattn_bwd_kernel(const __nv_bfloat16* __restrict__ dqc, long long ld_qc, const __nv_bfloat16* __restrict__ y,
-                 const float* __restrict__ wf, const int* __restrict__ qlen, const __nv_bfloat16* __restrict__ words,
+qattn_bwd_kernel(const act_t* __restrict__ dqc, long long ld_qc, const act_t* __restrict__ y,
+                 const float* __restrict__ wf, const int* __restrict__ qlen, const act_t* __restrict__ words,
                  long long ld_w, int L, int D, int W, const float* __restrict__ alpha, const float* __restrict__ nrm,
-                 const float* __restrict__ prob, const float* __restrict__ ssum, __nv_bfloat16* __restrict__ dy,
-                 __nv_bfloat16* __restrict__ dwords, int accumulate, float* __restrict__ dwf_part,
+                 const float* __restrict__ prob, const float* __restrict__ ssum, act_t* __restrict__ dy,
+                 act_t* __restrict__ dwords, int accumulate, float* __restrict__ dwf_part,
                  float* __restrict__ dcf_part) {
   __shared__ float dal[kMaxL];    // d alpha, then d score
   __shared__ float dq[512];       // dqc of this sample (W <= 512)
   const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = kQThreads / 32;
-  for (int w = tid; w < W; w += kQThreads) dq[w] = __bfloat162float(dqc[(long long)b * ld_qc + w]);
+  for (int w = tid; w < W; w += kQThreads) dq[w] = ld1(&dqc[(long long)b * ld_qc + w]);
   __syncthreads();
-  const __nv_bfloat16* wb = words + (long long)b * L * ld_w;
-  __nv_bfloat16* dwb = dwords + (long long)b * L * ld_w;
+  const act_t* wb = words + (long long)b * L * ld_w;
+  act_t* dwb = dwords + (long long)b * L * ld_w;
   // d alpha_l = dqc . words_l ; dwords_l = alpha_l * dqc
   for (int l = warp; l < L; l += nwarps) {
     const float a = alpha[(long long)b * L + l];
     float acc = 0.f;
     for (int w = lane; w < W; w += 32) {
-      acc += dq[w] * __bfloat162float(wb[(long long)l * ld_w + w]);
+      acc += dq[w] * ld1(&wb[(long long)l * ld_w + w]);
       float g = a * dq[w];
-      if (accumulate) g += __bfloat162float(dwb[(long long)l * ld_w + w]);
-      dwb[(long long)l * ld_w + w] = __float2bfloat16_rn(g);
+      if (accumulate) g += ld1(&dwb[(long long)l * ld_w + w]);
+      st1(&dwb[(long long)l * ld_w + w], g);
     }
     acc = warp_sum(acc);
     if (lane == 0) dal[l] = acc;
@@ -140,19 +143,19 @@ qattn_bwd_kernel(const __nv_bfloat16* __restrict__ dqc, long long ld_qc, const _
   }
   __syncthreads();
   // score_l = wf.y_l / n_l + cf  ->  dy_l = ds_l * (wf / n - (wf.y) y / n^3)   (n clamped: gradient of the clamp branch is wf/n)
-  const __nv_bfloat16* yb = y + (long long)b * L * D;
-  __nv_bfloat16* dyb = dy + (long long)b * L * D;
+  const act_t* yb = y + (long long)b * L * D;
+  act_t* dyb = dy + (long long)b * L * D;
   for (int l = warp; l < L; l += nwarps) {
     const float n = nrm[(long long)b * L + l];
     const float ds = dal[l];
-    const __nv_bfloat16* row = yb + (long long)l * D;
+    const act_t* row = yb + (long long)l * D;
     float dot = 0.f;
     for (int c = lane * 8; c < D; c += 256) {
-      uint4 v = *reinterpret_cast<const uint4*>(row + c);
-      const uint32_t* w = reinterpret_cast<const uint32_t*>(&v);
+      float w8_[8];
+      ld8(row + c, w8_);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        float2 f = unpack_bf16x2(w[q]);
+        float2 f = make_float2(w8_[2 * q], w8_[2 * q + 1]);
         dot += f.x * wf[c + 2 * q] + f.y * wf[c + 2 * q + 1];
       }
     }
@@ -160,22 +163,22 @@ qattn_bwd_kernel(const __nv_bfloat16* __restrict__ dqc, long long ld_qc, const _
     const bool clamped = n <= 1e-12f;
     const float k1 = ds / n, k2 = clamped ? 0.f : ds * dot / (n * n * n);
     for (int c = lane * 8; c < D; c += 256) {
-      uint4 v = *reinterpret_cast<const uint4*>(row + c);
-      const uint32_t* w = reinterpret_cast<const uint32_t*>(&v);
-      uint4 o;
-      uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+      float w8_[8];
+      ld8(row + c, w8_);
+      float o8_[8];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        float2 f = unpack_bf16x2(w[q]);
-        ow[q] = pack_bf16x2(k1 * wf[c + 2 * q] - k2 * f.x, k1 * wf[c + 2 * q + 1] - k2 * f.y);
+        float2 f = make_float2(w8_[2 * q], w8_[2 * q + 1]);
+        o8_[2 * q] = k1 * wf[c + 2 * q] - k2 * f.x;
+        o8_[2 * q + 1] = k1 * wf[c + 2 * q + 1] - k2 * f.y;
       }
-      *reinterpret_cast<uint4*>(dyb + (long long)l * D + c) = o;
+      st8(dyb + (long long)l * D + c, o8_);
     }
   }
   // d wf (partial for this sample) = sum_l ds_l * y_l / n_l
   for (int c = tid; c < D; c += kQThreads) {
     float acc = 0.f;
-    for (int l = 0; l < L; ++l) acc += dal[l] / nrm[(long long)b * L + l] * __bfloat162float(yb[(long long)l * D + c]);
+    for (int l = 0; l < L; ++l) acc += dal[l] / nrm[(long long)b * L + l] * ld1(&yb[(long long)l * D + c]);
     dwf_part[(long long)b * D + c] = acc;
   }
 }
@@ -183,10 +186,10 @@ qattn_bwd_kernel(const __nv_bfloat16* __restrict__ dqc, long long ld_qc, const _
 // ---------------------------------------------------------------------------------------------- gates fwd / bwd
 // X [S streams][B][N][D] via per-stream pointers; query [B][ld_q] bf16 with stream s at column s*D
 struct GateParams {
-  const __nv_bfloat16* X[2];
-  __nv_bfloat16* dX[2];
-  const __nv_bfloat16* query;
-  __nv_bfloat16* dquery;
+  const act_t* X[2];
+  act_t* dX[2];
+  const act_t* query;
+  act_t* dquery;
   long long ld_q;
   float* gate[2];
   const float* dgate_a[2];
@@ -200,17 +203,16 @@ __global__ void __launch_bounds__(256) gate_fwd_kernel(const GateParams p) {
   const int s = blockIdx.y;
   for (long long r = (long long)blockIdx.x * 8 + warp; r < rows; r += (long long)gridDim.x * 8) {
     const int b = (int)(r / p.N);
-    const __nv_bfloat16* x = p.X[s] + r * p.D;
-    const __nv_bfloat16* q = p.query + (long long)b * p.ld_q + (long long)s * p.D;
+    const act_t* x = p.X[s] + r * p.D;
+    const act_t* q = p.query + (long long)b * p.ld_q + (long long)s * p.D;
     float acc = 0.f;
     for (int c = lane * 8; c < p.D; c += 256) {
-      uint4 xv = *reinterpret_cast<const uint4*>(x + c);
-      uint4 qv = *reinterpret_cast<const uint4*>(q + c);
-      const uint32_t* xw = reinterpret_cast<const uint32_t*>(&xv);
-      const uint32_t* qw = reinterpret_cast<const uint32_t*>(&qv);
+      float xw8_[8], qw8_[8];
+      ld8(x + c, xw8_);
+      ld8(q + c, qw8_);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        float2 a = unpack_bf16x2(xw[k]), c2 = unpack_bf16x2(qw[k]);
+        float2 a = make_float2(xw8_[2 * k], xw8_[2 * k + 1]), c2 = make_float2(qw8_[2 * k], qw8_[2 * k + 1]);
         acc += a.x * c2.x + a.y * c2.y;
       }
     }
@@ -231,31 +233,33 @@ __global__ void __launch_bounds__(256) gate_bwd_kernel(const GateParams p) {
     dz[n] = d * g * (1.f - g);
   }
   __syncthreads();
-  const __nv_bfloat16* q = p.query + (long long)b * p.ld_q + (long long)s * p.D;
-  __nv_bfloat16* dq = p.dquery + (long long)b * p.ld_q + (long long)s * p.D;
+  const act_t* q = p.query + (long long)b * p.ld_q + (long long)s * p.D;
+  act_t* dq = p.dquery + (long long)b * p.ld_q + (long long)s * p.D;
   for (int c = tid * 2; c < p.D; c += blockDim.x * 2) {
-    const float2 qv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(q + c));
+    const float2 qv = ld2(q + c);
     float ax = 0.f, ay = 0.f;
     for (int n = 0; n < p.N; ++n) {
       const long long off = ((long long)b * p.N + n) * p.D + c;
-      const float2 xv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p.X[s] + off));
+      const float2 xv = ld2(p.X[s] + off);
       ax += dz[n] * xv.x;
       ay += dz[n] * xv.y;
-      float2 old = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p.dX[s] + off));
+      float2 old = ld2(p.dX[s] + off);
       old.x += dz[n] * qv.x;
       old.y += dz[n] * qv.y;
-      *reinterpret_cast<__nv_bfloat162*>(p.dX[s] + off) = __floats2bfloat162_rn(old.x, old.y);
+      st2(p.dX[s] + off, old.x, old.y);
     }
-    *reinterpret_cast<__nv_bfloat162*>(dq + c) = __floats2bfloat162_rn(ax, ay);
+    st2(dq + c, ax, ay);
   }
 }
 
+}  // namespace DVGR_VNS
 }  // namespace dvgr
 
 using namespace dvgr;
-typedef __nv_bfloat16 bf16;
+using namespace dvgr::DVGR_VNS;
+typedef act_t bf16;      // (the launchers below cast the ABI's void* activations to the build's storage type)
 
-extern "C" int dvgr_qattn_fwd(const void* y, const float* wf, const float* cf, const int* qlen, const void* words,
+extern "C" int DVGR_FN(dvgr_qattn_fwd)(const void* y, const float* wf, const float* cf, const int* qlen, const void* words,
                               long long ld_w, int B, int L, int D, int W, float* alpha, float* nrm, float* prob,
                               float* ssum, void* qc, long long ld_qc, void* stream) {
   if (B <= 0) return 0;
@@ -268,7 +272,7 @@ extern "C" int dvgr_qattn_fwd(const void* y, const float* wf, const float* cf, c
   return 0;
 }
 
-extern "C" int dvgr_qattn_bwd(const void* dqc, long long ld_qc, const void* y, const float* wf, const int* qlen,
+extern "C" int DVGR_FN(dvgr_qattn_bwd)(const void* dqc, long long ld_qc, const void* y, const float* wf, const int* qlen,
                               const void* words, long long ld_w, int B, int L, int D, int W, const float* alpha,
                               const float* nrm, const float* prob, const float* ssum, void* dy, void* dwords,
                               int accumulate_dwords, float* dwf_part, float* dcf_part, void* stream) {
@@ -284,7 +288,7 @@ extern "C" int dvgr_qattn_bwd(const void* dqc, long long ld_qc, const void* y, c
   return 0;
 }
 
-extern "C" int dvgr_gate_fwd(const void* x0, const void* x1, const void* query, long long ld_q, int B, int N, int D,
+extern "C" int DVGR_FN(dvgr_gate_fwd)(const void* x0, const void* x1, const void* query, long long ld_q, int B, int N, int D,
                              float* gate0, float* gate1, void* stream) {
   if (B <= 0 || N <= 0) return 0;
   if (D % 8 != 0) return set_error("gate: D=%d must be a multiple of 8", D);
@@ -301,7 +305,7 @@ extern "C" int dvgr_gate_fwd(const void* x0, const void* x1, const void* query, 
   return 0;
 }
 
-extern "C" int dvgr_gate_bwd(const void* x0, const void* x1, const void* query, long long ld_q, int B, int N, int D,
+extern "C" int DVGR_FN(dvgr_gate_bwd)(const void* x0, const void* x1, const void* query, long long ld_q, int B, int N, int D,
                              const float* gate0, const float* gate1, const float* dg0a, const float* dg0b,
                              const float* dg1a, const float* dg1b, void* dx0, void* dx1, void* dquery, void* stream) {
   if (B <= 0 || N <= 0) return 0;

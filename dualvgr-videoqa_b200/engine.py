@@ -112,7 +112,7 @@ class TrainEngine:
         # stream they are recorded on (the critical path must win SMs over the low-priority auxiliary-loss stream), and
         # autograd remembers the stream a parameter was first used on — eager steps on the caller's stream followed by a
         # capture on another one made the captured backward wait on uncaptured work
-        self.stream = torch.cuda.Stream(device=dev, priority=-1)
+        self.stream = torch.cuda.Stream(device=dev, priority=-1) if dev.type == "cuda" else None   # (CPU: layout inspection only)
         self.last_stats = None           # [4] f32 device tensor of the last step: total, common sum, dependence sum, #timeouts
         self._step_flags = []
         if self.world > 1:      # replicas must start identical (the reference seeds every process the same, train.py:425-428)
@@ -193,7 +193,32 @@ class TrainEngine:
         with self._on_stream():
             return self._forward_backward(app, mot, question, question_len, answers)
 
+    def _forward_backward_fp32(self, app, mot, question, question_len, answers):
+        """fp32 mode (DualVGR.set_precision("fp32")): module-by-module forward, the auxiliary terms as ordinary autograd nodes
+        on the fp32 graph outputs, gradients accumulated by autograd into the bound views of gflat (no deferred launches)."""
+        model = self.model
+        model.train()
+        self.gflat.zero_()
+        ag.begin_step_flags()
+        unit = model.visual_input_unit
+        B, N = app.shape[0], app.shape[1]
+        outputs = model(app, mot, question, question_len)
+        self.last_logits = outputs[0].detach()
+        ce, correct = ag.CrossEntropyFn.apply(outputs[0], answers, False)
+        loss, parts = ce, []
+        if unit.layers > 0 and (self.alpha != 0 or self.beta != 0):
+            c_com, c_dep = self._loss_coefs(B, N, unit.layers)
+            for i in range(unit.layers):
+                tot, vals = ag.AuxLossFn.apply(outputs[3][i], outputs[4][i], outputs[5][i], outputs[6][i], c_com, c_dep, False)
+                loss = loss + tot
+                parts.append(vals)
+        loss.backward()
+        self.last_stats = ops.finalize_loss(ce.detach().reshape(1), torch.stack(parts) if parts else None, [])
+        return self.last_stats[0], correct
+
     def _forward_backward(self, app, mot, question, question_len, answers):
+        if ag.ACT[0] == torch.float32:
+            return self._forward_backward_fp32(app, mot, question, question_len, answers)
         model = self.model
         model.train()
         self.gflat.zero_()

@@ -20,10 +20,10 @@ class ContextSelfAttn(nn.Module):
     def forward(self, visual_feat):
         """[B,N,D] -> [B,D]: the dropped-out features are both scored and pooled (reference :173-180)."""
         dt = visual_feat.dtype
-        v = ag.dropout(visual_feat.to(BF16), self.dropout.p, self.training)
+        v = ag.dropout(visual_feat.to(ag.ACT[0]), self.dropout.p, self.training)
         u = ag.linear(v, self.v_proj.weight, None, act="elu", act_grad_folded=True)
         pooled = ag.ReadoutFn.apply(v, u, self.attn.weight, self.attn.bias)
-        return pooled if dt == BF16 else pooled.to(dt)
+        return pooled if dt == pooled.dtype else pooled.to(dt)
 
 
 class SimpleOutputUnitOpenEnded(nn.Module):
@@ -36,8 +36,8 @@ class SimpleOutputUnitOpenEnded(nn.Module):
     def forward(self, question_embedding, visual_embedding):
         """([B,D], [B,D]) -> logits [B,A] fp32 (reference :197-202)."""
         c = self.classifier
-        q = ag.linear(question_embedding.to(BF16), self.question_proj.weight, self.question_proj.bias)
-        x = torch.cat([visual_embedding.to(BF16), q], dim=1)
+        q = ag.linear(question_embedding.to(ag.ACT[0]), self.question_proj.weight, self.question_proj.bias)
+        x = torch.cat([visual_embedding.to(ag.ACT[0]), q], dim=1)
         x = ag.dropout(x, c[0].p, self.training)
         # fp32 out: BatchNorm centres its input, which would amplify bf16 rounding of x by |x| / std
         x = ag.linear(x, c[1].weight, c[1].bias, act="elu", out_f32=True)

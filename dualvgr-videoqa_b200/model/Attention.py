@@ -23,8 +23,8 @@ class AttentionSFGCN(nn.Module):
         if z.dim() != 4 or z.shape[1] != 2:
             raise NotImplementedError("AttentionSFGCN on sm_100a fuses exactly two views (reference model/models.py:163-166)")
         B, _, N, D = z.shape
-        zs = z.to(BF16).transpose(0, 1).reshape(2, B * N, D)
-        zero = torch.zeros((B, N, D), dtype=BF16, device=z.device)
+        zs = z.to(ag.ACT[0]).transpose(0, 1).reshape(2, B * N, D)
+        zero = torch.zeros((B, N, D), dtype=ag.ACT[0], device=z.device)
         _, embed = self.fused(zs, zero)
         hidden = ag.linear(zs, self.project[0].weight, self.project[0].bias, act="tanh")
         w = (hidden.float() @ self.project[2].weight.float().t()).view(2, B, N, 1).transpose(0, 1)

@@ -52,13 +52,16 @@ class punishGAT(nn.Module):
         B, N, _ = x.shape
         gate = gate_from_scores(scores, B, N, x.device)
         outs = ag.GatLayerFn.apply((0,), adj.float().contiguous(), self.dropout, self.training, self.n_heads,
-                                   x.to(BF16), gate, *self.flat_params())
+                                   x.to(ag.ACT[0]), gate, *self.flat_params())
         return outs[0][0].view(B, N, -1).to(x.dtype)
 
 
 def fused_gat_layer(gats, streams, xs, gates, adj, training):
     """Runs several punishGATs (<= 4) with one attention launch. gats[i] reads xs[streams[i]] / gates[streams[i]].
     Returns (per-stream stacks [n, B*N, D] bf16, per-graph fp32 [B,N,D])."""
+    if xs[0].dtype == torch.float32:
+        from dualvgr_videoqa_b200 import fp32_path
+        return fp32_path.gat_layer32(gats, streams, xs, gates, adj, training)
     ns = max(streams) + 1
     params = [p for g in gats for p in g.flat_params()]
     outs = ag.GatLayerFn.apply(tuple(streams), adj, gats[0].dropout, training, gats[0].n_heads, *xs, *gates, *params)

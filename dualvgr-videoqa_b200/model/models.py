@@ -58,6 +58,47 @@ class DualVGR(nn.Module):
         init_modules(self.modules(), w_init="xavier_uniform")
         nn.init.uniform_(self.linguistic_input_unit.encoder_embed.weight, -1.0, 1.0)
 
+    def set_precision(self, precision):
+        """"bf16" (default): bf16 activations / bf16 tensor-core products with fp32 accumulation, the fast path.
+        "fp32": fp32 activations, every product a 3 x bf16 split product (fp32_path.py) — the mode that meets the reference's
+        fp32 results to 1e-4. The setting is process-wide (autograd.ACT): one precision per process."""
+        if precision not in ("bf16", "fp32"):
+            raise ValueError(f"precision must be 'bf16' or 'fp32', got {precision!r}")
+        self.precision = precision
+        ag.ACT[0] = torch.float32 if precision == "fp32" else BF16
+        return self
+
+    def _forward_fp32(self, video_appearance_feat, video_motion_feat, question, question_len):
+        """fp32 mode: module-by-module, fp32 activations (fp32_path.py). Same returns as forward()."""
+        from dualvgr_videoqa_b200 import fp32_path as f32
+        ag.begin_forward()
+        training = self.training
+        B, N, T, Dv = video_appearance_feat.shape
+        D = self.visual_motion_input_unit.out_features
+        qlen = question_len.to(torch.int32)
+        lin = self.linguistic_input_unit
+        words, x_tm = f32.Embed32Fn.apply(question, lin.encoder_embed.weight,
+                                          float(lin.embedding_dropout.p) if training else 0.0)
+        seq, last = f32.Lstm32Fn.apply(x_tm, qlen, True, *lin._lstm_params())
+        dynamic_q = seq[:, :, :D]
+        question_embedding = ag.dropout(last[:, D:], lin.final_dropout.p, training)
+        enc = self.visual_appearance_input_unit
+        seed, sid = ag._site()
+        feats = video_appearance_feat if video_appearance_feat.dtype == BF16 else video_appearance_feat.float()
+        xa = ag.ops.prep_features(feats.contiguous().view(B * N * T, Dv), T, True, True,
+                                  enc.embedding_dropout.p if training else 0.0, seed, sid, out_dtype=torch.float32)
+        e = enc.encoder
+        _, h = f32.Lstm32Fn.apply(xa.view(T, B * N, Dv), None, False, e.weight_ih_l0, e.weight_hh_l0, e.bias_ih_l0, e.bias_hh_l0,
+                                  e.weight_ih_l0_reverse, e.weight_hh_l0_reverse, e.bias_ih_l0_reverse, e.bias_hh_l0_reverse)
+        app = ag.dropout(h, enc.finalvisual_dropout.p, training).view(B, N, D)
+        mot = ag.linear(video_motion_feat.float().contiguous().view(B * N, Dv), self.visual_motion_input_unit.weight,
+                        self.visual_motion_input_unit.bias).view(B, N, D)
+        visual, aq_embed, mq_embed, com_app, com_motion, aq_fusion, mq_fusion = self.visual_input_unit(
+            app, mot, dynamic_q, words, qlen)
+        pooled = self.feature_aggregation(visual)
+        out = self.output_unit(question_embedding, pooled)
+        return out, aq_embed, mq_embed, com_app, com_motion, aq_fusion, mq_fusion
+
     def forward(self, video_appearance_feat, video_motion_feat, question, question_len):
         """
         video_appearance_feat [B, N, F, vision_dim] fp32, video_motion_feat [B, N, vision_dim] fp32,
@@ -66,6 +107,8 @@ class DualVGR(nn.Module):
         """
         if not video_appearance_feat.is_cuda:
             raise RuntimeError("dualvgr_b200: DualVGR runs on sm_100a CUDA devices only; there is no CPU path")
+        if ag.ACT[0] == torch.float32:
+            return self._forward_fp32(video_appearance_feat, video_motion_feat, question, question_len)
         ag.begin_forward()
         dev = video_appearance_feat.device
         B, N = video_motion_feat.shape[:2]
@@ -162,10 +205,10 @@ class DualVGRUnit_multiple(nn.Module):
         (visual [B,N,D], aq_embed, mq_embed, com_app[U], com_motion[U], aq_fusion[U], mq_fusion[U])
         Module-by-module path (one autograd Function per mirrored module); DualVGR.forward uses fused()."""
         B, N, D = appearance_video_feat.shape
-        app = appearance_video_feat.to(BF16)
-        mot = motion_video_feat.to(BF16)
-        dq = dynamic_question_embedding.to(BF16)
-        words = pad_last(word_embedding).to(BF16)
+        app = appearance_video_feat.to(ag.ACT[0])
+        mot = motion_video_feat.to(ag.ACT[0])
+        dq = dynamic_question_embedding.to(ag.ACT[0])
+        words = pad_last(word_embedding).to(ag.ACT[0])
         qlen = question_len.to(torch.int32)
         adj = self.appearance_adj
         aq_fusion_list, mq_fusion_list, com_app_list, com_motion_list = [], [], [], []

@@ -50,8 +50,8 @@ class QueryAttn(nn.Module):
         returned as the padded bf16 [B, Wp] operand of the QueryPunish projections."""
         fast = word_dim is not None
         W = word_dim if fast else word_embedding.shape[-1]
-        words = word_embedding if fast else pad_last(word_embedding).to(BF16)
-        dq = dynamic_question_embedding if fast else dynamic_question_embedding.to(BF16)
+        words = word_embedding if fast else pad_last(word_embedding).to(ag.ACT[0])
+        dq = dynamic_question_embedding if fast else dynamic_question_embedding.to(ag.ACT[0])
         qlen = question_len if fast else question_len.to(torch.int32)
         y = ag.linear(dq, self.feat_enhance.weight, self.feat_enhance.bias)
         qc, attn = ag.QAttnFn.apply(y, words, qlen, self.fc.weight, self.fc.bias, W)
@@ -72,8 +72,8 @@ class QueryPunish(nn.Module):
     def forward(self, question_guided, visual_feature):
         """question_guided [B,W], visual_feature [B,N,D] -> scores [B,N,D/4] (a stride-0 expansion of [B,N,1], as in the
         reference :103)."""
-        q = self.query(pad_last(question_guided).to(BF16))
-        x = visual_feature.to(BF16)
+        q = self.query(pad_last(question_guided).to(ag.ACT[0]))
+        x = visual_feature.to(ag.ACT[0])
         g, _ = ag.GateFn.apply(x, x, torch.cat([q, q], dim=1))
         g = g.to(visual_feature.dtype).unsqueeze(-1)
         return g.expand(g.size(0), g.size(1), visual_feature.size(2) // 4)

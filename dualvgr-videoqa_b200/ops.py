@@ -428,6 +428,13 @@ def _empty(shape, dtype, like):
     return torch.empty(shape, dtype=dtype, device=like.device)
 
 
+def _v(name, t):
+    """Entry point `name` for the activation dtype of tensor t (bf16: the default build; fp32: the _f32 variant)."""
+    dt = t if isinstance(t, torch.dtype) else t.dtype
+    assert dt in (BF16, F32), dt
+    return _lib.variant(name, dt == F32)
+
+
 def colsum(x, out=None, accumulate=False, scale=1.0):
     """out[C] (+)= scale * sum over rows of x[R, C] (bf16 or fp32, last dim contiguous)."""
     assert x.dim() == 2 and x.stride(1) == 1
@@ -466,34 +473,35 @@ def cast_rows(w, out=None, out_cols=None, lstm_H=0):
     return out
 
 
-def prep_features(x, T, do_tanh, time_major, p=0.0, seed=0, stream_id=0):
+def prep_features(x, T, do_tanh, time_major, p=0.0, seed=0, stream_id=0, out_dtype=BF16):
     """x fp32 [S*T, C] (S sequences of T steps) -> bf16 [T*S, C] (time_major) / [S*T, C]: tanh(dropout(x)) in one pass."""
     assert x.dtype in (F32, BF16) and x.is_contiguous()
     C = x.shape[-1]
     rows = x.numel() // C
     S = rows // T
-    out = _empty((rows, C), BF16, x)
-    _lib.check(_lib.prep_features_ex(_ptr(x), 1 if x.dtype == BF16 else 0, _ptr(out), S, T, C, 1 if do_tanh else 0,
+    out = _empty((rows, C), out_dtype, x)
+    _lib.check(_v("prep_features_ex", out_dtype)(_ptr(x), 1 if x.dtype == BF16 else 0, _ptr(out), S, T, C, 1 if do_tanh else 0,
                                      1 if time_major else 0, float(p), int(seed), int(stream_id), _stream()),
                "dvgr_prep_features_ex")
     return out
 
 
 def dropout_raw(x, p, seed, stream_id, out=None):
-    assert x.dtype == BF16 and x.is_contiguous()
+    assert x.is_contiguous()
     if out is None:
         out = torch.empty_like(x)
-    _lib.check(_lib.dropout(_ptr(x), _ptr(out), x.numel(), float(p), int(seed), int(stream_id), _stream()), "dvgr_dropout")
+    assert out.dtype == x.dtype
+    _lib.check(_v("dropout", x)(_ptr(x), _ptr(out), x.numel(), float(p), int(seed), int(stream_id), _stream()), "dvgr_dropout")
     return out
 
 
 def act_bwd(dy, y, act, out=None, accumulate=False, p=0.0, seed=0, stream_id=0):
     """out (+)= dy * dropout_mask * act'(y) with y the activation output."""
-    assert dy.dtype == BF16 and dy.is_contiguous()
+    assert dy.is_contiguous() and (y is None or y.dtype == dy.dtype)
     if out is None:
         out = torch.empty_like(dy)
     a = _ACT[act] if not isinstance(act, int) else act
-    _lib.check(_lib.act_bwd(_ptr(dy), _ptr(y) if y is not None else _ptr(dy), _ptr(out), dy.numel(), a,
+    _lib.check(_v("act_bwd", dy)(_ptr(dy), _ptr(y) if y is not None else _ptr(dy), _ptr(out), dy.numel(), a,
                             1 if accumulate else 0, float(p), int(seed), int(stream_id), _stream()), "dvgr_act_bwd")
     return out
 
@@ -517,8 +525,8 @@ def scatter_add(pairs):
 
 
 def add_(a, b):
-    assert a.dtype == BF16 and b.dtype == BF16 and a.is_contiguous() and b.is_contiguous() and a.numel() == b.numel()
-    _lib.check(_lib.add(_ptr(a), _ptr(b), a.numel(), _stream()), "dvgr_add")
+    assert a.dtype == b.dtype and a.is_contiguous() and b.is_contiguous() and a.numel() == b.numel()
+    _lib.check(_v("add", a)(_ptr(a), _ptr(b), a.numel(), _stream()), "dvgr_add")
     return a
 
 
@@ -526,8 +534,9 @@ def qattn_fwd(y, wf, cf, qlen, words, W, ld_qc):
     B, L, D = y.shape
     alpha, nrm, prob = (_empty((B, L), F32, y) for _ in range(3))
     ssum = _empty((B,), F32, y)
-    qc = _empty((B, ld_qc), BF16, y)
-    _lib.check(_lib.qattn_fwd(_ptr(y), _ptr(wf), _ptr(cf), _ptr(qlen), _ptr(words), words.stride(1), B, L, D, W,
+    qc = _empty((B, ld_qc), y.dtype, y)
+    assert words.dtype == y.dtype
+    _lib.check(_v("qattn_fwd", y)(_ptr(y), _ptr(wf), _ptr(cf), _ptr(qlen), _ptr(words), words.stride(1), B, L, D, W,
                               _ptr(alpha), _ptr(nrm), _ptr(prob), _ptr(ssum), _ptr(qc), ld_qc, _stream()), "dvgr_qattn_fwd")
     return qc, alpha, nrm, prob, ssum
 
@@ -541,7 +550,8 @@ def qattn_bwd(dqc, y, wf, qlen, words, W, alpha, nrm, prob, ssum, dwords=None, r
         dwords = torch.zeros_like(words)
     dwf_part = _empty((B, D), F32, y)
     dcf_part = _empty((B, 1), F32, y)
-    _lib.check(_lib.qattn_bwd(_ptr(dqc), dqc.stride(0), _ptr(y), _ptr(wf), _ptr(qlen), _ptr(words), words.stride(1), B, L,
+    assert dqc.dtype == y.dtype
+    _lib.check(_v("qattn_bwd", y)(_ptr(dqc), dqc.stride(0), _ptr(y), _ptr(wf), _ptr(qlen), _ptr(words), words.stride(1), B, L,
                               D, W, _ptr(alpha), _ptr(nrm), _ptr(prob), _ptr(ssum), _ptr(dy), _ptr(dwords),
                               1 if acc else 0, _ptr(dwf_part), _ptr(dcf_part), _stream()), "dvgr_qattn_bwd")
     if raw:
@@ -552,7 +562,8 @@ def qattn_bwd(dqc, y, wf, qlen, words, W, alpha, nrm, prob, ssum, dwords=None, r
 def gate_fwd(xa, xm, query):
     B, N, D = xa.shape
     ga, gm = _empty((B, N), F32, xa), _empty((B, N), F32, xa)
-    _lib.check(_lib.gate_fwd(_ptr(xa), _ptr(xm), _ptr(query), query.stride(0), B, N, D, _ptr(ga), _ptr(gm), _stream()),
+    assert xm.dtype == xa.dtype == query.dtype
+    _lib.check(_v("gate_fwd", xa)(_ptr(xa), _ptr(xm), _ptr(query), query.stride(0), B, N, D, _ptr(ga), _ptr(gm), _stream()),
                "dvgr_gate_fwd")
     return ga, gm
 
@@ -561,7 +572,8 @@ def gate_bwd(xa, xm, query, ga, gm, dga, dga2, dgm, dgm2, dxa, dxm):
     """dxa / dxm are accumulated into; returns dquery [B, ld_q]."""
     B, N, D = xa.shape
     dquery = torch.empty_like(query)
-    _lib.check(_lib.gate_bwd(_ptr(xa), _ptr(xm), _ptr(query), query.stride(0), B, N, D, _ptr(ga), _ptr(gm), _ptr(dga),
+    assert dxa.dtype == xa.dtype and dxm.dtype == xa.dtype
+    _lib.check(_v("gate_bwd", xa)(_ptr(xa), _ptr(xm), _ptr(query), query.stride(0), B, N, D, _ptr(ga), _ptr(gm), _ptr(dga),
                              _ptr(dga2), _ptr(dgm), _ptr(dgm2), _ptr(dxa), _ptr(dxm), _ptr(dquery), _stream()),
                "dvgr_gate_bwd")
     return dquery
@@ -588,14 +600,14 @@ def gat_attn_fwd(whs, gates, avecs, adj, B, N, heads=4, slope=0.01, p_att=0.0, p
     G = len(whs)
     streams = streams or [2 * i for i in range(G)]
     if outs is None:
-        outs = [_empty((B * N, D), BF16, whs[0]) for _ in range(G)]
+        outs = [_empty((B * N, D), whs[0].dtype, whs[0]) for _ in range(G)]
     a = _gat_args(whs, gates, avecs, outs, adj, B, N, D, heads, slope, p_att, p_out, seed, streams)
     outs32 = None
     if want_f32:
         outs32 = [_empty((B, N, D), F32, whs[0]) for _ in range(G)]
         for i in range(G):
             a.graphs[i].out_f32 = outs32[i].data_ptr()
-    _lib.check(_lib.gat_attn_fwd(ctypes.byref(a), _stream()), "dvgr_gat_attn_fwd")
+    _lib.check(_v("gat_attn_fwd", whs[0])(ctypes.byref(a), _stream()), "dvgr_gat_attn_fwd")
     return outs, outs32
 
 
@@ -617,7 +629,7 @@ def gat_attn_bwd(whs, gates, avecs, outs, douts, adj, B, N, heads=4, slope=0.01,
         g.dout, g.dwh, g.dgate, g.davec = douts[i].data_ptr(), dwhs[i].data_ptr(), dgates[i].data_ptr(), dav_part[i].data_ptr()
         if douts32 is not None and douts32[i] is not None:
             g.dout_f32 = douts32[i].data_ptr()
-    _lib.check(_lib.gat_attn_bwd(ctypes.byref(a), _stream()), "dvgr_gat_attn_bwd")
+    _lib.check(_v("gat_attn_bwd", whs[0])(ctypes.byref(a), _stream()), "dvgr_gat_attn_bwd")
     if raw:                                             # per-video partials [G, B, heads * (2 Dh + 1)]: the caller reduces them
         return dwhs, dgates, dav_all
     dav = colsum_batched(dav_all)                       # per-video partial sums -> [G, heads * (2 Dh + 1)] in one launch pair
@@ -631,7 +643,7 @@ def view_attn_fwd(hidden, z, x, w2, want_embed=True):
     xnew = torch.empty_like(x)
     embed = torch.empty_like(x) if want_embed else None
     beta = _empty((M, 2), F32, x)
-    _lib.check(_lib.view_attn_fwd(_ptr(hidden), _ptr(z), _ptr(x), _ptr(w2), M, D, _ptr(xnew), _ptr(embed), _ptr(beta),
+    _lib.check(_v("view_attn_fwd", z)(_ptr(hidden), _ptr(z), _ptr(x), _ptr(w2), M, D, _ptr(xnew), _ptr(embed), _ptr(beta),
                                   _stream()), "dvgr_view_attn_fwd")
     return xnew, embed, beta
 
@@ -641,22 +653,22 @@ def view_attn_bwd(dxnew, dembed, hidden, z, w2, beta):
     dz, dhid = torch.empty_like(z), torch.empty_like(hidden)
     blocks = int(_lib.lib.dvgr_view_attn_bwd_blocks(M))
     part = _empty((blocks, D), F32, z)
-    _lib.check(_lib.view_attn_bwd(_ptr(dxnew), _ptr(dembed), _ptr(hidden), _ptr(z), _ptr(w2), _ptr(beta), M, D, _ptr(dz),
+    _lib.check(_v("view_attn_bwd", z)(_ptr(dxnew), _ptr(dembed), _ptr(hidden), _ptr(z), _ptr(w2), _ptr(beta), M, D, _ptr(dz),
                                   _ptr(dhid), _ptr(part), _stream()), "dvgr_view_attn_bwd")
     return dz, dhid, colsum(part)
 
 
 def mfb_fwd(x0, x1):
     M, mm2 = x0.shape
-    z = _empty((M, mm2 // 2), BF16, x0)
-    _lib.check(_lib.mfb_fwd(_ptr(x0), _ptr(x1), _ptr(z), M, mm2, _stream()), "dvgr_mfb_fwd")
+    z = _empty((M, mm2 // 2), x0.dtype, x0)
+    _lib.check(_v("mfb_fwd", x0)(_ptr(x0), _ptr(x1), _ptr(z), M, mm2, _stream()), "dvgr_mfb_fwd")
     return z
 
 
 def mfb_bwd(dz, x0, x1):
     M, mm2 = x0.shape
     d0, d1 = torch.empty_like(x0), torch.empty_like(x1)
-    _lib.check(_lib.mfb_bwd(_ptr(dz), _ptr(x0), _ptr(x1), _ptr(d0), _ptr(d1), M, mm2, _stream()), "dvgr_mfb_bwd")
+    _lib.check(_v("mfb_bwd", x0)(_ptr(dz), _ptr(x0), _ptr(x1), _ptr(d0), _ptr(d1), M, mm2, _stream()), "dvgr_mfb_bwd")
     return d0, d1
 
 
@@ -664,8 +676,8 @@ def readout_fwd(v, u, w, c, pooled=None):
     B, N, D = v.shape
     alpha = _empty((B, N), F32, v)
     if pooled is None:
-        pooled = _empty((B, D), BF16, v)
-    _lib.check(_lib.readout_fwd(_ptr(v), _ptr(u), _ptr(w), _ptr(c), B, N, D, _ptr(alpha), _ptr(pooled), pooled.stride(0),
+        pooled = _empty((B, D), v.dtype, v)
+    _lib.check(_v("readout_fwd", v)(_ptr(v), _ptr(u), _ptr(w), _ptr(c), B, N, D, _ptr(alpha), _ptr(pooled), pooled.stride(0),
                                 _stream()), "dvgr_readout_fwd")
     return pooled, alpha
 
@@ -674,7 +686,7 @@ def readout_bwd(dpooled, v, u, w, alpha):
     B, N, D = v.shape
     dv, du = torch.empty_like(v), torch.empty_like(u)
     dw_part, dc_part = _empty((B, D), F32, v), _empty((B, 1), F32, v)
-    _lib.check(_lib.readout_bwd(_ptr(dpooled), dpooled.stride(0), _ptr(v), _ptr(u), _ptr(w), _ptr(alpha), B, N, D, _ptr(dv),
+    _lib.check(_v("readout_bwd", v)(_ptr(dpooled), dpooled.stride(0), _ptr(v), _ptr(u), _ptr(w), _ptr(alpha), B, N, D, _ptr(dv),
                                 _ptr(du), _ptr(dw_part), _ptr(dc_part), _stream()), "dvgr_readout_bwd")
     return dv, du, colsum(dw_part), colsum(dc_part)
 
@@ -687,12 +699,12 @@ def bn_stats(x):
     return out
 
 
-def bn_fwd(x, gamma, beta, run_mean, run_var, training, momentum=0.1, eps=1e-5, ext_stats=None, Btot=0):
+def bn_fwd(x, gamma, beta, run_mean, run_var, training, momentum=0.1, eps=1e-5, ext_stats=None, Btot=0, out_dtype=BF16):
     """ext_stats [2, D] = all-reduced bn_stats over a global batch of Btot rows (synchronised BatchNorm)."""
     B, D = x.shape
-    y = _empty((B, D), BF16, x)
+    y = _empty((B, D), out_dtype, x)
     mean, rstd = _empty((D,), F32, x), _empty((D,), F32, x)
-    _lib.check(_lib.bn_fwd_ex(_ptr(x), 1 if x.dtype == F32 else 0, B, D, _ptr(gamma), _ptr(beta), _ptr(run_mean), _ptr(run_var),
+    _lib.check(_v("bn_fwd_ex", out_dtype)(_ptr(x), 1 if x.dtype == F32 else 0, B, D, _ptr(gamma), _ptr(beta), _ptr(run_mean), _ptr(run_var),
                               1 if training else 0, momentum, eps, _ptr(y), _ptr(mean), _ptr(rstd), _ptr(ext_stats),
                               Btot if ext_stats is not None else B, _stream()), "dvgr_bn_fwd")
     return y, mean, rstd
@@ -704,7 +716,8 @@ def bn_bwd(dy, x, gamma, mean, rstd, training, ext_sums=None, Btot=0, stats_only
     B, D = x.shape
     dx = None if stats_only else torch.empty_like(x)
     dgamma, dbeta = _empty((D,), F32, x), _empty((D,), F32, x)
-    _lib.check(_lib.bn_bwd_ex(_ptr(dy), _ptr(x), 1 if x.dtype == F32 else 0, B, D, _ptr(gamma), _ptr(mean), _ptr(rstd),
+    assert dy.dtype == BF16 or x.dtype == F32
+    _lib.check(_v("bn_bwd_ex", dy)(_ptr(dy), _ptr(x), 1 if x.dtype == F32 else 0, B, D, _ptr(gamma), _ptr(mean), _ptr(rstd),
                               1 if training else 0, _ptr(dx), _ptr(dgamma), _ptr(dbeta), _ptr(ext_sums),
                               Btot if ext_sums is not None else B, 1 if stats_only else 0, _stream()), "dvgr_bn_bwd")
     return dx, dgamma, dbeta
@@ -835,15 +848,15 @@ def gat_input_bwd(dxts, streams, per_stream, bases, outs, p, seed):
     return outs
 
 
-def embed_fwd(tokens, table, Wp, p=0.0, seed=0, stream_id=0):
+def embed_fwd(tokens, table, Wp, p=0.0, seed=0, stream_id=0, out_dtype=BF16):
     """words [B, L, Wp] bf16 and time-major x [L, B, Wp] bf16 = tanh(dropout(table[tokens])), zero-padded to Wp columns."""
     _check_cuda(tokens, table)
     B, L = tokens.shape
     V, W = table.shape
     assert tokens.dtype == torch.int64 and tokens.is_contiguous() and table.dtype == F32 and table.is_contiguous()
-    words = torch.empty((B, L, Wp), dtype=BF16, device=table.device)
-    x_tm = torch.empty((L, B, Wp), dtype=BF16, device=table.device)
-    _lib.check(_lib.embed_fwd(_ptr(tokens), _ptr(table), B, L, W, Wp, _ptr(words), _ptr(x_tm), float(p), int(seed),
+    words = torch.empty((B, L, Wp), dtype=out_dtype, device=table.device)
+    x_tm = torch.empty((L, B, Wp), dtype=out_dtype, device=table.device)
+    _lib.check(_v("embed_fwd", out_dtype)(_ptr(tokens), _ptr(table), B, L, W, Wp, _ptr(words), _ptr(x_tm), float(p), int(seed),
                               int(stream_id), _stream()), "dvgr_embed_fwd")
     return words, x_tm
 
@@ -853,8 +866,8 @@ def embed_bwd(tokens, words, d_words, d_x_tm, W, dtable, p=0.0, seed=0, stream_i
     B, L, Wp = words.shape
     assert dtable.dtype == F32 and dtable.is_contiguous() and dtable.shape[1] == W
     for t in (d_words, d_x_tm):
-        assert t is None or (t.dtype == BF16 and t.is_contiguous() and t.numel() == words.numel())
-    _lib.check(_lib.embed_bwd(_ptr(tokens), _ptr(words), _ptr(d_words), _ptr(d_x_tm), B, L, W, Wp, _ptr(dtable), float(p),
+        assert t is None or (t.dtype == words.dtype and t.is_contiguous() and t.numel() == words.numel())
+    _lib.check(_v("embed_bwd", words)(_ptr(tokens), _ptr(words), _ptr(d_words), _ptr(d_x_tm), B, L, W, Wp, _ptr(dtable), float(p),
                               int(seed), int(stream_id), _stream()), "dvgr_embed_bwd")
     return dtable
 
@@ -968,10 +981,13 @@ def split3(x, out=None):
     return out
 
 
-def gemm3(A3, a_major, B3, b_major, M, N, K, C, **kw):
+def gemm3(A3, a_major, B3, b_major, M, N, K, C, batch=1, a_shared=False, b_shared=False, **kw):
     """fp32-accurate product of two split operands (split3 planes, [3, rows, cols]): C (fp32) = act(A B^T + bias) (+ C).
-    K is the TRUE reduction length; operands as for gemm() (major 0: [rows, K], major 1: [K, rows])."""
-    assert C.dtype == F32 and A3.shape[0] == 3 and B3.shape[0] == 3
+    K is the TRUE reduction length; operands as for gemm() (major 0: [rows, K], major 1: [K, rows]).
+    batch > 1: operands are [batch * 3, rows, cols] (the planes of problem b at 3b .. 3b+2; a_shared / b_shared: every problem
+    reads the planes of problem 0), C is [batch, M, N] with c_batch given by the caller."""
+    assert C.dtype == F32 and A3.shape[0] == (3 if a_shared else 3 * batch) and B3.shape[0] == (3 if b_shared else 3 * batch)
     kin = (K + 63) // 64
-    return gemm(A3, a_major, B3, b_major, M, N, 3 * kin * 64, C, k_inner=kin, a_c2=[0], a_c2_step=[1], b_c2=[2], b_c2_step=[-1],
-                **kw)
+    return gemm(A3, a_major, B3, b_major, M, N, 3 * kin * 64, C, k_inner=kin, batch=batch,
+                a_c2=[0 if a_shared else 3 * b for b in range(batch)], a_c2_step=[1] * batch,
+                b_c2=[2 if b_shared else 3 * b + 2 for b in range(batch)], b_c2_step=[-1] * batch, **kw)

@@ -441,6 +441,96 @@ int dvgr_adam_step(float* params, const float* grads, float* exp_avg, float* exp
 int dvgr_finalize_loss(const float* ce, const float* parts, int rows, const int* const* flags, int n_flags, float* out,
                        void* stream);
 
+/* ======================================================================================================================
+ * fp32 mode (north_star: "within 1e-4 relative error in fp32"). The streaming kernel families above are compiled a second
+ * time with fp32 activations (csrc/act.cuh: act_t = float) and exported under the suffix _f32: IDENTICAL signatures, every
+ * activation pointer documented as bf16 above is a float pointer here (row strides stay in elements). GEMM-shaped work in
+ * fp32 mode runs on the same tcgen05 kernel through three bf16 planes per operand (dvgr_split3 + the k_inner plane
+ * segmentation of dvgr_gemm: a_lo b_hi + a_hi b_hi + a_hi b_lo, < 2e-5 of the float64 product); the recurrent cells run in
+ * dvgr_lstm32_cell_fwd / _bwd below.
+ * ====================================================================================================================== */
+int dvgr_gat_attn_fwd_f32(const dvgr_gat_args* args, void* stream);
+int dvgr_gat_attn_bwd_f32(const dvgr_gat_args* args, void* stream);
+int dvgr_qattn_fwd_f32(const void* y, const float* wf, const float* cf, const int* qlen, const void* words, long long ld_w,
+                   int B, int L, int D, int W, float* alpha, float* nrm, float* prob, float* ssum, void* qc,
+                   long long ld_qc, void* stream);
+int dvgr_qattn_bwd_f32(const void* dqc, long long ld_qc, const void* y, const float* wf, const int* qlen, const void* words,
+                   long long ld_w, int B, int L, int D, int W, const float* alpha, const float* nrm, const float* prob,
+                   const float* ssum, void* dy, void* dwords, int accumulate_dwords, float* dwf_part, float* dcf_part,
+                   void* stream);
+int dvgr_gate_fwd_f32(const void* x0, const void* x1, const void* query, long long ld_q, int B, int N, int D, float* gate0,
+                  float* gate1, void* stream);
+int dvgr_gate_bwd_f32(const void* x0, const void* x1, const void* query, long long ld_q, int B, int N, int D,
+                  const float* gate0, const float* gate1, const float* dg0a, const float* dg0b, const float* dg1a,
+                  const float* dg1b, void* dx0, void* dx1, void* dquery, void* stream);
+int dvgr_view_attn_fwd_f32(const void* hidden, const void* z, const void* x, const float* w2, long long M, int D, void* xnew,
+                       void* embed, float* beta, void* stream);
+int dvgr_view_attn_bwd_f32(const void* dxnew, const void* dembed_ext, const void* hidden, const void* z, const float* w2,
+                       const float* beta, long long M, int D, void* dz, void* dhid, float* dw2_part, void* stream);
+int dvgr_mfb_fwd_f32(const void* x0, const void* x1, void* z, long long M, int mm2, void* stream);
+int dvgr_mfb_bwd_f32(const void* dz, const void* x0, const void* x1, void* d0, void* d1, long long M, int mm2, void* stream);
+int dvgr_readout_fwd_f32(const void* v, const void* u, const float* w, const float* c, int B, int N, int D, float* alpha,
+                     void* pooled, long long ld_p, void* stream);
+int dvgr_readout_bwd_f32(const void* dpooled, long long ld_p, const void* v, const void* u, const float* w,
+                     const float* alpha, int B, int N, int D, void* dv, void* du, float* dw_part, float* dc_part,
+                     void* stream);
+int dvgr_bn_fwd_ex_f32(const void* x, int x_is_f32, int B, int D, const float* gamma, const float* beta, float* run_mean,
+                   float* run_var, int training, float momentum, float eps, void* y, float* mean_out, float* rstd_out,
+                   const float* ext_stats, int Btot, void* stream);
+int dvgr_bn_bwd_ex_f32(const void* dy, const void* x, int x_is_f32, int B, int D, const float* gamma, const float* mean,
+                   const float* rstd, int training, void* dx, float* dgamma, float* dbeta, const float* ext_sums, int Btot,
+                   int stats_only, void* stream);
+int dvgr_prep_features_ex_f32(const void* in, int in_is_bf16, void* out, long long S, int T, int C, int do_tanh,
+                          int time_major, float p, unsigned long long seed, unsigned int drop_stream, void* stream);
+int dvgr_dropout_f32(const void* in, void* out, long long n, float p, unsigned long long seed, unsigned int drop_stream,
+                 void* stream);
+int dvgr_act_bwd_f32(const void* dy, const void* y, void* out, long long n, int act, int accumulate, float p,
+                 unsigned long long seed, unsigned int drop_stream, void* stream);
+int dvgr_add_f32(void* a, const void* b, long long n, void* stream);
+int dvgr_embed_fwd_f32(const long long* tokens, const float* table, int B, int L, int W, int Wp, void* words, void* x_tm,
+                   float p, unsigned long long seed, unsigned int drop_stream, void* stream);
+int dvgr_embed_bwd_f32(const long long* tokens, const void* words, const void* d_words, const void* d_x_tm, int B, int L, int W,
+                   int Wp, float* dtable, float p, unsigned long long seed, unsigned int drop_stream, void* stream);
+
+/* fp32 recurrent cell (csrc/lstm32.cu), one launch per time step s of all `ndir` directions (odd directions run backwards:
+ * time t = T-1-s). nn.LSTM gate order (i|f|g|o blocks of H). Replaces the cuDNN cell of nn.LSTM for fp32 mode
+ * (reference model/Preprocessing.py:97-101,202).
+ *   gates        [T][S][ndir*4H] f32: x W_ih^T + b_ih + b_hh on entry; forward overwrites the step's rows with the ACTIVATED
+ *                gates, backward overwrites them with the pre-activation gate gradients
+ *   rec          [ndir][S][4H] f32: h_{prev} W_hh^T of this step (unused at s == 0)
+ *   h            [ndir][S][H] f32 running state; h_planes [ndir][3][S][H] bf16 split of the new state (next step's operand)
+ *   c_hist       [T+1][ndir][S][H] f32 by step (slot s in, slot s+1 out; slot 0 is never read)
+ *   hprev_t      [ndir][T][S][H] f32: the state BEFORE time t (operand of the W_hh gradient)
+ *   seq_out      optional [S][T][seq_out_ld]: h_t at valid positions, 0 at padded ones; h_last [S][h_last_ld] (written at the
+ *                last step: the state after the last VALID position, like a packed sequence)
+ *   seq_len      optional [S] int32
+ * backward: dh / dc [ndir][S][H] f32 running gradients (dh is re-initialised with the part that by-passes the gates; the
+ * caller then accumulates dgates W_hh into it), dgate_planes [ndir][3][S][4H] bf16, dh_last [S][dh_last_ld], dh_seq
+ * [S][T][dh_seq_ld] (optional). */
+typedef struct dvgr_lstm32_args {
+  int S, H, T, ndir, s;
+  float* gates;
+  const float* rec;
+  float* h;
+  float* c_hist;
+  void* h_planes;
+  float* hprev_t;
+  float* seq_out;
+  long long seq_out_ld;
+  float* h_last;
+  long long h_last_ld;
+  const int* seq_len;
+  float* dh;
+  float* dc;
+  void* dgate_planes;
+  const float* dh_last;
+  long long dh_last_ld;
+  const float* dh_seq;
+  long long dh_seq_ld;
+} dvgr_lstm32_args;
+int dvgr_lstm32_cell_fwd(const dvgr_lstm32_args* args, void* stream);
+int dvgr_lstm32_cell_bwd(const dvgr_lstm32_args* args, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,6 +19,18 @@ for f in "$SRC"/*.cu; do
     pids+=($!)
   fi
 done
-for p in "${pids[@]:-}"; do [[ -n "$p" ]] && wait "$p"; done
+# fp32-activation variants of the streaming kernel families (same sources, act_t = float, entry points suffixed _f32)
+for n in qpm fused gat; do
+  f="$SRC/$n.cu"
+  o="$ROOT/build/${n}_f32.o"
+  objs+=("$o")
+  if [[ ! -f "$o" || "$f" -nt "$o" || -n "$(find "$SRC" -name '*.cuh' -newer "$o" -print -quit)" || -n "$(find "$SRC" "$ROOT/include" -name '*.h' -newer "$o" -print -quit)" ]]; then
+    "$NVCC" "${FLAGS[@]}" -DDVGR_F32 -c "$f" -o "$o" &
+    pids+=($!)
+  fi
+done
+rc=0
+for p in "${pids[@]:-}"; do [[ -n "$p" ]] && { wait "$p" || rc=1; }; done
+[[ $rc -eq 0 ]] || { echo "compile failed" >&2; exit 1; }
 "$NVCC" -shared -o "$OUT" "${objs[@]}" -lcudart_static -lpthread -ldl -lrt
 echo "built $OUT"

@@ -191,7 +191,7 @@ class Lstm32Args(ctypes.Structure):
                 ("gates", c_void_p), ("rec", c_void_p), ("h", c_void_p), ("c_hist", c_void_p), ("h_planes", c_void_p),
                 ("hprev_t", c_void_p), ("seq_out", c_void_p), ("seq_out_ld", c_ll), ("h_last", c_void_p), ("h_last_ld", c_ll),
                 ("seq_len", c_void_p), ("dh", c_void_p), ("dc", c_void_p), ("dgate_planes", c_void_p),
-                ("dh_last", c_void_p), ("dh_last_ld", c_ll), ("dh_seq", c_void_p), ("dh_seq_ld", c_ll)]
+                ("dh_last", c_void_p), ("dh_last_ld", c_ll), ("dh_seq", c_void_p), ("dh_seq_ld", c_ll), ("dgates", c_void_p)]
 
 
 lstm32_cell_fwd = _sig("dvgr_lstm32_cell_fwd", [ctypes.POINTER(Lstm32Args), P])

@@ -672,7 +672,7 @@ __global__ void __launch_bounds__(kGatThreads) gat_attn_bwd_kernel(const GatPara
 //   dV[j][c]     = sum_i P~^T[k][j][i] dz[i][c]               A = P~^T (bf16 high + low halves), B = dz (ldmatrix.trans)
 // and everything that hangs off them (gate / attention-vector gradients, dWh) is folded into the fragment epilogues.
 // dgate receives the two head pairs' partial sums by atomicAdd: the caller zeroes it (two addends: deterministic).
-// NP = 32 nodes: kBH = 2 heads per CTA (72 KB, 3 CTAs / SM); NP = 64 nodes (BASELINE config 5): kBH = 1 head per CTA (93 KB, 2 / SM)
+// NP = 32 nodes: kBH = 2 heads per CTA (97 KB, 2 CTAs / SM); NP = 64 nodes (BASELINE config 5): kBH = 1 head per CTA (119 KB, 1 / SM)
 template <int NP, int kBH> struct GatFastBwd {
   static constexpr int BC = kBH * kFDh;            // columns per CTA
   static constexpr int BWP = BC + 8;               // tile row pitch (elements): an odd multiple of 16 B
@@ -682,11 +682,15 @@ template <int NP, int kBH> struct GatFastBwd {
   static constexpr size_t DP_BYTES = (size_t)kBH * NP * NPF * 4;
   static constexpr size_t SMALL_BYTES = (size_t)(4 * kBH * NP + 2 * NP + 8) * 4;      // s, t, ds, dt, gate, dg, dc
   static constexpr size_t ADJ_BYTES = (size_t)NP * NP;
-  static constexpr size_t BYTES = 2 * TILE_BYTES + PT_BYTES + DP_BYTES + SMALL_BYTES + ADJ_BYTES;
+  // + a third tile: the LOW half of dz. dV_j = sum_i P_ij dz_i averages dz over the (near-uniformly attended) nodes, and the
+  // gradients of the auxiliary losses are centred over the nodes: the true sum is a small residual of large terms, so dz
+  // rounded to ONE bf16 turns it into noise (measured: 6x error on the full-loss gradient of config 2); dz = hi + lo does not.
+  static constexpr size_t LO_OFFSET = 2 * TILE_BYTES + PT_BYTES + DP_BYTES + SMALL_BYTES + ((ADJ_BYTES + 15) & ~(size_t)15);
+  static constexpr size_t BYTES = LO_OFFSET + TILE_BYTES;
 };
 
 template <int NP, int kBH>
-__global__ void __launch_bounds__(kFThreads, (NP == 32) ? 3 : 2) gat_attn_bwd_mma_kernel(const GatParams p) {
+__global__ void __launch_bounds__(kFThreads, (NP == 32) ? 2 : 1) gat_attn_bwd_mma_kernel(const GatParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   using FB = GatFastBwd<NP, kBH>;
   constexpr int PP = FB::PP, NPF = FB::NPF, MT = FB::MT, kBC = FB::BC, kBWP = FB::BWP;
@@ -694,6 +698,7 @@ __global__ void __launch_bounds__(kFThreads, (NP == 32) ? 3 : 2) gat_attn_bwd_mm
   constexpr int WPH = (kFThreads / 32) / kBH;      // warps per head
   __nv_bfloat16* wh = reinterpret_cast<__nv_bfloat16*>(smem_raw);                                // [NP][kBWP]
   __nv_bfloat16* dz = reinterpret_cast<__nv_bfloat16*>(smem_raw + FB::TILE_BYTES);
+  __nv_bfloat16* dzl = reinterpret_cast<__nv_bfloat16*>(smem_raw + FB::LO_OFFSET);                // low half of dz
   __nv_bfloat16* PThi = reinterpret_cast<__nv_bfloat16*>(smem_raw + 2 * FB::TILE_BYTES);         // [kBH][NP (j)][PP (i)]
   __nv_bfloat16* PTlo = PThi + (size_t)kBH * NP * PP;
   float* dP = reinterpret_cast<float*>(smem_raw + 2 * FB::TILE_BYTES + FB::PT_BYTES);            // [kBH][NP (i)][NPF (j)]
@@ -781,8 +786,9 @@ __global__ void __launch_bounds__(kFThreads, (NP == 32) ? 3 : 2) gat_attn_bwd_mm
           const uint32_t* hw = reinterpret_cast<const uint32_t*>(&hv[u]);
           const uint32_t* dw = reinterpret_cast<const uint32_t*>(&dv[u]);
           const unsigned long long mrow = ((unsigned long long)b * N + i) * (kFD / 2) + ((col0 + c) >> 1);
-          uint4 o;
+          uint4 o, ol;
           uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+          uint32_t* olw = reinterpret_cast<uint32_t*>(&ol);
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             float2 h = unpack_bf16x2(hw[e]);
@@ -796,15 +802,20 @@ __global__ void __launch_bounds__(kFThreads, (NP == 32) ? 3 : 2) gat_attn_bwd_mm
               h.x *= keepf;     // recover ELU(z) of the kept elements (dropped ones have zero gradient anyway)
               h.y *= keepf;
             }
-            ow[e] = pack_bf16x2(d.x * elu_grad_from_out(h.x), d.y * elu_grad_from_out(h.y));
+            const float zx = d.x * elu_grad_from_out(h.x), zy = d.y * elu_grad_from_out(h.y);
+            ow[e] = pack_bf16x2(zx, zy);
+            const float2 hi = unpack_bf16x2(ow[e]);
+            olw[e] = pack_bf16x2(zx - hi.x, zy - hi.y);
           }
           *reinterpret_cast<uint4*>(dz + (size_t)i * kBWP + c) = o;
+          *reinterpret_cast<uint4*>(dzl + (size_t)i * kBWP + c) = ol;
         }
       }
     }
     for (int v = items + tid; v < NP * (kBC / 8); v += kFThreads) {      // zero rows N .. NP-1
       const int i = v / (kBC / 8), c = (v - i * (kBC / 8)) * 8;
       *reinterpret_cast<uint4*>(dz + (size_t)i * kBWP + c) = make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(dzl + (size_t)i * kBWP + c) = make_uint4(0, 0, 0, 0);
     }
   }
   fast_stage_wait();
@@ -955,7 +966,7 @@ __global__ void __launch_bounds__(kFThreads, (NP == 32) ? 3 : 2) gat_attn_bwd_mm
     constexpr int CW = kBC / (kFThreads / 32), NT4 = CW / 8;
     constexpr bool kResident = (MT == 2);            // A fragments of both row blocks fit in registers only for NP = 32
     const int kl = warp / WPH, k = head0 + kl, cbl = CW * warp;      // column base inside the CTA's columns
-    const uint32_t dz_s = smem_u32(dz), phi_s = smem_u32(PThi), plo_s = smem_u32(PTlo);
+    const uint32_t dz_s = smem_u32(dz), dzl_s = smem_u32(dzl), phi_s = smem_u32(PThi), plo_s = smem_u32(PTlo);
     const int ksteps = (N + 15) >> 4;
     const float* a1 = gr.avec + k * (2 * kFDh + 1);
     const float* a2 = a1 + kFDh;
@@ -986,10 +997,12 @@ __global__ void __launch_bounds__(kFThreads, (NP == 32) ? 3 : 2) gat_attn_bwd_mm
 #pragma unroll 1
     for (int nt = 0; nt < NT4; ++nt) {
       const int c = cbl + nt * 8 + 2 * t, cl = c - kl * kFDh;      // column inside the CTA's columns / inside the head
-      uint32_t bfr[MT][2];
+      uint32_t bfr[MT][2], bfl[MT][2];
 #pragma unroll
-      for (int ks = 0; ks < MT; ++ks)
+      for (int ks = 0; ks < MT; ++ks) {
         ldsm_x2_trans(bfr[ks][0], bfr[ks][1], dz_s + (uint32_t)((((size_t)ks * 16 + lrow) * kBWP + cbl + nt * 8) * 2));
+        ldsm_x2_trans(bfl[ks][0], bfl[ks][1], dzl_s + (uint32_t)((((size_t)ks * 16 + lrow) * kBWP + cbl + nt * 8) * 2));
+      }
       const float a1x = __ldg(a1 + cl), a1y = __ldg(a1 + cl + 1), a2x = __ldg(a2 + cl), a2y = __ldg(a2 + cl + 1);
       float da1x = 0.f, da1y = 0.f, da2x = 0.f, da2y = 0.f;
 #pragma unroll
@@ -1007,8 +1020,9 @@ __global__ void __launch_bounds__(kFThreads, (NP == 32) ? 3 : 2) gat_attn_bwd_mm
 #pragma unroll
           for (int ks = 0; ks < MT; ++ks) {
             if (ks < ksteps) {
-              mma_bf16(acc, ahi[kResident ? mt : 0][ks], bfr[ks][0], bfr[ks][1]);
+              mma_bf16(acc, ahi[kResident ? mt : 0][ks], bfl[ks][0], bfl[ks][1]);
               mma_bf16(acc, alo[kResident ? mt : 0][ks], bfr[ks][0], bfr[ks][1]);
+              mma_bf16(acc, ahi[kResident ? mt : 0][ks], bfr[ks][0], bfr[ks][1]);
             }
           }
 #pragma unroll

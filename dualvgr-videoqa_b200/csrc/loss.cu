@@ -60,7 +60,7 @@ __device__ __forceinline__ void load_centered_chunk(const float* __restrict__ x,
   }
 }
 
-// pass 1: partial centred Gram matrices of one (video, job, column chunk): T T^T on the tensor cores (TF32 m16n8k8)
+// pass 1: partial centred Gram matrices of one (video, job, column chunk): T T^T on the tensor cores (error-compensated 3 x TF32 m16n8k8: ptx.cuh)
 __global__ void __launch_bounds__(kLossThreads) pair_gram_kernel(const PairParams p) {
   extern __shared__ __align__(16) float sm[];
   float* tile = sm;   // [2][NP16][kTS]
@@ -79,8 +79,7 @@ __global__ void __launch_bounds__(kLossThreads) pair_gram_kernel(const PairParam
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 4
     for (int k0 = 0; k0 < kChunk; k0 += 8)
-      mma_tf32(acc, to_tf32(ar[k0]), to_tf32(ar[8 * kTS + k0]), to_tf32(ar[k0 + 4]), to_tf32(ar[8 * kTS + k0 + 4]),
-               to_tf32(br[k0]), to_tf32(br[k0 + 4]));
+      mma_tf32x3(acc, ar[k0], ar[8 * kTS + k0], ar[k0 + 4], ar[8 * kTS + k0 + 4], br[k0], br[k0 + 4]);
     const int row = mt * 16 + g, col = nt * 8 + 2 * t;
     float* o = out + which * N * N;
     if (row < N && col < N) o[row * N + col] = acc[0];
@@ -187,14 +186,6 @@ __global__ void __launch_bounds__(kLossThreads) pair_grad_kernel(const PairParam
   }
   __syncthreads();
   if (J.dx == nullptr && J.dy == nullptr) return;
-  // the N x N left operands of the gradient products are used as TF32 from here on: round them ONCE instead of
-  // converting every fragment element inside the MMA loop
-  if (J.mode == 0) {
-    for (int e = tid; e < NP * CS; e += kLossThreads) Delta[e] = __uint_as_float(to_tf32(Delta[e]));
-  } else {
-    for (int e = tid; e < 2 * NP * CS; e += kLossThreads) C[e] = __uint_as_float(to_tf32(C[e]));
-  }
-  __syncthreads();
 
   const int MT = NP / 16;
   for (int which = 0; which < 2; ++which) {
@@ -210,14 +201,13 @@ __global__ void __launch_bounds__(kLossThreads) pair_grad_kernel(const PairParam
 #pragma unroll
       for (int m = 0; m < 4; ++m) acc[m][0] = acc[m][1] = acc[m][2] = acc[m][3] = 0.f;
       for (int k0 = 0; k0 < NP; k0 += 8) {
-        const uint32_t b0 = to_tf32(Bt[(size_t)(k0 + t) * kTS + nt * 8 + g]);
-        const uint32_t b1 = to_tf32(Bt[(size_t)(k0 + t + 4) * kTS + nt * 8 + g]);
+        const float b0 = Bt[(size_t)(k0 + t) * kTS + nt * 8 + g];
+        const float b1 = Bt[(size_t)(k0 + t + 4) * kTS + nt * 8 + g];
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
           if (m < MT) {
             const float* ar = A + (size_t)(m * 16 + g) * CS + k0 + t;
-            mma_tf32(acc[m], __float_as_uint(ar[0]), __float_as_uint(ar[8 * CS]), __float_as_uint(ar[4]),
-                     __float_as_uint(ar[8 * CS + 4]), b0, b1);
+            mma_tf32x3(acc[m], ar[0], ar[8 * CS], ar[4], ar[8 * CS + 4], b0, b1);
           }
         }
       }
@@ -324,8 +314,7 @@ __global__ void __launch_bounds__(kLossThreads) aux_gram_kernel(const AuxParams 
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 4
     for (int k0 = 0; k0 < kChunk; k0 += 8)
-      mma_tf32(acc, to_tf32(ar[k0]), to_tf32(ar[8 * kTS + k0]), to_tf32(ar[k0 + 4]), to_tf32(ar[8 * kTS + k0 + 4]),
-               to_tf32(br[k0]), to_tf32(br[k0 + 4]));
+      mma_tf32x3(acc, ar[k0], ar[8 * kTS + k0], ar[k0 + 4], ar[8 * kTS + k0 + 4], br[k0], br[k0 + 4]);
     const int row = mt * 16 + g, col = nt * 8 + 2 * t;
     if (row < N && col < N) atomicAdd(out + row * N + col, acc[0]);
     if (row < N && col + 1 < N) atomicAdd(out + row * N + col + 1, acc[1]);

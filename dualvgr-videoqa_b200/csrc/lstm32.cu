@@ -98,7 +98,8 @@ lstm32_cell_bwd_kernel(dvgr_lstm32_args a) {
       dc = dct * gf;
       dh = 0.f;
     }
-    g[0] = di; g[a.H] = df; g[2 * a.H] = dg; g[3 * a.H] = dov;
+    float* go_ = a.dgates != nullptr ? a.dgates + (g - a.gates) : g;
+    go_[0] = di; go_[a.H] = df; go_[2 * a.H] = dg; go_[3 * a.H] = dov;
     store_planes(gp, plane, di);
     store_planes(gp + a.H, plane, df);
     store_planes(gp + 2 * a.H, plane, dg);

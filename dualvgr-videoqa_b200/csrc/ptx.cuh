@@ -181,6 +181,23 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1
                : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
+// error-compensated TF32 product ("3 x TF32"): every fp32 operand is split into hi = tf32(x) and lo = tf32(x - hi) and the
+// product accumulated as a_lo b_hi + a_hi b_lo + a_hi b_hi (small terms first): fp32-grade accuracy (~2^-21 per product
+// instead of TF32's 2^-11) on the tensor cores. The auxiliary losses need it: they subtract nearly equal Gram matrices, which
+// amplifies a plain TF32 rounding of the centred embeddings into a 50 % gradient error.
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  hi = to_tf32(x);
+  lo = to_tf32(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32x3(float (&c)[4], float a0, float a1, float a2, float a3, float b0, float b1) {
+  uint32_t ah[4], al[4], bh[2], bl[2];
+  split_tf32(a0, ah[0], al[0]); split_tf32(a1, ah[1], al[1]); split_tf32(a2, ah[2], al[2]); split_tf32(a3, ah[3], al[3]);
+  split_tf32(b0, bh[0], bl[0]); split_tf32(b1, bh[1], bl[1]);
+  mma_tf32(c, al[0], al[1], al[2], al[3], bh[0], bh[1]);
+  mma_tf32(c, ah[0], ah[1], ah[2], ah[3], bl[0], bl[1]);
+  mma_tf32(c, ah[0], ah[1], ah[2], ah[3], bh[0], bh[1]);
+}
+
 // warp-level BF16 tensor-core MMA (m16n8k16, fp32 accumulate) + ldmatrix fragment loads, for the per-video N x N graph
 // products whose operands already sit in shared memory as bf16 (tiles far too small for a tcgen05 128-row MMA).
 //   A (16x16, row): a0 (g, 2t..2t+1) a1 (g+8, 2t..) a2 (g, 2t+8..) a3 (g+8, 2t+8..) ; B (16x8, col): b0 (k=2t..2t+1, n=g)

@@ -168,7 +168,8 @@ class Lstm32Fn(Function):
         dc = torch.empty((D, S, H), dtype=F32, device=dev)
         dgp = torch.empty((D, 3, S, 4 * H), dtype=BF16, device=dev)
         a = _lstm32_args(S, H, T, D, gates, c_hist, seq_len)
-        a.dh, a.dc, a.dgate_planes = dh.data_ptr(), dc.data_ptr(), dgp.data_ptr()
+        dgates = torch.empty_like(gates)        # (the saved activated gates stay intact: the graph can be back-propagated again)
+        a.dh, a.dc, a.dgate_planes, a.dgates = dh.data_ptr(), dc.data_ptr(), dgp.data_ptr(), dgates.data_ptr()
         if d_last is not None:
             d_last = _c(d_last)
             a.dh_last, a.dh_last_ld = d_last.data_ptr(), d_last.stride(0)
@@ -181,10 +182,10 @@ class Lstm32Fn(Function):
             if s > 0:        # dh_{s-1} += dgates_s W_hh (W_hh read MN-major)
                 ops.gemm3(dgp.view(D * 3, S, 4 * H), 0, whh_p.view(D * 3, 4 * H, H), 1, S, H, 4 * H, dh, batch=D,
                           c_batch=S * H, ldc=H, beta=True)
-        dgp_all = ops.split3(gates)                               # [3, T*S, D*4H]: gate gradients of every step
+        dgp_all = ops.split3(dgates)                              # [3, T*S, D*4H]: gate gradients of every step
         dwih = torch.empty((D * 4 * H, K), dtype=F32, device=dev)
         ops.gemm3(dgp_all, 1, xp, 1, D * 4 * H, K, T * S, dwih)
-        db = ops.colsum(gates)
+        db = ops.colsum(dgates)
         dwhh = torch.empty((D, 4 * H, H), dtype=F32, device=dev)
         for d in range(D):
             hp = ops.split3(hprev_t[d].view(T * S, H))

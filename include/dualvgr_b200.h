@@ -496,7 +496,7 @@ int dvgr_embed_bwd_f32(const long long* tokens, const void* words, const void* d
  * time t = T-1-s). nn.LSTM gate order (i|f|g|o blocks of H). Replaces the cuDNN cell of nn.LSTM for fp32 mode
  * (reference model/Preprocessing.py:97-101,202).
  *   gates        [T][S][ndir*4H] f32: x W_ih^T + b_ih + b_hh on entry; forward overwrites the step's rows with the ACTIVATED
- *                gates, backward overwrites them with the pre-activation gate gradients
+ *                gates, backward writes the pre-activation gate gradients to `dgates` (or over them when dgates is NULL)
  *   rec          [ndir][S][4H] f32: h_{prev} W_hh^T of this step (unused at s == 0)
  *   h            [ndir][S][H] f32 running state; h_planes [ndir][3][S][H] bf16 split of the new state (next step's operand)
  *   c_hist       [T+1][ndir][S][H] f32 by step (slot s in, slot s+1 out; slot 0 is never read)
@@ -527,6 +527,7 @@ typedef struct dvgr_lstm32_args {
   long long dh_last_ld;
   const float* dh_seq;
   long long dh_seq_ld;
+  float* dgates; /* backward: where the gate gradients go ([T][S][ndir*4H]); NULL = over the activated gates */
 } dvgr_lstm32_args;
 int dvgr_lstm32_cell_fwd(const dvgr_lstm32_args* args, void* stream);
 int dvgr_lstm32_cell_bwd(const dvgr_lstm32_args* args, void* stream);

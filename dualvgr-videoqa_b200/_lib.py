@@ -145,6 +145,7 @@ pair_loss_multi = _sig("dvgr_pair_loss_multi", [ctypes.POINTER(PairJob), c_int, 
 lib.dvgr_aux_loss_workspace.argtypes = [c_int, c_int, c_int]
 lib.dvgr_aux_loss_workspace.restype = c_ll
 aux_loss_unit = _sig("dvgr_aux_loss_unit", [P, P, P, P, c_float, c_float, c_int, c_int, c_int, P, P, P, P, P, P, P])
+aux_loss_unit_ex = _sig("dvgr_aux_loss_unit_ex", [P, P, P, P, c_float, c_float, c_int, c_int, c_int, P, P, P, P, P, P, c_int, P])
 prep_features = _sig("dvgr_prep_features", [P, P, c_ll, c_int, c_int, c_int, c_int, c_float, c_ull, c_uint, P])
 prep_features_ex = _sig("dvgr_prep_features_ex", [P, c_int, P, c_ll, c_int, c_int, c_int, c_int, c_float, c_ull, c_uint, P])
 cast_rows = _sig("dvgr_cast_rows", [P, c_ll, P, c_ll, c_int, c_int, c_int, c_int, P])
@@ -216,7 +217,7 @@ EXPORTED = [
     "dvgr_lstm_step_fwd", "dvgr_lstm_step_bwd", "dvgr_lstm_seq_fwd", "dvgr_lstm_seq_sync_words", "dvgr_lstm_seq_bwd", "dvgr_gat_attn_fwd", "dvgr_gat_attn_bwd", "dvgr_qattn_fwd",
     "dvgr_qattn_bwd", "dvgr_gate_fwd", "dvgr_gate_bwd", "dvgr_view_attn_fwd", "dvgr_view_attn_bwd_blocks",
     "dvgr_view_attn_bwd", "dvgr_mfb_fwd", "dvgr_mfb_bwd", "dvgr_readout_fwd", "dvgr_readout_bwd", "dvgr_bn_fwd",
-    "dvgr_bn_bwd", "dvgr_cross_entropy", "dvgr_pair_loss_workspace", "dvgr_pair_loss_multi", "dvgr_aux_loss_workspace", "dvgr_aux_loss_unit", "dvgr_prep_features", "dvgr_prep_features_ex", "dvgr_cast_rows", "dvgr_dropout",
+    "dvgr_bn_bwd", "dvgr_cross_entropy", "dvgr_pair_loss_workspace", "dvgr_pair_loss_multi", "dvgr_aux_loss_workspace", "dvgr_aux_loss_unit", "dvgr_aux_loss_unit_ex", "dvgr_prep_features", "dvgr_prep_features_ex", "dvgr_cast_rows", "dvgr_dropout",
     "dvgr_act_bwd", "dvgr_add", "dvgr_scatter", "dvgr_colsum_workspace", "dvgr_colsum", "dvgr_colsum_batched", "dvgr_colsum_grouped", "dvgr_sumsq_blocks", "dvgr_sumsq",
     "dvgr_adam_step", "dvgr_dropout_multi", "dvgr_gat_input_bwd", "dvgr_embed_fwd", "dvgr_embed_bwd",
     "dvgr_view_attn_fwd_multi", "dvgr_view_attn_bwd_multi", "dvgr_cast_rows_grouped", "dvgr_lstm_pack_bias",

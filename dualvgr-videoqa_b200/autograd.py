@@ -460,6 +460,8 @@ class AppearanceEncoderFn(Function):
         unmap = _lstm_unmap(H, 2, dg.device)
         t_ih, t_hh = grad_target(ctx.wih_params), grad_target(ctx.whh_params)
         if t_ih is not None:
+            # (measured, r2: dealing ONE tile per CTA so that the question encoder's backward chain interleaves on a higher-
+            #  priority stream moves that chain inside this launch but does not shorten the step: SM-time is conserved)
             ops.linear_wgrad(dg, xa, out=t_ih, row_map=unmap, atomic=True, dynamic=True, max_ctas=ops._cap())   # long launch next to the question encoder's backward
             dwih = None
         else:
@@ -925,7 +927,7 @@ class AuxLossFn(Function):
         of launching four [B,N,D] multiplications by a scalar that is 1."""
         ctx.unit_grad = bool(unit_grad)
         ca, cm, aq, mq = (_c(t.float()) for t in (ca, cm, aq, mq))
-        vals, (d_ca, d_cm, d_aq, d_mq) = ops.aux_loss_unit(ca, cm, aq, mq, coef_com, coef_dep)
+        vals, (d_ca, d_cm, d_aq, d_mq) = ops.aux_loss_unit(ca, cm, aq, mq, coef_com, coef_dep, precise=ACT[0] == F32)
         ctx.save_for_backward(d_ca, d_cm, d_aq, d_mq)
         ctx.mark_non_differentiable(vals)
         return vals.sum(), vals

@@ -280,6 +280,7 @@ struct AuxParams {
   float coef_com, coef_dep;
   int B, N, D, chunks;
   float* ws;             // [4][B][N][N] centred Grams, accumulated over the column chunks
+  int x3;                // Gram products on error-compensated 3 x TF32 (1) or plain TF32 (0)
 };
 
 __device__ __forceinline__ void load_centered_tile(const float* __restrict__ x, int N, int D, int c0, float* t) {
@@ -312,9 +313,16 @@ __global__ void __launch_bounds__(kLossThreads) aux_gram_kernel(const AuxParams 
     const float* ar = tile + (size_t)(mt * 16 + g) * kTS + t;
     const float* br = tile + (size_t)(nt * 8 + g) * kTS + t;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (p.x3) {
 #pragma unroll 4
-    for (int k0 = 0; k0 < kChunk; k0 += 8)
-      mma_tf32x3(acc, ar[k0], ar[8 * kTS + k0], ar[k0 + 4], ar[8 * kTS + k0 + 4], br[k0], br[k0 + 4]);
+      for (int k0 = 0; k0 < kChunk; k0 += 8)
+        mma_tf32x3(acc, ar[k0], ar[8 * kTS + k0], ar[k0 + 4], ar[8 * kTS + k0 + 4], br[k0], br[k0 + 4]);
+    } else {
+#pragma unroll 4
+      for (int k0 = 0; k0 < kChunk; k0 += 8)
+        mma_tf32(acc, to_tf32(ar[k0]), to_tf32(ar[8 * kTS + k0]), to_tf32(ar[k0 + 4]), to_tf32(ar[8 * kTS + k0 + 4]),
+                 to_tf32(br[k0]), to_tf32(br[k0 + 4]));
+    }
     const int row = mt * 16 + g, col = nt * 8 + 2 * t;
     if (row < N && col < N) atomicAdd(out + row * N + col, acc[0]);
     if (row < N && col + 1 < N) atomicAdd(out + row * N + col + 1, acc[1]);
@@ -519,6 +527,12 @@ extern "C" long long dvgr_aux_loss_workspace(int B, int N, int D) {
 extern "C" int dvgr_aux_loss_unit(const float* ca, const float* cm, const float* aq, const float* mq, float coef_com,
                                   float coef_dep, int B, int N, int D, float* d_ca, float* d_cm, float* d_aq, float* d_mq,
                                   float* loss_part, float* gram_ws, void* stream) {
+  return dvgr_aux_loss_unit_ex(ca, cm, aq, mq, coef_com, coef_dep, B, N, D, d_ca, d_cm, d_aq, d_mq, loss_part, gram_ws, 0, stream);
+}
+
+extern "C" int dvgr_aux_loss_unit_ex(const float* ca, const float* cm, const float* aq, const float* mq, float coef_com,
+                                     float coef_dep, int B, int N, int D, float* d_ca, float* d_cm, float* d_aq, float* d_mq,
+                                     float* loss_part, float* gram_ws, int precise, void* stream) {
   if (B <= 0) return 0;
   if (N < 1 || N > 64) return set_error("aux_loss: N=%d out of [1,64]", N);
   if (!ca || !cm || !aq || !mq || !loss_part || !gram_ws) return set_error("aux_loss: null buffer");
@@ -528,6 +542,7 @@ extern "C" int dvgr_aux_loss_unit(const float* ca, const float* cm, const float*
   p.dx[0] = d_ca; p.dx[1] = d_cm; p.dx[2] = d_aq; p.dx[3] = d_mq;
   p.loss_part = loss_part; p.coef_com = coef_com; p.coef_dep = coef_dep;
   p.B = B; p.N = N; p.D = D; p.chunks = (D + kChunk - 1) / kChunk; p.ws = gram_ws;
+  p.x3 = precise ? 1 : 0;
   const size_t smem1 = (size_t)round16(N) * kTS * sizeof(float);
   const size_t smem2 = (size_t)(7 * N * N + 6 * N) * sizeof(float);
   static size_t conf1 = 0, conf2 = 0;

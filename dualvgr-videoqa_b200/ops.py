@@ -213,8 +213,12 @@ def clear_deferred():
     _SMALL_QUEUE.clear()
 
 
-def flush_wgrads():
-    """Launches every queued weight gradient (one grouped GEMM per 32 problems) and bias gradient (one grouped column sum)."""
+def flush_wgrads(keep_alive=None):
+    """Launches every queued weight gradient (one grouped GEMM per 32 problems) and bias gradient (one grouped column sum).
+    keep_alive: a list that receives the queued operands — for a flush on a SIDE stream, whose kernels may still be reading
+    them when the caller's stream would otherwise free (and re-use) their memory."""
+    if keep_alive is not None:
+        keep_alive.extend([list(_SMALL_QUEUE), list(_COLSUM_QUEUE), list(_WGRAD_QUEUE)])
     if _SMALL_QUEUE:
         scatter(list(_SMALL_QUEUE), True)
         _SMALL_QUEUE.clear()
@@ -755,7 +759,7 @@ def pair_loss_multi(jobs, B, N, D, like):
     return colsum(part)
 
 
-def aux_loss_unit(ca, cm, aq, mq, coef_com, coef_dep, want_grad=True):
+def aux_loss_unit(ca, cm, aq, mq, coef_com, coef_dep, want_grad=True, precise=False):
     """The three auxiliary terms of one DualVGR unit (tensor-centric kernels). Inputs fp32 [B, N, D] contiguous.
     Returns (vals [3] f32 = coef-scaled (common, HSIC(aq, ca), HSIC(mq, cm)), (d_ca, d_cm, d_aq, d_mq) | None)."""
     B, N, D = ca.shape
@@ -764,9 +768,9 @@ def aux_loss_unit(ca, cm, aq, mq, coef_com, coef_dep, want_grad=True):
     grads = tuple(torch.empty_like(t) for t in (ca, cm, aq, mq)) if want_grad else (None,) * 4
     part = _empty((B, 3), F32, ca)
     ws = _empty((int(_lib.lib.dvgr_aux_loss_workspace(B, N, D)),), F32, ca)
-    _lib.check(_lib.aux_loss_unit(_ptr(ca), _ptr(cm), _ptr(aq), _ptr(mq), float(coef_com), float(coef_dep), B, N, D,
-                                  _ptr(grads[0]), _ptr(grads[1]), _ptr(grads[2]), _ptr(grads[3]), _ptr(part), _ptr(ws),
-                                  _stream()), "dvgr_aux_loss_unit")
+    _lib.check(_lib.aux_loss_unit_ex(_ptr(ca), _ptr(cm), _ptr(aq), _ptr(mq), float(coef_com), float(coef_dep), B, N, D,
+                                     _ptr(grads[0]), _ptr(grads[1]), _ptr(grads[2]), _ptr(grads[3]), _ptr(part), _ptr(ws),
+                                     1 if precise else 0, _stream()), "dvgr_aux_loss_unit_ex")
     return colsum(part), (grads if want_grad else None)
 
 

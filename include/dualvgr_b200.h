@@ -341,6 +341,10 @@ long long dvgr_aux_loss_workspace(int B, int N, int D);
 int dvgr_aux_loss_unit(const float* ca, const float* cm, const float* aq, const float* mq, float coef_com, float coef_dep,
                        int B, int N, int D, float* d_ca, float* d_cm, float* d_aq, float* d_mq, float* loss_part,
                        float* gram_ws, void* stream);
+/* precise != 0: the Gram products run on error-compensated 3 x TF32 (fp32-grade; fp32 mode) instead of plain TF32. */
+int dvgr_aux_loss_unit_ex(const float* ca, const float* cm, const float* aq, const float* mq, float coef_com, float coef_dep,
+                       int B, int N, int D, float* d_ca, float* d_cm, float* d_aq, float* d_mq, float* loss_part,
+                       float* gram_ws, int precise, void* stream);
 
 /* Streaming helpers.
  * dvgr_prep_features: model/Preprocessing.py:220-223 — tanh(dropout(x)), fp32 -> bf16, [S][T][C] -> [T][S][C] in one pass.

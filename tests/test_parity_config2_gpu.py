@@ -120,7 +120,7 @@ def test_benchmark_config_engine_path_against_fp64_oracle():
     assert bool((got_arg[confident] == ref_logits.argmax(1)[confident]).all())
     assert agree >= int(0.97 * B)
     assert err_ce < TOL, worst_ce
-    assert err_full < max(TOL, 4 * floor_full), (err_full, floor_full, worst_full)
+    assert err_full < max(TOL, floor_full), (err_full, floor_full, worst_full)      # no further from fp64 than the oracle in fp32
     assert abs(tot - ref_losses[0]) < max(TOL * abs(ref_losses[0]), 4 * abs(f32_losses[0] - ref_losses[0]))
     assert abs(com - ref_losses[2]) < max(0.05 * abs(ref_losses[2]), 4 * abs(f32_losses[2] - ref_losses[2]))
     assert abs(dep - ref_losses[3]) < max(0.05 * abs(ref_losses[3]), 4 * abs(f32_losses[3] - ref_losses[3]))

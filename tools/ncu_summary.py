@@ -25,6 +25,7 @@ def find(*subs):
 
 C = dict(
     t=find("gpu__time_duration.sum"), rd=find("dram__bytes_read.sum"), wr=find("dram__bytes_write.sum"),
+    rate=find("dram__bytes.sum.per_second"),
     dram=find("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
     tensor=find("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active") or find("sm__inst_executed_pipe_tensor"),
     smthr=find("sm__throughput.avg.pct_of_peak_sustained_elapsed"),
@@ -40,7 +41,8 @@ def val(r, k, scale_unit=False):
     if scale_unit:
         u = units[i]
         v *= {"ns": 1e-3, "nsecond": 1e-3, "us": 1.0, "usecond": 1.0, "ms": 1e3, "msecond": 1e3, "s": 1e6, "second": 1e6,
-              "byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1.0)
+              "byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte/s": 1.0, "Kbyte/s": 1e3, "Mbyte/s": 1e6,
+              "Gbyte/s": 1e9, "Tbyte/s": 1e12}.get(u, 1.0)
     return v
 
 
@@ -53,8 +55,11 @@ for r in rows[first:]:
     a = agg.setdefault(name, dict(n=0, t=0.0, rd=0.0, wr=0.0, dram=[], tensor=[], smthr=[], occ=[], regs=None, smem=None, grid=None))
     a["n"] += 1
     a["t"] += val(r, "t", True) or 0.0
-    a["rd"] += val(r, "rd", True) or 0.0
-    a["wr"] += val(r, "wr", True) or 0.0
+    if C["rd"] is not None:
+        a["rd"] += val(r, "rd", True) or 0.0
+        a["wr"] += val(r, "wr", True) or 0.0
+    elif C["rate"] is not None:          # sections without the byte counters: bytes = DRAM rate x duration
+        a["rd"] += (val(r, "rate", True) or 0.0) * (val(r, "t", True) or 0.0) * 1e-6
     for k in ("dram", "tensor", "smthr", "occ"):
         v = val(r, k)
         if v is not None:

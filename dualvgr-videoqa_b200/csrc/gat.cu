@@ -38,6 +38,11 @@ struct GatGraph {
   float* dgate;               // bwd: [B, N] this graph's contribution to the gate gradient
   float* davec;               // bwd: [B][heads][2*Dh + 1] per-video partial sums (reduced by dvgr_colsum)
   unsigned int drop_stream;   // dropout stream id of this graph (attention: +0, output: +1)
+  // head-split launches (one virtual single-head graph per head, see launch_head_split): position of this slice in the real
+  // graph, so that the dropout masks and the per-video partials land where the whole-graph kernel puts them
+  int mask_k0, mask_pair0;    // first head / first column pair of this slice
+  long long ld_davec;         // elements per video in davec (0: heads * (2*Dh + 1))
+  int atomic_dgate;           // accumulate the gate gradient with atomics (the heads of a graph add into one buffer)
 };
 
 struct GatParams {
@@ -49,6 +54,7 @@ struct GatParams {
   float p_att, p_out;         // dropout probabilities (0 in eval)
   unsigned long long seed;
   const unsigned long long* seed_off;
+  int mask_heads, mask_D;     // head count / width of the REAL graph in the dropout-mask indices (0: heads / D)
 };
 
 struct GatSmem {
@@ -172,11 +178,13 @@ __device__ __forceinline__ void gat_softmax_row(const GatParams& p, const GatSme
 //   attention mask (b, k, i, j)  : murmur-hashed element index ((b*K + k)*N + i)*N + j   (rng.cuh: dropout_scale1_hash)
 //   output mask    (b, i, c)     : murmur-hashed column-PAIR index (b*N + i)*(D/2) + c/2, 16 bits per element
 //                                  (rng.cuh: dropout_scale2_hash) — a thread of the tensor-core kernels owns column pairs
-__device__ __forceinline__ float att_keep(const GatParams& p, const DropoutCfg& cfg, int b, int k, int i, int j) {
-  return dropout_scale1_hash(cfg, (((unsigned long long)b * p.heads + k) * p.N + i) * p.N + j);
+__device__ __forceinline__ float att_keep(const GatParams& p, const GatGraph& gr, const DropoutCfg& cfg, int b, int k, int i, int j) {
+  const int heads = p.mask_heads > 0 ? p.mask_heads : p.heads;
+  return dropout_scale1_hash(cfg, (((unsigned long long)b * heads + gr.mask_k0 + k) * p.N + i) * p.N + j);
 }
-__device__ __forceinline__ float2 out_keep2(const GatParams& p, const DropoutCfg& cfg, int b, int i, int pair) {
-  return dropout_scale2_hash(cfg, ((unsigned long long)b * p.N + i) * (p.D >> 1) + pair);
+__device__ __forceinline__ float2 out_keep2(const GatParams& p, const GatGraph& gr, const DropoutCfg& cfg, int b, int i, int pair) {
+  const int D = p.mask_D > 0 ? p.mask_D : p.D;
+  return dropout_scale2_hash(cfg, ((unsigned long long)b * p.N + i) * (D >> 1) + gr.mask_pair0 + pair);
 }
 
 // ------------------------------------------------------------------------------------------------------ forward
@@ -196,7 +204,7 @@ __global__ void __launch_bounds__(kGatThreads) gat_attn_fwd_kernel(const GatPara
     __syncwarp();
     float* Prow = sm.P + ((size_t)k * N + i) * NP;
     for (int j = lane; j < N; j += 32)
-      Prow[j] = Prow[j] * sm.gate[j] * att_keep(p, datt, b, k, i, j);   // gate multiplies the values: fold it into P
+      Prow[j] = Prow[j] * sm.gate[j] * att_keep(p, gr, datt, b, k, i, j);   // gate multiplies the values: fold it into P
   }
   __syncthreads();
 
@@ -231,7 +239,7 @@ __global__ void __launch_bounds__(kGatThreads) gat_attn_fwd_kernel(const GatPara
         if (i < N) {
           float o0 = eluf_(acc[r][0]), o1 = eluf_(acc[r][1]);
           if (p.p_out > 0.f) {
-            const float2 keep = out_keep2(p, dout, b, i, pair);
+            const float2 keep = out_keep2(p, gr, dout, b, i, pair);
             o0 *= keep.x;
             o1 *= keep.y;
           }
@@ -508,7 +516,7 @@ __global__ void __launch_bounds__(kGatThreads) gat_attn_bwd_kernel(const GatPara
       for (int r = 0; r < 4; ++r) {
         const int i = rq * 4 + r;
         if (i >= N) break;
-        const float2 keep = out_keep2(p, dout, b, i, pair);
+        const float2 keep = out_keep2(p, gr, dout, b, i, pair);
         float2 h = ld2(hp + (long long)i * p.ld_out + c);
         float2 d = ld2(dop + (long long)i * p.ld_out + c);
         if (gr.dout_f32 != nullptr) {
@@ -553,7 +561,7 @@ __global__ void __launch_bounds__(kGatThreads) gat_attn_bwd_kernel(const GatPara
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
       const int j = lane + 32 * q;
-      if (j < N) dP[((size_t)k * N + i) * NP + j] = mine[q] * sm.gate[j] * att_keep(p, datt, b, k, i, j);
+      if (j < N) dP[((size_t)k * N + i) * NP + j] = mine[q] * sm.gate[j] * att_keep(p, gr, datt, b, k, i, j);
     }
   }
   __syncthreads();
@@ -596,13 +604,13 @@ __global__ void __launch_bounds__(kGatThreads) gat_attn_bwd_kernel(const GatPara
   // du is consumed: reuse its buffer for the TRANSPOSED P~[k][j][i] = P_ij * mask_ij (ungated), zero padded along i
   for (int e = tid; e < K * N * NP; e += blockDim.x) {
     const int k = e / (N * NP), r = e - k * N * NP, j = r / NP, i = r - j * NP;
-    dP[e] = (i < N) ? sm.P[((size_t)k * N + i) * NP + j] * att_keep(p, datt, b, k, i, j) : 0.f;
+    dP[e] = (i < N) ? sm.P[((size_t)k * N + i) * NP + j] * att_keep(p, gr, datt, b, k, i, j) : 0.f;
   }
   __syncthreads();
 
   // 4. dV_j[c] = sum_i P~_ij dz_i[c] ; dWh_j = g_j dV_j + ds_j a1 + dt_j a2 ; dgate_j ; da1, da2   (8 j x 2 columns / pass)
   act_t* dwhp = gr.dwh + (long long)b * N * p.ld_wh;
-  float* dav = gr.davec + ((long long)b * K) * (2 * Dh + 1);
+  float* dav = gr.davec + (long long)b * (gr.ld_davec > 0 ? gr.ld_davec : (long long)K * (2 * Dh + 1));
   for (int pair0 = 0; pair0 < D / 2; pair0 += blockDim.x) {
     const int pair = pair0 + tid;
     const bool active = pair < D / 2;
@@ -657,7 +665,10 @@ __global__ void __launch_bounds__(kGatThreads) gat_attn_bwd_kernel(const GatPara
     }
   }
   __syncthreads();
-  for (int i = tid; i < N; i += blockDim.x) gr.dgate[(long long)b * N + i] = dg[i];
+  for (int i = tid; i < N; i += blockDim.x) {
+    if (gr.atomic_dgate) atomicAdd(gr.dgate + (long long)b * N + i, dg[i]);
+    else gr.dgate[(long long)b * N + i] = dg[i];
+  }
   if (tid < K) dav[tid * (2 * Dh + 1) + 2 * Dh] = dc_s[tid];
 }
 
@@ -1111,6 +1122,49 @@ static int fill_gat(GatParams& p, const dvgr_gat_args* a, bool bwd) {
   return 0;
 }
 
+// Whole-graph tiles too large for shared memory (fp32 activations: N > 28 at D = 768): run every head of a graph as its own
+// single-head "virtual graph" of width Dh (the heads only share the gate gradient, accumulated with atomics). One launch per
+// real graph, grid (B, heads). Not available when the fp32 side outputs / gradients are requested (bf16 build only).
+static int launch_head_split(const GatParams& p, int n_graphs, bool bwd, cudaStream_t st) {
+  const int K = p.heads, Dh = p.D / K;
+  const size_t smem = gat_smem_common(p.N, Dh, 1) + (bwd ? gat_smem_bwd_extra(p.N, Dh, 1) : 0);
+  if (smem > 227 * 1024) return set_error("gat %s: %zu bytes of shared memory needed even per head", bwd ? "bwd" : "fwd", smem);
+  auto kern = bwd ? gat_attn_bwd_kernel : gat_attn_fwd_kernel;
+  if (smem > 48 * 1024) {      // (the limit itself: never lowers what a whole-graph launch of the same kernel configured)
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, kern);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - (int)fa.sharedSizeBytes);
+    if (e != cudaSuccess) return set_error("gat (head split): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  }
+  for (int g = 0; g < n_graphs; ++g) {
+    const GatGraph& src = p.g[g];
+    if (src.out_f32 != nullptr || src.dout_f32 != nullptr) return set_error("gat: head-split launch does not take fp32 side buffers");
+    GatParams q = p;
+    q.heads = 1; q.D = Dh; q.mask_heads = K; q.mask_D = p.D;
+    for (int k = 0; k < K; ++k) {
+      GatGraph& d = q.g[k];
+      d = src;
+      d.wh = src.wh + k * Dh;
+      d.out = src.out + k * Dh;
+      d.avec = src.avec + k * (2 * Dh + 1);
+      d.mask_k0 = k; d.mask_pair0 = k * (Dh / 2);
+      if (bwd) {
+        d.dout = src.dout + k * Dh;
+        d.dwh = src.dwh + k * Dh;
+        d.davec = src.davec + k * (2 * Dh + 1);
+        d.ld_davec = (long long)K * (2 * Dh + 1);
+        d.atomic_dgate = 1;
+      }
+    }
+    if (bwd && cudaMemsetAsync(src.dgate, 0, sizeof(float) * (size_t)p.B * p.N, st) != cudaSuccess)
+      return set_error("gat bwd (head split): cudaMemsetAsync failed");
+    kern<<<dim3(p.B, K), kGatThreads, smem, st>>>(q);
+    DVGR_CHECK_LAUNCH(bwd ? "gat_attn_bwd (head split)" : "gat_attn_fwd (head split)");
+  }
+  return 0;
+}
+
 #ifndef DVGR_F32
 static int gat_fast_knob() {      // read per call (tests flip it to compare the two paths): bit 0 forward, bit 1 backward
   const char* e = getenv("DVGR_GAT_FAST");
@@ -1147,6 +1201,7 @@ extern "C" int DVGR_FN(dvgr_gat_attn_fwd)(const dvgr_gat_args* a, void* stream) 
   }
 #endif
   const size_t smem = gat_smem_common(p.N, p.D, p.heads);
+  if (smem > 227 * 1024 && p.heads > 1) return launch_head_split(p, a->n_graphs, false, reinterpret_cast<cudaStream_t>(stream));
   if (smem > 227 * 1024) return set_error("gat fwd: %zu bytes of shared memory needed", smem);
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
@@ -1192,6 +1247,7 @@ extern "C" int DVGR_FN(dvgr_gat_attn_bwd)(const dvgr_gat_args* a, void* stream) 
   }
 #endif
   const size_t smem = gat_smem_common(p.N, p.D, p.heads) + gat_smem_bwd_extra(p.N, p.D, p.heads);
+  if (smem > 227 * 1024 && p.heads > 1) return launch_head_split(p, a->n_graphs, true, reinterpret_cast<cudaStream_t>(stream));
   if (smem > 227 * 1024) return set_error("gat bwd: %zu bytes of shared memory needed", smem);
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {

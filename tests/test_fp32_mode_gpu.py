@@ -175,7 +175,7 @@ def test_fp32_mode_against_reference_golden(golden, fp32_mode, name):
     assert err_f < max(TOL32, 4 * floor32, 1e-3), (err_f, floor32)
 
 
-@pytest.mark.parametrize("cfg", [(6, 20, 8, 32, 60, 3), (24, 8, 8, 32, 60, 2), (8, 16, 8, 4002, 60, 1)])
+@pytest.mark.parametrize("cfg", [(6, 20, 8, 32, 60, 3), (24, 8, 8, 32, 60, 2), (8, 16, 8, 4002, 60, 1), (4, 64, 8, 50, 60, 1)])
 def test_fp32_mode_full_gradient_tensors_against_oracle(fp32_mode, cfg):
     """Every parameter's full CE-gradient tensor against the oracle's float64 autograd: global relative L2 < 1e-4."""
     B, N, L, A, V, U = cfg
@@ -237,3 +237,43 @@ def test_fp32_mode_engine_step_matches_torch_adam(fp32_mode):
     print(f"fp32 engine step: loss {float(total):.6f} vs {float(loss):.6f}; update rel-L2 {(num / den) ** 0.5:.2e}")
     assert (num / den) ** 0.5 < 2e-2        # Adam's first step is sign(g) * lr: only sign flips of ~zero gradients differ
     eng.close()
+
+
+def test_fp32_gat_head_split_matches_whole_graph_launch(ops):
+    """fp32 graph attention at a node count whose whole-graph tiles do not fit shared memory (N = 40: head-split launches, one
+    virtual single-head graph per head) against the float64 formula: forward and every gradient at 1e-5; with dropout ON the
+    keep rate of the output mask must be 1 - p for both launch shapes (the slices index the real graph's mask streams)."""
+    import dualvgr_videoqa_b200.autograd as ag
+    B, D, heads = 3, 768, 4
+    Dh = D // heads
+    for N, p_drop in ((40, 0.0), (40, 0.15), (20, 0.15)):
+        g = torch.Generator().manual_seed(N)
+        wh = torch.randn((B * N, D), generator=g).cuda()
+        gate = torch.rand((B, N), generator=g).cuda()
+        avec = (torch.randn((heads, 2 * Dh + 1), generator=g) * 0.1).cuda()
+        adj = torch.full((N, N), 1.0 / N).cuda()
+        dout = torch.randn((B * N, D), generator=g).cuda()
+        outs, _ = ops.gat_attn_fwd([wh], [gate], [avec], adj, B, N, heads=heads, p_att=p_drop, p_out=p_drop, seed=77, streams=[5])
+        out = outs[0]
+        dwhs, dgates, davecs = ops.gat_attn_bwd([wh], [gate], [avec], [out], [dout], adj, B, N, heads=heads, p_att=p_drop,
+                                                p_out=p_drop, seed=77, streams=[5])
+        if p_drop == 0.0:
+            whd = wh.double().cpu().view(B, N, heads, Dh).requires_grad_(True)
+            gd, ad = gate.double().cpu().requires_grad_(True), avec.double().cpu().requires_grad_(True)
+            s = (whd * ad[:, :Dh]).sum(-1)                      # [B, N, heads]
+            t = (whd * ad[:, Dh:2 * Dh]).sum(-1)
+            e = torch.nn.functional.leaky_relu(s[:, :, None, :] + t[:, None, :, :] + ad[:, 2 * Dh], 0.01)   # [B, i, j, heads]
+            P = torch.softmax(e, dim=2)
+            agg = torch.einsum("bijk,bjkc->bikc", P, whd * gd[:, :, None, None])
+            ref = torch.nn.functional.elu(agg).reshape(B * N, D)
+            assert rel(out, ref) < 1e-5, rel(out, ref)
+            ref.backward(dout.double().cpu())
+            assert rel(dwhs[0], whd.grad.reshape(B * N, D)) < 1e-5
+            assert rel(dgates[0], gd.grad) < 1e-5
+            assert rel(davecs[0], ad.grad) < 1e-5
+        else:
+            kept = float((out != 0).float().mean())
+            assert abs(kept - (1 - p_drop)) < 0.02, kept
+            if N == 40:
+                first20 = out.view(B, N, heads, Dh)[0, :, :, :]
+                assert bool(torch.isfinite(out).all()) and float(first20.abs().sum()) > 0

@@ -54,6 +54,7 @@ PROFILE = {}
 # two-kernel path (A/B measurements). SYNC_WORDS collects the kernels' sync buffers (last word = sticky timeout flag) of the
 # most recent forward passes so that tests / bench can assert the dependency protocol never timed out.
 LSTM_SEQ = [os.environ.get("DVGR_LSTM_SEQ", "1") != "0"]
+WHH_TRANSPOSED = [os.environ.get("DVGR_WHH_T", "1") != "0"]
 
 
 class _SyncLog(collections.deque):
@@ -462,7 +463,7 @@ class AppearanceEncoderFn(Function):
         if t_ih is not None:
             # (measured, r2: dealing ONE tile per CTA so that the question encoder's backward chain interleaves on a higher-
             #  priority stream moves that chain inside this launch but does not shorten the step: SM-time is conserved)
-            ops.linear_wgrad(dg, xa, out=t_ih, row_map=unmap, atomic=True, dynamic=True, max_ctas=ops._cap())   # long launch next to the question encoder's backward
+            ops.linear_wgrad(dg, xa, out=t_ih, row_map=unmap, atomic=True, dynamic=True, max_ctas=ops._cap(1))   # long launch next to the question encoder's backward
             dwih = None
         else:
             dwih = ops.linear_wgrad(dg, xa, row_map=unmap, bn=256)  # [8H, Dv] fp32 in nn.LSTM row order
@@ -473,10 +474,24 @@ class AppearanceEncoderFn(Function):
         wbn, wks = ops.wgrad_split(4 * H, H, (T - 1) * kin * 64, batch=2) if t_hh is not None else (0, 0)
         # (the step-0 term is skipped: h_0 = 0, and its slot is not even initialised in the whole-sequence layout)
         s0 = 1 if LSTM_SEQ[0] else 0
-        ops.gemm(gates, 1, h_hist, 1, 4 * H, H, (T - s0) * kin * 64, dwhh, ldc=H, batch=2, c_batch=4 * H * H,
-                 row_map=_lstm_unmap(H, 1, dg.device), a_c0=[0, 4 * H], a_c2=[s0, T - 1 - s0], a_c2_step=[1, -1],
-                 b_c2=[s0, s0], b_c2_step=[1, 1], b_c3=[0, 1], k_inner=kin, beta=2 if t_hh is not None else 0,
-                 bn=wbn, ksplit=wks, dynamic=True, max_ctas=ops._cap())
+        if WHH_TRANSPOSED[0]:
+            # computed TRANSPOSED, dW_hh^T [H, 4H] = h^T dgates: the 4H side becomes the 256-wide tile dimension (36 tiles of
+            # 128 x 256 instead of 72 of 128 x 128 — the narrow tiles are bound by the operand traffic from L2, not by the
+            # tensor pipe), then one small permuted add un-interleaves the gates into nn.LSTM row order
+            dwt = torch.zeros((2, H, 4 * H), dtype=F32, device=dg.device)
+            ops.gemm(h_hist, 1, gates, 1, H, 4 * H, (T - s0) * kin * 64, dwt, ldc=4 * H, batch=2, c_batch=4 * H * H,
+                     a_c2=[s0, s0], a_c2_step=[1, 1], a_c3=[0, 1], b_c0=[0, 4 * H], b_c2=[s0, T - 1 - s0], b_c2_step=[1, -1],
+                     k_inner=kin, beta=2, bn=256, ksplit=4, dynamic=True, max_ctas=ops._cap(1))
+            nat = dwt.view(2, H, H, 4).permute(0, 3, 2, 1).reshape(2, 4 * H, H)       # [d][k][4j+g] -> [d][g*H+j][k]
+            if t_hh is not None:
+                dwhh.add_(nat)
+            else:
+                dwhh = nat
+        else:
+            ops.gemm(gates, 1, h_hist, 1, 4 * H, H, (T - s0) * kin * 64, dwhh, ldc=H, batch=2, c_batch=4 * H * H,
+                     row_map=_lstm_unmap(H, 1, dg.device), a_c0=[0, 4 * H], a_c2=[s0, T - 1 - s0], a_c2_step=[1, -1],
+                     b_c2=[s0, s0], b_c2_step=[1, 1], b_c3=[0, 1], k_inner=kin, beta=2 if t_hh is not None else 0,
+                     bn=wbn, ksplit=wks, dynamic=True, max_ctas=ops._cap(1))
         g_ih = (None, None) if dwih is None else (dwih[:4 * H], dwih[4 * H:])
         g_hh = (None, None) if t_hh is not None else (dwhh[0], dwhh[1])
         # b_ih, b_hh, b_ih_reverse, b_hh_reverse: both biases of a direction get the same gradient

@@ -47,6 +47,9 @@ class _EarlyBucketHook:
         self.pending -= 1
         if self.pending == 0 and not self.engine.skip_allreduce:
             e = self.engine
+            ev = fs.LAST_QUERY_CHAIN_BWD[0]
+            if ev is not None:       # the question side of the unit stack ran its backward on the question stream
+                torch.cuda.current_stream().wait_event(ev)
             ops.flush_wgrads()       # the queued (deferred) weight gradients of the early bucket must land before it is reduced
             self.side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self.side):
@@ -123,7 +126,7 @@ class TrainEngine:
         ag.set_rank_seed(self.rank)
         ag.DIRECT_GRAD[0] = True      # weight-gradient GEMMs accumulate straight into the flat gradient buffer
         # SMs the appearance encoder's persistent backward launches leave to the streams running next to them (ops.RESERVE_SMS)
-        ops.RESERVE_SMS[0] = int(os.environ.get("DVGR_RESERVE_SMS", "0"))     # (measured: reserving SMs does not pay, r2)
+        ops.RESERVE_SMS[0] = int(os.environ.get("DVGR_RESERVE_SMS", "32"))     # (measured: reserving SMs does not pay, r2)
         _LIVE_ENGINES.add(self)
         overlap_ok = os.environ.get("DVGR_ALLREDUCE_OVERLAP", "1") != "0"        # A/B knob: 0 = one all-reduce after backward
         self._overlap = _EarlyBucketHook(self) if (self.world > 1 and overlap_ok and 0 < self.late_numel < total) else None

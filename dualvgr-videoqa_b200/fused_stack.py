@@ -64,6 +64,7 @@ def _stack2(a, b, M, D):
 
 
 _SIDE = {}
+LAST_QUERY_CHAIN_BWD = [None]      # CUDA event recorded at the end of the most recent QueryChainFn.backward
 
 
 def side_stream(device, key="aux"):
@@ -73,7 +74,9 @@ def side_stream(device, key="aux"):
     if k not in _SIDE:
         # the auxiliary losses are filler work (low priority: their CTAs only take SMs the critical path leaves idle); the
         # question encoder is on the critical path of the forward pass (high priority, like the engine's main stream)
-        _SIDE[k] = torch.cuda.Stream(device=device, priority=0 if key == "aux" else -1)
+        # question stream: one level ABOVE the engine's main stream (-1) — when the question encoder's 48 CTAs retire, the
+        # query chain behind it must get those SMs before the appearance encoder's still-pending CTAs do
+        _SIDE[k] = torch.cuda.Stream(device=device, priority=0 if key == "aux" else -2)
     return _SIDE[k]
 
 
@@ -142,10 +145,6 @@ def _pack_small(PL, heads, D, Dh, dev):
         "gat_b": torch.empty((U, G, D), dtype=F32, device=dev),
         "v_b": torch.empty((U, 2, D), dtype=F32, device=dev),
         "v_w2": torch.empty((U, 2, D), dtype=F32, device=dev),
-        "q_b": torch.empty((U, 2 * D), dtype=F32, device=dev),
-        "fe_b": torch.empty((U, D), dtype=F32, device=dev),
-        "fc_w": torch.empty((U, D), dtype=F32, device=dev),
-        "fc_b": torch.empty((U, 8), dtype=F32, device=dev),
     }
     segs = []
     for i, p in enumerate(PL):
@@ -157,11 +156,6 @@ def _pack_small(PL, heads, D, Dh, dev):
         for s in range(2):
             segs.append((pk["v_b"][i, s], p.v_b[s].detach()))
             segs.append((pk["v_w2"][i, s], p.v_w2[s].detach().reshape(-1)))
-        segs.append((pk["q_b"][i, :D], p.qa_b.detach()))
-        segs.append((pk["q_b"][i, D:], p.qm_b.detach()))
-        segs.append((pk["fe_b"][i], p.fe_b.detach()))
-        segs.append((pk["fc_w"][i], p.fc_w.detach().reshape(-1)))
-        segs.append((pk["fc_b"][i, :1], p.fc_b.detach().reshape(-1)))
     ops.scatter(segs, False)
     return pk
 
@@ -175,22 +169,23 @@ class UnitStackFn(Function):
     (coef_common, coef_dependence, parts [U, B, 3] f32): with aux the three auxiliary-loss terms of every layer
     (train.py:148-154) and their gradients are computed inside this Function on a side stream (values land in `parts`, the
     gradients are applied in backward with coefficient exactly 1 — the engine's contract, see engine.TrainEngine.loss).
-    Inputs: app, mot [B,N,D] bf16; dq [B*L, D] bf16 (row stride free); words [B,L,Wp] bf16; qlen [B] int32; adj [N,N] f32;
-    then N_LAYER_PARAMS tensors per layer (unit_layer_params).
+    Inputs: app, mot [B,N,D] bf16; query [U, B, 2D] bf16 (QueryChainFn: the cycle queries of every layer, appearance |
+    motion); adj [N,N] f32; then N_LAYER_PARAMS tensors per layer (unit_layer_params; the first 8 of a layer belong to
+    QueryChainFn and are not touched here).
     Returns (app_out, mot_out [B,N,D] bf16, aq_embed, mq_embed [B,N,D] bf16, then per layer the dense fp32 outputs of
     acGCN, appearance_GCN, mcGCN, motion_GCN [B,N,D])."""
 
     @staticmethod
-    def forward(ctx, cfg, app, mot, dq, words, qlen, adj, *params):
-        U, heads, pdrop, W, aux, want_f32 = cfg
+    def forward(ctx, cfg, app, mot, query_all, adj, *params):
+        U, heads, pdrop, W, aux, want_f32 = cfg[:6]
+        ctx.chain = cfg[6] if len(cfg) > 6 else None        # QueryChainFn's state: its backward is driven from ours (below)
         B, N, D = app.shape
-        M, Dh, Wp = B * N, D // heads, words.shape[-1]
-        L = words.shape[1]
+        M, Dh = B * N, D // heads
         dev = app.device
+        query_all = ag._c(query_all)
         PL = [_LP(params[i * N_LAYER_PARAMS:(i + 1) * N_LAYER_PARAMS], heads) for i in range(U)]
         pk = _pack_small(PL, heads, D, Dh, dev)
         X = _stack2(app, mot, M, D)
-        words = ag._c(words)
         seed, sid0 = ag._site(3 * G * U)
         want_f32 = bool(want_f32) or aux is not None      # (grad mode is always off inside Function.forward: the caller decides)
         keep, f32_all, embed = [], [], None
@@ -198,12 +193,8 @@ class UnitStackFn(Function):
         events, aux_jobs = [None] * U, []
         for i, p in enumerate(PL):
             sid = sid0 + 3 * G * i
-            # ---- Query Punishment Module: word attention -> cycle query -> per-clip gates of both streams
-            we = ag.bf16_rows([p.fe_w])
-            y = ops.linear_fwd(dq, we, bias=pk["fe_b"][i])
-            qc, alpha, nrm, prob, ssum = ops.qattn_fwd(y.view(B, L, D), pk["fc_w"][i], pk["fc_b"][i], qlen, words, W, Wp)
-            wq = ag.bf16_rows([p.qa_w, p.qm_w], out_cols=Wp, tag="cat")
-            query = ops.linear_fwd(qc, wq, bias=pk["q_b"][i])
+            # ---- Query Punishment Module: per-clip gates of both streams from this layer's cycle queries (QueryChainFn)
+            query = query_all[i]
             ga, gm = ops.gate_fwd(X[0].view(B, N, D), X[1].view(B, N, D), query)
             # ---- multi-view GAT: every graph projects its own dropped copy of its stream; ONE batched GEMM, ONE attention launch
             if pdrop > 0:
@@ -237,9 +228,8 @@ class UnitStackFn(Function):
                      c_batch=2 * M * D, bias_batch=D, a_c2=[0, 1], b_c2=[0, 1])
             Xn, embed, beta = ops.view_attn_fwd_multi(hidden.view(2, 2, M, D), z.view(2, 2, M, D), X, pk["v_w2"][i],
                                                       want_embed=(i == U - 1))
-            keep.append(dict(y=y, qc=qc, alpha=alpha, nrm=nrm, prob=prob, ssum=ssum, query=query, ga=ga, gm=gm,
-                             xt=xt if pdrop > 0 else None, wh=wh, z=z, hidden=hidden, beta=beta, X=X, we=we, wq=wq, wb=wb,
-                             w1=w1, aux_grads=aux_grads))
+            keep.append(dict(query=query, ga=ga, gm=gm, xt=xt if pdrop > 0 else None, wh=wh, z=z, hidden=hidden, beta=beta, X=X,
+                             wb=wb, w1=w1, aux_grads=aux_grads))
             X = Xn
         if aux_jobs:
             # auxiliary losses of every layer (values + all four gradients each) on the low-priority side stream, forked HERE:
@@ -261,9 +251,9 @@ class UnitStackFn(Function):
         # block freed here could be handed to the next allocation while the (low-priority) side stream still reads it
         ctx.aux_jobs = aux_jobs
         ctx.keep, ctx.pk, ctx.events = keep, pk, events
-        ctx.cfg = (U, heads, pdrop, W, B, N, D, L, Wp, seed, sid0)
+        ctx.cfg = (U, heads, pdrop, W, B, N, D, seed, sid0)
         ctx.PL, ctx.params = PL, params
-        ctx.save_for_backward(dq, words, qlen, adj)
+        ctx.save_for_backward(adj, query_all)
         if embed is None:
             embed = torch.zeros((2, M, D), dtype=BF16, device=dev)
         outs = (X[0].view(B, N, D), X[1].view(B, N, D), embed[0].view(B, N, D), embed[1].view(B, N, D)) + tuple(f32_all)
@@ -271,10 +261,13 @@ class UnitStackFn(Function):
 
     @staticmethod
     def backward(ctx, dapp, dmot, dea, dem, *d32_all):
-        U, heads, pdrop, W, B, N, D, L, Wp, seed, sid0 = ctx.cfg
-        dq, words, qlen, adj = ctx.saved_tensors
+        U, heads, pdrop, W, B, N, D, seed, sid0 = ctx.cfg
+        adj, query_all = ctx.saved_tensors
         M, Dh = B * N, D // heads
-        dev = dq.device
+        dev = adj.device
+        dquery_all = torch.empty_like(query_all)
+        chain = ctx.chain
+        chain_acc = dict(sink=_GradSink(), d_dq=None, dwords=None) if chain is not None else None
         pk, PL = ctx.pk, ctx.PL
         sink = _GradSink()
         cur = torch.cuda.current_stream()
@@ -292,7 +285,6 @@ class UnitStackFn(Function):
         if dX is None:
             dX = torch.zeros((2, M, D), dtype=BF16, device=dev)
         dembed = pair(dea, dem)
-        d_dq = dwords = None
         for i in reversed(range(U)):
             k, p = ctx.keep[i], PL[i]
             sid = sid0 + 3 * G * i
@@ -336,24 +328,115 @@ class UnitStackFn(Function):
             dXin = torch.empty((2, M, D), dtype=BF16, device=dev)
             ops.gat_input_bwd([dxt[g] for g in range(G)], [sid + g for g in range(G)], 2, [dX[0], dX[1]], [dXin[0], dXin[1]],
                               pdrop, seed)
-            # ---- gates -> cycle query -> word attention -> feat_enhance
-            dquery = ops.gate_bwd(Xin[0].view(B, N, D), Xin[1].view(B, N, D), k["query"], k["ga"], k["gm"], dgates[0],
-                                  dgates[1], dgates[2], dgates[3], dXin[0], dXin[1])
-            dqc = ops.linear_dgrad(dquery, k["wq"])
-            sink.weight([p.qa_w, p.qm_w], dquery, k["qc"])
-            sink.colsum([p.qa_b, p.qm_b], dquery)
-            dy, dwords, dwf_part, dcf_part = ops.qattn_bwd(dqc, k["y"].view(B, L, D), pk["fc_w"][i], qlen, words, W, k["alpha"],
-                                                           k["nrm"], k["prob"], k["ssum"], dwords=dwords, raw=True)
-            sink.colsum([p.fc_w], dwf_part)
-            sink.colsum([p.fc_b], dcf_part)
-            dy2 = dy.view(B * L, D)
-            d_dq = ops.linear_dgrad(dy2, k["we"], out=d_dq, beta=d_dq is not None)
-            sink.weight([p.fe_w], dy2, dq)
-            sink.colsum([p.fe_b], dy2)
+            # ---- gates -> gradient of this layer's cycle queries (QueryChainFn.backward takes it from there)
+            ops.gate_bwd(Xin[0].view(B, N, D), Xin[1].view(B, N, D), k["query"], k["ga"], k["gm"], dgates[0], dgates[1], dgates[2],
+                         dgates[3], dXin[0], dXin[1], dquery=dquery_all[i])
+            if chain is not None:
+                # the question side of this layer's Query Punishment Module goes backward on the question stream NOW, under
+                # the remaining layers of this loop (small kernels: SMs to spare) — by the time the stack is done only layer
+                # 0's chain is left, and the question encoder's own backward starts right behind it
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                with torch.cuda.stream(chain["stream"]):
+                    chain["stream"].wait_event(ev)
+                    QueryChainFn.layer_backward(chain, i, dquery_all[i], chain_acc)
             dX = dXin
+        if chain is not None:
+            chain["bwd"] = chain_acc
         need = ctx.needs_input_grad
         return ((None, dX[0].view(B, N, D) if need[1] else None, dX[1].view(B, N, D) if need[2] else None,
-                 d_dq if need[3] else None, dwords if need[4] else None, None, None) + sink.grads_for(ctx.params))
+                 dquery_all if need[3] else None, None) + sink.grads_for(ctx.params))
+
+
+class QueryChainFn(Function):
+    """The QUESTION side of the Query Punishment Module of all U unit layers (reference model/utils.py:60-100, called per layer
+    at model/models.py:142-147): feat_enhance GEMM -> word attention -> the two cycle-query projections (one GEMM), giving
+    query [U, B, 2D] (appearance | motion). It depends on the question encoder only, so it is hoisted out of the per-layer
+    critical path of the unit stack: forward right behind the question encoder on its side stream (under the appearance
+    encoder's recurrence), backward on that same stream next to the encoders' backward — the stack's main-stream chain
+    loses 4 launches per layer forward and 3 backward.
+    cfg = (W, pre | None); dq [B*L, D] bf16 (row stride free), words [B, L, Wp] bf16, qlen [B] int32; then per layer the 8
+    tensors feat_enhance.weight/bias, fc.weight/bias, query_weight (appear).weight/bias, query_weight (motion).weight/bias."""
+
+    @staticmethod
+    def launch(W, dq, words, qlen, params):
+        U = len(params) // 8
+        B, L, Wp = words.shape
+        D = params[0].shape[0]
+        dev = words.device
+        P = [params[8 * i:8 * i + 8] for i in range(U)]
+        small = {"q_b": torch.empty((U, 2 * D), dtype=F32, device=dev), "fe_b": torch.empty((U, D), dtype=F32, device=dev),
+                 "fc_w": torch.empty((U, D), dtype=F32, device=dev), "fc_b": torch.empty((U, 8), dtype=F32, device=dev)}
+        segs = []
+        for i, (fe_w, fe_b, fc_w, fc_b, qa_w, qa_b, qm_w, qm_b) in enumerate(P):
+            segs += [(small["q_b"][i, :D], qa_b.detach()), (small["q_b"][i, D:], qm_b.detach()), (small["fe_b"][i], fe_b.detach()),
+                     (small["fc_w"][i], fc_w.detach().reshape(-1)), (small["fc_b"][i, :1], fc_b.detach().reshape(-1))]
+        ops.scatter(segs, False)
+        words = ag._c(words)
+        query = torch.empty((U, B, 2 * D), dtype=BF16, device=dev)
+        keep = []
+        for i, (fe_w, fe_b, fc_w, fc_b, qa_w, qa_b, qm_w, qm_b) in enumerate(P):
+            we = ag.bf16_rows([fe_w])
+            y = ops.linear_fwd(dq, we, bias=small["fe_b"][i])
+            qc, alpha, nrm, prob, ssum = ops.qattn_fwd(y.view(B, L, D), small["fc_w"][i], small["fc_b"][i], qlen, words, W, Wp)
+            wq = ag.bf16_rows([qa_w, qm_w], out_cols=Wp, tag="cat")
+            ops.linear_fwd(qc, wq, bias=small["q_b"][i], out=query[i])
+            keep.append(dict(y=y, qc=qc, alpha=alpha, nrm=nrm, prob=prob, ssum=ssum, we=we, wq=wq))
+        return dict(query=query, keep=keep, small=small, words=words, dq=dq, qlen=qlen, params=list(params),
+                    cfg=(U, B, L, D, W, Wp))
+
+    @staticmethod
+    def forward(ctx, cfg, dq, words, qlen, *params):
+        W, pre = cfg
+        if pre is None:
+            pre = QueryChainFn.launch(W, dq, words, qlen, params)
+        pre["params"] = list(params)
+        ctx.pre = pre
+        ctx.params = params
+        ctx.stream = torch.cuda.current_stream()
+        pre["stream"] = ctx.stream
+        return pre["query"]
+
+    @staticmethod
+    def layer_backward(pre, i, dquery, acc):
+        """Backward of layer i's chain from the gradient of its cycle queries; acc = dict(sink, d_dq, dwords) accumulates over
+        the layers. Called either from backward() below or — layer by layer, on the question stream, while the unit stack's
+        backward is still running on the main stream — from UnitStackFn.backward (which then leaves the result in
+        pre["bwd"] for backward() to hand on)."""
+        U, B, L, D, W, Wp = pre["cfg"]
+        small, params, k = pre["small"], pre["params"], pre["keep"][i]
+        fe_w, fe_b, fc_w, fc_b, qa_w, qa_b, qm_w, qm_b = params[8 * i:8 * i + 8]
+        sink = acc["sink"]
+        dqc = ops.linear_dgrad(dquery, k["wq"])
+        sink.weight([qa_w, qm_w], dquery, k["qc"])
+        sink.colsum([qa_b, qm_b], dquery)
+        dy, acc["dwords"], dwf_part, dcf_part = ops.qattn_bwd(dqc, k["y"].view(B, L, D), small["fc_w"][i], pre["qlen"], pre["words"],
+                                                              W, k["alpha"], k["nrm"], k["prob"], k["ssum"], dwords=acc["dwords"],
+                                                              raw=True)
+        sink.colsum([fc_w], dwf_part)
+        sink.colsum([fc_b], dcf_part)
+        dy2 = dy.view(B * L, D)
+        acc["d_dq"] = ops.linear_dgrad(dy2, k["we"], out=acc["d_dq"], beta=acc["d_dq"] is not None)
+        sink.weight([fe_w], dy2, pre["dq"])
+        sink.colsum([fe_b], dy2)
+        acc.setdefault("keep", []).append((dquery, dqc, dy))      # side-stream launches: operands outlive the caller's scope
+
+    @staticmethod
+    def backward(ctx, dquery_all):
+        pre, params = ctx.pre, ctx.params
+        U = pre["cfg"][0]
+        acc = pre.pop("bwd", None)
+        if acc is None:                          # not driven by UnitStackFn.backward: do the whole chain here
+            acc = dict(sink=_GradSink(), d_dq=None, dwords=None)
+            dquery_all = ag._c(dquery_all)
+            for i in reversed(range(U)):
+                QueryChainFn.layer_backward(pre, i, dquery_all[i], acc)
+        ev = torch.cuda.Event()
+        ev.record()
+        LAST_QUERY_CHAIN_BWD[0] = ev          # (the data-parallel hook flushes these gradients from another stream)
+        need = ctx.needs_input_grad
+        return ((None, acc["d_dq"] if need[1] else None, acc["dwords"] if need[2] else None, None)
+                + acc["sink"].grads_for(params))
 
 
 class QuestionInputFn(Function):
@@ -391,7 +474,7 @@ class QuestionInputFn(Function):
         gates, h_hist, c_hist, h_last, seq_out, sync = ops.lstm_seq_fwd(x, wih, whh, bias, seq_len=qlen, want_seq=True)
         ag.SYNC_WORDS.append(sync)
         return dict(tokens=tokens, words=words, x=x, wih=wih, whh=whh, gates=gates, h_hist=h_hist, c_hist=c_hist,
-                    h_last=h_last, seq_out=seq_out, cfg=(B, L, W, Wp, H, p_emb, seed, sid))
+                    h_last=h_last, seq_out=seq_out, qlen=qlen, cfg=(B, L, W, Wp, H, p_emb, seed, sid))
 
     @staticmethod
     def forward(ctx, cfg, tokens, qlen, table, *params):

@@ -123,6 +123,9 @@ class DualVGR(nn.Module):
         side.wait_stream(cur)
         with torch.cuda.stream(side):
             launched = self.linguistic_input_unit.launch(question, qlen)       # kernels out first, autograd node last (below)
+            # the question side of the Query Punishment Module of every unit layer only needs the question encoder: its
+            # kernels go out right behind it, on the same stream, under the appearance encoder's recurrence
+            chain = self.visual_input_unit.launch_query_chain(launched[1])
         # the two clip streams are carried as ONE stacked [2, B*N, D] tensor: both encoders write into its halves
         x0 = torch.empty((2, B * N, D), dtype=BF16, device=dev)
         app = self.visual_appearance_input_unit(video_appearance_feat, out=x0[0])
@@ -131,8 +134,9 @@ class DualVGR(nn.Module):
         mot = ag.linear(mot_in, self.visual_motion_input_unit.weight, self.visual_motion_input_unit.bias, out=x0[1]).view(B, N, D)
         with torch.cuda.stream(side):
             question_embedding, word_embedding, dynamic_q = self.linguistic_input_unit.fused(question, qlen, launched)
+            query_all = self.visual_input_unit.query_chain(dynamic_q, word_embedding, qlen, chain)
         cur.wait_stream(side)
-        for t in (question_embedding, word_embedding, dynamic_q):
+        for t in (question_embedding, word_embedding, dynamic_q, query_all):
             t.record_stream(cur)
         hook = getattr(self, "_unit_inputs_grad_hook", None)
         if hook is not None and torch.is_grad_enabled():
@@ -143,7 +147,7 @@ class DualVGR(nn.Module):
             for t in hooked:
                 t.register_hook(hook)
         visual, aq_embed, mq_embed, com_app, com_motion, aq_fusion, mq_fusion = self.visual_input_unit.fused(
-            app, mot, dynamic_q, word_embedding, qlen)
+            app, mot, dynamic_q, word_embedding, qlen, query_all=query_all)
         pooled = self.feature_aggregation(visual)
         out = self.output_unit(question_embedding, pooled)
         return out, aq_embed, mq_embed, com_app, com_motion, aq_fusion, mq_fusion
@@ -181,16 +185,38 @@ class DualVGRUnit_multiple(nn.Module):
         self.register_buffer("appearance_adj", adj.clone(), persistent=False)
         self.register_buffer("motion_adj", adj.clone(), persistent=False)
 
-    def fused(self, app, mot, dq2, words_p, qlen):
+    def _query_params(self):
+        return [p for i in range(self.layers) for p in fs.unit_layer_params(self, i)[:8]]
+
+    def launch_query_chain(self, question_state):
+        """Launches the forward kernels of fused_stack.QueryChainFn on the current stream from the question encoder's raw
+        launch state (fused_stack.QuestionInputFn.launch) — no autograd node yet; query_chain() adopts the result."""
+        if self.layers == 0:
+            return None
+        B, L, W, Wp, H = question_state["cfg"][:5]
+        dq = question_state["seq_out"].view(B * L, 4 * H)[:, :2 * H]
+        qlen = question_state["qlen"]
+        return fs.QueryChainFn.launch(self.word_dim, dq, question_state["words"], qlen, self._query_params())
+
+    def query_chain(self, dq2, words_p, qlen, launched=None):
+        """The cycle queries of every layer, [U, B, 2D] bf16 (fused_stack.QueryChainFn)."""
+        if self.layers == 0:
+            return torch.zeros((0, words_p.shape[0], 2 * self.module_dim), dtype=BF16, device=words_p.device)
+        return fs.QueryChainFn.apply((self.word_dim, launched), dq2, words_p, qlen, *self._query_params())
+
+    def fused(self, app, mot, dq2, words_p, qlen, query_all=None):
         """The whole stack as ONE autograd Function (fused_stack.UnitStackFn): app / mot [B,N,D] bf16, dq2 [B*L, D] bf16
         (row stride free), words_p [B,L,Wp] bf16 zero-padded, qlen int32. Same returns as forward()."""
         U = self.layers
+        if query_all is None:
+            query_all = self.query_chain(dq2, words_p, qlen)
         heads = self.acGCN[0].n_heads if U > 0 else 4
         pdrop = self.acGCN[0].dropout if (U > 0 and self.training) else 0.0
         params = [p for i in range(U) for p in fs.unit_layer_params(self, i)]
         grad = torch.is_grad_enabled()
-        cfg = (U, heads, float(pdrop), self.word_dim, getattr(self, "_aux", None) if grad else None, grad)
-        outs = fs.UnitStackFn.apply(cfg, app, mot, dq2, words_p, qlen, self.appearance_adj, *params)
+        chain = getattr(query_all.grad_fn, "pre", None) if (grad and query_all.grad_fn is not None) else None
+        cfg = (U, heads, float(pdrop), self.word_dim, getattr(self, "_aux", None) if grad else None, grad, chain)
+        outs = fs.UnitStackFn.apply(cfg, app, mot, query_all, self.appearance_adj, *params)
         app, mot, aq_embed, mq_embed = outs[:4]
         f32 = outs[4:]
         com_app_list = [f32[4 * i] for i in range(U)]

@@ -3,6 +3,7 @@ memory and streams are torch's), and launches the library's kernels on the curre
 
 No arithmetic of the hot path happens in PyTorch here; there is no fallback if the library is missing."""
 import ctypes
+import os
 
 import torch
 
@@ -326,7 +327,11 @@ def lstm_block_c(c, ):
 RESERVE_SMS = [0]
 
 
-def _cap():
+def _cap(which=0):
+    """Grid cap of the appearance encoder's backward launches: which = 0 the recurrence, 1 the weight-gradient GEMMs (only
+    capped when DVGR_RESERVE_WGRAD=1: they start when the question encoder's recurrence is nearly done)."""
+    if which == 1 and os.environ.get("DVGR_RESERVE_WGRAD", "0") == "0":
+        return 0
     return NUM_SMS - RESERVE_SMS[0] if RESERVE_SMS[0] > 0 else 0
 
 
@@ -572,10 +577,12 @@ def gate_fwd(xa, xm, query):
     return ga, gm
 
 
-def gate_bwd(xa, xm, query, ga, gm, dga, dga2, dgm, dgm2, dxa, dxm):
-    """dxa / dxm are accumulated into; returns dquery [B, ld_q]."""
+def gate_bwd(xa, xm, query, ga, gm, dga, dga2, dgm, dgm2, dxa, dxm, dquery=None):
+    """dxa / dxm are accumulated into; returns dquery [B, ld_q] (written into `dquery` when given: same strides as query)."""
     B, N, D = xa.shape
-    dquery = torch.empty_like(query)
+    if dquery is None:
+        dquery = torch.empty_like(query)
+    assert dquery.shape == query.shape and dquery.stride() == query.stride() and dquery.dtype == query.dtype
     assert dxa.dtype == xa.dtype and dxm.dtype == xa.dtype
     _lib.check(_v("gate_bwd", xa)(_ptr(xa), _ptr(xm), _ptr(query), query.stride(0), B, N, D, _ptr(ga), _ptr(gm), _ptr(dga),
                              _ptr(dga2), _ptr(dgm), _ptr(dgm2), _ptr(dxa), _ptr(dxm), _ptr(dquery), _stream()),

@@ -178,7 +178,8 @@ class UnitStackFn(Function):
     @staticmethod
     def forward(ctx, cfg, app, mot, query_all, adj, *params):
         U, heads, pdrop, W, aux, want_f32 = cfg[:6]
-        ctx.chain = cfg[6] if len(cfg) > 6 else None        # QueryChainFn's state: its backward is driven from ours (below)
+        chain_fwd = cfg[6] if len(cfg) > 6 else None        # QueryChainFn's state: per-layer ready events (forward) ...
+        ctx.chain = chain_fwd if (chain_fwd is not None and want_f32) else None      # ... and its backward is driven from ours
         B, N, D = app.shape
         M, Dh = B * N, D // heads
         dev = app.device
@@ -194,6 +195,8 @@ class UnitStackFn(Function):
         for i, p in enumerate(PL):
             sid = sid0 + 3 * G * i
             # ---- Query Punishment Module: per-clip gates of both streams from this layer's cycle queries (QueryChainFn)
+            if chain_fwd is not None and chain_fwd["stream"] != cur:
+                cur.wait_event(chain_fwd["events"][i])
             query = query_all[i]
             ga, gm = ops.gate_fwd(X[0].view(B, N, D), X[1].view(B, N, D), query)
             # ---- multi-view GAT: every graph projects its own dropped copy of its stream; ONE batched GEMM, ONE attention launch
@@ -374,7 +377,7 @@ class QueryChainFn(Function):
         ops.scatter(segs, False)
         words = ag._c(words)
         query = torch.empty((U, B, 2 * D), dtype=BF16, device=dev)
-        keep = []
+        keep, events = [], []
         for i, (fe_w, fe_b, fc_w, fc_b, qa_w, qa_b, qm_w, qm_b) in enumerate(P):
             we = ag.bf16_rows([fe_w])
             y = ops.linear_fwd(dq, we, bias=small["fe_b"][i])
@@ -382,8 +385,11 @@ class QueryChainFn(Function):
             wq = ag.bf16_rows([qa_w, qm_w], out_cols=Wp, tag="cat")
             ops.linear_fwd(qc, wq, bias=small["q_b"][i], out=query[i])
             keep.append(dict(y=y, qc=qc, alpha=alpha, nrm=nrm, prob=prob, ssum=ssum, we=we, wq=wq))
-        return dict(query=query, keep=keep, small=small, words=words, dq=dq, qlen=qlen, params=list(params),
-                    cfg=(U, B, L, D, W, Wp))
+            ev = torch.cuda.Event()
+            ev.record()
+            events.append(ev)             # layer i's queries are ready: the unit stack waits per layer, not for the whole chain
+        return dict(query=query, keep=keep, small=small, words=words, dq=dq, qlen=qlen, params=list(params), events=events,
+                    stream=torch.cuda.current_stream(), cfg=(U, B, L, D, W, Wp))
 
     @staticmethod
     def forward(ctx, cfg, dq, words, qlen, *params):

@@ -135,7 +135,8 @@ class DualVGR(nn.Module):
         with torch.cuda.stream(side):
             question_embedding, word_embedding, dynamic_q = self.linguistic_input_unit.fused(question, qlen, launched)
             query_all = self.visual_input_unit.query_chain(dynamic_q, word_embedding, qlen, chain)
-        cur.wait_stream(side)
+        # (no join here: the unit stack waits for each layer's queries through the chain's per-layer events, and the main
+        #  stream only needs the question embedding at the classifier)
         for t in (question_embedding, word_embedding, dynamic_q, query_all):
             t.record_stream(cur)
         hook = getattr(self, "_unit_inputs_grad_hook", None)
@@ -147,8 +148,9 @@ class DualVGR(nn.Module):
             for t in hooked:
                 t.register_hook(hook)
         visual, aq_embed, mq_embed, com_app, com_motion, aq_fusion, mq_fusion = self.visual_input_unit.fused(
-            app, mot, dynamic_q, word_embedding, qlen, query_all=query_all)
+            app, mot, dynamic_q, word_embedding, qlen, query_all=query_all, chain=chain)
         pooled = self.feature_aggregation(visual)
+        cur.wait_stream(side)
         out = self.output_unit(question_embedding, pooled)
         return out, aq_embed, mq_embed, com_app, com_motion, aq_fusion, mq_fusion
 
@@ -204,7 +206,7 @@ class DualVGRUnit_multiple(nn.Module):
             return torch.zeros((0, words_p.shape[0], 2 * self.module_dim), dtype=BF16, device=words_p.device)
         return fs.QueryChainFn.apply((self.word_dim, launched), dq2, words_p, qlen, *self._query_params())
 
-    def fused(self, app, mot, dq2, words_p, qlen, query_all=None):
+    def fused(self, app, mot, dq2, words_p, qlen, query_all=None, chain=None):
         """The whole stack as ONE autograd Function (fused_stack.UnitStackFn): app / mot [B,N,D] bf16, dq2 [B*L, D] bf16
         (row stride free), words_p [B,L,Wp] bf16 zero-padded, qlen int32. Same returns as forward()."""
         U = self.layers
@@ -214,7 +216,8 @@ class DualVGRUnit_multiple(nn.Module):
         pdrop = self.acGCN[0].dropout if (U > 0 and self.training) else 0.0
         params = [p for i in range(U) for p in fs.unit_layer_params(self, i)]
         grad = torch.is_grad_enabled()
-        chain = getattr(query_all.grad_fn, "pre", None) if (grad and query_all.grad_fn is not None) else None
+        if chain is None and grad and query_all.grad_fn is not None:
+            chain = getattr(query_all.grad_fn, "pre", None)
         cfg = (U, heads, float(pdrop), self.word_dim, getattr(self, "_aux", None) if grad else None, grad, chain)
         outs = fs.UnitStackFn.apply(cfg, app, mot, query_all, self.appearance_adj, *params)
         app, mot, aq_embed, mq_embed = outs[:4]

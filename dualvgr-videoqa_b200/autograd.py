@@ -213,8 +213,10 @@ class LinearFn(Function):
     x: [..., K'] bf16 with K' >= K (zero padded to a multiple of 8); W fp32 [N, K]; output bf16 (or fp32: the logits)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, act, out_f32, act_grad_folded=False, out_slot=None):
-        """out_slot: optional 1-tuple with a preallocated [M, N] output buffer (see AppearanceEncoderFn)."""
+    def forward(ctx, x, weight, bias, act, out_f32, act_grad_folded=False, out_slot=None, dx_slot=None):
+        """out_slot: optional 1-tuple with a preallocated [M, N] output buffer (see AppearanceEncoderFn).
+        dx_slot: optional (PairSlot, index): the input gradient is written into that half of a shared [2, M, K] buffer."""
+        ctx.dx_slot = dx_slot
         Kp = x.shape[-1]
         x2 = _rows2d(x)
         w = bf16_rows([weight], out_cols=Kp)
@@ -243,7 +245,10 @@ class LinearFn(Function):
             d = ops.act_bwd(d, y, ctx.act)
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            dx = ops.linear_dgrad(d, w).view(*ctx.lead, w.shape[1])
+            slot = None
+            if ctx.dx_slot is not None:
+                slot = ctx.dx_slot[0].take(ctx.dx_slot[1], M, w.shape[1], d.device)
+            dx = ops.linear_dgrad(d, w, out=slot).view(*ctx.lead, w.shape[1])
         if ctx.needs_input_grad[1]:
             tgt = grad_target([ctx.wparam])
             if tgt is not None:
@@ -256,7 +261,21 @@ class LinearFn(Function):
                 ops.colsum(d[:, :N], out=tgt, accumulate=True)
             else:
                 db = ops.colsum(d)[:N]
-        return dx, dw, db, None, None, None, None
+        return dx, dw, db, None, None, None, None, None
+
+
+class PairSlot:
+    """[2, M, K] bf16 gradient buffer shared by the backward passes of two Functions whose input gradients the consumer wants
+    adjacent in memory (the MFB's two projections feed the unit stack's stacked [2, M, D] layout: no stacking copy)."""
+
+    def __init__(self):
+        self.buf, self.used = None, 2
+
+    def take(self, idx, M, K, device):
+        if self.used >= 2 or self.buf is None or tuple(self.buf.shape[1:]) != (M, K):
+            self.buf, self.used = torch.empty((2, M, K), dtype=BF16, device=device), 0
+        self.used += 1
+        return self.buf[idx]
 
 
 def _rows2d(x):
@@ -340,7 +359,7 @@ def _route_small(param, grad):
     return grad
 
 
-def linear(x, weight, bias=None, act=None, out_f32=False, act_grad_folded=False, out=None):
+def linear(x, weight, bias=None, act=None, out_f32=False, act_grad_folded=False, out=None, dx_slot=None):
     """act_grad_folded: the consumer's backward kernel already returns d(pre-activation) (view attention, MFB pair-sum,
     read-out fold act' into their own pass), so this backward must not apply act' again."""
     if x.dtype == F32:          # fp32 mode: 3 x bf16 split products (fp32_path.Linear32Fn); `out` slots are a bf16-path layout
@@ -349,7 +368,7 @@ def linear(x, weight, bias=None, act=None, out_f32=False, act_grad_folded=False,
         if out is not None:
             raise ValueError("preallocated output slots are not supported in fp32 mode")
         return y
-    return LinearFn.apply(x, weight, bias, act, out_f32, act_grad_folded, (out,) if out is not None else None)
+    return LinearFn.apply(x, weight, bias, act, out_f32, act_grad_folded, (out,) if out is not None else None, dx_slot)
 
 
 # ---------------------------------------------------------------------------------------------------------------------

@@ -76,16 +76,22 @@ def side_stream(device, key="aux"):
         # question encoder is on the critical path of the forward pass (high priority, like the engine's main stream)
         # question stream: one level ABOVE the engine's main stream (-1) — when the question encoder's 48 CTAs retire, the
         # query chain behind it must get those SMs before the appearance encoder's still-pending CTAs do
-        _SIDE[k] = torch.cuda.Stream(device=device, priority=0 if key == "aux" else -2)
+        _SIDE[k] = torch.cuda.Stream(device=device, priority=0 if key.startswith("aux") else -2)
+    _ACTIVE.add(k)
     return _SIDE[k]
 
 
+_ACTIVE = set()        # side streams handed out since the last join (a stream that took no part in a capture must not be joined)
+
+
 def join_side_streams(device):
-    """The current stream waits for everything queued on this device's side streams (question encoder, auxiliary losses)."""
+    """The current stream waits for everything queued on the side streams of this device that were used since the last join
+    (question encoder, auxiliary losses)."""
     cur = torch.cuda.current_stream()
-    for (dev, _), st in _SIDE.items():
-        if dev == str(device):
-            cur.wait_stream(st)
+    for k in sorted(_ACTIVE):
+        if k[0] == str(device):
+            cur.wait_stream(_SIDE[k])
+            _ACTIVE.discard(k)
 
 
 class _GradSink:
@@ -241,10 +247,13 @@ class UnitStackFn(Function):
             # (Forked right after each layer's graph attention they fought the stack's own GEMMs for SMs: a GEMM CTA needs a
             # whole SM's shared memory and cannot start while any small CTA is resident there — measured +0.4 ms.)
             c_com, c_dep, parts = aux
-            side = side_stream(dev)
-            side.wait_stream(cur)
-            with torch.cuda.stream(side):
-                for i, o32, gr, ws in reversed(aux_jobs):
+            n_side = max(1, min(len(aux_jobs), int(os.environ.get("DVGR_AUX_STREAMS", "3"))))
+            for r, (i, o32, gr, ws) in enumerate(reversed(aux_jobs)):
+                # one low-priority stream per layer (round-robin): the three layers' latency-bound launches overlap each other
+                side = side_stream(dev, "aux" if r % n_side == 0 else f"aux{r % n_side}")
+                if r < n_side:
+                    side.wait_stream(cur)
+                with torch.cuda.stream(side):
                     ops.aux_loss_unit_into(o32[0], o32[2], o32[1], o32[3], c_com, c_dep, gr[0], gr[2], gr[1], gr[3], parts[i], ws)
                     ev = torch.cuda.Event()
                     ev.record(side)

@@ -23,7 +23,8 @@ class MFB(nn.Module):
             nn.init.constant_(lin.bias, 0)
 
     def forward(self, x):
-        x0 = ag.linear(x[0], self.linear0.weight, self.linear0.bias, act="elu", act_grad_folded=True)
-        x1 = ag.linear(x[1], self.linear1.weight, self.linear1.bias, act="elu", act_grad_folded=True)
+        slot = ag.PairSlot()        # the two input gradients land in the halves of ONE buffer (the unit stack's stacked layout)
+        x0 = ag.linear(x[0], self.linear0.weight, self.linear0.bias, act="elu", act_grad_folded=True, dx_slot=(slot, 0))
+        x1 = ag.linear(x[1], self.linear1.weight, self.linear1.bias, act="elu", act_grad_folded=True, dx_slot=(slot, 1))
         z = ag.MfbPairFn.apply(x0, x1)
         return ag.linear(z, self.linear_out.weight, self.linear_out.bias, act="elu")

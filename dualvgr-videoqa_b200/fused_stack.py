@@ -328,6 +328,28 @@ class UnitStackFn(Function):
                                               [z[g] for g in range(G)], [dz4[g] for g in range(G)], adj, B, N, heads=heads,
                                               p_att=pdrop, p_out=pdrop, seed=seed, streams=streams, douts32=d32,
                                               dwhs=[dwh[g] for g in range(G)], raw=True)
+            # ---- gates -> gradient of this layer's cycle queries; the gates' contribution to the layer input goes into dX (the
+            #      residual-branch gradient: nobody else reads it any more) so that it only depends on the attention backward
+            if chain is not None:
+                # gate backward + the question side of this layer's Query Punishment Module run on the question stream NOW,
+                # next to the projection dgrad below and under the remaining layers of this loop (small kernels: SMs to
+                # spare) — by the time the stack is done only layer 0's chain is left, and the question encoder's own
+                # backward starts right behind it
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                with torch.cuda.stream(chain["stream"]):
+                    chain["stream"].wait_event(ev)
+                    ops.gate_bwd(Xin[0].view(B, N, D), Xin[1].view(B, N, D), k["query"], k["ga"], k["gm"], dgates[0], dgates[1],
+                                 dgates[2], dgates[3], dX[0], dX[1], dquery=dquery_all[i])
+                    ev_gate = torch.cuda.Event()
+                    ev_gate.record()
+                    QueryChainFn.layer_backward(chain, i, dquery_all[i], chain_acc)
+            else:
+                ev_gate = None
+                ops.gate_bwd(Xin[0].view(B, N, D), Xin[1].view(B, N, D), k["query"], k["ga"], k["gm"], dgates[0], dgates[1], dgates[2],
+                             dgates[3], dX[0], dX[1], dquery=dquery_all[i])
+            # ---- projection dgrad (batched over the 4 graphs), then the gradient of the layer input: residual branch (+ gates)
+            #      + the (dropped) inputs of the two graphs of each stream
             dxt = torch.empty((G, M, D), dtype=BF16, device=dev)
             ops.gemm(dwh, 0, k["wb"], 1, M, D, D, dxt, ldc=D, batch=G, c_batch=M * D, a_c2=[0, 1, 2, 3], b_c2=[0, 1, 2, 3])
             for g in range(G):
@@ -336,22 +358,11 @@ class UnitStackFn(Function):
                 sink.colsum(p.Wb[g], dwh[g])
                 for h in range(heads):
                     sink.colsum([p.aw[g][h], p.ab[g][h]], dav[g][:, h * (2 * Dh + 1):(h + 1) * (2 * Dh + 1)])
-            # ---- gradient of the layer input: residual branch + the (dropped) inputs of the two graphs of each stream
+            if ev_gate is not None:
+                cur.wait_event(ev_gate)
             dXin = torch.empty((2, M, D), dtype=BF16, device=dev)
             ops.gat_input_bwd([dxt[g] for g in range(G)], [sid + g for g in range(G)], 2, [dX[0], dX[1]], [dXin[0], dXin[1]],
                               pdrop, seed)
-            # ---- gates -> gradient of this layer's cycle queries (QueryChainFn.backward takes it from there)
-            ops.gate_bwd(Xin[0].view(B, N, D), Xin[1].view(B, N, D), k["query"], k["ga"], k["gm"], dgates[0], dgates[1], dgates[2],
-                         dgates[3], dXin[0], dXin[1], dquery=dquery_all[i])
-            if chain is not None:
-                # the question side of this layer's Query Punishment Module goes backward on the question stream NOW, under
-                # the remaining layers of this loop (small kernels: SMs to spare) — by the time the stack is done only layer
-                # 0's chain is left, and the question encoder's own backward starts right behind it
-                ev = torch.cuda.Event()
-                ev.record(cur)
-                with torch.cuda.stream(chain["stream"]):
-                    chain["stream"].wait_event(ev)
-                    QueryChainFn.layer_backward(chain, i, dquery_all[i], chain_acc)
             dX = dXin
         if chain is not None:
             chain["bwd"] = chain_acc

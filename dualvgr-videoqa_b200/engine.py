@@ -224,7 +224,14 @@ class TrainEngine:
             return self._forward_backward_fp32(app, mot, question, question_len, answers)
         model = self.model
         model.train()
-        self.gflat.zero_()
+        # the 122 MB gradient buffer is cleared on a side stream, under the forward pass (nothing writes it before backward)
+        cur = torch.cuda.current_stream()
+        zs = fs.side_stream(app.device, "aux")
+        zs.wait_stream(cur)
+        with torch.cuda.stream(zs):
+            self.gflat.zero_()
+            ev_zero = torch.cuda.Event()
+            ev_zero.record()
         ag.begin_step_flags()
         ops.begin_step_counters(app.device)        # zeroed tile counters of this step's dynamically scheduled GEMMs
         unit = model.visual_input_unit
@@ -240,6 +247,7 @@ class TrainEngine:
             unit._aux = None
         self.last_logits = outputs[0].detach()
         ce, correct = ag.CrossEntropyFn.apply(outputs[0], answers, True)
+        cur.wait_event(ev_zero)
         ops.DEFER_WGRAD[0] = True          # weight / bias gradients of the nn.Linear layers: queued during backward ...
         try:
             ce.backward()                  # the auxiliary terms' gradients are injected inside the unit stack's backward

@@ -238,7 +238,8 @@ class LinearFn(Function):
         if ctx.out_f32:      # fp32 gradient of an fp32 output -> zero-padded bf16 operand, one library pass
             d = ops.cast_rows(_c(dy.reshape(M, N)).float(), out_cols=(N + 7) // 8 * 8)
         else:
-            d = _c(dy.reshape(M, N))
+            # (a column slice of a wider gradient — torch.cat's backward — is a valid GEMM operand as it is: no copy)
+            d = _rows2d(dy) if (dy.dim() == 2 and y is None and dy.dtype == BF16) else _c(dy.reshape(M, N))
             if d.dtype != BF16:
                 d = d.to(BF16)
         if y is not None:
@@ -887,7 +888,7 @@ class ReadoutFn(Function):
     @staticmethod
     def backward(ctx, dp):
         v, u, wv, alpha = ctx.saved_tensors
-        dv, du, dw, dc = ops.readout_bwd(_c(dp), v, u, wv, alpha)
+        dv, du, dw, dc = ops.readout_bwd(dp if (dp.dim() == 2 and dp.stride(1) == 1) else _c(dp), v, u, wv, alpha)
         return dv, du, _route_small(ctx.wc[0], dw.view(1, -1)), _route_small(ctx.wc[1], dc.view(1))
 
 

@@ -888,7 +888,15 @@ class ReadoutFn(Function):
     @staticmethod
     def backward(ctx, dp):
         v, u, wv, alpha = ctx.saved_tensors
-        dv, du, dw, dc = ops.readout_bwd(dp if (dp.dim() == 2 and dp.stride(1) == 1) else _c(dp), v, u, wv, alpha)
+        dpc = dp if (dp.dim() == 2 and dp.stride(1) == 1) else _c(dp)
+        tw, tc = _bias_target(ctx.wc[0]), _bias_target(ctx.wc[1])
+        if ops.DEFER_WGRAD[0] and tw is not None and tc is not None:
+            # engine step: the two per-sample partial reductions ride the grouped column sum at the end of the step
+            dv, du, dw_part, dc_part = ops.readout_bwd(dpc, v, u, wv, alpha, raw=True)
+            ops.colsum_enqueue(dw_part, tw.view(-1))
+            ops.colsum_enqueue(dc_part, tc.view(-1))
+            return dv, du, None, None
+        dv, du, dw, dc = ops.readout_bwd(dpc, v, u, wv, alpha)
         return dv, du, _route_small(ctx.wc[0], dw.view(1, -1)), _route_small(ctx.wc[1], dc.view(1))
 
 

@@ -318,25 +318,27 @@ readout_bwd_kernel(const bf16* __restrict__ dpooled, long long ld_p, const bf16*
 // =============================================================================================== BatchNorm1d
 // reference model/AnswerDecoder.py:193 (nn.BatchNorm1d(module_dim)): batch statistics (biased variance) in training,
 // running statistics in eval; running stats updated with momentum 0.1 and the UNBIASED variance, as torch does.
-// Block = 32 feature columns x 8 row lanes: the batch dimension is walked by 8 threads per column and reduced through
-// shared memory in a fixed order (one thread per column walking all B rows took 100 us for the backward at B = 256).
+// Block = 32 feature columns x kBnRL row lanes: the batch dimension is walked by kBnRL threads per column and reduced through
+// shared memory in a fixed order (one thread per column walking all B rows took 100 us for the backward at B = 256; 8 row
+// lanes 31 us: 24 CTAs of serial 32-row walks; 32 row lanes put 4x more loads in flight).
+constexpr int kBnRL = 32;
 __device__ __forceinline__ float bn_reduce8(float v, float (*red)[33], int cl, int rl) {
   __syncthreads();
   red[rl][cl] = v;
   __syncthreads();
   float s = 0.f;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) s += red[k][cl];
+  for (int k = 0; k < kBnRL; ++k) s += red[k][cl];
   return s;
 }
 
 template <typename TX>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(32 * kBnRL)
 bn_fwd_kernel(const TX* __restrict__ x, int B, int D, const float* __restrict__ gamma, const float* __restrict__ betap,
               float* __restrict__ run_mean, float* __restrict__ run_var, int training, float momentum, float eps,
               bf16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out,
               const float* __restrict__ ext_stats, int Btot) {
-  __shared__ float red[8][33];
+  __shared__ float red[kBnRL][33];
   const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
   const bool ok = c < D;
@@ -354,11 +356,11 @@ bn_fwd_kernel(const TX* __restrict__ x, int B, int D, const float* __restrict__ 
   } else if (training) {
     float s = 0.f;
     if (ok)
-      for (int r = rl; r < B; r += 8) s += ldf<TX>(x + (long long)r * D + c);
+      for (int r = rl; r < B; r += kBnRL) s += ldf<TX>(x + (long long)r * D + c);
     mean = bn_reduce8(s, red, cl, rl) / B;
     float v = 0.f;
     if (ok)
-      for (int r = rl; r < B; r += 8) {
+      for (int r = rl; r < B; r += kBnRL) {
         const float d = ldf<TX>(x + (long long)r * D + c) - mean;
         v += d * d;
       }
@@ -379,20 +381,20 @@ bn_fwd_kernel(const TX* __restrict__ x, int B, int D, const float* __restrict__ 
     rstd_out[c] = rstd;
   }
   const float g = gamma[c], bt = betap[c];
-  for (int r = rl; r < B; r += 8)
+  for (int r = rl; r < B; r += kBnRL)
     act::st1(y + (long long)r * D + c, (ldf<TX>(x + (long long)r * D + c) - mean) * rstd * g + bt);
 }
 
 // per-column (sum, sum of squares) of the local batch: out [2][D] (the operand of the SyncBN all-reduce)
 template <typename TX>
-__global__ void __launch_bounds__(256) bn_stats_kernel(const TX* __restrict__ x, int B, int D, float* __restrict__ out) {
-  __shared__ float red[8][33];
+__global__ void __launch_bounds__(32 * kBnRL) bn_stats_kernel(const TX* __restrict__ x, int B, int D, float* __restrict__ out) {
+  __shared__ float red[kBnRL][33];
   const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
   const bool ok = c < D;
   float s = 0.f, ss = 0.f;
   if (ok)
-    for (int r = rl; r < B; r += 8) {
+    for (int r = rl; r < B; r += kBnRL) {
       const float v = ldf<TX>(x + (long long)r * D + c);
       s += v;
       ss += v * v;
@@ -408,19 +410,19 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const TX* __restrict__ x,
 // ext_sums [2][D] = (sum dy, sum dy * xhat) over the GLOBAL batch of Btot rows (SyncBN, second pass); stats_only: write the
 // LOCAL sums to dbeta / dgamma and stop (SyncBN, first pass)
 template <typename TX>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(32 * kBnRL)
 bn_bwd_kernel(const bf16* __restrict__ dy, const TX* __restrict__ x, int B, int D, const float* __restrict__ gamma,
               const float* __restrict__ mean, const float* __restrict__ rstd, int training, TX* __restrict__ dx,
               float* __restrict__ dgamma, float* __restrict__ dbeta, const float* __restrict__ ext_sums, int Btot,
               int stats_only) {
-  __shared__ float red[8][33];
+  __shared__ float red[kBnRL][33];
   const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
   const bool ok = c < D;
   const float m = ok ? mean[c] : 0.f, rs = ok ? rstd[c] : 0.f, g = ok ? gamma[c] : 0.f;
   float sdy = 0.f, sdyx = 0.f;
   if (ok)
-    for (int r = rl; r < B; r += 8) {
+    for (int r = rl; r < B; r += kBnRL) {
       const float d = act::ld1(dy + (long long)r * D + c);
       const float xh = (ldf<TX>(x + (long long)r * D + c) - m) * rs;
       sdy += d;
@@ -440,7 +442,7 @@ bn_bwd_kernel(const bf16* __restrict__ dy, const TX* __restrict__ x, int B, int 
     sdyx = ext_sums[D + c];
     nb = (float)Btot;
   }
-  for (int r = rl; r < B; r += 8) {
+  for (int r = rl; r < B; r += kBnRL) {
     const float d = act::ld1(dy + (long long)r * D + c);
     const float xh = (ldf<TX>(x + (long long)r * D + c) - m) * rs;
     const float o = training ? g * rs * (d - sdy / nb - xh * sdyx / nb) : g * rs * d;
@@ -1069,11 +1071,11 @@ extern "C" int DVGR_FN(dvgr_bn_fwd_ex)(const void* x, int x_is_f32, int B, int D
   if (B <= 0 || D <= 0) return 0;
   if (ext_stats != nullptr && Btot < B) return set_error("bn_fwd: global batch %d smaller than the local one %d", Btot, B);
   if (x_is_f32)
-    bn_fwd_kernel<float><<<(D + 31) / 32, 256, 0, ST(stream)>>>(reinterpret_cast<const float*>(x), B, D, gamma, beta,
+    bn_fwd_kernel<float><<<(D + 31) / 32, 32 * kBnRL, 0, ST(stream)>>>(reinterpret_cast<const float*>(x), B, D, gamma, beta,
                                                                  run_mean, run_var, training, momentum, eps, BF(y),
                                                                  mean_out, rstd_out, ext_stats, Btot);
   else
-    bn_fwd_kernel<bf16><<<(D + 31) / 32, 256, 0, ST(stream)>>>(CBF(x), B, D, gamma, beta, run_mean, run_var, training,
+    bn_fwd_kernel<bf16><<<(D + 31) / 32, 32 * kBnRL, 0, ST(stream)>>>(CBF(x), B, D, gamma, beta, run_mean, run_var, training,
                                                                 momentum, eps, BF(y), mean_out, rstd_out, ext_stats, Btot);
   DVGR_CHECK_LAUNCH("bn_fwd");
   return 0;
@@ -1086,8 +1088,8 @@ extern "C" int DVGR_FN(dvgr_bn_fwd)(const void* x, int x_is_f32, int B, int D, c
 }
 extern "C" int DVGR_FN(dvgr_bn_stats)(const void* x, int x_is_f32, int B, int D, float* out, void* stream) {
   if (B <= 0 || D <= 0) return 0;
-  if (x_is_f32) bn_stats_kernel<float><<<(D + 31) / 32, 256, 0, ST(stream)>>>(reinterpret_cast<const float*>(x), B, D, out);
-  else bn_stats_kernel<bf16><<<(D + 31) / 32, 256, 0, ST(stream)>>>(CBF(x), B, D, out);
+  if (x_is_f32) bn_stats_kernel<float><<<(D + 31) / 32, 32 * kBnRL, 0, ST(stream)>>>(reinterpret_cast<const float*>(x), B, D, out);
+  else bn_stats_kernel<bf16><<<(D + 31) / 32, 32 * kBnRL, 0, ST(stream)>>>(CBF(x), B, D, out);
   DVGR_CHECK_LAUNCH("bn_stats");
   return 0;
 }
@@ -1096,11 +1098,11 @@ extern "C" int DVGR_FN(dvgr_bn_bwd_ex)(const void* dy, const void* x, int x_is_f
                               const float* ext_sums, int Btot, int stats_only, void* stream) {
   if (B <= 0 || D <= 0) return 0;
   if (x_is_f32)
-    bn_bwd_kernel<float><<<(D + 31) / 32, 256, 0, ST(stream)>>>(CBF(dy), reinterpret_cast<const float*>(x), B, D, gamma,
+    bn_bwd_kernel<float><<<(D + 31) / 32, 32 * kBnRL, 0, ST(stream)>>>(CBF(dy), reinterpret_cast<const float*>(x), B, D, gamma,
                                                                  mean, rstd, training, reinterpret_cast<float*>(dx),
                                                                  dgamma, dbeta, ext_sums, Btot, stats_only);
   else
-    bn_bwd_kernel<bf16><<<(D + 31) / 32, 256, 0, ST(stream)>>>(CBF(dy), CBF(x), B, D, gamma, mean, rstd, training,
+    bn_bwd_kernel<bf16><<<(D + 31) / 32, 32 * kBnRL, 0, ST(stream)>>>(CBF(dy), CBF(x), B, D, gamma, mean, rstd, training,
                                                                 BF(dx), dgamma, dbeta, ext_sums, Btot, stats_only);
   DVGR_CHECK_LAUNCH("bn_bwd");
   return 0;

@@ -693,12 +693,15 @@ def readout_fwd(v, u, w, c, pooled=None):
     return pooled, alpha
 
 
-def readout_bwd(dpooled, v, u, w, alpha):
+def readout_bwd(dpooled, v, u, w, alpha, raw=False):
+    """raw=True: returns the per-sample partials (dw_part [B, D], dc_part [B, 1]) instead of their column sums."""
     B, N, D = v.shape
     dv, du = torch.empty_like(v), torch.empty_like(u)
     dw_part, dc_part = _empty((B, D), F32, v), _empty((B, 1), F32, v)
     _lib.check(_v("readout_bwd", v)(_ptr(dpooled), dpooled.stride(0), _ptr(v), _ptr(u), _ptr(w), _ptr(alpha), B, N, D, _ptr(dv),
                                 _ptr(du), _ptr(dw_part), _ptr(dc_part), _stream()), "dvgr_readout_bwd")
+    if raw:
+        return dv, du, dw_part, dc_part
     return dv, du, colsum(dw_part), colsum(dc_part)
 
 

@@ -125,8 +125,10 @@ class TrainEngine:
         # the rank goes into the seed; weights were identical before this point
         ag.set_rank_seed(self.rank)
         ag.DIRECT_GRAD[0] = True      # weight-gradient GEMMs accumulate straight into the flat gradient buffer
-        # SMs the appearance encoder's persistent backward launches leave to the streams running next to them (ops.RESERVE_SMS)
-        ops.RESERVE_SMS[0] = int(os.environ.get("DVGR_RESERVE_SMS", "32"))     # (measured: reserving SMs does not pay, r2)
+        # SMs the appearance encoder's backward RECURRENCE leaves to the question encoder's (32 tiles per step: 32 SMs). It is
+        # HBM-bound and loses nothing on 116 CTAs, while the question chain behind it no longer queues for SMs (-0.05 ms; the
+        # tensor-bound weight-gradient launches are NOT capped: measured slower, DVGR_RESERVE_WGRAD=1 to repeat)
+        ops.RESERVE_SMS[0] = int(os.environ.get("DVGR_RESERVE_SMS", "32"))
         _LIVE_ENGINES.add(self)
         overlap_ok = os.environ.get("DVGR_ALLREDUCE_OVERLAP", "1") != "0"        # A/B knob: 0 = one all-reduce after backward
         self._overlap = _EarlyBucketHook(self) if (self.world > 1 and overlap_ok and 0 < self.late_numel < total) else None

@@ -321,9 +321,9 @@ def lstm_block_c(c, ):
     return x.view(D, T1, RB, 32, UG, 2, 4).permute(0, 1, 2, 4, 5, 3, 6).contiguous()
 
 
-# SMs left free by the long persistent launches of the appearance encoder's BACKWARD (recurrence, W_ih / W_hh weight gradients)
-# for the kernels that run next to them on other streams: the question encoder's backward and, with more than one rank, the
-# NCCL all-reduce of the early gradient bucket. The engine sets it; 0 = take every SM.
+# SMs left free by the persistent launch of the appearance encoder's backward recurrence for the kernels that run next to it
+# on other streams: the question encoder's backward and, with more than one rank, the NCCL all-reduce of the early gradient
+# bucket. The engine sets it (32); 0 = take every SM.
 RESERVE_SMS = [0]
 
 

@@ -538,32 +538,55 @@ __global__ void accuracy_counters_kernel(const float* __restrict__ logits, const
 // re-layout (two full transposed copies in the reference) fused with the fp32 -> bf16 cast in ONE pass.
 // TIN = float (the reference's feature format) or bf16 (features stored / shipped as bf16: half the host-to-device bytes)
 template <typename TIN>
+__device__ __forceinline__ void prep_item(const TIN* __restrict__ in, bf16* __restrict__ out, long long i, float (&f)[8],
+                                          long long S, int T, int c8, int do_tanh, int time_major, const DropoutCfg& dc) {
+  if (dc.p > 0.f) {
+    float sc[8];
+    dropout_scale8(dc, i, sc);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) f[q] *= sc[q];
+  }
+  if (do_tanh) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) f[q] = tanh_fast(f[q]);   // output is bf16: the 2^-11 approximation is below its ulp
+  }
+  long long o = i;
+  if (time_major) {
+    // (32-bit index arithmetic whenever the tensor allows it: two 64-bit divisions per item were a third of the kernel's
+    //  instructions)
+    if (i < 0x7fffffffLL) {
+      const unsigned iu = (unsigned)i, row = iu / (unsigned)c8, cc = iu - row * (unsigned)c8;
+      const unsigned s_ = row / (unsigned)T, t = row - s_ * (unsigned)T;
+      o = ((long long)t * S + s_) * c8 + cc;
+    } else {
+      const long long row = i / c8;     // = s * T + t
+      const int cc = (int)(i - row * c8);
+      const long long s_ = row / T;
+      const int t = (int)(row - s_ * T);
+      o = ((long long)t * S + s_) * c8 + cc;
+    }
+  }
+  store8(out + o * 8, f);
+}
+
+template <typename TIN>
 __global__ void prep_features_kernel(const TIN* __restrict__ in, bf16* __restrict__ out, long long S, int T, int C,
                                      int do_tanh, int time_major, DropoutCfg dc) {
   const long long n8 = S * T * (long long)C / 8;
   const int c8 = C / 8;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
-    float f[8];
-    load8g(in + i * 8, f);
-    if (dc.p > 0.f) {
-      float sc[8];
-      dropout_scale8(dc, i, sc);
-#pragma unroll
-      for (int q = 0; q < 8; ++q) f[q] *= sc[q];
-    }
-    if (do_tanh) {
-#pragma unroll
-      for (int q = 0; q < 8; ++q) f[q] = tanh_fast(f[q]);   // output is bf16: the 2^-11 approximation is below its ulp
-    }
-    long long o = i;
-    if (time_major) {
-      const long long row = i / c8;     // = s * T + t
-      const int cc = (int)(i - row * c8);
-      const long long s = row / T;
-      const int t = (int)(row - s * T);
-      o = ((long long)t * S + s) * c8 + cc;
-    }
-    store8(out + o * 8, f);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  for (; i + stride < n8; i += 2 * stride) {      // two items per trip: both loads are in flight before either is consumed
+    float f0[8], f1[8];
+    load8g(in + i * 8, f0);
+    load8g(in + (i + stride) * 8, f1);
+    prep_item<TIN>(in, out, i, f0, S, T, c8, do_tanh, time_major, dc);
+    prep_item<TIN>(in, out, i + stride, f1, S, T, c8, do_tanh, time_major, dc);
+  }
+  if (i < n8) {
+    float f0[8];
+    load8g(in + i * 8, f0);
+    prep_item<TIN>(in, out, i, f0, S, T, c8, do_tanh, time_major, dc);
   }
 }
 

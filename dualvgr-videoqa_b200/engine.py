@@ -320,6 +320,10 @@ class TrainEngine:
     # NOTE: capture() runs `warmup` REAL optimizer steps on the given batch before recording (kernel attribute setup, NCCL
     # channel setup and allocator warm-up must not happen during capture): the parameters move, as with any train step.
     def capture(self, app, mot, question, question_len, answers, warmup=3):
+        """Records one whole train step (forward, losses, backward, all-reduce, clip + Adam) as a CUDA graph over static
+        input buffers; afterwards: load_batch(...) + replay(). NOTE: the `warmup` eager steps that precede the capture are
+        REAL optimizer steps on the given batch (they warm the allocator, the weight caches and the side streams); pass the
+        first training batch, or warmup=0 after at least one eager train_step()."""
         from . import _lib
         self.static = {k: torch.empty_like(v) for k, v in
                        dict(app=app, mot=mot, q=question, qlen=question_len, ans=answers).items()}

@@ -128,7 +128,10 @@ class TrainEngine:
         # SMs the appearance encoder's backward RECURRENCE leaves to the question encoder's (32 tiles per step: 32 SMs). It is
         # HBM-bound and loses nothing on 116 CTAs, while the question chain behind it no longer queues for SMs (-0.05 ms; the
         # tensor-bound weight-gradient launches are NOT capped: measured slower, DVGR_RESERVE_WGRAD=1 to repeat)
-        ops.RESERVE_SMS[0] = int(os.environ.get("DVGR_RESERVE_SMS", "32"))
+        # default: one SM per tile of a question-encoder step (4 directions x ceil(B / 32) row blocks), at most 64 — measured:
+        # SVQA (B=256) 32: -0.05 ms; MSVD (B=1024) 32: +0.14 ms, 64: neutral; 64-clip videos (B=512) 32: -0.5 ms
+        self._reserve_env = os.environ.get("DVGR_RESERVE_SMS")
+        ops.RESERVE_SMS[0] = int(self._reserve_env) if self._reserve_env is not None else 32
         _LIVE_ENGINES.add(self)
         overlap_ok = os.environ.get("DVGR_ALLREDUCE_OVERLAP", "1") != "0"        # A/B knob: 0 = one all-reduce after backward
         self._overlap = _EarlyBucketHook(self) if (self.world > 1 and overlap_ok and 0 < self.late_numel < total) else None
@@ -238,6 +241,8 @@ class TrainEngine:
         ops.begin_step_counters(app.device)        # zeroed tile counters of this step's dynamically scheduled GEMMs
         unit = model.visual_input_unit
         B, N = app.shape[0], app.shape[1]
+        if self._reserve_env is None:
+            ops.RESERVE_SMS[0] = min(64, 4 * ((B + 31) // 32))
         parts = None
         if unit.layers > 0 and (self.alpha != 0 or self.beta != 0):
             c_com, c_dep = self._loss_coefs(B, N, unit.layers)
